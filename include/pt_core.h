@@ -1,0 +1,405 @@
+/*
+ * pt_core.h — C ABI of the B200-native path-tracing core.
+ *
+ * This is the drop-in boundary for the hot path of piotrprzybyszdev/Path-Tracing:
+ * the work the reference does in Renderer::UpdateSceneData + Renderer::Render
+ * (vkCmdTraceRaysKHR over raygen.rgen / closestHit.rchit / anyhit.rahit /
+ * occlusionAnyhit.rahit / miss.rmiss / occlusion.rmiss with a driver-built
+ * TLAS/BLAS).  The reference has no FFI for this path (Renderer is a static
+ * C++ class, Path-Tracing/Renderer/Renderer.h:42-85); every entry point below
+ * cites the reference interface it replaces.  All citations are relative to
+ * the reference checkout (Path-Tracing/ = PT/).
+ *
+ * Conventions
+ *   - plain C, no torch / CUDA types in any signature; pointers are HOST
+ *     pointers unless the name says "device";
+ *   - every function returns pt_status (0 = ok, negative = error); the text of
+ *     the last error is available through pt_last_error();
+ *   - caller owns all host arrays; nothing is retained after a call returns;
+ *   - a pt_context is externally synchronised (one thread at a time), like the
+ *     reference's Renderer, which is only ever called from the main thread;
+ *   - there is NO CPU fallback: without a CUDA device pt_context_create fails.
+ */
+#ifndef PT_CORE_H
+#define PT_CORE_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(_WIN32)
+#define PT_API __declspec(dllexport)
+#else
+#define PT_API __attribute__((visibility("default")))
+#endif
+
+/* ------------------------------------------------------------------------- */
+/* status                                                                    */
+/* ------------------------------------------------------------------------- */
+
+typedef int32_t pt_status;
+enum {
+    PT_OK = 0,
+    PT_ERR_INVALID_ARGUMENT = -1, /* null pointer, index out of range, bad enum                */
+    PT_ERR_NO_DEVICE = -2,        /* no CUDA device / wrong architecture (no CPU fallback)       */
+    PT_ERR_CUDA = -3,             /* a CUDA call failed; see pt_last_error                       */
+    PT_ERR_OUT_OF_MEMORY = -4,
+    PT_ERR_NO_SCENE = -5,         /* render/trace before pt_scene_upload                         */
+    PT_ERR_NO_TARGET = -6,        /* render/readback before pt_render_begin                      */
+    PT_ERR_UNSUPPORTED = -7       /* e.g. animated geometry, BC textures            */
+};
+
+typedef struct pt_context pt_context;
+
+/* ------------------------------------------------------------------------- */
+/* scene data contract — byte-identical to the reference's host structs      */
+/* ------------------------------------------------------------------------- */
+
+/* Shaders::Vertex, PT/Shaders/ShaderTypes.incl:40-47 (56 bytes, scalar-aligned). */
+typedef struct pt_vertex {
+    float position[3];
+    float texcoords[2];
+    float normal[3];
+    float tangent[3];
+    float bitangent[3];
+} pt_vertex;
+
+/* PathTracing::Geometry, PT/Scene.h:63-71 (bools widened to u32; IsAnimated must be 0). */
+typedef struct pt_geometry {
+    uint32_t vertex_offset; /* first vertex; indices are relative to it (PT/Shaders/common.glsl:27-34) */
+    uint32_t vertex_length;
+    uint32_t index_offset;
+    uint32_t index_length;
+    uint32_t is_opaque; /* 0 => alpha-tested any-hit runs (PT/Renderer/AccelerationStructure.cpp:94-97) */
+} pt_geometry;
+
+/* Shaders::SBTBuffer, PT/Shaders/ShaderRendererTypes.incl:42-47; one per (model, mesh) in model
+ * order, exactly the records Renderer::UpdateSceneData adds (PT/Renderer/Renderer.cpp:381-399). */
+typedef struct pt_mesh_record {
+    uint32_t geometry_index;
+    uint32_t material_id;     /* (index << 8) | type, PT/Shaders/ShaderTypes.incl:155-168 */
+    uint32_t transform_index; /* into transforms[]; 0 = identity (PT/Scene.h:306)          */
+} pt_mesh_record;
+
+/* PathTracing::Model, PT/Scene.h:96-100. */
+typedef struct pt_model {
+    uint32_t mesh_offset; /* index of the model's first pt_mesh_record */
+    uint32_t mesh_count;
+} pt_model;
+
+/* PathTracing::ModelInstance, PT/Scene.h:102-107, in the form BuildTlas hands to Vulkan
+ * (PT/Renderer/AccelerationStructure.cpp:268-275): first 12 floats of the row-vector
+ * glm::mat4 == a 3x4 row-major object-to-world matrix. */
+typedef struct pt_instance {
+    float transform[12];
+    uint32_t model_index;
+} pt_instance;
+
+enum {
+    PT_MATERIAL_METALLIC_ROUGHNESS = 0, /* PT/Shaders/ShaderTypes.incl:143-145 */
+    PT_MATERIAL_SPECULAR_GLOSSINESS = 1,
+    PT_MATERIAL_PHONG = 2
+};
+
+/* Shaders::MetallicRoughnessMaterial, PT/Shaders/ShaderTypes.incl:61-80 (96 bytes). */
+typedef struct pt_material_mr {
+    float emissive_color[3];
+    float emissive_intensity;
+    float color[4];
+    float roughness;
+    float metalness;
+    float ior;
+    float transmission;
+    float attenuation_color[3];
+    float attenuation_distance;
+    float pad0, pad1, pad2;
+    uint32_t emissive_idx;
+    uint32_t color_idx;
+    uint32_t normal_idx;
+    uint32_t roughness_idx;
+    uint32_t metallic_idx;
+} pt_material_mr;
+
+/* Shaders::SpecularGlossinessMaterial, PT/Shaders/ShaderTypes.incl:82-99 (96 bytes).
+ * Shaders::PhongMaterial (:101-118) has the same layout with Shininess for Glossiness. */
+typedef struct pt_material_sg {
+    float emissive_color[3];
+    float emissive_intensity;
+    float color[4];
+    float specular[3];
+    float glossiness; /* Phong: shininess */
+    float attenuation_color[3];
+    float attenuation_distance;
+    float ior;
+    float transmission;
+    uint32_t emissive_idx;
+    uint32_t color_idx;
+    uint32_t normal_idx;
+    uint32_t specular_idx;
+    uint32_t glossiness_idx; /* Phong: shininess_idx */
+    float pad0;
+} pt_material_sg;
+
+typedef pt_material_sg pt_material_phong;
+
+/* Shaders::DirectionalLight / PointLight, PT/Shaders/ShaderTypes.incl:120-141. */
+typedef struct pt_directional_light {
+    float color[3];
+    float pad0;
+    float direction[3];
+    float pad1;
+} pt_directional_light;
+
+typedef struct pt_point_light {
+    float color[3];
+    float pad0;
+    float position[3];
+    float pad1;
+    float attenuation_constant;
+    float attenuation_linear;
+    float attenuation_quadratic;
+    float pad2;
+} pt_point_light;
+
+#define PT_MAX_LIGHT_COUNT 64u       /* PT/Shaders/ShaderTypes.incl:30 */
+#define PT_SCENE_TEXTURE_OFFSET 9u   /* PT/Shaders/ShaderTypes.incl:27; slots 0-8 are built in */
+
+enum {
+    PT_TEXTURE_RGBA8 = 0,  /* TextureFormat::RGBAU8,  PT/Scene.h:35-42 */
+    PT_TEXTURE_RGBAF32 = 1 /* TextureFormat::RGBAF32 */
+};
+
+/* One decoded level-0 image (what TextureImporter::LoadTextureData returns,
+ * PT/TextureImporter.cpp:413-424).  The core builds the full mip chain itself
+ * (PT/Renderer/Image.cpp:14-17,264-305).  srgb follows the reference's rule
+ * Color/Specular/Emissive/Skybox => sRGB (PT/Renderer/TextureUploader.cpp:571-595). */
+typedef struct pt_texture_desc {
+    uint32_t width;
+    uint32_t height;
+    uint32_t format; /* PT_TEXTURE_* */
+    uint32_t srgb;   /* RGBA8 only */
+    const void *pixels;
+} pt_texture_desc;
+
+enum {
+    PT_MISS_FLAGS_NONE = 0x0,      /* PT/Shaders/ShaderRendererTypes.incl:92-95 */
+    PT_MISS_FLAGS_SKYBOX_2D = 0x1,
+    PT_MISS_FLAGS_SKYBOX_CUBE = 0x2 /* not implemented in this round: PT_ERR_UNSUPPORTED */
+};
+enum {
+    PT_HIT_FLAGS_NONE = 0x0,       /* PT/Shaders/ShaderRendererTypes.incl:97-99 */
+    PT_HIT_FLAGS_DX_NORMAL_TEXTURES = 0x1
+};
+
+/* Everything Renderer::UpdateSceneData pulls out of a Scene (PT/Scene.h:182-212;
+ * use sites PT/Renderer/Renderer.cpp:257-331, 381-399, 1719-1726). */
+typedef struct pt_scene_desc {
+    const pt_vertex *vertices;
+    uint64_t vertex_count;
+    const uint32_t *indices;
+    uint64_t index_count;
+    const float *transforms; /* transform_count x 12 floats, 3x4 row-major; [0] = identity */
+    uint32_t transform_count;
+    const pt_geometry *geometries;
+    uint32_t geometry_count;
+    const pt_mesh_record *mesh_records;
+    uint32_t mesh_record_count;
+    const pt_model *models;
+    uint32_t model_count;
+    const pt_instance *instances;
+    uint32_t instance_count;
+    const pt_material_mr *mr_materials;
+    uint32_t mr_material_count;
+    const pt_material_sg *sg_materials;
+    uint32_t sg_material_count;
+    const pt_material_phong *phong_materials;
+    uint32_t phong_material_count;
+    const pt_texture_desc *textures; /* scene texture i lives in slot PT_SCENE_TEXTURE_OFFSET + i */
+    uint32_t texture_count;
+    const pt_point_light *point_lights;
+    uint32_t point_light_count; /* <= PT_MAX_LIGHT_COUNT */
+    pt_directional_light directional_light;
+    const pt_texture_desc *skybox_2d; /* equirect sky for PT_MISS_FLAGS_SKYBOX_2D, or NULL */
+} pt_scene_desc;
+
+/* Shaders::RaygenUniformData (PT/Shaders/ShaderRendererTypes.incl:26-34) plus the two
+ * specialisation constants (:89-99).  SampleCount/TotalSamples are arguments of
+ * pt_render_samples.  Matrices are column-major exactly as glm stores them. */
+typedef struct pt_render_params {
+    float view_inverse[16];
+    float proj_inverse[16];
+    uint32_t bounce_count;
+    float lens_radius;
+    float focal_distance;
+    uint32_t miss_flags;
+    uint32_t hit_flags;
+} pt_render_params;
+
+/* Pixel rectangle [x0,x1) x [y0,y1) of the full image; used to partition one frame over GPUs. */
+typedef struct pt_tile {
+    uint32_t x0, y0, x1, y1;
+} pt_tile;
+
+/* A ray query and its result (traceRayEXT contract, PT/Shaders/raygen.rgen:31,68). */
+typedef struct pt_ray {
+    float origin[3];
+    float tmin;
+    float direction[3];
+    float tmax;
+} pt_ray;
+
+#define PT_NO_HIT 0xffffffffu
+
+typedef struct pt_hit {
+    uint32_t instance;   /* gl_InstanceID; PT_NO_HIT on a miss                         */
+    uint32_t geometry;   /* geometry index inside the model's BLAS (gl_GeometryIndexEXT) */
+    uint32_t primitive;  /* gl_PrimitiveID                                              */
+    float t;             /* gl_RayTmaxEXT at the closest hit                            */
+    float u, v;          /* hitAttributeEXT barycentrics (weights of v1, v2)            */
+} pt_hit;
+
+/* Device counters of the last pt_render_samples / pt_trace_* call plus build info. */
+typedef struct pt_stats {
+    uint64_t rays_closest;    /* closest-hit queries traced (raygen.rgen:68)              */
+    uint64_t rays_shadow;     /* occlusion queries traced (raygen.rgen:31)                 */
+    uint64_t samples;         /* finished iterations of the sample loop (raygen.rgen:42)   */
+    uint64_t hits;            /* closest-hit queries that hit                              */
+    uint64_t box_tests;       /* child AABBs tested (all rays)                             */
+    uint64_t tri_tests;       /* ray-triangle tests (all rays)                             */
+    uint64_t alpha_tests;     /* any-hit alpha evaluations (all rays)                      */
+    uint64_t restarts;        /* NaN/Inf sample restarts (raygen.rgen:99-112)              */
+    uint64_t wavefront_iterations;
+    uint64_t kernel_launches; /* launches of this library's kernels in the last render call */
+    uint64_t triangle_count;  /* flattened (instanced) triangles in the BVH                */
+    uint64_t bvh_node_count;
+    uint64_t bvh_bytes;
+    float bvh_build_ms;
+    float scene_upload_ms;
+    float last_render_ms;     /* CUDA-event time of the last pt_render_samples             */
+} pt_stats;
+
+/* ------------------------------------------------------------------------- */
+/* context                                                                   */
+/* ------------------------------------------------------------------------- */
+
+/* Replaces DeviceContext::Init + Renderer::Init (PT/Renderer/DeviceContext.cpp:30,
+ * PT/Renderer/Renderer.cpp:77): binds the CUDA device's primary context, creates the
+ * stream and the nine built-in 1x1 textures (Renderer.cpp:127-173). */
+PT_API pt_status pt_context_create(int32_t cuda_device, pt_context **out_ctx);
+
+/* Replaces Renderer::Shutdown (PT/Renderer/Renderer.cpp:176-218). */
+PT_API void pt_context_destroy(pt_context *ctx);
+
+/* Error text of the last failed call on ctx (ctx may be NULL for create failures).
+ * Replaces the PathTracing::error exception text (PT/Core/Core.cpp:82-90). */
+PT_API const char *pt_last_error(const pt_context *ctx);
+
+/* ------------------------------------------------------------------------- */
+/* scene                                                                     */
+/* ------------------------------------------------------------------------- */
+
+/* Replaces Renderer::UpdateSceneData for a new scene (PT/Renderer/Renderer.cpp:238-439)
+ * and the AccelerationStructure constructor (PT/Renderer/AccelerationStructure.cpp:12-35):
+ * copies the scene to the device, bakes instance x mesh transforms, builds the BVH on
+ * the GPU, builds texture mip chains.  Blocking. */
+PT_API pt_status pt_scene_upload(pt_context *ctx, const pt_scene_desc *scene);
+
+/* Replaces Renderer::UpdateTexture(index) (PT/Renderer/Renderer.cpp:441-471): replace the
+ * content of one texture slot (slot = PT_SCENE_TEXTURE_OFFSET + scene texture index). */
+PT_API pt_status pt_texture_upload(pt_context *ctx, uint32_t slot, const pt_texture_desc *texture);
+
+/* ------------------------------------------------------------------------- */
+/* rendering                                                                 */
+/* ------------------------------------------------------------------------- */
+
+/* Replaces the accumulation-image (re)creation and clear (PT/Renderer/Renderer.cpp:1284-1288,
+ * 1734-1748, OnResize / SetSettings(RenderSettings) :825-852): allocates a zeroed
+ * width x height float4 sum buffer and the wavefront path state. */
+PT_API pt_status pt_render_begin(pt_context *ctx, uint32_t width, uint32_t height);
+
+/* Replaces Renderer::Render's trace pass (PT/Renderer/Renderer.cpp:1686-1700, 892-917)
+ * run sample_count times with SampleCount = 1 and TotalSamples = first_sample + i — the
+ * schedule the reference's Profile/Debug builds use (PT/Core/Config.h:34-36).  tiles == NULL
+ * renders the whole frame; otherwise only pixels inside the tile_count rectangles are
+ * rendered (RNG still uses global pixel coordinates and the full resolution, so the result is
+ * bit-identical to the same pixels of a full-frame render).  Asynchronous on the context
+ * stream; pt_readback / pt_get_stats / pt_synchronize wait for it. */
+PT_API pt_status pt_render_samples(pt_context *ctx, const pt_render_params *params, uint32_t first_sample,
+                                   uint32_t sample_count, const pt_tile *tiles, uint32_t tile_count);
+
+/* Device address of the float4 accumulation (sum) buffer, row pitch in bytes, and the CUDA
+ * stream (cudaStream_t as void*) work is queued on — for an NCCL reduce/gather in the caller. */
+PT_API pt_status pt_accum_device_ptr(pt_context *ctx, void **out_float4_device_ptr, size_t *out_pitch_bytes,
+                                     void **out_cuda_stream);
+
+/* Replaces OutputSaver's GPU->host copy (PT/Renderer/OutputSaver.cpp:113-181) for the raw
+ * float4 sum image: copies width*height*4 floats (RGB = sum of samples, A = 1) to host. */
+PT_API pt_status pt_readback(pt_context *ctx, float *out_rgba, size_t out_bytes);
+
+/* Waits for all queued work of the context. */
+PT_API pt_status pt_synchronize(pt_context *ctx);
+
+/* Primary-hit AOV (the information Debug/debugClosestHit.rchit's RenderModePrimitive /
+ * Instance / WorldPosition modes visualise, PT/Shaders/Debug/DebugShaderTypes.incl:18-26):
+ * traces the pixel-centre primary ray (PT/Shaders/ray.glsl:87-90) of every pixel of a
+ * width x height frame and writes width*height pt_hit records (row-major) to host. */
+PT_API pt_status pt_first_hit_aov(pt_context *ctx, const pt_render_params *params, uint32_t width,
+                                  uint32_t height, pt_hit *out_hits);
+
+/* traceRayEXT for a batch of host rays: closest hit with the alpha-tested any-hit
+ * (PT/Shaders/raygen.rgen:68 + anyhit.rahit). */
+PT_API pt_status pt_trace_closest(pt_context *ctx, const pt_ray *rays, uint64_t ray_count, pt_hit *out_hits);
+
+/* traceRayEXT with TerminateOnFirstHit + occlusionAnyhit.rahit (PT/Shaders/raygen.rgen:22-34):
+ * out_occluded[i] = 1 if anything with alpha >= 1 lies in (tmin, tmax). */
+PT_API pt_status pt_trace_occlusion(pt_context *ctx, const pt_ray *rays, uint64_t ray_count,
+                                    uint8_t *out_occluded);
+
+PT_API pt_status pt_get_stats(pt_context *ctx, pt_stats *out_stats);
+
+/* ------------------------------------------------------------------------- */
+/* shader unit-test entry point                                              */
+/* ------------------------------------------------------------------------- */
+
+/* Modes of pt_test_shading: the eight functions PTT/Shaders/testShading.comp dispatches on
+ * (PTT/Shaders/ShadingTestShaderTypes.incl:18-26), the BSDF test (BsdfTestShaderTypes.incl:13)
+ * and the remaining units SURVEY §8(a) lists.  Input/output records are arrays of floats. */
+enum {
+    PT_TEST_GGX_DISTRIBUTION = 0,    /* in: H.xyz, alpha            out: D                         */
+    PT_TEST_LAMBDA = 1,              /* in: V.xyz, alpha            out: Lambda                    */
+    PT_TEST_GGX_SMITH = 2,           /* in: V.xyz, alpha            out: G1                        */
+    PT_TEST_DIELECTRIC_FRESNEL = 3,  /* in: VdotH, eta              out: F                         */
+    PT_TEST_SCHLICK_FRESNEL = 4,     /* in: VdotH                   out: F                         */
+    PT_TEST_EVALUATE_REFLECTION = 5, /* in: V.xyz, L.xyz, F.xyz, alpha       out: f.xyz, pdf       */
+    PT_TEST_EVALUATE_REFRACTION = 6, /* in: V.xyz, L.xyz, F.xyz, alpha, eta  out: f.xyz, pdf       */
+    PT_TEST_SAMPLE_GGX = 7,          /* in: u.xy, V.xyz, alpha      out: H.xyz                     */
+    PT_TEST_SAMPLE_LOBE_PDFS = 8,    /* in: metalness, transmission, F  out: D, G, M, T            */
+    PT_TEST_EVALUATE_BSDF = 9,       /* in: material[17], V.xyz, L.xyz  out: f.xyz, pdf            */
+    PT_TEST_SAMPLE_BSDF = 10,        /* in: material[17], V.xyz, rng(bits) out: dir.xyz, pdf, color.xyz, rng(bits) */
+    PT_TEST_RNG = 11,                /* in: px, py, width, frame (bits)  out: seed, 4 x state (bits), 4 x float   */
+    PT_TEST_PRIMARY_RAY = 12,        /* in: px,py,w,h (bits), u.xy, u2.xy, lens, focal, view_inv[16], proj_inv[16]
+                                        out: ray o,d; rx o,d; ry o,d (18 floats)                    */
+    PT_TEST_OFFSET_SELF_INTERSECTION = 13, /* in: origin.xyz, normal.xyz   out: p.xyz              */
+    PT_TEST_CONCENTRIC_DISK = 14,    /* in: u.xy                     out: d.xy                     */
+    PT_TEST_TANGENT_SPACE = 15,      /* in: n.xyz                    out: t.xyz, b.xyz, n.xyz      */
+    PT_TEST_MODE_COUNT = 16
+};
+
+/* Number of floats per input / output record of a mode (0 for an unknown mode). */
+PT_API uint32_t pt_test_input_stride(uint32_t mode);
+PT_API uint32_t pt_test_output_stride(uint32_t mode);
+
+/* Replaces TestRenderer::ExecutePipeline("testShading.comp" / "testBsdf.comp", {mode}, N)
+ * (PTT/TestRenderer.cpp:79-106): runs the production __device__ function of `mode` on
+ * `count` input records in a one-thread-per-record kernel. */
+PT_API pt_status pt_test_shading(pt_context *ctx, uint32_t mode, const float *input, float *output,
+                                 uint32_t count);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif /* PT_CORE_H */

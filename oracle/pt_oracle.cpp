@@ -1,0 +1,2316 @@
+/*
+ * pt_oracle.cpp — CPU oracle for the path-tracing hot path.
+ *
+ * TEST INFRASTRUCTURE, NOT PRODUCT: only tests/, __graft_entry__.smoke() and bench.py's
+ * cpu_baseline / --impl reference legs may load the library built from this file.
+ *
+ * What it is: a literal, scalar restatement of the reference's GLSL ray-tracing stages,
+ * function for function and in the same evaluation order (the RNG stream is threaded through
+ * every stage), one pixel at a time like one raygen invocation.  Every
+ * function cites the reference file:line it follows (paths relative to the reference checkout,
+ * PT/ = Path-Tracing/).
+ *
+ * Parity pinning:
+ *   - RNG: pinned bit-exactly by the known answers derived from the integer spec
+ *     (tests/test_oracle_rng.py).
+ *   - shading.glsl / bsdf.glsl: the reference's own tests (PTT/ShadingTest.cpp, BsdfTest.cpp)
+ *     pin INPUT GRIDS and invariants only (finite; lobe weights sum to 1) — the oracle is
+ *     checked against those and against fp64 closed forms of the same formulas.
+ *   - struct layouts: pinned by PTT/PaddingTest.cpp literals (tests/test_layout.py).
+ *   - ray/box, ray/triangle, BVH: PARITY UNPINNED — in the reference they run inside the
+ *     Vulkan driver / RT hardware and there is no source or test.  The oracle's fp32
+ *     watertight test (Woop, Benthin, Wald 2013) is validated against an fp64 brute force.
+ *   - texture filtering (textureGrad, anisotropic): PARITY UNPINNED — sampler hardware.
+ *     The oracle defines isotropic trilinear filtering per the GL 4.6 spec §8.14.
+ *   - the full pipeline (images): PARITY UNPINNED by any reference artefact — the reference
+ *     cannot run here (no Vulkan); the oracle itself is the arbiter.
+ */
+#include "pt_oracle.h"
+#include "glsl_math.h"
+
+#include <algorithm>
+#include <atomic>
+#include <cstdio>
+#include <cstdlib>
+#include <thread>
+#include <vector>
+
+using namespace glsl;
+
+namespace
+{
+
+/* ========================================================================= */
+/* common.glsl                                                               */
+/* ========================================================================= */
+
+const float PI = 3.14159265359f; /* PT/Shaders/common.glsl:3 */
+
+/* PT/Shaders/common.glsl:12-15 */
+float maxComponent(vec3 rgb) { return max(rgb.x, max(rgb.y, rgb.z)); }
+/* PT/Shaders/common.glsl:17-20 */
+vec3 hdrToLdr(vec3 rgb) { return rgb / (1.0f + maxComponent(rgb)); }
+/* PT/Shaders/common.glsl:22-25 */
+vec3 computeBarycentricCoords(vec2 attribs) { return V3(1.0f - attribs.x - attribs.y, attribs.x, attribs.y); }
+
+/* Shaders::Vertex, PT/Shaders/ShaderTypes.incl:40-47 */
+struct Vertex
+{
+    vec3 Position;
+    vec2 TexCoords;
+    vec3 Normal;
+    vec3 Tangent;
+    vec3 Bitangent;
+};
+
+Vertex toVertex(const pt_vertex &v)
+{
+    Vertex r;
+    r.Position = V3(v.position[0], v.position[1], v.position[2]);
+    r.TexCoords = V2(v.texcoords[0], v.texcoords[1]);
+    r.Normal = V3(v.normal[0], v.normal[1], v.normal[2]);
+    r.Tangent = V3(v.tangent[0], v.tangent[1], v.tangent[2]);
+    r.Bitangent = V3(v.bitangent[0], v.bitangent[1], v.bitangent[2]);
+    return r;
+}
+
+/* PT/Shaders/common.glsl:102-122 */
+vec2 interpolate(vec2 v1, vec2 v2, vec2 v3, vec3 b) { return v1 * b.x + v2 * b.y + v3 * b.z; }
+vec3 interpolate(vec3 v1, vec3 v2, vec3 v3, vec3 b) { return v1 * b.x + v2 * b.y + v3 * b.z; }
+Vertex interpolate(const Vertex &v1, const Vertex &v2, const Vertex &v3, vec3 b)
+{
+    Vertex v;
+    v.Position = interpolate(v1.Position, v2.Position, v3.Position, b);
+    v.TexCoords = interpolate(v1.TexCoords, v2.TexCoords, v3.TexCoords, b);
+    v.Normal = interpolate(v1.Normal, v2.Normal, v3.Normal, b);
+    v.Tangent = interpolate(v1.Tangent, v2.Tangent, v3.Tangent, b);
+    v.Bitangent = interpolate(v1.Bitangent, v2.Bitangent, v3.Bitangent, b);
+    return v;
+}
+
+/* PT/Shaders/common.glsl:133-141 */
+uint32_t jenkinsHash(uint32_t x)
+{
+    x += x << 10;
+    x ^= x >> 6;
+    x += x << 3;
+    x ^= x >> 11;
+    x += x << 15;
+    return x;
+}
+/* PT/Shaders/common.glsl:143-147 — dot(uvec2, uvec2) is an integer dot product (Q1) */
+uint32_t initRng(uint32_t px, uint32_t py, uint32_t resX, uint32_t frame)
+{
+    uint32_t rngState = (px * 1u + py * resX) ^ jenkinsHash(frame);
+    return jenkinsHash(rngState);
+}
+/* PT/Shaders/common.glsl:149-152 */
+float uintToFloat(uint32_t x) { return uintBitsToFloat(0x3f800000u | (x >> 9)) - 1.0f; }
+/* PT/Shaders/common.glsl:154-160 */
+uint32_t xorshift(uint32_t &s)
+{
+    s ^= s << 13;
+    s ^= s >> 17;
+    s ^= s << 5;
+    return s;
+}
+/* PT/Shaders/common.glsl:162-165 */
+float rnd(uint32_t &s) { return uintToFloat(xorshift(s)); }
+
+/* PT/Shaders/common.glsl:168-184 */
+vec2 sampleUniformDiskConcentric(vec2 u)
+{
+    vec2 offset = 2.0f * u - 1.0f;
+    if (offset.x == 0.0f && offset.y == 0.0f)
+        return V2(0.0f, 0.0f);
+    if (abs(offset.x) > abs(offset.y))
+    {
+        float theta = PI / 4 * (offset.y / offset.x);
+        return offset.x * V2(std::cos(theta), std::sin(theta));
+    }
+    else
+    {
+        float theta = PI / 2 - PI / 4 * (offset.x / offset.y);
+        return offset.y * V2(std::cos(theta), std::sin(theta));
+    }
+}
+/* PT/Shaders/common.glsl:186-191 */
+vec3 sampleCosineHemisphere(vec2 u)
+{
+    vec2 d = sampleUniformDiskConcentric(u);
+    float z = std::sqrt(1 - d.x * d.x - d.y * d.y);
+    return V3(d.x, d.y, z);
+}
+/* PT/Shaders/common.glsl:193-202 */
+mat3 computeTangentSpace(vec3 normal)
+{
+    vec3 t1 = cross(normal, V3(1.0f, 0.0f, 0.0f));
+    vec3 t2 = cross(normal, V3(0.0f, 1.0f, 0.0f));
+    vec3 tangent = length(t1) > length(t2) ? t1 : t2;
+    vec3 bitangent = cross(normal, tangent);
+    return M3(normalize(tangent), normalize(bitangent), normal);
+}
+
+/* ========================================================================= */
+/* shading.glsl                                                              */
+/* ========================================================================= */
+
+/* PT/Shaders/shading.glsl:3-14 — D is clamped to <= 1 by max(denom, 1) */
+float GGXDistribution(vec3 H, float alpha)
+{
+    const float Hx2 = H.x * H.x;
+    const float Hy2 = H.y * H.y;
+    const float Hz2 = H.z * H.z;
+    const float alpha2 = alpha * alpha;
+    const float denom = PI * alpha2 * std::pow(Hx2 / alpha2 + Hy2 / alpha2 + Hz2, 2.0f);
+    return 1.0f / max(denom, 1.0f);
+}
+/* PT/Shaders/shading.glsl:16-27 */
+float Lambda(vec3 V, float alpha)
+{
+    const float Vx2 = V.x * V.x;
+    const float Vy2 = V.y * V.y;
+    const float Vz2 = abs(V.z) * abs(V.z);
+    const float alpha2 = alpha * alpha;
+    const float nom = std::sqrt(1.0f + (alpha2 * Vx2 + alpha2 * Vy2) / Vz2) - 1.0f;
+    return nom / 2.0f;
+}
+/* PT/Shaders/shading.glsl:29-32 */
+float GGXSmith(vec3 V, float alpha) { return 1.0f / (1.0f + Lambda(V, alpha)); }
+/* PT/Shaders/shading.glsl:34-48 */
+float DielectricFresnel(float VdotH, float eta)
+{
+    float cosThetaI = VdotH;
+    float sinThetaT2 = eta * eta * (1.0f - cosThetaI * cosThetaI);
+    if (sinThetaT2 > 1.0f)
+        return 1.0f;
+    const float cosThetaT = std::sqrt(max(1.0f - sinThetaT2, 0.0f));
+    const float rs = (eta * cosThetaT - cosThetaI) / (eta * cosThetaT + cosThetaI);
+    const float rp = (eta * cosThetaI - cosThetaT) / (eta * cosThetaI + cosThetaT);
+    return (rs * rs + rp * rp) / 2.0f;
+}
+/* PT/Shaders/shading.glsl:50-53 */
+float SchlickFresnel(float VdotH) { return std::pow(clamp(1.0f - VdotH, 0.0f, 1.0f), 5.0f); }
+
+/* PT/Shaders/shading.glsl:56-77 */
+vec3 EvaluateReflection(vec3 V, vec3 L, vec3 F, float alpha, float &pdf)
+{
+    if (L.z < 0.00001f)
+    {
+        pdf = 0.0f;
+        return V3(0.0f);
+    }
+    const vec3 H = normalize(V + L);
+    const float VdotH = dot(V, H);
+    const float D = GGXDistribution(H, alpha);
+    const float Gv = GGXSmith(V, alpha);
+    const float Gl = GGXSmith(L, alpha);
+    const float G = Gv * Gl;
+    const float Dv = (Gv * max(VdotH, 0.0f) * D) / V.z;
+    pdf = Dv / (4.0f * VdotH);
+    return (D * G * F) / (4.0f * V.z);
+}
+
+/* PT/Shaders/shading.glsl:80-108 */
+vec3 EvaluateRefraction(vec3 V, vec3 L, vec3 F, float alpha, float eta, float &pdf)
+{
+    if (L.z > -0.00001f)
+    {
+        pdf = 0.0f;
+        return V3(0.0f);
+    }
+    vec3 H = normalize(eta * V + L);
+    if (H.z < 0.0f)
+        H = -H;
+    const float VdotH = dot(V, H);
+    const float LdotH = dot(L, H);
+    const float D = GGXDistribution(H, alpha);
+    const float Gv = GGXSmith(V, alpha);
+    const float Gl = GGXSmith(L, alpha);
+    const float G = Gv * Gl;
+    const float Dv = (Gv * abs(VdotH) * D) / V.z;
+    const float denominator = LdotH + eta * VdotH;
+    const float jacobian = (std::pow(eta, 2.0f) * abs(LdotH)) / std::pow(denominator, 2.0f);
+    pdf = Dv * jacobian;
+    return (abs(VdotH) / abs(V.z)) * (D * G * F) * jacobian;
+}
+
+/* PT/Shaders/shading.glsl:111-129 */
+vec3 SampleGGX(vec2 u, vec3 V, float alpha)
+{
+    vec3 Vh = normalize(V3(alpha * V.x, alpha * V.y, abs(V.z)));
+    const float lensq = Vh.x * Vh.x + Vh.y * Vh.y;
+    const vec3 T1 = lensq > 0 ? V3(-Vh.y, Vh.x, 0) * inversesqrt(lensq) : V3(1, 0, 0);
+    const vec3 T2 = cross(Vh, T1);
+    const float r = std::sqrt(u.x);
+    const float phi = 2.0f * PI * u.y;
+    const float t1 = r * std::cos(phi);
+    float t2 = r * std::sin(phi);
+    const float s = 0.5f * (1.0f + Vh.z);
+    t2 = (1.0f - s) * std::sqrt(1.0f - t1 * t1) + s * t2;
+    const vec3 Nh = t1 * T1 + t2 * T2 + std::sqrt(max(0.0f, 1.0f - t1 * t1 - t2 * t2)) * Vh;
+    return normalize(V3(alpha * Nh.x, alpha * Nh.y, max(0.0f, Nh.z)));
+}
+
+/* ========================================================================= */
+/* bsdf.glsl                                                                 */
+/* ========================================================================= */
+
+/* Shaders::MaterialSample, PT/Shaders/ShaderRendererTypes.incl:129-140 */
+struct MaterialSample
+{
+    vec3 EmissiveColor;
+    vec3 Color;
+    vec3 Normal;
+    float Roughness;
+    float Metalness;
+    float Transmission;
+    float Eta;
+    vec3 AttenuationColor;
+    float AttenuationDistance;
+};
+
+/* PT/Shaders/bsdf.glsl:4-9 */
+struct BSDFSample
+{
+    vec3 Direction;
+    float Pdf;
+    vec3 Color;
+};
+
+/* PT/Shaders/bsdf.glsl:11-15 */
+vec3 evaluateDiffuseBRDF(const MaterialSample &m, vec3, vec3 L, float &pdf)
+{
+    pdf = L.z * 1.0f / PI;
+    return L.z * m.Color / PI;
+}
+/* PT/Shaders/bsdf.glsl:22-25 */
+vec3 evaluateGlossyBSDF(const MaterialSample &m, vec3 V, vec3 L, float &pdf)
+{
+    return EvaluateReflection(V, L, V3(1.0f), m.Roughness * m.Roughness, pdf);
+}
+/* PT/Shaders/bsdf.glsl:32-37 */
+vec3 evaluateMetallicBRDF(const MaterialSample &m, vec3 V, vec3 L, float &pdf)
+{
+    const vec3 H = normalize(V + L);
+    const vec3 F0 = mix(m.Color, V3(1.0f), SchlickFresnel(dot(V, H)));
+    return EvaluateReflection(V, L, F0, m.Roughness * m.Roughness, pdf);
+}
+/* PT/Shaders/bsdf.glsl:44-47 */
+vec3 evaluateBTDF(const MaterialSample &m, vec3 V, vec3 L, float &pdf)
+{
+    return EvaluateRefraction(V, L, m.Color, m.Roughness * m.Roughness, m.Eta, pdf);
+}
+
+/* PT/Shaders/bsdf.glsl:54-70 */
+struct LobePdfs
+{
+    float Diffuse, Glossy, Metallic, Transmissive;
+};
+LobePdfs sampleLobePdfs(const MaterialSample &m, float F)
+{
+    LobePdfs p;
+    p.Diffuse = (1.0f - m.Metalness) * (1.0f - F) * (1.0f - m.Transmission);
+    p.Glossy = (1.0f - m.Metalness) * F;
+    p.Metallic = m.Metalness;
+    p.Transmissive = (1.0f - m.Metalness) * (1.0f - F) * m.Transmission;
+    return p;
+}
+
+/* PT/Shaders/bsdf.glsl:72-103 */
+vec3 evaluateBSDF(const MaterialSample &m, vec3 V, vec3 L, float &outPdf)
+{
+    const bool isReflection = L.z > 0.0f;
+    vec3 H = isReflection ? normalize(V + L) : normalize(m.Eta * V + L);
+    const float FD = DielectricFresnel(abs(dot(V, H)), m.Eta);
+    LobePdfs pdfs = sampleLobePdfs(m, FD);
+    vec3 bsdf = V3(0.0f);
+    outPdf = 0.0f;
+    float pdf;
+    if (isReflection)
+    {
+        bsdf += evaluateDiffuseBRDF(m, V, L, pdf) * pdfs.Diffuse;
+        outPdf += pdf * pdfs.Diffuse;
+        bsdf += evaluateGlossyBSDF(m, V, L, pdf) * pdfs.Glossy;
+        outPdf += pdf * pdfs.Glossy;
+        bsdf += evaluateMetallicBRDF(m, V, L, pdf) * pdfs.Metallic;
+        outPdf += pdf * pdfs.Metallic;
+    }
+    else
+    {
+        bsdf += evaluateBTDF(m, V, L, pdf) * pdfs.Transmissive;
+        outPdf += pdf * pdfs.Transmissive;
+    }
+    return bsdf;
+}
+
+/* PT/Shaders/bsdf.glsl:105-132.  vec2(rand, rand) is evaluated left to right (Appendix B). */
+BSDFSample sampleBSDF(const MaterialSample &m, vec3 V, uint32_t &rngState)
+{
+    const float alpha = m.Roughness * m.Roughness;
+    const float u0 = rnd(rngState);
+    const float u1 = rnd(rngState);
+    const vec3 H = SampleGGX(V2(u0, u1), V, alpha);
+    const float FD = DielectricFresnel(abs(dot(V, H)), m.Eta);
+    vec3 L;
+    if (rnd(rngState) < m.Metalness)
+        L = normalize(reflect(-V, H)); /* sampleMetallicBRDF :39-42 */
+    else
+    {
+        if (rnd(rngState) < FD)
+            L = normalize(reflect(-V, H)); /* sampleGlossyBSDF :27-30 */
+        else
+        {
+            if (rnd(rngState) < m.Transmission)
+                L = normalize(refract(-V, H, m.Eta)); /* sampleBTDF :49-52 */
+            else
+            {
+                const float d0 = rnd(rngState);
+                const float d1 = rnd(rngState);
+                L = sampleCosineHemisphere(V2(d0, d1)); /* sampleDiffuseBRDF :17-20 */
+            }
+        }
+    }
+    BSDFSample ret;
+    ret.Direction = L;
+    ret.Color = evaluateBSDF(m, V, L, ret.Pdf);
+    return ret;
+}
+
+/* ========================================================================= */
+/* ray.glsl                                                                  */
+/* ========================================================================= */
+
+const float origin_const = 1.0f / 32.0f;   /* PT/Shaders/ray.glsl:3-5 */
+const float float_scale = 1.0f / 65536.0f;
+const float int_scale = 256.0f;
+
+struct Ray
+{
+    vec3 Origin;
+    float tmin;
+    vec3 Direction;
+    float tmax;
+};
+
+mat4 toMat4(const float *m)
+{
+    mat4 r;
+    std::memcpy(&r, m, 64);
+    return r;
+}
+
+/* PT/Shaders/ray.glsl:16-56 (thin lens) */
+Ray constructPrimaryRayLens(vec2 pixel, vec2 resolution, const mat4 &ViewInverse, const mat4 &ProjInverse, vec2 u,
+                            vec2 u2, float lensRadius, float focalDistance, Ray &rx, Ray &ry)
+{
+    const vec2 pixelCenter = pixel + u;
+    const vec2 pixelCenterOffsetX = pixelCenter + V2(1.0f, 0.0f);
+    const vec2 pixelCenterOffsetY = pixelCenter + V2(0.0f, 1.0f);
+    const vec2 pLens = lensRadius * sampleUniformDiskConcentric(u2);
+    const vec2 inUV = pixelCenter / resolution;
+    vec2 d = inUV * 2.0f - 1.0f;
+    const vec2 inUVOffsetX = pixelCenterOffsetX / resolution;
+    vec2 dOffsetX = inUVOffsetX * 2.0f - 1.0f;
+    const vec2 inUVOffsetY = pixelCenterOffsetY / resolution;
+    vec2 dOffsetY = inUVOffsetY * 2.0f - 1.0f;
+
+    vec3 originCameraSpace = V3(pLens.x, pLens.y, 0);
+    vec3 origin = xyz(ViewInverse * V4(originCameraSpace, 1));
+
+    vec3 target = xyz(ProjInverse * V4(d.x, d.y, 1, 1));
+    float ft = focalDistance / target.z;
+    vec3 pFocus = ft * target;
+    vec3 direction = xyz(ViewInverse * V4(normalize(pFocus - originCameraSpace), 0));
+
+    vec3 targetOffsetX = xyz(ProjInverse * V4(dOffsetX.x, dOffsetX.y, 1, 1));
+    float ftOffsetX = focalDistance / targetOffsetX.z;
+    vec3 pFocusOffsetX = ftOffsetX * targetOffsetX;
+    vec3 directionOffsetX = xyz(ViewInverse * V4(normalize(pFocusOffsetX - originCameraSpace), 0));
+
+    vec3 targetOffsetY = xyz(ProjInverse * V4(dOffsetY.x, dOffsetY.y, 1, 1));
+    float ftOffsetY = focalDistance / targetOffsetY.z;
+    vec3 pFocusOffsetY = ftOffsetY * targetOffsetY;
+    vec3 directionOffsetY = xyz(ViewInverse * V4(normalize(pFocusOffsetY - originCameraSpace), 0));
+
+    float tmin = 0.00001f;
+    float tmax = 10000.0f;
+    rx = Ray { origin, tmin, directionOffsetX, tmax };
+    ry = Ray { origin, tmin, directionOffsetY, tmax };
+    return Ray { origin, tmin, direction, tmax };
+}
+
+/* PT/Shaders/ray.glsl:58-85 (pinhole) */
+Ray constructPrimaryRay(vec2 pixel, vec2 resolution, const mat4 &ViewInverse, const mat4 &ProjInverse, vec2 u, Ray &rx,
+                        Ray &ry)
+{
+    const vec2 pixelCenter = pixel + u;
+    const vec2 pixelCenterOffsetX = pixelCenter + V2(1.0f, 0.0f);
+    const vec2 pixelCenterOffsetY = pixelCenter + V2(0.0f, 1.0f);
+    const vec2 inUV = pixelCenter / resolution;
+    vec2 d = inUV * 2.0f - 1.0f;
+    const vec2 inUVOffsetX = pixelCenterOffsetX / resolution;
+    vec2 dOffsetX = inUVOffsetX * 2.0f - 1.0f;
+    const vec2 inUVOffsetY = pixelCenterOffsetY / resolution;
+    vec2 dOffsetY = inUVOffsetY * 2.0f - 1.0f;
+
+    vec3 origin = xyz(ViewInverse * V4(0, 0, 0, 1));
+    vec3 target = xyz(ProjInverse * V4(d.x, d.y, 1, 1));
+    vec3 direction = xyz(ViewInverse * V4(normalize(target), 0));
+    vec3 targetOffsetX = xyz(ProjInverse * V4(dOffsetX.x, dOffsetX.y, 1, 1));
+    vec3 targetOffsetY = xyz(ProjInverse * V4(dOffsetY.x, dOffsetY.y, 1, 1));
+    vec3 directionOffsetX = xyz(ViewInverse * V4(normalize(targetOffsetX), 0));
+    vec3 directionOffsetY = xyz(ViewInverse * V4(normalize(targetOffsetY), 0));
+
+    float tmin = 0.00001f;
+    float tmax = 10000.0f;
+    rx = Ray { origin, tmin, directionOffsetX, tmax };
+    ry = Ray { origin, tmin, directionOffsetY, tmax };
+    return Ray { origin, tmin, direction, tmax };
+}
+
+/* PT/Shaders/ray.glsl:93-106 (Waechter & Binder, RT Gems ch. 6) */
+vec3 offsetRayOriginSelfIntersection(vec3 origin, vec3 normal)
+{
+    const int32_t ofx = (int32_t)(int_scale * normal.x);
+    const int32_t ofy = (int32_t)(int_scale * normal.y);
+    const int32_t ofz = (int32_t)(int_scale * normal.z);
+    vec3 p_i = V3(intBitsToFloat(floatBitsToInt(origin.x) + ((origin.x < 0) ? -ofx : ofx)),
+                  intBitsToFloat(floatBitsToInt(origin.y) + ((origin.y < 0) ? -ofy : ofy)),
+                  intBitsToFloat(floatBitsToInt(origin.z) + ((origin.z < 0) ? -ofz : ofz)));
+    return V3((abs(origin.x) < origin_const) ? origin.x + float_scale * normal.x : p_i.x,
+              (abs(origin.y) < origin_const) ? origin.y + float_scale * normal.y : p_i.y,
+              (abs(origin.z) < origin_const) ? origin.z + float_scale * normal.z : p_i.z);
+}
+
+/* PT/Shaders/ray.glsl:109-131 (Hanika, RT Gems II ch. 4); v0..v2 are by-value copies in GLSL */
+vec3 offsetRayOriginShadowTerminator(const Vertex &vertex, Vertex v0, Vertex v1, Vertex v2, vec3 bary, bool isRefracted)
+{
+    vec3 tmpu = vertex.Position - v0.Position;
+    vec3 tmpv = vertex.Position - v1.Position;
+    vec3 tmpw = vertex.Position - v2.Position;
+    if (isRefracted)
+    {
+        v0.Normal *= -1.0f;
+        v1.Normal *= -1.0f;
+        v2.Normal *= -1.0f;
+    }
+    float dotu = min(0.0f, dot(tmpu, v0.Normal));
+    float dotv = min(0.0f, dot(tmpv, v1.Normal));
+    float dotw = min(0.0f, dot(tmpw, v2.Normal));
+    tmpu -= dotu * v0.Normal;
+    tmpv -= dotv * v1.Normal;
+    tmpw -= dotw * v2.Normal;
+    return vertex.Position + bary.x * tmpu + bary.y * tmpv + bary.z * tmpw;
+}
+
+/* ========================================================================= */
+/* tracing.glsl                                                              */
+/* ========================================================================= */
+
+/* PT/Shaders/tracing.glsl:2-28 */
+void computeDpnDuv(const Vertex &v0, const Vertex &v1, const Vertex &v2, const Vertex &vertex, vec3 &dpdu, vec3 &dpdv,
+                   vec3 &dndu, vec3 &dndv)
+{
+    vec3 e1 = v1.Position - v0.Position;
+    vec3 e2 = v2.Position - v0.Position;
+    vec3 en1 = v1.Normal - v0.Normal;
+    vec3 en2 = v2.Normal - v0.Normal;
+    vec2 duv1 = v1.TexCoords - v0.TexCoords;
+    vec2 duv2 = v2.TexCoords - v0.TexCoords;
+    float det = duv1.x * duv2.y - duv2.x * duv1.y;
+    if (abs(det) < 1e-8f)
+    {
+        dpdu = vertex.Tangent;
+        dpdv = vertex.Bitangent;
+        dndu = V3(0.0f);
+        dndv = V3(0.0f);
+    }
+    else
+    {
+        float invDet = 1.0f / det;
+        dpdu = (duv2.y * e1 - duv1.y * e2) * invDet;
+        dpdv = (-duv2.x * e1 + duv1.x * e2) * invDet;
+        dndu = (duv2.y * en1 - duv1.y * en2) * invDet;
+        dndv = (-duv2.x * en1 + duv1.x * en2) * invDet;
+    }
+}
+
+/* PT/Shaders/tracing.glsl:31-41 (origin/direction parameters are unused there too) */
+void computeDpDxy(vec3 p, vec3 rxOrigin, vec3 rxDirection, vec3 ryOrigin, vec3 ryDirection, vec3 n, vec3 &dpdx,
+                  vec3 &dpdy)
+{
+    float d = -dot(n, p);
+    float tx = (-dot(n, rxOrigin) - d) / dot(n, rxDirection);
+    vec3 px = rxOrigin + tx * rxDirection;
+    float ty = (-dot(n, ryOrigin) - d) / dot(n, ryDirection);
+    vec3 py = ryOrigin + ty * ryDirection;
+    dpdx = px - p;
+    dpdy = py - p;
+}
+
+/* PT/Shaders/tracing.glsl:44-50 — the only place the shaders ask for a fused multiply-add */
+float differenceOfProducts(float a, float b, float c, float d)
+{
+    float cd = c * d;
+    float dop = std::fma(a, b, -cd);
+    float error = std::fma(-c, d, cd);
+    return dop + error;
+}
+
+/* PT/Shaders/tracing.glsl:53-78 */
+vec4 computeDerivatives(vec3 dpdx, vec3 dpdy, vec3 dpdu, vec3 dpdv)
+{
+    float ata00 = dot(dpdu, dpdu);
+    float ata01 = dot(dpdu, dpdv);
+    float ata11 = dot(dpdv, dpdv);
+    float invDet = 1 / differenceOfProducts(ata00, ata11, ata01, ata01);
+    invDet = isinf(invDet) ? 0.0f : invDet;
+    float atb0x = dot(dpdu, dpdx);
+    float atb1x = dot(dpdv, dpdx);
+    float atb0y = dot(dpdu, dpdy);
+    float atb1y = dot(dpdv, dpdy);
+    float dudx = differenceOfProducts(ata11, atb0x, ata01, atb1x) * invDet;
+    float dvdx = differenceOfProducts(ata00, atb1x, ata01, atb0x) * invDet;
+    float dudy = differenceOfProducts(ata11, atb0y, ata01, atb1y) * invDet;
+    float dvdy = differenceOfProducts(ata00, atb1y, ata01, atb0y) * invDet;
+    dudx = isinf(dudx) ? 0.0f : clamp(dudx, -1e8f, 1e8f);
+    dvdx = isinf(dvdx) ? 0.0f : clamp(dvdx, -1e8f, 1e8f);
+    dudy = isinf(dudy) ? 0.0f : clamp(dudy, -1e8f, 1e8f);
+    dvdy = isinf(dvdy) ? 0.0f : clamp(dvdy, -1e8f, 1e8f);
+    return V4(dudx, dvdx, dudy, dvdy);
+}
+
+/* PT/Shaders/tracing.glsl:81-108 */
+void computeReflectedDifferentialRays(vec4 derivatives, vec3 n, vec3 p, vec3 viewDir, vec3 reflectedDir, vec3 dndu,
+                                      vec3 dndv, vec3 &rxOrigin, vec3 &rxDirection, vec3 &ryOrigin, vec3 &ryDirection)
+{
+    float dudx = derivatives.x, dvdx = derivatives.y, dudy = derivatives.z, dvdy = derivatives.w;
+    vec3 dndx = dndu * dudx + dndv * dvdx;
+    vec3 dndy = dndu * dudy + dndv * dvdy;
+    float d = -dot(n, p);
+    float tx = (-dot(n, rxOrigin) - d) / dot(n, rxDirection);
+    vec3 px = rxOrigin + tx * rxDirection;
+    float ty = (-dot(n, ryOrigin) - d) / dot(n, ryDirection);
+    vec3 py = ryOrigin + ty * ryDirection;
+    vec3 dwodx = -rxDirection - viewDir;
+    vec3 dwody = -ryDirection - viewDir;
+    rxOrigin = px;
+    ryOrigin = py;
+    float dwoDotn_dx = dot(dwodx, n) + dot(viewDir, dndx);
+    float dwoDotn_dy = dot(dwody, n) + dot(viewDir, dndy);
+    rxDirection = normalize(reflectedDir - dwodx + 2 * (dot(viewDir, n) * dndx + dwoDotn_dx * n));
+    ryDirection = normalize(reflectedDir - dwody + 2 * (dot(viewDir, n) * dndy + dwoDotn_dy * n));
+}
+
+/* PT/Shaders/tracing.glsl:111-148 */
+void computeRefractedDifferentialRays(vec4 derivatives, vec3 n, vec3 p, vec3 viewDir, vec3 refractedDir, vec3 dndu,
+                                      vec3 dndv, float eta, vec3 &rxOrigin, vec3 &rxDirection, vec3 &ryOrigin,
+                                      vec3 &ryDirection)
+{
+    float dudx = derivatives.x, dvdx = derivatives.y, dudy = derivatives.z, dvdy = derivatives.w;
+    vec3 dndx = dndu * dudx + dndv * dvdx;
+    vec3 dndy = dndu * dudy + dndv * dvdy;
+    float d = -dot(n, p);
+    float tx = (-dot(n, rxOrigin) - d) / dot(n, rxDirection);
+    vec3 px = rxOrigin + tx * rxDirection;
+    float ty = (-dot(n, ryOrigin) - d) / dot(n, ryDirection);
+    vec3 py = ryOrigin + ty * ryDirection;
+    vec3 dwodx = -rxDirection - viewDir;
+    vec3 dwody = -ryDirection - viewDir;
+    rxOrigin = px;
+    ryOrigin = py;
+    if (dot(viewDir, n) < 0.0f)
+    {
+        n = -n;
+        dndx = -dndx;
+        dndy = -dndy;
+    }
+    float dwoDotn_dx = dot(dwodx, n) + dot(viewDir, dndx);
+    float dwoDotn_dy = dot(dwody, n) + dot(viewDir, dndy);
+    float mu = dot(viewDir, n) / eta - abs(dot(refractedDir, n));
+    float dmudx = dwoDotn_dx * (1.0f / eta + 1.0f / (eta * eta) * dot(viewDir, n) / dot(refractedDir, n));
+    float dmudy = dwoDotn_dy * (1.0f / eta + 1.0f / (eta * eta) * dot(viewDir, n) / dot(refractedDir, n));
+    rxDirection = normalize(refractedDir - eta * dwodx + (mu * dndx + dmudx * n));
+    ryDirection = normalize(refractedDir - eta * dwody + (mu * dndy + dmudy * n));
+}
+
+/* ========================================================================= */
+/* textures: sampler2D with the reference's sampler (PT/Renderer/Renderer.cpp:103-112):    */
+/* linear mag/min, linear mip, repeat.  Anisotropy is hardware-defined and NOT modelled     */
+/* (parity unpinned) — isotropic trilinear per GL 4.6 §8.14 is the definition here and in   */
+/* the CUDA core.                                                                           */
+/* ========================================================================= */
+
+struct Luts
+{
+    float unorm[256];
+    float srgb[256];
+    float srgbMid[255]; /* midpoints between consecutive srgb[] entries, for encoding */
+    Luts()
+    {
+        for (int i = 0; i < 256; i++)
+        {
+            const double c = i / 255.0;
+            unorm[i] = (float)i / 255.0f;
+            srgb[i] = (float)(c <= 0.04045 ? c / 12.92 : std::pow((c + 0.055) / 1.055, 2.4));
+        }
+        for (int i = 0; i < 255; i++)
+            srgbMid[i] = 0.5f * (srgb[i] + srgb[i + 1]);
+    }
+};
+const Luts g_luts;
+
+uint8_t encodeUnorm8(float v)
+{
+    if (!(v > 0.0f))
+        return 0;
+    if (v >= 1.0f)
+        return 255;
+    return (uint8_t)(v * 255.0f + 0.5f);
+}
+/* nearest sRGB code in LINEAR space: smallest i with v < mid[i] (binary search) */
+uint8_t encodeSrgb8(float v)
+{
+    int lo = 0, hi = 255;
+    while (lo < hi)
+    {
+        const int mid = (lo + hi) >> 1;
+        if (v < g_luts.srgbMid[mid])
+            hi = mid;
+        else
+            lo = mid + 1;
+    }
+    return (uint8_t)lo;
+}
+
+struct TexLevel
+{
+    uint32_t w = 0, h = 0;
+    std::vector<uint8_t> rgba8;
+    std::vector<float> rgbaf;
+};
+
+struct Texture
+{
+    bool isFloat = false;
+    bool srgb = false;
+    std::vector<TexLevel> levels;
+
+    vec4 texel(uint32_t level, uint32_t x, uint32_t y) const
+    {
+        const TexLevel &l = levels[level];
+        const size_t o = ((size_t)y * l.w + x) * 4;
+        if (isFloat)
+            return V4(l.rgbaf[o], l.rgbaf[o + 1], l.rgbaf[o + 2], l.rgbaf[o + 3]);
+        const float *lut = srgb ? g_luts.srgb : g_luts.unorm;
+        return V4(lut[l.rgba8[o]], lut[l.rgba8[o + 1]], lut[l.rgba8[o + 2]], g_luts.unorm[l.rgba8[o + 3]]);
+    }
+};
+
+/* Mip chain: levels = floor(log2(max(w,h))) + 1 (PT/Renderer/Image.cpp:14-17), each level a linear
+ * vkCmdBlitImage of the previous one (Image.cpp:264-305): destination texel centre mapped to the
+ * source, bilinear with clamp-to-edge; filtering in linear space, stored back as 8-bit. */
+void buildMips(Texture &t)
+{
+    uint32_t w = t.levels[0].w, h = t.levels[0].h;
+    uint32_t count = 1;
+    for (uint32_t m = std::max(w, h); m > 1; m >>= 1)
+        count++;
+    for (uint32_t k = 1; k < count; k++)
+    {
+        const TexLevel &src = t.levels[k - 1];
+        TexLevel dst;
+        dst.w = std::max(1u, w >> k);
+        dst.h = std::max(1u, h >> k);
+        if (t.isFloat)
+            dst.rgbaf.resize((size_t)dst.w * dst.h * 4);
+        else
+            dst.rgba8.resize((size_t)dst.w * dst.h * 4);
+        const float sxScale = (float)src.w / (float)dst.w;
+        const float syScale = (float)src.h / (float)dst.h;
+        for (uint32_t y = 0; y < dst.h; y++)
+            for (uint32_t x = 0; x < dst.w; x++)
+            {
+                const float sx = ((float)x + 0.5f) * sxScale - 0.5f;
+                const float sy = ((float)y + 0.5f) * syScale - 0.5f;
+                const float fx0 = std::floor(sx), fy0 = std::floor(sy);
+                const float fx = sx - fx0, fy = sy - fy0;
+                const int x0 = std::clamp((int)fx0, 0, (int)src.w - 1), x1 = std::clamp((int)fx0 + 1, 0, (int)src.w - 1);
+                const int y0 = std::clamp((int)fy0, 0, (int)src.h - 1), y1 = std::clamp((int)fy0 + 1, 0, (int)src.h - 1);
+                const vec4 t00 = t.texel(k - 1, x0, y0), t10 = t.texel(k - 1, x1, y0);
+                const vec4 t01 = t.texel(k - 1, x0, y1), t11 = t.texel(k - 1, x1, y1);
+                const vec4 top = t00 * (1.0f - fx) + t10 * fx;
+                const vec4 bot = t01 * (1.0f - fx) + t11 * fx;
+                const vec4 v = top * (1.0f - fy) + bot * fy;
+                const size_t o = ((size_t)y * dst.w + x) * 4;
+                if (t.isFloat)
+                {
+                    dst.rgbaf[o] = v.x;
+                    dst.rgbaf[o + 1] = v.y;
+                    dst.rgbaf[o + 2] = v.z;
+                    dst.rgbaf[o + 3] = v.w;
+                }
+                else
+                {
+                    dst.rgba8[o] = t.srgb ? encodeSrgb8(v.x) : encodeUnorm8(v.x);
+                    dst.rgba8[o + 1] = t.srgb ? encodeSrgb8(v.y) : encodeUnorm8(v.y);
+                    dst.rgba8[o + 2] = t.srgb ? encodeSrgb8(v.z) : encodeUnorm8(v.z);
+                    dst.rgba8[o + 3] = encodeUnorm8(v.w);
+                }
+            }
+        t.levels.push_back(std::move(dst));
+    }
+}
+
+Texture makeTexture(const pt_texture_desc &d)
+{
+    Texture t;
+    t.isFloat = d.format == PT_TEXTURE_RGBAF32;
+    t.srgb = !t.isFloat && d.srgb != 0;
+    TexLevel l;
+    l.w = d.width;
+    l.h = d.height;
+    const size_t n = (size_t)d.width * d.height * 4;
+    if (t.isFloat)
+        l.rgbaf.assign((const float *)d.pixels, (const float *)d.pixels + n);
+    else
+        l.rgba8.assign((const uint8_t *)d.pixels, (const uint8_t *)d.pixels + n);
+    t.levels.push_back(std::move(l));
+    buildMips(t);
+    return t;
+}
+
+Texture makeDefaultTexture(uint32_t rgba, bool srgb)
+{
+    /* PT/Renderer/Renderer.cpp:127-173: 1x1 RGBA8 from a little-endian uint */
+    pt_texture_desc d;
+    d.width = d.height = 1;
+    d.format = PT_TEXTURE_RGBA8;
+    d.srgb = srgb;
+    d.pixels = &rgba;
+    return makeTexture(d);
+}
+
+struct TexelCounter
+{
+    uint64_t n = 0;
+};
+
+/* bilinear fetch of one level with repeat addressing, normalised coordinates */
+vec4 sampleBilinear(const Texture &t, uint32_t level, vec2 uv, TexelCounter *tc)
+{
+    const TexLevel &l = t.levels[level];
+    if (l.w == 1 && l.h == 1)
+    {
+        if (tc)
+            tc->n += 1;
+        return t.texel(level, 0, 0);
+    }
+    float u = std::isfinite(uv.x) ? uv.x : 0.0f;
+    float v = std::isfinite(uv.y) ? uv.y : 0.0f;
+    u = u - std::floor(u);
+    v = v - std::floor(v);
+    const float x = u * (float)l.w - 0.5f;
+    const float y = v * (float)l.h - 0.5f;
+    const float fx0 = std::floor(x), fy0 = std::floor(y);
+    const float fx = x - fx0, fy = y - fy0;
+    const int W = (int)l.w, H = (int)l.h;
+    const int x0 = (((int)fx0 % W) + W) % W, x1 = (x0 + 1) % W;
+    const int y0 = (((int)fy0 % H) + H) % H, y1 = (y0 + 1) % H;
+    const vec4 t00 = t.texel(level, x0, y0), t10 = t.texel(level, x1, y0);
+    const vec4 t01 = t.texel(level, x0, y1), t11 = t.texel(level, x1, y1);
+    if (tc)
+        tc->n += 4;
+    const vec4 top = t00 * (1.0f - fx) + t10 * fx;
+    const vec4 bot = t01 * (1.0f - fx) + t11 * fx;
+    return top * (1.0f - fy) + bot * fy;
+}
+
+/* texture() outside a fragment shader has no implicit derivatives: level 0
+ * (anyhit.rahit:51, occlusionAnyhit.rahit:50, miss.rmiss:27) */
+vec4 textureLod0(const Texture &t, vec2 uv, TexelCounter *tc = nullptr) { return sampleBilinear(t, 0, uv, tc); }
+
+/* textureGrad(sampler2D, P, dPdx, dPdy), GL 4.6 §8.14: rho = max(|dPdx * size|, |dPdy * size|),
+ * lambda = log2(rho), trilinear between floor(lambda) and floor(lambda) + 1 */
+vec4 textureGrad(const Texture &t, vec2 uv, vec2 dPdx, vec2 dPdy, TexelCounter *tc)
+{
+    const uint32_t last = (uint32_t)t.levels.size() - 1;
+    if (last == 0)
+        return sampleBilinear(t, 0, uv, tc);
+    const float w = (float)t.levels[0].w, h = (float)t.levels[0].h;
+    const float ax = dPdx.x * w, ay = dPdx.y * h;
+    const float bx = dPdy.x * w, by = dPdy.y * h;
+    const float rho2 = max(ax * ax + ay * ay, bx * bx + by * by);
+    const float lambda = 0.5f * std::log2(rho2);
+    if (!(lambda > 0.0f))
+        return sampleBilinear(t, 0, uv, tc);
+    if (lambda >= (float)last)
+        return sampleBilinear(t, last, uv, tc);
+    const float fl = std::floor(lambda);
+    const uint32_t l0 = (uint32_t)fl;
+    const float f = lambda - fl;
+    const vec4 a = sampleBilinear(t, l0, uv, tc);
+    const vec4 b = sampleBilinear(t, l0 + 1, uv, tc);
+    return a * (1.0f - f) + b * f;
+}
+
+/* ========================================================================= */
+/* scene                                                                     */
+/* ========================================================================= */
+
+struct FlatTri
+{
+    vec3 p0, p1, p2;    /* world space */
+    uint32_t instance;  /* gl_InstanceID */
+    uint32_t geometry;  /* mesh index inside the model == gl_GeometryIndexEXT */
+    uint32_t primitive; /* gl_PrimitiveID */
+    uint32_t opaque;
+};
+
+struct BvhNode
+{
+    float bmin[3], bmax[3];
+    uint32_t left;  /* internal: index of left child (right = left + 1); leaf: first triangle */
+    uint32_t count; /* 0 => internal */
+};
+
+} // namespace
+
+struct pto_scene
+{
+    std::vector<pt_vertex> vertices;
+    std::vector<uint32_t> indices;
+    std::vector<mat3x4> transforms; /* GLSL `mat3x4 transforms[]`: column j = row j of the 3x4 matrix */
+    std::vector<pt_geometry> geometries;
+    std::vector<pt_mesh_record> meshRecords;
+    std::vector<pt_model> models;
+    std::vector<pt_instance> instances;
+    std::vector<pt_material_mr> mr;
+    std::vector<pt_material_sg> sg;
+    std::vector<pt_material_phong> phong;
+    std::vector<Texture> textures;
+    std::vector<pt_point_light> pointLights;
+    pt_directional_light directional;
+    bool hasSky2D = false;
+    Texture sky2D;
+
+    std::vector<FlatTri> tris;      /* flattening order: instance, mesh-in-model, primitive */
+    std::vector<uint32_t> triOrder; /* BVH leaf order -> index into tris */
+    std::vector<BvhNode> nodes;
+};
+
+namespace
+{
+
+/* gl_ObjectToWorld3x4EXT of an instance: mat3x4 whose column j is row j of the 3x4 matrix */
+mat3x4 objectToWorld3x4(const pt_instance &inst)
+{
+    const float *m = inst.transform;
+    return mat3x4 { { V4(m[0], m[1], m[2], m[3]), V4(m[4], m[5], m[6], m[7]), V4(m[8], m[9], m[10], m[11]) } };
+}
+
+/* PT/Shaders/sampling.glsl:5-15 */
+Vertex transformVertex(const pto_scene &s, Vertex vertex, uint32_t transformIndex, const mat3x4 &objectToWorld)
+{
+    const mat3x4 transform = M4(s.transforms[transformIndex]) * objectToWorld;
+    vertex.Position = V4(vertex.Position, 1.0f) * transform;
+    vertex.Tangent = normalize(V4(vertex.Tangent, 0.0f) * transform);
+    vertex.Bitangent = normalize(V4(vertex.Bitangent, 0.0f) * transform);
+    vertex.Normal = normalize(xyz(V4(vertex.Normal, 0.0f) * transpose(inverse(M4(transform)))));
+    return vertex;
+}
+
+/* PT/Shaders/common.glsl:27-46 — indices are relative to the geometry's first vertex */
+Vertex getVertex(const pto_scene &s, const pt_geometry &g, uint32_t offset)
+{
+    const uint32_t index = s.indices[g.index_offset + offset];
+    return toVertex(s.vertices[g.vertex_offset + index]);
+}
+
+/* ------------------------------------------------------------------------- */
+/* BVH2, binned SAH (the reference has no BVH code: the Vulkan driver builds it) */
+/* ------------------------------------------------------------------------- */
+
+struct Aabb
+{
+    float mn[3], mx[3];
+    void reset()
+    {
+        mn[0] = mn[1] = mn[2] = INFINITY;
+        mx[0] = mx[1] = mx[2] = -INFINITY;
+    }
+    void grow(vec3 p)
+    {
+        const float v[3] = { p.x, p.y, p.z };
+        for (int a = 0; a < 3; a++)
+        {
+            mn[a] = std::min(mn[a], v[a]);
+            mx[a] = std::max(mx[a], v[a]);
+        }
+    }
+    void grow(const Aabb &b)
+    {
+        for (int a = 0; a < 3; a++)
+        {
+            mn[a] = std::min(mn[a], b.mn[a]);
+            mx[a] = std::max(mx[a], b.mx[a]);
+        }
+    }
+    float area() const
+    {
+        const float dx = mx[0] - mn[0], dy = mx[1] - mn[1], dz = mx[2] - mn[2];
+        return dx * dy + dy * dz + dz * dx;
+    }
+};
+
+struct BvhBuilder
+{
+    pto_scene &s;
+    std::vector<Aabb> triBox;
+    std::vector<vec3> centroid;
+
+    explicit BvhBuilder(pto_scene &scene) : s(scene) {}
+
+    void build()
+    {
+        const size_t n = s.tris.size();
+        s.triOrder.resize(n);
+        triBox.resize(n);
+        centroid.resize(n);
+        for (size_t i = 0; i < n; i++)
+        {
+            s.triOrder[i] = (uint32_t)i;
+            triBox[i].reset();
+            triBox[i].grow(s.tris[i].p0);
+            triBox[i].grow(s.tris[i].p1);
+            triBox[i].grow(s.tris[i].p2);
+            centroid[i] = V3(0.5f * (triBox[i].mn[0] + triBox[i].mx[0]), 0.5f * (triBox[i].mn[1] + triBox[i].mx[1]),
+                             0.5f * (triBox[i].mn[2] + triBox[i].mx[2]));
+        }
+        s.nodes.clear();
+        s.nodes.reserve(2 * n + 1);
+        s.nodes.emplace_back();
+        if (n == 0)
+        {
+            BvhNode &r = s.nodes[0];
+            for (int a = 0; a < 3; a++)
+            {
+                r.bmin[a] = 0;
+                r.bmax[a] = 0;
+            }
+            r.left = 0;
+            r.count = 0;
+            return;
+        }
+        subdivide(0, 0, (uint32_t)n);
+    }
+
+    void setBounds(uint32_t node, uint32_t first, uint32_t count)
+    {
+        Aabb b;
+        b.reset();
+        for (uint32_t i = first; i < first + count; i++)
+            b.grow(triBox[s.triOrder[i]]);
+        for (int a = 0; a < 3; a++)
+        {
+            s.nodes[node].bmin[a] = b.mn[a];
+            s.nodes[node].bmax[a] = b.mx[a];
+        }
+    }
+
+    void subdivide(uint32_t node, uint32_t first, uint32_t count)
+    {
+        setBounds(node, first, count);
+        s.nodes[node].left = first;
+        s.nodes[node].count = count;
+        if (count <= 2)
+            return;
+        Aabb cb;
+        cb.reset();
+        for (uint32_t i = first; i < first + count; i++)
+            cb.grow(centroid[s.triOrder[i]]);
+        const int BINS = 16;
+        float bestCost = INFINITY;
+        int bestAxis = -1, bestSplit = -1;
+        for (int axis = 0; axis < 3; axis++)
+        {
+            const float lo = cb.mn[axis], hi = cb.mx[axis];
+            if (!(hi > lo))
+                continue;
+            Aabb binBox[BINS];
+            uint32_t binCount[BINS] = {};
+            for (auto &b : binBox)
+                b.reset();
+            const float scale = BINS / (hi - lo);
+            for (uint32_t i = first; i < first + count; i++)
+            {
+                const uint32_t t = s.triOrder[i];
+                int b = std::min(BINS - 1, (int)((centroid[t][axis] - lo) * scale));
+                binCount[b]++;
+                binBox[b].grow(triBox[t]);
+            }
+            float leftArea[BINS - 1], rightArea[BINS - 1];
+            uint32_t leftN[BINS - 1], rightN[BINS - 1];
+            Aabb l, r;
+            l.reset();
+            r.reset();
+            uint32_t ln = 0, rn = 0;
+            for (int i = 0; i < BINS - 1; i++)
+            {
+                ln += binCount[i];
+                l.grow(binBox[i]);
+                leftN[i] = ln;
+                leftArea[i] = l.area();
+                rn += binCount[BINS - 1 - i];
+                r.grow(binBox[BINS - 1 - i]);
+                rightN[BINS - 2 - i] = rn;
+                rightArea[BINS - 2 - i] = r.area();
+            }
+            for (int i = 0; i < BINS - 1; i++)
+            {
+                if (leftN[i] == 0 || rightN[i] == 0)
+                    continue;
+                const float cost = leftN[i] * leftArea[i] + rightN[i] * rightArea[i];
+                if (cost < bestCost)
+                {
+                    bestCost = cost;
+                    bestAxis = axis;
+                    bestSplit = i;
+                }
+            }
+        }
+        uint32_t mid;
+        if (bestAxis < 0)
+        {
+            if (count <= 4)
+                return;
+            mid = first + count / 2; /* all centroids coincide: median split */
+        }
+        else
+        {
+            Aabb nb;
+            for (int a = 0; a < 3; a++)
+            {
+                nb.mn[a] = s.nodes[node].bmin[a];
+                nb.mx[a] = s.nodes[node].bmax[a];
+            }
+            const float leafCost = count * nb.area();
+            if (count <= 4 && bestCost >= leafCost)
+                return;
+            const float lo = cb.mn[bestAxis], hi = cb.mx[bestAxis];
+            const float scale = BINS / (hi - lo);
+            auto it = std::partition(s.triOrder.begin() + first, s.triOrder.begin() + first + count, [&](uint32_t t) {
+                int b = std::min(BINS - 1, (int)((centroid[t][bestAxis] - lo) * scale));
+                return b <= bestSplit;
+            });
+            mid = (uint32_t)(it - s.triOrder.begin());
+            if (mid == first || mid == first + count)
+                mid = first + count / 2;
+        }
+        const uint32_t left = (uint32_t)s.nodes.size();
+        s.nodes.emplace_back();
+        s.nodes.emplace_back();
+        s.nodes[node].left = left;
+        s.nodes[node].count = 0;
+        subdivide(left, first, mid - first);
+        subdivide(left + 1, mid, first + count - mid);
+    }
+};
+
+/* ------------------------------------------------------------------------- */
+/* watertight ray/triangle (Woop, Benthin, Wald, JCGT 2013), fp32 with the    */
+/* paper's fp64 fallback for zero edge functions                              */
+/* ------------------------------------------------------------------------- */
+
+struct RayPrep
+{
+    int kx, ky, kz;
+    float Sx, Sy, Sz;
+    vec3 org;
+    float invDir[3];
+    float orgA[3];
+};
+
+RayPrep prepareRay(vec3 org, vec3 dir)
+{
+    RayPrep r;
+    const float ad[3] = { std::fabs(dir.x), std::fabs(dir.y), std::fabs(dir.z) };
+    r.kz = (ad[0] > ad[1]) ? ((ad[0] > ad[2]) ? 0 : 2) : ((ad[1] > ad[2]) ? 1 : 2);
+    r.kx = (r.kz + 1) % 3;
+    r.ky = (r.kx + 1) % 3;
+    if (dir[r.kz] < 0.0f)
+        std::swap(r.kx, r.ky);
+    r.Sx = dir[r.kx] / dir[r.kz];
+    r.Sy = dir[r.ky] / dir[r.kz];
+    r.Sz = 1.0f / dir[r.kz];
+    r.org = org;
+    r.invDir[0] = 1.0f / dir.x;
+    r.invDir[1] = 1.0f / dir.y;
+    r.invDir[2] = 1.0f / dir.z;
+    r.orgA[0] = org.x;
+    r.orgA[1] = org.y;
+    r.orgA[2] = org.z;
+    return r;
+}
+
+/* returns true and (t, b1, b2) when the ray hits; no culling; t range is checked by the caller */
+bool intersectTriangle(const RayPrep &r, const FlatTri &tri, float &t, float &b1, float &b2)
+{
+    const vec3 A = tri.p0 - r.org, B = tri.p1 - r.org, C = tri.p2 - r.org;
+    const float Ax = A[r.kx] - r.Sx * A[r.kz], Ay = A[r.ky] - r.Sy * A[r.kz];
+    const float Bx = B[r.kx] - r.Sx * B[r.kz], By = B[r.ky] - r.Sy * B[r.kz];
+    const float Cx = C[r.kx] - r.Sx * C[r.kz], Cy = C[r.ky] - r.Sy * C[r.kz];
+    float U = Cx * By - Cy * Bx;
+    float V = Ax * Cy - Ay * Cx;
+    float W = Bx * Ay - By * Ax;
+    if (U == 0.0f || V == 0.0f || W == 0.0f)
+    {
+        U = (float)((double)Cx * (double)By - (double)Cy * (double)Bx);
+        V = (float)((double)Ax * (double)Cy - (double)Ay * (double)Cx);
+        W = (float)((double)Bx * (double)Ay - (double)By * (double)Ax);
+    }
+    if ((U < 0.0f || V < 0.0f || W < 0.0f) && (U > 0.0f || V > 0.0f || W > 0.0f))
+        return false;
+    const float det = U + V + W;
+    if (det == 0.0f)
+        return false;
+    const float Az = r.Sz * A[r.kz], Bz = r.Sz * B[r.kz], Cz = r.Sz * C[r.kz];
+    const float T = U * Az + V * Bz + W * Cz;
+    const float rcpDet = 1.0f / det;
+    t = T * rcpDet;
+    b1 = V * rcpDet;
+    b2 = W * rcpDet;
+    return true;
+}
+
+/* slab test; returns entry distance or INFINITY.  Conservative: uses <= so that ties are kept. */
+float intersectBox(const RayPrep &r, const float *bmin, const float *bmax, float tmin, float tmax)
+{
+    float t0 = tmin, t1 = tmax;
+    for (int a = 0; a < 3; a++)
+    {
+        const float ta = (bmin[a] - r.orgA[a]) * r.invDir[a];
+        const float tb = (bmax[a] - r.orgA[a]) * r.invDir[a];
+        /* fmin/fmax drop NaNs (0 * inf when the origin lies on a slab of a flat box) */
+        t0 = std::fmax(t0, std::fmin(ta, tb));
+        t1 = std::fmin(t1, std::fmax(ta, tb));
+    }
+    /* widen by 2 ulp-ish so that rounding in the slab test can never cull a true hit */
+    return (t0 <= t1 * 1.0000004f) ? t0 : INFINITY;
+}
+
+struct Counters
+{
+    uint64_t rays_closest = 0, rays_shadow = 0, samples = 0, hits = 0;
+    uint64_t box_c = 0, tri_c = 0, box_s = 0, tri_s = 0, alpha_c = 0, alpha_s = 0, texels = 0, restarts = 0;
+    void add(const Counters &o)
+    {
+        rays_closest += o.rays_closest;
+        rays_shadow += o.rays_shadow;
+        samples += o.samples;
+        hits += o.hits;
+        box_c += o.box_c;
+        tri_c += o.tri_c;
+        box_s += o.box_s;
+        tri_s += o.tri_s;
+        alpha_c += o.alpha_c;
+        alpha_s += o.alpha_s;
+        texels += o.texels;
+        restarts += o.restarts;
+    }
+};
+
+/* ------------------------------------------------------------------------- */
+/* material.glsl helpers shared by the any-hit stages                          */
+/* ------------------------------------------------------------------------- */
+
+/* PT/Shaders/ShaderTypes.incl:162-167 */
+uint32_t unpackMaterialId(uint32_t materialId, uint32_t &materialType)
+{
+    materialType = materialId & 0xffu;
+    return materialId >> 8;
+}
+/* PT/Shaders/material.glsl:25-38 */
+uint32_t getColorTextureIdx(const pto_scene &s, uint32_t materialIndex, uint32_t materialType)
+{
+    switch (materialType)
+    {
+    case PT_MATERIAL_METALLIC_ROUGHNESS:
+        return s.mr[materialIndex].color_idx;
+    case PT_MATERIAL_SPECULAR_GLOSSINESS:
+        return s.sg[materialIndex].color_idx;
+    case PT_MATERIAL_PHONG:
+        return s.phong[materialIndex].color_idx;
+    default:
+        return 0;
+    }
+}
+/* PT/Shaders/material.glsl:40-53 */
+vec4 getColorFactor(const pto_scene &s, uint32_t materialIndex, uint32_t materialType)
+{
+    const float *c;
+    switch (materialType)
+    {
+    case PT_MATERIAL_METALLIC_ROUGHNESS:
+        c = s.mr[materialIndex].color;
+        break;
+    case PT_MATERIAL_SPECULAR_GLOSSINESS:
+        c = s.sg[materialIndex].color;
+        break;
+    case PT_MATERIAL_PHONG:
+        c = s.phong[materialIndex].color;
+        break;
+    default:
+        return V4(1.0f, 0.0f, 0.0f, 1.0f);
+    }
+    return V4(c[0], c[1], c[2], c[3]);
+}
+
+const pt_mesh_record &meshRecordOf(const pto_scene &s, const FlatTri &t)
+{
+    /* instanceShaderBindingTableRecordOffset = MeshOffset * 2, stride 2, + geometry index
+     * (PT/Renderer/AccelerationStructure.cpp:268-275, raygen.rgen:31,68) */
+    return s.meshRecords[s.models[s.instances[t.instance].model_index].mesh_offset + t.geometry];
+}
+
+/* colour texture x colour factor at the candidate hit — the common part of anyhit.rahit:36-51 and
+ * occlusionAnyhit.rahit:35-50 (full vertex interpolation, only TexCoords used) */
+vec4 anyHitColor(const pto_scene &s, const FlatTri &t, float b1, float b2)
+{
+    const vec3 bary = computeBarycentricCoords(V2(b1, b2));
+    const pt_mesh_record &rec = meshRecordOf(s, t);
+    const pt_geometry &g = s.geometries[rec.geometry_index];
+    const Vertex vertex = interpolate(getVertex(s, g, t.primitive * 3), getVertex(s, g, t.primitive * 3 + 1),
+                                      getVertex(s, g, t.primitive * 3 + 2), bary);
+    uint32_t materialType;
+    const uint32_t materialIndex = unpackMaterialId(rec.material_id, materialType);
+    const uint32_t colorTextureIdx = getColorTextureIdx(s, materialIndex, materialType);
+    const vec4 colorFactor = getColorFactor(s, materialIndex, materialType);
+    return textureLod0(s.textures[colorTextureIdx], vertex.TexCoords) * colorFactor;
+}
+
+/* ------------------------------------------------------------------------- */
+/* traceRayEXT                                                                */
+/* ------------------------------------------------------------------------- */
+
+struct HitInfo
+{
+    uint32_t tri = PT_NO_HIT; /* index into scene.tris */
+    float t = 0, b1 = 0, b2 = 0;
+    /* decal record written by anyhit.rahit:54-62 (payload aliases, ShaderRendererTypes.incl:112-114) */
+    float decalDist = -1.0f;
+    vec3 decalColor = { 0, 0, 0 };
+    float decalAlpha = 0.0f;
+};
+
+/* closest hit with the primary any-hit shader.  Ties in t are broken towards the smaller flattened
+ * triangle index so that the result does not depend on the BVH (the hardware's choice is
+ * implementation-defined). */
+HitInfo traceClosest(const pto_scene &s, vec3 org, vec3 dir, float tmin, float tmax, Counters &c)
+{
+    HitInfo hit;
+    c.rays_closest++;
+    if (s.tris.empty())
+        return hit;
+    const RayPrep r = prepareRay(org, dir);
+    float best = tmax;
+    uint32_t stack[128];
+    int sp = 0;
+    stack[sp++] = 0;
+    c.box_c++;
+    if (intersectBox(r, s.nodes[0].bmin, s.nodes[0].bmax, tmin, best) == INFINITY)
+        return hit;
+    while (sp > 0)
+    {
+        const BvhNode &n = s.nodes[stack[--sp]];
+        if (n.count == 0)
+        {
+            const BvhNode &l = s.nodes[n.left], &rr = s.nodes[n.left + 1];
+            c.box_c += 2;
+            const float tl = intersectBox(r, l.bmin, l.bmax, tmin, best);
+            const float tr = intersectBox(r, rr.bmin, rr.bmax, tmin, best);
+            if (tl != INFINITY && tr != INFINITY)
+            {
+                if (tl <= tr)
+                {
+                    stack[sp++] = n.left + 1;
+                    stack[sp++] = n.left;
+                }
+                else
+                {
+                    stack[sp++] = n.left;
+                    stack[sp++] = n.left + 1;
+                }
+            }
+            else if (tl != INFINITY)
+                stack[sp++] = n.left;
+            else if (tr != INFINITY)
+                stack[sp++] = n.left + 1;
+            continue;
+        }
+        /* NOTE: a node pushed earlier may now lie beyond `best`; re-testing it costs more than it saves here */
+        for (uint32_t i = n.left; i < n.left + n.count; i++)
+        {
+            const uint32_t ti = s.triOrder[i];
+            const FlatTri &tri = s.tris[ti];
+            float t, b1, b2;
+            c.tri_c++;
+            if (!intersectTriangle(r, tri, t, b1, b2))
+                continue;
+            if (!(t > tmin))
+                continue;
+            if (!(t < best || (t == best && hit.tri != PT_NO_HIT && ti < hit.tri)))
+                continue;
+            if (!tri.opaque)
+            {
+                /* anyhit.rahit:36-65 */
+                c.alpha_c++;
+                const vec4 color = anyHitColor(s, tri, b1, b2);
+                if (color.w < 0.5f)
+                {
+                    if (hit.decalDist == -1.0f || t < hit.decalDist)
+                    {
+                        hit.decalColor = xyz(color);
+                        hit.decalAlpha = color.w;
+                        hit.decalDist = t;
+                    }
+                    continue; /* ignoreIntersectionEXT */
+                }
+            }
+            best = t;
+            hit.tri = ti;
+            hit.t = t;
+            hit.b1 = b1;
+            hit.b2 = b2;
+        }
+    }
+    if (hit.tri != PT_NO_HIT)
+        c.hits++;
+    return hit;
+}
+
+/* raygen.rgen:22-34 checkOccluded's traceRayEXT: TerminateOnFirstHit, occlusionAnyhit.rahit, occlusion.rmiss */
+bool traceOccluded(const pto_scene &s, vec3 org, vec3 dir, float tmin, float tmax, Counters &c)
+{
+    c.rays_shadow++;
+    if (s.tris.empty())
+        return false;
+    const RayPrep r = prepareRay(org, dir);
+    uint32_t stack[128];
+    int sp = 0;
+    c.box_s++;
+    if (intersectBox(r, s.nodes[0].bmin, s.nodes[0].bmax, tmin, tmax) == INFINITY)
+        return false;
+    stack[sp++] = 0;
+    while (sp > 0)
+    {
+        const BvhNode &n = s.nodes[stack[--sp]];
+        if (n.count == 0)
+        {
+            const BvhNode &l = s.nodes[n.left], &rr = s.nodes[n.left + 1];
+            c.box_s += 2;
+            if (intersectBox(r, l.bmin, l.bmax, tmin, tmax) != INFINITY)
+                stack[sp++] = n.left;
+            if (intersectBox(r, rr.bmin, rr.bmax, tmin, tmax) != INFINITY)
+                stack[sp++] = n.left + 1;
+            continue;
+        }
+        for (uint32_t i = n.left; i < n.left + n.count; i++)
+        {
+            const FlatTri &tri = s.tris[s.triOrder[i]];
+            float t, b1, b2;
+            c.tri_s++;
+            if (!intersectTriangle(r, tri, t, b1, b2))
+                continue;
+            if (!(t > tmin && t < tmax))
+                continue;
+            if (!tri.opaque)
+            {
+                /* occlusionAnyhit.rahit:35-54 */
+                c.alpha_s++;
+                const float alpha = anyHitColor(s, tri, b1, b2).w;
+                if (alpha < 1.0f)
+                    continue;
+            }
+            return true;
+        }
+    }
+    return false;
+}
+
+/* ========================================================================= */
+/* material.glsl                                                             */
+/* ========================================================================= */
+
+/* PT/Shaders/material.glsl:55-60 */
+vec3 ReconstructNormalFromXY(vec3 normal)
+{
+    normal = 2.0f * normal - 1.0f;
+    return V3(normal.x, normal.y, std::sqrt(max(1 - normal.x * normal.x - normal.y * normal.y, 0.0f)));
+}
+
+struct TexCtx
+{
+    const pto_scene &s;
+    vec2 uv, dpdx, dpdy;
+    TexelCounter tc;
+    vec4 grad(uint32_t idx) { return textureGrad(s.textures[idx], uv, dpdx, dpdy, &tc); }
+};
+
+/* PT/Shaders/material.glsl:62-84 */
+MaterialSample sampleMaterialMR(const pt_material_mr &m, TexCtx &tx, bool isHitFromInside)
+{
+    MaterialSample ret;
+    const vec3 EmissiveColor = V3(m.emissive_color[0], m.emissive_color[1], m.emissive_color[2]);
+    ret.EmissiveColor = (xyz(tx.grad(m.emissive_idx)) + EmissiveColor) * m.emissive_intensity;
+    ret.Color = xyz(tx.grad(m.color_idx)) * V3(m.color[0], m.color[1], m.color[2]);
+    ret.Normal = ReconstructNormalFromXY(xyz(tx.grad(m.normal_idx)));
+    ret.Roughness = tx.grad(m.roughness_idx).y * m.roughness;
+    ret.Metalness = tx.grad(m.metallic_idx).z * m.metalness;
+    ret.Transmission = m.transmission;
+    ret.AttenuationColor = V3(m.attenuation_color[0], m.attenuation_color[1], m.attenuation_color[2]);
+    ret.AttenuationDistance = m.attenuation_distance;
+    ret.Eta = isHitFromInside ? m.ior : (1.0f / m.ior);
+    return ret;
+}
+
+/* PT/Shaders/material.glsl:86-113 (specular-glossiness) and :115-142 (Phong: same code with
+ * Shininess / ShininessIdx in the Glossiness slots — identical struct layout) */
+MaterialSample sampleMaterialSG(const pt_material_sg &m, TexCtx &tx, bool isHitFromInside)
+{
+    MaterialSample ret;
+    const vec3 EmissiveColor = V3(m.emissive_color[0], m.emissive_color[1], m.emissive_color[2]);
+    ret.EmissiveColor = (xyz(tx.grad(m.emissive_idx)) + EmissiveColor) * m.emissive_intensity;
+    ret.Color = xyz(tx.grad(m.color_idx)) * V3(m.color[0], m.color[1], m.color[2]);
+    ret.Normal = ReconstructNormalFromXY(xyz(tx.grad(m.normal_idx)));
+    ret.Transmission = m.transmission;
+    ret.AttenuationColor = V3(m.attenuation_color[0], m.attenuation_color[1], m.attenuation_color[2]);
+    ret.AttenuationDistance = m.attenuation_distance;
+    ret.Eta = isHitFromInside ? m.ior : (1.0f / m.ior);
+    vec3 specular = xyz(tx.grad(m.specular_idx)) * V3(m.specular[0], m.specular[1], m.specular[2]);
+    float glossiness = tx.grad(m.glossiness_idx).w * m.glossiness;
+    ret.Roughness = 1.0f - glossiness;
+    const vec3 diff = max(specular - 0.04f, 0.0f) / ((ret.Color - 0.04f) + 0.00001f);
+    ret.Metalness = (diff.x + diff.y + diff.z) / 3.0f;
+    return ret;
+}
+
+/* PT/Shaders/material.glsl:144-171 (flags is always 0 in closestHit.rchit:102) */
+MaterialSample sampleMaterial(const pto_scene &s, uint32_t materialId, vec2 texCoords, vec4 derivatives,
+                              bool isHitFromInside, bool flipNormalY, Counters &c)
+{
+    uint32_t materialType;
+    const uint32_t materialIndex = unpackMaterialId(materialId, materialType);
+    TexCtx tx { s, texCoords, V2(derivatives.x, derivatives.y), V2(derivatives.z, derivatives.w), {} };
+    MaterialSample ret;
+    switch (materialType)
+    {
+    case PT_MATERIAL_METALLIC_ROUGHNESS:
+        ret = sampleMaterialMR(s.mr[materialIndex], tx, isHitFromInside);
+        break;
+    case PT_MATERIAL_SPECULAR_GLOSSINESS:
+        ret = sampleMaterialSG(s.sg[materialIndex], tx, isHitFromInside);
+        break;
+    case PT_MATERIAL_PHONG:
+        ret = sampleMaterialSG(s.phong[materialIndex], tx, isHitFromInside);
+        break;
+    default:
+        /* the GLSL leaves the other members undefined; zero them here */
+        std::memset(&ret, 0, sizeof(ret));
+        ret.Color = V3(1.0f, 0.0f, 0.0f);
+        ret.EmissiveColor = V3(1.0f, 0.0f, 0.0f);
+        break;
+    }
+    if (flipNormalY)
+        ret.Normal.y *= -1.0f;
+    c.texels += tx.tc.n;
+    return ret;
+}
+
+/* ========================================================================= */
+/* sampling.glsl                                                             */
+/* ========================================================================= */
+
+const float DirectionalLightDistance = 100000.0f; /* PT/Shaders/sampling.glsl:3 */
+
+struct LightSample
+{
+    vec3 Direction;
+    float Distance;
+    vec3 Color;
+    float Attenuation;
+};
+
+/* PT/Shaders/sampling.glsl:25-56 */
+LightSample sampleLight(const pto_scene &s, vec3 u, vec3 position, float &pdf)
+{
+    const uint32_t u_LightCount = (uint32_t)s.pointLights.size();
+    uint32_t lightIndex = (uint32_t)(u.x * (float)(u_LightCount + 1));
+    pdf = 1.0f / (float)(u_LightCount + 1);
+    LightSample ret;
+    if (lightIndex >= u_LightCount)
+    {
+        const vec2 dp = sampleUniformDiskConcentric(V2(u.y, u.z));
+        vec3 diskPoint = V3(dp.x, dp.y, 0.0f) * 0.001f;
+        vec3 direction =
+            normalize(V3(s.directional.direction[0], s.directional.direction[1], s.directional.direction[2]));
+        ret.Direction = normalize(direction + computeTangentSpace(direction) * diskPoint);
+        ret.Color = V3(s.directional.color[0], s.directional.color[1], s.directional.color[2]);
+        ret.Distance = DirectionalLightDistance;
+        ret.Attenuation = 1.0f;
+        return ret;
+    }
+    const pt_point_light &light = s.pointLights[lightIndex];
+    const vec3 lightPosition = V3(light.position[0], light.position[1], light.position[2]);
+    const vec2 dp = sampleUniformDiskConcentric(V2(u.y, u.z));
+    vec3 diskPoint = V3(dp.x, dp.y, 0.0f) * 0.1f;
+    vec3 direction = normalize(position - lightPosition);
+    vec3 newPosition = lightPosition + computeTangentSpace(direction) * diskPoint;
+    ret.Distance = distance(position, newPosition);
+    ret.Direction = normalize(position - newPosition);
+    ret.Color = V3(light.color[0], light.color[1], light.color[2]);
+    const float attenuation = 1.0f / (light.attenuation_constant + ret.Distance * light.attenuation_linear +
+                                      ret.Distance * ret.Distance * light.attenuation_quadratic);
+    ret.Attenuation = clamp(attenuation, 0.0f, 1.0f);
+    return ret;
+}
+
+/* ========================================================================= */
+/* Payload + stages                                                          */
+/* ========================================================================= */
+
+/* Shaders::Payload, PT/Shaders/ShaderRendererTypes.incl:101-118 */
+struct Payload
+{
+    vec3 Position;
+    vec3 Direction;
+    float MaxRoughness;
+    vec3 Bsdf;
+    float Pdf;
+    vec3 Emissive;
+    uint32_t RngState;
+    vec3 DirectLight;
+    float DirectLightPdf; /* DecalDist   */
+    vec3 LightDirection;  /* DecalAlbedo */
+    float LightDistance;  /* DecalAlpha  */
+    vec4 RayDifferentials0, RayDifferentials1, RayDifferentials2;
+};
+
+/* PT/Shaders/miss.rmiss:16-39 */
+void missShader(const pto_scene &s, const pt_render_params &p, vec3 rayDir, Payload &payload)
+{
+    if ((p.miss_flags & PT_MISS_FLAGS_SKYBOX_2D) != 0 && s.hasSky2D)
+    {
+        const vec3 dir = rayDir;
+        const float longitude = std::atan2(dir.z, dir.x);
+        const float latitude = std::asin(-dir.y);
+        const vec2 texCoords = V2(longitude / 2.0f / PI + 0.5f, latitude / PI + 0.5f);
+        payload.Emissive = xyz(textureLod0(s.sky2D, texCoords));
+        payload.Emissive = hdrToLdr(payload.Emissive);
+    }
+    else
+        payload.Emissive = V3(0.08f, 0.09f, 0.1f);
+    payload.Pdf = -1.0f;
+}
+
+/* PT/Shaders/closestHit.rchit:52-161 */
+void closestHitShader(const pto_scene &s, const pt_render_params &p, const HitInfo &hit, vec3 rayOriginWorld,
+                      vec3 rayDirWorld, Payload &payload, Counters &c)
+{
+    const FlatTri &ft = s.tris[hit.tri];
+    const pt_instance &inst = s.instances[ft.instance];
+    const pt_mesh_record &sbt = meshRecordOf(s, ft);
+    const pt_geometry &geom = s.geometries[sbt.geometry_index];
+    const mat3x4 objectToWorld = objectToWorld3x4(inst);
+    const uint32_t primitiveID = ft.primitive;
+    const float rayTmax = hit.t;
+
+    const vec3 barycentricCoords = computeBarycentricCoords(V2(hit.b1, hit.b2));
+
+    Vertex v0 = getVertex(s, geom, primitiveID * 3);
+    Vertex v1 = getVertex(s, geom, primitiveID * 3 + 1);
+    Vertex v2 = getVertex(s, geom, primitiveID * 3 + 2);
+    const Vertex originalVertex = interpolate(v0, v1, v2, barycentricCoords);
+    Vertex vertex = transformVertex(s, originalVertex, sbt.transform_index, objectToWorld);
+
+    v0 = transformVertex(s, v0, sbt.transform_index, objectToWorld);
+    v1 = transformVertex(s, v1, sbt.transform_index, objectToWorld);
+    v2 = transformVertex(s, v2, sbt.transform_index, objectToWorld);
+
+    vec3 edge1 = v1.Position - v0.Position;
+    vec3 edge2 = v2.Position - v0.Position;
+    vec3 geometricNormal = normalize(cross(edge1, edge2));
+
+    const bool isHitFromInside = dot(geometricNormal, rayDirWorld) > 0.0f;
+    if (isHitFromInside)
+    {
+        geometricNormal *= -1.0f;
+        vertex.Normal *= -1.0f;
+        vertex.Tangent *= -1.0f;
+        vertex.Bitangent *= -1.0f;
+    }
+
+    const vec3 viewDir = rayDirWorld;
+    (void)rayOriginWorld;
+
+    vec3 dpdu, dpdv, dndu, dndv;
+    computeDpnDuv(v0, v1, v2, vertex, dpdu, dpdv, dndu, dndv);
+
+    vec3 rxOrigin = xyz(payload.RayDifferentials0);
+    vec3 rxDirection = V3(payload.RayDifferentials0.w, payload.RayDifferentials1.x, payload.RayDifferentials1.y);
+    vec3 ryOrigin = V3(payload.RayDifferentials1.z, payload.RayDifferentials1.w, payload.RayDifferentials2.x);
+    vec3 ryDirection = V3(payload.RayDifferentials2.y, payload.RayDifferentials2.z, payload.RayDifferentials2.w);
+
+    vec3 dpdx, dpdy;
+    computeDpDxy(vertex.Position, rxOrigin, rxDirection, ryOrigin, ryDirection, vertex.Normal, dpdx, dpdy);
+
+    const vec4 derivatives = computeDerivatives(dpdx, dpdy, dpdu, dpdv);
+
+    const bool flipYNormal = (p.hit_flags & PT_HIT_FLAGS_DX_NORMAL_TEXTURES) != 0;
+    MaterialSample material =
+        sampleMaterial(s, sbt.material_id, vertex.TexCoords, derivatives, isHitFromInside, flipYNormal, c);
+
+    /* decals (Q9) */
+    if (payload.DirectLightPdf != -1.0f && rayTmax > payload.DirectLightPdf)
+        material.Color = mix(material.Color, payload.LightDirection, payload.LightDistance);
+
+    payload.MaxRoughness = max(material.Roughness, payload.MaxRoughness);
+    material.Roughness = max(payload.MaxRoughness, 0.01f);
+
+    const mat3 geometryTBN = M3(vertex.Tangent, vertex.Bitangent, vertex.Normal);
+    const vec3 N = normalize(vertex.Normal + geometryTBN * material.Normal);
+    const mat3 TBN = computeTangentSpace(N);
+    const mat3 invTBN = inverse(TBN);
+    const vec3 V = normalize(invTBN * normalize(-rayDirWorld));
+
+    uint32_t rngState = payload.RngState;
+
+    BSDFSample bsdf = sampleBSDF(material, V, rngState);
+
+    if (isHitFromInside)
+    {
+        bsdf.Color.x *= std::pow(material.AttenuationColor.x, rayTmax / material.AttenuationDistance);
+        bsdf.Color.y *= std::pow(material.AttenuationColor.y, rayTmax / material.AttenuationDistance);
+        bsdf.Color.z *= std::pow(material.AttenuationColor.z, rayTmax / material.AttenuationDistance);
+    }
+
+    const bool isRefracted = bsdf.Direction.z < 0.0f;
+
+    const vec3 rayOrigin = offsetRayOriginShadowTerminator(vertex, v0, v1, v2, barycentricCoords, isRefracted);
+
+    float lightPdf, lightSmplPdf;
+    const float l0 = rnd(rngState);
+    const float l1 = rnd(rngState);
+    const float l2 = rnd(rngState);
+    LightSample light = sampleLight(s, V3(l0, l1, l2), rayOrigin, lightPdf);
+    const vec3 L = normalize(invTBN * -light.Direction);
+    const vec3 lightBsdf = evaluateBSDF(material, V, L, lightSmplPdf);
+
+    payload.Direction = normalize(TBN * bsdf.Direction);
+    if (isRefracted)
+        payload.Position = offsetRayOriginSelfIntersection(vertex.Position, -geometricNormal);
+    else
+        payload.Position = rayOrigin;
+    payload.Bsdf = bsdf.Color;
+    payload.Pdf = bsdf.Pdf;
+    payload.Emissive = material.EmissiveColor;
+    payload.RngState = rngState;
+    payload.DirectLight = light.Color * light.Attenuation * lightBsdf;
+    payload.DirectLightPdf = lightPdf;
+    payload.LightDirection = light.Direction;
+    payload.LightDistance = light.Distance;
+
+    if (isRefracted)
+        computeRefractedDifferentialRays(derivatives, vertex.Normal, rayOrigin, -viewDir, payload.Direction, dndu, dndv,
+                                         material.Eta, rxOrigin, rxDirection, ryOrigin, ryDirection);
+    else
+        computeReflectedDifferentialRays(derivatives, vertex.Normal, rayOrigin, -viewDir, payload.Direction, dndu, dndv,
+                                         rxOrigin, rxDirection, ryOrigin, ryDirection);
+
+    payload.RayDifferentials0 = V4(rxOrigin, rxDirection.x);
+    payload.RayDifferentials1 = V4(rxDirection.y, rxDirection.z, ryOrigin.x, ryOrigin.y);
+    payload.RayDifferentials2 = V4(ryOrigin.z, ryDirection.x, ryDirection.y, ryDirection.z);
+}
+
+/* traceRayEXT(... PrimaryRayHitGroupIndex ...) of raygen.rgen:68 */
+void tracePrimaryType(const pto_scene &s, const pt_render_params &p, const Ray &ray, Payload &payload, Counters &c)
+{
+    const HitInfo hit = traceClosest(s, ray.Origin, ray.Direction, ray.tmin, ray.tmax, c);
+    /* the any-hit stage wrote its decal record into the payload before closest-hit / miss run */
+    if (hit.decalDist != -1.0f)
+    {
+        payload.LightDirection = hit.decalColor;
+        payload.LightDistance = hit.decalAlpha;
+        payload.DirectLightPdf = hit.decalDist;
+    }
+    if (hit.tri == PT_NO_HIT)
+        missShader(s, p, ray.Direction, payload);
+    else
+        closestHitShader(s, p, hit, ray.Origin, ray.Direction, payload, c);
+}
+
+/* PT/Shaders/raygen.rgen:22-34 */
+bool checkOccluded(const pto_scene &s, vec3 lightDir, vec3 position, float dist, Counters &c)
+{
+    vec3 direction = -normalize(lightDir);
+    float tmin = 0.00001f;
+    float tmax = dist;
+    return traceOccluded(s, position, direction, tmin, tmax, c);
+}
+
+const uint32_t kMaxRestarts = 1024; /* raygen.rgen:99-112 can spin forever; the oracle and the core both cap it */
+
+/* PT/Shaders/raygen.rgen:36-118, one invocation (SampleCount samples of one pixel) */
+vec3 raygenPixel(const pto_scene &s, const pt_render_params &p, uint32_t px, uint32_t py, uint32_t width, uint32_t height,
+                 uint32_t sampleCount, uint32_t totalSamples, Counters &c)
+{
+    const mat4 ViewInverse = toMat4(p.view_inverse);
+    const mat4 ProjInverse = toMat4(p.proj_inverse);
+    uint32_t rngState = initRng(px, py, width, totalSamples);
+    vec3 radiance = V3(0.0f);
+    Payload payload;
+    std::memset(&payload, 0, sizeof(payload));
+    uint32_t restarts = 0;
+
+    for (int smpl = 0; smpl < (int)sampleCount; smpl++)
+    {
+        vec3 throughput = V3(1.0f);
+        const float ux = rnd(rngState);
+        const float uy = rnd(rngState);
+        vec2 u = V2(ux, uy);
+        Ray ray, rx, ry;
+        const vec2 pixel = V2((float)px, (float)py), resolution = V2((float)width, (float)height);
+        if (p.lens_radius > 0)
+        {
+            const float u2x = rnd(rngState);
+            const float u2y = rnd(rngState);
+            ray = constructPrimaryRayLens(pixel, resolution, ViewInverse, ProjInverse, u, V2(u2x, u2y), p.lens_radius,
+                                          p.focal_distance, rx, ry);
+        }
+        else
+            ray = constructPrimaryRay(pixel, resolution, ViewInverse, ProjInverse, u, rx, ry);
+
+        payload.RayDifferentials0 = V4(rx.Origin, rx.Direction.x);
+        payload.RayDifferentials1 = V4(rx.Direction.y, rx.Direction.z, ry.Origin.x, ry.Origin.y);
+        payload.RayDifferentials2 = V4(ry.Origin.z, ry.Direction.x, ry.Direction.y, ry.Direction.z);
+        payload.MaxRoughness = 0.0f;
+
+        for (uint32_t bounce = 0; bounce < p.bounce_count; bounce++)
+        {
+            payload.RngState = rngState;
+            payload.DirectLightPdf = -1.0f;
+            payload.LightDirection = V3(0.0f);
+            payload.LightDistance = 0.0f;
+            tracePrimaryType(s, p, ray, payload, c);
+            rngState = payload.RngState;
+
+            if (payload.Pdf == -1.0f)
+            {
+                radiance += throughput * payload.Emissive;
+                break;
+            }
+            radiance += throughput * payload.Emissive;
+
+            if (payload.DirectLightPdf > 0.0f)
+                if (!checkOccluded(s, payload.LightDirection, payload.Position, payload.LightDistance, c))
+                    radiance += throughput * payload.DirectLight / payload.DirectLightPdf;
+
+            if (payload.Pdf > 0.001f)
+                throughput *= payload.Bsdf / payload.Pdf;
+
+            const float prob = min(maxComponent(throughput), 1.0f);
+            if (prob < 0.001f)
+                break;
+            if (prob < rnd(rngState))
+                break;
+            throughput /= prob;
+
+            ray.Origin = payload.Position;
+            ray.Direction = payload.Direction;
+        }
+        c.samples++;
+
+        if (isnan(radiance.x) || isnan(radiance.y) || isnan(radiance.z) || isinf(radiance.x) || isinf(radiance.y) ||
+            isinf(radiance.z))
+        {
+            radiance = V3(0.0f);
+            if (++restarts > kMaxRestarts)
+                break;
+            c.restarts++;
+            smpl = -1;
+            continue;
+        }
+    }
+    return radiance;
+}
+
+pt_hit toPtHit(const pto_scene &s, const HitInfo &h)
+{
+    pt_hit r;
+    if (h.tri == PT_NO_HIT)
+    {
+        r.instance = r.geometry = r.primitive = PT_NO_HIT;
+        r.t = r.u = r.v = 0.0f;
+        return r;
+    }
+    const FlatTri &t = s.tris[h.tri];
+    r.instance = t.instance;
+    r.geometry = t.geometry;
+    r.primitive = t.primitive;
+    r.t = h.t;
+    r.u = h.b1;
+    r.v = h.b2;
+    return r;
+}
+
+bool inTiles(uint32_t x, uint32_t y, const pt_tile *tiles, uint32_t n)
+{
+    if (!tiles)
+        return true;
+    for (uint32_t i = 0; i < n; i++)
+        if (x >= tiles[i].x0 && x < tiles[i].x1 && y >= tiles[i].y0 && y < tiles[i].y1)
+            return true;
+    return false;
+}
+
+MaterialSample materialFromFloats(const float *f)
+{
+    MaterialSample m;
+    m.EmissiveColor = V3(f[0], f[1], f[2]);
+    m.Color = V3(f[3], f[4], f[5]);
+    m.Normal = V3(f[6], f[7], f[8]);
+    m.Roughness = f[9];
+    m.Metalness = f[10];
+    m.Transmission = f[11];
+    m.Eta = f[12];
+    m.AttenuationColor = V3(f[13], f[14], f[15]);
+    m.AttenuationDistance = f[16];
+    return m;
+}
+
+const uint32_t kTestIn[PT_TEST_MODE_COUNT] = { 4, 4, 4, 2, 1, 10, 11, 6, 3, 23, 21, 4, 42, 6, 2, 3 };
+const uint32_t kTestOut[PT_TEST_MODE_COUNT] = { 1, 1, 1, 1, 1, 4, 4, 3, 4, 4, 8, 9, 18, 3, 2, 9 };
+
+} // namespace
+
+/* ========================================================================= */
+/* C ABI                                                                     */
+/* ========================================================================= */
+
+extern "C" {
+
+pto_scene *pto_scene_create(const pt_scene_desc *d)
+{
+    if (!d)
+        return nullptr;
+    pto_scene *s = new pto_scene();
+    s->vertices.assign(d->vertices, d->vertices + d->vertex_count);
+    s->indices.assign(d->indices, d->indices + d->index_count);
+    for (uint32_t i = 0; i < d->transform_count; i++)
+    {
+        const float *m = d->transforms + 12 * i;
+        s->transforms.push_back(
+            mat3x4 { { V4(m[0], m[1], m[2], m[3]), V4(m[4], m[5], m[6], m[7]), V4(m[8], m[9], m[10], m[11]) } });
+    }
+    s->geometries.assign(d->geometries, d->geometries + d->geometry_count);
+    s->meshRecords.assign(d->mesh_records, d->mesh_records + d->mesh_record_count);
+    s->models.assign(d->models, d->models + d->model_count);
+    s->instances.assign(d->instances, d->instances + d->instance_count);
+    if (d->mr_material_count)
+        s->mr.assign(d->mr_materials, d->mr_materials + d->mr_material_count);
+    if (d->sg_material_count)
+        s->sg.assign(d->sg_materials, d->sg_materials + d->sg_material_count);
+    if (d->phong_material_count)
+        s->phong.assign(d->phong_materials, d->phong_materials + d->phong_material_count);
+    if (d->point_light_count)
+        s->pointLights.assign(d->point_lights, d->point_lights + d->point_light_count);
+    s->directional = d->directional_light;
+
+    /* built-in textures, slots 0-8 (PT/Shaders/ShaderTypes.incl:18-26; texel values
+     * ShaderRendererTypes.incl:49-56; sRGB rule TextureUploader.cpp:571-595 applied to the type) */
+    s->textures.push_back(makeDefaultTexture(0xffffffffu, true));  /* 0 colour      */
+    s->textures.push_back(makeDefaultTexture(0xffff8080u, false)); /* 1 normal      */
+    s->textures.push_back(makeDefaultTexture(0xffffffffu, false)); /* 2 roughness   */
+    s->textures.push_back(makeDefaultTexture(0xffffffffu, false)); /* 3 metalness   */
+    s->textures.push_back(makeDefaultTexture(0x00000000u, true));  /* 4 emissive    */
+    s->textures.push_back(makeDefaultTexture(0xffffffffu, true));  /* 5 specular    */
+    s->textures.push_back(makeDefaultTexture(0x00000000u, false)); /* 6 glossiness  */
+    s->textures.push_back(makeDefaultTexture(0x00000000u, false)); /* 7 shininess   */
+    s->textures.push_back(makeDefaultTexture(0xffffffffu, true));  /* 8 placeholder */
+    for (uint32_t i = 0; i < d->texture_count; i++)
+        s->textures.push_back(makeTexture(d->textures[i]));
+    if (d->skybox_2d)
+    {
+        s->hasSky2D = true;
+        s->sky2D = makeTexture(*d->skybox_2d);
+    }
+
+    /* flatten TLAS -> BLAS -> geometry into world-space triangles
+     * (PT/Renderer/AccelerationStructure.cpp:64-165, 260-301) */
+    for (uint32_t ii = 0; ii < d->instance_count; ii++)
+    {
+        const pt_instance &inst = s->instances[ii];
+        const pt_model &model = s->models[inst.model_index];
+        const mat3x4 o2w = objectToWorld3x4(inst);
+        for (uint32_t mi = 0; mi < model.mesh_count; mi++)
+        {
+            const pt_mesh_record &rec = s->meshRecords[model.mesh_offset + mi];
+            const pt_geometry &g = s->geometries[rec.geometry_index];
+            const mat3x4 transform = M4(s->transforms[rec.transform_index]) * o2w;
+            for (uint32_t pi = 0; pi < g.index_length / 3; pi++)
+            {
+                FlatTri t;
+                t.p0 = V4(getVertex(*s, g, pi * 3).Position, 1.0f) * transform;
+                t.p1 = V4(getVertex(*s, g, pi * 3 + 1).Position, 1.0f) * transform;
+                t.p2 = V4(getVertex(*s, g, pi * 3 + 2).Position, 1.0f) * transform;
+                t.instance = ii;
+                t.geometry = mi;
+                t.primitive = pi;
+                t.opaque = g.is_opaque;
+                s->tris.push_back(t);
+            }
+        }
+    }
+    BvhBuilder(*s).build();
+    return s;
+}
+
+void pto_scene_destroy(pto_scene *s) { delete s; }
+
+uint64_t pto_scene_triangle_count(const pto_scene *s) { return s ? s->tris.size() : 0; }
+
+int32_t pto_render(const pto_scene *s, const pt_render_params *p, uint32_t width, uint32_t height, uint32_t first_sample,
+                   uint32_t sample_count, const pt_tile *tiles, uint32_t tile_count, float *accum, int32_t threads,
+                   pto_counters *out)
+{
+    if (!s || !p || !accum)
+        return PT_ERR_INVALID_ARGUMENT;
+    int nthreads = threads > 0 ? threads : (int)std::thread::hardware_concurrency();
+    if (nthreads < 1)
+        nthreads = 1;
+    std::vector<Counters> counters(nthreads);
+    std::atomic<uint32_t> nextRow { 0 };
+    auto worker = [&](int tid) {
+        Counters &c = counters[tid];
+        for (;;)
+        {
+            const uint32_t y = nextRow.fetch_add(1);
+            if (y >= height)
+                break;
+            for (uint32_t x = 0; x < width; x++)
+            {
+                if (!inTiles(x, y, tiles, tile_count))
+                    continue;
+                float *px = accum + ((size_t)y * width + x) * 4;
+                for (uint32_t f = 0; f < sample_count; f++)
+                {
+                    /* one frame: SampleCount = 1, TotalSamples = first_sample + f; raygen.rgen:115-117 */
+                    const vec3 radiance = raygenPixel(*s, *p, x, y, width, height, 1, first_sample + f, c);
+                    px[0] = radiance.x + px[0];
+                    px[1] = radiance.y + px[1];
+                    px[2] = radiance.z + px[2];
+                    px[3] = 1.0f;
+                }
+            }
+        }
+    };
+    if (nthreads == 1)
+        worker(0);
+    else
+    {
+        std::vector<std::thread> pool;
+        for (int i = 0; i < nthreads; i++)
+            pool.emplace_back(worker, i);
+        for (auto &t : pool)
+            t.join();
+    }
+    if (out)
+    {
+        Counters total;
+        for (auto &c : counters)
+            total.add(c);
+        out->rays_closest = total.rays_closest;
+        out->rays_shadow = total.rays_shadow;
+        out->samples = total.samples;
+        out->hits = total.hits;
+        out->box_tests_closest = total.box_c;
+        out->tri_tests_closest = total.tri_c;
+        out->box_tests_shadow = total.box_s;
+        out->tri_tests_shadow = total.tri_s;
+        out->alpha_tests_closest = total.alpha_c;
+        out->alpha_tests_shadow = total.alpha_s;
+        out->texel_fetches = total.texels;
+        out->restarts = total.restarts;
+    }
+    return PT_OK;
+}
+
+int32_t pto_first_hit_aov(const pto_scene *s, const pt_render_params *p, uint32_t width, uint32_t height,
+                          pt_hit *out_hits)
+{
+    if (!s || !p || !out_hits)
+        return PT_ERR_INVALID_ARGUMENT;
+    const mat4 ViewInverse = toMat4(p->view_inverse);
+    const mat4 ProjInverse = toMat4(p->proj_inverse);
+    Counters c;
+    for (uint32_t y = 0; y < height; y++)
+        for (uint32_t x = 0; x < width; x++)
+        {
+            Ray rx, ry;
+            /* PT/Shaders/ray.glsl:87-90: pixel centre */
+            const Ray ray = constructPrimaryRay(V2((float)x, (float)y), V2((float)width, (float)height), ViewInverse,
+                                                ProjInverse, V2(0.5f, 0.5f), rx, ry);
+            const HitInfo h = traceClosest(*s, ray.Origin, ray.Direction, ray.tmin, ray.tmax, c);
+            out_hits[(size_t)y * width + x] = toPtHit(*s, h);
+        }
+    return PT_OK;
+}
+
+int32_t pto_trace_closest(const pto_scene *s, const pt_ray *rays, uint64_t n, pt_hit *out_hits)
+{
+    if (!s || !rays || !out_hits)
+        return PT_ERR_INVALID_ARGUMENT;
+    Counters c;
+    for (uint64_t i = 0; i < n; i++)
+    {
+        const pt_ray &r = rays[i];
+        const HitInfo h = traceClosest(*s, V3(r.origin[0], r.origin[1], r.origin[2]),
+                                       V3(r.direction[0], r.direction[1], r.direction[2]), r.tmin, r.tmax, c);
+        out_hits[i] = toPtHit(*s, h);
+    }
+    return PT_OK;
+}
+
+int32_t pto_trace_occlusion(const pto_scene *s, const pt_ray *rays, uint64_t n, uint8_t *out)
+{
+    if (!s || !rays || !out)
+        return PT_ERR_INVALID_ARGUMENT;
+    Counters c;
+    for (uint64_t i = 0; i < n; i++)
+    {
+        const pt_ray &r = rays[i];
+        out[i] = traceOccluded(*s, V3(r.origin[0], r.origin[1], r.origin[2]),
+                               V3(r.direction[0], r.direction[1], r.direction[2]), r.tmin, r.tmax, c)
+                     ? 1
+                     : 0;
+    }
+    return PT_OK;
+}
+
+int32_t pto_trace_closest_bruteforce_f64(const pto_scene *s, const pt_ray *rays, uint64_t n, pt_hit *out_hits,
+                                         double *out_t)
+{
+    if (!s || !rays || !out_hits)
+        return PT_ERR_INVALID_ARGUMENT;
+    for (uint64_t i = 0; i < n; i++)
+    {
+        const pt_ray &r = rays[i];
+        const double o[3] = { r.origin[0], r.origin[1], r.origin[2] };
+        const double d[3] = { r.direction[0], r.direction[1], r.direction[2] };
+        double best = r.tmax;
+        HitInfo h;
+        double bu = 0, bv = 0;
+        for (size_t ti = 0; ti < s->tris.size(); ti++)
+        {
+            const FlatTri &t = s->tris[ti];
+            const double p0[3] = { t.p0.x, t.p0.y, t.p0.z };
+            const double e1[3] = { t.p1.x - p0[0], t.p1.y - p0[1], t.p1.z - p0[2] };
+            const double e2[3] = { t.p2.x - p0[0], t.p2.y - p0[1], t.p2.z - p0[2] };
+            const double pv[3] = { d[1] * e2[2] - d[2] * e2[1], d[2] * e2[0] - d[0] * e2[2], d[0] * e2[1] - d[1] * e2[0] };
+            const double det = e1[0] * pv[0] + e1[1] * pv[1] + e1[2] * pv[2];
+            if (det == 0.0)
+                continue;
+            const double inv = 1.0 / det;
+            const double tv[3] = { o[0] - p0[0], o[1] - p0[1], o[2] - p0[2] };
+            const double u = (tv[0] * pv[0] + tv[1] * pv[1] + tv[2] * pv[2]) * inv;
+            if (u < 0.0 || u > 1.0)
+                continue;
+            const double qv[3] = { tv[1] * e1[2] - tv[2] * e1[1], tv[2] * e1[0] - tv[0] * e1[2],
+                                   tv[0] * e1[1] - tv[1] * e1[0] };
+            const double v = (d[0] * qv[0] + d[1] * qv[1] + d[2] * qv[2]) * inv;
+            if (v < 0.0 || u + v > 1.0)
+                continue;
+            const double tt = (e2[0] * qv[0] + e2[1] * qv[1] + e2[2] * qv[2]) * inv;
+            if (!(tt > r.tmin && tt < best))
+                continue;
+            if (!t.opaque)
+            {
+                const vec4 color = anyHitColor(*s, t, (float)u, (float)v);
+                if (color.w < 0.5f)
+                    continue;
+            }
+            best = tt;
+            h.tri = (uint32_t)ti;
+            bu = u;
+            bv = v;
+        }
+        h.t = (float)best;
+        h.b1 = (float)bu;
+        h.b2 = (float)bv;
+        out_hits[i] = toPtHit(*s, h);
+        if (out_t)
+            out_t[i] = h.tri == PT_NO_HIT ? 0.0 : best;
+    }
+    return PT_OK;
+}
+
+int32_t pto_test_shading(uint32_t mode, const float *in, float *out, uint32_t count)
+{
+    if (mode >= PT_TEST_MODE_COUNT || !in || !out)
+        return PT_ERR_INVALID_ARGUMENT;
+    const uint32_t is = kTestIn[mode], os = kTestOut[mode];
+    for (uint32_t i = 0; i < count; i++)
+    {
+        const float *a = in + (size_t)i * is;
+        float *o = out + (size_t)i * os;
+        switch (mode)
+        {
+        case PT_TEST_GGX_DISTRIBUTION:
+            o[0] = GGXDistribution(V3(a[0], a[1], a[2]), a[3]);
+            break;
+        case PT_TEST_LAMBDA:
+            o[0] = Lambda(V3(a[0], a[1], a[2]), a[3]);
+            break;
+        case PT_TEST_GGX_SMITH:
+            o[0] = GGXSmith(V3(a[0], a[1], a[2]), a[3]);
+            break;
+        case PT_TEST_DIELECTRIC_FRESNEL:
+            o[0] = DielectricFresnel(a[0], a[1]);
+            break;
+        case PT_TEST_SCHLICK_FRESNEL:
+            o[0] = SchlickFresnel(a[0]);
+            break;
+        case PT_TEST_EVALUATE_REFLECTION: {
+            float pdf;
+            const vec3 f = EvaluateReflection(V3(a[0], a[1], a[2]), V3(a[3], a[4], a[5]), V3(a[6], a[7], a[8]), a[9], pdf);
+            o[0] = f.x, o[1] = f.y, o[2] = f.z, o[3] = pdf;
+            break;
+        }
+        case PT_TEST_EVALUATE_REFRACTION: {
+            float pdf;
+            const vec3 f =
+                EvaluateRefraction(V3(a[0], a[1], a[2]), V3(a[3], a[4], a[5]), V3(a[6], a[7], a[8]), a[9], a[10], pdf);
+            o[0] = f.x, o[1] = f.y, o[2] = f.z, o[3] = pdf;
+            break;
+        }
+        case PT_TEST_SAMPLE_GGX: {
+            const vec3 h = SampleGGX(V2(a[0], a[1]), V3(a[2], a[3], a[4]), a[5]);
+            o[0] = h.x, o[1] = h.y, o[2] = h.z;
+            break;
+        }
+        case PT_TEST_SAMPLE_LOBE_PDFS: {
+            MaterialSample m;
+            std::memset(&m, 0, sizeof(m));
+            m.Metalness = a[0];
+            m.Transmission = a[1];
+            const LobePdfs p = sampleLobePdfs(m, a[2]);
+            o[0] = p.Diffuse, o[1] = p.Glossy, o[2] = p.Metallic, o[3] = p.Transmissive;
+            break;
+        }
+        case PT_TEST_EVALUATE_BSDF: {
+            const MaterialSample m = materialFromFloats(a);
+            float pdf;
+            const vec3 f = evaluateBSDF(m, V3(a[17], a[18], a[19]), V3(a[20], a[21], a[22]), pdf);
+            o[0] = f.x, o[1] = f.y, o[2] = f.z, o[3] = pdf;
+            break;
+        }
+        case PT_TEST_SAMPLE_BSDF: {
+            const MaterialSample m = materialFromFloats(a);
+            uint32_t rng = floatBitsToUint(a[20]);
+            const BSDFSample b = sampleBSDF(m, V3(a[17], a[18], a[19]), rng);
+            o[0] = b.Direction.x, o[1] = b.Direction.y, o[2] = b.Direction.z, o[3] = b.Pdf;
+            o[4] = b.Color.x, o[5] = b.Color.y, o[6] = b.Color.z, o[7] = uintBitsToFloat(rng);
+            break;
+        }
+        case PT_TEST_RNG: {
+            uint32_t st = initRng(floatBitsToUint(a[0]), floatBitsToUint(a[1]), floatBitsToUint(a[2]), floatBitsToUint(a[3]));
+            o[0] = uintBitsToFloat(st);
+            for (int k = 0; k < 4; k++)
+            {
+                const float f = rnd(st);
+                o[1 + k] = uintBitsToFloat(st);
+                o[5 + k] = f;
+            }
+            break;
+        }
+        case PT_TEST_PRIMARY_RAY: {
+            const vec2 pixel = V2((float)floatBitsToUint(a[0]), (float)floatBitsToUint(a[1]));
+            const vec2 res = V2((float)floatBitsToUint(a[2]), (float)floatBitsToUint(a[3]));
+            const mat4 vi = toMat4(a + 10), pi = toMat4(a + 26);
+            Ray rx, ry, r;
+            if (a[8] > 0)
+                r = constructPrimaryRayLens(pixel, res, vi, pi, V2(a[4], a[5]), V2(a[6], a[7]), a[8], a[9], rx, ry);
+            else
+                r = constructPrimaryRay(pixel, res, vi, pi, V2(a[4], a[5]), rx, ry);
+            const Ray *rs[3] = { &r, &rx, &ry };
+            for (int k = 0; k < 3; k++)
+            {
+                o[k * 6 + 0] = rs[k]->Origin.x, o[k * 6 + 1] = rs[k]->Origin.y, o[k * 6 + 2] = rs[k]->Origin.z;
+                o[k * 6 + 3] = rs[k]->Direction.x, o[k * 6 + 4] = rs[k]->Direction.y, o[k * 6 + 5] = rs[k]->Direction.z;
+            }
+            break;
+        }
+        case PT_TEST_OFFSET_SELF_INTERSECTION: {
+            const vec3 r = offsetRayOriginSelfIntersection(V3(a[0], a[1], a[2]), V3(a[3], a[4], a[5]));
+            o[0] = r.x, o[1] = r.y, o[2] = r.z;
+            break;
+        }
+        case PT_TEST_CONCENTRIC_DISK: {
+            const vec2 r = sampleUniformDiskConcentric(V2(a[0], a[1]));
+            o[0] = r.x, o[1] = r.y;
+            break;
+        }
+        case PT_TEST_TANGENT_SPACE: {
+            const mat3 m = computeTangentSpace(V3(a[0], a[1], a[2]));
+            for (int k = 0; k < 3; k++)
+                o[k * 3] = m.c[k].x, o[k * 3 + 1] = m.c[k].y, o[k * 3 + 2] = m.c[k].z;
+            break;
+        }
+        }
+    }
+    return PT_OK;
+}
+
+int32_t pto_texture_info(const pto_scene *s, uint32_t slot, uint32_t *w, uint32_t *h, uint32_t *levels)
+{
+    if (!s || slot >= s->textures.size())
+        return PT_ERR_INVALID_ARGUMENT;
+    const Texture &t = s->textures[slot];
+    if (w)
+        *w = t.levels[0].w;
+    if (h)
+        *h = t.levels[0].h;
+    if (levels)
+        *levels = (uint32_t)t.levels.size();
+    return PT_OK;
+}
+
+int32_t pto_texture_level(const pto_scene *s, uint32_t slot, uint32_t level, uint8_t *out)
+{
+    if (!s || slot >= s->textures.size() || !out)
+        return PT_ERR_INVALID_ARGUMENT;
+    const Texture &t = s->textures[slot];
+    if (t.isFloat || level >= t.levels.size())
+        return PT_ERR_INVALID_ARGUMENT;
+    std::memcpy(out, t.levels[level].rgba8.data(), t.levels[level].rgba8.size());
+    return PT_OK;
+}
+
+int32_t pto_texture_sample(const pto_scene *s, uint32_t slot, const float *in6, float *out4, uint32_t count,
+                           int32_t use_grad)
+{
+    if (!s || slot >= s->textures.size() || !in6 || !out4)
+        return PT_ERR_INVALID_ARGUMENT;
+    const Texture &t = s->textures[slot];
+    for (uint32_t i = 0; i < count; i++)
+    {
+        const float *a = in6 + (size_t)i * 6;
+        const vec4 r = use_grad ? textureGrad(t, V2(a[0], a[1]), V2(a[2], a[3]), V2(a[4], a[5]), nullptr)
+                                : textureLod0(t, V2(a[0], a[1]));
+        out4[i * 4] = r.x, out4[i * 4 + 1] = r.y, out4[i * 4 + 2] = r.z, out4[i * 4 + 3] = r.w;
+    }
+    return PT_OK;
+}
+
+} /* extern "C" */

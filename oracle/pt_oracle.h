@@ -1,0 +1,83 @@
+/*
+ * pt_oracle.h — C ABI of the CPU oracle.
+ *
+ * TEST INFRASTRUCTURE, NOT PRODUCT.  Only tests/, __graft_entry__.smoke() and
+ * bench.py's cpu_baseline / --impl reference legs may load this library; the
+ * product path (path-tracing_b200/, include/pt_core.h) never does.
+ *
+ * The oracle is a literal, scalar CPU restatement of the reference's GLSL hot
+ * path (PT/Shaders/{common,ray,tracing,shading,bsdf,sampling,material}.glsl,
+ * raygen.rgen, closestHit.rchit, anyhit.rahit, occlusionAnyhit.rahit,
+ * miss.rmiss, occlusion.rmiss), one thread of control per pixel like the
+ * reference's raygen invocation.  See pt_oracle.cpp for per-function
+ * citations and for what is and is not pinned by the reference's own tests.
+ *
+ * It consumes the same scene / parameter PODs as the product ABI (pt_core.h).
+ */
+#ifndef PT_ORACLE_H
+#define PT_ORACLE_H
+
+#include "../include/pt_core.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct pto_scene pto_scene;
+
+/* Extra per-run counters the roofline formula of SURVEY §8(d) needs. */
+typedef struct pto_counters {
+    uint64_t rays_closest;
+    uint64_t rays_shadow;
+    uint64_t samples;
+    uint64_t hits;
+    uint64_t box_tests_closest;
+    uint64_t tri_tests_closest;
+    uint64_t box_tests_shadow;
+    uint64_t tri_tests_shadow;
+    uint64_t alpha_tests_closest;
+    uint64_t alpha_tests_shadow;
+    uint64_t texel_fetches; /* texels read by the material textureGrad fetches */
+    uint64_t restarts;
+} pto_counters;
+
+PT_API pto_scene *pto_scene_create(const pt_scene_desc *scene);
+PT_API void pto_scene_destroy(pto_scene *scene);
+PT_API uint64_t pto_scene_triangle_count(const pto_scene *scene);
+
+/* accum: width*height*4 floats, updated in place exactly like imageLoad/imageStore in
+ * raygen.rgen:115-117 (rgb += radiance, a = 1), for frames TotalSamples = first_sample ..
+ * first_sample + sample_count - 1 with SampleCount = 1.  Only pixels inside the tiles are
+ * touched (tiles == NULL: all).  threads <= 0 uses std::thread::hardware_concurrency(). */
+PT_API int32_t pto_render(const pto_scene *scene, const pt_render_params *params, uint32_t width,
+                          uint32_t height, uint32_t first_sample, uint32_t sample_count, const pt_tile *tiles,
+                          uint32_t tile_count, float *accum, int32_t threads, pto_counters *out_counters);
+
+PT_API int32_t pto_first_hit_aov(const pto_scene *scene, const pt_render_params *params, uint32_t width,
+                                 uint32_t height, pt_hit *out_hits);
+PT_API int32_t pto_trace_closest(const pto_scene *scene, const pt_ray *rays, uint64_t ray_count,
+                                 pt_hit *out_hits);
+PT_API int32_t pto_trace_occlusion(const pto_scene *scene, const pt_ray *rays, uint64_t ray_count,
+                                   uint8_t *out_occluded);
+
+/* Brute-force double-precision closest hit over all triangles (no BVH, Moller-Trumbore in
+ * fp64) — the independent check of the oracle's own BVH + fp32 watertight test. */
+PT_API int32_t pto_trace_closest_bruteforce_f64(const pto_scene *scene, const pt_ray *rays,
+                                                uint64_t ray_count, pt_hit *out_hits, double *out_t);
+
+/* Same modes / record layouts as pt_test_shading in pt_core.h. */
+PT_API int32_t pto_test_shading(uint32_t mode, const float *input, float *output, uint32_t count);
+
+/* Texture sampler probes (slot indexes the bindless array: 0-8 built in, 9+ scene). */
+PT_API int32_t pto_texture_info(const pto_scene *scene, uint32_t slot, uint32_t *out_width,
+                                uint32_t *out_height, uint32_t *out_levels);
+/* Copies RGBA8 level `level` of an 8-bit texture (width*height*4 bytes). */
+PT_API int32_t pto_texture_level(const pto_scene *scene, uint32_t slot, uint32_t level, uint8_t *out_rgba8);
+/* records: in uv.xy, ddx.xy, ddy.xy (6 floats) -> out rgba; use_grad = 0 samples LOD 0 (texture()). */
+PT_API int32_t pto_texture_sample(const pto_scene *scene, uint32_t slot, const float *in6, float *out4,
+                                  uint32_t count, int32_t use_grad);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

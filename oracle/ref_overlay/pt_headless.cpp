@@ -1,0 +1,59 @@
+/*
+ * pt_headless — the reference's host code driving the B200 core: SceneManager loads a scene
+ * with the reference's own loaders, HeadlessRenderer (the Renderer stand-in) uploads it through
+ * the C ABI, renders `spp` samples and writes a PNG, i.e. the reference's "Render" button flow
+ * (Path-Tracing/UserInterface.cpp:1074-1092) without a window.
+ *
+ *   pt_headless <group> <scene> <width> <height> <spp> <bounces> <out.png>
+ */
+#include <cstdio>
+
+#include "Core/Core.h"
+
+#include "HeadlessRenderer.h"
+#include "SceneManager.h"
+
+using namespace PathTracing;
+
+int main(int argc, char **argv)
+{
+    if (argc != 8)
+    {
+        std::fprintf(stderr, "usage: pt_headless <group> <scene> <width> <height> <spp> <bounces> <out.png>\n");
+        return 2;
+    }
+    try
+    {
+        SceneManager::Init();
+        if (std::string(argv[1]) != "Test Scenes" || std::string(argv[2]) != "Default")
+            SceneManager::SetActiveScene(argv[1], argv[2]);
+        std::shared_ptr<Scene> scene = SceneManager::GetActiveScene();
+        InputCamera::DisableInput();
+
+        HeadlessRenderer renderer(0);
+        renderer.OnResize(std::atoi(argv[3]), std::atoi(argv[4]));
+        renderer.SetSettings(HeadlessRenderer::PathTracingSettings { .BounceCount = (uint32_t)std::atoi(argv[6]) });
+
+        const uint32_t spp = std::atoi(argv[5]);
+        const bool updated = scene->Update(0.0f);
+        renderer.UpdateSceneData(scene, updated);
+        renderer.Render(spp);
+        renderer.SavePng(argv[7]);
+
+        const pt_stats stats = renderer.GetStats();
+        std::printf(
+            "%u spp, %.3f ms, %.1f Mrays/s (%llu closest + %llu shadow), %llu tris, BVH build %.3f ms\n",
+            renderer.GetTotalSamples(), stats.last_render_ms,
+            (stats.rays_closest + stats.rays_shadow) / (stats.last_render_ms * 1e3),
+            (unsigned long long)stats.rays_closest, (unsigned long long)stats.rays_shadow,
+            (unsigned long long)stats.triangle_count, stats.bvh_build_ms
+        );
+        SceneManager::Shutdown();
+    }
+    catch (const std::exception &e)
+    {
+        std::fprintf(stderr, "error: %s\n", e.what());
+        return 1;
+    }
+    return 0;
+}

@@ -1,0 +1,143 @@
+#include "HeadlessRenderer.h"
+
+#include <stb_image_write.h>
+
+#include <cmath>
+#include <cstring>
+#include <format>
+
+#include "Core/Core.h"
+
+
+namespace PathTracing
+{
+
+HeadlessRenderer::HeadlessRenderer(int cudaDevice)
+{
+    const pt_status status = pt_context_create(cudaDevice, &m_Context);
+    if (status != PT_OK)
+        throw error(std::format("pt_context_create failed ({}): {}", status, pt_last_error(nullptr)));
+}
+
+HeadlessRenderer::~HeadlessRenderer()
+{
+    pt_context_destroy(m_Context);
+}
+
+void HeadlessRenderer::Check(pt_status status, const char *what)
+{
+    if (status != PT_OK)
+        throw error(std::format("{} failed ({}): {}", what, status, pt_last_error(m_Context)));
+}
+
+void HeadlessRenderer::ResetAccumulation()
+{
+    m_TotalSamples = 0;
+    if (m_Width != 0 && m_Height != 0)
+        Check(pt_render_begin(m_Context, m_Width, m_Height), "pt_render_begin");
+}
+
+void HeadlessRenderer::UpdateSceneData(const std::shared_ptr<Scene> &scene, bool updated)
+{
+    if (updated)
+        ResetAccumulation();
+
+    if (m_Scene == scene)
+        return;
+
+    m_Scene = scene;
+    const auto flat = FlattenScene(*scene);
+    Check(pt_scene_upload(m_Context, &flat->Desc), "pt_scene_upload");
+    ResetAccumulation();
+}
+
+void HeadlessRenderer::OnResize(uint32_t width, uint32_t height)
+{
+    m_Width = width;
+    m_Height = height;
+    ResetAccumulation();
+}
+
+void HeadlessRenderer::SetSettings(const PathTracingSettings &settings)
+{
+    m_PathTracing = settings;
+    ResetAccumulation();
+}
+
+void HeadlessRenderer::SetSettings(const PostProcessSettings &settings)
+{
+    m_PostProcess = settings;
+}
+
+void HeadlessRenderer::Render(uint32_t samples)
+{
+    if (m_Scene == nullptr)
+        throw error("HeadlessRenderer::Render called without a scene");
+
+    /* Renderer.cpp:1686-1694 */
+    Camera &camera = m_Scene->GetActiveCamera();
+    camera.OnResize(m_Width, m_Height);
+    const glm::mat4 invView = camera.GetInvViewMatrix();
+    const glm::mat4 invProj = camera.GetInvProjectionMatrix();
+
+    pt_render_params params = {};
+    std::memcpy(params.view_inverse, &invView, sizeof(params.view_inverse));
+    std::memcpy(params.proj_inverse, &invProj, sizeof(params.proj_inverse));
+    params.bounce_count = m_PathTracing.BounceCount;
+    params.lens_radius = m_PathTracing.LensRadius;
+    params.focal_distance = m_PathTracing.FocalDistance;
+    /* UpdateScenePipelineConfig: specialisation constants follow the scene (Renderer.cpp:711-754) */
+    params.miss_flags = std::holds_alternative<Skybox2D>(m_Scene->GetSkybox()) ? PT_MISS_FLAGS_SKYBOX_2D
+                                                                                : PT_MISS_FLAGS_NONE;
+    params.hit_flags = m_Scene->HasDxNormalTextures() ? PT_HIT_FLAGS_DX_NORMAL_TEXTURES : PT_HIT_FLAGS_NONE;
+
+    Check(pt_render_samples(m_Context, &params, m_TotalSamples, samples, nullptr, 0), "pt_render_samples");
+    m_TotalSamples += samples;
+}
+
+std::vector<float> HeadlessRenderer::ReadAccumulation()
+{
+    std::vector<float> pixels(static_cast<size_t>(m_Width) * m_Height * 4);
+    Check(pt_readback(m_Context, pixels.data(), pixels.size() * sizeof(float)), "pt_readback");
+    return pixels;
+}
+
+void HeadlessRenderer::SavePng(const std::string &path)
+{
+    const std::vector<float> sum = ReadAccumulation();
+    std::vector<uint8_t> out(static_cast<size_t>(m_Width) * m_Height * 4);
+    const float scale = m_PostProcess.Exposure / static_cast<float>(std::max(1u, m_TotalSamples));
+    for (size_t i = 0; i < out.size(); i += 4)
+    {
+        for (int c = 0; c < 3; c++)
+        {
+            const float linear = 1.0f - std::exp(-sum[i + c] * scale);
+            const float srgb =
+                linear <= 0.0031308f ? 12.92f * linear : 1.055f * std::pow(linear, 1.0f / 2.4f) - 0.055f;
+            out[i + c] = static_cast<uint8_t>(std::clamp(srgb, 0.0f, 1.0f) * 255.0f + 0.5f);
+        }
+        out[i + 3] = 255;
+    }
+    if (stbi_write_png(path.c_str(), m_Width, m_Height, 4, out.data(), m_Width * 4) == 0)
+        throw error(std::format("Could not write {}", path));
+}
+
+void HeadlessRenderer::SaveHdr(const std::string &path)
+{
+    std::vector<float> sum = ReadAccumulation();
+    const float scale = m_PostProcess.Exposure / static_cast<float>(std::max(1u, m_TotalSamples));
+    for (size_t i = 0; i < sum.size(); i += 4)
+        for (int c = 0; c < 3; c++)
+            sum[i + c] *= scale;
+    if (stbi_write_hdr(path.c_str(), m_Width, m_Height, 4, sum.data()) == 0)
+        throw error(std::format("Could not write {}", path));
+}
+
+pt_stats HeadlessRenderer::GetStats()
+{
+    pt_stats stats = {};
+    Check(pt_get_stats(m_Context, &stats), "pt_get_stats");
+    return stats;
+}
+
+}

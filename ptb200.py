@@ -1,0 +1,10 @@
+"""Import shim: ``import ptb200`` == the ``path-tracing_b200`` package (hyphenated directory)."""
+import importlib
+import os
+import sys
+
+_root = os.path.dirname(os.path.abspath(__file__))
+if _root not in sys.path:
+    sys.path.insert(0, _root)
+_pkg = importlib.import_module("path-tracing_b200")
+sys.modules[__name__] = _pkg
