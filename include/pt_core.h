@@ -325,8 +325,8 @@ PT_API pt_status pt_render_begin(pt_context *ctx, uint32_t width, uint32_t heigh
  * schedule the reference's Profile/Debug builds use (PT/Core/Config.h:34-36).  tiles == NULL
  * renders the whole frame; otherwise only pixels inside the tile_count rectangles are
  * rendered (RNG still uses global pixel coordinates and the full resolution, so the result is
- * bit-identical to the same pixels of a full-frame render).  Asynchronous on the context
- * stream; pt_readback / pt_get_stats / pt_synchronize wait for it. */
+ * bit-identical to the same pixels of a full-frame render).  Blocking: returns when every
+ * sample has been accumulated (the host polls the wavefront's active-path counter). */
 PT_API pt_status pt_render_samples(pt_context *ctx, const pt_render_params *params, uint32_t first_sample,
                                    uint32_t sample_count, const pt_tile *tiles, uint32_t tile_count);
 
@@ -359,6 +359,12 @@ PT_API pt_status pt_trace_occlusion(pt_context *ctx, const pt_ray *rays, uint64_
                                     uint8_t *out_occluded);
 
 PT_API pt_status pt_get_stats(pt_context *ctx, pt_stats *out_stats);
+
+/* Enables (1) / disables (0, default) the per-ray box / triangle / alpha test counters of
+ * pt_stats for subsequent pt_render_samples calls.  Counting costs a few instructions per node,
+ * so timed runs leave it off and the roofline's N_box / N_tri come from a second, identical
+ * (deterministic) run with it on.  rays / samples / hits are always counted. */
+PT_API pt_status pt_set_traversal_stats(pt_context *ctx, int32_t enable);
 
 /* ------------------------------------------------------------------------- */
 /* shader unit-test entry point                                              */

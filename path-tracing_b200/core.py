@@ -1,0 +1,244 @@
+"""ctypes binding of the C ABI (include/pt_core.h) — the Python face of the drop-in boundary.
+
+``Renderer`` mirrors the verbs of the reference's ``Renderer`` facade
+(Path-Tracing/Renderer/Renderer.h:42-85) the same way the C++ ``HeadlessRenderer`` does:
+``update_scene_data`` / ``on_resize`` / ``set_settings`` / ``render`` / ``read_accumulation``.
+There is no CPU fallback: if the CUDA library is missing or no sm_100 device is present the
+constructor raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+from . import scene as sc
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(_HERE, "csrc")
+LIB_PATH = os.path.join(CSRC, "libpt_core.so")
+
+ABI_SYMBOLS = [
+    "pt_context_create",
+    "pt_context_destroy",
+    "pt_last_error",
+    "pt_scene_upload",
+    "pt_texture_upload",
+    "pt_render_begin",
+    "pt_render_samples",
+    "pt_accum_device_ptr",
+    "pt_readback",
+    "pt_synchronize",
+    "pt_first_hit_aov",
+    "pt_trace_closest",
+    "pt_trace_occlusion",
+    "pt_get_stats",
+    "pt_set_traversal_stats",
+    "pt_test_input_stride",
+    "pt_test_output_stride",
+    "pt_test_shading",
+]
+
+
+class PtError(RuntimeError):
+    """Counterpart of PathTracing::error (Path-Tracing/Core/Core.cpp:82-90)."""
+
+    def __init__(self, status: int, message: str):
+        super().__init__(f"[{status}] {message}")
+        self.status = status
+
+
+class Stats(C.Structure):
+    _fields_ = [
+        ("rays_closest", C.c_uint64),
+        ("rays_shadow", C.c_uint64),
+        ("samples", C.c_uint64),
+        ("hits", C.c_uint64),
+        ("box_tests", C.c_uint64),
+        ("tri_tests", C.c_uint64),
+        ("alpha_tests", C.c_uint64),
+        ("restarts", C.c_uint64),
+        ("wavefront_iterations", C.c_uint64),
+        ("kernel_launches", C.c_uint64),
+        ("triangle_count", C.c_uint64),
+        ("bvh_node_count", C.c_uint64),
+        ("bvh_bytes", C.c_uint64),
+        ("bvh_build_ms", C.c_float),
+        ("scene_upload_ms", C.c_float),
+        ("last_render_ms", C.c_float),
+    ]
+
+    def as_dict(self):
+        return {n: getattr(self, n) for n, _ in self._fields_}
+
+
+def build(verbose: bool = False) -> str:
+    """Compiles every CUDA source for sm_100a with the committed Makefile (nvcc cross-compiles)."""
+    subprocess.check_call(["make", "-C", CSRC, "-j4", "libpt_core.so"], stdout=None if verbose else subprocess.DEVNULL)
+    return LIB_PATH
+
+
+_lib = None
+
+
+def lib():
+    """Loads libpt_core.so.  Raises if it has not been built — the product never falls back."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise PtError(-2, f"{LIB_PATH} is missing: run __graft_entry__.build() (there is no CPU fallback)")
+    L = C.CDLL(LIB_PATH)
+    vp, u32, u64, i32 = C.c_void_p, C.c_uint32, C.c_uint64, C.c_int32
+    L.pt_context_create.argtypes = [i32, C.POINTER(vp)]
+    L.pt_context_destroy.argtypes = [vp]
+    L.pt_context_destroy.restype = None
+    L.pt_last_error.argtypes = [vp]
+    L.pt_last_error.restype = C.c_char_p
+    L.pt_scene_upload.argtypes = [vp, vp]
+    L.pt_texture_upload.argtypes = [vp, u32, vp]
+    L.pt_render_begin.argtypes = [vp, u32, u32]
+    L.pt_render_samples.argtypes = [vp, vp, u32, u32, vp, u32]
+    L.pt_accum_device_ptr.argtypes = [vp, C.POINTER(vp), C.POINTER(C.c_size_t), C.POINTER(vp)]
+    L.pt_readback.argtypes = [vp, vp, C.c_size_t]
+    L.pt_synchronize.argtypes = [vp]
+    L.pt_first_hit_aov.argtypes = [vp, vp, u32, u32, vp]
+    L.pt_trace_closest.argtypes = [vp, vp, u64, vp]
+    L.pt_trace_occlusion.argtypes = [vp, vp, u64, vp]
+    L.pt_get_stats.argtypes = [vp, vp]
+    L.pt_set_traversal_stats.argtypes = [vp, i32]
+    L.pt_test_input_stride.argtypes = [u32]
+    L.pt_test_input_stride.restype = u32
+    L.pt_test_output_stride.argtypes = [u32]
+    L.pt_test_output_stride.restype = u32
+    L.pt_test_shading.argtypes = [vp, u32, vp, vp, u32]
+    _lib = L
+    return L
+
+
+class Renderer:
+    def __init__(self, cuda_device: int = 0):
+        self._L = lib()
+        h = C.c_void_p()
+        st = self._L.pt_context_create(cuda_device, C.byref(h))
+        if st != 0:
+            raise PtError(st, (self._L.pt_last_error(None) or b"").decode())
+        self._h = h
+        self.width = self.height = 0
+        self.total_samples = 0
+        self.params: sc.RenderParams | None = None
+
+    # -- plumbing ---------------------------------------------------------------------------
+    def _check(self, st: int):
+        if st != 0:
+            raise PtError(st, (self._L.pt_last_error(self._h) or b"").decode())
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.pt_context_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    # -- Renderer verbs ---------------------------------------------------------------------
+    def update_scene_data(self, scene: sc.SceneData):
+        """Renderer::UpdateSceneData for a new scene: upload + GPU BVH build (blocking)."""
+        desc, keep = scene.to_c()
+        self._check(self._L.pt_scene_upload(self._h, C.addressof(desc)))
+        del keep
+        self.total_samples = 0
+        if self.width:
+            self.on_resize(self.width, self.height)
+
+    def upload_texture(self, slot: int, tex: sc.Texture):
+        px = np.ascontiguousarray(tex.pixels)
+        d = sc.CTextureDesc(tex.width, tex.height, tex.format, 1 if tex.srgb else 0, px.ctypes.data)
+        self._check(self._L.pt_texture_upload(self._h, slot, C.addressof(d)))
+
+    def on_resize(self, width: int, height: int):
+        """Renderer::OnResize / accumulation reset."""
+        self._check(self._L.pt_render_begin(self._h, width, height))
+        self.width, self.height = width, height
+        self.total_samples = 0
+
+    def set_settings(self, params: sc.RenderParams):
+        self.params = params
+
+    def render(self, samples: int = 1, tiles=None, params: sc.RenderParams | None = None, first_sample: int | None = None):
+        """Renderer::Render with SamplesPerFrame = samples (frames of 1 sample, TotalSamples advancing)."""
+        p = (params or self.params).to_c()
+        first = self.total_samples if first_sample is None else first_sample
+        tl = None if tiles is None else np.ascontiguousarray(tiles, sc.TILE)
+        self._check(
+            self._L.pt_render_samples(
+                self._h, C.addressof(p), first, samples, None if tl is None else tl.ctypes.data, 0 if tl is None else len(tl)
+            )
+        )
+        if first_sample is None:
+            self.total_samples += samples
+
+    def read_accumulation(self, out: np.ndarray | None = None) -> np.ndarray:
+        if out is None:
+            out = np.empty((self.height, self.width, 4), np.float32)
+        assert out.dtype == np.float32 and out.flags.c_contiguous and out.size == self.width * self.height * 4
+        self._check(self._L.pt_readback(self._h, out.ctypes.data, out.nbytes))
+        return out
+
+    def readback_into(self, host_ptr: int, nbytes: int):
+        """pt_readback into caller-owned (e.g. pinned) host memory."""
+        self._check(self._L.pt_readback(self._h, host_ptr, nbytes))
+
+    def accum_device_ptr(self):
+        ptr, pitch, stream = C.c_void_p(), C.c_size_t(), C.c_void_p()
+        self._check(self._L.pt_accum_device_ptr(self._h, C.byref(ptr), C.byref(pitch), C.byref(stream)))
+        return ptr.value, pitch.value, stream.value
+
+    def synchronize(self):
+        self._check(self._L.pt_synchronize(self._h))
+
+    # -- queries ----------------------------------------------------------------------------
+    def first_hit_aov(self, params: sc.RenderParams, width: int, height: int) -> np.ndarray:
+        out = np.zeros(width * height, sc.HIT)
+        p = params.to_c()
+        self._check(self._L.pt_first_hit_aov(self._h, C.addressof(p), width, height, out.ctypes.data))
+        return out.reshape(height, width)
+
+    def trace_closest(self, rays: np.ndarray) -> np.ndarray:
+        rays = np.ascontiguousarray(rays, sc.RAY)
+        out = np.zeros(len(rays), sc.HIT)
+        self._check(self._L.pt_trace_closest(self._h, rays.ctypes.data, len(rays), out.ctypes.data))
+        return out
+
+    def trace_occlusion(self, rays: np.ndarray) -> np.ndarray:
+        rays = np.ascontiguousarray(rays, sc.RAY)
+        out = np.zeros(len(rays), np.uint8)
+        self._check(self._L.pt_trace_occlusion(self._h, rays.ctypes.data, len(rays), out.ctypes.data))
+        return out
+
+    def stats(self) -> dict:
+        s = Stats()
+        self._check(self._L.pt_get_stats(self._h, C.addressof(s)))
+        return s.as_dict()
+
+    def set_traversal_stats(self, enable: bool):
+        self._check(self._L.pt_set_traversal_stats(self._h, 1 if enable else 0))
+
+    def test_shading(self, mode: int, inputs: np.ndarray) -> np.ndarray:
+        """TestRenderer::ExecutePipeline equivalent (Path-Tracing-Tests/TestRenderer.cpp:79-106)."""
+        n_in, n_out = self._L.pt_test_input_stride(mode), self._L.pt_test_output_stride(mode)
+        inputs = np.ascontiguousarray(inputs, np.float32).reshape(-1, n_in)
+        out = np.zeros((inputs.shape[0], n_out), np.float32)
+        self._check(self._L.pt_test_shading(self._h, mode, inputs.ctypes.data, out.ctypes.data, inputs.shape[0]))
+        return out

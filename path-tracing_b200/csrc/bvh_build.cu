@@ -1,0 +1,877 @@
+// bvh_build.cu — scene upload: transform baking, texture mip chains and the GPU BVH build.
+//
+// Replaces Renderer::UpdateSceneData's uploads (PT/Renderer/Renderer.cpp:251-399) and the
+// driver-side acceleration-structure build requested by AccelerationStructure's constructor
+// (PT/Renderer/AccelerationStructure.cpp:12-35, 64-165, 260-301) — the reference itself has no BVH
+// code.  Pipeline, all on the GPU:
+//   bake (instance x mesh transforms -> world-space triangles + shading records)
+//   -> centroid bounds -> 63-bit Morton codes -> radix sort (CUB)
+//   -> LBVH hierarchy (Karras 2012) -> bottom-up refit
+//   -> surface-area-guided collapse into 4-wide 128-byte nodes with <= 4-triangle leaves
+//   -> gather triangles into leaf order.
+#include "core_internal.h"
+
+#include <cub/device/device_radix_sort.cuh>
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+
+namespace pt
+{
+
+namespace
+{
+
+// One (instance, mesh) pair of the flattened TLAS/BLAS hierarchy.
+struct MeshInstance
+{
+    float P[12];  // P[j*4 + c]: world_j = p.x*P[j][0] + p.y*P[j][1] + p.z*P[j][2] + P[j][3]
+    float N[9];   // normal matrix (inverse transpose of the linear part), row-major
+    uint32_t triOffset, triCount;
+    uint32_t vertexOffset, indexOffset;
+    uint32_t instance, geometry; // gl_InstanceID, geometry index inside the model
+    uint32_t materialId, flags;
+};
+
+struct Aabb
+{
+    float lo[3], hi[3];
+};
+
+__device__ __forceinline__ uint32_t floatFlip(float f)
+{
+    const uint32_t u = __float_as_uint(f);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float floatUnflip(uint32_t u)
+{
+    return __uint_as_float((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u);
+}
+
+// ---------------------------------------------------------------------------------------------
+// bake
+// ---------------------------------------------------------------------------------------------
+__global__ void k_bake(const MeshInstance *__restrict__ mis, uint32_t miCount, const float *__restrict__ vertices,
+                       const uint32_t *__restrict__ indices, uint32_t triCount, float4 *__restrict__ triPos,
+                       TriShade *__restrict__ triShade, Aabb *__restrict__ boxes, uint32_t *__restrict__ sceneBounds)
+{
+    const uint32_t tri = blockIdx.x * blockDim.x + threadIdx.x;
+    if (tri >= triCount)
+        return;
+    // binary search: last mesh instance with triOffset <= tri
+    uint32_t lo = 0, hi = miCount - 1;
+    while (lo < hi)
+    {
+        const uint32_t mid = (lo + hi + 1) >> 1;
+        if (mis[mid].triOffset <= tri)
+            lo = mid;
+        else
+            hi = mid - 1;
+    }
+    const MeshInstance &mi = mis[lo];
+    const uint32_t prim = tri - mi.triOffset;
+
+    float pos[3][3], nrm[3][3], tan[3][3], bit[3][3], uv[3][2];
+#pragma unroll
+    for (int k = 0; k < 3; k++)
+    {
+        // indices are relative to the geometry's first vertex (PT/Shaders/common.glsl:27-34)
+        const uint32_t index = indices[mi.indexOffset + prim * 3 + k];
+        const float *v = vertices + (size_t)(mi.vertexOffset + index) * 14;
+        const float px = v[0], py = v[1], pz = v[2];
+#pragma unroll
+        for (int j = 0; j < 3; j++)
+        {
+            // same operation order as `vec4(p, 1) * transform`, unfused, so that the oracle and the
+            // core intersect bit-identical triangles
+            const float *P = mi.P + j * 4;
+            pos[k][j] = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(px, P[0]), __fmul_rn(py, P[1])), __fmul_rn(pz, P[2])), P[3]);
+            nrm[k][j] = mi.N[j * 3 + 0] * v[5] + mi.N[j * 3 + 1] * v[6] + mi.N[j * 3 + 2] * v[7];
+            tan[k][j] = P[0] * v[8] + P[1] * v[9] + P[2] * v[10];
+            bit[k][j] = P[0] * v[11] + P[1] * v[12] + P[2] * v[13];
+        }
+        uv[k][0] = v[3];
+        uv[k][1] = v[4];
+    }
+    triPos[3 * (size_t)tri + 0] = make_float4(pos[0][0], pos[0][1], pos[0][2], __uint_as_float(tri));
+    triPos[3 * (size_t)tri + 1] = make_float4(pos[1][0], pos[1][1], pos[1][2], __uint_as_float(mi.flags));
+    triPos[3 * (size_t)tri + 2] = make_float4(pos[2][0], pos[2][1], pos[2][2], __uint_as_float(mi.materialId));
+
+    TriShade ts;
+    ts.a[0] = make_float4(nrm[0][0], nrm[0][1], nrm[0][2], nrm[1][0]);
+    ts.a[1] = make_float4(nrm[1][1], nrm[1][2], nrm[2][0], nrm[2][1]);
+    ts.a[2] = make_float4(nrm[2][2], tan[0][0], tan[0][1], tan[0][2]);
+    ts.a[3] = make_float4(tan[1][0], tan[1][1], tan[1][2], tan[2][0]);
+    ts.a[4] = make_float4(tan[2][1], tan[2][2], bit[0][0], bit[0][1]);
+    ts.a[5] = make_float4(bit[0][2], bit[1][0], bit[1][1], bit[1][2]);
+    ts.a[6] = make_float4(bit[2][0], bit[2][1], bit[2][2], uv[0][0]);
+    ts.a[7] = make_float4(uv[0][1], uv[1][0], uv[1][1], uv[2][0]);
+    ts.a[8] = make_float4(uv[2][1], __uint_as_float(mi.instance), __uint_as_float(mi.geometry), __uint_as_float(prim));
+    triShade[tri] = ts;
+
+    Aabb b;
+#pragma unroll
+    for (int j = 0; j < 3; j++)
+    {
+        b.lo[j] = fminf(pos[0][j], fminf(pos[1][j], pos[2][j]));
+        b.hi[j] = fmaxf(pos[0][j], fmaxf(pos[1][j], pos[2][j]));
+    }
+    boxes[tri] = b;
+    // centroid bounds (of box centres), order-preserving uint encoding
+#pragma unroll
+    for (int j = 0; j < 3; j++)
+    {
+        const float c = 0.5f * (b.lo[j] + b.hi[j]);
+        atomicMin(sceneBounds + j, floatFlip(c));
+        atomicMax(sceneBounds + 3 + j, floatFlip(c));
+    }
+}
+
+__device__ __forceinline__ uint64_t expandBits21(uint64_t v)
+{
+    v &= 0x1fffffull;
+    v = (v | v << 32) & 0x1f00000000ffffull;
+    v = (v | v << 16) & 0x1f0000ff0000ffull;
+    v = (v | v << 8) & 0x100f00f00f00f00full;
+    v = (v | v << 4) & 0x10c30c30c30c30c3ull;
+    v = (v | v << 2) & 0x1249249249249249ull;
+    return v;
+}
+
+__global__ void k_morton(const Aabb *__restrict__ boxes, uint32_t n, const uint32_t *__restrict__ sceneBounds,
+                         uint64_t *__restrict__ keys, uint32_t *__restrict__ values)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n)
+        return;
+    uint64_t code = 0;
+#pragma unroll
+    for (int j = 0; j < 3; j++)
+    {
+        const float lo = floatUnflip(sceneBounds[j]), hi = floatUnflip(sceneBounds[3 + j]);
+        const float c = 0.5f * (boxes[i].lo[j] + boxes[i].hi[j]);
+        const float ext = hi - lo;
+        float f = ext > 0.0f ? (c - lo) / ext : 0.0f;
+        f = fminf(fmaxf(f * 2097152.0f, 0.0f), 2097151.0f);
+        code |= expandBits21((uint64_t)f) << (2 - j);
+    }
+    keys[i] = code;
+    values[i] = i;
+}
+
+// ---------------------------------------------------------------------------------------------
+// LBVH (Karras 2012).  Nodes 0..n-2 internal, n-1..2n-2 leaves (leaf k <-> sorted primitive k).
+// ---------------------------------------------------------------------------------------------
+struct Bvh2
+{
+    int *left, *right, *parent;
+    uint32_t *first, *last; // covered range of sorted primitives
+    Aabb *box;
+    uint32_t *visit;
+};
+
+__device__ __forceinline__ int delta(const uint64_t *keys, int n, int i, int j)
+{
+    if (j < 0 || j >= n)
+        return -1;
+    const uint64_t a = keys[i], b = keys[j];
+    if (a == b)
+        return 64 + __clz(i ^ j);
+    return __clzll(a ^ b);
+}
+
+__global__ void k_hierarchy(const uint64_t *__restrict__ keys, int n, Bvh2 t)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n - 1)
+        return;
+    const int d = (delta(keys, n, i, i + 1) - delta(keys, n, i, i - 1)) >= 0 ? 1 : -1;
+    const int deltaMin = delta(keys, n, i, i - d);
+    int lmax = 2;
+    while (delta(keys, n, i, i + lmax * d) > deltaMin)
+        lmax *= 2;
+    int l = 0;
+    for (int s = lmax / 2; s >= 1; s /= 2)
+        if (delta(keys, n, i, i + (l + s) * d) > deltaMin)
+            l += s;
+    const int j = i + l * d;
+    const int deltaNode = delta(keys, n, i, j);
+    int s = 0;
+    int tt = l;
+    do
+    {
+        tt = (tt + 1) >> 1;
+        if (delta(keys, n, i, i + (s + tt) * d) > deltaNode)
+            s += tt;
+    } while (tt > 1);
+    const int gamma = i + s * d + min(d, 0);
+    const int lo = min(i, j), hi = max(i, j);
+    const int leftIdx = (lo == gamma) ? (n - 1 + gamma) : gamma;
+    const int rightIdx = (hi == gamma + 1) ? (n - 1 + gamma + 1) : (gamma + 1);
+    t.left[i] = leftIdx;
+    t.right[i] = rightIdx;
+    t.parent[leftIdx] = i;
+    t.parent[rightIdx] = i;
+    t.first[i] = lo;
+    t.last[i] = hi;
+    if (i == 0)
+        t.parent[0] = -1;
+}
+
+__global__ void k_refit(const Aabb *__restrict__ primBoxes, const uint32_t *__restrict__ sortedIdx, int n, Bvh2 t)
+{
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n)
+        return;
+    const int leaf = n - 1 + k;
+    t.box[leaf] = primBoxes[sortedIdx[k]];
+    t.first[leaf] = k;
+    t.last[leaf] = k;
+    int node = t.parent[leaf];
+    while (node >= 0)
+    {
+        __threadfence();
+        if (atomicAdd(t.visit + node, 1u) == 0)
+            return; // the sibling will finish this node
+        const Aabb a = t.box[t.left[node]], b = t.box[t.right[node]];
+        Aabb m;
+#pragma unroll
+        for (int j = 0; j < 3; j++)
+        {
+            m.lo[j] = fminf(a.lo[j], b.lo[j]);
+            m.hi[j] = fmaxf(a.hi[j], b.hi[j]);
+        }
+        t.box[node] = m;
+        node = t.parent[node];
+    }
+}
+
+__device__ __forceinline__ float halfArea(const Aabb &b)
+{
+    const float dx = b.hi[0] - b.lo[0], dy = b.hi[1] - b.lo[1], dz = b.hi[2] - b.lo[2];
+    return dx * dy + dy * dz + dz * dx;
+}
+
+// One work item = (BVH2 internal node, wide node index).  Children are opened largest-area first
+// until the node is 4 wide; sub-trees of <= PT_MAX_LEAF_TRIS primitives become leaves.
+__global__ void k_collapse(Bvh2 t, int n, const uint2 *__restrict__ work, uint32_t workCount, uint2 *__restrict__ next,
+                           uint32_t *__restrict__ nextCount, BvhNode *__restrict__ nodes, uint32_t *__restrict__ nodeCount)
+{
+    const uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= workCount)
+        return;
+    const int src = (int)work[w].x;
+    const uint32_t dst = work[w].y;
+    int c[4];
+    int cc = 2;
+    c[0] = t.left[src];
+    c[1] = t.right[src];
+    auto isLeaf = [&](int node) { return t.last[node] - t.first[node] + 1 <= PT_MAX_LEAF_TRIS; };
+    while (cc < 4)
+    {
+        int bestSlot = -1;
+        float bestArea = -1.0f;
+        for (int i = 0; i < cc; i++)
+            if (!isLeaf(c[i]))
+            {
+                const float a = halfArea(t.box[c[i]]);
+                if (a > bestArea)
+                {
+                    bestArea = a;
+                    bestSlot = i;
+                }
+            }
+        if (bestSlot < 0)
+            break;
+        const int open = c[bestSlot];
+        c[bestSlot] = t.left[open];
+        c[cc++] = t.right[open];
+    }
+    float lo[3][4], hi[3][4];
+    int ref[4];
+    for (int i = 0; i < 4; i++)
+    {
+        if (i >= cc)
+        {
+            for (int j = 0; j < 3; j++)
+            {
+                lo[j][i] = INFINITY;
+                hi[j][i] = -INFINITY;
+            }
+            ref[i] = PT_CHILD_EMPTY;
+            continue;
+        }
+        const Aabb b = t.box[c[i]];
+        for (int j = 0; j < 3; j++)
+        {
+            lo[j][i] = b.lo[j];
+            hi[j][i] = b.hi[j];
+        }
+        if (isLeaf(c[i]))
+            ref[i] = encodeLeaf(t.first[c[i]], t.last[c[i]] - t.first[c[i]] + 1);
+        else
+        {
+            const uint32_t idx = atomicAdd(nodeCount, 1u);
+            ref[i] = (int)idx;
+            next[atomicAdd(nextCount, 1u)] = make_uint2((uint32_t)c[i], idx);
+        }
+    }
+    BvhNode out;
+    out.lox = make_float4(lo[0][0], lo[0][1], lo[0][2], lo[0][3]);
+    out.loy = make_float4(lo[1][0], lo[1][1], lo[1][2], lo[1][3]);
+    out.loz = make_float4(lo[2][0], lo[2][1], lo[2][2], lo[2][3]);
+    out.hix = make_float4(hi[0][0], hi[0][1], hi[0][2], hi[0][3]);
+    out.hiy = make_float4(hi[1][0], hi[1][1], hi[1][2], hi[1][3]);
+    out.hiz = make_float4(hi[2][0], hi[2][1], hi[2][2], hi[2][3]);
+    out.child = make_int4(ref[0], ref[1], ref[2], ref[3]);
+    out.pad = make_int4(cc, 0, 0, 0);
+    nodes[dst] = out;
+}
+
+// root of a scene whose whole BVH2 is one leaf (1..PT_MAX_LEAF_TRIS primitives)
+__global__ void k_single_leaf_root(const Aabb *__restrict__ primBoxes, const uint32_t *__restrict__ sortedIdx, uint32_t n,
+                                   BvhNode *__restrict__ nodes)
+{
+    Aabb m;
+    for (int j = 0; j < 3; j++)
+    {
+        m.lo[j] = INFINITY;
+        m.hi[j] = -INFINITY;
+    }
+    for (uint32_t k = 0; k < n; k++)
+        for (int j = 0; j < 3; j++)
+        {
+            m.lo[j] = fminf(m.lo[j], primBoxes[sortedIdx[k]].lo[j]);
+            m.hi[j] = fmaxf(m.hi[j], primBoxes[sortedIdx[k]].hi[j]);
+        }
+    BvhNode out;
+    out.lox = make_float4(m.lo[0], INFINITY, INFINITY, INFINITY);
+    out.loy = make_float4(m.lo[1], INFINITY, INFINITY, INFINITY);
+    out.loz = make_float4(m.lo[2], INFINITY, INFINITY, INFINITY);
+    out.hix = make_float4(m.hi[0], -INFINITY, -INFINITY, -INFINITY);
+    out.hiy = make_float4(m.hi[1], -INFINITY, -INFINITY, -INFINITY);
+    out.hiz = make_float4(m.hi[2], -INFINITY, -INFINITY, -INFINITY);
+    out.child = make_int4(encodeLeaf(0, n), PT_CHILD_EMPTY, PT_CHILD_EMPTY, PT_CHILD_EMPTY);
+    out.pad = make_int4(1, 0, 0, 0);
+    nodes[0] = out;
+}
+
+__global__ void k_gather(const uint32_t *__restrict__ sortedIdx, uint32_t n, const float4 *__restrict__ posIn,
+                         const TriShade *__restrict__ shadeIn, float4 *__restrict__ posOut, TriShade *__restrict__ shadeOut)
+{
+    const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n)
+        return;
+    const uint32_t src = sortedIdx[k];
+    posOut[3 * (size_t)k + 0] = posIn[3 * (size_t)src + 0];
+    posOut[3 * (size_t)k + 1] = posIn[3 * (size_t)src + 1];
+    posOut[3 * (size_t)k + 2] = posIn[3 * (size_t)src + 2];
+    shadeOut[k] = shadeIn[src];
+}
+
+// ---------------------------------------------------------------------------------------------
+// textures
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float4 mipTexel(const DevTexture &t, const float *lut, uint32_t level, int x, int y, uint32_t lw)
+{
+    const size_t idx = (size_t)t.levelOffset[level] + (size_t)y * lw + x;
+    if (t.flags & PT_TEX_FLAG_FLOAT)
+        return reinterpret_cast<const float4 *>(t.base)[idx];
+    const uchar4 c = reinterpret_cast<const uchar4 *>(t.base)[idx];
+    const float *l = lut + ((t.flags & PT_TEX_FLAG_SRGB) ? 256 : 0);
+    return make_float4(l[c.x], l[c.y], l[c.z], lut[c.w]);
+}
+__device__ __forceinline__ float lerpExact(float a, float b, float f)
+{
+    // a * (1 - f) + b * f without contraction, to match the oracle bit for bit
+    return __fadd_rn(__fmul_rn(a, __fsub_rn(1.0f, f)), __fmul_rn(b, f));
+}
+__device__ __forceinline__ uint8_t encodeUnorm8(float v)
+{
+    if (!(v > 0.0f))
+        return 0;
+    if (v >= 1.0f)
+        return 255;
+    return (uint8_t)__fadd_rn(__fmul_rn(v, 255.0f), 0.5f);
+}
+__device__ __forceinline__ uint8_t encodeSrgb8(const float *lut, float v)
+{
+    // nearest sRGB code in linear space: smallest i with v < (srgb[i] + srgb[i+1]) / 2
+    int lo = 0, hi = 255;
+    while (lo < hi)
+    {
+        const int mid = (lo + hi) >> 1;
+        const float m = __fmul_rn(0.5f, __fadd_rn(lut[256 + mid], lut[256 + mid + 1]));
+        if (v < m)
+            hi = mid;
+        else
+            lo = mid + 1;
+    }
+    return (uint8_t)lo;
+}
+
+// level k from level k-1: linear vkCmdBlitImage (PT/Renderer/Image.cpp:264-305)
+__global__ void k_mip(DevTexture t, const float *__restrict__ lut, uint32_t level)
+{
+    const uint32_t sw = max(1u, t.width >> (level - 1)), sh = max(1u, t.height >> (level - 1));
+    const uint32_t dw = max(1u, t.width >> level), dh = max(1u, t.height >> level);
+    const uint32_t x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= dw || y >= dh)
+        return;
+    const float sxScale = __fdiv_rn((float)sw, (float)dw), syScale = __fdiv_rn((float)sh, (float)dh);
+    const float sx = __fsub_rn(__fmul_rn(__fadd_rn((float)x, 0.5f), sxScale), 0.5f);
+    const float sy = __fsub_rn(__fmul_rn(__fadd_rn((float)y, 0.5f), syScale), 0.5f);
+    const float fx0 = floorf(sx), fy0 = floorf(sy);
+    const float fx = __fsub_rn(sx, fx0), fy = __fsub_rn(sy, fy0);
+    const int x0 = min(max((int)fx0, 0), (int)sw - 1), x1 = min(max((int)fx0 + 1, 0), (int)sw - 1);
+    const int y0 = min(max((int)fy0, 0), (int)sh - 1), y1 = min(max((int)fy0 + 1, 0), (int)sh - 1);
+    const float4 t00 = mipTexel(t, lut, level - 1, x0, y0, sw), t10 = mipTexel(t, lut, level - 1, x1, y0, sw);
+    const float4 t01 = mipTexel(t, lut, level - 1, x0, y1, sw), t11 = mipTexel(t, lut, level - 1, x1, y1, sw);
+    float4 v;
+    v.x = lerpExact(lerpExact(t00.x, t10.x, fx), lerpExact(t01.x, t11.x, fx), fy);
+    v.y = lerpExact(lerpExact(t00.y, t10.y, fx), lerpExact(t01.y, t11.y, fx), fy);
+    v.z = lerpExact(lerpExact(t00.z, t10.z, fx), lerpExact(t01.z, t11.z, fx), fy);
+    v.w = lerpExact(lerpExact(t00.w, t10.w, fx), lerpExact(t01.w, t11.w, fx), fy);
+    const size_t idx = (size_t)t.levelOffset[level] + (size_t)y * dw + x;
+    if (t.flags & PT_TEX_FLAG_FLOAT)
+    {
+        reinterpret_cast<float4 *>(t.base)[idx] = v;
+        return;
+    }
+    uchar4 o;
+    if (t.flags & PT_TEX_FLAG_SRGB)
+        o = make_uchar4(encodeSrgb8(lut, v.x), encodeSrgb8(lut, v.y), encodeSrgb8(lut, v.z), encodeUnorm8(v.w));
+    else
+        o = make_uchar4(encodeUnorm8(v.x), encodeUnorm8(v.y), encodeUnorm8(v.z), encodeUnorm8(v.w));
+    reinterpret_cast<uchar4 *>(t.base)[idx] = o;
+}
+
+pt_status createTexture(Context *ctx, const pt_texture_desc &d, DevTexture &out, void **outAlloc)
+{
+    if (d.width == 0 || d.height == 0 || !d.pixels)
+        return fail(ctx, PT_ERR_INVALID_ARGUMENT, "texture", "empty texture");
+    if (d.format != PT_TEXTURE_RGBA8 && d.format != PT_TEXTURE_RGBAF32)
+        return fail(ctx, PT_ERR_UNSUPPORTED, "texture", "only RGBA8 and RGBAF32 textures are supported");
+    DevTexture t = {};
+    t.width = d.width;
+    t.height = d.height;
+    t.flags = d.format == PT_TEXTURE_RGBAF32 ? PT_TEX_FLAG_FLOAT : (d.srgb ? PT_TEX_FLAG_SRGB : 0u);
+    // floor(log2(max(w, h))) + 1 levels (PT/Renderer/Image.cpp:14-17)
+    uint32_t levels = 1;
+    for (uint32_t m = std::max(d.width, d.height); m > 1; m >>= 1)
+        levels++;
+    if (levels > PT_MAX_TEX_LEVELS)
+        return fail(ctx, PT_ERR_UNSUPPORTED, "texture", "texture larger than 32768 texels per side");
+    t.levels = levels;
+    uint64_t texels = 0;
+    for (uint32_t l = 0; l < levels; l++)
+    {
+        t.levelOffset[l] = (uint32_t)texels;
+        texels += (uint64_t)std::max(1u, d.width >> l) * std::max(1u, d.height >> l);
+    }
+    const uint64_t bpp = (t.flags & PT_TEX_FLAG_FLOAT) ? 16 : 4;
+    void *mem = nullptr;
+    PT_CUDA_CHECK(ctx, cudaMalloc(&mem, texels * bpp));
+    t.base = (uint64_t)mem;
+    PT_CUDA_CHECK(ctx, cudaMemcpyAsync(mem, d.pixels, (uint64_t)d.width * d.height * bpp, cudaMemcpyHostToDevice, ctx->stream));
+    for (uint32_t l = 1; l < levels; l++)
+    {
+        const uint32_t dw = std::max(1u, d.width >> l), dh = std::max(1u, d.height >> l);
+        const dim3 block(16, 16), grid((dw + 15) / 16, (dh + 15) / 16);
+        k_mip<<<grid, block, 0, ctx->stream>>>(t, ctx->dLut, l);
+    }
+    PT_CUDA_CHECK(ctx, cudaGetLastError());
+    // the host pixels may be released as soon as we return
+    PT_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+    out = t;
+    *outAlloc = mem;
+    return PT_OK;
+}
+
+pt_texture_desc defaultTexture(const uint32_t *rgba, bool srgb)
+{
+    pt_texture_desc d = {};
+    d.width = d.height = 1;
+    d.format = PT_TEXTURE_RGBA8;
+    d.srgb = srgb;
+    d.pixels = rgba;
+    return d;
+}
+
+template <typename T> pt_status devAlloc(Context *ctx, T **ptr, size_t count, std::vector<void *> &owner)
+{
+    *ptr = nullptr;
+    if (count == 0)
+        count = 1;
+    PT_CUDA_CHECK(ctx, cudaMalloc((void **)ptr, count * sizeof(T)));
+    owner.push_back(*ptr);
+    return PT_OK;
+}
+
+void invert3x3(const double m[9], double out[9])
+{
+    const double det = m[0] * (m[4] * m[8] - m[5] * m[7]) - m[1] * (m[3] * m[8] - m[5] * m[6]) + m[2] * (m[3] * m[7] - m[4] * m[6]);
+    const double inv = 1.0 / det;
+    out[0] = (m[4] * m[8] - m[5] * m[7]) * inv;
+    out[1] = (m[2] * m[7] - m[1] * m[8]) * inv;
+    out[2] = (m[1] * m[5] - m[2] * m[4]) * inv;
+    out[3] = (m[5] * m[6] - m[3] * m[8]) * inv;
+    out[4] = (m[0] * m[8] - m[2] * m[6]) * inv;
+    out[5] = (m[2] * m[3] - m[0] * m[5]) * inv;
+    out[6] = (m[3] * m[7] - m[4] * m[6]) * inv;
+    out[7] = (m[1] * m[6] - m[0] * m[7]) * inv;
+    out[8] = (m[0] * m[4] - m[1] * m[3]) * inv;
+}
+
+} // namespace
+
+void freeScene(Context *ctx)
+{
+    for (void *p : ctx->sceneAllocs)
+        cudaFree(p);
+    ctx->sceneAllocs.clear();
+    ctx->hostTextures.clear();
+    ctx->hasScene = false;
+    ctx->scene = DeviceScene {};
+}
+
+pt_status uploadTextureSlot(Context *ctx, uint32_t slot, const pt_texture_desc *tex)
+{
+    if (!ctx->hasScene)
+        return fail(ctx, PT_ERR_NO_SCENE, "pt_texture_upload", "no scene uploaded");
+    if (!tex || slot >= ctx->hostTextures.size())
+        return fail(ctx, PT_ERR_INVALID_ARGUMENT, "pt_texture_upload", "slot out of range");
+    DevTexture t;
+    void *mem = nullptr;
+    const pt_status st = createTexture(ctx, *tex, t, &mem);
+    if (st != PT_OK)
+        return st;
+    // the old allocation stays owned by the scene until the next scene upload
+    ctx->sceneAllocs.push_back(mem);
+    ctx->hostTextures[slot] = t;
+    PT_CUDA_CHECK(ctx, cudaMemcpyAsync(const_cast<DevTexture *>(ctx->scene.textures) + slot, &t, sizeof(t),
+                                       cudaMemcpyHostToDevice, ctx->stream));
+    PT_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+    return PT_OK;
+}
+
+pt_status uploadScene(Context *ctx, const pt_scene_desc *d)
+{
+    if (!d)
+        return fail(ctx, PT_ERR_INVALID_ARGUMENT, "pt_scene_upload", "scene is NULL");
+    if (d->point_light_count > PT_MAX_LIGHT_COUNT)
+        return fail(ctx, PT_ERR_INVALID_ARGUMENT, "pt_scene_upload", "more than 64 point lights");
+    if (d->transform_count == 0 || !d->transforms)
+        return fail(ctx, PT_ERR_INVALID_ARGUMENT, "pt_scene_upload", "transforms[0] (identity) is required");
+    if ((d->vertex_count && !d->vertices) || (d->index_count && !d->indices) || (d->geometry_count && !d->geometries) ||
+        (d->mesh_record_count && !d->mesh_records) || (d->model_count && !d->models) ||
+        (d->instance_count && !d->instances) || (d->texture_count && !d->textures))
+        return fail(ctx, PT_ERR_INVALID_ARGUMENT, "pt_scene_upload", "array pointer is NULL with a non-zero count");
+
+    freeScene(ctx);
+    std::vector<void *> &own = ctx->sceneAllocs;
+    std::vector<void *> temp;
+    auto freeTemp = [&]() {
+        for (void *p : temp)
+            cudaFree(p);
+        temp.clear();
+    };
+    cudaEvent_t ev0, ev1, ev2;
+    cudaEventCreate(&ev0);
+    cudaEventCreate(&ev1);
+    cudaEventCreate(&ev2);
+    cudaEventRecord(ev0, ctx->stream);
+
+#define PT_TRY(expr)                                                                                                  \
+    do                                                                                                                \
+    {                                                                                                                 \
+        const pt_status st__ = (expr);                                                                                \
+        if (st__ != PT_OK)                                                                                            \
+        {                                                                                                             \
+            freeTemp();                                                                                               \
+            freeScene(ctx);                                                                                           \
+            return st__;                                                                                              \
+        }                                                                                                             \
+    } while (0)
+
+    // ---- flatten instances x meshes (host, tiny) ------------------------------------------
+    std::vector<MeshInstance> mis;
+    uint64_t triTotal = 0;
+    bool hasAlpha = false;
+    for (uint32_t ii = 0; ii < d->instance_count; ii++)
+    {
+        const pt_instance &inst = d->instances[ii];
+        if (inst.model_index >= d->model_count)
+        {
+            freeTemp();
+            return fail(ctx, PT_ERR_INVALID_ARGUMENT, "pt_scene_upload", "instance.model_index out of range");
+        }
+        const pt_model &model = d->models[inst.model_index];
+        for (uint32_t mi = 0; mi < model.mesh_count; mi++)
+        {
+            if (model.mesh_offset + mi >= d->mesh_record_count)
+                return fail(ctx, PT_ERR_INVALID_ARGUMENT, "pt_scene_upload", "model mesh range out of range");
+            const pt_mesh_record &rec = d->mesh_records[model.mesh_offset + mi];
+            if (rec.geometry_index >= d->geometry_count || rec.transform_index >= d->transform_count)
+                return fail(ctx, PT_ERR_INVALID_ARGUMENT, "pt_scene_upload", "mesh record index out of range");
+            const pt_geometry &g = d->geometries[rec.geometry_index];
+            if ((uint64_t)g.index_offset + g.index_length > d->index_count ||
+                (uint64_t)g.vertex_offset + g.vertex_length > d->vertex_count)
+                return fail(ctx, PT_ERR_INVALID_ARGUMENT, "pt_scene_upload", "geometry range out of range");
+            const uint32_t type = rec.material_id & 0xffu, index = rec.material_id >> 8;
+            const uint32_t limit = type == 0 ? d->mr_material_count : type == 1 ? d->sg_material_count
+                                                                  : type == 2   ? d->phong_material_count
+                                                                                : 0xffffffffu;
+            if (index >= limit)
+                return fail(ctx, PT_ERR_INVALID_ARGUMENT, "pt_scene_upload", "material index out of range");
+            MeshInstance m = {};
+            // P = Instance * Mesh with the evaluation order of
+            // `mat4(transforms[i]) * gl_ObjectToWorld3x4EXT` (PT/Shaders/sampling.glsl:7)
+            const float *A = d->transforms + 12 * (size_t)rec.transform_index; // mesh, rows
+            const float *B = inst.transform;                                   // instance, rows
+            for (int j = 0; j < 3; j++)
+                for (int c = 0; c < 4; c++)
+                {
+                    float v = A[0 * 4 + c] * B[j * 4 + 0] + A[1 * 4 + c] * B[j * 4 + 1];
+                    v = v + A[2 * 4 + c] * B[j * 4 + 2];
+                    if (c == 3)
+                        v = v + 1.0f * B[j * 4 + 3];
+                    m.P[j * 4 + c] = v;
+                }
+            double R[9], Ri[9];
+            for (int j = 0; j < 3; j++)
+                for (int c = 0; c < 3; c++)
+                    R[j * 3 + c] = m.P[j * 4 + c];
+            invert3x3(R, Ri);
+            for (int j = 0; j < 3; j++)
+                for (int c = 0; c < 3; c++)
+                    m.N[j * 3 + c] = (float)Ri[c * 3 + j]; // inverse transpose
+            m.triOffset = (uint32_t)triTotal;
+            m.triCount = g.index_length / 3;
+            m.vertexOffset = g.vertex_offset;
+            m.indexOffset = g.index_offset;
+            m.instance = ii;
+            m.geometry = mi;
+            m.materialId = rec.material_id;
+            m.flags = g.is_opaque ? PT_TRI_FLAG_OPAQUE : 0u;
+            hasAlpha |= !g.is_opaque;
+            if (m.triCount == 0)
+                continue;
+            triTotal += m.triCount;
+            mis.push_back(m);
+        }
+    }
+    if (triTotal >= (1ull << 29))
+        return fail(ctx, PT_ERR_UNSUPPORTED, "pt_scene_upload", "more than 2^29 instanced triangles");
+    const uint32_t n = (uint32_t)triTotal;
+
+    // ---- materials, lights, LUT, textures -------------------------------------------------
+    DeviceScene &s = ctx->scene;
+    {
+        MaterialRaw *dm[3];
+        const void *src[3] = { d->mr_materials, d->sg_materials, d->phong_materials };
+        const uint32_t cnt[3] = { d->mr_material_count, d->sg_material_count, d->phong_material_count };
+        for (int k = 0; k < 3; k++)
+        {
+            PT_TRY(devAlloc(ctx, &dm[k], cnt[k], own));
+            if (cnt[k])
+                PT_CUDA_CHECK(ctx, cudaMemcpyAsync(dm[k], src[k], (size_t)cnt[k] * 96, cudaMemcpyHostToDevice, ctx->stream));
+            s.materials[k] = dm[k];
+        }
+        LightBlock lb = {};
+        lb.count = d->point_light_count;
+        lb.dirColor = make_float4(d->directional_light.color[0], d->directional_light.color[1], d->directional_light.color[2], 0);
+        lb.dirDirection = make_float4(d->directional_light.direction[0], d->directional_light.direction[1],
+                                      d->directional_light.direction[2], 0);
+        if (d->point_light_count)
+            std::memcpy(lb.point, d->point_lights, (size_t)d->point_light_count * 48);
+        LightBlock *dl;
+        PT_TRY(devAlloc(ctx, &dl, 1, own));
+        PT_CUDA_CHECK(ctx, cudaMemcpyAsync(dl, &lb, sizeof(lb), cudaMemcpyHostToDevice, ctx->stream));
+        PT_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream)); // lb is a stack object
+        s.lights = dl;
+        s.lut = ctx->dLut;
+    }
+    {
+        // built-in 1x1 textures, slots 0-8 (PT/Renderer/Renderer.cpp:127-173; texel values
+        // PT/Shaders/ShaderRendererTypes.incl:49-56; colour space per texture type).  Slot 8 is the
+        // reference's "placeholder" shown while uploads are pending; uploads here are synchronous.
+        static const uint32_t kDefaults[9] = { 0xffffffffu, 0xffff8080u, 0xffffffffu, 0xffffffffu, 0x00000000u,
+                                               0xffffffffu, 0x00000000u, 0x00000000u, 0xffffffffu };
+        static const bool kSrgb[9] = { true, false, false, false, true, true, false, false, true };
+        ctx->hostTextures.resize(PT_SCENE_TEXTURE_OFFSET + d->texture_count);
+        for (uint32_t i = 0; i < ctx->hostTextures.size(); i++)
+        {
+            const pt_texture_desc desc =
+                i < PT_SCENE_TEXTURE_OFFSET ? defaultTexture(&kDefaults[i], kSrgb[i]) : d->textures[i - PT_SCENE_TEXTURE_OFFSET];
+            void *mem = nullptr;
+            PT_TRY(createTexture(ctx, desc, ctx->hostTextures[i], &mem));
+            own.push_back(mem);
+        }
+        DevTexture *dt;
+        PT_TRY(devAlloc(ctx, &dt, ctx->hostTextures.size(), own));
+        PT_CUDA_CHECK(ctx, cudaMemcpyAsync(dt, ctx->hostTextures.data(), ctx->hostTextures.size() * sizeof(DevTexture),
+                                           cudaMemcpyHostToDevice, ctx->stream));
+        s.textures = dt;
+        s.textureCount = (uint32_t)ctx->hostTextures.size();
+        s.hasSky2D = 0;
+        if (d->skybox_2d)
+        {
+            void *mem = nullptr;
+            PT_TRY(createTexture(ctx, *d->skybox_2d, s.sky2D, &mem));
+            own.push_back(mem);
+            s.hasSky2D = 1;
+        }
+    }
+    // material texture indices must address existing slots
+    {
+        auto checkIdx = [&](uint32_t idx) { return idx < ctx->hostTextures.size(); };
+        bool ok = true;
+        for (uint32_t i = 0; i < d->mr_material_count; i++)
+        {
+            const pt_material_mr &m = d->mr_materials[i];
+            ok &= checkIdx(m.emissive_idx) && checkIdx(m.color_idx) && checkIdx(m.normal_idx) && checkIdx(m.roughness_idx) &&
+                  checkIdx(m.metallic_idx);
+        }
+        for (int k = 0; k < 2; k++)
+        {
+            const pt_material_sg *arr = k == 0 ? d->sg_materials : d->phong_materials;
+            const uint32_t cnt = k == 0 ? d->sg_material_count : d->phong_material_count;
+            for (uint32_t i = 0; i < cnt; i++)
+                ok &= checkIdx(arr[i].emissive_idx) && checkIdx(arr[i].color_idx) && checkIdx(arr[i].normal_idx) &&
+                      checkIdx(arr[i].specular_idx) && checkIdx(arr[i].glossiness_idx);
+        }
+        if (!ok)
+        {
+            freeTemp();
+            freeScene(ctx);
+            return fail(ctx, PT_ERR_INVALID_ARGUMENT, "pt_scene_upload", "material texture index out of range");
+        }
+    }
+
+    s.triCount = n;
+    s.hasAlpha = hasAlpha ? 1u : 0u;
+    ctx->nodeCount = 0;
+    ctx->bvhBytes = 0;
+    cudaEventRecord(ev1, ctx->stream);
+
+    if (n > 0)
+    {
+        // ---- bake -------------------------------------------------------------------------
+        float *dVertices;
+        uint32_t *dIndices;
+        MeshInstance *dMis;
+        float4 *posUnsorted;
+        TriShade *shadeUnsorted;
+        Aabb *primBoxes;
+        uint32_t *sceneBounds;
+        PT_TRY(devAlloc(ctx, &dVertices, (size_t)d->vertex_count * 14, temp));
+        PT_TRY(devAlloc(ctx, &dIndices, (size_t)d->index_count, temp));
+        PT_TRY(devAlloc(ctx, &dMis, mis.size(), temp));
+        PT_TRY(devAlloc(ctx, &posUnsorted, (size_t)n * 3, temp));
+        PT_TRY(devAlloc(ctx, &shadeUnsorted, (size_t)n, temp));
+        PT_TRY(devAlloc(ctx, &primBoxes, (size_t)n, temp));
+        PT_TRY(devAlloc(ctx, &sceneBounds, 6, temp));
+        PT_CUDA_CHECK(ctx, cudaMemcpyAsync(dVertices, d->vertices, (size_t)d->vertex_count * 56, cudaMemcpyHostToDevice, ctx->stream));
+        PT_CUDA_CHECK(ctx, cudaMemcpyAsync(dIndices, d->indices, (size_t)d->index_count * 4, cudaMemcpyHostToDevice, ctx->stream));
+        PT_CUDA_CHECK(ctx, cudaMemcpyAsync(dMis, mis.data(), mis.size() * sizeof(MeshInstance), cudaMemcpyHostToDevice, ctx->stream));
+        const uint32_t boundsInit[6] = { 0xffffffffu, 0xffffffffu, 0xffffffffu, 0u, 0u, 0u };
+        PT_CUDA_CHECK(ctx, cudaMemcpyAsync(sceneBounds, boundsInit, sizeof(boundsInit), cudaMemcpyHostToDevice, ctx->stream));
+        PT_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+        const uint32_t T = 256, G = (n + T - 1) / T;
+        k_bake<<<G, T, 0, ctx->stream>>>(dMis, (uint32_t)mis.size(), dVertices, dIndices, n, posUnsorted, shadeUnsorted,
+                                         primBoxes, sceneBounds);
+
+        // ---- Morton codes + sort ------------------------------------------------------------
+        uint64_t *keysIn, *keysOut;
+        uint32_t *valsIn, *valsOut;
+        PT_TRY(devAlloc(ctx, &keysIn, (size_t)n, temp));
+        PT_TRY(devAlloc(ctx, &keysOut, (size_t)n, temp));
+        PT_TRY(devAlloc(ctx, &valsIn, (size_t)n, temp));
+        PT_TRY(devAlloc(ctx, &valsOut, (size_t)n, temp));
+        k_morton<<<G, T, 0, ctx->stream>>>(primBoxes, n, sceneBounds, keysIn, valsIn);
+        size_t sortBytes = 0;
+        cub::DeviceRadixSort::SortPairs(nullptr, sortBytes, keysIn, keysOut, valsIn, valsOut, (int)n, 0, 63, ctx->stream);
+        uint8_t *sortTemp;
+        PT_TRY(devAlloc(ctx, &sortTemp, sortBytes, temp));
+        PT_CUDA_CHECK(ctx, cub::DeviceRadixSort::SortPairs(sortTemp, sortBytes, keysIn, keysOut, valsIn, valsOut, (int)n, 0,
+                                                           63, ctx->stream));
+
+        // ---- final triangle streams ---------------------------------------------------------
+        float4 *triPos;
+        TriShade *triShade;
+        PT_TRY(devAlloc(ctx, &triPos, (size_t)n * 3, own));
+        PT_TRY(devAlloc(ctx, &triShade, (size_t)n, own));
+        k_gather<<<G, T, 0, ctx->stream>>>(valsOut, n, posUnsorted, shadeUnsorted, triPos, triShade);
+        s.triPos = triPos;
+        s.triShade = triShade;
+
+        // ---- hierarchy ------------------------------------------------------------------------
+        BvhNode *wide;
+        const uint32_t wideCapacity = std::max(1u, n); // <= n - 1 internal nodes (+ 1 for tiny scenes)
+        PT_TRY(devAlloc(ctx, &wide, (size_t)wideCapacity, temp));
+        uint32_t wideCount = 1;
+        if (n <= PT_MAX_LEAF_TRIS)
+            k_single_leaf_root<<<1, 1, 0, ctx->stream>>>(primBoxes, valsOut, n, wide);
+        else
+        {
+            Bvh2 t;
+            const size_t nodes2 = 2 * (size_t)n - 1;
+            PT_TRY(devAlloc(ctx, &t.left, (size_t)n, temp));
+            PT_TRY(devAlloc(ctx, &t.right, (size_t)n, temp));
+            PT_TRY(devAlloc(ctx, &t.parent, nodes2, temp));
+            PT_TRY(devAlloc(ctx, &t.first, nodes2, temp));
+            PT_TRY(devAlloc(ctx, &t.last, nodes2, temp));
+            PT_TRY(devAlloc(ctx, &t.box, nodes2, temp));
+            PT_TRY(devAlloc(ctx, &t.visit, (size_t)n, temp));
+            PT_CUDA_CHECK(ctx, cudaMemsetAsync(t.visit, 0, (size_t)n * 4, ctx->stream));
+            k_hierarchy<<<G, T, 0, ctx->stream>>>(keysOut, (int)n, t);
+            k_refit<<<G, T, 0, ctx->stream>>>(primBoxes, valsOut, (int)n, t);
+
+            uint2 *work[2];
+            uint32_t *counters; // [0] node count, [1], [2] work counts
+            PT_TRY(devAlloc(ctx, &work[0], (size_t)n, temp));
+            PT_TRY(devAlloc(ctx, &work[1], (size_t)n, temp));
+            PT_TRY(devAlloc(ctx, &counters, 3, temp));
+            const uint2 rootItem = make_uint2(0u, 0u);
+            const uint32_t initCounters[3] = { 1u, 0u, 0u };
+            PT_CUDA_CHECK(ctx, cudaMemcpyAsync(work[0], &rootItem, sizeof(rootItem), cudaMemcpyHostToDevice, ctx->stream));
+            PT_CUDA_CHECK(ctx, cudaMemcpyAsync(counters, initCounters, sizeof(initCounters), cudaMemcpyHostToDevice, ctx->stream));
+            PT_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+            uint32_t workCount = 1;
+            int cur = 0;
+            while (workCount > 0)
+            {
+                PT_CUDA_CHECK(ctx, cudaMemsetAsync(counters + 1 + (cur ^ 1), 0, 4, ctx->stream));
+                k_collapse<<<(workCount + 127) / 128, 128, 0, ctx->stream>>>(t, (int)n, work[cur], workCount, work[cur ^ 1],
+                                                                             counters + 1 + (cur ^ 1), wide, counters);
+                PT_CUDA_CHECK(ctx, cudaMemcpyAsync(&workCount, counters + 1 + (cur ^ 1), 4, cudaMemcpyDeviceToHost, ctx->stream));
+                PT_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+                cur ^= 1;
+            }
+            PT_CUDA_CHECK(ctx, cudaMemcpyAsync(&wideCount, counters, 4, cudaMemcpyDeviceToHost, ctx->stream));
+            PT_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+        }
+        BvhNode *nodes;
+        PT_TRY(devAlloc(ctx, &nodes, (size_t)wideCount, own));
+        PT_CUDA_CHECK(ctx, cudaMemcpyAsync(nodes, wide, (size_t)wideCount * sizeof(BvhNode), cudaMemcpyDeviceToDevice, ctx->stream));
+        s.nodes = nodes;
+        ctx->nodeCount = wideCount;
+        ctx->bvhBytes = (uint64_t)wideCount * sizeof(BvhNode) + (uint64_t)n * (48 + 144);
+    }
+    cudaEventRecord(ev2, ctx->stream);
+    PT_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+    PT_CUDA_CHECK(ctx, cudaGetLastError());
+    freeTemp();
+    cudaEventElapsedTime(&ctx->sceneUploadMs, ev0, ev2);
+    cudaEventElapsedTime(&ctx->bvhBuildMs, ev1, ev2);
+    cudaEventDestroy(ev0);
+    cudaEventDestroy(ev1);
+    cudaEventDestroy(ev2);
+    ctx->hasScene = true;
+    return PT_OK;
+#undef PT_TRY
+}
+
+} // namespace pt

@@ -1,0 +1,334 @@
+// pt_core.cu — the C ABI of include/pt_core.h: context, render target and dispatch.
+#include "core_internal.h"
+
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+
+namespace pt
+{
+
+static thread_local std::string g_createError;
+
+pt_status fail(Context *ctx, pt_status code, const char *what, const char *detail)
+{
+    std::string msg = std::string(what) + ": " + detail;
+    if (ctx)
+        ctx->lastError = msg;
+    else
+        g_createError = msg;
+    return code;
+}
+
+static void freeTarget(Context *ctx)
+{
+    for (void *p : ctx->targetAllocs)
+        cudaFree(p);
+    ctx->targetAllocs.clear();
+    ctx->accum = nullptr;
+    ctx->ps = PathState {};
+    ctx->slotCapacity = 0;
+    ctx->slotMapValid = false;
+    ctx->width = ctx->height = 0;
+}
+
+template <typename T> static pt_status targetAlloc(Context *ctx, T **ptr, size_t count)
+{
+    PT_CUDA_CHECK(ctx, cudaMalloc((void **)ptr, std::max<size_t>(count, 1) * sizeof(T)));
+    ctx->targetAllocs.push_back(*ptr);
+    return PT_OK;
+}
+
+} // namespace pt
+
+using namespace pt;
+
+extern "C" {
+
+pt_status pt_context_create(int32_t cuda_device, pt_context **out_ctx)
+{
+    if (!out_ctx)
+        return fail(nullptr, PT_ERR_INVALID_ARGUMENT, "pt_context_create", "out_ctx is NULL");
+    *out_ctx = nullptr;
+    int count = 0;
+    cudaError_t err = cudaGetDeviceCount(&count);
+    if (err != cudaSuccess || count == 0)
+        return fail(nullptr, PT_ERR_NO_DEVICE, "pt_context_create",
+                    err != cudaSuccess ? cudaGetErrorString(err) : "no CUDA device (there is no CPU fallback)");
+    if (cuda_device < 0 || cuda_device >= count)
+        return fail(nullptr, PT_ERR_INVALID_ARGUMENT, "pt_context_create", "cuda_device out of range");
+    cudaDeviceProp prop;
+    err = cudaGetDeviceProperties(&prop, cuda_device);
+    if (err != cudaSuccess)
+        return fail(nullptr, PT_ERR_CUDA, "cudaGetDeviceProperties", cudaGetErrorString(err));
+    if (prop.major != 10)
+    {
+        char buf[128];
+        std::snprintf(buf, sizeof(buf), "device %d is sm_%d%d; this library is built for sm_100a only", cuda_device,
+                      prop.major, prop.minor);
+        return fail(nullptr, PT_ERR_NO_DEVICE, "pt_context_create", buf);
+    }
+    err = cudaSetDevice(cuda_device);
+    if (err != cudaSuccess)
+        return fail(nullptr, PT_ERR_CUDA, "cudaSetDevice", cudaGetErrorString(err));
+
+    pt_context *ctx = new pt_context();
+    ctx->device = cuda_device;
+    ctx->smCount = prop.multiProcessorCount;
+#define PT_CREATE_CHECK(expr)                                                                                         \
+    do                                                                                                                \
+    {                                                                                                                 \
+        cudaError_t e__ = (expr);                                                                                     \
+        if (e__ != cudaSuccess)                                                                                       \
+        {                                                                                                             \
+            fail(nullptr, PT_ERR_CUDA, #expr, cudaGetErrorString(e__));                                               \
+            pt_context_destroy(ctx);                                                                                  \
+            return PT_ERR_CUDA;                                                                                       \
+        }                                                                                                             \
+    } while (0)
+    PT_CREATE_CHECK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    PT_CREATE_CHECK(cudaEventCreate(&ctx->evStart));
+    PT_CREATE_CHECK(cudaEventCreate(&ctx->evStop));
+    PT_CREATE_CHECK(cudaMalloc((void **)&ctx->dCounters, sizeof(DeviceCounters)));
+    PT_CREATE_CHECK(cudaMemset(ctx->dCounters, 0, sizeof(DeviceCounters)));
+    PT_CREATE_CHECK(cudaMalloc((void **)&ctx->dQueueCounts, sizeof(QueueCounts)));
+    PT_CREATE_CHECK(cudaMallocHost((void **)&ctx->hQueueCounts, sizeof(QueueCounts)));
+    // decode tables: [0..255] UNORM8 -> float, [256..511] sRGB8 -> linear float (same formulas as the oracle)
+    float lut[512];
+    for (int i = 0; i < 256; i++)
+    {
+        const double c = i / 255.0;
+        lut[i] = (float)i / 255.0f;
+        lut[256 + i] = (float)(c <= 0.04045 ? c / 12.92 : std::pow((c + 0.055) / 1.055, 2.4));
+    }
+    PT_CREATE_CHECK(cudaMalloc((void **)&ctx->dLut, sizeof(lut)));
+    PT_CREATE_CHECK(cudaMemcpy(ctx->dLut, lut, sizeof(lut), cudaMemcpyHostToDevice));
+#undef PT_CREATE_CHECK
+    *out_ctx = ctx;
+    return PT_OK;
+}
+
+void pt_context_destroy(pt_context *ctx)
+{
+    if (!ctx)
+        return;
+    cudaSetDevice(ctx->device);
+    if (ctx->stream)
+        cudaStreamSynchronize(ctx->stream);
+    freeScene(ctx);
+    freeTarget(ctx);
+    cudaFree(ctx->dCounters);
+    cudaFree(ctx->dQueueCounts);
+    cudaFree(ctx->dLut);
+    if (ctx->hQueueCounts)
+        cudaFreeHost(ctx->hQueueCounts);
+    if (ctx->evStart)
+        cudaEventDestroy(ctx->evStart);
+    if (ctx->evStop)
+        cudaEventDestroy(ctx->evStop);
+    if (ctx->stream)
+        cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+const char *pt_last_error(const pt_context *ctx) { return ctx ? ctx->lastError.c_str() : g_createError.c_str(); }
+
+pt_status pt_scene_upload(pt_context *ctx, const pt_scene_desc *scene)
+{
+    if (!ctx)
+        return PT_ERR_INVALID_ARGUMENT;
+    cudaSetDevice(ctx->device);
+    const bool hadAlpha = ctx->scene.hasAlpha != 0;
+    const pt_status st = uploadScene(ctx, scene);
+    // the decal streams of the path state exist only for scenes with alpha-tested geometry
+    if (st == PT_OK && ctx->accum && (ctx->scene.hasAlpha != 0) != hadAlpha)
+    {
+        const uint32_t w = ctx->width, h = ctx->height;
+        return pt_render_begin(ctx, w, h);
+    }
+    return st;
+}
+
+pt_status pt_texture_upload(pt_context *ctx, uint32_t slot, const pt_texture_desc *texture)
+{
+    if (!ctx)
+        return PT_ERR_INVALID_ARGUMENT;
+    cudaSetDevice(ctx->device);
+    return uploadTextureSlot(ctx, slot, texture);
+}
+
+pt_status pt_render_begin(pt_context *ctx, uint32_t width, uint32_t height)
+{
+    if (!ctx)
+        return PT_ERR_INVALID_ARGUMENT;
+    if (width == 0 || height == 0 || (uint64_t)width * height > 0x7fffffffull)
+        return fail(ctx, PT_ERR_INVALID_ARGUMENT, "pt_render_begin", "bad extent");
+    cudaSetDevice(ctx->device);
+    const size_t n = (size_t)width * height;
+    const bool needDecal = ctx->scene.hasAlpha != 0;
+    const bool reuse = ctx->accum && ctx->width == width && ctx->height == height && ((ctx->ps.decal != nullptr) == needDecal);
+    if (!reuse)
+    {
+        PT_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+        freeTarget(ctx);
+        PathState &ps = ctx->ps;
+#define PT_T(expr)                                                                                                    \
+    do                                                                                                                \
+    {                                                                                                                 \
+        const pt_status s__ = (expr);                                                                                 \
+        if (s__ != PT_OK)                                                                                             \
+        {                                                                                                             \
+            freeTarget(ctx);                                                                                          \
+            return s__;                                                                                               \
+        }                                                                                                             \
+    } while (0)
+        PT_T(targetAlloc(ctx, &ctx->accum, n));
+        PT_T(targetAlloc(ctx, &ps.rayO, n));
+        PT_T(targetAlloc(ctx, &ps.rayD, n));
+        PT_T(targetAlloc(ctx, &ps.thr, n));
+        PT_T(targetAlloc(ctx, &ps.rad, n));
+        PT_T(targetAlloc(ctx, &ps.diff0, n));
+        PT_T(targetAlloc(ctx, &ps.diff1, n));
+        PT_T(targetAlloc(ctx, &ps.diff2, n));
+        PT_T(targetAlloc(ctx, &ps.hit, n));
+        if (needDecal)
+        {
+            PT_T(targetAlloc(ctx, &ps.decal, n));
+            PT_T(targetAlloc(ctx, &ps.decalA, n));
+        }
+        PT_T(targetAlloc(ctx, &ps.shO, n));
+        PT_T(targetAlloc(ctx, &ps.shD, n));
+        PT_T(targetAlloc(ctx, &ps.shC, n));
+        PT_T(targetAlloc(ctx, &ps.sample, n));
+        PT_T(targetAlloc(ctx, &ps.slotPixel, n));
+        PT_T(targetAlloc(ctx, &ps.queue[0], n));
+        PT_T(targetAlloc(ctx, &ps.queue[1], n));
+        PT_T(targetAlloc(ctx, &ps.shadowQueue, n));
+#undef PT_T
+        ctx->width = width;
+        ctx->height = height;
+        ctx->slotCapacity = (uint32_t)n;
+    }
+    PT_CUDA_CHECK(ctx, cudaMemsetAsync(ctx->accum, 0, n * sizeof(float4), ctx->stream));
+    return PT_OK;
+}
+
+pt_status pt_render_samples(pt_context *ctx, const pt_render_params *params, uint32_t first_sample, uint32_t sample_count,
+                            const pt_tile *tiles, uint32_t tile_count)
+{
+    if (!ctx)
+        return PT_ERR_INVALID_ARGUMENT;
+    cudaSetDevice(ctx->device);
+    return renderSamples(ctx, params, first_sample, sample_count, tiles, tile_count);
+}
+
+pt_status pt_accum_device_ptr(pt_context *ctx, void **out_ptr, size_t *out_pitch, void **out_stream)
+{
+    if (!ctx)
+        return PT_ERR_INVALID_ARGUMENT;
+    if (!ctx->accum)
+        return fail(ctx, PT_ERR_NO_TARGET, "pt_accum_device_ptr", "pt_render_begin has not been called");
+    if (out_ptr)
+        *out_ptr = ctx->accum;
+    if (out_pitch)
+        *out_pitch = (size_t)ctx->width * sizeof(float4);
+    if (out_stream)
+        *out_stream = ctx->stream;
+    return PT_OK;
+}
+
+pt_status pt_readback(pt_context *ctx, float *out_rgba, size_t out_bytes)
+{
+    if (!ctx)
+        return PT_ERR_INVALID_ARGUMENT;
+    if (!ctx->accum)
+        return fail(ctx, PT_ERR_NO_TARGET, "pt_readback", "pt_render_begin has not been called");
+    const size_t need = (size_t)ctx->width * ctx->height * sizeof(float4);
+    if (!out_rgba || out_bytes < need)
+        return fail(ctx, PT_ERR_INVALID_ARGUMENT, "pt_readback", "output buffer too small");
+    cudaSetDevice(ctx->device);
+    PT_CUDA_CHECK(ctx, cudaMemcpyAsync(out_rgba, ctx->accum, need, cudaMemcpyDeviceToHost, ctx->stream));
+    PT_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+    return PT_OK;
+}
+
+pt_status pt_synchronize(pt_context *ctx)
+{
+    if (!ctx)
+        return PT_ERR_INVALID_ARGUMENT;
+    cudaSetDevice(ctx->device);
+    PT_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+    return PT_OK;
+}
+
+pt_status pt_first_hit_aov(pt_context *ctx, const pt_render_params *params, uint32_t width, uint32_t height,
+                           pt_hit *out_hits)
+{
+    if (!ctx)
+        return PT_ERR_INVALID_ARGUMENT;
+    cudaSetDevice(ctx->device);
+    return firstHitAov(ctx, params, width, height, out_hits);
+}
+
+pt_status pt_trace_closest(pt_context *ctx, const pt_ray *rays, uint64_t ray_count, pt_hit *out_hits)
+{
+    if (!ctx)
+        return PT_ERR_INVALID_ARGUMENT;
+    cudaSetDevice(ctx->device);
+    return traceClosest(ctx, rays, ray_count, out_hits);
+}
+
+pt_status pt_trace_occlusion(pt_context *ctx, const pt_ray *rays, uint64_t ray_count, uint8_t *out_occluded)
+{
+    if (!ctx)
+        return PT_ERR_INVALID_ARGUMENT;
+    cudaSetDevice(ctx->device);
+    return traceOcclusion(ctx, rays, ray_count, out_occluded);
+}
+
+pt_status pt_get_stats(pt_context *ctx, pt_stats *out)
+{
+    if (!ctx || !out)
+        return PT_ERR_INVALID_ARGUMENT;
+    cudaSetDevice(ctx->device);
+    DeviceCounters c;
+    PT_CUDA_CHECK(ctx, cudaMemcpyAsync(&c, ctx->dCounters, sizeof(c), cudaMemcpyDeviceToHost, ctx->stream));
+    PT_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+    pt_stats s = ctx->stats;
+    s.rays_closest = c.raysClosest;
+    s.rays_shadow = c.raysShadow;
+    s.samples = c.samples;
+    s.hits = c.hits;
+    s.box_tests = c.boxTests;
+    s.tri_tests = c.triTests;
+    s.alpha_tests = c.alphaTests;
+    s.restarts = c.restarts;
+    s.triangle_count = ctx->scene.triCount;
+    s.bvh_node_count = ctx->nodeCount;
+    s.bvh_bytes = ctx->bvhBytes;
+    s.bvh_build_ms = ctx->bvhBuildMs;
+    s.scene_upload_ms = ctx->sceneUploadMs;
+    *out = s;
+    return PT_OK;
+}
+
+pt_status pt_set_traversal_stats(pt_context *ctx, int32_t enable)
+{
+    if (!ctx)
+        return PT_ERR_INVALID_ARGUMENT;
+    ctx->collectTraversalStats = enable != 0;
+    return PT_OK;
+}
+
+uint32_t pt_test_input_stride(uint32_t mode) { return testInputStride(mode); }
+uint32_t pt_test_output_stride(uint32_t mode) { return testOutputStride(mode); }
+
+pt_status pt_test_shading(pt_context *ctx, uint32_t mode, const float *input, float *output, uint32_t count)
+{
+    if (!ctx)
+        return PT_ERR_INVALID_ARGUMENT;
+    cudaSetDevice(ctx->device);
+    return testShading(ctx, mode, input, output, count);
+}
+
+} // extern "C"

@@ -1,0 +1,166 @@
+// scene.cuh — device-resident scene layout (HBM) and the software texture sampler.
+//
+// Layout, designed for the traversal / shade kernels rather than copied from the reference:
+//   * instances x meshes are FLATTENED at upload: every instanced triangle is baked to world
+//     space once (the reference re-derives the 4x4 transform and inverts it four times per hit,
+//     PT/Shaders/sampling.glsl:5-15).  Flattened triangle id order = instance, mesh-in-model,
+//     primitive (this id breaks ties in t, so results do not depend on the BVH).
+//   * triangles are stored in BVH leaf order in two streams:
+//       TriPos   48 B  — three float4: world positions, .w lanes carry flat id / flags / material
+//                        id; read by the intersection loop (coalesced 16-B loads);
+//       TriShade 144 B — nine float4: un-normalised world normals / tangents / bitangents of
+//                        the three corners, the three UVs and the (instance, geometry,
+//                        primitive) triple; read once per shaded hit.
+//   * wide BVH nodes are 128 B (one L2 line): SoA child boxes + 4 child references.
+//   * textures: RGBA8 (or float) mip chains, one allocation per texture, sampled in software (bilinear x
+//     trilinear, repeat) so that CPU oracle and GPU agree; sRGB decode through a 256-entry LUT.
+#pragma once
+#include "vecmath.cuh"
+
+namespace pt
+{
+
+// ---------------------------------------------------------------------------------------------
+// BVH4 node, 128 bytes
+// ---------------------------------------------------------------------------------------------
+struct __align__(16) BvhNode
+{
+    float4 lox, loy, loz; // child i: lo = (lox[i], loy[i], loz[i])
+    float4 hix, hiy, hiz;
+    int4 child;           // >= 0: internal node index; < 0: leaf, ~child = (firstTri << 2) | (count - 1)
+    int4 pad;
+};
+static_assert(sizeof(BvhNode) == 128, "BvhNode must be one 128-byte line");
+
+#define PT_CHILD_EMPTY 0x7fffffff
+#define PT_MAX_LEAF_TRIS 4
+
+PT_HD int encodeLeaf(uint32_t first, uint32_t count) { return ~(int)((first << 2) | (count - 1)); }
+
+#define PT_TRI_FLAG_OPAQUE 1u
+
+struct __align__(16) TriShade
+{
+    float4 a[9];
+    // a[0] = n0.xyz, n1.x   a[1] = n1.yz, n2.xy   a[2] = n2.z, t0.xyz
+    // a[3] = t1.xyz, t2.x   a[4] = t2.yz, b0.xy   a[5] = b0.z, b1.xyz
+    // a[6] = b2.xyz, uv0.x  a[7] = uv0.y, uv1.xy, uv2.x   a[8] = uv2.y, instance, geometry, primitive (bits)
+};
+static_assert(sizeof(TriShade) == 144, "TriShade must be 144 bytes");
+
+// ---------------------------------------------------------------------------------------------
+// materials: the reference's 96-byte structs, verbatim (PT/Shaders/ShaderTypes.incl:61-118)
+// ---------------------------------------------------------------------------------------------
+struct __align__(16) MaterialRaw
+{
+    float4 q[6];
+};
+
+// ---------------------------------------------------------------------------------------------
+// textures
+// ---------------------------------------------------------------------------------------------
+#define PT_MAX_TEX_LEVELS 16
+#define PT_TEX_FLAG_SRGB 1u
+#define PT_TEX_FLAG_FLOAT 2u
+
+struct DevTexture
+{
+    uint64_t base; // device address of level 0 (levels follow contiguously)
+    uint32_t width, height;
+    uint32_t levels;
+    uint32_t flags;
+    uint32_t levelOffset[PT_MAX_TEX_LEVELS]; // in texels, relative to base
+};
+
+struct LightBlock
+{
+    uint32_t count;
+    uint32_t pad[3];
+    float4 dirColor;     // DirectionalLight.Color
+    float4 dirDirection; // DirectionalLight.Direction
+    float4 point[64 * 3]; // PointLight: color|pad, position|pad, (c, l, q, pad)
+};
+
+struct DeviceScene
+{
+    const BvhNode *nodes;
+    const float4 *triPos;     // 3 per triangle, leaf order
+    const TriShade *triShade; // leaf order
+    const MaterialRaw *materials[3]; // by material type
+    const DevTexture *textures;
+    const float *lut; // [0..255] unorm, [256..511] sRGB -> linear
+    const LightBlock *lights;
+    DevTexture sky2D;
+    uint32_t triCount;
+    uint32_t textureCount;
+    uint32_t hasAlpha; // any non-opaque triangle
+    uint32_t hasSky2D;
+};
+
+// ---------------------------------------------------------------------------------------------
+// sampler (linear / linear-mip / repeat; isotropic — see oracle/pt_oracle.cpp for the definition)
+// ---------------------------------------------------------------------------------------------
+PT_DEV float4 fetchTexel(const DeviceScene &s, const DevTexture &t, uint32_t level, uint32_t x, uint32_t y, uint32_t lw)
+{
+    const size_t idx = (size_t)t.levelOffset[level] + (size_t)y * lw + x;
+    if (t.flags & PT_TEX_FLAG_FLOAT)
+        return __ldg(reinterpret_cast<const float4 *>(t.base) + idx);
+    const uchar4 c = __ldg(reinterpret_cast<const uchar4 *>(t.base) + idx);
+    const float *lut = s.lut + ((t.flags & PT_TEX_FLAG_SRGB) ? 256 : 0);
+    return make_float4(__ldg(lut + c.x), __ldg(lut + c.y), __ldg(lut + c.z), __ldg(s.lut + c.w));
+}
+
+PT_DEV float4 lerp4(float4 a, float4 b, float f)
+{
+    const float g = 1.0f - f;
+    return make_float4(a.x * g + b.x * f, a.y * g + b.y * f, a.z * g + b.z * f, a.w * g + b.w * f);
+}
+
+PT_DEV float4 sampleBilinear(const DeviceScene &s, const DevTexture &t, uint32_t level, float u, float v)
+{
+    const uint32_t lw = max(1u, t.width >> level), lh = max(1u, t.height >> level);
+    if (lw == 1 && lh == 1)
+        return fetchTexel(s, t, level, 0, 0, 1);
+    u = isfinite(u) ? u : 0.0f;
+    v = isfinite(v) ? v : 0.0f;
+    u = u - floorf(u);
+    v = v - floorf(v);
+    const float x = u * (float)lw - 0.5f, y = v * (float)lh - 0.5f;
+    const float fx0 = floorf(x), fy0 = floorf(y);
+    const float fx = x - fx0, fy = y - fy0;
+    const int W = (int)lw, H = (int)lh;
+    const int x0 = (((int)fx0 % W) + W) % W, x1 = (x0 + 1) % W;
+    const int y0 = (((int)fy0 % H) + H) % H, y1 = (y0 + 1) % H;
+    const float4 t00 = fetchTexel(s, t, level, x0, y0, lw), t10 = fetchTexel(s, t, level, x1, y0, lw);
+    const float4 t01 = fetchTexel(s, t, level, x0, y1, lw), t11 = fetchTexel(s, t, level, x1, y1, lw);
+    return lerp4(lerp4(t00, t10, fx), lerp4(t01, t11, fx), fy);
+}
+
+// texture() outside a fragment stage: level 0
+PT_DEV float4 textureLod0(const DeviceScene &s, const DevTexture &t, float u, float v)
+{
+    return sampleBilinear(s, t, 0, u, v);
+}
+
+// textureGrad(): lambda = log2(max(|dPdx * size|, |dPdy * size|))
+PT_DEV float4 textureGrad(const DeviceScene &s, const DevTexture &t, float u, float v, float4 deriv)
+{
+    const uint32_t last = t.levels - 1;
+    if (last == 0)
+        return sampleBilinear(s, t, 0, u, v);
+    const float w = (float)t.width, h = (float)t.height;
+    const float ax = deriv.x * w, ay = deriv.y * h, bx = deriv.z * w, by = deriv.w * h;
+    const float rho2 = fmaxf(ax * ax + ay * ay, bx * bx + by * by);
+    const float lambda = 0.5f * log2f(rho2);
+    if (!(lambda > 0.0f))
+        return sampleBilinear(s, t, 0, u, v);
+    if (lambda >= (float)last)
+        return sampleBilinear(s, t, last, u, v);
+    const float fl = floorf(lambda);
+    const uint32_t l0 = (uint32_t)fl;
+    const float4 a = sampleBilinear(s, t, l0, u, v);
+    const float4 b = sampleBilinear(s, t, l0 + 1, u, v);
+    return lerp4(a, b, lambda - fl);
+}
+
+} // namespace pt

@@ -1,0 +1,174 @@
+// unit_kernels.cu — pt_test_shading: runs the production __device__ functions one record per
+// thread, the CUDA counterpart of the reference's shader unit-test harness
+// (PTT/Shaders/testShading.comp, testBsdf.comp driven by PTT/TestRenderer.cpp:79-106).
+#include "core_internal.h"
+#include "shading.cuh"
+
+namespace pt
+{
+
+namespace
+{
+
+__constant__ uint32_t c_in[PT_TEST_MODE_COUNT] = { 4, 4, 4, 2, 1, 10, 11, 6, 3, 23, 21, 4, 42, 6, 2, 3 };
+__constant__ uint32_t c_out[PT_TEST_MODE_COUNT] = { 1, 1, 1, 1, 1, 4, 4, 3, 4, 4, 8, 9, 18, 3, 2, 9 };
+const uint32_t h_in[PT_TEST_MODE_COUNT] = { 4, 4, 4, 2, 1, 10, 11, 6, 3, 23, 21, 4, 42, 6, 2, 3 };
+const uint32_t h_out[PT_TEST_MODE_COUNT] = { 1, 1, 1, 1, 1, 4, 4, 3, 4, 4, 8, 9, 18, 3, 2, 9 };
+
+__device__ MaterialSample materialFromFloats(const float *f)
+{
+    MaterialSample m;
+    m.EmissiveColor = V3(f[0], f[1], f[2]);
+    m.Color = V3(f[3], f[4], f[5]);
+    m.Normal = V3(f[6], f[7], f[8]);
+    m.Roughness = f[9];
+    m.Metalness = f[10];
+    m.Transmission = f[11];
+    m.Eta = f[12];
+    m.AttenuationColor = V3(f[13], f[14], f[15]);
+    m.AttenuationDistance = f[16];
+    return m;
+}
+
+__global__ void k_test(uint32_t mode, const float *__restrict__ in, float *__restrict__ out, uint32_t count)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count)
+        return;
+    const float *a = in + (size_t)i * c_in[mode];
+    float *o = out + (size_t)i * c_out[mode];
+    switch (mode)
+    {
+    case PT_TEST_GGX_DISTRIBUTION:
+        o[0] = GGXDistribution(V3(a[0], a[1], a[2]), a[3]);
+        break;
+    case PT_TEST_LAMBDA:
+        o[0] = Lambda(V3(a[0], a[1], a[2]), a[3]);
+        break;
+    case PT_TEST_GGX_SMITH:
+        o[0] = GGXSmith(V3(a[0], a[1], a[2]), a[3]);
+        break;
+    case PT_TEST_DIELECTRIC_FRESNEL:
+        o[0] = DielectricFresnel(a[0], a[1]);
+        break;
+    case PT_TEST_SCHLICK_FRESNEL:
+        o[0] = SchlickFresnel(a[0]);
+        break;
+    case PT_TEST_EVALUATE_REFLECTION: {
+        float pdf;
+        const vec3 f = EvaluateReflection(V3(a[0], a[1], a[2]), V3(a[3], a[4], a[5]), V3(a[6], a[7], a[8]), a[9], pdf);
+        o[0] = f.x, o[1] = f.y, o[2] = f.z, o[3] = pdf;
+        break;
+    }
+    case PT_TEST_EVALUATE_REFRACTION: {
+        float pdf;
+        const vec3 f =
+            EvaluateRefraction(V3(a[0], a[1], a[2]), V3(a[3], a[4], a[5]), V3(a[6], a[7], a[8]), a[9], a[10], pdf);
+        o[0] = f.x, o[1] = f.y, o[2] = f.z, o[3] = pdf;
+        break;
+    }
+    case PT_TEST_SAMPLE_GGX: {
+        const vec3 h = SampleGGX(V2(a[0], a[1]), V3(a[2], a[3], a[4]), a[5]);
+        o[0] = h.x, o[1] = h.y, o[2] = h.z;
+        break;
+    }
+    case PT_TEST_SAMPLE_LOBE_PDFS: {
+        const LobePdfs p = sampleLobePdfs(a[0], a[1], a[2]);
+        o[0] = p.Diffuse, o[1] = p.Glossy, o[2] = p.Metallic, o[3] = p.Transmissive;
+        break;
+    }
+    case PT_TEST_EVALUATE_BSDF: {
+        const MaterialSample m = materialFromFloats(a);
+        float pdf;
+        const vec3 f = evaluateBSDF(m, V3(a[17], a[18], a[19]), V3(a[20], a[21], a[22]), pdf);
+        o[0] = f.x, o[1] = f.y, o[2] = f.z, o[3] = pdf;
+        break;
+    }
+    case PT_TEST_SAMPLE_BSDF: {
+        const MaterialSample m = materialFromFloats(a);
+        uint32_t rng = __float_as_uint(a[20]);
+        const BSDFSample b = sampleBSDF(m, V3(a[17], a[18], a[19]), rng);
+        o[0] = b.Direction.x, o[1] = b.Direction.y, o[2] = b.Direction.z, o[3] = b.Pdf;
+        o[4] = b.Color.x, o[5] = b.Color.y, o[6] = b.Color.z, o[7] = __uint_as_float(rng);
+        break;
+    }
+    case PT_TEST_RNG: {
+        uint32_t st = initRng(__float_as_uint(a[0]), __float_as_uint(a[1]), __float_as_uint(a[2]), __float_as_uint(a[3]));
+        o[0] = __uint_as_float(st);
+        for (int k = 0; k < 4; k++)
+        {
+            const float f = rnd(st);
+            o[1 + k] = __uint_as_float(st);
+            o[5 + k] = f;
+        }
+        break;
+    }
+    case PT_TEST_PRIMARY_RAY: {
+        CameraMatrices cam;
+        for (int k = 0; k < 16; k++)
+        {
+            cam.view[k] = a[10 + k];
+            cam.proj[k] = a[26 + k];
+        }
+        const PrimaryRays r = constructPrimaryRay((float)__float_as_uint(a[0]), (float)__float_as_uint(a[1]),
+                                                  (float)__float_as_uint(a[2]), (float)__float_as_uint(a[3]), cam,
+                                                  V2(a[4], a[5]), V2(a[6], a[7]), a[8], a[9]);
+        const vec3 dirs[3] = { r.direction, r.rxDirection, r.ryDirection };
+        for (int k = 0; k < 3; k++)
+        {
+            o[k * 6 + 0] = r.origin.x, o[k * 6 + 1] = r.origin.y, o[k * 6 + 2] = r.origin.z;
+            o[k * 6 + 3] = dirs[k].x, o[k * 6 + 4] = dirs[k].y, o[k * 6 + 5] = dirs[k].z;
+        }
+        break;
+    }
+    case PT_TEST_OFFSET_SELF_INTERSECTION: {
+        const vec3 r = offsetRayOriginSelfIntersection(V3(a[0], a[1], a[2]), V3(a[3], a[4], a[5]));
+        o[0] = r.x, o[1] = r.y, o[2] = r.z;
+        break;
+    }
+    case PT_TEST_CONCENTRIC_DISK: {
+        const vec2 r = sampleUniformDiskConcentric(V2(a[0], a[1]));
+        o[0] = r.x, o[1] = r.y;
+        break;
+    }
+    case PT_TEST_TANGENT_SPACE: {
+        const mat3 m = computeTangentSpace(V3(a[0], a[1], a[2]));
+        o[0] = m.c0.x, o[1] = m.c0.y, o[2] = m.c0.z;
+        o[3] = m.c1.x, o[4] = m.c1.y, o[5] = m.c1.z;
+        o[6] = m.c2.x, o[7] = m.c2.y, o[8] = m.c2.z;
+        break;
+    }
+    }
+}
+
+} // namespace
+
+uint32_t testInputStride(uint32_t mode) { return mode < PT_TEST_MODE_COUNT ? h_in[mode] : 0; }
+uint32_t testOutputStride(uint32_t mode) { return mode < PT_TEST_MODE_COUNT ? h_out[mode] : 0; }
+
+pt_status testShading(Context *ctx, uint32_t mode, const float *input, float *output, uint32_t count)
+{
+    if (mode >= PT_TEST_MODE_COUNT || (count && (!input || !output)))
+        return fail(ctx, PT_ERR_INVALID_ARGUMENT, "pt_test_shading", "bad mode or NULL buffer");
+    if (count == 0)
+        return PT_OK;
+    const size_t inBytes = (size_t)count * h_in[mode] * 4, outBytes = (size_t)count * h_out[mode] * 4;
+    float *dIn = nullptr, *dOut = nullptr;
+    PT_CUDA_CHECK(ctx, cudaMalloc((void **)&dIn, inBytes));
+    cudaError_t err = cudaMalloc((void **)&dOut, outBytes);
+    if (err == cudaSuccess)
+        err = cudaMemcpyAsync(dIn, input, inBytes, cudaMemcpyHostToDevice, ctx->stream);
+    if (err == cudaSuccess)
+    {
+        k_test<<<(count + 63) / 64, 64, 0, ctx->stream>>>(mode, dIn, dOut, count);
+        err = cudaMemcpyAsync(output, dOut, outBytes, cudaMemcpyDeviceToHost, ctx->stream);
+    }
+    if (err == cudaSuccess)
+        err = cudaStreamSynchronize(ctx->stream);
+    cudaFree(dIn);
+    cudaFree(dOut);
+    PT_CUDA_CHECK(ctx, err);
+    return PT_OK;
+}
+
+} // namespace pt

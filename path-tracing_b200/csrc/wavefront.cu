@@ -1,0 +1,842 @@
+// wavefront.cu — the path-tracing hot path as wavefront kernels for sm_100a.
+//
+// One SLOT per pixel of the current tile set; a slot traces the pixel's samples one after the
+// other (path regeneration), so the wavefront stays full until the last samples and every pixel
+// accumulates its samples in the reference's order.  Per iteration:
+//
+//   k_extend   closest-hit traversal of every active slot's ray          (raygen.rgen:68)
+//   k_shade    miss.rmiss / closestHit.rchit + the raygen bounce logic     (raygen.rgen:71-96)
+//              emits a shadow ray into a compacted queue when NEE can contribute
+//   k_shadow   occlusion traversal, adds the direct-light contribution    (raygen.rgen:79-81)
+//   k_finish   finished paths: NaN/Inf restart or accumulate, next sample's primary ray
+//              (raygen.rgen:38-58, 99-117); builds the next compacted active queue
+//
+// Path state is SoA float4 streams indexed by slot (coalesced 16-byte accesses); queues hold slot
+// indices and are compacted with warp-aggregated atomics.  Queue order never influences a slot's
+// arithmetic, so results are deterministic.
+#include "core_internal.h"
+#include "shading.cuh"
+#include "traverse.cuh"
+
+#include <algorithm>
+#include <cstring>
+
+namespace pt
+{
+
+namespace
+{
+
+constexpr uint32_t kStateDone = 0x100u;
+constexpr uint32_t kMaxRestarts = 1024; // the reference's restart loop is unbounded; see oracle
+
+struct RenderConst
+{
+    DeviceScene scene;
+    PathState ps;
+    CameraMatrices cam;
+    float4 *accum;
+    DeviceCounters *counters;
+    QueueCounts *qc;
+    uint32_t width, height;
+    uint32_t firstSample, sampleCount;
+    uint32_t bounceCount;
+    float lensRadius, focalDistance;
+    uint32_t missFlags, hitFlags;
+    uint32_t slotCount;
+};
+
+__device__ __forceinline__ uint32_t laneId() { return threadIdx.x & 31u; }
+
+// warp-aggregated atomic increment (all currently converged lanes that call it share one atomic)
+__device__ __forceinline__ uint32_t atomicAggInc(uint32_t *counter)
+{
+    const unsigned mask = __activemask();
+    const int leader = __ffs(mask) - 1;
+    uint32_t base = 0;
+    if ((int)laneId() == leader)
+        base = atomicAdd(counter, (uint32_t)__popc(mask));
+    base = __shfl_sync(mask, base, leader);
+    return base + __popc(mask & ((1u << laneId()) - 1u));
+}
+
+__device__ __forceinline__ void warpAdd(unsigned long long *counter, uint32_t value)
+{
+    for (int o = 16; o > 0; o >>= 1)
+        value += __shfl_down_sync(0xffffffffu, value, o);
+    if (laneId() == 0 && value)
+        atomicAdd(counter, (unsigned long long)value);
+}
+
+// ---------------------------------------------------------------------------------------------
+// raygen.rgen:44-60 — start one sample of a slot's pixel
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void generatePath(const RenderConst &rc, uint32_t slot, uint32_t pixel, uint32_t rng,
+                                             uint32_t restarts)
+{
+    const uint32_t px = pixel % rc.width, py = pixel / rc.width;
+    const float ux = rnd(rng);
+    const float uy = rnd(rng);
+    vec2 u2 = V2(0.0f, 0.0f);
+    if (rc.lensRadius > 0)
+    {
+        u2.x = rnd(rng);
+        u2.y = rnd(rng);
+    }
+    const PrimaryRays pr = constructPrimaryRay((float)px, (float)py, (float)rc.width, (float)rc.height, rc.cam, V2(ux, uy),
+                                               u2, rc.lensRadius, rc.focalDistance);
+    rc.ps.rayO[slot] = make_float4(pr.origin.x, pr.origin.y, pr.origin.z, 0.0f); // MaxRoughness = 0
+    rc.ps.rayD[slot] = make_float4(pr.direction.x, pr.direction.y, pr.direction.z, __uint_as_float(rng));
+    rc.ps.thr[slot] = make_float4(1.0f, 1.0f, 1.0f, __uint_as_float(0u));
+    rc.ps.rad[slot] = make_float4(0.0f, 0.0f, 0.0f, __uint_as_float(restarts));
+    rc.ps.diff0[slot] = make_float4(pr.origin.x, pr.origin.y, pr.origin.z, pr.rxDirection.x);
+    rc.ps.diff1[slot] = make_float4(pr.rxDirection.y, pr.rxDirection.z, pr.origin.x, pr.origin.y);
+    rc.ps.diff2[slot] = make_float4(pr.origin.z, pr.ryDirection.x, pr.ryDirection.y, pr.ryDirection.z);
+}
+
+__global__ void __launch_bounds__(256) k_init(RenderConst rc)
+{
+    const uint32_t stride = gridDim.x * blockDim.x;
+    for (uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x; slot < rc.slotCount; slot += stride)
+    {
+        const uint32_t pixel = rc.ps.slotPixel[slot];
+        rc.ps.sample[slot] = 0;
+        rc.ps.queue[0][slot] = slot;
+        generatePath(rc, slot, pixel, initRng(pixel % rc.width, pixel / rc.width, rc.width, rc.firstSample), 0);
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0)
+    {
+        rc.qc->active[0] = rc.slotCount;
+        rc.qc->active[1] = 0;
+        rc.qc->shadow = 0;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// extend
+// ---------------------------------------------------------------------------------------------
+template <bool ALPHA, bool STATS> __global__ void __launch_bounds__(128) k_extend(RenderConst rc, int cur)
+{
+    const uint32_t n = rc.qc->active[cur];
+    if (blockIdx.x == 0 && threadIdx.x == 0)
+    {
+        rc.qc->active[cur ^ 1] = 0;
+        rc.qc->shadow = 0;
+    }
+    const uint32_t stride = gridDim.x * blockDim.x;
+    uint32_t hits = 0;
+    TraversalStats st = { 0, 0, 0 };
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+    {
+        const uint32_t slot = (cur ? rc.ps.queue[1] : rc.ps.queue[0])[i];
+        const float4 o = rc.ps.rayO[slot], d = rc.ps.rayD[slot];
+        Hit hit;
+        Decal decal;
+        traverse<true, ALPHA, STATS>(rc.scene, V3(o), V3(d), 0.00001f, 10000.0f, hit, decal, st);
+        rc.ps.hit[slot] = make_float4(__uint_as_float(hit.tri), hit.t, hit.b1, hit.b2);
+        if (ALPHA)
+        {
+            rc.ps.decal[slot] = make_float4(decal.r, decal.g, decal.b, decal.dist);
+            rc.ps.decalA[slot] = decal.a;
+        }
+        hits += hit.tri != 0xffffffffu;
+    }
+    warpAdd(&rc.counters->hits, hits);
+    if (STATS)
+    {
+        warpAdd(&rc.counters->boxTests, st.boxTests);
+        warpAdd(&rc.counters->triTests, st.triTests);
+        warpAdd(&rc.counters->alphaTests, st.alphaTests);
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0)
+        atomicAdd(&rc.counters->raysClosest, (unsigned long long)n);
+}
+
+// ---------------------------------------------------------------------------------------------
+// material.glsl
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ vec3 reconstructNormalFromXY(float4 t)
+{
+    const float x = 2.0f * t.x - 1.0f, y = 2.0f * t.y - 1.0f;
+    return V3(x, y, sqrtf(fmaxf(1 - x * x - y * y, 0.0f)));
+}
+
+__device__ __forceinline__ MaterialSample sampleMaterial(const DeviceScene &s, uint32_t materialId, float u, float v,
+                                                         float4 deriv, bool inside, bool flipNormalY)
+{
+    const uint32_t type = materialId & 0xffu, index = materialId >> 8;
+    MaterialSample r;
+    if (type > 2)
+    {
+        // material.glsl:163-166 leaves everything else undefined; zero like the oracle
+        r = MaterialSample {};
+        r.Color = V3(1.0f, 0.0f, 0.0f);
+        r.EmissiveColor = V3(1.0f, 0.0f, 0.0f);
+        return r;
+    }
+    const MaterialRaw *m = (type == 0 ? s.materials[0] : type == 1 ? s.materials[1] : s.materials[2]) + index;
+    const float4 q0 = __ldg(&m->q[0]), q1 = __ldg(&m->q[1]), q2 = __ldg(&m->q[2]);
+    const float4 q3 = __ldg(&m->q[3]), q4 = __ldg(&m->q[4]), q5 = __ldg(&m->q[5]);
+    auto tex = [&](float idxBits) { return textureGrad(s, s.textures[__float_as_uint(idxBits)], u, v, deriv); };
+    r.AttenuationColor = V3(q3.x, q3.y, q3.z);
+    r.AttenuationDistance = q3.w;
+    if (type == 0)
+    {
+        // material.glsl:62-84
+        const float4 e = tex(q4.w), c = tex(q5.x), nm = tex(q5.y);
+        r.EmissiveColor = (V3(e) + V3(q0)) * q0.w;
+        r.Color = V3(c) * V3(q1);
+        r.Normal = reconstructNormalFromXY(nm);
+        r.Roughness = tex(q5.z).y * q2.x;
+        r.Metalness = tex(q5.w).z * q2.y;
+        r.Transmission = q2.w;
+        r.Eta = inside ? q2.z : (1.0f / q2.z);
+    }
+    else
+    {
+        // material.glsl:86-113 / 115-142 (specular-glossiness and Phong share the layout)
+        const float4 e = tex(q4.z), c = tex(q4.w), nm = tex(q5.x);
+        r.EmissiveColor = (V3(e) + V3(q0)) * q0.w;
+        r.Color = V3(c) * V3(q1);
+        r.Normal = reconstructNormalFromXY(nm);
+        r.Transmission = q4.y;
+        r.Eta = inside ? q4.x : (1.0f / q4.x);
+        const vec3 specular = V3(tex(q5.y)) * V3(q2);
+        const float glossiness = tex(q5.z).w * q2.w;
+        r.Roughness = 1.0f - glossiness;
+        const vec3 diff = vmax(specular - 0.04f, 0.0f) / ((r.Color - 0.04f) + 0.00001f);
+        r.Metalness = (diff.x + diff.y + diff.z) / 3.0f;
+    }
+    if (flipNormalY)
+        r.Normal.y *= -1.0f;
+    return r;
+}
+
+// ---------------------------------------------------------------------------------------------
+// sampling.glsl:25-56
+// ---------------------------------------------------------------------------------------------
+struct LightSample
+{
+    vec3 Direction;
+    float Distance;
+    vec3 Color;
+    float Attenuation;
+};
+
+__device__ __forceinline__ LightSample sampleLight(const LightBlock *lb, vec3 u, vec3 position, float &pdf)
+{
+    const uint32_t count = __ldg(&lb->count);
+    const uint32_t lightIndex = (uint32_t)(u.x * (float)(count + 1));
+    pdf = 1.0f / (float)(count + 1);
+    const vec2 dp = sampleUniformDiskConcentric(V2(u.y, u.z));
+    LightSample r;
+    if (lightIndex >= count)
+    {
+        const vec3 diskPoint = V3(dp.x, dp.y, 0.0f) * 0.001f;
+        const vec3 direction = normalize(V3(__ldg(&lb->dirDirection)));
+        r.Direction = normalize(direction + mul(computeTangentSpace(direction), diskPoint));
+        r.Color = V3(__ldg(&lb->dirColor));
+        r.Distance = 100000.0f;
+        r.Attenuation = 1.0f;
+        return r;
+    }
+    const float4 lc = __ldg(&lb->point[lightIndex * 3]), lp = __ldg(&lb->point[lightIndex * 3 + 1]);
+    const float4 la = __ldg(&lb->point[lightIndex * 3 + 2]);
+    const vec3 diskPoint = V3(dp.x, dp.y, 0.0f) * 0.1f;
+    const vec3 direction = normalize(position - V3(lp));
+    const vec3 newPosition = V3(lp) + mul(computeTangentSpace(direction), diskPoint);
+    r.Distance = length(position - newPosition);
+    r.Direction = normalize(position - newPosition);
+    r.Color = V3(lc);
+    const float attenuation = 1.0f / (la.x + r.Distance * la.y + r.Distance * r.Distance * la.z);
+    r.Attenuation = clampf(attenuation, 0.0f, 1.0f);
+    return r;
+}
+
+// miss.rmiss:16-39
+__device__ __forceinline__ vec3 skyRadiance(const RenderConst &rc, vec3 dir)
+{
+    if ((rc.missFlags & PT_MISS_FLAGS_SKYBOX_2D) && rc.scene.hasSky2D)
+    {
+        const float longitude = atan2f(dir.z, dir.x);
+        const float latitude = asinf(-dir.y);
+        const float4 c = textureLod0(rc.scene, rc.scene.sky2D, longitude / 2.0f / PT_PI + 0.5f, latitude / PT_PI + 0.5f);
+        const vec3 rgb = V3(c);
+        return rgb / (1.0f + maxComponent(rgb)); // hdrToLdr
+    }
+    return V3(0.08f, 0.09f, 0.1f);
+}
+
+// ---------------------------------------------------------------------------------------------
+// shade: miss.rmiss | closestHit.rchit, then the raygen bounce logic
+// ---------------------------------------------------------------------------------------------
+template <bool ALPHA> __global__ void __launch_bounds__(128) k_shade(RenderConst rc, int cur)
+{
+    const uint32_t n = rc.qc->active[cur];
+    const uint32_t stride = gridDim.x * blockDim.x;
+    const DeviceScene &s = rc.scene;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+    {
+        const uint32_t slot = (cur ? rc.ps.queue[1] : rc.ps.queue[0])[i];
+        const float4 hitv = rc.ps.hit[slot];
+        const float4 rayO = rc.ps.rayO[slot], rayD = rc.ps.rayD[slot];
+        float4 thr4 = rc.ps.thr[slot];
+        float4 rad4 = rc.ps.rad[slot];
+        vec3 throughput = V3(thr4), radiance = V3(rad4);
+        uint32_t state = __float_as_uint(thr4.w);
+        const vec3 rayDir = V3(rayD);
+        const uint32_t tri = __float_as_uint(hitv.x);
+
+        if (tri == 0xffffffffu)
+        {
+            // raygen.rgen:71-75
+            radiance += throughput * skyRadiance(rc, rayDir);
+            rc.ps.rad[slot] = make_float4(radiance.x, radiance.y, radiance.z, rad4.w);
+            rc.ps.thr[slot] = make_float4(throughput.x, throughput.y, throughput.z, __uint_as_float(state | kStateDone));
+            continue;
+        }
+
+        uint32_t rng = __float_as_uint(rayD.w);
+        float maxRoughness = rayO.w;
+        const float rayTmax = hitv.y;
+        const vec3 bary = V3(1.0f - hitv.z - hitv.w, hitv.z, hitv.w);
+
+        // ---- closestHit.rchit:54-83 with baked world-space data ---------------------------------
+        const float4 q0 = __ldg(s.triPos + 3 * (size_t)tri), q1 = __ldg(s.triPos + 3 * (size_t)tri + 1);
+        const float4 q2 = __ldg(s.triPos + 3 * (size_t)tri + 2);
+        const TriShade &ts = s.triShade[tri];
+        const float4 a0 = __ldg(&ts.a[0]), a1 = __ldg(&ts.a[1]), a2 = __ldg(&ts.a[2]), a3 = __ldg(&ts.a[3]);
+        const float4 a4 = __ldg(&ts.a[4]), a5 = __ldg(&ts.a[5]), a6 = __ldg(&ts.a[6]), a7 = __ldg(&ts.a[7]);
+        const float4 a8 = __ldg(&ts.a[8]);
+        const uint32_t materialId = __float_as_uint(q2.w);
+        const vec3 p0 = V3(q0), p1 = V3(q1), p2 = V3(q2);
+        const vec3 n0r = V3(a0.x, a0.y, a0.z), n1r = V3(a0.w, a1.x, a1.y), n2r = V3(a1.z, a1.w, a2.x);
+        const vec3 t0r = V3(a2.y, a2.z, a2.w), t1r = V3(a3.x, a3.y, a3.z), t2r = V3(a3.w, a4.x, a4.y);
+        const vec3 b0r = V3(a4.z, a4.w, a5.x), b1r = V3(a5.y, a5.z, a5.w), b2r = V3(a6.x, a6.y, a6.z);
+        const vec2 uv0 = V2(a6.w, a7.x), uv1 = V2(a7.y, a7.z), uv2 = V2(a7.w, a8.x);
+
+        const vec3 position = p0 * bary.x + p1 * bary.y + p2 * bary.z;
+        const vec2 texCoords = uv0 * bary.x + uv1 * bary.y + uv2 * bary.z;
+        vec3 normal = normalize(n0r * bary.x + n1r * bary.y + n2r * bary.z);
+        vec3 tangent = normalize(t0r * bary.x + t1r * bary.y + t2r * bary.z);
+        vec3 bitangent = normalize(b0r * bary.x + b1r * bary.y + b2r * bary.z);
+        const vec3 n0 = normalize(n0r), n1 = normalize(n1r), n2 = normalize(n2r);
+
+        const vec3 edge1 = p1 - p0, edge2 = p2 - p0;
+        vec3 geometricNormal = normalize(cross(edge1, edge2));
+        const bool inside = dot(geometricNormal, rayDir) > 0.0f;
+        if (inside)
+        {
+            geometricNormal = -geometricNormal;
+            normal = -normal;
+            tangent = -tangent;
+            bitangent = -bitangent;
+        }
+
+        // ---- tracing.glsl:2-28 -------------------------------------------------------------
+        vec3 dpdu, dpdv, dndu, dndv;
+        {
+            const vec3 en1 = n1 - n0, en2 = n2 - n0;
+            const vec2 duv1 = uv1 - uv0, duv2 = uv2 - uv0;
+            const float det = duv1.x * duv2.y - duv2.x * duv1.y;
+            if (fabsf(det) < 1e-8f)
+            {
+                dpdu = tangent;
+                dpdv = bitangent;
+                dndu = V3(0.0f);
+                dndv = V3(0.0f);
+            }
+            else
+            {
+                const float invDet = 1.0f / det;
+                dpdu = (duv2.y * edge1 - duv1.y * edge2) * invDet;
+                dpdv = (-duv2.x * edge1 + duv1.x * edge2) * invDet;
+                dndu = (duv2.y * en1 - duv1.y * en2) * invDet;
+                dndv = (-duv2.x * en1 + duv1.x * en2) * invDet;
+            }
+        }
+        const float4 d0 = rc.ps.diff0[slot], d1 = rc.ps.diff1[slot], d2 = rc.ps.diff2[slot];
+        RayDifferentials rd;
+        rd.rxOrigin = V3(d0.x, d0.y, d0.z);
+        rd.rxDirection = V3(d0.w, d1.x, d1.y);
+        rd.ryOrigin = V3(d1.z, d1.w, d2.x);
+        rd.ryDirection = V3(d2.y, d2.z, d2.w);
+        // tracing.glsl:31-41
+        vec3 dpdx, dpdy;
+        {
+            const float d = -dot(normal, position);
+            const float tx = (-dot(normal, rd.rxOrigin) - d) / dot(normal, rd.rxDirection);
+            const float ty = (-dot(normal, rd.ryOrigin) - d) / dot(normal, rd.ryDirection);
+            dpdx = (rd.rxOrigin + tx * rd.rxDirection) - position;
+            dpdy = (rd.ryOrigin + ty * rd.ryDirection) - position;
+        }
+        const float4 derivatives = computeDerivatives(dpdx, dpdy, dpdu, dpdv);
+
+        // ---- material, closestHit.rchit:101-117 -------------------------------------------------
+        MaterialSample material = sampleMaterial(s, materialId, texCoords.x, texCoords.y, derivatives, inside,
+                                                 (rc.hitFlags & PT_HIT_FLAGS_DX_NORMAL_TEXTURES) != 0);
+        if (ALPHA)
+        {
+            const float4 dec = rc.ps.decal[slot];
+            if (dec.w != -1.0f && rayTmax > dec.w)
+                material.Color = mix(material.Color, V3(dec), rc.ps.decalA[slot]);
+        }
+        maxRoughness = fmaxf(material.Roughness, maxRoughness);
+        material.Roughness = fmaxf(maxRoughness, 0.01f);
+
+        const mat3 geometryTBN = mat3 { tangent, bitangent, normal };
+        const vec3 N = normalize(normal + mul(geometryTBN, material.Normal));
+        const mat3 TBN = computeTangentSpace(N);
+        // TBN is orthonormal: inverse(TBN) == transpose(TBN)
+        const vec3 V = normalize(mulT(TBN, normalize(-rayDir)));
+
+        BSDFSample bsdf = sampleBSDF(material, V, rng);
+
+        if (inside)
+        {
+            const float e = rayTmax / material.AttenuationDistance;
+            bsdf.Color.x *= powf(material.AttenuationColor.x, e);
+            bsdf.Color.y *= powf(material.AttenuationColor.y, e);
+            bsdf.Color.z *= powf(material.AttenuationColor.z, e);
+        }
+        const bool isRefracted = bsdf.Direction.z < 0.0f;
+        const vec3 rayOrigin = offsetRayOriginShadowTerminator(position, p0, p1, p2, n0, n1, n2, bary, isRefracted);
+
+        float lightPdf, lightSmplPdf;
+        const float l0 = rnd(rng);
+        const float l1 = rnd(rng);
+        const float l2 = rnd(rng);
+        const LightSample light = sampleLight(s.lights, V3(l0, l1, l2), rayOrigin, lightPdf);
+        const vec3 L = normalize(mulT(TBN, -light.Direction));
+        const vec3 lightBsdf = evaluateBSDF(material, V, L, lightSmplPdf);
+
+        const vec3 newDir = normalize(mul(TBN, bsdf.Direction));
+        const vec3 newPos = isRefracted ? offsetRayOriginSelfIntersection(position, -geometricNormal) : rayOrigin;
+        const vec3 directLight = light.Color * light.Attenuation * lightBsdf;
+
+        propagateDifferentials(derivatives, normal, rayOrigin, -rayDir, newDir, dndu, dndv, material.Eta, isRefracted, rd);
+
+        // ---- raygen.rgen:71-96 ----------------------------------------------------------------
+        radiance += throughput * material.EmissiveColor;
+        bool done = false;
+        if (bsdf.Pdf == -1.0f)
+            done = true; // raygen.rgen:71 cannot tell this from a miss
+        else
+        {
+            if (lightPdf > 0.0f)
+            {
+                const vec3 c = throughput * directLight / lightPdf;
+                // a contribution of exactly +-0 cannot change the radiance: the occlusion query is skipped
+                if (!(c.x == 0.0f && c.y == 0.0f && c.z == 0.0f))
+                {
+                    const vec3 sd = -normalize(light.Direction);
+                    rc.ps.shO[slot] = make_float4(newPos.x, newPos.y, newPos.z, light.Distance);
+                    rc.ps.shD[slot] = make_float4(sd.x, sd.y, sd.z, 0.0f);
+                    rc.ps.shC[slot] = make_float4(c.x, c.y, c.z, 0.0f);
+                    rc.ps.shadowQueue[atomicAggInc(&rc.qc->shadow)] = slot;
+                }
+            }
+            if (bsdf.Pdf > 0.001f)
+                throughput *= bsdf.Color / bsdf.Pdf;
+            const float prob = fminf(maxComponent(throughput), 1.0f);
+            if (prob < 0.001f)
+                done = true;
+            else if (prob < rnd(rng))
+                done = true;
+            else
+                throughput = throughput / prob;
+        }
+        uint32_t bounce = (state & 0xffu) + 1;
+        if (bounce >= rc.bounceCount)
+            done = true;
+        state = bounce | (done ? kStateDone : 0u);
+
+        rc.ps.rad[slot] = make_float4(radiance.x, radiance.y, radiance.z, rad4.w);
+        rc.ps.thr[slot] = make_float4(throughput.x, throughput.y, throughput.z, __uint_as_float(state));
+        rc.ps.rayO[slot] = make_float4(newPos.x, newPos.y, newPos.z, maxRoughness);
+        rc.ps.rayD[slot] = make_float4(newDir.x, newDir.y, newDir.z, __uint_as_float(rng));
+        rc.ps.diff0[slot] = make_float4(rd.rxOrigin.x, rd.rxOrigin.y, rd.rxOrigin.z, rd.rxDirection.x);
+        rc.ps.diff1[slot] = make_float4(rd.rxDirection.y, rd.rxDirection.z, rd.ryOrigin.x, rd.ryOrigin.y);
+        rc.ps.diff2[slot] = make_float4(rd.ryOrigin.z, rd.ryDirection.x, rd.ryDirection.y, rd.ryDirection.z);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// shadow
+// ---------------------------------------------------------------------------------------------
+template <bool ALPHA, bool STATS> __global__ void __launch_bounds__(128) k_shadow(RenderConst rc)
+{
+    const uint32_t n = rc.qc->shadow;
+    const uint32_t stride = gridDim.x * blockDim.x;
+    TraversalStats st = { 0, 0, 0 };
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+    {
+        const uint32_t slot = rc.ps.shadowQueue[i];
+        const float4 o = rc.ps.shO[slot], d = rc.ps.shD[slot];
+        Hit hit;
+        Decal decal;
+        traverse<false, ALPHA, STATS>(rc.scene, V3(o), V3(d), 0.00001f, o.w, hit, decal, st);
+        if (hit.tri == 0xffffffffu)
+        {
+            const float4 c = rc.ps.shC[slot];
+            float4 r = rc.ps.rad[slot];
+            r.x += c.x;
+            r.y += c.y;
+            r.z += c.z;
+            rc.ps.rad[slot] = r;
+        }
+    }
+    if (STATS)
+    {
+        warpAdd(&rc.counters->boxTests, st.boxTests);
+        warpAdd(&rc.counters->triTests, st.triTests);
+        warpAdd(&rc.counters->alphaTests, st.alphaTests);
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0)
+        atomicAdd(&rc.counters->raysShadow, (unsigned long long)n);
+}
+
+// ---------------------------------------------------------------------------------------------
+// finish: raygen.rgen:99-117 for finished paths, then the next sample
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_finish(RenderConst rc, int cur)
+{
+    const uint32_t n = rc.qc->active[cur];
+    const uint32_t stride = gridDim.x * blockDim.x;
+    uint32_t samples = 0, restarts = 0;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+    {
+        const uint32_t slot = (cur ? rc.ps.queue[1] : rc.ps.queue[0])[i];
+        const uint32_t state = __float_as_uint(rc.ps.thr[slot].w);
+        bool active = true;
+        if (state & kStateDone)
+        {
+            const float4 r = rc.ps.rad[slot];
+            const uint32_t pixel = rc.ps.slotPixel[slot];
+            uint32_t restartCount = __float_as_uint(r.w);
+            samples++;
+            if ((bad(r.x) || bad(r.y) || bad(r.z)) && restartCount < kMaxRestarts)
+            {
+                // radiance = 0; smpl = -1: the sample is redone with the ADVANCED rng state
+                restarts++;
+                generatePath(rc, slot, pixel, __float_as_uint(rc.ps.rayD[slot].w), restartCount + 1);
+            }
+            else
+            {
+                float4 a = rc.accum[pixel];
+                if (!(bad(r.x) || bad(r.y) || bad(r.z)))
+                {
+                    a.x = r.x + a.x;
+                    a.y = r.y + a.y;
+                    a.z = r.z + a.z;
+                }
+                a.w = 1.0f;
+                rc.accum[pixel] = a;
+                const uint32_t next = rc.ps.sample[slot] + 1;
+                rc.ps.sample[slot] = next;
+                if (next < rc.sampleCount)
+                    generatePath(rc, slot, pixel,
+                                 initRng(pixel % rc.width, pixel / rc.width, rc.width, rc.firstSample + next), 0);
+                else
+                    active = false;
+            }
+        }
+        if (active)
+            (cur ? rc.ps.queue[0] : rc.ps.queue[1])[atomicAggInc(&rc.qc->active[cur ^ 1])] = slot;
+    }
+    warpAdd(&rc.counters->samples, samples);
+    warpAdd(&rc.counters->restarts, restarts);
+}
+
+// ---------------------------------------------------------------------------------------------
+// standalone queries
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ pt_hit toPtHit(const DeviceScene &s, const Hit &h)
+{
+    pt_hit r;
+    if (h.tri == 0xffffffffu)
+    {
+        r.instance = r.geometry = r.primitive = PT_NO_HIT;
+        r.t = r.u = r.v = 0.0f;
+        return r;
+    }
+    const float4 a8 = __ldg(&s.triShade[h.tri].a[8]);
+    r.instance = __float_as_uint(a8.y);
+    r.geometry = __float_as_uint(a8.z);
+    r.primitive = __float_as_uint(a8.w);
+    r.t = h.t;
+    r.u = h.b1;
+    r.v = h.b2;
+    return r;
+}
+
+template <bool ALPHA> __global__ void k_first_hit(DeviceScene s, CameraMatrices cam, uint32_t width, uint32_t height, pt_hit *out)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= width * height)
+        return;
+    const uint32_t px = i % width, py = i / width;
+    // ray.glsl:87-90: pixel centre
+    const PrimaryRays pr = constructPrimaryRay((float)px, (float)py, (float)width, (float)height, cam, V2(0.5f, 0.5f),
+                                               V2(0.0f, 0.0f), 0.0f, 0.0f);
+    Hit hit;
+    Decal decal;
+    TraversalStats st;
+    traverse<true, ALPHA, false>(s, pr.origin, pr.direction, 0.00001f, 10000.0f, hit, decal, st);
+    out[i] = toPtHit(s, hit);
+}
+
+template <bool ALPHA> __global__ void k_trace_closest(DeviceScene s, const pt_ray *rays, uint64_t n, pt_hit *out)
+{
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n)
+        return;
+    const pt_ray r = rays[i];
+    Hit hit;
+    Decal decal;
+    TraversalStats st;
+    traverse<true, ALPHA, false>(s, V3(r.origin[0], r.origin[1], r.origin[2]),
+                                 V3(r.direction[0], r.direction[1], r.direction[2]), r.tmin, r.tmax, hit, decal, st);
+    out[i] = toPtHit(s, hit);
+}
+
+template <bool ALPHA> __global__ void k_trace_occlusion(DeviceScene s, const pt_ray *rays, uint64_t n, uint8_t *out)
+{
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n)
+        return;
+    const pt_ray r = rays[i];
+    Hit hit;
+    Decal decal;
+    TraversalStats st;
+    traverse<false, ALPHA, false>(s, V3(r.origin[0], r.origin[1], r.origin[2]),
+                                  V3(r.direction[0], r.direction[1], r.direction[2]), r.tmin, r.tmax, hit, decal, st);
+    out[i] = hit.tri != 0xffffffffu;
+}
+
+CameraMatrices toCamera(const pt_render_params *p)
+{
+    CameraMatrices c;
+    std::memcpy(c.view, p->view_inverse, 64);
+    std::memcpy(c.proj, p->proj_inverse, 64);
+    return c;
+}
+
+} // namespace
+
+// ---------------------------------------------------------------------------------------------
+// host drivers
+// ---------------------------------------------------------------------------------------------
+pt_status renderSamples(Context *ctx, const pt_render_params *params, uint32_t firstSample, uint32_t sampleCount,
+                        const pt_tile *tiles, uint32_t tileCount)
+{
+    if (!params)
+        return fail(ctx, PT_ERR_INVALID_ARGUMENT, "pt_render_samples", "params is NULL");
+    if (!ctx->hasScene)
+        return fail(ctx, PT_ERR_NO_SCENE, "pt_render_samples", "no scene uploaded");
+    if (!ctx->accum)
+        return fail(ctx, PT_ERR_NO_TARGET, "pt_render_samples", "pt_render_begin has not been called");
+    if (params->miss_flags & PT_MISS_FLAGS_SKYBOX_CUBE)
+        return fail(ctx, PT_ERR_UNSUPPORTED, "pt_render_samples", "cube skyboxes are not supported");
+    if (params->bounce_count == 0 || params->bounce_count > 255)
+        return fail(ctx, PT_ERR_INVALID_ARGUMENT, "pt_render_samples", "bounce_count must be in 1..255");
+    if (tiles == nullptr)
+        tileCount = 0;
+
+    // ---- slot -> pixel map: 8x4 pixel blocks so that a warp's primary rays are coherent --------
+    const uint32_t W = ctx->width, H = ctx->height;
+    {
+        const pt_tile whole = { 0, 0, W, H };
+        std::vector<pt_tile> want(tileCount ? tiles : &whole, tileCount ? tiles + tileCount : &whole + 1);
+        const bool same = ctx->slotMapValid && want.size() == ctx->slotTiles.size() &&
+                          (want.empty() || std::memcmp(want.data(), ctx->slotTiles.data(), want.size() * sizeof(pt_tile)) == 0);
+        if (!same)
+        {
+            std::vector<uint32_t> slotPixel;
+            for (const pt_tile &in : want)
+            {
+                const pt_tile t = { std::min(in.x0, W), std::min(in.y0, H), std::min(in.x1, W), std::min(in.y1, H) };
+                for (uint32_t by = t.y0; by < t.y1; by += 4)
+                    for (uint32_t bx = t.x0; bx < t.x1; bx += 8)
+                        for (uint32_t y = by; y < std::min(by + 4, t.y1); y++)
+                            for (uint32_t x = bx; x < std::min(bx + 8, t.x1); x++)
+                                slotPixel.push_back(y * W + x);
+            }
+            if (slotPixel.size() > ctx->slotCapacity)
+                return fail(ctx, PT_ERR_INVALID_ARGUMENT, "pt_render_samples", "tiles overlap or exceed the frame");
+            if (!slotPixel.empty())
+                PT_CUDA_CHECK(ctx, cudaMemcpyAsync(ctx->ps.slotPixel, slotPixel.data(), slotPixel.size() * 4,
+                                                   cudaMemcpyHostToDevice, ctx->stream));
+            PT_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+            ctx->slotTiles = want;
+            ctx->slotCount = (uint32_t)slotPixel.size();
+            ctx->slotMapValid = true;
+        }
+    }
+    const uint32_t slots = ctx->slotCount;
+
+    ctx->stats.kernel_launches = 0;
+    ctx->stats.wavefront_iterations = 0;
+    PT_CUDA_CHECK(ctx, cudaMemsetAsync(ctx->dCounters, 0, sizeof(DeviceCounters), ctx->stream));
+    PT_CUDA_CHECK(ctx, cudaEventRecord(ctx->evStart, ctx->stream));
+    if (slots > 0 && sampleCount > 0)
+    {
+        RenderConst rc = {};
+        rc.scene = ctx->scene;
+        rc.ps = ctx->ps;
+        rc.cam = toCamera(params);
+        rc.accum = ctx->accum;
+        rc.counters = ctx->dCounters;
+        rc.qc = ctx->dQueueCounts;
+        rc.width = W;
+        rc.height = H;
+        rc.firstSample = firstSample;
+        rc.sampleCount = sampleCount;
+        rc.bounceCount = params->bounce_count;
+        rc.lensRadius = params->lens_radius;
+        rc.focalDistance = params->focal_distance;
+        rc.missFlags = params->miss_flags;
+        rc.hitFlags = params->hit_flags;
+        rc.slotCount = slots;
+
+        const bool alpha = ctx->scene.hasAlpha != 0;
+        const bool statsOn = ctx->collectTraversalStats;
+        const uint32_t gridTrace = std::min((slots + 127) / 128, (uint32_t)ctx->smCount * 16);
+        const uint32_t gridWide = std::min((slots + 255) / 256, (uint32_t)ctx->smCount * 8);
+        k_init<<<gridWide, 256, 0, ctx->stream>>>(rc);
+        ctx->stats.kernel_launches++;
+
+        int cur = 0;
+        const uint32_t checkEvery = 4;
+        for (uint64_t iter = 0;; iter++)
+        {
+#define PT_LAUNCH_EXTEND(A, S) k_extend<A, S><<<gridTrace, 128, 0, ctx->stream>>>(rc, cur)
+#define PT_LAUNCH_SHADOW(A, S) k_shadow<A, S><<<gridTrace, 128, 0, ctx->stream>>>(rc)
+            if (alpha && statsOn)
+                PT_LAUNCH_EXTEND(true, true);
+            else if (alpha)
+                PT_LAUNCH_EXTEND(true, false);
+            else if (statsOn)
+                PT_LAUNCH_EXTEND(false, true);
+            else
+                PT_LAUNCH_EXTEND(false, false);
+            if (alpha)
+                k_shade<true><<<gridTrace, 128, 0, ctx->stream>>>(rc, cur);
+            else
+                k_shade<false><<<gridTrace, 128, 0, ctx->stream>>>(rc, cur);
+            if (alpha && statsOn)
+                PT_LAUNCH_SHADOW(true, true);
+            else if (alpha)
+                PT_LAUNCH_SHADOW(true, false);
+            else if (statsOn)
+                PT_LAUNCH_SHADOW(false, true);
+            else
+                PT_LAUNCH_SHADOW(false, false);
+            k_finish<<<gridWide, 256, 0, ctx->stream>>>(rc, cur);
+#undef PT_LAUNCH_EXTEND
+#undef PT_LAUNCH_SHADOW
+            ctx->stats.kernel_launches += 4;
+            ctx->stats.wavefront_iterations++;
+            cur ^= 1;
+            if ((iter + 1) % checkEvery == 0)
+            {
+                PT_CUDA_CHECK(ctx, cudaMemcpyAsync(ctx->hQueueCounts, ctx->dQueueCounts, sizeof(QueueCounts),
+                                                   cudaMemcpyDeviceToHost, ctx->stream));
+                PT_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+                if (ctx->hQueueCounts->active[cur] == 0)
+                    break;
+            }
+        }
+    }
+    PT_CUDA_CHECK(ctx, cudaEventRecord(ctx->evStop, ctx->stream));
+    PT_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+    PT_CUDA_CHECK(ctx, cudaGetLastError());
+    PT_CUDA_CHECK(ctx, cudaEventElapsedTime(&ctx->stats.last_render_ms, ctx->evStart, ctx->evStop));
+    return PT_OK;
+}
+
+pt_status firstHitAov(Context *ctx, const pt_render_params *params, uint32_t width, uint32_t height, pt_hit *out)
+{
+    if (!params || !out || width == 0 || height == 0)
+        return fail(ctx, PT_ERR_INVALID_ARGUMENT, "pt_first_hit_aov", "bad argument");
+    if (!ctx->hasScene)
+        return fail(ctx, PT_ERR_NO_SCENE, "pt_first_hit_aov", "no scene uploaded");
+    const size_t n = (size_t)width * height;
+    pt_hit *dOut = nullptr;
+    PT_CUDA_CHECK(ctx, cudaMalloc((void **)&dOut, n * sizeof(pt_hit)));
+    const uint32_t grid = (uint32_t)((n + 127) / 128);
+    if (ctx->scene.hasAlpha)
+        k_first_hit<true><<<grid, 128, 0, ctx->stream>>>(ctx->scene, toCamera(params), width, height, dOut);
+    else
+        k_first_hit<false><<<grid, 128, 0, ctx->stream>>>(ctx->scene, toCamera(params), width, height, dOut);
+    cudaError_t err = cudaMemcpyAsync(out, dOut, n * sizeof(pt_hit), cudaMemcpyDeviceToHost, ctx->stream);
+    if (err == cudaSuccess)
+        err = cudaStreamSynchronize(ctx->stream);
+    cudaFree(dOut);
+    PT_CUDA_CHECK(ctx, err);
+    return PT_OK;
+}
+
+pt_status traceClosest(Context *ctx, const pt_ray *rays, uint64_t n, pt_hit *out)
+{
+    if ((n && (!rays || !out)))
+        return fail(ctx, PT_ERR_INVALID_ARGUMENT, "pt_trace_closest", "bad argument");
+    if (!ctx->hasScene)
+        return fail(ctx, PT_ERR_NO_SCENE, "pt_trace_closest", "no scene uploaded");
+    if (n == 0)
+        return PT_OK;
+    pt_ray *dRays = nullptr;
+    pt_hit *dOut = nullptr;
+    PT_CUDA_CHECK(ctx, cudaMalloc((void **)&dRays, n * sizeof(pt_ray)));
+    cudaError_t err = cudaMalloc((void **)&dOut, n * sizeof(pt_hit));
+    if (err == cudaSuccess)
+        err = cudaMemcpyAsync(dRays, rays, n * sizeof(pt_ray), cudaMemcpyHostToDevice, ctx->stream);
+    if (err == cudaSuccess)
+    {
+        const uint32_t grid = (uint32_t)((n + 127) / 128);
+        if (ctx->scene.hasAlpha)
+            k_trace_closest<true><<<grid, 128, 0, ctx->stream>>>(ctx->scene, dRays, n, dOut);
+        else
+            k_trace_closest<false><<<grid, 128, 0, ctx->stream>>>(ctx->scene, dRays, n, dOut);
+        err = cudaMemcpyAsync(out, dOut, n * sizeof(pt_hit), cudaMemcpyDeviceToHost, ctx->stream);
+    }
+    if (err == cudaSuccess)
+        err = cudaStreamSynchronize(ctx->stream);
+    cudaFree(dRays);
+    cudaFree(dOut);
+    PT_CUDA_CHECK(ctx, err);
+    return PT_OK;
+}
+
+pt_status traceOcclusion(Context *ctx, const pt_ray *rays, uint64_t n, uint8_t *out)
+{
+    if ((n && (!rays || !out)))
+        return fail(ctx, PT_ERR_INVALID_ARGUMENT, "pt_trace_occlusion", "bad argument");
+    if (!ctx->hasScene)
+        return fail(ctx, PT_ERR_NO_SCENE, "pt_trace_occlusion", "no scene uploaded");
+    if (n == 0)
+        return PT_OK;
+    pt_ray *dRays = nullptr;
+    uint8_t *dOut = nullptr;
+    PT_CUDA_CHECK(ctx, cudaMalloc((void **)&dRays, n * sizeof(pt_ray)));
+    cudaError_t err = cudaMalloc((void **)&dOut, n);
+    if (err == cudaSuccess)
+        err = cudaMemcpyAsync(dRays, rays, n * sizeof(pt_ray), cudaMemcpyHostToDevice, ctx->stream);
+    if (err == cudaSuccess)
+    {
+        const uint32_t grid = (uint32_t)((n + 127) / 128);
+        if (ctx->scene.hasAlpha)
+            k_trace_occlusion<true><<<grid, 128, 0, ctx->stream>>>(ctx->scene, dRays, n, dOut);
+        else
+            k_trace_occlusion<false><<<grid, 128, 0, ctx->stream>>>(ctx->scene, dRays, n, dOut);
+        err = cudaMemcpyAsync(out, dOut, n, cudaMemcpyDeviceToHost, ctx->stream);
+    }
+    if (err == cudaSuccess)
+        err = cudaStreamSynchronize(ctx->stream);
+    cudaFree(dRays);
+    cudaFree(dOut);
+    PT_CUDA_CHECK(ctx, err);
+    return PT_OK;
+}
+
+} // namespace pt
