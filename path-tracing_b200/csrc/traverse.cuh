@@ -73,9 +73,12 @@ PT_DEV bool intersectTriangle(const RaySetup &r, vec3 p0, vec3 p1, vec3 p2, floa
     const float Ax = comp(A, r.kx) - r.Sx * Akz, Ay = comp(A, r.ky) - r.Sy * Akz;
     const float Bx = comp(B, r.kx) - r.Sx * Bkz, By = comp(B, r.ky) - r.Sy * Bkz;
     const float Cx = comp(C, r.kx) - r.Sx * Ckz, Cy = comp(C, r.ky) - r.Sy * Ckz;
-    float U = Cx * By - Cy * Bx;
-    float V = Ax * Cy - Ay * Cx;
-    float W = Bx * Ay - By * Ax;
+    // The edge functions must NOT be contracted into FMAs: watertightness relies on the two
+    // triangles sharing an edge computing exactly opposite values (a*b - c*d with both products
+    // rounded), which fma(a, b, -(c*d)) breaks — it also makes zero-area triangles "hit".
+    float U = __fsub_rn(__fmul_rn(Cx, By), __fmul_rn(Cy, Bx));
+    float V = __fsub_rn(__fmul_rn(Ax, Cy), __fmul_rn(Ay, Cx));
+    float W = __fsub_rn(__fmul_rn(Bx, Ay), __fmul_rn(By, Ax));
     if (U == 0.0f || V == 0.0f || W == 0.0f)
     {
         U = (float)((double)Cx * (double)By - (double)Cy * (double)Bx);

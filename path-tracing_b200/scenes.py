@@ -1,0 +1,574 @@
+"""Procedural scenes, built through a Python mirror of the reference's ``SceneBuilder``
+(Path-Tracing/Scene.h:268-361): the same calls (AddGeometry / AddMaterial / AddTexture / AddModel /
+AddModelInstance / AddLight ...) produce the same flat arrays the reference's Scene holds, so a
+generated scene crosses the C ABI exactly like one loaded by the reference's importers.
+
+Scenes:
+  * ``feature_scene``  — small scene touching every hot-path feature (mesh + instance transforms,
+    three material models, alpha-tested cards, transmission + attenuation, point + directional
+    lights, textures with mips).  Parity-test fodder.
+  * ``chess_scene``    — BASELINE.json configs[1]: "ABeautifulGame-class" stand-in (the Khronos
+    asset is not available offline): a chessboard with 32 lathe-turned pieces.  Triangle and
+    material counts are DECLARED BY THIS BUILDER (see ``chess_scene.__doc__``), not quoted from
+    the real asset.
+All content is generated from fixed integer seeds.
+"""
+from __future__ import annotations
+
+import math
+
+import numpy as np
+
+from . import scene as sc
+
+F = np.float32
+
+
+# ---------------------------------------------------------------------------------------------
+# camera: glm with GLM_FORCE_LEFT_HANDED + GLM_FORCE_DEPTH_ZERO_TO_ONE (Core/Camera.cpp:1-2,52-71)
+# ---------------------------------------------------------------------------------------------
+def look_at_lh(eye, center, up) -> np.ndarray:
+    eye, center, up = (np.asarray(v, np.float64) for v in (eye, center, up))
+    f = center - eye
+    f /= np.linalg.norm(f)
+    s = np.cross(up, f)
+    s /= np.linalg.norm(s)
+    u = np.cross(f, s)
+    m = np.eye(4)
+    m[0, :3], m[1, :3], m[2, :3] = s, u, f
+    m[0, 3], m[1, 3], m[2, 3] = -s @ eye, -u @ eye, -f @ eye
+    return m
+
+
+def perspective_fov_lh_zo(fov_deg, width, height, near, far) -> np.ndarray:
+    h = 1.0 / math.tan(math.radians(fov_deg) / 2)
+    w = h * height / width
+    m = np.zeros((4, 4))
+    m[0, 0], m[1, 1] = w, h
+    m[2, 2] = far / (far - near)
+    m[2, 3] = -(far * near) / (far - near)
+    m[3, 2] = 1.0
+    return m
+
+
+def camera_matrices(position, direction, width, height, fov_deg=45.0, near=100.0, far=0.1, up=(0.0, -1.0, 0.0)):
+    """(ViewInverse, ProjInverse) as 16 floats, column-major like glm.  Defaults are the reference's
+    InputCamera (Scene.h:259-260 — note its near/far arguments are 100 / 0.1)."""
+    position = np.asarray(position, np.float64)
+    view = look_at_lh(position, position + np.asarray(direction, np.float64), up)
+    proj = perspective_fov_lh_zo(fov_deg, width, height, near, far)
+    return (np.linalg.inv(view).T.astype(F).reshape(-1), np.linalg.inv(proj).T.astype(F).reshape(-1))
+
+
+# ---------------------------------------------------------------------------------------------
+# SceneBuilder mirror
+# ---------------------------------------------------------------------------------------------
+def translate(x, y, z):
+    m = np.eye(4)
+    m[:3, 3] = (x, y, z)
+    return m
+
+
+def scale(x, y=None, z=None):
+    y = x if y is None else y
+    z = x if z is None else z
+    return np.diag([x, y, z, 1.0])
+
+
+def rotate_y(deg):
+    c, s = math.cos(math.radians(deg)), math.sin(math.radians(deg))
+    m = np.eye(4)
+    m[0, 0], m[0, 2], m[2, 0], m[2, 2] = c, s, -s, c
+    return m
+
+
+def rotate_x(deg):
+    c, s = math.cos(math.radians(deg)), math.sin(math.radians(deg))
+    m = np.eye(4)
+    m[1, 1], m[1, 2], m[2, 1], m[2, 2] = c, -s, s, c
+    return m
+
+
+class SceneBuilder:
+    """Python counterpart of PathTracing::SceneBuilder.  Matrices are standard column-vector 4x4
+    (world = M @ [p, 1]); the 3x4 row-major form the reference stores is produced at build()."""
+
+    def __init__(self):
+        self.vertices = []
+        self.indices = []
+        self.vertex_count = 0
+        self.index_count = 0
+        self.transforms = [np.array([1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0], F)]  # IdentityTransformIndex = 0
+        self.geometries = []
+        self.mesh_records = []
+        self.models = []
+        self.instances = []
+        self.mr, self.sg, self.phong = [], [], []
+        self.textures = []
+        self.point_lights = []
+        self.directional = np.zeros((), sc.DIRECTIONAL_LIGHT)
+        # SceneBuilder::g_DefaultLight (Scene.h:352-355)
+        self.directional["color"] = (10, 10, 10)
+        self.directional["direction"] = (-0.4, -1.0, -0.2)
+        self.skybox = None
+        self.hit_flags = sc.HIT_FLAGS_NONE
+
+    def add_geometry(self, vertices: np.ndarray, indices: np.ndarray, is_opaque: bool = True) -> int:
+        vertices = np.ascontiguousarray(vertices, sc.VERTEX)
+        indices = np.ascontiguousarray(indices, np.uint32).reshape(-1)
+        assert len(indices) % 3 == 0 and (len(indices) == 0 or indices.max() < len(vertices))
+        self.geometries.append((self.vertex_count, len(vertices), self.index_count, len(indices), 1 if is_opaque else 0))
+        self.vertices.append(vertices)
+        self.indices.append(indices)
+        self.vertex_count += len(vertices)
+        self.index_count += len(indices)
+        return len(self.geometries) - 1
+
+    def add_texture(self, pixels: np.ndarray, srgb: bool) -> int:
+        """Returns the bindless slot, SceneTextureOffset + i (Scene.cpp:125-140)."""
+        self.textures.append(sc.Texture(np.ascontiguousarray(pixels), srgb))
+        return sc.SCENE_TEXTURE_OFFSET + len(self.textures) - 1
+
+    def add_material_mr(self, color=(1, 1, 1, 1), roughness=1.0, metalness=0.0, ior=1.5, transmission=0.0,
+                        emissive=(0, 0, 0), emissive_intensity=0.0, attenuation_color=(1, 1, 1), attenuation_distance=1e32,
+                        color_idx=sc.TEX_DEFAULT_COLOR, normal_idx=sc.TEX_DEFAULT_NORMAL, roughness_idx=sc.TEX_DEFAULT_ROUGHNESS,
+                        metallic_idx=sc.TEX_DEFAULT_METALLIC, emissive_idx=sc.TEX_DEFAULT_EMISSIVE) -> int:
+        m = np.zeros((), sc.MATERIAL_MR)
+        m["emissive_color"], m["emissive_intensity"] = emissive, emissive_intensity
+        m["color"], m["roughness"], m["metalness"], m["ior"], m["transmission"] = color, roughness, metalness, ior, transmission
+        m["attenuation_color"], m["attenuation_distance"] = attenuation_color, attenuation_distance
+        m["emissive_idx"], m["color_idx"], m["normal_idx"] = emissive_idx, color_idx, normal_idx
+        m["roughness_idx"], m["metallic_idx"] = roughness_idx, metallic_idx
+        self.mr.append(m)
+        return sc.material_id(len(self.mr) - 1, sc.MATERIAL_TYPE_MR)
+
+    def _add_sg(self, store, mtype, color, specular, gloss, ior, transmission, emissive, emissive_intensity,
+                attenuation_color, attenuation_distance, color_idx, normal_idx, specular_idx, gloss_idx, emissive_idx):
+        m = np.zeros((), sc.MATERIAL_SG)
+        m["emissive_color"], m["emissive_intensity"] = emissive, emissive_intensity
+        m["color"], m["specular"], m["glossiness"] = color, specular, gloss
+        m["attenuation_color"], m["attenuation_distance"] = attenuation_color, attenuation_distance
+        m["ior"], m["transmission"] = ior, transmission
+        m["emissive_idx"], m["color_idx"], m["normal_idx"] = emissive_idx, color_idx, normal_idx
+        m["specular_idx"], m["glossiness_idx"] = specular_idx, gloss_idx
+        store.append(m)
+        return sc.material_id(len(store) - 1, mtype)
+
+    def add_material_sg(self, color=(1, 1, 1, 1), specular=(1, 1, 1), glossiness=1.0, ior=1.5, transmission=0.0,
+                        emissive=(0, 0, 0), emissive_intensity=0.0, attenuation_color=(1, 1, 1), attenuation_distance=1e32,
+                        color_idx=sc.TEX_DEFAULT_COLOR, normal_idx=sc.TEX_DEFAULT_NORMAL, specular_idx=sc.TEX_DEFAULT_SPECULAR,
+                        glossiness_idx=sc.TEX_DEFAULT_GLOSSINESS, emissive_idx=sc.TEX_DEFAULT_EMISSIVE) -> int:
+        return self._add_sg(self.sg, sc.MATERIAL_TYPE_SG, color, specular, glossiness, ior, transmission, emissive,
+                            emissive_intensity, attenuation_color, attenuation_distance, color_idx, normal_idx, specular_idx,
+                            glossiness_idx, emissive_idx)
+
+    def add_material_phong(self, color=(1, 1, 1, 1), specular=(1, 1, 1), shininess=1.0, ior=1.5, transmission=0.0,
+                           emissive=(0, 0, 0), emissive_intensity=0.0, attenuation_color=(1, 1, 1), attenuation_distance=1e32,
+                           color_idx=sc.TEX_DEFAULT_COLOR, normal_idx=sc.TEX_DEFAULT_NORMAL, specular_idx=sc.TEX_DEFAULT_SPECULAR,
+                           shininess_idx=sc.TEX_DEFAULT_SHININESS, emissive_idx=sc.TEX_DEFAULT_EMISSIVE) -> int:
+        return self._add_sg(self.phong, sc.MATERIAL_TYPE_PHONG, color, specular, shininess, ior, transmission, emissive,
+                            emissive_intensity, attenuation_color, attenuation_distance, color_idx, normal_idx, specular_idx,
+                            shininess_idx, emissive_idx)
+
+    def add_model(self, meshes) -> int:
+        """meshes: iterable of (geometry_index, material_id, transform 4x4 or None) — MeshInfo, Scene.h:80-86."""
+        offset = len(self.mesh_records)
+        count = 0
+        for geometry, material, transform in meshes:
+            tindex = 0
+            if transform is not None and not np.allclose(transform, np.eye(4)):
+                self.transforms.append(np.asarray(transform, np.float64)[:3, :].astype(F).reshape(-1))
+                tindex = len(self.transforms) - 1
+            self.mesh_records.append((geometry, material, tindex))
+            count += 1
+        self.models.append((offset, count))
+        return len(self.models) - 1
+
+    def add_instance(self, model: int, transform=None) -> int:
+        t = np.eye(4) if transform is None else np.asarray(transform, np.float64)
+        self.instances.append((t[:3, :].astype(F).reshape(-1), model))
+        return len(self.instances) - 1
+
+    def add_light(self, color, position, constant=1.0, linear=0.0, quadratic=1.0):
+        l = np.zeros((), sc.POINT_LIGHT)
+        l["color"], l["position"] = color, position
+        l["attenuation_constant"], l["attenuation_linear"], l["attenuation_quadratic"] = constant, linear, quadratic
+        self.point_lights.append(l)
+
+    def set_directional_light(self, color, direction):
+        self.directional["color"], self.directional["direction"] = color, direction
+
+    def set_skybox_2d(self, pixels: np.ndarray, srgb: bool = False):
+        self.skybox = sc.Texture(np.ascontiguousarray(pixels), srgb)
+
+    def build(self, camera=None, extent=(0, 0)) -> sc.SceneData:
+        s = sc.SceneData()
+        s.vertices = np.concatenate(self.vertices) if self.vertices else np.zeros(0, sc.VERTEX)
+        s.indices = np.concatenate(self.indices) if self.indices else np.zeros(0, np.uint32)
+        s.transforms = np.stack(self.transforms).astype(F)
+        s.geometries = np.array(self.geometries, sc.GEOMETRY) if self.geometries else np.zeros(0, sc.GEOMETRY)
+        s.mesh_records = np.array(self.mesh_records, sc.MESH_RECORD) if self.mesh_records else np.zeros(0, sc.MESH_RECORD)
+        s.models = np.array(self.models, sc.MODEL) if self.models else np.zeros(0, sc.MODEL)
+        inst = np.zeros(len(self.instances), sc.INSTANCE)
+        for i, (t, m) in enumerate(self.instances):
+            inst[i]["transform"], inst[i]["model_index"] = t, m
+        s.instances = inst
+        s.mr_materials = np.array(self.mr, sc.MATERIAL_MR) if self.mr else np.zeros(0, sc.MATERIAL_MR)
+        s.sg_materials = np.array(self.sg, sc.MATERIAL_SG) if self.sg else np.zeros(0, sc.MATERIAL_SG)
+        s.phong_materials = np.array(self.phong, sc.MATERIAL_SG) if self.phong else np.zeros(0, sc.MATERIAL_SG)
+        s.textures = list(self.textures)
+        s.point_lights = np.array(self.point_lights, sc.POINT_LIGHT) if self.point_lights else np.zeros(0, sc.POINT_LIGHT)
+        s.directional_light = self.directional.copy()
+        s.skybox_2d = self.skybox
+        s.miss_flags = sc.MISS_FLAGS_SKYBOX_2D if self.skybox is not None else sc.MISS_FLAGS_NONE
+        s.hit_flags = self.hit_flags
+        if camera is not None:
+            s.view_inverse, s.proj_inverse = camera
+            s.camera_extent = tuple(extent)
+        return s
+
+
+# ---------------------------------------------------------------------------------------------
+# mesh primitives (vertices carry position, uv, normal, tangent, bitangent like Shaders::Vertex)
+# ---------------------------------------------------------------------------------------------
+def _vertices(pos, uv, nrm, tan, bit) -> np.ndarray:
+    v = np.zeros(len(pos), sc.VERTEX)
+    v["position"], v["texcoords"], v["normal"], v["tangent"], v["bitangent"] = pos, uv, nrm, tan, bit
+    return v
+
+
+def quad(size_x=1.0, size_z=1.0, uv_scale=1.0):
+    """Horizontal quad in the xz-plane facing +y, two triangles."""
+    x, z = size_x / 2, size_z / 2
+    pos = np.array([[-x, 0, z], [x, 0, z], [x, 0, -z], [-x, 0, -z]], F)
+    uv = np.array([[0, 1], [1, 1], [1, 0], [0, 0]], F) * uv_scale
+    n = np.tile(np.array([0, 1, 0], F), (4, 1))
+    t = np.tile(np.array([1, 0, 0], F), (4, 1))
+    b = np.tile(np.array([0, 0, -1], F), (4, 1))
+    return _vertices(pos, uv, n, t, b), np.array([0, 1, 2, 2, 3, 0], np.uint32)
+
+
+def grid(nx, nz, size_x=1.0, size_z=1.0, uv_scale=1.0, height=None):
+    """Tessellated horizontal patch; height(x, z) -> y optionally displaces it."""
+    xs = np.linspace(-size_x / 2, size_x / 2, nx + 1)
+    zs = np.linspace(-size_z / 2, size_z / 2, nz + 1)
+    X, Z = np.meshgrid(xs, zs, indexing="xy")
+    Y = np.zeros_like(X) if height is None else height(X, Z)
+    pos = np.stack([X, Y, Z], -1).reshape(-1, 3)
+    uv = np.stack([(X / size_x + 0.5) * uv_scale, (0.5 - Z / size_z) * uv_scale], -1).reshape(-1, 2)
+    if height is None:
+        n = np.tile([0.0, 1.0, 0.0], (len(pos), 1))
+    else:
+        e = 1e-3 * max(size_x, size_z)
+        dx = (height(X + e, Z) - height(X - e, Z)) / (2 * e)
+        dz = (height(X, Z + e) - height(X, Z - e)) / (2 * e)
+        n = np.stack([-dx, np.ones_like(dx), -dz], -1).reshape(-1, 3)
+        n /= np.linalg.norm(n, axis=1, keepdims=True)
+    t = np.cross(n, [0, 0, -1.0])
+    t /= np.linalg.norm(t, axis=1, keepdims=True)
+    b = np.cross(n, t)
+    i = (np.arange(nz)[:, None] * (nx + 1) + np.arange(nx)[None, :]).reshape(-1)
+    idx = np.stack([i, i + nx + 1, i + nx + 2, i, i + nx + 2, i + 1], -1).reshape(-1)  # CCW seen from +y
+    return _vertices(pos, uv, n, t, b), idx.astype(np.uint32)
+
+
+def box(sx=1.0, sy=1.0, sz=1.0):
+    """Axis-aligned box centred at the origin, 24 vertices / 12 triangles, per-face frames."""
+    faces = [  # normal, tangent, bitangent
+        ((0, 0, 1), (1, 0, 0), (0, 1, 0)), ((0, 0, -1), (-1, 0, 0), (0, 1, 0)), ((-1, 0, 0), (0, 0, 1), (0, 1, 0)),
+        ((1, 0, 0), (0, 0, -1), (0, 1, 0)), ((0, 1, 0), (1, 0, 0), (0, 0, -1)), ((0, -1, 0), (1, 0, 0), (0, 0, 1)),
+    ]
+    half = np.array([sx, sy, sz]) / 2
+    pos, uv, nrm, tan, bit, idx = [], [], [], [], [], []
+    for k, (n, t, b) in enumerate(faces):
+        n, t, b = (np.array(v, np.float64) for v in (n, t, b))
+        for (a, c), (u, v) in zip(((-1, -1), (1, -1), (1, 1), (-1, 1)), ((0, 1), (1, 1), (1, 0), (0, 0))):
+            pos.append((n + a * t + c * b) * half)
+            uv.append((u, v))
+            nrm.append(n), tan.append(t), bit.append(b)
+        idx += [4 * k + i for i in (0, 1, 2, 2, 3, 0)]
+    return _vertices(np.array(pos), np.array(uv), np.array(nrm), np.array(tan), np.array(bit)), np.array(idx, np.uint32)
+
+
+def lathe(profile: np.ndarray, segments: int, uv_scale=(1.0, 1.0)):
+    """Surface of revolution around +y of a profile [(radius, y), ...] (bottom to top)."""
+    profile = np.asarray(profile, np.float64)
+    rings = len(profile)
+    d = np.gradient(profile, axis=0)
+    d /= np.maximum(np.linalg.norm(d, axis=1, keepdims=True), 1e-12)
+    theta = np.linspace(0, 2 * np.pi, segments + 1)
+    c, s = np.cos(theta), np.sin(theta)
+    r, y = profile[:, 0][:, None], profile[:, 1][:, None]
+    pos = np.stack([r * c, np.broadcast_to(y, (rings, segments + 1)), r * s], -1)
+    # outward normal of the profile curve: (dy, -dr) rotated around the axis
+    nr, ny = d[:, 1][:, None], -d[:, 0][:, None]
+    nrm = np.stack([nr * c, np.broadcast_to(ny, (rings, segments + 1)), nr * s], -1)
+    tan = np.stack([-s, np.zeros_like(s), c], -1)[None].repeat(rings, 0)
+    bit = np.stack([d[:, 0][:, None] * c, np.broadcast_to(d[:, 1][:, None], (rings, segments + 1)), d[:, 0][:, None] * s], -1)
+    arc = np.concatenate([[0], np.cumsum(np.linalg.norm(np.diff(profile, axis=0), axis=1))])
+    arc /= max(arc[-1], 1e-12)
+    uv = np.stack([np.broadcast_to(theta / (2 * np.pi) * uv_scale[0], (rings, segments + 1)),
+                   np.broadcast_to((1 - arc)[:, None] * uv_scale[1], (rings, segments + 1))], -1)
+    i = (np.arange(rings - 1)[:, None] * (segments + 1) + np.arange(segments)[None, :]).reshape(-1)
+    idx = np.stack([i, i + segments + 1, i + segments + 2, i + segments + 2, i + 1, i], -1).reshape(-1)
+    flat = lambda a: a.reshape(-1, a.shape[-1])
+    return _vertices(flat(pos), flat(uv), flat(nrm), flat(tan), flat(bit)), idx.astype(np.uint32)
+
+
+def sphere(radius=1.0, segments=32, rings=16):
+    phi = np.linspace(-np.pi / 2, np.pi / 2, rings + 1)
+    return lathe(np.stack([radius * np.cos(phi), radius * np.sin(phi)], -1), segments)
+
+
+# ---------------------------------------------------------------------------------------------
+# procedural textures
+# ---------------------------------------------------------------------------------------------
+def value_noise(rs: np.random.Generator, size: int, octaves: int = 5, base: int = 4) -> np.ndarray:
+    """Tileable fractal value noise in [0, 1], (size, size) float32."""
+    out = np.zeros((size, size), np.float64)
+    amp, total = 1.0, 0.0
+    for o in range(octaves):
+        n = base << o
+        if n > size:
+            break
+        lattice = rs.uniform(0, 1, (n, n))
+        t = np.arange(size) * (n / size)
+        i0 = np.floor(t).astype(int)
+        f = t - i0
+        f = f * f * (3 - 2 * f)
+        i1 = (i0 + 1) % n
+        rows = lattice[i0][:, i0] * (1 - f)[None, :] + lattice[i0][:, i1] * f[None, :]
+        rows1 = lattice[i1][:, i0] * (1 - f)[None, :] + lattice[i1][:, i1] * f[None, :]
+        out += amp * (rows * (1 - f)[:, None] + rows1 * f[:, None])
+        total += amp
+        amp *= 0.5
+    return (out / total).astype(F)
+
+
+def rgba8(r, g, b, a=None) -> np.ndarray:
+    a = np.ones_like(r) if a is None else a
+    return (np.clip(np.stack([r, g, b, a], -1), 0, 1) * 255 + 0.5).astype(np.uint8)
+
+
+def normal_map_from_height(h: np.ndarray, strength: float) -> np.ndarray:
+    dx = (np.roll(h, -1, 1) - np.roll(h, 1, 1)) * strength
+    dy = (np.roll(h, -1, 0) - np.roll(h, 1, 0)) * strength
+    n = np.stack([-dx, -dy, np.ones_like(h)], -1)
+    n /= np.linalg.norm(n, axis=-1, keepdims=True)
+    return rgba8(n[..., 0] * 0.5 + 0.5, n[..., 1] * 0.5 + 0.5, n[..., 2] * 0.5 + 0.5)
+
+
+# ---------------------------------------------------------------------------------------------
+# scenes
+# ---------------------------------------------------------------------------------------------
+def feature_scene(seed: int = 1234, width: int = 160, height: int = 120, texture_size: int = 64) -> sc.SceneData:
+    """A few hundred triangles exercising every branch of the hot path (see module docstring)."""
+    rs = np.random.default_rng(seed)
+    b = SceneBuilder()
+    n = texture_size
+    noise = value_noise(rs, n, 4)
+    checker = ((np.indices((n, n)).sum(0) // (n // 8)) % 2).astype(F)
+    color_tex = b.add_texture(rgba8(0.2 + 0.6 * noise, 0.3 + 0.5 * checker, 0.8 - 0.5 * noise), srgb=True)
+    normal_tex = b.add_texture(normal_map_from_height(noise, 4.0), srgb=False)
+    orm_tex = b.add_texture(rgba8(np.ones_like(noise), 0.2 + 0.8 * noise, checker), srgb=False)
+    # leaf card: binary alpha from thresholded noise, plus a soft band of 0 < a < 1 and RGB zeroed where a == 0
+    # like the reference's importer does (TextureImporter.cpp:24-51)
+    alpha = np.clip((noise - 0.45) * 8, 0, 1)
+    leaf = rgba8(0.1 + 0.2 * noise, 0.5 + 0.4 * noise, 0.1 * np.ones_like(noise), alpha)
+    leaf[leaf[..., 3] == 0, :3] = 0
+    leaf_tex = b.add_texture(leaf, srgb=True)
+    emissive_tex = b.add_texture(rgba8(checker, 0.5 * checker, 0.1 * checker), srgb=True)
+    spec_tex = b.add_texture(rgba8(0.3 + 0.5 * noise, 0.3 + 0.5 * noise, 0.3 + 0.5 * noise, 0.3 + 0.6 * checker), srgb=True)
+
+    m_floor = b.add_material_mr(color=(0.9, 0.9, 0.9, 1), roughness=0.8, color_idx=color_tex, normal_idx=normal_tex,
+                                roughness_idx=orm_tex, metallic_idx=orm_tex, metalness=0.6)
+    m_red = b.add_material_mr(color=(0.8, 0.1, 0.1, 1), roughness=0.4)
+    m_gold = b.add_material_mr(color=(1.0, 0.77, 0.34, 1), roughness=0.25, metalness=1.0)
+    m_glass = b.add_material_mr(color=(0.9, 0.95, 1.0, 1), roughness=0.05, transmission=1.0, ior=1.5,
+                                attenuation_color=(0.6, 0.9, 0.7), attenuation_distance=0.8)
+    m_lamp = b.add_material_mr(color=(1, 1, 1, 1), emissive=(1.0, 0.9, 0.7), emissive_intensity=6.0, emissive_idx=emissive_tex)
+    m_leaf = b.add_material_mr(color=(1, 1, 1, 1), roughness=0.7, color_idx=leaf_tex)
+    m_sg = b.add_material_sg(color=(0.5, 0.5, 0.9, 1), specular=(0.9, 0.8, 0.7), glossiness=0.8, specular_idx=spec_tex,
+                             glossiness_idx=spec_tex)
+    m_phong = b.add_material_phong(color=(0.3, 0.8, 0.4, 1), specular=(0.5, 0.5, 0.5), shininess=0.6, shininess_idx=spec_tex)
+
+    g_floor = b.add_geometry(*grid(6, 6, 8, 8, uv_scale=3.0, height=lambda x, z: 0.15 * np.sin(1.3 * x) * np.cos(0.9 * z)))
+    g_box = b.add_geometry(*box(1, 1, 1))
+    g_sphere = b.add_geometry(*sphere(0.5, 20, 10))
+    g_card = b.add_geometry(*quad(1.5, 1.5), is_opaque=False)
+    g_lamp = b.add_geometry(*quad(1.0, 1.0))
+    vase_profile = [(0.25, 0.0), (0.4, 0.2), (0.3, 0.6), (0.15, 0.9), (0.25, 1.1)]
+    g_vase = b.add_geometry(*lathe(vase_profile, 16))
+
+    floor = b.add_model([(g_floor, m_floor, None)])
+    # one model with two meshes, the second with a non-identity mesh transform (BLAS-baked transform)
+    stack = b.add_model([(g_box, m_red, None), (g_sphere, m_gold, translate(0, 0.95, 0) @ scale(1.0, 0.8, 1.0))])
+    glass = b.add_model([(g_sphere, m_glass, None)])
+    vase = b.add_model([(g_vase, m_sg, None)])
+    blob = b.add_model([(g_sphere, m_phong, scale(1.2, 0.6, 1.2))])
+    cards = b.add_model([(g_card, m_leaf, rotate_x(90)), (g_card, m_leaf, translate(0.3, 0, 0.4) @ rotate_x(90) @ rotate_y(40))])
+    lamp = b.add_model([(g_lamp, m_lamp, None)])
+
+    b.add_instance(floor)
+    b.add_instance(stack, translate(-1.6, 0.65, 0.8) @ rotate_y(30))
+    b.add_instance(stack, translate(1.9, 0.45, 1.4) @ rotate_y(-50) @ scale(0.7, 0.7, 0.7))
+    b.add_instance(glass, translate(0.2, 0.75, -0.3) @ scale(1.3, 1.3, 1.3))
+    b.add_instance(vase, translate(-0.4, 0.1, 1.9))
+    b.add_instance(blob, translate(1.4, 0.5, -1.2))
+    b.add_instance(cards, translate(-1.0, 1.0, -1.6))
+    b.add_instance(cards, translate(2.2, 1.0, -0.4) @ rotate_y(70) @ scale(0.8, 1.1, 0.8))
+    b.add_instance(lamp, translate(0, 3.2, 0) @ rotate_x(180))
+
+    b.add_light((6.0, 5.0, 4.0), (-2.5, 2.5, 2.0), 1.0, 0.1, 0.3)
+    b.add_light((2.0, 3.0, 6.0), (2.5, 1.8, -2.0), 1.0, 0.0, 0.5)
+    b.set_directional_light((2.5, 2.4, 2.2), (-0.4, -1.0, -0.2))
+    eye = np.array([0.3, 2.2, 5.2])
+    cam = camera_matrices(eye, np.array([0, 0.6, 0]) - eye, width, height, fov_deg=50)
+    return b.build(cam, (width, height))
+
+
+# chess-piece profiles: (radius, height) pairs, unit = one board square
+_PIECES = {
+    "pawn": [(0.0, 0.0), (0.30, 0.0), (0.32, 0.05), (0.26, 0.12), (0.14, 0.22), (0.11, 0.42), (0.17, 0.47), (0.11, 0.52),
+             (0.16, 0.60), (0.18, 0.70), (0.13, 0.80), (0.0, 0.84)],
+    "rook": [(0.0, 0.0), (0.34, 0.0), (0.36, 0.06), (0.28, 0.14), (0.20, 0.30), (0.19, 0.62), (0.27, 0.68), (0.28, 0.90),
+             (0.20, 0.90), (0.20, 0.82), (0.0, 0.82)],
+    "knight": [(0.0, 0.0), (0.34, 0.0), (0.36, 0.06), (0.27, 0.15), (0.18, 0.30), (0.22, 0.55), (0.27, 0.75), (0.20, 0.95),
+               (0.10, 1.05), (0.0, 1.08)],
+    "bishop": [(0.0, 0.0), (0.33, 0.0), (0.35, 0.06), (0.26, 0.15), (0.13, 0.32), (0.10, 0.68), (0.19, 0.74), (0.10, 0.80),
+               (0.15, 0.95), (0.10, 1.10), (0.04, 1.18), (0.06, 1.22), (0.0, 1.26)],
+    "queen": [(0.0, 0.0), (0.36, 0.0), (0.38, 0.07), (0.28, 0.17), (0.14, 0.38), (0.11, 0.85), (0.22, 0.92), (0.12, 0.98),
+              (0.20, 1.20), (0.24, 1.30), (0.12, 1.32), (0.07, 1.40), (0.0, 1.44)],
+    "king": [(0.0, 0.0), (0.37, 0.0), (0.39, 0.07), (0.29, 0.17), (0.15, 0.40), (0.12, 0.92), (0.23, 0.99), (0.13, 1.05),
+             (0.19, 1.30), (0.22, 1.40), (0.08, 1.42), (0.05, 1.58), (0.0, 1.60)],
+}
+
+
+def _refine_profile(profile, rings):
+    """Resamples a piecewise-linear profile to `rings` points with a little smoothing."""
+    p = np.asarray(profile, np.float64)
+    arc = np.concatenate([[0], np.cumsum(np.linalg.norm(np.diff(p, axis=0), axis=1))])
+    t = np.linspace(0, arc[-1], rings)
+    out = np.stack([np.interp(t, arc, p[:, 0]), np.interp(t, arc, p[:, 1])], -1)
+    k = np.array([0.25, 0.5, 0.25])
+    sm = out.copy()
+    for c in range(2):
+        sm[1:-1, c] = np.convolve(out[:, c], k, mode="valid")
+    return sm
+
+
+def chess_scene(width: int = 1920, height: int = 1080, segments: int = 192, rings: int = 160, board_tess: int = 256,
+                texture_size: int = 2048, seed: int = 0xAB600D) -> sc.SceneData:
+    """BASELINE.json configs[1] stand-in ("ABeautifulGame-class"; the Khronos asset is not
+    available offline, so every number here is declared by this builder, not by the asset).
+
+    Defaults: 6 piece types turned on a lathe with `segments` x `rings` tessellation
+    (2 * 192 * 159 = 61,056 triangles each), 32 piece instances, a 256 x 256-cell displaced board
+    top (131,072 triangles), a frame of 4 boxes and a ground quad:
+        32 * 61,056 + 131,072 + 48 + 2 = 2,084,914 instanced triangles, 15 metallic-roughness
+    materials (rough dielectrics, glossy lacquer, brass / steel metals, two transmissive glass
+    sets with volume attenuation), seven 2048^2 RGBA8 textures (colour sRGB, normal, ORM) from
+    fixed-seed value noise, a directional sun plus 4 point lights and the constant sky."""
+    rs = np.random.default_rng(seed)
+    b = SceneBuilder()
+    n = texture_size
+
+    wood = value_noise(rs, n, 6, 4)
+    grain = 0.5 + 0.5 * np.sin((np.arange(n)[None, :] / n * 40 + wood * 6) * 2 * np.pi)
+    squares = ((np.indices((n, n)) // (n // 8)).sum(0) % 2).astype(F)
+    light_sq = np.stack([0.80 + 0.1 * grain, 0.68 + 0.1 * grain, 0.45 + 0.1 * grain], -1)
+    dark_sq = np.stack([0.22 + 0.08 * grain, 0.12 + 0.05 * grain, 0.07 + 0.03 * grain], -1)
+    board_rgb = light_sq * squares[..., None] + dark_sq * (1 - squares[..., None])
+    t_board = b.add_texture(rgba8(board_rgb[..., 0], board_rgb[..., 1], board_rgb[..., 2]), srgb=True)
+    t_board_n = b.add_texture(normal_map_from_height(grain * 0.3 + wood, 6.0), srgb=False)
+    t_board_orm = b.add_texture(rgba8(np.ones_like(wood), 0.25 + 0.35 * wood, np.zeros_like(wood)), srgb=False)
+    marble = value_noise(rs, n, 7, 2)
+    veins = np.abs(np.sin((marble * 5 + np.arange(n)[:, None] / n * 3) * np.pi)) ** 0.4
+    t_white = b.add_texture(rgba8(0.92 * veins + 0.05, 0.90 * veins + 0.05, 0.84 * veins + 0.05), srgb=True)
+    t_black = b.add_texture(rgba8(0.10 + 0.1 * (1 - veins), 0.10 + 0.09 * (1 - veins), 0.11 + 0.1 * (1 - veins)), srgb=True)
+    t_piece_n = b.add_texture(normal_map_from_height(marble, 3.0), srgb=False)
+    scratches = value_noise(rs, n, 6, 8)
+    t_metal_orm = b.add_texture(rgba8(np.ones_like(scratches), 0.15 + 0.45 * scratches, 0.9 + 0.1 * scratches), srgb=False)
+
+    mats = {
+        "board": b.add_material_mr(roughness=0.9, color_idx=t_board, normal_idx=t_board_n, roughness_idx=t_board_orm),
+        "frame": b.add_material_mr(color=(0.25, 0.14, 0.08, 1), roughness=0.45, normal_idx=t_board_n),
+        "ground": b.add_material_mr(color=(0.55, 0.55, 0.58, 1), roughness=0.85),
+        "white": b.add_material_mr(roughness=0.35, color_idx=t_white, normal_idx=t_piece_n),
+        "white_gloss": b.add_material_mr(color=(0.95, 0.93, 0.88, 1), roughness=0.08, color_idx=t_white),
+        "black": b.add_material_mr(roughness=0.30, color_idx=t_black, normal_idx=t_piece_n),
+        "black_gloss": b.add_material_mr(color=(0.9, 0.9, 0.9, 1), roughness=0.06, color_idx=t_black),
+        "brass": b.add_material_mr(color=(0.95, 0.76, 0.36, 1), roughness=0.6, metalness=1.0, roughness_idx=t_metal_orm,
+                                   metallic_idx=t_metal_orm),
+        "steel": b.add_material_mr(color=(0.77, 0.78, 0.80, 1), roughness=0.5, metalness=1.0, roughness_idx=t_metal_orm,
+                                   metallic_idx=t_metal_orm),
+        "gold": b.add_material_mr(color=(1.0, 0.80, 0.38, 1), roughness=0.18, metalness=1.0),
+        "glass_clear": b.add_material_mr(color=(0.97, 0.98, 1.0, 1), roughness=0.02, transmission=1.0, ior=1.5),
+        "glass_amber": b.add_material_mr(color=(1.0, 0.95, 0.85, 1), roughness=0.04, transmission=1.0, ior=1.52,
+                                         attenuation_color=(0.95, 0.55, 0.15), attenuation_distance=0.6),
+        "glass_smoke": b.add_material_mr(color=(0.9, 0.9, 0.95, 1), roughness=0.12, transmission=0.9, ior=1.45,
+                                         attenuation_color=(0.35, 0.38, 0.45), attenuation_distance=0.5),
+        "rubber": b.add_material_mr(color=(0.05, 0.05, 0.05, 1), roughness=0.95),
+        "lacquer_red": b.add_material_mr(color=(0.65, 0.05, 0.04, 1), roughness=0.12),
+    }
+    assert len(mats) == 15
+
+    geo = {k: b.add_geometry(*lathe(_refine_profile(p, rings), segments, uv_scale=(3.0, 2.0))) for k, p in _PIECES.items()}
+    bump = value_noise(rs, 512, 5, 4).astype(np.float64)
+
+    def board_height(x, z):
+        ix = np.clip(((x / 8 + 0.5) * 511).astype(int), 0, 511)
+        iz = np.clip(((z / 8 + 0.5) * 511).astype(int), 0, 511)
+        return 0.004 * bump[iz, ix]
+
+    g_board = b.add_geometry(*grid(board_tess, board_tess, 8, 8, uv_scale=1.0, height=board_height))
+    g_box = b.add_geometry(*box(1, 1, 1))
+    g_ground = b.add_geometry(*quad(60, 60, uv_scale=10))
+
+    board = b.add_model([
+        (g_board, mats["board"], None),
+        (g_box, mats["frame"], translate(0, -0.15, 4.3) @ scale(9.2, 0.4, 0.6)),
+        (g_box, mats["frame"], translate(0, -0.15, -4.3) @ scale(9.2, 0.4, 0.6)),
+        (g_box, mats["frame"], translate(4.3, -0.15, 0) @ scale(0.6, 0.4, 8.0)),
+        (g_box, mats["frame"], translate(-4.3, -0.15, 0) @ scale(0.6, 0.4, 8.0)),
+    ])
+    b.add_instance(board)
+    b.add_instance(b.add_model([(g_ground, mats["ground"], None)]), translate(0, -0.36, 0))
+
+    # one model per (piece type, material): the piece body plus nothing else, instanced per square
+    def piece_model(kind, material):
+        return b.add_model([(geo[kind], mats[material], None)])
+
+    back = ["rook", "knight", "bishop", "queen", "king", "bishop", "knight", "rook"]
+    white_special = {2: "glass_clear", 5: "glass_amber", 3: "gold", 0: "white_gloss", 7: "white_gloss"}
+    black_special = {2: "glass_smoke", 5: "glass_smoke", 3: "steel", 4: "brass", 1: "lacquer_red", 6: "black_gloss"}
+    models = {}
+
+    def get(kind, material):
+        if (kind, material) not in models:
+            models[(kind, material)] = piece_model(kind, material)
+        return models[(kind, material)]
+
+    def square(file, rank):
+        return (file - 3.5, 0.004, rank - 3.5)
+
+    for f in range(8):
+        jitter = rs.uniform(-0.06, 0.06, (4, 2))
+        spin = rs.uniform(0, 360, 4)
+        x, y, z = square(f, 0)
+        b.add_instance(get(back[f], white_special.get(f, "white")), translate(x + jitter[0, 0], y, z + jitter[0, 1]) @ rotate_y(spin[0]))
+        x, y, z = square(f, 1)
+        b.add_instance(get("pawn", "white" if f % 3 else "white_gloss"), translate(x + jitter[1, 0], y, z + jitter[1, 1]) @ rotate_y(spin[1]))
+        x, y, z = square(f, 6 if f != 4 else 4)  # one advanced pawn
+        b.add_instance(get("pawn", "black" if f % 2 else "rubber"), translate(x + jitter[2, 0], y, z + jitter[2, 1]) @ rotate_y(spin[2]))
+        x, y, z = square(f, 7)
+        b.add_instance(get(back[f], black_special.get(f, "black")), translate(x + jitter[3, 0], y, z + jitter[3, 1]) @ rotate_y(spin[3]))
+
+    b.set_directional_light((3.2, 3.0, 2.7), (-0.45, -1.0, -0.35))
+    b.add_light((9.0, 7.0, 5.0), (-5.0, 3.0, 4.0), 1.0, 0.05, 0.08)
+    b.add_light((4.0, 6.0, 9.0), (5.5, 2.5, -3.0), 1.0, 0.05, 0.10)
+    b.add_light((6.0, 6.0, 6.0), (0.0, 5.0, 0.0), 1.0, 0.0, 0.12)
+    b.add_light((5.0, 3.0, 2.0), (3.0, 1.2, 5.0), 1.0, 0.1, 0.2)
+    eye = np.array([5.6, 4.2, -7.4])
+    cam = camera_matrices(eye, np.array([0.2, 0.3, 0.2]) - eye, width, height, fov_deg=38)
+    return b.build(cam, (width, height))

@@ -1,0 +1,174 @@
+"""Full hot path on the GPU vs the oracle, same scenes, cameras and (pixel, sample) seeds."""
+import importlib
+
+import numpy as np
+import pytest
+
+import conftest
+import metrics
+
+pytestmark = pytest.mark.gpu
+sc = conftest.pkg.scene
+scenes = importlib.import_module("path-tracing_b200.scenes")
+
+
+def test_default_scene_config0(default_renderer, default_oracle, default_scene):
+    """BASELINE.json configs[0]: Default scene 512x512, 16 spp (TotalSamples 0..15), depth 8."""
+    p = default_scene.default_params(bounce_count=8)
+    r = default_renderer
+    r.on_resize(512, 512)
+    r.render(16, params=p)
+    img = r.read_accumulation()
+    st = r.stats()
+    ref, cnt = default_oracle.render(p, 512, 512, 0, 16)
+    assert np.isfinite(img).all() and (img[..., 3] == 1).all()
+    # per-pixel: a path is a chaotic function of its inputs, so a 1-ulp difference can send a
+    # few paths elsewhere; the overwhelming majority of pixels must agree to 1e-4
+    assert metrics.close_fraction(img, ref, 1e-4) > 0.995
+    # image-level bars of BASELINE.md §5 at matched spp
+    assert metrics.rel_mse(img / 16, ref / 16) <= 1e-3
+    assert metrics.flip_lite(img / 16, ref / 16) <= 5e-3
+    assert abs(img[..., :3].mean() - ref[..., :3].mean()) <= 1e-3 * ref[..., :3].mean()
+    # same work: ray and sample counts agree to a handful of diverged paths
+    assert st["samples"] == cnt["samples"] == 512 * 512 * 16
+    assert abs(st["rays_closest"] - cnt["rays_closest"]) <= 1e-4 * cnt["rays_closest"]
+    assert abs(st["hits"] - cnt["hits"]) <= 1e-4 * cnt["hits"]
+
+
+def test_incremental_equals_batch_and_is_deterministic(default_renderer, default_scene):
+    """16 frames of 1 sample == one call of 16 samples; reruns are bit-identical."""
+    p = default_scene.default_params()
+    r = default_renderer
+    r.on_resize(256, 256)
+    r.render(6, params=p)
+    a = r.read_accumulation().copy()
+    r.on_resize(256, 256)
+    for _ in range(6):
+        r.render(1, params=p)
+    b = r.read_accumulation().copy()
+    assert r.total_samples == 6
+    assert (a == b).all()
+    r.on_resize(256, 256)
+    r.render(4, params=p)
+    r.render(2, params=p)
+    assert (r.read_accumulation() == a).all()
+
+
+def test_tiles_are_bit_identical_to_full_frame(default_renderer, default_scene):
+    """Image-tile partitioning (multi-GPU) uses global pixel coordinates for the RNG."""
+    p = default_scene.default_params()
+    r = default_renderer
+    r.on_resize(200, 120)
+    r.render(3, params=p)
+    full = r.read_accumulation().copy()
+    r.on_resize(200, 120)
+    tiles = np.array([(0, 0, 200, 37), (0, 37, 99, 120)], sc.TILE)
+    r.render(3, params=p, tiles=tiles, first_sample=0)
+    part = r.read_accumulation().copy()
+    inside = np.zeros((120, 200), bool)
+    inside[:37] = True
+    inside[37:, :99] = True
+    assert (part[inside] == full[inside]).all()
+    assert (part[~inside] == 0).all()
+    r.render(3, params=p, tiles=np.array([(99, 37, 200, 120)], sc.TILE), first_sample=0)
+    assert (r.read_accumulation() == full).all()
+
+
+def test_sample_slices_sum_to_full(default_renderer, default_scene):
+    """Sample-sliced partitioning: [0,3) + [3,8) == [0,8) up to fp32 summation order."""
+    p = default_scene.default_params()
+    r = default_renderer
+    r.on_resize(128, 128)
+    r.render(8, params=p)
+    full = r.read_accumulation().copy()
+    r.on_resize(128, 128)
+    r.render(3, params=p, first_sample=0)
+    a = r.read_accumulation().copy()
+    r.on_resize(128, 128)
+    r.render(5, params=p, first_sample=3)
+    b = r.read_accumulation().copy()
+    assert np.allclose(a[..., :3] + b[..., :3], full[..., :3], rtol=1e-6, atol=1e-6)
+
+
+@pytest.fixture(scope="module")
+def feature(oracle_mod):
+    s = scenes.feature_scene()
+    r = conftest.core.Renderer(0)
+    r.update_scene_data(s)
+    yield s, r, oracle_mod.OracleScene(s)
+    r.close()
+
+
+@pytest.mark.parametrize("lens", [0.0, 0.08])
+def test_feature_scene(feature, lens):
+    """Every material model, textures + mips, alpha-tested decals, transmission with volume
+    attenuation, point + directional NEE with shadow rays, thin lens."""
+    s, r, o = feature
+    p = s.default_params(bounce_count=6)
+    p.lens_radius, p.focal_distance = lens, 5.0
+    W, H, spp = 160, 120, 32
+    r.on_resize(W, H)
+    r.render(spp, params=p)
+    img = r.read_accumulation()
+    st = r.stats()
+    ref, cnt = o.render(p, W, H, 0, spp)
+    assert np.isfinite(img).all()
+    assert st["rays_shadow"] > 0 and cnt["alpha_tests_closest"] > 0
+    assert metrics.close_fraction(img, ref, 1e-3) > 0.97
+    assert metrics.rel_mse(img / spp, ref / spp) <= 1e-3
+    assert metrics.flip_lite(img / spp, ref / spp) <= 5e-3
+    assert abs(st["rays_closest"] - cnt["rays_closest"]) <= 2e-3 * cnt["rays_closest"]
+    # the core skips occlusion queries whose contribution is exactly zero, the oracle traces them
+    assert st["rays_shadow"] <= cnt["rays_shadow"]
+
+
+def test_traversal_stats_toggle(feature):
+    s, r, _ = feature
+    p = s.default_params(bounce_count=4)
+    r.on_resize(64, 48)
+    r.set_traversal_stats(True)
+    r.render(2, params=p)
+    a, st = r.read_accumulation().copy(), r.stats()
+    r.set_traversal_stats(False)
+    r.on_resize(64, 48)
+    r.render(2, params=p)
+    assert (r.read_accumulation() == a).all()  # counting does not change the image
+    assert st["box_tests"] > st["tri_tests"] > 0 and st["alpha_tests"] > 0
+    assert r.stats()["box_tests"] == 0
+
+
+def test_skybox_2d(oracle_mod):
+    b = scenes.SceneBuilder()
+    rs = np.random.default_rng(31)
+    sky = (rs.uniform(0, 4, (32, 64, 4))).astype(np.float32)
+    b.set_skybox_2d(sky)
+    g = b.add_geometry(*scenes.sphere(1.0, 24, 12))
+    b.add_instance(b.add_model([(g, b.add_material_mr(color=(0.9, 0.9, 0.9, 1), roughness=0.1, metalness=1.0), None)]))
+    b.set_directional_light((0, 0, 0), (0, -1, 0))
+    s = b.build(scenes.camera_matrices((0, 0.5, -4), (0, -0.1, 1), 96, 64, fov_deg=60), (96, 64))
+    o = oracle_mod.OracleScene(s)
+    with conftest.core.Renderer(0) as r:
+        r.update_scene_data(s)
+        r.on_resize(96, 64)
+        p = s.default_params(4)
+        assert p.miss_flags == sc.MISS_FLAGS_SKYBOX_2D
+        r.render(8, params=p)
+        img = r.read_accumulation()
+        ref, _ = o.render(p, 96, 64, 0, 8)
+        assert metrics.close_fraction(img, ref, 1e-3) > 0.98
+        assert metrics.rel_mse(img / 8, ref / 8) <= 1e-3
+
+
+def test_errors(default_scene):
+    core = conftest.core
+    with core.Renderer(0) as r:
+        with pytest.raises(core.PtError) as e:
+            r.on_resize(4, 4)
+            r.render(1, params=default_scene.default_params())
+        assert e.value.status == -5  # PT_ERR_NO_SCENE
+        r.update_scene_data(default_scene)
+        bad = default_scene.default_params(bounce_count=0)
+        with pytest.raises(core.PtError):
+            r.render(1, params=bad)
+    with pytest.raises(core.PtError):
+        core.Renderer(99)

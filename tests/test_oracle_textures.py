@@ -1,0 +1,76 @@
+"""The oracle's sampler definition: mip chain (floor(log2(max)) + 1 levels, linear-blit
+down-sampling, Image.cpp:14-17,264-305), sRGB decode, repeat addressing, textureGrad LOD."""
+import numpy as np
+
+import conftest
+
+sc = conftest.pkg.scene
+
+
+def srgb_to_linear(c):
+    c = c / 255.0
+    return np.where(c <= 0.04045, c / 12.92, ((c + 0.055) / 1.055) ** 2.4)
+
+
+def test_default_textures(default_oracle):
+    assert default_oracle.texture_info(0) == (1, 1, 1)
+    assert (default_oracle.texture_level(1, 0) == [0x80, 0x80, 0xFF, 0xFF]).all()  # Q10: (128,128,255)/255
+    n = default_oracle.texture_sample(1, [[0.3, 0.7, 0.1, 0, 0, 0.1]])
+    assert np.allclose(n, [[128 / 255, 128 / 255, 1, 1]])
+    assert np.allclose(default_oracle.texture_sample(4, [[0, 0, 0, 0, 0, 0]]), 0)
+
+
+def test_mip_chain_shapes(default_oracle, default_scene):
+    for i, tex in enumerate(default_scene.textures):
+        w, h, levels = default_oracle.texture_info(sc.SCENE_TEXTURE_OFFSET + i)
+        assert (h, w) == tex.pixels.shape[:2]
+        assert levels == int(np.floor(np.log2(max(w, h)))) + 1
+    # 2024 -> 1012 -> 506 -> 253 -> 126 ... (truncating halving, non-power-of-two)
+    slot = sc.SCENE_TEXTURE_OFFSET + 3
+    assert default_oracle.texture_level(slot, 3).shape[:2] == (253, 253)
+    assert default_oracle.texture_level(slot, 4).shape[:2] == (126, 126)
+    assert default_oracle.texture_level(slot, 10).shape[:2] == (1, 1)
+
+
+def test_power_of_two_mip_is_box_filter_in_linear_space(default_oracle, default_scene):
+    slot = sc.SCENE_TEXTURE_OFFSET + 1  # 512x512 sRGB colour texture
+    l0 = default_oracle.texture_level(slot, 0).astype(np.float64)
+    l1 = default_oracle.texture_level(slot, 1).astype(np.float64)
+    assert (l0 == default_scene.textures[1].pixels).all()
+    lin = srgb_to_linear(l0[..., :3])
+    box = (lin[0::2, 0::2] + lin[1::2, 0::2] + lin[0::2, 1::2] + lin[1::2, 1::2]) / 4
+    back = srgb_to_linear(l1[..., :3])
+    # re-quantised to 8-bit sRGB: within one code of the exact box filter
+    lo, hi = srgb_to_linear(np.maximum(l1[..., :3] - 1, 0)), srgb_to_linear(np.minimum(l1[..., :3] + 1, 255))
+    assert ((box >= lo - 1e-9) & (box <= hi + 1e-9)).all() and np.abs(back - box).max() < 0.01
+    a_box = (l0[0::2, 0::2, 3] + l0[1::2, 0::2, 3] + l0[0::2, 1::2, 3] + l0[1::2, 1::2, 3]) / 4
+    assert np.abs(l1[..., 3] - a_box).max() <= 0.5 + 1e-9
+
+
+def test_bilinear_and_repeat(default_oracle, default_scene):
+    slot = sc.SCENE_TEXTURE_OFFSET + 1
+    px = default_scene.textures[1].pixels
+    W = px.shape[1]
+    # texel centres reproduce the texel
+    u, v = (17 + 0.5) / W, (33 + 0.5) / W
+    got = default_oracle.texture_sample(slot, [[u, v, 0, 0, 0, 0]], use_grad=False)[0]
+    want = np.concatenate([srgb_to_linear(px[33, 17, :3].astype(np.float64)), [px[33, 17, 3] / 255]])
+    assert np.allclose(got, want, atol=1e-6)
+    # repeat addressing: u and u + 3, v and v - 2 agree
+    a = default_oracle.texture_sample(slot, [[0.123, 0.456, 0, 0, 0, 0]], use_grad=False)
+    b = default_oracle.texture_sample(slot, [[3.123, -1.544, 0, 0, 0, 0]], use_grad=False)
+    assert np.allclose(a, b, atol=1e-5)
+
+
+def test_texture_grad_lod_selection(default_oracle):
+    slot = sc.SCENE_TEXTURE_OFFSET + 1  # 512^2, 10 levels
+    uv = [0.3, 0.6]
+    mag = default_oracle.texture_sample(slot, [[*uv, 1e-4, 0, 0, 1e-4]])
+    lod0 = default_oracle.texture_sample(slot, [[*uv, 0, 0, 0, 0]], use_grad=False)
+    assert np.allclose(mag, lod0)  # rho < 1 texel: magnification
+    coarse = default_oracle.texture_sample(slot, [[*uv, 10.0, 0, 0, 10.0]])
+    top = default_oracle.texture_level(slot, 9).astype(np.float64)[0, 0]
+    assert np.allclose(coarse[0, :3], srgb_to_linear(top[:3]), atol=1e-6)
+    # NaN / Inf derivatives fall back to level 0 (derivative clamp in tracing.glsl lets NaN through)
+    nan = default_oracle.texture_sample(slot, [[*uv, np.nan, 0, 0, 0]])
+    assert np.allclose(nan, lod0)
