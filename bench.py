@@ -1,0 +1,444 @@
+#!/usr/bin/env python
+"""Benchmark of the path-tracing hot path (BASELINE.json metric: Mrays/s and path samples/s at
+1080p, depth 8).
+
+    python bench.py --gpus N --steps K --warmup W            # our CUDA core
+    python bench.py --impl reference --gpus N --steps K ...   # CPU oracle on the host cores
+
+One STEP = one render of the workload (configs[1]: the ABeautifulGame-class chess scene,
+1920x1080, `--spp` samples per pixel, depth 8) through `pt_render_samples`, plus — for N > 1 —
+the sum-reduce of the float4 accumulation buffer onto rank 0.
+
+  value  : Mrays/s (closest-hit + occlusion queries of all ranks) over the device time of the
+           step: CUDA events recorded by the library on its launching stream around the
+           wavefront loop, plus torch CUDA events around the NCCL reduce; max over ranks.
+  e2e    : the same metric over wall time of the public call sequence with HOST buffers:
+           pt_render_samples (parameters cross host->device) + reduce + pt_readback of the
+           accumulation image into pinned host memory.
+  roofline: HBM; algorithmic bytes of the dominant kernel (SURVEY §8d formula with the measured
+           N_box / N_tri / N_texel of this very run) / its CUDA-event duration.
+  cpu_baseline: the CPU oracle (port of the reference's shaders) on a bounded tile of the same
+           workload, all host threads.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes
+import importlib
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "Mrays/s (closest-hit + occlusion rays; path samples/s alongside), 1080p, depth 8"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--spp", type=int, default=256, help="samples per pixel of one step (configs[1]: 256)")
+    ap.add_argument("--width", type=int, default=1920)
+    ap.add_argument("--height", type=int, default=1080)
+    ap.add_argument("--bounces", type=int, default=8)
+    ap.add_argument("--partition", default="samples", choices=["tiles", "samples"],
+                    help="samples (default, weak scaling): rank g renders samples [g*spp, (g+1)*spp) of the whole frame; "
+                         "tiles (strong scaling): the frame's row blocks are dealt to the ranks, spp is the total")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--small", action="store_true", help="reduced tessellation (debugging only; reported in config)")
+    return ap.parse_args()
+
+
+def build_scene(args):
+    scenes = importlib.import_module("path-tracing_b200.scenes")
+    if args.small:
+        return scenes.chess_scene(args.width, args.height, segments=48, rings=40, board_tess=32, texture_size=256), "chess_scene(small)"
+    return scenes.chess_scene(args.width, args.height), "chess_scene"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device_index: int):
+        self.proc = None
+        self.lines = []
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={device_index}", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "200"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, smax, power, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.lines:
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) < 8:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                smax.append(float(parts[1]))
+                power.append(float(parts[2]))
+            except ValueError:
+                continue
+            for name, val in zip(names, parts[4:8]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {
+            "sm_mhz": statistics.median(sm) if sm else None,
+            "sm_max_mhz": max(smax) if smax else None,
+            "power_w_max": max(power) if power else None,
+            "samples": len(sm),
+            "reasons": sorted(reasons),
+        }
+
+
+class CudaArray:
+    """Zero-copy view of a device pointer for torch.as_tensor (__cuda_array_interface__)."""
+
+    def __init__(self, ptr: int, shape, typestr="<f4"):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr, "data": (ptr, False), "version": 3}
+
+
+def algorithmic_bytes(st: dict, kernel: str) -> float:
+    """SURVEY §8(d) constants, split per kernel class; counters come from a stats run of the same
+    (deterministic) workload."""
+    rc, rs, hits, samples = st["rays_closest"], st["rays_shadow"], st["hits"], st["samples"]
+    if kernel == "extend":  # ray in (32 B) + hit out (16 B) + 32 B per box test + 36 B per triangle test
+        return 48.0 * rc + 32.0 * st["box_tests_closest"] + 36.0 * st["tri_tests_closest"] + 184.0 * st["alpha_tests_closest"]
+    if kernel == "shade":  # per hit 384 B geometry/material + 4 B per texel; 288 B path state per bounce
+        return 384.0 * hits + 4.0 * st["texel_fetches"] + 288.0 * rc
+    if kernel == "shadow":
+        return 36.0 * rs + 32.0 * st["box_tests_shadow"] + 36.0 * st["tri_tests_shadow"] + 184.0 * st["alpha_tests_shadow"]
+    if kernel == "finish":  # accumulation read + write per sample
+        return 32.0 * samples
+    raise KeyError(kernel)
+
+
+def load_peak():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        return float(json.load(open(path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def load_traffic():
+    """dram bytes per launch of the dominant kernel from the committed ncu capture, if any."""
+    path = os.path.join(ROOT, "profiles", "traffic.json")
+    try:
+        return json.load(open(path))
+    except Exception:
+        return {}
+
+
+def cpu_baseline(scene, params, args, threads=None, tile=(720, 405, 1200, 675), spp=1):
+    """Times the CPU oracle on a bounded tile of the same frame (default: the central 480x270 pixels,
+    1/16 of the frame, `spp` samples, full depth)."""
+    from oracle import oracle
+
+    threads = threads or os.cpu_count() or 1
+    t0 = time.perf_counter()
+    o = oracle.OracleScene(scene)
+    build_s = time.perf_counter() - t0
+    x0, y0, x1, y1 = (min(tile[0], args.width), min(tile[1], args.height), min(tile[2], args.width), min(tile[3], args.height))
+    tiles = np.array([(x0, y0, x1, y1)], importlib.import_module("path-tracing_b200.scene").TILE)
+    t0 = time.perf_counter()
+    _, cnt = o.render(params, args.width, args.height, 0, spp, tiles=tiles, threads=threads)
+    dt = time.perf_counter() - t0
+    rays = cnt["rays_closest"] + cnt["rays_shadow"]
+    return {
+        "value": rays / dt / 1e6,
+        "unit": "Mrays/s",
+        "samples_per_s": cnt["samples"] / dt,
+        "cores": threads,
+        "kind": "port",
+        "sample": f"CPU restatement of the reference shaders (lavapipe unavailable): pixels [{x0},{x1})x[{y0},{y1}) of the "
+                  f"{args.width}x{args.height} frame, {spp} spp, depth {args.bounces}; {rays} rays in {dt:.2f} s "
+                  f"(+ {build_s:.1f} s CPU SAH BVH build, not counted)",
+        "oracle": o,
+    }
+
+
+def run_reference(args):
+    """--impl reference: the reference semantics on the host CPU (oracle port; the reference's own
+    Vulkan path cannot run: no Vulkan loader / lavapipe / shaderc on the box)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    scene, scene_name = build_scene(args)
+    params = scene.default_params(args.bounces)
+    threads = os.cpu_count() or 1
+    base = cpu_baseline(scene, params, args, threads=threads, spp=1)  # also warms the caches
+    o = base.pop("oracle")
+    sc = importlib.import_module("path-tracing_b200.scene")
+    tiles = np.array([(720, 405, 1200, 675)], sc.TILE)
+    for _ in range(max(0, args.warmup - 1)):
+        o.render(params, args.width, args.height, 0, 1, tiles=tiles, threads=threads)
+    rays = samples = 0
+    t0 = time.perf_counter()
+    for k in range(args.steps):
+        _, cnt = o.render(params, args.width, args.height, k, 1, tiles=tiles, threads=threads)
+        rays += cnt["rays_closest"] + cnt["rays_shadow"]
+        samples += cnt["samples"]
+    dt = time.perf_counter() - t0
+    value = rays / dt / 1e6
+    line = {
+        "impl": "reference",
+        "metric": METRIC,
+        "value": value,
+        "unit": "Mrays/s",
+        "samples_per_s": samples / dt,
+        "n_gpus": args.gpus,
+        "steps": args.steps,
+        "warmup": args.warmup,
+        "ms_per_step": dt / args.steps * 1e3,
+        "higher_is_better": True,
+        "scaling": "weak",
+        "vs_baseline": None,
+        "dtype": "f32",
+        "data": "synthetic",
+        "config": {"workload": f"{scene_name} {args.width}x{args.height} depth {args.bounces}: each step = 1 spp of the central "
+                               "480x270 tile on the host CPU", "triangles": scene.instanced_triangle_count()},
+        "cpu_baseline": {"value": value, "unit": "Mrays/s", "cores": threads, "kind": "port", "sample": base["sample"]},
+        "e2e": {"value": value, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    core = importlib.import_module("path-tracing_b200.core")
+    partition = importlib.import_module("path-tracing_b200.partition")
+    sc = importlib.import_module("path-tracing_b200.scene")
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    assert world == args.gpus or world == 1, f"--gpus {args.gpus} but WORLD_SIZE={world}"
+
+    scene, scene_name = build_scene(args)
+    params = scene.default_params(args.bounces)
+    W, H, spp = args.width, args.height, args.spp
+
+    r = core.Renderer(local_rank)  # raises if the CUDA library / device is missing: no fallback
+    r.update_scene_data(scene)
+    r.on_resize(W, H)
+    build_stats = r.stats()
+
+    ptr, pitch, _ = r.accum_device_ptr()
+    accum_t = torch.as_tensor(CudaArray(ptr, (H, W, 4)), device=torch.device("cuda", local_rank)) if world > 1 else None
+    host_img = torch.empty((H, W, 4), dtype=torch.float32).pin_memory()
+    host_ptr, host_bytes = host_img.data_ptr(), host_img.numel() * 4
+
+    if args.partition == "tiles":  # strong scaling: one frame of `spp` samples, pixels dealt to the ranks
+        tiles = None if world == 1 else partition.row_block_tiles(W, H, rank, world, block_rows=8)
+        first, count = 0, spp
+    else:  # weak scaling: every rank adds its own `spp` samples of the whole frame (world * spp in total)
+        tiles = None
+        first, count = partition.sample_slice(0, spp * world, rank, world)
+
+    def one_step():
+        """Returns (device_ms, e2e_wall_ms, stats) of this rank."""
+        t0 = time.perf_counter()
+        r.on_resize(W, H)  # accumulation reset (a new render)
+        r.render(count, tiles=tiles, params=params, first_sample=first)
+        st = r.stats()
+        dev_ms = st["last_render_ms"]
+        if world > 1:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            partition.reduce_accumulation(accum_t, dst=0)
+            e1.record()
+            e1.synchronize()
+            dev_ms += e0.elapsed_time(e1)
+        r.readback_into(host_ptr, host_bytes)  # D2H of the (reduced) float4 image into pinned memory
+        return dev_ms, (time.perf_counter() - t0) * 1e3, st
+
+    def sync_all():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        one_step()
+
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    sync_all()
+    wall0 = time.perf_counter()
+    dev_ms_total = e2e_ms_total = 0.0
+    launches = rays_c = rays_s = samples = 0
+    for _ in range(args.steps):
+        dev_ms, e2e_ms, st = one_step()
+        dev_ms_total += dev_ms
+        e2e_ms_total += e2e_ms
+        launches += st["kernel_launches"]
+        rays_c, rays_s, samples = rays_c + st["rays_closest"], rays_s + st["rays_shadow"], samples + st["samples"]
+    sync_all()
+    wall_ms = (time.perf_counter() - wall0) * 1e3
+    clocks = sampler.stop() if sampler else None
+
+    # aggregate over ranks: times -> max, work -> sum
+    if world > 1:
+        t = torch.tensor([dev_ms_total, e2e_ms_total, wall_ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dev_ms_total, e2e_ms_total, wall_ms = t.tolist()
+        w = torch.tensor([rays_c, rays_s, samples, launches], dtype=torch.float64, device="cuda")
+        dist.all_reduce(w, op=dist.ReduceOp.SUM)
+        rays_c, rays_s, samples, launches = (int(x) for x in w.tolist())
+
+    # ---- roofline inputs: one stats run + one kernel-timing run of the same workload (rank 0's share)
+    r.set_traversal_stats(True)
+    r.on_resize(W, H)
+    r.render(count, tiles=tiles, params=params, first_sample=first)
+    cst = r.stats()
+    r.set_traversal_stats(False)
+    r.set_kernel_timing(True)
+    r.on_resize(W, H)
+    r.render(count, tiles=tiles, params=params, first_sample=first)
+    tst = r.stats()
+    r.set_kernel_timing(False)
+
+    if rank != 0:
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
+
+    peak, peak_src = load_peak()
+    kernels = {}
+    total_kernel_ms = sum(tst["kernel_ms"].values()) or 1.0
+    for name in core.KERNEL_CLASSES:
+        ms, n = tst["kernel_ms"][name], max(1, tst["kernel_launch_count"][name])
+        nbytes = algorithmic_bytes(cst, name)
+        kernels[name] = {
+            "ms_total": ms,
+            "launches": n,
+            "avg_launch_us": ms / n * 1e3,
+            "share": ms / total_kernel_ms,
+            "algorithmic_bytes_per_launch": nbytes / n,
+            "achieved_gbs": nbytes / (ms * 1e-3) / 1e9 if ms > 0 else None,
+        }
+    dominant = max(kernels, key=lambda k: kernels[k]["ms_total"])
+    traffic = load_traffic().get(dominant)
+    rays_total = rays_c + rays_s
+    per_ray = {
+        "n_box_closest": cst["box_tests_closest"] / max(1, cst["rays_closest"]),
+        "n_tri_closest": cst["tri_tests_closest"] / max(1, cst["rays_closest"]),
+        "n_box_shadow": cst["box_tests_shadow"] / max(1, cst["rays_shadow"]),
+        "n_tri_shadow": cst["tri_tests_shadow"] / max(1, cst["rays_shadow"]),
+        "hit_rate": cst["hits"] / max(1, cst["rays_closest"]),
+        "n_texel_per_hit": cst["texel_fetches"] / max(1, cst["hits"]),
+        "alpha_tests_per_ray": (cst["alpha_tests_closest"] + cst["alpha_tests_shadow"]) / max(1, cst["rays_closest"] + cst["rays_shadow"]),
+        "rays_per_sample": rays_total / max(1, samples),
+    }
+    all_bytes = sum(algorithmic_bytes(cst, k) for k in core.KERNEL_CLASSES)
+
+    line = {
+        "metric": METRIC,
+        "value": rays_total / (dev_ms_total * 1e-3) / 1e6,
+        "unit": "Mrays/s",
+        "samples_per_s": samples / (dev_ms_total * 1e-3),
+        "rays_closest": rays_c,
+        "rays_shadow": rays_s,
+        "samples": samples,
+        "n_gpus": world,
+        "steps": args.steps,
+        "warmup": args.warmup,
+        "ms_per_step": dev_ms_total / args.steps,
+        "wall_ms_per_step": wall_ms / args.steps,
+        "higher_is_better": True,
+        "scaling": "weak" if args.partition == "samples" else "strong",
+        "vs_baseline": None,
+        "dtype": "f32",
+        "data": "synthetic",
+        "config": {
+            "workload": f"{scene_name}: ABeautifulGame-class procedural stand-in, {W}x{H}, "
+                        + (f"{spp} spp per GPU per step ({spp * world} spp per frame)" if args.partition == "samples" else f"{spp} spp per step")
+                        + f", depth {args.bounces}",
+            "triangles": int(build_stats["triangle_count"]),
+            "bvh_nodes": int(build_stats["bvh_node_count"]),
+            "bvh_bytes": int(build_stats["bvh_bytes"]),
+            "materials": int(len(scene.mr_materials)),
+            "textures": len(scene.textures),
+            "partition": "none" if world == 1 else args.partition,
+            "l2": "working set (path state + triangles + BVH + textures, > 1 GB) exceeds the 126 MB L2; no explicit flush",
+            "bvh_build_ms": build_stats["bvh_build_ms"],
+            "scene_upload_ms": build_stats["scene_upload_ms"],
+        },
+        "per_ray": per_ray,
+        "roofline": {
+            "bound": "hbm",
+            "kernel": f"k_{dominant}",
+            "achieved": kernels[dominant]["achieved_gbs"],
+            "peak": peak,
+            "unit": "GB/s",
+            "frac": (kernels[dominant]["achieved_gbs"] or 0.0) / peak,
+            "peak_source": peak_src,
+            "traffic": traffic,
+            "all_kernels_achieved_gbs": all_bytes / (total_kernel_ms * 1e-3) / 1e9,
+            "kernels": kernels,
+        },
+        "e2e": {
+            "value": rays_total / (e2e_ms_total * 1e-3) / 1e6,
+            "unit": "Mrays/s",
+            "ms_per_step": e2e_ms_total / args.steps,
+            "h2d_bytes_per_step": int(params.nbytes()),
+            "d2h_bytes_per_step": int(host_bytes),
+        },
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+    }
+    if not args.no_cpu_baseline:
+        base = cpu_baseline(scene, params, args)
+        base.pop("oracle")
+        line["cpu_baseline"] = base
+    print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

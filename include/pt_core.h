@@ -261,24 +261,39 @@ typedef struct pt_hit {
     float u, v;          /* hitAttributeEXT barycentrics (weights of v1, v2)            */
 } pt_hit;
 
-/* Device counters of the last pt_render_samples / pt_trace_* call plus build info. */
+/* Kernel classes of the wavefront (indices of pt_stats.kernel_ms / kernel_launch_count). */
+enum {
+    PT_KERNEL_EXTEND = 0, /* closest-hit traversal                        */
+    PT_KERNEL_SHADE = 1,  /* miss / closest-hit shading + bounce logic     */
+    PT_KERNEL_SHADOW = 2, /* occlusion traversal                           */
+    PT_KERNEL_FINISH = 3, /* accumulate / restart / regenerate + compaction */
+    PT_KERNEL_CLASS_COUNT = 4
+};
+
+/* Device counters of the last pt_render_samples call plus build info. */
 typedef struct pt_stats {
-    uint64_t rays_closest;    /* closest-hit queries traced (raygen.rgen:68)              */
-    uint64_t rays_shadow;     /* occlusion queries traced (raygen.rgen:31)                 */
-    uint64_t samples;         /* finished iterations of the sample loop (raygen.rgen:42)   */
-    uint64_t hits;            /* closest-hit queries that hit                              */
-    uint64_t box_tests;       /* child AABBs tested (all rays)                             */
-    uint64_t tri_tests;       /* ray-triangle tests (all rays)                             */
-    uint64_t alpha_tests;     /* any-hit alpha evaluations (all rays)                      */
-    uint64_t restarts;        /* NaN/Inf sample restarts (raygen.rgen:99-112)              */
+    uint64_t rays_closest;        /* closest-hit queries traced (raygen.rgen:68)                 */
+    uint64_t rays_shadow;         /* occlusion queries traced (raygen.rgen:31)                    */
+    uint64_t samples;             /* finished iterations of the sample loop (raygen.rgen:42)      */
+    uint64_t hits;                /* closest-hit queries that hit                                 */
+    uint64_t box_tests_closest;   /* child AABBs tested by closest-hit rays   (traversal stats)   */
+    uint64_t tri_tests_closest;   /* ray-triangle tests of closest-hit rays   (traversal stats)   */
+    uint64_t alpha_tests_closest; /* anyhit.rahit evaluations                 (traversal stats)   */
+    uint64_t box_tests_shadow;    /*                                          (traversal stats)   */
+    uint64_t tri_tests_shadow;    /*                                          (traversal stats)   */
+    uint64_t alpha_tests_shadow;  /* occlusionAnyhit.rahit evaluations        (traversal stats)   */
+    uint64_t texel_fetches;       /* texels read by the material fetches      (traversal stats)   */
+    uint64_t restarts;            /* NaN/Inf sample restarts (raygen.rgen:99-112)                 */
     uint64_t wavefront_iterations;
-    uint64_t kernel_launches; /* launches of this library's kernels in the last render call */
-    uint64_t triangle_count;  /* flattened (instanced) triangles in the BVH                */
+    uint64_t kernel_launches;     /* launches of this library's kernels in the last render call   */
+    uint64_t triangle_count;      /* flattened (instanced) triangles in the BVH                   */
     uint64_t bvh_node_count;
     uint64_t bvh_bytes;
     float bvh_build_ms;
     float scene_upload_ms;
-    float last_render_ms;     /* CUDA-event time of the last pt_render_samples             */
+    float last_render_ms;         /* CUDA-event time of the last pt_render_samples                */
+    float kernel_ms[PT_KERNEL_CLASS_COUNT];              /* with pt_set_kernel_timing(1) only     */
+    uint32_t kernel_launch_count[PT_KERNEL_CLASS_COUNT];
 } pt_stats;
 
 /* ------------------------------------------------------------------------- */
@@ -360,11 +375,16 @@ PT_API pt_status pt_trace_occlusion(pt_context *ctx, const pt_ray *rays, uint64_
 
 PT_API pt_status pt_get_stats(pt_context *ctx, pt_stats *out_stats);
 
-/* Enables (1) / disables (0, default) the per-ray box / triangle / alpha test counters of
+/* Enables (1) / disables (0, default) the per-ray box / triangle / alpha / texel counters of
  * pt_stats for subsequent pt_render_samples calls.  Counting costs a few instructions per node,
  * so timed runs leave it off and the roofline's N_box / N_tri come from a second, identical
  * (deterministic) run with it on.  rays / samples / hits are always counted. */
 PT_API pt_status pt_set_traversal_stats(pt_context *ctx, int32_t enable);
+
+/* Enables (1) / disables (0, default) CUDA-event timing of every kernel launch of subsequent
+ * pt_render_samples calls, summed per kernel class into pt_stats.kernel_ms (the per-kernel
+ * durations the roofline is computed from; events are recorded on the launching stream). */
+PT_API pt_status pt_set_kernel_timing(pt_context *ctx, int32_t enable);
 
 /* ------------------------------------------------------------------------- */
 /* shader unit-test entry point                                              */

@@ -1304,6 +1304,16 @@ struct HitInfo
     float decalAlpha = 0.0f;
 };
 
+/* A ray with a NaN/Inf component or a zero direction can never satisfy a triangle test (everything
+ * evaluates to NaN) but would visit every node, NaN defeating the slab test.  refract() == 0 on
+ * total internal reflection followed by normalize() produces exactly such rays (Q12).  Vulkan
+ * leaves non-finite rays undefined; oracle and core both define them as a miss. */
+bool rayCanHit(vec3 org, vec3 dir)
+{
+    const float sum = org.x + org.y + org.z + dir.x + dir.y + dir.z;
+    return std::isfinite(sum) && !(dir.x == 0.0f && dir.y == 0.0f && dir.z == 0.0f);
+}
+
 /* closest hit with the primary any-hit shader.  Ties in t are broken towards the smaller flattened
  * triangle index so that the result does not depend on the BVH (the hardware's choice is
  * implementation-defined). */
@@ -1311,7 +1321,7 @@ HitInfo traceClosest(const pto_scene &s, vec3 org, vec3 dir, float tmin, float t
 {
     HitInfo hit;
     c.rays_closest++;
-    if (s.tris.empty())
+    if (s.tris.empty() || !rayCanHit(org, dir))
         return hit;
     const RayPrep r = prepareRay(org, dir);
     float best = tmax;
@@ -1394,7 +1404,7 @@ HitInfo traceClosest(const pto_scene &s, vec3 org, vec3 dir, float tmin, float t
 bool traceOccluded(const pto_scene &s, vec3 org, vec3 dir, float tmin, float tmax, Counters &c)
 {
     c.rays_shadow++;
-    if (s.tris.empty())
+    if (s.tris.empty() || !rayCanHit(org, dir))
         return false;
     const RayPrep r = prepareRay(org, dir);
     uint32_t stack[128];

@@ -36,6 +36,7 @@ ABI_SYMBOLS = [
     "pt_trace_occlusion",
     "pt_get_stats",
     "pt_set_traversal_stats",
+    "pt_set_kernel_timing",
     "pt_test_input_stride",
     "pt_test_output_stride",
     "pt_test_shading",
@@ -50,15 +51,22 @@ class PtError(RuntimeError):
         self.status = status
 
 
+KERNEL_CLASSES = ("extend", "shade", "shadow", "finish")
+
+
 class Stats(C.Structure):
     _fields_ = [
         ("rays_closest", C.c_uint64),
         ("rays_shadow", C.c_uint64),
         ("samples", C.c_uint64),
         ("hits", C.c_uint64),
-        ("box_tests", C.c_uint64),
-        ("tri_tests", C.c_uint64),
-        ("alpha_tests", C.c_uint64),
+        ("box_tests_closest", C.c_uint64),
+        ("tri_tests_closest", C.c_uint64),
+        ("alpha_tests_closest", C.c_uint64),
+        ("box_tests_shadow", C.c_uint64),
+        ("tri_tests_shadow", C.c_uint64),
+        ("alpha_tests_shadow", C.c_uint64),
+        ("texel_fetches", C.c_uint64),
         ("restarts", C.c_uint64),
         ("wavefront_iterations", C.c_uint64),
         ("kernel_launches", C.c_uint64),
@@ -68,10 +76,15 @@ class Stats(C.Structure):
         ("bvh_build_ms", C.c_float),
         ("scene_upload_ms", C.c_float),
         ("last_render_ms", C.c_float),
+        ("kernel_ms", C.c_float * 4),
+        ("kernel_launch_count", C.c_uint32 * 4),
     ]
 
     def as_dict(self):
-        return {n: getattr(self, n) for n, _ in self._fields_}
+        d = {n: getattr(self, n) for n, _ in self._fields_}
+        d["kernel_ms"] = dict(zip(KERNEL_CLASSES, [float(x) for x in self.kernel_ms]))
+        d["kernel_launch_count"] = dict(zip(KERNEL_CLASSES, [int(x) for x in self.kernel_launch_count]))
+        return d
 
 
 def build(verbose: bool = False) -> str:
@@ -109,6 +122,7 @@ def lib():
     L.pt_trace_occlusion.argtypes = [vp, vp, u64, vp]
     L.pt_get_stats.argtypes = [vp, vp]
     L.pt_set_traversal_stats.argtypes = [vp, i32]
+    L.pt_set_kernel_timing.argtypes = [vp, i32]
     L.pt_test_input_stride.argtypes = [u32]
     L.pt_test_input_stride.restype = u32
     L.pt_test_output_stride.argtypes = [u32]
@@ -234,6 +248,9 @@ class Renderer:
 
     def set_traversal_stats(self, enable: bool):
         self._check(self._L.pt_set_traversal_stats(self._h, 1 if enable else 0))
+
+    def set_kernel_timing(self, enable: bool):
+        self._check(self._L.pt_set_kernel_timing(self._h, 1 if enable else 0))
 
     def test_shading(self, mode: int, inputs: np.ndarray) -> np.ndarray:
         """TestRenderer::ExecutePipeline equivalent (Path-Tracing-Tests/TestRenderer.cpp:79-106)."""

@@ -23,7 +23,8 @@ namespace pt
 // device counters, one cache line each would be overkill: they are touched once per block
 struct DeviceCounters
 {
-    unsigned long long raysClosest, raysShadow, samples, hits, boxTests, triTests, alphaTests, restarts;
+    unsigned long long raysClosest, raysShadow, samples, hits, boxClosest, triClosest, alphaClosest, boxShadow, triShadow,
+        alphaShadow, texels, restarts;
 };
 
 // wavefront queue bookkeeping living in device memory
@@ -83,6 +84,7 @@ struct Context
     uint32_t slotCount = 0;
     bool slotMapValid = false;
     bool collectTraversalStats = false;
+    bool kernelTiming = false;
 
     DeviceCounters *dCounters = nullptr;
     QueueCounts *dQueueCounts = nullptr;

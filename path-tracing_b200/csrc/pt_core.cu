@@ -299,9 +299,13 @@ pt_status pt_get_stats(pt_context *ctx, pt_stats *out)
     s.rays_shadow = c.raysShadow;
     s.samples = c.samples;
     s.hits = c.hits;
-    s.box_tests = c.boxTests;
-    s.tri_tests = c.triTests;
-    s.alpha_tests = c.alphaTests;
+    s.box_tests_closest = c.boxClosest;
+    s.tri_tests_closest = c.triClosest;
+    s.alpha_tests_closest = c.alphaClosest;
+    s.box_tests_shadow = c.boxShadow;
+    s.tri_tests_shadow = c.triShadow;
+    s.alpha_tests_shadow = c.alphaShadow;
+    s.texel_fetches = c.texels;
     s.restarts = c.restarts;
     s.triangle_count = ctx->scene.triCount;
     s.bvh_node_count = ctx->nodeCount;
@@ -317,6 +321,14 @@ pt_status pt_set_traversal_stats(pt_context *ctx, int32_t enable)
     if (!ctx)
         return PT_ERR_INVALID_ARGUMENT;
     ctx->collectTraversalStats = enable != 0;
+    return PT_OK;
+}
+
+pt_status pt_set_kernel_timing(pt_context *ctx, int32_t enable)
+{
+    if (!ctx)
+        return PT_ERR_INVALID_ARGUMENT;
+    ctx->kernelTiming = enable != 0;
     return PT_OK;
 }
 

@@ -116,9 +116,12 @@ PT_DEV float4 lerp4(float4 a, float4 b, float f)
     return make_float4(a.x * g + b.x * f, a.y * g + b.y * f, a.z * g + b.z * f, a.w * g + b.w * f);
 }
 
-PT_DEV float4 sampleBilinear(const DeviceScene &s, const DevTexture &t, uint32_t level, float u, float v)
+PT_DEV float4 sampleBilinear(const DeviceScene &s, const DevTexture &t, uint32_t level, float u, float v,
+                             uint32_t *texels = nullptr)
 {
     const uint32_t lw = max(1u, t.width >> level), lh = max(1u, t.height >> level);
+    if (texels)
+        *texels += (lw == 1 && lh == 1) ? 1u : 4u;
     if (lw == 1 && lh == 1)
         return fetchTexel(s, t, level, 0, 0, 1);
     u = isfinite(u) ? u : 0.0f;
@@ -143,23 +146,24 @@ PT_DEV float4 textureLod0(const DeviceScene &s, const DevTexture &t, float u, fl
 }
 
 // textureGrad(): lambda = log2(max(|dPdx * size|, |dPdy * size|))
-PT_DEV float4 textureGrad(const DeviceScene &s, const DevTexture &t, float u, float v, float4 deriv)
+PT_DEV float4 textureGrad(const DeviceScene &s, const DevTexture &t, float u, float v, float4 deriv,
+                          uint32_t *texels = nullptr)
 {
     const uint32_t last = t.levels - 1;
     if (last == 0)
-        return sampleBilinear(s, t, 0, u, v);
+        return sampleBilinear(s, t, 0, u, v, texels);
     const float w = (float)t.width, h = (float)t.height;
     const float ax = deriv.x * w, ay = deriv.y * h, bx = deriv.z * w, by = deriv.w * h;
     const float rho2 = fmaxf(ax * ax + ay * ay, bx * bx + by * by);
     const float lambda = 0.5f * log2f(rho2);
     if (!(lambda > 0.0f))
-        return sampleBilinear(s, t, 0, u, v);
+        return sampleBilinear(s, t, 0, u, v, texels);
     if (lambda >= (float)last)
-        return sampleBilinear(s, t, last, u, v);
+        return sampleBilinear(s, t, last, u, v, texels);
     const float fl = floorf(lambda);
     const uint32_t l0 = (uint32_t)fl;
-    const float4 a = sampleBilinear(s, t, l0, u, v);
-    const float4 b = sampleBilinear(s, t, l0 + 1, u, v);
+    const float4 a = sampleBilinear(s, t, l0, u, v, texels);
+    const float4 b = sampleBilinear(s, t, l0 + 1, u, v, texels);
     return lerp4(a, b, lambda - fl);
 }
 

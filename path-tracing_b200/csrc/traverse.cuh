@@ -168,6 +168,15 @@ PT_DEV void traverse(const DeviceScene &s, vec3 org, vec3 dir, float tmin, float
         decal.dist = -1.0f;
     if (s.triCount == 0)
         return;
+    // A ray with a non-finite component or a zero direction cannot hit anything (every triangle
+    // test evaluates to NaN), but NaN also defeats box culling, so it would walk the WHOLE tree.
+    // Such rays exist by design: refract() returns 0 on total internal reflection and
+    // normalize(0) is NaN; the sample is then restarted (Q7).  Miss immediately.
+    {
+        const float sum = org.x + org.y + org.z + dir.x + dir.y + dir.z;
+        if (!isfinite(sum) || (dir.x == 0.0f && dir.y == 0.0f && dir.z == 0.0f))
+            return;
+    }
     const RaySetup r = setupRay(org, dir);
 
     int stackNode[PT_STACK_SIZE];

@@ -144,9 +144,9 @@ template <bool ALPHA, bool STATS> __global__ void __launch_bounds__(128) k_exten
     warpAdd(&rc.counters->hits, hits);
     if (STATS)
     {
-        warpAdd(&rc.counters->boxTests, st.boxTests);
-        warpAdd(&rc.counters->triTests, st.triTests);
-        warpAdd(&rc.counters->alphaTests, st.alphaTests);
+        warpAdd(&rc.counters->boxClosest, st.boxTests);
+        warpAdd(&rc.counters->triClosest, st.triTests);
+        warpAdd(&rc.counters->alphaClosest, st.alphaTests);
     }
     if (blockIdx.x == 0 && threadIdx.x == 0)
         atomicAdd(&rc.counters->raysClosest, (unsigned long long)n);
@@ -162,7 +162,7 @@ __device__ __forceinline__ vec3 reconstructNormalFromXY(float4 t)
 }
 
 __device__ __forceinline__ MaterialSample sampleMaterial(const DeviceScene &s, uint32_t materialId, float u, float v,
-                                                         float4 deriv, bool inside, bool flipNormalY)
+                                                         float4 deriv, bool inside, bool flipNormalY, uint32_t *texels)
 {
     const uint32_t type = materialId & 0xffu, index = materialId >> 8;
     MaterialSample r;
@@ -177,7 +177,7 @@ __device__ __forceinline__ MaterialSample sampleMaterial(const DeviceScene &s, u
     const MaterialRaw *m = (type == 0 ? s.materials[0] : type == 1 ? s.materials[1] : s.materials[2]) + index;
     const float4 q0 = __ldg(&m->q[0]), q1 = __ldg(&m->q[1]), q2 = __ldg(&m->q[2]);
     const float4 q3 = __ldg(&m->q[3]), q4 = __ldg(&m->q[4]), q5 = __ldg(&m->q[5]);
-    auto tex = [&](float idxBits) { return textureGrad(s, s.textures[__float_as_uint(idxBits)], u, v, deriv); };
+    auto tex = [&](float idxBits) { return textureGrad(s, s.textures[__float_as_uint(idxBits)], u, v, deriv, texels); };
     r.AttenuationColor = V3(q3.x, q3.y, q3.z);
     r.AttenuationDistance = q3.w;
     if (type == 0)
@@ -270,11 +270,12 @@ __device__ __forceinline__ vec3 skyRadiance(const RenderConst &rc, vec3 dir)
 // ---------------------------------------------------------------------------------------------
 // shade: miss.rmiss | closestHit.rchit, then the raygen bounce logic
 // ---------------------------------------------------------------------------------------------
-template <bool ALPHA> __global__ void __launch_bounds__(128) k_shade(RenderConst rc, int cur)
+template <bool ALPHA, bool STATS> __global__ void __launch_bounds__(128) k_shade(RenderConst rc, int cur)
 {
     const uint32_t n = rc.qc->active[cur];
     const uint32_t stride = gridDim.x * blockDim.x;
     const DeviceScene &s = rc.scene;
+    uint32_t texels = 0;
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
     {
         const uint32_t slot = (cur ? rc.ps.queue[1] : rc.ps.queue[0])[i];
@@ -374,7 +375,8 @@ template <bool ALPHA> __global__ void __launch_bounds__(128) k_shade(RenderConst
 
         // ---- material, closestHit.rchit:101-117 -------------------------------------------------
         MaterialSample material = sampleMaterial(s, materialId, texCoords.x, texCoords.y, derivatives, inside,
-                                                 (rc.hitFlags & PT_HIT_FLAGS_DX_NORMAL_TEXTURES) != 0);
+                                                 (rc.hitFlags & PT_HIT_FLAGS_DX_NORMAL_TEXTURES) != 0,
+                                                 STATS ? &texels : nullptr);
         if (ALPHA)
         {
             const float4 dec = rc.ps.decal[slot];
@@ -459,6 +461,8 @@ template <bool ALPHA> __global__ void __launch_bounds__(128) k_shade(RenderConst
         rc.ps.diff1[slot] = make_float4(rd.rxDirection.y, rd.rxDirection.z, rd.ryOrigin.x, rd.ryOrigin.y);
         rc.ps.diff2[slot] = make_float4(rd.ryOrigin.z, rd.ryDirection.x, rd.ryDirection.y, rd.ryDirection.z);
     }
+    if (STATS)
+        warpAdd(&rc.counters->texels, texels);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -488,9 +492,9 @@ template <bool ALPHA, bool STATS> __global__ void __launch_bounds__(128) k_shado
     }
     if (STATS)
     {
-        warpAdd(&rc.counters->boxTests, st.boxTests);
-        warpAdd(&rc.counters->triTests, st.triTests);
-        warpAdd(&rc.counters->alphaTests, st.alphaTests);
+        warpAdd(&rc.counters->boxShadow, st.boxTests);
+        warpAdd(&rc.counters->triShadow, st.triTests);
+        warpAdd(&rc.counters->alphaShadow, st.alphaTests);
     }
     if (blockIdx.x == 0 && threadIdx.x == 0)
         atomicAdd(&rc.counters->raysShadow, (unsigned long long)n);
@@ -708,33 +712,61 @@ pt_status renderSamples(Context *ctx, const pt_render_params *params, uint32_t f
 
         int cur = 0;
         const uint32_t checkEvery = 4;
+        // optional per-launch CUDA-event timing (pt_set_kernel_timing): (class, start, stop) triples
+        struct Timed
+        {
+            int cls;
+            cudaEvent_t a, b;
+        };
+        std::vector<Timed> timed;
+        const bool timing = ctx->kernelTiming;
+        auto begin = [&](int cls) {
+            if (!timing)
+                return;
+            Timed t { cls, nullptr, nullptr };
+            cudaEventCreate(&t.a);
+            cudaEventCreate(&t.b);
+            cudaEventRecord(t.a, ctx->stream);
+            timed.push_back(t);
+        };
+        auto end = [&]() {
+            if (timing)
+                cudaEventRecord(timed.back().b, ctx->stream);
+        };
+        for (int k = 0; k < PT_KERNEL_CLASS_COUNT; k++)
+        {
+            ctx->stats.kernel_ms[k] = 0.0f;
+            ctx->stats.kernel_launch_count[k] = 0;
+        }
         for (uint64_t iter = 0;; iter++)
         {
-#define PT_LAUNCH_EXTEND(A, S) k_extend<A, S><<<gridTrace, 128, 0, ctx->stream>>>(rc, cur)
-#define PT_LAUNCH_SHADOW(A, S) k_shadow<A, S><<<gridTrace, 128, 0, ctx->stream>>>(rc)
-            if (alpha && statsOn)
-                PT_LAUNCH_EXTEND(true, true);
-            else if (alpha)
-                PT_LAUNCH_EXTEND(true, false);
-            else if (statsOn)
-                PT_LAUNCH_EXTEND(false, true);
-            else
-                PT_LAUNCH_EXTEND(false, false);
-            if (alpha)
-                k_shade<true><<<gridTrace, 128, 0, ctx->stream>>>(rc, cur);
-            else
-                k_shade<false><<<gridTrace, 128, 0, ctx->stream>>>(rc, cur);
-            if (alpha && statsOn)
-                PT_LAUNCH_SHADOW(true, true);
-            else if (alpha)
-                PT_LAUNCH_SHADOW(true, false);
-            else if (statsOn)
-                PT_LAUNCH_SHADOW(false, true);
-            else
-                PT_LAUNCH_SHADOW(false, false);
+#define PT_DISPATCH(KERNEL, GRID, BLOCK, ...)                                                                         \
+    do                                                                                                                \
+    {                                                                                                                 \
+        if (alpha && statsOn)                                                                                         \
+            KERNEL<true, true><<<GRID, BLOCK, 0, ctx->stream>>>(__VA_ARGS__);                                         \
+        else if (alpha)                                                                                               \
+            KERNEL<true, false><<<GRID, BLOCK, 0, ctx->stream>>>(__VA_ARGS__);                                        \
+        else if (statsOn)                                                                                             \
+            KERNEL<false, true><<<GRID, BLOCK, 0, ctx->stream>>>(__VA_ARGS__);                                        \
+        else                                                                                                          \
+            KERNEL<false, false><<<GRID, BLOCK, 0, ctx->stream>>>(__VA_ARGS__);                                       \
+    } while (0)
+            begin(PT_KERNEL_EXTEND);
+            PT_DISPATCH(k_extend, gridTrace, 128, rc, cur);
+            end();
+            begin(PT_KERNEL_SHADE);
+            PT_DISPATCH(k_shade, gridTrace, 128, rc, cur);
+            end();
+            begin(PT_KERNEL_SHADOW);
+            PT_DISPATCH(k_shadow, gridTrace, 128, rc);
+            end();
+            begin(PT_KERNEL_FINISH);
             k_finish<<<gridWide, 256, 0, ctx->stream>>>(rc, cur);
-#undef PT_LAUNCH_EXTEND
-#undef PT_LAUNCH_SHADOW
+            end();
+#undef PT_DISPATCH
+            for (int k = 0; k < PT_KERNEL_CLASS_COUNT; k++)
+                ctx->stats.kernel_launch_count[k]++;
             ctx->stats.kernel_launches += 4;
             ctx->stats.wavefront_iterations++;
             cur ^= 1;
@@ -745,6 +777,18 @@ pt_status renderSamples(Context *ctx, const pt_render_params *params, uint32_t f
                 PT_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
                 if (ctx->hQueueCounts->active[cur] == 0)
                     break;
+            }
+        }
+        if (timing)
+        {
+            cudaStreamSynchronize(ctx->stream);
+            for (Timed &t : timed)
+            {
+                float ms = 0.0f;
+                cudaEventElapsedTime(&ms, t.a, t.b);
+                ctx->stats.kernel_ms[t.cls] += ms;
+                cudaEventDestroy(t.a);
+                cudaEventDestroy(t.b);
             }
         }
     }

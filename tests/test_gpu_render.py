@@ -133,8 +133,21 @@ def test_traversal_stats_toggle(feature):
     r.on_resize(64, 48)
     r.render(2, params=p)
     assert (r.read_accumulation() == a).all()  # counting does not change the image
-    assert st["box_tests"] > st["tri_tests"] > 0 and st["alpha_tests"] > 0
-    assert r.stats()["box_tests"] == 0
+    assert st["box_tests_closest"] > st["tri_tests_closest"] > 0 and st["alpha_tests_closest"] > 0
+    assert st["box_tests_shadow"] > 0 and st["texel_fetches"] >= 5 * st["hits"]
+    assert r.stats()["box_tests_closest"] == 0
+
+
+def test_kernel_timing(feature):
+    s, r, _ = feature
+    r.on_resize(64, 48)
+    r.set_kernel_timing(True)
+    r.render(2, params=s.default_params(bounce_count=4))
+    st = r.stats()
+    r.set_kernel_timing(False)
+    assert all(ms > 0 for ms in st["kernel_ms"].values())
+    assert sum(st["kernel_launch_count"].values()) == st["kernel_launches"] - 1  # + k_init
+    assert sum(st["kernel_ms"].values()) <= st["last_render_ms"] * 1.05
 
 
 def test_skybox_2d(oracle_mod):
