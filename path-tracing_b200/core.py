@@ -18,7 +18,8 @@ from . import scene as sc
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
-LIB_PATH = os.path.join(CSRC, "libpt_core.so")
+# PT_CORE_LIB selects another build of the same library (A/B experiments with kernel variants)
+LIB_PATH = os.environ.get("PT_CORE_LIB") or os.path.join(CSRC, "libpt_core.so")
 
 ABI_SYMBOLS = [
     "pt_context_create",

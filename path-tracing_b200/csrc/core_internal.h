@@ -30,12 +30,15 @@ struct DeviceCounters
 // wavefront queue bookkeeping living in device memory
 struct QueueCounts
 {
-    uint32_t active[2]; // double-buffered active-slot queue sizes
+    uint32_t cont[2];  // double-buffered queue sizes: continuing paths ...
+    uint32_t fresh[2]; // ... and freshly generated primary rays
+    uint32_t hit;      // slots whose closest-hit query hit (input of k_shade)
     uint32_t shadow;
+    uint32_t nextItem; // next work item (sample * pixelCount + pixel-list index) of the round
     uint32_t pad;
 };
 
-// SoA path state, one entry per slot (slot <-> pixel of the current tile set)
+// SoA path state, one entry per slot of the pool (a slot carries one path = one work item at a time)
 struct PathState
 {
     float4 *rayO;  // origin.xyz, maxRoughness
@@ -51,9 +54,10 @@ struct PathState
     float4 *shO;   // shadow origin.xyz, tmax
     float4 *shD;   // shadow direction.xyz, -
     float4 *shC;   // contribution.xyz (throughput * DirectLight / pdf), -
-    uint32_t *sample;    // next sample index (relative to first_sample) of the slot
-    uint32_t *slotPixel; // y * width + x
-    uint32_t *queue[2];  // active slots, double buffered
+    uint32_t *item;      // work item of the slot (round-relative sample * pixelCount + pixel-list index)
+    uint32_t *contQ[2];  // active slots with a continuing path, double buffered
+    uint32_t *freshQ[2]; // active slots with a fresh primary ray, double buffered
+    uint32_t *hitQ;      // slots to shade
     uint32_t *shadowQueue;
 };
 
@@ -78,11 +82,17 @@ struct Context
     float4 *accum = nullptr;
     PathState ps = {};
     std::vector<void *> targetAllocs;
-    uint32_t slotCapacity = 0;
-    // slot -> pixel map cache (rebuilt only when the tile list changes)
-    std::vector<pt_tile> slotTiles;
-    uint32_t slotCount = 0;
-    bool slotMapValid = false;
+    size_t slotPoolSize = (size_t)1 << 21;     // paths in flight (PT_SLOTS)
+    size_t sbufBudgetBytes = (size_t)8 << 30;  // sample-buffer budget (PT_SBUF_MB)
+    uint32_t slotCapacity = 0; // size of the slot pool
+    // pixel list of the current tile set in 8x4-block order (rebuilt only when the tile list changes)
+    uint32_t *pixelList = nullptr;
+    std::vector<pt_tile> pixelTiles;
+    uint32_t pixelCount = 0;
+    bool pixelListValid = false;
+    // sample buffer of one round: [samples][pixelCount] float4, grown on demand
+    float4 *sbuf = nullptr;
+    uint64_t sbufCapacity = 0; // float4 entries
     bool collectTraversalStats = false;
     bool kernelTiming = false;
 

@@ -2,7 +2,9 @@
 #include "core_internal.h"
 
 #include <cmath>
+#include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 namespace pt
@@ -28,7 +30,12 @@ static void freeTarget(Context *ctx)
     ctx->accum = nullptr;
     ctx->ps = PathState {};
     ctx->slotCapacity = 0;
-    ctx->slotMapValid = false;
+    ctx->pixelList = nullptr;
+    ctx->pixelListValid = false;
+    ctx->pixelCount = 0;
+    cudaFree(ctx->sbuf);
+    ctx->sbuf = nullptr;
+    ctx->sbufCapacity = 0;
     ctx->width = ctx->height = 0;
 }
 
@@ -75,6 +82,11 @@ pt_status pt_context_create(int32_t cuda_device, pt_context **out_ctx)
     pt_context *ctx = new pt_context();
     ctx->device = cuda_device;
     ctx->smCount = prop.multiProcessorCount;
+    // tuning knobs (not part of the ABI): PT_SLOTS = paths in flight, PT_SBUF_MB = sample-buffer budget
+    if (const char *e = std::getenv("PT_SLOTS"))
+        ctx->slotPoolSize = std::max<size_t>(1024, std::strtoull(e, nullptr, 10));
+    if (const char *e = std::getenv("PT_SBUF_MB"))
+        ctx->sbufBudgetBytes = std::max<size_t>(1, std::strtoull(e, nullptr, 10)) << 20;
 #define PT_CREATE_CHECK(expr)                                                                                         \
     do                                                                                                                \
     {                                                                                                                 \
@@ -182,32 +194,39 @@ pt_status pt_render_begin(pt_context *ctx, uint32_t width, uint32_t height)
             return s__;                                                                                               \
         }                                                                                                             \
     } while (0)
+        // slot pool: enough paths in flight to fill the GPU many times over (148 SMs x 2048 threads =
+        // 0.3 M resident threads), independent of the image size beyond tiny frames
+        size_t slots = ctx->slotPoolSize;
+        slots = std::min(slots, std::max<size_t>(n * 4, 4096));
         PT_T(targetAlloc(ctx, &ctx->accum, n));
-        PT_T(targetAlloc(ctx, &ps.rayO, n));
-        PT_T(targetAlloc(ctx, &ps.rayD, n));
-        PT_T(targetAlloc(ctx, &ps.thr, n));
-        PT_T(targetAlloc(ctx, &ps.rad, n));
-        PT_T(targetAlloc(ctx, &ps.diff0, n));
-        PT_T(targetAlloc(ctx, &ps.diff1, n));
-        PT_T(targetAlloc(ctx, &ps.diff2, n));
-        PT_T(targetAlloc(ctx, &ps.hit, n));
+        PT_T(targetAlloc(ctx, &ctx->pixelList, n));
+        PT_T(targetAlloc(ctx, &ps.rayO, slots));
+        PT_T(targetAlloc(ctx, &ps.rayD, slots));
+        PT_T(targetAlloc(ctx, &ps.thr, slots));
+        PT_T(targetAlloc(ctx, &ps.rad, slots));
+        PT_T(targetAlloc(ctx, &ps.diff0, slots));
+        PT_T(targetAlloc(ctx, &ps.diff1, slots));
+        PT_T(targetAlloc(ctx, &ps.diff2, slots));
+        PT_T(targetAlloc(ctx, &ps.hit, slots));
         if (needDecal)
         {
-            PT_T(targetAlloc(ctx, &ps.decal, n));
-            PT_T(targetAlloc(ctx, &ps.decalA, n));
+            PT_T(targetAlloc(ctx, &ps.decal, slots));
+            PT_T(targetAlloc(ctx, &ps.decalA, slots));
         }
-        PT_T(targetAlloc(ctx, &ps.shO, n));
-        PT_T(targetAlloc(ctx, &ps.shD, n));
-        PT_T(targetAlloc(ctx, &ps.shC, n));
-        PT_T(targetAlloc(ctx, &ps.sample, n));
-        PT_T(targetAlloc(ctx, &ps.slotPixel, n));
-        PT_T(targetAlloc(ctx, &ps.queue[0], n));
-        PT_T(targetAlloc(ctx, &ps.queue[1], n));
-        PT_T(targetAlloc(ctx, &ps.shadowQueue, n));
+        PT_T(targetAlloc(ctx, &ps.shO, slots));
+        PT_T(targetAlloc(ctx, &ps.shD, slots));
+        PT_T(targetAlloc(ctx, &ps.shC, slots));
+        PT_T(targetAlloc(ctx, &ps.item, slots));
+        PT_T(targetAlloc(ctx, &ps.contQ[0], slots));
+        PT_T(targetAlloc(ctx, &ps.contQ[1], slots));
+        PT_T(targetAlloc(ctx, &ps.freshQ[0], slots));
+        PT_T(targetAlloc(ctx, &ps.freshQ[1], slots));
+        PT_T(targetAlloc(ctx, &ps.hitQ, slots));
+        PT_T(targetAlloc(ctx, &ps.shadowQueue, slots));
 #undef PT_T
         ctx->width = width;
         ctx->height = height;
-        ctx->slotCapacity = (uint32_t)n;
+        ctx->slotCapacity = (uint32_t)slots;
     }
     PT_CUDA_CHECK(ctx, cudaMemsetAsync(ctx->accum, 0, n * sizeof(float4), ctx->stream));
     return PT_OK;

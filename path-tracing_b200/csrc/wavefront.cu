@@ -1,19 +1,25 @@
 // wavefront.cu — the path-tracing hot path as wavefront kernels for sm_100a.
 //
-// One SLOT per pixel of the current tile set; a slot traces the pixel's samples one after the
-// other (path regeneration), so the wavefront stays full until the last samples and every pixel
-// accumulates its samples in the reference's order.  Per iteration:
+// A fixed pool of path SLOTS pulls WORK ITEMS (pixel, sample) from a global counter, in
+// sample-major order, so the wavefront stays full until the very last items of a round
+// regardless of how path lengths differ between pixels.  A finished path parks its radiance in
+// the round's sample buffer sbuf[sample][pixel]; k_resolve then adds the samples of every pixel
+// to the accumulation image IN SAMPLE ORDER, which is the reference's summation order
+// (raygen.rgen:115-117 runs once per frame with SampleCount = 1) — so the image does not depend
+// on scheduling, slot count or tile partition, bit for bit.  Per iteration:
 //
 //   k_extend   closest-hit traversal of every active slot's ray          (raygen.rgen:68)
 //   k_shade    miss.rmiss / closestHit.rchit + the raygen bounce logic     (raygen.rgen:71-96)
 //              emits a shadow ray into a compacted queue when NEE can contribute
 //   k_shadow   occlusion traversal, adds the direct-light contribution    (raygen.rgen:79-81)
-//   k_finish   finished paths: NaN/Inf restart or accumulate, next sample's primary ray
-//              (raygen.rgen:38-58, 99-117); builds the next compacted active queue
+//   k_finish   finished paths: NaN/Inf restart or park the sample and pull the next work item
+//              (raygen.rgen:38-58, 99-117); builds the next compacted queues
 //
 // Path state is SoA float4 streams indexed by slot (coalesced 16-byte accesses); queues hold slot
-// indices and are compacted with warp-aggregated atomics.  Queue order never influences a slot's
-// arithmetic, so results are deterministic.
+// indices and are compacted with warp-aggregated atomics.  Continuing (incoherent) paths and
+// freshly generated (coherent, consecutive pixels of an 8x4 block) primary rays go to separate
+// queues so that warps of k_extend are not a mix of both.  Queue order never influences a
+// slot's arithmetic, so results are deterministic.
 #include "core_internal.h"
 #include "shading.cuh"
 #include "traverse.cuh"
@@ -43,7 +49,13 @@ struct RenderConst
     uint32_t bounceCount;
     float lensRadius, focalDistance;
     uint32_t missFlags, hitFlags;
-    uint32_t slotCount;
+    uint32_t slotCount;          // slots in use (<= slot capacity, <= itemCount)
+    const uint32_t *pixelList;   // pixels of the tile set in 8x4-block order
+    uint32_t pixelCount;
+    float4 *sbuf;                // [roundSamples][pixelCount] radiance of the finished samples of the round
+    uint32_t roundBase;          // first sample of the round, relative to firstSample
+    uint32_t roundSamples;
+    uint32_t itemCount;          // roundSamples * pixelCount; item = sample * pixelCount + pixel-list index
 };
 
 __device__ __forceinline__ uint32_t laneId() { return threadIdx.x & 31u; }
@@ -74,7 +86,7 @@ __device__ __forceinline__ void warpAdd(unsigned long long *counter, uint32_t va
 __device__ __forceinline__ void generatePath(const RenderConst &rc, uint32_t slot, uint32_t pixel, uint32_t rng,
                                              uint32_t restarts)
 {
-    const uint32_t px = pixel % rc.width, py = pixel / rc.width;
+    const uint32_t py = pixel / rc.width, px = pixel - py * rc.width;
     const float ux = rnd(rng);
     const float uy = rnd(rng);
     vec2 u2 = V2(0.0f, 0.0f);
@@ -94,22 +106,55 @@ __device__ __forceinline__ void generatePath(const RenderConst &rc, uint32_t slo
     rc.ps.diff2[slot] = make_float4(pr.origin.z, pr.ryDirection.x, pr.ryDirection.y, pr.ryDirection.z);
 }
 
+// work item -> (pixel, absolute sample index); starts the item's path in `slot`
+__device__ __forceinline__ void startItem(const RenderConst &rc, uint32_t slot, uint32_t item)
+{
+    const uint32_t s = item / rc.pixelCount, pi = item - s * rc.pixelCount;
+    const uint32_t pixel = __ldg(rc.pixelList + pi);
+    const uint32_t py = pixel / rc.width, px = pixel - py * rc.width;
+    rc.ps.item[slot] = item;
+    generatePath(rc, slot, pixel, initRng(px, py, rc.width, rc.firstSample + rc.roundBase + s), 0);
+}
+
+// slot i starts with work item i of the round
 __global__ void __launch_bounds__(256) k_init(RenderConst rc)
 {
     const uint32_t stride = gridDim.x * blockDim.x;
     for (uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x; slot < rc.slotCount; slot += stride)
     {
-        const uint32_t pixel = rc.ps.slotPixel[slot];
-        rc.ps.sample[slot] = 0;
-        rc.ps.queue[0][slot] = slot;
-        generatePath(rc, slot, pixel, initRng(pixel % rc.width, pixel / rc.width, rc.width, rc.firstSample), 0);
+        rc.ps.freshQ[0][slot] = slot;
+        startItem(rc, slot, slot);
     }
     if (blockIdx.x == 0 && threadIdx.x == 0)
     {
-        rc.qc->active[0] = rc.slotCount;
-        rc.qc->active[1] = 0;
+        rc.qc->cont[0] = 0;
+        rc.qc->fresh[0] = rc.slotCount;
+        rc.qc->cont[1] = 0;
+        rc.qc->fresh[1] = 0;
         rc.qc->shadow = 0;
+        rc.qc->hit = 0;
+        rc.qc->nextItem = rc.slotCount;
     }
+}
+
+// i-th active slot of queue pair `cur`: continuing paths first, then fresh primary rays
+__device__ __forceinline__ uint32_t activeSlot(const RenderConst &rc, int cur, uint32_t i, uint32_t nCont)
+{
+    return i < nCont ? (cur ? rc.ps.contQ[1] : rc.ps.contQ[0])[i] : (cur ? rc.ps.freshQ[1] : rc.ps.freshQ[0])[i - nCont];
+}
+
+// miss.rmiss:16-39
+__device__ __forceinline__ vec3 skyRadiance(const RenderConst &rc, vec3 dir)
+{
+    if ((rc.missFlags & PT_MISS_FLAGS_SKYBOX_2D) && rc.scene.hasSky2D)
+    {
+        const float longitude = atan2f(dir.z, dir.x);
+        const float latitude = asinf(-dir.y);
+        const float4 c = textureLod0(rc.scene, rc.scene.sky2D, longitude / 2.0f / PT_PI + 0.5f, latitude / PT_PI + 0.5f);
+        const vec3 rgb = V3(c);
+        return rgb / (1.0f + maxComponent(rgb)); // hdrToLdr
+    }
+    return V3(0.08f, 0.09f, 0.1f);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -117,10 +162,11 @@ __global__ void __launch_bounds__(256) k_init(RenderConst rc)
 // ---------------------------------------------------------------------------------------------
 template <bool ALPHA, bool STATS> __global__ void __launch_bounds__(128) k_extend(RenderConst rc, int cur)
 {
-    const uint32_t n = rc.qc->active[cur];
+    const uint32_t nCont = rc.qc->cont[cur], n = nCont + rc.qc->fresh[cur];
     if (blockIdx.x == 0 && threadIdx.x == 0)
     {
-        rc.qc->active[cur ^ 1] = 0;
+        rc.qc->cont[cur ^ 1] = 0;
+        rc.qc->fresh[cur ^ 1] = 0;
         rc.qc->shadow = 0;
     }
     const uint32_t stride = gridDim.x * blockDim.x;
@@ -128,18 +174,29 @@ template <bool ALPHA, bool STATS> __global__ void __launch_bounds__(128) k_exten
     TraversalStats st = { 0, 0, 0 };
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
     {
-        const uint32_t slot = (cur ? rc.ps.queue[1] : rc.ps.queue[0])[i];
+        const uint32_t slot = activeSlot(rc, cur, i, nCont);
         const float4 o = rc.ps.rayO[slot], d = rc.ps.rayD[slot];
         Hit hit;
         Decal decal;
         traverse<true, ALPHA, STATS>(rc.scene, V3(o), V3(d), 0.00001f, 10000.0f, hit, decal, st);
+        if (hit.tri == 0xffffffffu)
+        {
+            // miss.rmiss + raygen.rgen:71-75: the path ends with the sky radiance
+            const float4 thr4 = rc.ps.thr[slot];
+            float4 rad4 = rc.ps.rad[slot];
+            const vec3 radiance = V3(rad4) + V3(thr4) * skyRadiance(rc, V3(d));
+            rc.ps.rad[slot] = make_float4(radiance.x, radiance.y, radiance.z, rad4.w);
+            rc.ps.thr[slot] = make_float4(thr4.x, thr4.y, thr4.z, __uint_as_float(__float_as_uint(thr4.w) | kStateDone));
+            continue;
+        }
         rc.ps.hit[slot] = make_float4(__uint_as_float(hit.tri), hit.t, hit.b1, hit.b2);
         if (ALPHA)
         {
             rc.ps.decal[slot] = make_float4(decal.r, decal.g, decal.b, decal.dist);
             rc.ps.decalA[slot] = decal.a;
         }
-        hits += hit.tri != 0xffffffffu;
+        rc.ps.hitQ[atomicAggInc(&rc.qc->hit)] = slot;
+        hits++;
     }
     warpAdd(&rc.counters->hits, hits);
     if (STATS)
@@ -253,32 +310,18 @@ __device__ __forceinline__ LightSample sampleLight(const LightBlock *lb, vec3 u,
     return r;
 }
 
-// miss.rmiss:16-39
-__device__ __forceinline__ vec3 skyRadiance(const RenderConst &rc, vec3 dir)
-{
-    if ((rc.missFlags & PT_MISS_FLAGS_SKYBOX_2D) && rc.scene.hasSky2D)
-    {
-        const float longitude = atan2f(dir.z, dir.x);
-        const float latitude = asinf(-dir.y);
-        const float4 c = textureLod0(rc.scene, rc.scene.sky2D, longitude / 2.0f / PT_PI + 0.5f, latitude / PT_PI + 0.5f);
-        const vec3 rgb = V3(c);
-        return rgb / (1.0f + maxComponent(rgb)); // hdrToLdr
-    }
-    return V3(0.08f, 0.09f, 0.1f);
-}
-
 // ---------------------------------------------------------------------------------------------
-// shade: miss.rmiss | closestHit.rchit, then the raygen bounce logic
+// shade: closestHit.rchit, then the raygen bounce logic (misses are finished by k_extend)
 // ---------------------------------------------------------------------------------------------
-template <bool ALPHA, bool STATS> __global__ void __launch_bounds__(128) k_shade(RenderConst rc, int cur)
+template <bool ALPHA, bool STATS> __global__ void __launch_bounds__(128) k_shade(RenderConst rc)
 {
-    const uint32_t n = rc.qc->active[cur];
+    const uint32_t n = rc.qc->hit;
     const uint32_t stride = gridDim.x * blockDim.x;
     const DeviceScene &s = rc.scene;
     uint32_t texels = 0;
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
     {
-        const uint32_t slot = (cur ? rc.ps.queue[1] : rc.ps.queue[0])[i];
+        const uint32_t slot = rc.ps.hitQ[i];
         const float4 hitv = rc.ps.hit[slot];
         const float4 rayO = rc.ps.rayO[slot], rayD = rc.ps.rayD[slot];
         float4 thr4 = rc.ps.thr[slot];
@@ -287,15 +330,6 @@ template <bool ALPHA, bool STATS> __global__ void __launch_bounds__(128) k_shade
         uint32_t state = __float_as_uint(thr4.w);
         const vec3 rayDir = V3(rayD);
         const uint32_t tri = __float_as_uint(hitv.x);
-
-        if (tri == 0xffffffffu)
-        {
-            // raygen.rgen:71-75
-            radiance += throughput * skyRadiance(rc, rayDir);
-            rc.ps.rad[slot] = make_float4(radiance.x, radiance.y, radiance.z, rad4.w);
-            rc.ps.thr[slot] = make_float4(throughput.x, throughput.y, throughput.z, __uint_as_float(state | kStateDone));
-            continue;
-        }
 
         uint32_t rng = __float_as_uint(rayD.w);
         float maxRoughness = rayO.w;
@@ -501,55 +535,82 @@ template <bool ALPHA, bool STATS> __global__ void __launch_bounds__(128) k_shado
 }
 
 // ---------------------------------------------------------------------------------------------
-// finish: raygen.rgen:99-117 for finished paths, then the next sample
+// finish: raygen.rgen:99-117 for finished paths, then the next work item
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_finish(RenderConst rc, int cur)
 {
-    const uint32_t n = rc.qc->active[cur];
+    const uint32_t nCont = rc.qc->cont[cur], n = nCont + rc.qc->fresh[cur];
     const uint32_t stride = gridDim.x * blockDim.x;
     uint32_t samples = 0, restarts = 0;
+    if (blockIdx.x == 0 && threadIdx.x == 0)
+        rc.qc->hit = 0; // consumed by this iteration's k_shade, refilled by the next k_extend
+    uint32_t *contOut = cur ? rc.ps.contQ[0] : rc.ps.contQ[1];
+    uint32_t *freshOut = cur ? rc.ps.freshQ[0] : rc.ps.freshQ[1];
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
     {
-        const uint32_t slot = (cur ? rc.ps.queue[1] : rc.ps.queue[0])[i];
+        const uint32_t slot = activeSlot(rc, cur, i, nCont);
         const uint32_t state = __float_as_uint(rc.ps.thr[slot].w);
-        bool active = true;
-        if (state & kStateDone)
+        if (!(state & kStateDone))
         {
-            const float4 r = rc.ps.rad[slot];
-            const uint32_t pixel = rc.ps.slotPixel[slot];
-            uint32_t restartCount = __float_as_uint(r.w);
-            samples++;
-            if ((bad(r.x) || bad(r.y) || bad(r.z)) && restartCount < kMaxRestarts)
-            {
-                // radiance = 0; smpl = -1: the sample is redone with the ADVANCED rng state
-                restarts++;
-                generatePath(rc, slot, pixel, __float_as_uint(rc.ps.rayD[slot].w), restartCount + 1);
-            }
-            else
-            {
-                float4 a = rc.accum[pixel];
-                if (!(bad(r.x) || bad(r.y) || bad(r.z)))
-                {
-                    a.x = r.x + a.x;
-                    a.y = r.y + a.y;
-                    a.z = r.z + a.z;
-                }
-                a.w = 1.0f;
-                rc.accum[pixel] = a;
-                const uint32_t next = rc.ps.sample[slot] + 1;
-                rc.ps.sample[slot] = next;
-                if (next < rc.sampleCount)
-                    generatePath(rc, slot, pixel,
-                                 initRng(pixel % rc.width, pixel / rc.width, rc.width, rc.firstSample + next), 0);
-                else
-                    active = false;
-            }
+            contOut[atomicAggInc(&rc.qc->cont[cur ^ 1])] = slot;
+            continue;
         }
-        if (active)
-            (cur ? rc.ps.queue[0] : rc.ps.queue[1])[atomicAggInc(&rc.qc->active[cur ^ 1])] = slot;
+        float4 r = rc.ps.rad[slot];
+        const uint32_t item = rc.ps.item[slot];
+        const uint32_t restartCount = __float_as_uint(r.w);
+        samples++;
+        const bool isBad = bad(r.x) || bad(r.y) || bad(r.z);
+        if (isBad && restartCount < kMaxRestarts)
+        {
+            // radiance = 0; smpl = -1: the sample is redone with the ADVANCED rng state
+            restarts++;
+            const uint32_t s = item / rc.pixelCount, pi = item - s * rc.pixelCount;
+            generatePath(rc, slot, __ldg(rc.pixelList + pi), __float_as_uint(rc.ps.rayD[slot].w), restartCount + 1);
+            freshOut[atomicAggInc(&rc.qc->fresh[cur ^ 1])] = slot;
+            continue;
+        }
+        // park the sample; k_resolve adds the round's samples to the image in sample order
+        rc.sbuf[item] = isBad ? make_float4(0.0f, 0.0f, 0.0f, 0.0f) : r;
+        // pull the next work item: the lanes of a warp that finish together take consecutive items
+        // (= consecutive pixels of an 8x4 block) and consecutive positions of the fresh queue
+        const unsigned mask = __activemask();
+        const int leader = __ffs(mask) - 1;
+        const uint32_t rank = __popc(mask & ((1u << laneId()) - 1u));
+        uint32_t base = 0;
+        if ((int)laneId() == leader)
+            base = atomicAdd(&rc.qc->nextItem, (uint32_t)__popc(mask));
+        base = __shfl_sync(mask, base, leader);
+        const uint32_t next = base + rank;
+        if (next < rc.itemCount)
+        {
+            startItem(rc, slot, next);
+            freshOut[atomicAggInc(&rc.qc->fresh[cur ^ 1])] = slot;
+        }
     }
     warpAdd(&rc.counters->samples, samples);
     warpAdd(&rc.counters->restarts, restarts);
+}
+
+// ---------------------------------------------------------------------------------------------
+// resolve: acc += radiance, one sample after the other (raygen.rgen:115-117 over consecutive frames)
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_resolve(RenderConst rc)
+{
+    const uint32_t stride = gridDim.x * blockDim.x;
+    for (uint32_t pi = blockIdx.x * blockDim.x + threadIdx.x; pi < rc.pixelCount; pi += stride)
+    {
+        const uint32_t pixel = __ldg(rc.pixelList + pi);
+        float4 a = rc.accum[pixel];
+        for (uint32_t s = 0; s < rc.roundSamples; s++)
+        {
+            const float4 r = __ldcs(rc.sbuf + (size_t)s * rc.pixelCount + pi);
+            a.x = r.x + a.x;
+            a.y = r.y + a.y;
+            a.z = r.z + a.z;
+        }
+        a.w = 1.0f;
+        rc.accum[pixel] = a;
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -647,16 +708,17 @@ pt_status renderSamples(Context *ctx, const pt_render_params *params, uint32_t f
     if (tiles == nullptr)
         tileCount = 0;
 
-    // ---- slot -> pixel map: 8x4 pixel blocks so that a warp's primary rays are coherent --------
+    // ---- pixel list of the tile set: 8x4 pixel blocks, so that consecutive work items are
+    //      neighbouring pixels and a warp's fresh primary rays are coherent -----------------------
     const uint32_t W = ctx->width, H = ctx->height;
     {
         const pt_tile whole = { 0, 0, W, H };
         std::vector<pt_tile> want(tileCount ? tiles : &whole, tileCount ? tiles + tileCount : &whole + 1);
-        const bool same = ctx->slotMapValid && want.size() == ctx->slotTiles.size() &&
-                          (want.empty() || std::memcmp(want.data(), ctx->slotTiles.data(), want.size() * sizeof(pt_tile)) == 0);
+        const bool same = ctx->pixelListValid && want.size() == ctx->pixelTiles.size() &&
+                          (want.empty() || std::memcmp(want.data(), ctx->pixelTiles.data(), want.size() * sizeof(pt_tile)) == 0);
         if (!same)
         {
-            std::vector<uint32_t> slotPixel;
+            std::vector<uint32_t> list;
             for (const pt_tile &in : want)
             {
                 const pt_tile t = { std::min(in.x0, W), std::min(in.y0, H), std::min(in.x1, W), std::min(in.y1, H) };
@@ -664,26 +726,78 @@ pt_status renderSamples(Context *ctx, const pt_render_params *params, uint32_t f
                     for (uint32_t bx = t.x0; bx < t.x1; bx += 8)
                         for (uint32_t y = by; y < std::min(by + 4, t.y1); y++)
                             for (uint32_t x = bx; x < std::min(bx + 8, t.x1); x++)
-                                slotPixel.push_back(y * W + x);
+                                list.push_back(y * W + x);
             }
-            if (slotPixel.size() > ctx->slotCapacity)
+            if (list.size() > (size_t)W * H)
                 return fail(ctx, PT_ERR_INVALID_ARGUMENT, "pt_render_samples", "tiles overlap or exceed the frame");
-            if (!slotPixel.empty())
-                PT_CUDA_CHECK(ctx, cudaMemcpyAsync(ctx->ps.slotPixel, slotPixel.data(), slotPixel.size() * 4,
-                                                   cudaMemcpyHostToDevice, ctx->stream));
+            if (!list.empty())
+                PT_CUDA_CHECK(ctx, cudaMemcpyAsync(ctx->pixelList, list.data(), list.size() * 4, cudaMemcpyHostToDevice,
+                                                   ctx->stream));
             PT_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
-            ctx->slotTiles = want;
-            ctx->slotCount = (uint32_t)slotPixel.size();
-            ctx->slotMapValid = true;
+            ctx->pixelTiles = want;
+            ctx->pixelCount = (uint32_t)list.size();
+            ctx->pixelListValid = true;
         }
     }
-    const uint32_t slots = ctx->slotCount;
+    const uint32_t pixels = ctx->pixelCount;
+
+    // ---- rounds: as many samples per round as the sample buffer budget allows ---------------------
+    uint32_t roundMax = 0;
+    if (pixels > 0 && sampleCount > 0)
+    {
+        size_t freeB = 0, totalB = 0;
+        PT_CUDA_CHECK(ctx, cudaMemGetInfo(&freeB, &totalB));
+        const uint64_t have = ctx->sbufCapacity * sizeof(float4);
+        const uint64_t budget = std::max<uint64_t>(have, std::min<uint64_t>(ctx->sbufBudgetBytes, (freeB + have) / 2));
+        // item indices are 32-bit
+        const uint64_t maxItems = std::min<uint64_t>(budget / sizeof(float4), 0xfffffff0ull);
+        roundMax = (uint32_t)std::min<uint64_t>(sampleCount, std::max<uint64_t>(1, maxItems / pixels));
+        const uint64_t need = (uint64_t)roundMax * pixels;
+        if (need > ctx->sbufCapacity)
+        {
+            PT_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+            cudaFree(ctx->sbuf);
+            ctx->sbuf = nullptr;
+            ctx->sbufCapacity = 0;
+            PT_CUDA_CHECK(ctx, cudaMalloc((void **)&ctx->sbuf, need * sizeof(float4)));
+            ctx->sbufCapacity = need;
+        }
+    }
 
     ctx->stats.kernel_launches = 0;
     ctx->stats.wavefront_iterations = 0;
+    for (int k = 0; k < PT_KERNEL_CLASS_COUNT; k++)
+    {
+        ctx->stats.kernel_ms[k] = 0.0f;
+        ctx->stats.kernel_launch_count[k] = 0;
+    }
     PT_CUDA_CHECK(ctx, cudaMemsetAsync(ctx->dCounters, 0, sizeof(DeviceCounters), ctx->stream));
     PT_CUDA_CHECK(ctx, cudaEventRecord(ctx->evStart, ctx->stream));
-    if (slots > 0 && sampleCount > 0)
+
+    // optional per-launch CUDA-event timing (pt_set_kernel_timing): (class, start, stop) triples
+    struct Timed
+    {
+        int cls;
+        cudaEvent_t a, b;
+    };
+    std::vector<Timed> timed;
+    const bool timing = ctx->kernelTiming;
+    auto begin = [&](int cls) {
+        if (!timing)
+            return;
+        Timed t { cls, nullptr, nullptr };
+        cudaEventCreate(&t.a);
+        cudaEventCreate(&t.b);
+        cudaEventRecord(t.a, ctx->stream);
+        timed.push_back(t);
+        ctx->stats.kernel_launch_count[cls]++;
+    };
+    auto end = [&]() {
+        if (timing)
+            cudaEventRecord(timed.back().b, ctx->stream);
+    };
+
+    for (uint32_t roundBase = 0; roundMax > 0 && roundBase < sampleCount; roundBase += roundMax)
     {
         RenderConst rc = {};
         rc.scene = ctx->scene;
@@ -701,7 +815,14 @@ pt_status renderSamples(Context *ctx, const pt_render_params *params, uint32_t f
         rc.focalDistance = params->focal_distance;
         rc.missFlags = params->miss_flags;
         rc.hitFlags = params->hit_flags;
-        rc.slotCount = slots;
+        rc.pixelList = ctx->pixelList;
+        rc.pixelCount = pixels;
+        rc.sbuf = ctx->sbuf;
+        rc.roundBase = roundBase;
+        rc.roundSamples = std::min(roundMax, sampleCount - roundBase);
+        rc.itemCount = rc.roundSamples * pixels;
+        rc.slotCount = std::min(ctx->slotCapacity, rc.itemCount);
+        const uint32_t slots = rc.slotCount;
 
         const bool alpha = ctx->scene.hasAlpha != 0;
         const bool statsOn = ctx->collectTraversalStats;
@@ -711,34 +832,11 @@ pt_status renderSamples(Context *ctx, const pt_render_params *params, uint32_t f
         ctx->stats.kernel_launches++;
 
         int cur = 0;
-        const uint32_t checkEvery = 4;
-        // optional per-launch CUDA-event timing (pt_set_kernel_timing): (class, start, stop) triples
-        struct Timed
-        {
-            int cls;
-            cudaEvent_t a, b;
-        };
-        std::vector<Timed> timed;
-        const bool timing = ctx->kernelTiming;
-        auto begin = [&](int cls) {
-            if (!timing)
-                return;
-            Timed t { cls, nullptr, nullptr };
-            cudaEventCreate(&t.a);
-            cudaEventCreate(&t.b);
-            cudaEventRecord(t.a, ctx->stream);
-            timed.push_back(t);
-        };
-        auto end = [&]() {
-            if (timing)
-                cudaEventRecord(timed.back().b, ctx->stream);
-        };
-        for (int k = 0; k < PT_KERNEL_CLASS_COUNT; k++)
-        {
-            ctx->stats.kernel_ms[k] = 0.0f;
-            ctx->stats.kernel_launch_count[k] = 0;
-        }
-        for (uint64_t iter = 0;; iter++)
+        // the host polls the queue sizes every few iterations; a round needs at least
+        // items / slots iterations, so polling starts sparse and gets denser towards the end
+        uint32_t sinceCheck = 0;
+        uint32_t checkEvery = 4;
+        for (;;)
         {
 #define PT_DISPATCH(KERNEL, GRID, BLOCK, ...)                                                                         \
     do                                                                                                                \
@@ -756,7 +854,7 @@ pt_status renderSamples(Context *ctx, const pt_render_params *params, uint32_t f
             PT_DISPATCH(k_extend, gridTrace, 128, rc, cur);
             end();
             begin(PT_KERNEL_SHADE);
-            PT_DISPATCH(k_shade, gridTrace, 128, rc, cur);
+            PT_DISPATCH(k_shade, gridTrace, 128, rc);
             end();
             begin(PT_KERNEL_SHADOW);
             PT_DISPATCH(k_shadow, gridTrace, 128, rc);
@@ -765,31 +863,38 @@ pt_status renderSamples(Context *ctx, const pt_render_params *params, uint32_t f
             k_finish<<<gridWide, 256, 0, ctx->stream>>>(rc, cur);
             end();
 #undef PT_DISPATCH
-            for (int k = 0; k < PT_KERNEL_CLASS_COUNT; k++)
-                ctx->stats.kernel_launch_count[k]++;
             ctx->stats.kernel_launches += 4;
             ctx->stats.wavefront_iterations++;
             cur ^= 1;
-            if ((iter + 1) % checkEvery == 0)
+            if (++sinceCheck >= checkEvery)
             {
+                sinceCheck = 0;
                 PT_CUDA_CHECK(ctx, cudaMemcpyAsync(ctx->hQueueCounts, ctx->dQueueCounts, sizeof(QueueCounts),
                                                    cudaMemcpyDeviceToHost, ctx->stream));
                 PT_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
-                if (ctx->hQueueCounts->active[cur] == 0)
+                const QueueCounts &q = *ctx->hQueueCounts;
+                if (q.cont[cur] + q.fresh[cur] == 0)
                     break;
+                // while work items remain, at least remaining / slots more iterations are needed
+                const uint64_t remaining = q.nextItem < rc.itemCount ? rc.itemCount - q.nextItem : 0;
+                checkEvery = (uint32_t)std::min<uint64_t>(64, std::max<uint64_t>(4, remaining / std::max(1u, slots)));
             }
         }
-        if (timing)
+        begin(PT_KERNEL_FINISH);
+        k_resolve<<<std::min((pixels + 255) / 256, (uint32_t)ctx->smCount * 8), 256, 0, ctx->stream>>>(rc);
+        end();
+        ctx->stats.kernel_launches++;
+    }
+    if (timing)
+    {
+        cudaStreamSynchronize(ctx->stream);
+        for (Timed &t : timed)
         {
-            cudaStreamSynchronize(ctx->stream);
-            for (Timed &t : timed)
-            {
-                float ms = 0.0f;
-                cudaEventElapsedTime(&ms, t.a, t.b);
-                ctx->stats.kernel_ms[t.cls] += ms;
-                cudaEventDestroy(t.a);
-                cudaEventDestroy(t.b);
-            }
+            float ms = 0.0f;
+            cudaEventElapsedTime(&ms, t.a, t.b);
+            ctx->stats.kernel_ms[t.cls] += ms;
+            cudaEventDestroy(t.a);
+            cudaEventDestroy(t.b);
         }
     }
     PT_CUDA_CHECK(ctx, cudaEventRecord(ctx->evStop, ctx->stream));
