@@ -33,8 +33,10 @@ struct QueueCounts
     uint32_t cont[2];  // double-buffered queue sizes: continuing paths ...
     uint32_t fresh[2]; // ... and freshly generated primary rays
     uint32_t hit;      // slots whose closest-hit query hit (input of k_shade)
+    uint32_t done[2];  // slots whose path ended in iteration parity [cur] (input of k_finish)
     uint32_t shadow;
-    uint32_t nextItem; // next work item (sample * pixelCount + pixel-list index) of the round
+    uint32_t extendWork; // ray-queue positions handed out to the persistent warps of k_extend ...
+    uint32_t shadowWork; // ... and k_shadow
     uint32_t pad;
 };
 
@@ -57,14 +59,20 @@ struct PathState
     uint32_t *item;      // work item of the slot (round-relative sample * pixelCount + pixel-list index)
     uint32_t *contQ[2];  // active slots with a continuing path, double buffered
     uint32_t *freshQ[2]; // active slots with a fresh primary ray, double buffered
-    uint32_t *hitQ;      // slots to shade
+    uint32_t *doneQ;     // slots whose path has ended (missed, terminated or out of bounces)
+    uint32_t *hitQ;      // slots to shade (k_extend order)
+    uint32_t *hitKey;    // sort key of hitQ[i]: leaf-order triangle index >> hitKeyShift (0xffffffff = unused)
+    uint32_t *hitQSorted, *hitKeySorted; // after the radix sort: coherent warps for k_shade
     uint32_t *shadowQueue;
 };
+
+#define PT_MAX_POOLS 8
 
 struct Context
 {
     int device = 0;
     int smCount = 0;
+    uint32_t traceBlocksPerSM = 0; // 0 = occupancy query; PT_TRACE_BLOCKS overrides (tuning)
     cudaStream_t stream = nullptr;
     std::string lastError;
 
@@ -82,7 +90,7 @@ struct Context
     float4 *accum = nullptr;
     PathState ps = {};
     std::vector<void *> targetAllocs;
-    size_t slotPoolSize = (size_t)1 << 21;     // paths in flight (PT_SLOTS)
+    size_t slotPoolSize = (size_t)1 << 23;     // paths in flight, all pools together (PT_SLOTS)
     size_t sbufBudgetBytes = (size_t)8 << 30;  // sample-buffer budget (PT_SBUF_MB)
     uint32_t slotCapacity = 0; // size of the slot pool
     // pixel list of the current tile set in 8x4-block order (rebuilt only when the tile list changes)
@@ -96,9 +104,19 @@ struct Context
     bool collectTraversalStats = false;
     bool kernelTiming = false;
 
+    bool sortHits = true;       // PT_SORT_HITS=0 disables (tuning)
+    void *sortTemp = nullptr;   // CUB radix-sort scratch for slotCapacity pairs
+    size_t sortTempBytes = 0;
+
+    uint32_t poolCount = 4;     // independent sub-wavefronts (PT_POOLS)
+    cudaStream_t poolStreams[PT_MAX_POOLS] = {};
+    cudaEvent_t evRound = nullptr;
+
     DeviceCounters *dCounters = nullptr;
-    QueueCounts *dQueueCounts = nullptr;
-    QueueCounts *hQueueCounts = nullptr; // pinned
+    QueueCounts *dQueueCounts = nullptr; // [PT_MAX_POOLS]
+    QueueCounts *hQueueCounts = nullptr; // [PT_MAX_POOLS], pinned
+    uint32_t *dNextItem = nullptr;       // next work item of the round, shared by the pools
+    uint32_t *hNextItem = nullptr;       // pinned
     float *dLut = nullptr;
 
     // stats of the last call
@@ -114,6 +132,7 @@ void freeScene(Context *ctx);
 pt_status uploadTextureSlot(Context *ctx, uint32_t slot, const pt_texture_desc *tex);
 
 // wavefront.cu
+pt_status allocSortTemp(Context *ctx, size_t slots);
 pt_status renderSamples(Context *ctx, const pt_render_params *params, uint32_t firstSample, uint32_t sampleCount,
                         const pt_tile *tiles, uint32_t tileCount);
 pt_status firstHitAov(Context *ctx, const pt_render_params *params, uint32_t width, uint32_t height, pt_hit *out);

@@ -33,6 +33,9 @@ static void freeTarget(Context *ctx)
     ctx->pixelList = nullptr;
     ctx->pixelListValid = false;
     ctx->pixelCount = 0;
+    cudaFree(ctx->sortTemp);
+    ctx->sortTemp = nullptr;
+    ctx->sortTempBytes = 0;
     cudaFree(ctx->sbuf);
     ctx->sbuf = nullptr;
     ctx->sbufCapacity = 0;
@@ -85,6 +88,12 @@ pt_status pt_context_create(int32_t cuda_device, pt_context **out_ctx)
     // tuning knobs (not part of the ABI): PT_SLOTS = paths in flight, PT_SBUF_MB = sample-buffer budget
     if (const char *e = std::getenv("PT_SLOTS"))
         ctx->slotPoolSize = std::max<size_t>(1024, std::strtoull(e, nullptr, 10));
+    if (const char *e = std::getenv("PT_TRACE_BLOCKS"))
+        ctx->traceBlocksPerSM = (uint32_t)std::max(1, std::atoi(e));
+    if (const char *e = std::getenv("PT_POOLS"))
+        ctx->poolCount = (uint32_t)std::min(PT_MAX_POOLS, std::max(1, std::atoi(e)));
+    if (const char *e = std::getenv("PT_SORT_HITS"))
+        ctx->sortHits = std::atoi(e) != 0;
     if (const char *e = std::getenv("PT_SBUF_MB"))
         ctx->sbufBudgetBytes = std::max<size_t>(1, std::strtoull(e, nullptr, 10)) << 20;
 #define PT_CREATE_CHECK(expr)                                                                                         \
@@ -103,8 +112,13 @@ pt_status pt_context_create(int32_t cuda_device, pt_context **out_ctx)
     PT_CREATE_CHECK(cudaEventCreate(&ctx->evStop));
     PT_CREATE_CHECK(cudaMalloc((void **)&ctx->dCounters, sizeof(DeviceCounters)));
     PT_CREATE_CHECK(cudaMemset(ctx->dCounters, 0, sizeof(DeviceCounters)));
-    PT_CREATE_CHECK(cudaMalloc((void **)&ctx->dQueueCounts, sizeof(QueueCounts)));
-    PT_CREATE_CHECK(cudaMallocHost((void **)&ctx->hQueueCounts, sizeof(QueueCounts)));
+    PT_CREATE_CHECK(cudaMalloc((void **)&ctx->dQueueCounts, sizeof(QueueCounts) * PT_MAX_POOLS));
+    PT_CREATE_CHECK(cudaMallocHost((void **)&ctx->hQueueCounts, sizeof(QueueCounts) * PT_MAX_POOLS));
+    PT_CREATE_CHECK(cudaMalloc((void **)&ctx->dNextItem, 4));
+    PT_CREATE_CHECK(cudaMallocHost((void **)&ctx->hNextItem, 4));
+    PT_CREATE_CHECK(cudaEventCreateWithFlags(&ctx->evRound, cudaEventDisableTiming));
+    for (int i = 0; i < PT_MAX_POOLS; i++)
+        PT_CREATE_CHECK(cudaStreamCreateWithFlags(&ctx->poolStreams[i], cudaStreamNonBlocking));
     // decode tables: [0..255] UNORM8 -> float, [256..511] sRGB8 -> linear float (same formulas as the oracle)
     float lut[512];
     for (int i = 0; i < 256; i++)
@@ -131,6 +145,14 @@ void pt_context_destroy(pt_context *ctx)
     freeTarget(ctx);
     cudaFree(ctx->dCounters);
     cudaFree(ctx->dQueueCounts);
+    cudaFree(ctx->dNextItem);
+    if (ctx->hNextItem)
+        cudaFreeHost(ctx->hNextItem);
+    if (ctx->evRound)
+        cudaEventDestroy(ctx->evRound);
+    for (int i = 0; i < PT_MAX_POOLS; i++)
+        if (ctx->poolStreams[i])
+            cudaStreamDestroy(ctx->poolStreams[i]);
     cudaFree(ctx->dLut);
     if (ctx->hQueueCounts)
         cudaFreeHost(ctx->hQueueCounts);
@@ -221,7 +243,19 @@ pt_status pt_render_begin(pt_context *ctx, uint32_t width, uint32_t height)
         PT_T(targetAlloc(ctx, &ps.contQ[1], slots));
         PT_T(targetAlloc(ctx, &ps.freshQ[0], slots));
         PT_T(targetAlloc(ctx, &ps.freshQ[1], slots));
+        PT_T(targetAlloc(ctx, &ps.doneQ, slots));
         PT_T(targetAlloc(ctx, &ps.hitQ, slots));
+        PT_T(targetAlloc(ctx, &ps.hitKey, slots));
+        PT_T(targetAlloc(ctx, &ps.hitQSorted, slots));
+        PT_T(targetAlloc(ctx, &ps.hitKeySorted, slots));
+        {
+            const pt_status s__ = allocSortTemp(ctx, slots);
+            if (s__ != PT_OK)
+            {
+                freeTarget(ctx);
+                return s__;
+            }
+        }
         PT_T(targetAlloc(ctx, &ps.shadowQueue, slots));
 #undef PT_T
         ctx->width = width;

@@ -13,6 +13,16 @@ namespace pt
 
 #define PT_STACK_SIZE 64
 
+// tuning switches (A/B-tested on the B200)
+#ifndef PT_PREFETCH_LEAF
+#define PT_PREFETCH_LEAF 1 // prefetch a leaf's first triangle into L1 when the leaf is postponed
+#endif
+#ifndef PT_PREFETCH_PUSH
+#define PT_PREFETCH_PUSH 0 // prefetch the nearest pushed child node into L1
+#endif
+
+PT_DEV void prefetchL1(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+
 struct Hit
 {
     uint32_t tri; // leaf-order triangle index, 0xffffffff = miss
@@ -37,6 +47,9 @@ struct RaySetup
     float idx, idy, idz; // 1 / dir
     float Sx, Sy, Sz;
     int kx, ky, kz;
+    // float4 index (0 = lo planes, 3 = hi planes) of the slab planes the ray enters through, per axis:
+    // chosen by the SIGN BIT of the direction (so that -0 pairs with idx = -inf)
+    int nearX, nearY, nearZ;
 };
 
 PT_DEV float comp(vec3 v, int k) { return k == 0 ? v.x : (k == 1 ? v.y : v.z); }
@@ -62,6 +75,9 @@ PT_DEV RaySetup setupRay(vec3 o, vec3 d)
     r.Sx = comp(d, r.kx) / dz;
     r.Sy = comp(d, r.ky) / dz;
     r.Sz = 1.0f / dz;
+    r.nearX = __float_as_int(d.x) < 0 ? 3 : 0;
+    r.nearY = __float_as_int(d.y) < 0 ? 3 : 0;
+    r.nearZ = __float_as_int(d.z) < 0 ? 3 : 0;
     return r;
 }
 
@@ -119,25 +135,29 @@ PT_DEV float4 anyHitColor(const DeviceScene &s, uint32_t tri, uint32_t materialI
 }
 
 // One BVH4 node: tests the four child boxes, returns entry distances (INF if missed / empty).
+// The entry / exit planes of every slab are picked by the ray's direction signs when the node is
+// LOADED (per-ray float4 offsets), so a box costs 6 subtractions, 6 multiplications and two
+// four-input max / min (FMNMX + FMNMX3) instead of twelve more two-input min / max.
 PT_DEV void intersectNode(const BvhNode *__restrict__ node, const RaySetup &r, float tmin, float tmax, float d[4],
                           int c[4])
 {
-    const float4 lox = __ldg(&node->lox), loy = __ldg(&node->loy), loz = __ldg(&node->loz);
-    const float4 hix = __ldg(&node->hix), hiy = __ldg(&node->hiy), hiz = __ldg(&node->hiz);
+    const float4 *q = reinterpret_cast<const float4 *>(node);
+    const float4 nx4 = __ldg(q + r.nearX), ny4 = __ldg(q + 1 + r.nearY), nz4 = __ldg(q + 2 + r.nearZ);
+    const float4 fx4 = __ldg(q + 3 - r.nearX), fy4 = __ldg(q + 4 - r.nearY), fz4 = __ldg(q + 5 - r.nearZ);
     const int4 ch = __ldg(&node->child);
-    const float lx[4] = { lox.x, lox.y, lox.z, lox.w }, ly[4] = { loy.x, loy.y, loy.z, loy.w };
-    const float lz[4] = { loz.x, loz.y, loz.z, loz.w }, hx[4] = { hix.x, hix.y, hix.z, hix.w };
-    const float hy[4] = { hiy.x, hiy.y, hiy.z, hiy.w }, hz[4] = { hiz.x, hiz.y, hiz.z, hiz.w };
+    const float nx[4] = { nx4.x, nx4.y, nx4.z, nx4.w }, ny[4] = { ny4.x, ny4.y, ny4.z, ny4.w };
+    const float nz[4] = { nz4.x, nz4.y, nz4.z, nz4.w }, fx[4] = { fx4.x, fx4.y, fx4.z, fx4.w };
+    const float fy[4] = { fy4.x, fy4.y, fy4.z, fy4.w }, fz[4] = { fz4.x, fz4.y, fz4.z, fz4.w };
     c[0] = ch.x, c[1] = ch.y, c[2] = ch.z, c[3] = ch.w;
 #pragma unroll
     for (int i = 0; i < 4; i++)
     {
-        const float ax = (lx[i] - r.org.x) * r.idx, bx = (hx[i] - r.org.x) * r.idx;
-        const float ay = (ly[i] - r.org.y) * r.idy, by = (hy[i] - r.org.y) * r.idy;
-        const float az = (lz[i] - r.org.z) * r.idz, bz = (hz[i] - r.org.z) * r.idz;
-        // fminf/fmaxf drop NaNs (0 * inf on flat boxes)
-        const float t0 = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fmaxf(fminf(az, bz), tmin));
-        const float t1 = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fminf(fmaxf(az, bz), tmax));
+        const float ax = (nx[i] - r.org.x) * r.idx, bx = (fx[i] - r.org.x) * r.idx;
+        const float ay = (ny[i] - r.org.y) * r.idy, by = (fy[i] - r.org.y) * r.idy;
+        const float az = (nz[i] - r.org.z) * r.idz, bz = (fz[i] - r.org.z) * r.idz;
+        // fminf/fmaxf drop NaNs (0 * inf when the origin lies in a slab plane of an axis-parallel ray)
+        const float t0 = fmaxf(fmaxf(ax, ay), fmaxf(az, tmin));
+        const float t1 = fminf(fminf(bx, by), fminf(bz, tmax));
         // conservative (Ize 2013): never cull a box the triangle test could still hit
         d[i] = (c[i] != PT_CHILD_EMPTY && t0 <= t1 * 1.0000004f) ? t0 : INFINITY;
     }
@@ -154,84 +174,134 @@ PT_DEV void intersectNode(const BvhNode *__restrict__ node, const RaySetup &r, f
         c[j] = tc;                                                                                                    \
     }
 
-// CLOSEST = true : nearest hit (+ decal record if ALPHA)
-// CLOSEST = false: any hit in (tmin, tmax) with alpha >= 1 -> hit.tri != miss
-template <bool CLOSEST, bool ALPHA, bool STATS>
-PT_DEV void traverse(const DeviceScene &s, vec3 org, vec3 dir, float tmin, float tmax, Hit &hit, Decal &decal,
-                     TraversalStats &st)
+// Per-lane traversal state machine.  `cur` is the next thing to do: an internal node (>= 0), a
+// leaf (< 0) or PT_CHILD_EMPTY = finished.  The kernels drive it either as a plain per-thread
+// loop (traverse(), standalone queries) or warp-synchronously with dynamic ray fetch (wavefront).
+//   CLOSEST = true : nearest hit (+ decal record if ALPHA)
+//   CLOSEST = false: any hit in (tmin, tmax) with alpha >= 1 -> hit.tri != miss
+template <bool CLOSEST, bool ALPHA, bool STATS> struct Traverser
 {
-    hit.tri = 0xffffffffu;
-    hit.t = tmax;
-    hit.b1 = hit.b2 = 0.0f;
-    uint32_t bestFlat = 0xffffffffu;
-    if (ALPHA)
-        decal.dist = -1.0f;
-    if (s.triCount == 0)
-        return;
-    // A ray with a non-finite component or a zero direction cannot hit anything (every triangle
-    // test evaluates to NaN), but NaN also defeats box culling, so it would walk the WHOLE tree.
-    // Such rays exist by design: refract() returns 0 on total internal reflection and
-    // normalize(0) is NaN; the sample is then restarted (Q7).  Miss immediately.
+    RaySetup r;
+    float tmin, tmax, best;
+    uint32_t bestFlat;
+    Hit hit;
+    Decal decal;
+    TraversalStats st;
+    int cur;
+    int leaf; // postponed leaf (speculative traversal), PT_CHILD_EMPTY = none
+    int sp;
+    // (entry distance bits << 32) | node reference.  The array lives OUTSIDE the struct (a
+    // dynamically indexed member would drag every scalar field into local memory with it).
+    unsigned long long *stack;
+
+    PT_DEV bool finished() const { return cur == PT_CHILD_EMPTY && leaf == PT_CHILD_EMPTY; }
+    PT_DEV bool hasLeaf() const { return leaf != PT_CHILD_EMPTY; }
+    PT_DEV bool atInternal() const { return (unsigned)cur < (unsigned)PT_CHILD_EMPTY; }
+
+    PT_DEV void begin(const DeviceScene &s, vec3 org, vec3 dir, float tmin_, float tmax_)
     {
+        tmin = tmin_;
+        tmax = tmax_;
+        best = tmax_;
+        bestFlat = 0xffffffffu;
+        hit.tri = 0xffffffffu;
+        hit.t = tmax_;
+        hit.b1 = hit.b2 = 0.0f;
+        if (ALPHA)
+            decal.dist = -1.0f;
+        sp = 0;
+        leaf = PT_CHILD_EMPTY;
+        cur = 0; // the root is always an internal node
+        // A ray with a non-finite component or a zero direction cannot hit anything (every triangle
+        // test evaluates to NaN), but NaN also defeats box culling, so it would walk the WHOLE tree.
+        // Such rays exist by design: refract() returns 0 on total internal reflection and
+        // normalize(0) is NaN; the sample is then restarted (Q7).  Miss immediately.
         const float sum = org.x + org.y + org.z + dir.x + dir.y + dir.z;
-        if (!isfinite(sum) || (dir.x == 0.0f && dir.y == 0.0f && dir.z == 0.0f))
-            return;
+        if (s.triCount == 0 || !isfinite(sum) || (dir.x == 0.0f && dir.y == 0.0f && dir.z == 0.0f))
+            cur = PT_CHILD_EMPTY;
+        r = setupRay(org, dir);
     }
-    const RaySetup r = setupRay(org, dir);
 
-    int stackNode[PT_STACK_SIZE];
-    float stackDist[PT_STACK_SIZE];
-    int sp = 0;
-    int cur = 0; // root is always an internal node
-    float best = tmax;
-
-    for (;;)
+    // pop, skipping sub-trees that start beyond the current best (ties are kept)
+    PT_DEV void pop()
     {
-        if (cur >= 0)
+        for (;;)
         {
-            float d[4];
-            int c[4];
-            intersectNode(s.nodes + cur, r, tmin, best, d, c);
-            if (STATS)
-                st.boxTests += 4;
-            // sorting network, ascending by distance (missed children carry INF)
-            PT_CSWAP(0, 1)
-            PT_CSWAP(2, 3)
-            PT_CSWAP(0, 2)
-            PT_CSWAP(1, 3)
-            PT_CSWAP(1, 2)
-            if (d[0] == INFINITY)
+            if (sp == 0)
             {
-                // nothing hit: pop
                 cur = PT_CHILD_EMPTY;
+                return;
             }
-            else
-            {
-                cur = c[0];
-                // push the rest, farthest first
-                if (d[3] != INFINITY && sp < PT_STACK_SIZE)
-                {
-                    stackNode[sp] = c[3];
-                    stackDist[sp++] = d[3];
-                }
-                if (d[2] != INFINITY && sp < PT_STACK_SIZE)
-                {
-                    stackNode[sp] = c[2];
-                    stackDist[sp++] = d[2];
-                }
-                if (d[1] != INFINITY && sp < PT_STACK_SIZE)
-                {
-                    stackNode[sp] = c[1];
-                    stackDist[sp++] = d[1];
-                }
-                continue;
-            }
+            const unsigned long long e = stack[--sp];
+            cur = (int)(uint32_t)e;
+            if (!CLOSEST || __uint_as_float((uint32_t)(e >> 32)) <= best)
+                return;
         }
-        else
+    }
+
+    PT_DEV void push(int node, float dist)
+    {
+        if (sp < PT_STACK_SIZE)
+            stack[sp++] = ((unsigned long long)__float_as_uint(dist) << 32) | (uint32_t)node;
+    }
+
+    // cur is an internal node: test its children, descend into the nearest, push the others
+    PT_DEV void nodeStep(const DeviceScene &s)
+    {
+        float d[4];
+        int c[4];
+        intersectNode(s.nodes + cur, r, tmin, best, d, c);
+        if (STATS)
+            st.boxTests += 4;
+        // sorting network, ascending by distance (missed children carry INF)
+        PT_CSWAP(0, 1)
+        PT_CSWAP(2, 3)
+        PT_CSWAP(0, 2)
+        PT_CSWAP(1, 3)
+        PT_CSWAP(1, 2)
+        if (d[0] == INFINITY)
         {
-            // leaf
-            const uint32_t code = (uint32_t)~cur;
+            pop();
+            return;
+        }
+        cur = c[0];
+        // push the rest, farthest first
+        if (d[3] != INFINITY)
+            push(c[3], d[3]);
+        if (d[2] != INFINITY)
+            push(c[2], d[2]);
+        if (d[1] != INFINITY)
+        {
+            push(c[1], d[1]);
+#if PT_PREFETCH_PUSH
+            if (c[1] >= 0)
+                prefetchL1(s.nodes + c[1]);
+#endif
+        }
+    }
+
+    // speculative traversal (Aila & Laine 2009): the first leaf found is set aside and the lane keeps
+    // descending, so that the lanes of a warp reach the triangle tests together
+    PT_DEV void postponeLeaf(const float4 *sPrefetchTri)
+    {
+        if (cur < 0 && leaf == PT_CHILD_EMPTY)
+        {
+            leaf = cur;
+#if PT_PREFETCH_LEAF
+            prefetchL1(sPrefetchTri + 3 * (size_t)(((uint32_t)~cur) >> 2));
+#endif
+            pop();
+        }
+    }
+
+    // tests the triangles of the postponed leaf (and of a second leaf waiting in cur)
+    PT_DEV void leafStep(const DeviceScene &s)
+    {
+        while (leaf != PT_CHILD_EMPTY)
+        {
+            const uint32_t code = (uint32_t)~leaf;
             const uint32_t first = code >> 2, count = (code & 3u) + 1;
+            leaf = PT_CHILD_EMPTY;
             for (uint32_t i = 0; i < count; i++)
             {
                 const uint32_t tri = first + i;
@@ -278,19 +348,187 @@ PT_DEV void traverse(const DeviceScene &s, vec3 org, vec3 dir, float tmin, float
                 hit.b1 = b1;
                 hit.b2 = b2;
                 if (!CLOSEST)
-                    return; // gl_RayFlagsTerminateOnFirstHitEXT
+                {
+                    cur = PT_CHILD_EMPTY; // gl_RayFlagsTerminateOnFirstHitEXT
+                    sp = 0;
+                    return;
+                }
                 best = t;
                 bestFlat = flat;
             }
+            // a second leaf found while this one was postponed
+            if (cur < 0)
+            {
+                leaf = cur;
+                pop();
+            }
         }
-        // pop, skipping sub-trees that start beyond the current best (ties are kept)
+    }
+};
+
+// plain per-thread traversal (standalone queries)
+template <bool CLOSEST, bool ALPHA, bool STATS>
+PT_DEV void traverse(const DeviceScene &s, vec3 org, vec3 dir, float tmin, float tmax, Hit &hit, Decal &decal,
+                     TraversalStats &st)
+{
+    unsigned long long stack[PT_STACK_SIZE];
+    Traverser<CLOSEST, ALPHA, STATS> tr;
+    tr.stack = stack;
+    tr.st = st;
+    tr.begin(s, org, dir, tmin, tmax);
+    while (!tr.finished())
+    {
+        while (tr.atInternal())
+            tr.nodeStep(s);
+        tr.postponeLeaf(s.triPos);
+        tr.leafStep(s);
+    }
+    hit = tr.hit;
+    decal = tr.decal;
+    st = tr.st;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Warp-synchronous traversal with dynamic ray fetch (Aila & Laine 2009, persistent warps).
+//
+// Every warp of a persistent grid keeps 32 traversal state machines.  Rays differ wildly in
+// length; instead of letting finished lanes idle until the longest ray of the warp is done, the
+// warp refills its idle lanes from the ray queue as soon as fewer than PT_REFILL_LANES lanes are
+// still traversing.  Queue positions are handed out to warps in chunks of PT_FETCH_CHUNK through
+// one atomic per chunk; inside a chunk lanes take positions by ballot arithmetic.
+//
+//   loadSlot(i)        : issue the load of queue entry i (the slot index)
+//   loadRay(slot)      : issue the loads of that slot's ray, return them as a RayPacket
+//   commit(tr, slot)   : ray finished — write the result
+//
+// Two details matter as much as the refill itself:
+//   * ray PREFETCH: a refill needs queue -> slot -> ray, two dependent DRAM round trips during which
+//     the whole warp would stall.  The warp therefore keeps the next 32 rays of its chunk in
+//     registers (lane L holds buffered ray L); a refill is a handful of shuffles, and the loads
+//     for the following 32 rays are issued right away, to complete behind the traversal work
+//     (two stages: the slot indices of batch k+2 are requested together with the rays of batch k+1,
+//     so neither of the two dependent loads is ever waited for).
+//   * DEFERRED commit: finished lanes keep their result until the next refill point, where all of
+//     them push to the hit / done queues together — one aggregated atomic per queue and refill
+//     instead of one per lane (same-address atomics are serialised by the L2).
+// ---------------------------------------------------------------------------------------------
+#define PT_FETCH_CHUNK 128u
+#ifndef PT_REFILL_LANES
+#define PT_REFILL_LANES 20
+#endif
+
+struct RayPacket
+{
+    uint32_t slot;
+    float ox, oy, oz, dx, dy, dz, tmax;
+};
+
+template <class TR, class LoadSlot, class LoadRay, class Commit>
+PT_DEV void tracePersistent(const DeviceScene &s, uint32_t n, uint32_t *workCounter, TR &tr, float tmin,
+                            LoadSlot loadSlot, LoadRay loadRay, Commit commit)
+{
+    const unsigned FULL = 0xffffffffu;
+    const unsigned lane = threadIdx.x & 31u;
+    const unsigned ltMask = (1u << lane) - 1u;
+    uint32_t wBase = 0, wEnd = 0; // warp-uniform: the not yet buffered rest of the warp's chunk
+    bool exhausted = false;       // warp-uniform: the queue has no more chunks
+    uint32_t pfPos = 0, pfCount = 0; // warp-uniform: lanes [pfPos, pfCount) hold buffered rays
+    RayPacket pf = {};
+    bool haveRay = false, pending = false;
+    uint32_t slot = 0;
+    tr.cur = tr.leaf = PT_CHILD_EMPTY;
+
+    uint32_t nxCount = 0; // warp-uniform: lanes [0, nxCount) hold the slot indices of the batch after the buffer
+    uint32_t nxSlot = 0;
+    // stage 1: request the slot indices of the next batch of the warp's chunk
+    auto prefetchSlots = [&]() {
+        nxCount = 0;
+        if (exhausted)
+            return;
+        if (wBase == wEnd)
+        {
+            uint32_t b = 0;
+            if (lane == 0)
+                b = atomicAdd(workCounter, PT_FETCH_CHUNK);
+            b = __shfl_sync(FULL, b, 0);
+            if (b >= n)
+            {
+                exhausted = true;
+                return;
+            }
+            wBase = b;
+            wEnd = min(b + PT_FETCH_CHUNK, n);
+        }
+        nxCount = min(32u, wEnd - wBase);
+        if (lane < nxCount)
+            nxSlot = loadSlot(wBase + lane);
+        wBase += nxCount;
+    };
+    // stage 2: request the rays of the batch whose slot indices arrived meanwhile, then stage 1 again
+    auto prefetch = [&]() {
+        pfPos = 0;
+        pfCount = nxCount;
+        if (lane < nxCount)
+            pf = loadRay(nxSlot);
+        prefetchSlots();
+    };
+    prefetchSlots();
+    prefetch();
+
+    for (;;)
+    {
+        // ---- results of the lanes that finished since the last refill -------------------------------
+        if (pending)
+            commit(tr, slot);
+        pending = false;
+        // ---- refill idle lanes from the register buffer ----------------------------------------
+        unsigned idle = __ballot_sync(FULL, !haveRay);
+        while (idle != 0 && pfPos < pfCount)
+        {
+            const uint32_t take = min((uint32_t)__popc(idle), pfCount - pfPos);
+            const uint32_t rank = __popc(idle & ltMask);
+            const int src = (int)((pfPos + rank) & 31u);
+            RayPacket p;
+            p.slot = __shfl_sync(FULL, pf.slot, src);
+            p.ox = __shfl_sync(FULL, pf.ox, src);
+            p.oy = __shfl_sync(FULL, pf.oy, src);
+            p.oz = __shfl_sync(FULL, pf.oz, src);
+            p.dx = __shfl_sync(FULL, pf.dx, src);
+            p.dy = __shfl_sync(FULL, pf.dy, src);
+            p.dz = __shfl_sync(FULL, pf.dz, src);
+            p.tmax = __shfl_sync(FULL, pf.tmax, src);
+            if (!haveRay && rank < take)
+            {
+                slot = p.slot;
+                tr.begin(s, V3(p.ox, p.oy, p.oz), V3(p.dx, p.dy, p.dz), tmin, p.tmax);
+                haveRay = true;
+            }
+            pfPos += take;
+            if (pfPos == pfCount && nxCount != 0)
+                prefetch(); // loads complete behind the traversal below
+            idle = __ballot_sync(FULL, !haveRay);
+        }
+        if (idle == FULL)
+            return; // nothing left anywhere
+        // ---- traverse until too many lanes have finished -----------------------------------------
+        const int keepGoing = (pfPos == pfCount) ? 1 : PT_REFILL_LANES;
         for (;;)
         {
-            if (sp == 0)
-                return;
-            --sp;
-            cur = stackNode[sp];
-            if (!CLOSEST || stackDist[sp] <= best)
+            // internal nodes, until every lane either holds a leaf or has nothing left to descend into;
+            // lanes that already hold a leaf keep traversing speculatively meanwhile
+            do
+            {
+                if (tr.atInternal())
+                    tr.nodeStep(s);
+                tr.postponeLeaf(s.triPos);
+            } while (__any_sync(FULL, tr.atInternal() && !tr.hasLeaf()));
+            tr.leafStep(s);
+            if (haveRay && tr.finished())
+            {
+                pending = true;
+                haveRay = false;
+            }
+            if (__popc(__ballot_sync(FULL, haveRay)) < keepGoing)
                 break;
         }
     }

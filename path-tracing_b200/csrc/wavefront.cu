@@ -24,6 +24,8 @@
 #include "shading.cuh"
 #include "traverse.cuh"
 
+#include <cub/device/device_radix_sort.cuh>
+
 #include <algorithm>
 #include <cstring>
 
@@ -33,7 +35,14 @@ namespace pt
 namespace
 {
 
-constexpr uint32_t kStateDone = 0x100u;
+// resident 128-thread blocks per SM the register allocation must allow (tuned on the B200)
+#ifndef PT_TRACE_MIN_BLOCKS
+#define PT_TRACE_MIN_BLOCKS 6
+#endif
+#ifndef PT_SHADE_MIN_BLOCKS
+#define PT_SHADE_MIN_BLOCKS 4
+#endif
+
 constexpr uint32_t kMaxRestarts = 1024; // the reference's restart loop is unbounded; see oracle
 
 struct RenderConst
@@ -49,13 +58,17 @@ struct RenderConst
     uint32_t bounceCount;
     float lensRadius, focalDistance;
     uint32_t missFlags, hitFlags;
-    uint32_t slotCount;          // slots in use (<= slot capacity, <= itemCount)
+    uint32_t slotBase;           // first slot of this pool
+    uint32_t slotCount;          // slots of this pool in use
+    uint32_t *nextItem;          // next work item of the round (shared by all pools)
     const uint32_t *pixelList;   // pixels of the tile set in 8x4-block order
     uint32_t pixelCount;
     float4 *sbuf;                // [roundSamples][pixelCount] radiance of the finished samples of the round
     uint32_t roundBase;          // first sample of the round, relative to firstSample
     uint32_t roundSamples;
     uint32_t itemCount;          // roundSamples * pixelCount; item = sample * pixelCount + pixel-list index
+    uint32_t hitKeyShift;        // hit sort key = leaf-order triangle index >> hitKeyShift
+    uint32_t sortHits;           // k_shade reads hitQSorted instead of hitQ
 };
 
 __device__ __forceinline__ uint32_t laneId() { return threadIdx.x & 31u; }
@@ -116,13 +129,14 @@ __device__ __forceinline__ void startItem(const RenderConst &rc, uint32_t slot, 
     generatePath(rc, slot, pixel, initRng(px, py, rc.width, rc.firstSample + rc.roundBase + s), 0);
 }
 
-// slot i starts with work item i of the round
+// slot i (of all pools together) starts with work item i of the round
 __global__ void __launch_bounds__(256) k_init(RenderConst rc)
 {
     const uint32_t stride = gridDim.x * blockDim.x;
-    for (uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x; slot < rc.slotCount; slot += stride)
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < rc.slotCount; i += stride)
     {
-        rc.ps.freshQ[0][slot] = slot;
+        const uint32_t slot = rc.slotBase + i;
+        rc.ps.freshQ[0][i] = slot;
         startItem(rc, slot, slot);
     }
     if (blockIdx.x == 0 && threadIdx.x == 0)
@@ -133,7 +147,10 @@ __global__ void __launch_bounds__(256) k_init(RenderConst rc)
         rc.qc->fresh[1] = 0;
         rc.qc->shadow = 0;
         rc.qc->hit = 0;
-        rc.qc->nextItem = rc.slotCount;
+        rc.qc->done[0] = 0;
+        rc.qc->done[1] = 0;
+        rc.qc->extendWork = 0;
+        rc.qc->shadowWork = 0;
     }
 }
 
@@ -160,50 +177,55 @@ __device__ __forceinline__ vec3 skyRadiance(const RenderConst &rc, vec3 dir)
 // ---------------------------------------------------------------------------------------------
 // extend
 // ---------------------------------------------------------------------------------------------
-template <bool ALPHA, bool STATS> __global__ void __launch_bounds__(128) k_extend(RenderConst rc, int cur)
+template <bool ALPHA, bool STATS> __global__ void __launch_bounds__(128, PT_TRACE_MIN_BLOCKS) k_extend(RenderConst rc, int cur)
 {
     const uint32_t nCont = rc.qc->cont[cur], n = nCont + rc.qc->fresh[cur];
-    if (blockIdx.x == 0 && threadIdx.x == 0)
-    {
-        rc.qc->cont[cur ^ 1] = 0;
-        rc.qc->fresh[cur ^ 1] = 0;
-        rc.qc->shadow = 0;
-    }
-    const uint32_t stride = gridDim.x * blockDim.x;
+    // (the counters of the queues this iteration fills were reset by k_init / the previous k_finish)
     uint32_t hits = 0;
-    TraversalStats st = { 0, 0, 0 };
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
-    {
-        const uint32_t slot = activeSlot(rc, cur, i, nCont);
-        const float4 o = rc.ps.rayO[slot], d = rc.ps.rayD[slot];
-        Hit hit;
-        Decal decal;
-        traverse<true, ALPHA, STATS>(rc.scene, V3(o), V3(d), 0.00001f, 10000.0f, hit, decal, st);
-        if (hit.tri == 0xffffffffu)
-        {
-            // miss.rmiss + raygen.rgen:71-75: the path ends with the sky radiance
-            const float4 thr4 = rc.ps.thr[slot];
-            float4 rad4 = rc.ps.rad[slot];
-            const vec3 radiance = V3(rad4) + V3(thr4) * skyRadiance(rc, V3(d));
-            rc.ps.rad[slot] = make_float4(radiance.x, radiance.y, radiance.z, rad4.w);
-            rc.ps.thr[slot] = make_float4(thr4.x, thr4.y, thr4.z, __uint_as_float(__float_as_uint(thr4.w) | kStateDone));
-            continue;
-        }
-        rc.ps.hit[slot] = make_float4(__uint_as_float(hit.tri), hit.t, hit.b1, hit.b2);
-        if (ALPHA)
-        {
-            rc.ps.decal[slot] = make_float4(decal.r, decal.g, decal.b, decal.dist);
-            rc.ps.decalA[slot] = decal.a;
-        }
-        rc.ps.hitQ[atomicAggInc(&rc.qc->hit)] = slot;
-        hits++;
-    }
+    unsigned long long stack[PT_STACK_SIZE];
+    Traverser<true, ALPHA, STATS> tr;
+    tr.stack = stack;
+    tr.st = TraversalStats { 0, 0, 0 };
+    tracePersistent(
+        rc.scene, n, &rc.qc->extendWork, tr, 0.00001f,
+        [&](uint32_t i) { return activeSlot(rc, cur, i, nCont); },
+        [&](uint32_t slot) {
+            RayPacket p;
+            p.slot = slot;
+            const float4 o = rc.ps.rayO[p.slot], d = rc.ps.rayD[p.slot];
+            p.ox = o.x, p.oy = o.y, p.oz = o.z;
+            p.dx = d.x, p.dy = d.y, p.dz = d.z;
+            p.tmax = 10000.0f;
+            return p;
+        },
+        [&](Traverser<true, ALPHA, STATS> &t, uint32_t slot) {
+            if (t.hit.tri == 0xffffffffu)
+            {
+                // miss.rmiss + raygen.rgen:71-75: the path ends with the sky radiance
+                const float4 thr4 = rc.ps.thr[slot], d = rc.ps.rayD[slot];
+                const float4 rad4 = rc.ps.rad[slot];
+                const vec3 radiance = V3(rad4) + V3(thr4) * skyRadiance(rc, V3(d));
+                rc.ps.rad[slot] = make_float4(radiance.x, radiance.y, radiance.z, rad4.w);
+                rc.ps.doneQ[atomicAggInc(&rc.qc->done[cur])] = slot;
+                return;
+            }
+            rc.ps.hit[slot] = make_float4(__uint_as_float(t.hit.tri), t.hit.t, t.hit.b1, t.hit.b2);
+            if (ALPHA)
+            {
+                rc.ps.decal[slot] = make_float4(t.decal.r, t.decal.g, t.decal.b, t.decal.dist);
+                rc.ps.decalA[slot] = t.decal.a;
+            }
+            const uint32_t pos = atomicAggInc(&rc.qc->hit);
+            rc.ps.hitQ[pos] = slot;
+            rc.ps.hitKey[pos] = t.hit.tri >> rc.hitKeyShift;
+            hits++;
+        });
     warpAdd(&rc.counters->hits, hits);
     if (STATS)
     {
-        warpAdd(&rc.counters->boxClosest, st.boxTests);
-        warpAdd(&rc.counters->triClosest, st.triTests);
-        warpAdd(&rc.counters->alphaClosest, st.alphaTests);
+        warpAdd(&rc.counters->boxClosest, tr.st.boxTests);
+        warpAdd(&rc.counters->triClosest, tr.st.triTests);
+        warpAdd(&rc.counters->alphaClosest, tr.st.alphaTests);
     }
     if (blockIdx.x == 0 && threadIdx.x == 0)
         atomicAdd(&rc.counters->raysClosest, (unsigned long long)n);
@@ -234,7 +256,12 @@ __device__ __forceinline__ MaterialSample sampleMaterial(const DeviceScene &s, u
     const MaterialRaw *m = (type == 0 ? s.materials[0] : type == 1 ? s.materials[1] : s.materials[2]) + index;
     const float4 q0 = __ldg(&m->q[0]), q1 = __ldg(&m->q[1]), q2 = __ldg(&m->q[2]);
     const float4 q3 = __ldg(&m->q[3]), q4 = __ldg(&m->q[4]), q5 = __ldg(&m->q[5]);
-    auto tex = [&](float idxBits) { return textureGrad(s, s.textures[__float_as_uint(idxBits)], u, v, deriv, texels); };
+    auto tex = [&](float idxBits) {
+        const uint32_t slot = __float_as_uint(idxBits);
+        if (texels)
+            *texels += textureGradTexels(s, slot, deriv);
+        return textureGrad(s, slot, u, v, deriv);
+    };
     r.AttenuationColor = V3(q3.x, q3.y, q3.z);
     r.AttenuationDistance = q3.w;
     if (type == 0)
@@ -313,7 +340,7 @@ __device__ __forceinline__ LightSample sampleLight(const LightBlock *lb, vec3 u,
 // ---------------------------------------------------------------------------------------------
 // shade: closestHit.rchit, then the raygen bounce logic (misses are finished by k_extend)
 // ---------------------------------------------------------------------------------------------
-template <bool ALPHA, bool STATS> __global__ void __launch_bounds__(128) k_shade(RenderConst rc)
+template <bool ALPHA, bool STATS> __global__ void __launch_bounds__(128, PT_SHADE_MIN_BLOCKS) k_shade(RenderConst rc, int cur)
 {
     const uint32_t n = rc.qc->hit;
     const uint32_t stride = gridDim.x * blockDim.x;
@@ -321,7 +348,7 @@ template <bool ALPHA, bool STATS> __global__ void __launch_bounds__(128) k_shade
     uint32_t texels = 0;
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
     {
-        const uint32_t slot = rc.ps.hitQ[i];
+        const uint32_t slot = (rc.sortHits ? rc.ps.hitQSorted : rc.ps.hitQ)[i];
         const float4 hitv = rc.ps.hit[slot];
         const float4 rayO = rc.ps.rayO[slot], rayD = rc.ps.rayD[slot];
         float4 thr4 = rc.ps.thr[slot];
@@ -485,15 +512,25 @@ template <bool ALPHA, bool STATS> __global__ void __launch_bounds__(128) k_shade
         uint32_t bounce = (state & 0xffu) + 1;
         if (bounce >= rc.bounceCount)
             done = true;
-        state = bounce | (done ? kStateDone : 0u);
+        state = bounce;
+        // continuing paths go straight to the next iteration's queue (in shading = triangle order, so
+        // the next extend starts from spatially coherent origins); finished ones to k_finish
+        if (done)
+            rc.ps.doneQ[atomicAggInc(&rc.qc->done[cur])] = slot;
+        else
+            (cur ? rc.ps.contQ[0] : rc.ps.contQ[1])[atomicAggInc(&rc.qc->cont[cur ^ 1])] = slot;
 
         rc.ps.rad[slot] = make_float4(radiance.x, radiance.y, radiance.z, rad4.w);
-        rc.ps.thr[slot] = make_float4(throughput.x, throughput.y, throughput.z, __uint_as_float(state));
-        rc.ps.rayO[slot] = make_float4(newPos.x, newPos.y, newPos.z, maxRoughness);
+        // the rng state outlives the path (a NaN/Inf restart continues the stream, raygen.rgen:99-112)
         rc.ps.rayD[slot] = make_float4(newDir.x, newDir.y, newDir.z, __uint_as_float(rng));
-        rc.ps.diff0[slot] = make_float4(rd.rxOrigin.x, rd.rxOrigin.y, rd.rxOrigin.z, rd.rxDirection.x);
-        rc.ps.diff1[slot] = make_float4(rd.rxDirection.y, rd.rxDirection.z, rd.ryOrigin.x, rd.ryOrigin.y);
-        rc.ps.diff2[slot] = make_float4(rd.ryOrigin.z, rd.ryDirection.x, rd.ryDirection.y, rd.ryDirection.z);
+        if (!done)
+        {
+            rc.ps.thr[slot] = make_float4(throughput.x, throughput.y, throughput.z, __uint_as_float(state));
+            rc.ps.rayO[slot] = make_float4(newPos.x, newPos.y, newPos.z, maxRoughness);
+            rc.ps.diff0[slot] = make_float4(rd.rxOrigin.x, rd.rxOrigin.y, rd.rxOrigin.z, rd.rxDirection.x);
+            rc.ps.diff1[slot] = make_float4(rd.rxDirection.y, rd.rxDirection.z, rd.ryOrigin.x, rd.ryOrigin.y);
+            rc.ps.diff2[slot] = make_float4(rd.ryOrigin.z, rd.ryDirection.x, rd.ryDirection.y, rd.ryDirection.z);
+        }
     }
     if (STATS)
         warpAdd(&rc.counters->texels, texels);
@@ -502,33 +539,41 @@ template <bool ALPHA, bool STATS> __global__ void __launch_bounds__(128) k_shade
 // ---------------------------------------------------------------------------------------------
 // shadow
 // ---------------------------------------------------------------------------------------------
-template <bool ALPHA, bool STATS> __global__ void __launch_bounds__(128) k_shadow(RenderConst rc)
+template <bool ALPHA, bool STATS> __global__ void __launch_bounds__(128, PT_TRACE_MIN_BLOCKS) k_shadow(RenderConst rc)
 {
     const uint32_t n = rc.qc->shadow;
-    const uint32_t stride = gridDim.x * blockDim.x;
-    TraversalStats st = { 0, 0, 0 };
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
-    {
-        const uint32_t slot = rc.ps.shadowQueue[i];
-        const float4 o = rc.ps.shO[slot], d = rc.ps.shD[slot];
-        Hit hit;
-        Decal decal;
-        traverse<false, ALPHA, STATS>(rc.scene, V3(o), V3(d), 0.00001f, o.w, hit, decal, st);
-        if (hit.tri == 0xffffffffu)
-        {
-            const float4 c = rc.ps.shC[slot];
-            float4 r = rc.ps.rad[slot];
-            r.x += c.x;
-            r.y += c.y;
-            r.z += c.z;
-            rc.ps.rad[slot] = r;
-        }
-    }
+    unsigned long long stack[PT_STACK_SIZE];
+    Traverser<false, ALPHA, STATS> tr;
+    tr.stack = stack;
+    tr.st = TraversalStats { 0, 0, 0 };
+    tracePersistent(
+        rc.scene, n, &rc.qc->shadowWork, tr, 0.00001f,
+        [&](uint32_t i) { return rc.ps.shadowQueue[i]; },
+        [&](uint32_t slot) {
+            RayPacket p;
+            p.slot = slot;
+            const float4 o = rc.ps.shO[p.slot], d = rc.ps.shD[p.slot];
+            p.ox = o.x, p.oy = o.y, p.oz = o.z;
+            p.dx = d.x, p.dy = d.y, p.dz = d.z;
+            p.tmax = o.w;
+            return p;
+        },
+        [&](Traverser<false, ALPHA, STATS> &t, uint32_t slot) {
+            if (t.hit.tri == 0xffffffffu)
+            {
+                const float4 c = rc.ps.shC[slot];
+                float4 r = rc.ps.rad[slot];
+                r.x += c.x;
+                r.y += c.y;
+                r.z += c.z;
+                rc.ps.rad[slot] = r;
+            }
+        });
     if (STATS)
     {
-        warpAdd(&rc.counters->boxShadow, st.boxTests);
-        warpAdd(&rc.counters->triShadow, st.triTests);
-        warpAdd(&rc.counters->alphaShadow, st.alphaTests);
+        warpAdd(&rc.counters->boxShadow, tr.st.boxTests);
+        warpAdd(&rc.counters->triShadow, tr.st.triTests);
+        warpAdd(&rc.counters->alphaShadow, tr.st.alphaTests);
     }
     if (blockIdx.x == 0 && threadIdx.x == 0)
         atomicAdd(&rc.counters->raysShadow, (unsigned long long)n);
@@ -537,54 +582,97 @@ template <bool ALPHA, bool STATS> __global__ void __launch_bounds__(128) k_shado
 // ---------------------------------------------------------------------------------------------
 // finish: raygen.rgen:99-117 for finished paths, then the next work item
 // ---------------------------------------------------------------------------------------------
+// Block-aggregated queue reservation: every thread of the block calls it (uniform control flow);
+// threads with want = true get consecutive positions, the whole block costs ONE atomic.  Hot
+// same-address atomics are serialised by the L2 (a few ns each), so per-warp reservations made
+// k_finish atomic-bound.
+template <int WARPS> __device__ __forceinline__ uint32_t blockReserve(bool want, uint32_t *counter, uint32_t *scratch)
+{
+    const unsigned lane = laneId(), warp = threadIdx.x >> 5;
+    const unsigned mask = __ballot_sync(0xffffffffu, want);
+    if (lane == 0)
+        scratch[warp] = __popc(mask);
+    __syncthreads();
+    if (warp == 0)
+    {
+        const uint32_t v = lane < WARPS ? scratch[lane] : 0;
+        uint32_t incl = v;
+#pragma unroll
+        for (int o = 1; o < WARPS; o <<= 1)
+        {
+            const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+            if ((int)lane >= o)
+                incl += t;
+        }
+        const uint32_t total = __shfl_sync(0xffffffffu, incl, WARPS - 1);
+        uint32_t base = 0;
+        if (lane == 0 && total)
+            base = atomicAdd(counter, total);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (lane < WARPS)
+            scratch[WARPS + lane] = base + incl - v;
+    }
+    __syncthreads();
+    return scratch[WARPS + warp] + __popc(mask & ((1u << lane) - 1u));
+}
+
 __global__ void __launch_bounds__(256) k_finish(RenderConst rc, int cur)
 {
-    const uint32_t nCont = rc.qc->cont[cur], n = nCont + rc.qc->fresh[cur];
+    __shared__ uint32_t scratch[2][16];
+    const uint32_t n = rc.qc->done[cur];
+    // Counters of the queues the NEXT iteration fills.  None of them is read by this kernel, and
+    // everything that read them in this iteration has completed (stream order).
+    if (blockIdx.x == 0 && threadIdx.x == 0)
+    {
+        rc.qc->cont[cur] = 0;
+        rc.qc->fresh[cur] = 0;
+        rc.qc->hit = 0;
+        rc.qc->shadow = 0;
+        rc.qc->extendWork = 0;
+        rc.qc->shadowWork = 0;
+        rc.qc->done[cur ^ 1] = 0;
+    }
     const uint32_t stride = gridDim.x * blockDim.x;
     uint32_t samples = 0, restarts = 0;
-    if (blockIdx.x == 0 && threadIdx.x == 0)
-        rc.qc->hit = 0; // consumed by this iteration's k_shade, refilled by the next k_extend
-    uint32_t *contOut = cur ? rc.ps.contQ[0] : rc.ps.contQ[1];
     uint32_t *freshOut = cur ? rc.ps.freshQ[0] : rc.ps.freshQ[1];
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+    // uniform trip count: every thread of the block takes part in the block-wide reservations
+    for (uint32_t first = blockIdx.x * blockDim.x; first < n; first += stride)
     {
-        const uint32_t slot = activeSlot(rc, cur, i, nCont);
-        const uint32_t state = __float_as_uint(rc.ps.thr[slot].w);
-        if (!(state & kStateDone))
+        const uint32_t i = first + threadIdx.x;
+        const bool valid = i < n;
+        uint32_t slot = 0, item = 0, restartCount = 0;
+        bool restart = false, park = false;
+        if (valid)
         {
-            contOut[atomicAggInc(&rc.qc->cont[cur ^ 1])] = slot;
-            continue;
-        }
-        float4 r = rc.ps.rad[slot];
-        const uint32_t item = rc.ps.item[slot];
-        const uint32_t restartCount = __float_as_uint(r.w);
-        samples++;
-        const bool isBad = bad(r.x) || bad(r.y) || bad(r.z);
-        if (isBad && restartCount < kMaxRestarts)
-        {
+            slot = rc.ps.doneQ[i];
+            const float4 r = rc.ps.rad[slot];
+            item = rc.ps.item[slot];
+            restartCount = __float_as_uint(r.w);
+            samples++;
+            const bool isBad = bad(r.x) || bad(r.y) || bad(r.z);
             // radiance = 0; smpl = -1: the sample is redone with the ADVANCED rng state
+            restart = isBad && restartCount < kMaxRestarts;
+            park = !restart;
+            // park the sample; k_resolve adds the round's samples to the image in sample order
+            if (park)
+                rc.sbuf[item] = isBad ? make_float4(0.0f, 0.0f, 0.0f, 0.0f) : r;
+        }
+        // pull the next work items: the threads of a block that finish together take consecutive
+        // items (= neighbouring pixels, 8x4 blocks) and consecutive positions of the fresh queue
+        const uint32_t next = blockReserve<8>(park, rc.nextItem, scratch[0]);
+        const bool regenerate = park && next < rc.itemCount;
+        const uint32_t pos = blockReserve<8>(restart || regenerate, &rc.qc->fresh[cur ^ 1], scratch[1]);
+        if (restart)
+        {
             restarts++;
             const uint32_t s = item / rc.pixelCount, pi = item - s * rc.pixelCount;
             generatePath(rc, slot, __ldg(rc.pixelList + pi), __float_as_uint(rc.ps.rayD[slot].w), restartCount + 1);
-            freshOut[atomicAggInc(&rc.qc->fresh[cur ^ 1])] = slot;
-            continue;
+            freshOut[pos] = slot;
         }
-        // park the sample; k_resolve adds the round's samples to the image in sample order
-        rc.sbuf[item] = isBad ? make_float4(0.0f, 0.0f, 0.0f, 0.0f) : r;
-        // pull the next work item: the lanes of a warp that finish together take consecutive items
-        // (= consecutive pixels of an 8x4 block) and consecutive positions of the fresh queue
-        const unsigned mask = __activemask();
-        const int leader = __ffs(mask) - 1;
-        const uint32_t rank = __popc(mask & ((1u << laneId()) - 1u));
-        uint32_t base = 0;
-        if ((int)laneId() == leader)
-            base = atomicAdd(&rc.qc->nextItem, (uint32_t)__popc(mask));
-        base = __shfl_sync(mask, base, leader);
-        const uint32_t next = base + rank;
-        if (next < rc.itemCount)
+        else if (regenerate)
         {
             startItem(rc, slot, next);
-            freshOut[atomicAggInc(&rc.qc->fresh[cur ^ 1])] = slot;
+            freshOut[pos] = slot;
         }
     }
     warpAdd(&rc.counters->samples, samples);
@@ -692,6 +780,22 @@ CameraMatrices toCamera(const pt_render_params *p)
 // ---------------------------------------------------------------------------------------------
 // host drivers
 // ---------------------------------------------------------------------------------------------
+pt_status allocSortTemp(Context *ctx, size_t slots)
+{
+    size_t bytes = 0;
+    PT_CUDA_CHECK(ctx, cub::DeviceRadixSort::SortPairs(nullptr, bytes, (const uint32_t *)nullptr, (uint32_t *)nullptr,
+                                                       (const uint32_t *)nullptr, (uint32_t *)nullptr, (int)slots, 0, 32,
+                                                       ctx->stream));
+    bytes = (std::max<size_t>(bytes, 16) + 255) & ~(size_t)255;
+    cudaFree(ctx->sortTemp);
+    ctx->sortTemp = nullptr;
+    ctx->sortTempBytes = 0;
+    // one scratch area per pool (a pool never sorts more than all slots)
+    PT_CUDA_CHECK(ctx, cudaMalloc(&ctx->sortTemp, bytes * PT_MAX_POOLS));
+    ctx->sortTempBytes = bytes;
+    return PT_OK;
+}
+
 pt_status renderSamples(Context *ctx, const pt_render_params *params, uint32_t firstSample, uint32_t sampleCount,
                         const pt_tile *tiles, uint32_t tileCount)
 {
@@ -782,112 +886,215 @@ pt_status renderSamples(Context *ctx, const pt_render_params *params, uint32_t f
     };
     std::vector<Timed> timed;
     const bool timing = ctx->kernelTiming;
-    auto begin = [&](int cls) {
+    auto begin = [&](int cls, cudaStream_t st) {
         if (!timing)
             return;
         Timed t { cls, nullptr, nullptr };
         cudaEventCreate(&t.a);
         cudaEventCreate(&t.b);
-        cudaEventRecord(t.a, ctx->stream);
+        cudaEventRecord(t.a, st);
         timed.push_back(t);
         ctx->stats.kernel_launch_count[cls]++;
     };
-    auto end = [&]() {
+    auto end = [&](cudaStream_t st) {
         if (timing)
-            cudaEventRecord(timed.back().b, ctx->stream);
+            cudaEventRecord(timed.back().b, st);
     };
+
+    const bool alpha = ctx->scene.hasAlpha != 0;
+    const bool statsOn = ctx->collectTraversalStats;
+    // Hits are shaded in triangle order (radix sort of the hit queue on the upper bits of the
+    // leaf-order = Morton-order triangle index): neighbouring lanes then shade neighbouring
+    // triangles — same material branch, same texture region, shared cache lines.  16 key bits
+    // (two 8-bit passes) are plenty for that.
+    uint32_t triBits = 1;
+    while (triBits < 32 && (ctx->scene.triCount >> triBits) != 0)
+        triBits++;
+    const uint32_t keyBits = std::min(triBits, 16u);
 
     for (uint32_t roundBase = 0; roundMax > 0 && roundBase < sampleCount; roundBase += roundMax)
     {
-        RenderConst rc = {};
-        rc.scene = ctx->scene;
-        rc.ps = ctx->ps;
-        rc.cam = toCamera(params);
-        rc.accum = ctx->accum;
-        rc.counters = ctx->dCounters;
-        rc.qc = ctx->dQueueCounts;
-        rc.width = W;
-        rc.height = H;
-        rc.firstSample = firstSample;
-        rc.sampleCount = sampleCount;
-        rc.bounceCount = params->bounce_count;
-        rc.lensRadius = params->lens_radius;
-        rc.focalDistance = params->focal_distance;
-        rc.missFlags = params->miss_flags;
-        rc.hitFlags = params->hit_flags;
-        rc.pixelList = ctx->pixelList;
-        rc.pixelCount = pixels;
-        rc.sbuf = ctx->sbuf;
-        rc.roundBase = roundBase;
-        rc.roundSamples = std::min(roundMax, sampleCount - roundBase);
-        rc.itemCount = rc.roundSamples * pixels;
-        rc.slotCount = std::min(ctx->slotCapacity, rc.itemCount);
-        const uint32_t slots = rc.slotCount;
+        RenderConst base = {};
+        base.scene = ctx->scene;
+        base.cam = toCamera(params);
+        base.accum = ctx->accum;
+        base.counters = ctx->dCounters;
+        base.width = W;
+        base.height = H;
+        base.firstSample = firstSample;
+        base.sampleCount = sampleCount;
+        base.bounceCount = params->bounce_count;
+        base.lensRadius = params->lens_radius;
+        base.focalDistance = params->focal_distance;
+        base.missFlags = params->miss_flags;
+        base.hitFlags = params->hit_flags;
+        base.pixelList = ctx->pixelList;
+        base.pixelCount = pixels;
+        base.sbuf = ctx->sbuf;
+        base.roundBase = roundBase;
+        base.roundSamples = std::min(roundMax, sampleCount - roundBase);
+        base.itemCount = base.roundSamples * pixels;
+        base.nextItem = ctx->dNextItem;
+        base.hitKeyShift = triBits - keyBits;
 
-        const bool alpha = ctx->scene.hasAlpha != 0;
-        const bool statsOn = ctx->collectTraversalStats;
-        const uint32_t gridTrace = std::min((slots + 127) / 128, (uint32_t)ctx->smCount * 16);
-        const uint32_t gridWide = std::min((slots + 255) / 256, (uint32_t)ctx->smCount * 8);
-        k_init<<<gridWide, 256, 0, ctx->stream>>>(rc);
-        ctx->stats.kernel_launches++;
-
-        int cur = 0;
-        // the host polls the queue sizes every few iterations; a round needs at least
-        // items / slots iterations, so polling starts sparse and gets denser towards the end
-        uint32_t sinceCheck = 0;
-        uint32_t checkEvery = 4;
-        for (;;)
+        // ---- pools: independent sub-wavefronts on their own streams ------------------------------
+        // A traversal kernel ends with its longest rays (a ray grazing the tessellated board visits
+        // thousands of nodes); with one wavefront the whole GPU waits for them every iteration.
+        // Several smaller wavefronts on separate streams fill those tails with each other's kernels.
+        const uint32_t slotsTotal = std::min(ctx->slotCapacity, base.itemCount);
+        uint32_t poolCount = std::max(1u, std::min(ctx->poolCount, slotsTotal / 65536u));
+        const uint32_t poolSlots = slotsTotal / poolCount; // the last pool takes the remainder
+        struct Pool
         {
+            RenderConst rc;
+            cudaStream_t stream;
+            QueueCounts *hq;
+            void *sortTemp;
+            uint32_t gridExtend, gridShadow, gridShade, gridWide;
+            int cur;
+            bool active;
+        };
+        std::vector<Pool> pools(poolCount);
+        PT_CUDA_CHECK(ctx, cudaMemcpyAsync(ctx->dNextItem, &slotsTotal, 4, cudaMemcpyHostToDevice, ctx->stream));
+        PT_CUDA_CHECK(ctx, cudaEventRecord(ctx->evRound, ctx->stream));
+        for (uint32_t p = 0; p < poolCount; p++)
+        {
+            Pool &pl = pools[p];
+            const uint32_t first = p * poolSlots;
+            const uint32_t slots = p + 1 == poolCount ? slotsTotal - first : poolSlots;
+            pl.rc = base;
+            pl.rc.ps = ctx->ps;
+            // queues are private to the pool: its sub-range of the queue arrays
+            pl.rc.ps.contQ[0] += first, pl.rc.ps.contQ[1] += first;
+            pl.rc.ps.freshQ[0] += first, pl.rc.ps.freshQ[1] += first;
+            pl.rc.ps.doneQ += first, pl.rc.ps.hitQ += first, pl.rc.ps.hitKey += first;
+            pl.rc.ps.hitQSorted += first, pl.rc.ps.hitKeySorted += first, pl.rc.ps.shadowQueue += first;
+            pl.rc.qc = ctx->dQueueCounts + p;
+            pl.rc.slotBase = first;
+            pl.rc.slotCount = slots;
+            pl.rc.sortHits = ctx->sortHits && slots >= 4096;
+            pl.stream = poolCount == 1 ? ctx->stream : ctx->poolStreams[p];
+            pl.hq = ctx->hQueueCounts + p;
+            pl.sortTemp = (char *)ctx->sortTemp + p * ctx->sortTempBytes;
+            pl.cur = 0;
+            pl.active = true;
+            pl.gridShade = std::min((slots + 127) / 128, (uint32_t)ctx->smCount * 16);
+            // persistent warps: exactly as many blocks as are resident on the machine (occupancy query per
+            // instantiation; PT_TRACE_BLOCKS overrides), never more than the rays need
+            auto residentGrid = [&](auto kernel) {
+                int perSM = 0;
+                if (ctx->traceBlocksPerSM)
+                    perSM = (int)ctx->traceBlocksPerSM;
+                else if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, kernel, 128, 0) != cudaSuccess || perSM < 1)
+                    perSM = 4;
+                return std::min((slots + 127) / 128, (uint32_t)(ctx->smCount * perSM));
+            };
+            if (alpha && statsOn)
+                pl.gridExtend = residentGrid(k_extend<true, true>), pl.gridShadow = residentGrid(k_shadow<true, true>);
+            else if (alpha)
+                pl.gridExtend = residentGrid(k_extend<true, false>), pl.gridShadow = residentGrid(k_shadow<true, false>);
+            else if (statsOn)
+                pl.gridExtend = residentGrid(k_extend<false, true>), pl.gridShadow = residentGrid(k_shadow<false, true>);
+            else
+                pl.gridExtend = residentGrid(k_extend<false, false>), pl.gridShadow = residentGrid(k_shadow<false, false>);
+            pl.gridWide = std::min((slots + 255) / 256, (uint32_t)ctx->smCount * 8);
+            if (pl.stream != ctx->stream)
+                PT_CUDA_CHECK(ctx, cudaStreamWaitEvent(pl.stream, ctx->evRound, 0));
+            k_init<<<pl.gridWide, 256, 0, pl.stream>>>(pl.rc);
+            ctx->stats.kernel_launches++;
+        }
+
+        auto iteration = [&](Pool &pl) -> pt_status {
+            const RenderConst &rc = pl.rc;
+            const int cur = pl.cur;
+            cudaStream_t st = pl.stream;
 #define PT_DISPATCH(KERNEL, GRID, BLOCK, ...)                                                                         \
     do                                                                                                                \
     {                                                                                                                 \
         if (alpha && statsOn)                                                                                         \
-            KERNEL<true, true><<<GRID, BLOCK, 0, ctx->stream>>>(__VA_ARGS__);                                         \
+            KERNEL<true, true><<<GRID, BLOCK, 0, st>>>(__VA_ARGS__);                                                  \
         else if (alpha)                                                                                               \
-            KERNEL<true, false><<<GRID, BLOCK, 0, ctx->stream>>>(__VA_ARGS__);                                        \
+            KERNEL<true, false><<<GRID, BLOCK, 0, st>>>(__VA_ARGS__);                                                 \
         else if (statsOn)                                                                                             \
-            KERNEL<false, true><<<GRID, BLOCK, 0, ctx->stream>>>(__VA_ARGS__);                                        \
+            KERNEL<false, true><<<GRID, BLOCK, 0, st>>>(__VA_ARGS__);                                                 \
         else                                                                                                          \
-            KERNEL<false, false><<<GRID, BLOCK, 0, ctx->stream>>>(__VA_ARGS__);                                       \
+            KERNEL<false, false><<<GRID, BLOCK, 0, st>>>(__VA_ARGS__);                                                \
     } while (0)
-            begin(PT_KERNEL_EXTEND);
-            PT_DISPATCH(k_extend, gridTrace, 128, rc, cur);
-            end();
-            begin(PT_KERNEL_SHADE);
-            PT_DISPATCH(k_shade, gridTrace, 128, rc);
-            end();
-            begin(PT_KERNEL_SHADOW);
-            PT_DISPATCH(k_shadow, gridTrace, 128, rc);
-            end();
-            begin(PT_KERNEL_FINISH);
-            k_finish<<<gridWide, 256, 0, ctx->stream>>>(rc, cur);
-            end();
+            begin(PT_KERNEL_EXTEND, st);
+            if (rc.sortHits)
+                PT_CUDA_CHECK(ctx, cudaMemsetAsync(rc.ps.hitKey, 0xff, (size_t)rc.slotCount * 4, st));
+            PT_DISPATCH(k_extend, pl.gridExtend, 128, rc, cur);
+            end(st);
+            begin(PT_KERNEL_SHADE, st);
+            if (rc.sortHits)
+            {
+                // unused tail of the key array sorts to the end (k_shade only reads qc->hit entries)
+                size_t bytes = ctx->sortTempBytes;
+                PT_CUDA_CHECK(ctx, cub::DeviceRadixSort::SortPairs(pl.sortTemp, bytes, rc.ps.hitKey, rc.ps.hitKeySorted,
+                                                                   rc.ps.hitQ, rc.ps.hitQSorted, (int)rc.slotCount, 0,
+                                                                   (int)keyBits + 1, st));
+            }
+            PT_DISPATCH(k_shade, pl.gridShade, 128, rc, cur);
+            end(st);
+            begin(PT_KERNEL_SHADOW, st);
+            PT_DISPATCH(k_shadow, pl.gridShadow, 128, rc);
+            end(st);
+            begin(PT_KERNEL_FINISH, st);
+            k_finish<<<pl.gridWide, 256, 0, st>>>(rc, cur);
+            end(st);
 #undef PT_DISPATCH
             ctx->stats.kernel_launches += 4;
-            ctx->stats.wavefront_iterations++;
-            cur ^= 1;
-            if (++sinceCheck >= checkEvery)
+            pl.cur ^= 1;
+            return PT_OK;
+        };
+
+        // the host polls the queue sizes every few iterations; a round needs at least
+        // items / slots iterations, so polling starts sparse and gets denser towards the end
+        uint32_t checkEvery = 4;
+        for (uint32_t live = poolCount; live > 0;)
+        {
+            for (uint32_t k = 0; k < checkEvery; k++)
             {
-                sinceCheck = 0;
-                PT_CUDA_CHECK(ctx, cudaMemcpyAsync(ctx->hQueueCounts, ctx->dQueueCounts, sizeof(QueueCounts),
-                                                   cudaMemcpyDeviceToHost, ctx->stream));
-                PT_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
-                const QueueCounts &q = *ctx->hQueueCounts;
-                if (q.cont[cur] + q.fresh[cur] == 0)
-                    break;
-                // while work items remain, at least remaining / slots more iterations are needed
-                const uint64_t remaining = q.nextItem < rc.itemCount ? rc.itemCount - q.nextItem : 0;
-                checkEvery = (uint32_t)std::min<uint64_t>(64, std::max<uint64_t>(4, remaining / std::max(1u, slots)));
+                for (Pool &pl : pools)
+                    if (pl.active)
+                    {
+                        const pt_status st = iteration(pl);
+                        if (st != PT_OK)
+                            return st;
+                    }
+                ctx->stats.wavefront_iterations++;
             }
+            for (Pool &pl : pools)
+                if (pl.active)
+                    PT_CUDA_CHECK(ctx, cudaMemcpyAsync(pl.hq, pl.rc.qc, sizeof(QueueCounts), cudaMemcpyDeviceToHost, pl.stream));
+            bool first = true;
+            for (Pool &pl : pools)
+                if (pl.active)
+                {
+                    if (first)
+                        PT_CUDA_CHECK(ctx, cudaMemcpyAsync(ctx->hNextItem, ctx->dNextItem, 4, cudaMemcpyDeviceToHost, pl.stream));
+                    first = false;
+                    PT_CUDA_CHECK(ctx, cudaStreamSynchronize(pl.stream));
+                    if (pl.hq->cont[pl.cur] + pl.hq->fresh[pl.cur] == 0)
+                    {
+                        pl.active = false;
+                        live--;
+                    }
+                }
+            // while work items remain, at least remaining / slots more iterations are needed
+            const uint32_t nextItem = *ctx->hNextItem;
+            const uint64_t remaining = nextItem < base.itemCount ? base.itemCount - nextItem : 0;
+            checkEvery = (uint32_t)std::min<uint64_t>(64, std::max<uint64_t>(4, remaining / std::max(1u, slotsTotal)));
         }
-        begin(PT_KERNEL_FINISH);
-        k_resolve<<<std::min((pixels + 255) / 256, (uint32_t)ctx->smCount * 8), 256, 0, ctx->stream>>>(rc);
-        end();
+        // every pool has been synchronised with the host: the round's samples are all parked
+        begin(PT_KERNEL_FINISH, ctx->stream);
+        k_resolve<<<std::min((pixels + 255) / 256, (uint32_t)ctx->smCount * 8), 256, 0, ctx->stream>>>(base);
+        end(ctx->stream);
         ctx->stats.kernel_launches++;
     }
     if (timing)
     {
-        cudaStreamSynchronize(ctx->stream);
+        cudaDeviceSynchronize();
         for (Timed &t : timed)
         {
             float ms = 0.0f;
