@@ -322,12 +322,15 @@ def run_ours(args):
         dist.all_reduce(w, op=dist.ReduceOp.SUM)
         rays_c, rays_s, samples, launches = (int(x) for x in w.tolist())
 
-    # ---- roofline inputs: one stats run + one kernel-timing run of the same workload (rank 0's share)
+    # ---- roofline inputs: one stats run + one kernel-timing run of the same workload (rank 0's share).
+    # The timing run uses ONE wavefront pool: with several pools the kernels of different streams
+    # overlap and a CUDA-event pair around one launch would also time its neighbours.
     r.set_traversal_stats(True)
     r.on_resize(W, H)
     r.render(count, tiles=tiles, params=params, first_sample=first)
     cst = r.stats()
     r.set_traversal_stats(False)
+    r.set_tuning("pools", 1)
     r.set_kernel_timing(True)
     r.on_resize(W, H)
     r.render(count, tiles=tiles, params=params, first_sample=first)
@@ -397,7 +400,9 @@ def run_ours(args):
             "materials": int(len(scene.mr_materials)),
             "textures": len(scene.textures),
             "partition": "none" if world == 1 else args.partition,
-            "l2": "working set (path state + triangles + BVH + textures, > 1 GB) exceeds the 126 MB L2; no explicit flush",
+            "l2": "working set (path state of 8 M paths in flight 2 GB + sample buffer 8 GB + triangles/BVH 0.44 GB + textures) "
+                  "exceeds the 126 MB L2 many times over; no explicit flush",
+            "scheduling": "8 M path slots in 8 wavefront pools on 8 CUDA streams, hits shaded in triangle order",
             "bvh_build_ms": build_stats["bvh_build_ms"],
             "scene_upload_ms": build_stats["scene_upload_ms"],
         },
@@ -405,6 +410,8 @@ def run_ours(args):
         "roofline": {
             "bound": "hbm",
             "kernel": f"k_{dominant}",
+            "timing": "CUDA events on the launching stream around every launch of a separate, identical render with ONE "
+                      "wavefront pool (kernels of different pools overlap otherwise); value/ms_per_step come from the 8-pool runs",
             "achieved": kernels[dominant]["achieved_gbs"],
             "peak": peak,
             "unit": "GB/s",

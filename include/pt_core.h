@@ -294,6 +294,13 @@ typedef struct pt_stats {
     float last_render_ms;         /* CUDA-event time of the last pt_render_samples                */
     float kernel_ms[PT_KERNEL_CLASS_COUNT];              /* with pt_set_kernel_timing(1) only     */
     uint32_t kernel_launch_count[PT_KERNEL_CLASS_COUNT];
+    /* traversal-tail diagnostics (traversal stats only): rays by the number of BVH nodes they visited,
+     * bins [0,16) [16,32) [32,64) [64,128) [128,256) [256,512) [512,1024) [1024,inf); and the
+     * warp-level loop iterations of the traversal kernels, in total and in drain mode (queue empty) */
+    uint64_t node_visit_hist[8];
+    uint64_t warp_iterations;
+    uint64_t warp_drain_iterations;
+    uint64_t max_warp_drain_iterations;
 } pt_stats;
 
 /* ------------------------------------------------------------------------- */
@@ -385,6 +392,14 @@ PT_API pt_status pt_set_traversal_stats(pt_context *ctx, int32_t enable);
  * pt_render_samples calls, summed per kernel class into pt_stats.kernel_ms (the per-kernel
  * durations the roofline is computed from; events are recorded on the launching stream). */
 PT_API pt_status pt_set_kernel_timing(pt_context *ctx, int32_t enable);
+
+/* Scheduling knobs of the wavefront (no reference counterpart; results do not depend on them,
+ * bit for bit).  Keys: "pools" (independent sub-wavefronts on separate CUDA streams, 1..8),
+ * "slots" (paths in flight, all pools together; takes effect at the next pt_render_begin that
+ * changes the extent, or immediately if no target exists), "sort_hits" (0/1: shade hits in triangle
+ * order), "sbuf_mb" (sample-buffer budget per round).  The same knobs are read from the
+ * environment at pt_context_create: PT_POOLS, PT_SLOTS, PT_SORT_HITS, PT_SBUF_MB. */
+PT_API pt_status pt_set_tuning(pt_context *ctx, const char *key, uint64_t value);
 
 /* ------------------------------------------------------------------------- */
 /* shader unit-test entry point                                              */

@@ -38,6 +38,7 @@ ABI_SYMBOLS = [
     "pt_get_stats",
     "pt_set_traversal_stats",
     "pt_set_kernel_timing",
+    "pt_set_tuning",
     "pt_test_input_stride",
     "pt_test_output_stride",
     "pt_test_shading",
@@ -79,12 +80,17 @@ class Stats(C.Structure):
         ("last_render_ms", C.c_float),
         ("kernel_ms", C.c_float * 4),
         ("kernel_launch_count", C.c_uint32 * 4),
+        ("node_visit_hist", C.c_uint64 * 8),
+        ("warp_iterations", C.c_uint64),
+        ("warp_drain_iterations", C.c_uint64),
+        ("max_warp_drain_iterations", C.c_uint64),
     ]
 
     def as_dict(self):
         d = {n: getattr(self, n) for n, _ in self._fields_}
         d["kernel_ms"] = dict(zip(KERNEL_CLASSES, [float(x) for x in self.kernel_ms]))
         d["kernel_launch_count"] = dict(zip(KERNEL_CLASSES, [int(x) for x in self.kernel_launch_count]))
+        d["node_visit_hist"] = [int(x) for x in self.node_visit_hist]
         return d
 
 
@@ -124,6 +130,7 @@ def lib():
     L.pt_get_stats.argtypes = [vp, vp]
     L.pt_set_traversal_stats.argtypes = [vp, i32]
     L.pt_set_kernel_timing.argtypes = [vp, i32]
+    L.pt_set_tuning.argtypes = [vp, C.c_char_p, u64]
     L.pt_test_input_stride.argtypes = [u32]
     L.pt_test_input_stride.restype = u32
     L.pt_test_output_stride.argtypes = [u32]
@@ -249,6 +256,10 @@ class Renderer:
 
     def set_traversal_stats(self, enable: bool):
         self._check(self._L.pt_set_traversal_stats(self._h, 1 if enable else 0))
+
+    def set_tuning(self, key: str, value: int):
+        """Scheduling knobs (pools, slots, sort_hits, sbuf_mb); results do not depend on them."""
+        self._check(self._L.pt_set_tuning(self._h, key.encode(), int(value)))
 
     def set_kernel_timing(self, enable: bool):
         self._check(self._L.pt_set_kernel_timing(self._h, 1 if enable else 0))

@@ -25,6 +25,7 @@ struct DeviceCounters
 {
     unsigned long long raysClosest, raysShadow, samples, hits, boxClosest, triClosest, alphaClosest, boxShadow, triShadow,
         alphaShadow, texels, restarts;
+    unsigned long long visitHist[8], warpIters, warpDrainIters, maxWarpDrainIters; // diagnostics (stats runs)
 };
 
 // wavefront queue bookkeeping living in device memory
@@ -40,23 +41,37 @@ struct QueueCounts
     uint32_t pad;
 };
 
-// SoA path state, one entry per slot of the pool (a slot carries one path = one work item at a time)
+// Path state: one 256-byte record per slot of the pool (a slot carries one path = one work item
+// at a time).  Array-of-structures ON PURPOSE: every kernel reaches the state through a queue of
+// slot indices, i.e. in random order, so what counts is how many DRAM pages / L2 lines one path
+// touches, not coalescing across neighbouring threads.  A structure-of-arrays layout (the first
+// version) spread one path over 13 lines in 13 pages and ran at the random-access DRAM rate.
+struct __align__(128) PathRecord
+{
+    // line A — the bounce state (k_extend reads rayO/rayD, k_shade reads and rewrites all of it)
+    float4 rayO;  // origin.xyz, maxRoughness
+    float4 rayD;  // direction.xyz, rng (bits)
+    float4 thr;   // throughput.xyz, bounce count (bits)
+    float4 rad;   // radiance.xyz, restarts (bits)
+    float4 diff0; // rxOrigin.xyz, rxDirection.x
+    float4 diff1; // rxDirection.yz, ryOrigin.xy
+    float4 diff2; // ryOrigin.z, ryDirection.xyz
+    float4 hit;   // tri (bits), t, b1, b2
+    // line B — the shadow ray, the decal record and the work item
+    float4 shO;   // shadow origin.xyz, tmax
+    float4 shD;   // shadow direction.xyz, -
+    float4 shC;   // contribution.xyz (throughput * DirectLight / pdf), -
+    float4 decal; // rgb, dist (scenes with alpha-tested geometry)
+    uint32_t item; // work item of the slot (round-relative sample * pixelCount + pixel-list index)
+    float decalA;
+    uint32_t pad[2];
+    float4 spare[3];
+};
+static_assert(sizeof(PathRecord) == 256, "PathRecord must be two 128-byte lines");
+
 struct PathState
 {
-    float4 *rayO;  // origin.xyz, maxRoughness
-    float4 *rayD;  // direction.xyz, rng (bits)
-    float4 *thr;   // throughput.xyz, bounce | flags (bits)
-    float4 *rad;   // radiance.xyz, restarts (bits)
-    float4 *diff0; // rxOrigin.xyz, rxDirection.x
-    float4 *diff1; // rxDirection.yz, ryOrigin.xy
-    float4 *diff2; // ryOrigin.z, ryDirection.xyz
-    float4 *hit;   // tri (bits), t, b1, b2
-    float4 *decal; // rgb, dist          (only when the scene has alpha-tested geometry)
-    float *decalA; // alpha
-    float4 *shO;   // shadow origin.xyz, tmax
-    float4 *shD;   // shadow direction.xyz, -
-    float4 *shC;   // contribution.xyz (throughput * DirectLight / pdf), -
-    uint32_t *item;      // work item of the slot (round-relative sample * pixelCount + pixel-list index)
+    PathRecord *rec;
     uint32_t *contQ[2];  // active slots with a continuing path, double buffered
     uint32_t *freshQ[2]; // active slots with a fresh primary ray, double buffered
     uint32_t *doneQ;     // slots whose path has ended (missed, terminated or out of bounces)
@@ -108,7 +123,7 @@ struct Context
     void *sortTemp = nullptr;   // CUB radix-sort scratch for slotCapacity pairs
     size_t sortTempBytes = 0;
 
-    uint32_t poolCount = 4;     // independent sub-wavefronts (PT_POOLS)
+    uint32_t poolCount = 8;     // independent sub-wavefronts (PT_POOLS)
     cudaStream_t poolStreams[PT_MAX_POOLS] = {};
     cudaEvent_t evRound = nullptr;
 

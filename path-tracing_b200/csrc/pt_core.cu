@@ -172,15 +172,7 @@ pt_status pt_scene_upload(pt_context *ctx, const pt_scene_desc *scene)
     if (!ctx)
         return PT_ERR_INVALID_ARGUMENT;
     cudaSetDevice(ctx->device);
-    const bool hadAlpha = ctx->scene.hasAlpha != 0;
-    const pt_status st = uploadScene(ctx, scene);
-    // the decal streams of the path state exist only for scenes with alpha-tested geometry
-    if (st == PT_OK && ctx->accum && (ctx->scene.hasAlpha != 0) != hadAlpha)
-    {
-        const uint32_t w = ctx->width, h = ctx->height;
-        return pt_render_begin(ctx, w, h);
-    }
-    return st;
+    return uploadScene(ctx, scene);
 }
 
 pt_status pt_texture_upload(pt_context *ctx, uint32_t slot, const pt_texture_desc *texture)
@@ -199,8 +191,7 @@ pt_status pt_render_begin(pt_context *ctx, uint32_t width, uint32_t height)
         return fail(ctx, PT_ERR_INVALID_ARGUMENT, "pt_render_begin", "bad extent");
     cudaSetDevice(ctx->device);
     const size_t n = (size_t)width * height;
-    const bool needDecal = ctx->scene.hasAlpha != 0;
-    const bool reuse = ctx->accum && ctx->width == width && ctx->height == height && ((ctx->ps.decal != nullptr) == needDecal);
+    const bool reuse = ctx->accum && ctx->width == width && ctx->height == height;
     if (!reuse)
     {
         PT_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
@@ -222,23 +213,7 @@ pt_status pt_render_begin(pt_context *ctx, uint32_t width, uint32_t height)
         slots = std::min(slots, std::max<size_t>(n * 4, 4096));
         PT_T(targetAlloc(ctx, &ctx->accum, n));
         PT_T(targetAlloc(ctx, &ctx->pixelList, n));
-        PT_T(targetAlloc(ctx, &ps.rayO, slots));
-        PT_T(targetAlloc(ctx, &ps.rayD, slots));
-        PT_T(targetAlloc(ctx, &ps.thr, slots));
-        PT_T(targetAlloc(ctx, &ps.rad, slots));
-        PT_T(targetAlloc(ctx, &ps.diff0, slots));
-        PT_T(targetAlloc(ctx, &ps.diff1, slots));
-        PT_T(targetAlloc(ctx, &ps.diff2, slots));
-        PT_T(targetAlloc(ctx, &ps.hit, slots));
-        if (needDecal)
-        {
-            PT_T(targetAlloc(ctx, &ps.decal, slots));
-            PT_T(targetAlloc(ctx, &ps.decalA, slots));
-        }
-        PT_T(targetAlloc(ctx, &ps.shO, slots));
-        PT_T(targetAlloc(ctx, &ps.shD, slots));
-        PT_T(targetAlloc(ctx, &ps.shC, slots));
-        PT_T(targetAlloc(ctx, &ps.item, slots));
+        PT_T(targetAlloc(ctx, &ps.rec, slots));
         PT_T(targetAlloc(ctx, &ps.contQ[0], slots));
         PT_T(targetAlloc(ctx, &ps.contQ[1], slots));
         PT_T(targetAlloc(ctx, &ps.freshQ[0], slots));
@@ -360,6 +335,11 @@ pt_status pt_get_stats(pt_context *ctx, pt_stats *out)
     s.alpha_tests_shadow = c.alphaShadow;
     s.texel_fetches = c.texels;
     s.restarts = c.restarts;
+    for (int i = 0; i < 8; i++)
+        s.node_visit_hist[i] = c.visitHist[i];
+    s.warp_iterations = c.warpIters;
+    s.warp_drain_iterations = c.warpDrainIters;
+    s.max_warp_drain_iterations = c.maxWarpDrainIters;
     s.triangle_count = ctx->scene.triCount;
     s.bvh_node_count = ctx->nodeCount;
     s.bvh_bytes = ctx->bvhBytes;
@@ -382,6 +362,35 @@ pt_status pt_set_kernel_timing(pt_context *ctx, int32_t enable)
     if (!ctx)
         return PT_ERR_INVALID_ARGUMENT;
     ctx->kernelTiming = enable != 0;
+    return PT_OK;
+}
+
+pt_status pt_set_tuning(pt_context *ctx, const char *key, uint64_t value)
+{
+    if (!ctx || !key)
+        return PT_ERR_INVALID_ARGUMENT;
+    const std::string k(key);
+    if (k == "pools")
+        ctx->poolCount = (uint32_t)std::min<uint64_t>(PT_MAX_POOLS, std::max<uint64_t>(1, value));
+    else if (k == "slots")
+    {
+        ctx->slotPoolSize = std::max<uint64_t>(1024, value);
+        if (ctx->accum)
+        {
+            // re-create the path state with the new pool size
+            const uint32_t w = ctx->width, h = ctx->height;
+            cudaSetDevice(ctx->device);
+            PT_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+            freeTarget(ctx);
+            return pt_render_begin(ctx, w, h);
+        }
+    }
+    else if (k == "sort_hits")
+        ctx->sortHits = value != 0;
+    else if (k == "sbuf_mb")
+        ctx->sbufBudgetBytes = std::max<uint64_t>(1, value) << 20;
+    else
+        return fail(ctx, PT_ERR_INVALID_ARGUMENT, "pt_set_tuning", "unknown key");
     return PT_OK;
 }
 

@@ -41,6 +41,13 @@ struct TraversalStats
     uint32_t boxTests, triTests, alphaTests;
 };
 
+// diagnostics of the persistent traversal (stats runs only): where the tail of a launch comes from
+struct TailStats
+{
+    unsigned long long *visitHist; // [8]
+    unsigned long long *warpIters, *warpDrainIters, *maxWarpDrainIters;
+};
+
 struct RaySetup
 {
     vec3 org;
@@ -181,12 +188,14 @@ PT_DEV void intersectNode(const BvhNode *__restrict__ node, const RaySetup &r, f
 //   CLOSEST = false: any hit in (tmin, tmax) with alpha >= 1 -> hit.tri != miss
 template <bool CLOSEST, bool ALPHA, bool STATS> struct Traverser
 {
+    static constexpr bool kClosest = CLOSEST, kAlpha = ALPHA, kStats = STATS;
     RaySetup r;
     float tmin, tmax, best;
     uint32_t bestFlat;
     Hit hit;
     Decal decal;
     TraversalStats st;
+    uint32_t visits; // nodes visited by the current ray (diagnostics)
     int cur;
     int leaf; // postponed leaf (speculative traversal), PT_CHILD_EMPTY = none
     int sp;
@@ -210,6 +219,7 @@ template <bool CLOSEST, bool ALPHA, bool STATS> struct Traverser
         if (ALPHA)
             decal.dist = -1.0f;
         sp = 0;
+        visits = 0;
         leaf = PT_CHILD_EMPTY;
         cur = 0; // the root is always an internal node
         // A ray with a non-finite component or a zero direction cannot hit anything (every triangle
@@ -252,7 +262,10 @@ template <bool CLOSEST, bool ALPHA, bool STATS> struct Traverser
         int c[4];
         intersectNode(s.nodes + cur, r, tmin, best, d, c);
         if (STATS)
+        {
             st.boxTests += 4;
+            visits++;
+        }
         // sorting network, ascending by distance (missed children carry INF)
         PT_CSWAP(0, 1)
         PT_CSWAP(2, 3)
@@ -278,6 +291,29 @@ template <bool CLOSEST, bool ALPHA, bool STATS> struct Traverser
                 prefetchL1(s.nodes + c[1]);
 #endif
         }
+    }
+
+    // result of another lane that traversed part of this ray's tree (straggler splitting)
+    PT_DEV void merge(uint32_t tri, float t, float b1, float b2, uint32_t flat)
+    {
+        if (tri == 0xffffffffu)
+            return;
+        if (CLOSEST)
+        {
+            if (!(t < best || (t == best && flat < bestFlat)))
+                return;
+            best = t;
+            bestFlat = flat;
+        }
+        else
+        {
+            cur = leaf = PT_CHILD_EMPTY; // occluded: nothing left to do
+            sp = 0;
+        }
+        hit.tri = tri;
+        hit.t = t;
+        hit.b1 = b1;
+        hit.b2 = b2;
     }
 
     // speculative traversal (Aila & Laine 2009): the first leaf found is set aside and the lane keeps
@@ -411,8 +447,16 @@ PT_DEV void traverse(const DeviceScene &s, vec3 org, vec3 dir, float tmin, float
 //   * DEFERRED commit: finished lanes keep their result until the next refill point, where all of
 //     them push to the hit / done queues together — one aggregated atomic per queue and refill
 //     instead of one per lane (same-address atomics are serialised by the L2).
+//   * STRAGGLER SPLITTING: once the queue is empty a warp only drains, and the kernel lasts as
+//     long as its longest ray (a ray grazing a tessellated floor visits thousands of nodes while
+//     the rest of the GPU idles).  In drain mode idle lanes therefore take sub-trees off the
+//     deepest stack of the warp: the donor pops an entry, the helper copies the ray and traverses
+//     that sub-tree, and its result is merged into the owner's with the same (t, triangle id)
+//     order the serial traversal uses — the answer is identical, the tail up to 32x shorter.
 // ---------------------------------------------------------------------------------------------
-#define PT_FETCH_CHUNK 128u
+#ifndef PT_FETCH_CHUNK
+#define PT_FETCH_CHUNK 32u
+#endif
 #ifndef PT_REFILL_LANES
 #define PT_REFILL_LANES 20
 #endif
@@ -425,8 +469,16 @@ struct RayPacket
 
 template <class TR, class LoadSlot, class LoadRay, class Commit>
 PT_DEV void tracePersistent(const DeviceScene &s, uint32_t n, uint32_t *workCounter, TR &tr, float tmin,
-                            LoadSlot loadSlot, LoadRay loadRay, Commit commit)
+                            LoadSlot loadSlot, LoadRay loadRay, Commit commit, TailStats tail)
 {
+    uint32_t dbgIters = 0, dbgDrainIters = 0;
+    auto countVisits = [&](uint32_t v) {
+        if (TR::kStats)
+        {
+            const int bin = v < 16 ? 0 : min(7, 28 - __clz(v));
+            atomicAdd(tail.visitHist + bin, 1ull);
+        }
+    };
     const unsigned FULL = 0xffffffffu;
     const unsigned lane = threadIdx.x & 31u;
     const unsigned ltMask = (1u << lane) - 1u;
@@ -436,6 +488,7 @@ PT_DEV void tracePersistent(const DeviceScene &s, uint32_t n, uint32_t *workCoun
     RayPacket pf = {};
     bool haveRay = false, pending = false;
     uint32_t slot = 0;
+    unsigned owner = lane; // lane whose ray this lane works on (differs only for drain-mode helpers)
     tr.cur = tr.leaf = PT_CHILD_EMPTY;
 
     uint32_t nxCount = 0; // warp-uniform: lanes [0, nxCount) hold the slot indices of the batch after the buffer
@@ -500,6 +553,7 @@ PT_DEV void tracePersistent(const DeviceScene &s, uint32_t n, uint32_t *workCoun
             if (!haveRay && rank < take)
             {
                 slot = p.slot;
+                owner = lane;
                 tr.begin(s, V3(p.ox, p.oy, p.oz), V3(p.dx, p.dy, p.dz), tmin, p.tmax);
                 haveRay = true;
             }
@@ -509,9 +563,17 @@ PT_DEV void tracePersistent(const DeviceScene &s, uint32_t n, uint32_t *workCoun
             idle = __ballot_sync(FULL, !haveRay);
         }
         if (idle == FULL)
+        {
+            if (TR::kStats && lane == 0)
+            {
+                atomicAdd(tail.warpIters, (unsigned long long)dbgIters);
+                atomicAdd(tail.warpDrainIters, (unsigned long long)dbgDrainIters);
+                atomicMax(tail.maxWarpDrainIters, (unsigned long long)dbgDrainIters);
+            }
             return; // nothing left anywhere
+        }
         // ---- traverse until too many lanes have finished -----------------------------------------
-        const int keepGoing = (pfPos == pfCount) ? 1 : PT_REFILL_LANES;
+        const bool drain = pfPos == pfCount; // warp-uniform: nothing left to refill with
         for (;;)
         {
             // internal nodes, until every lane either holds a leaf or has nothing left to descend into;
@@ -523,13 +585,114 @@ PT_DEV void tracePersistent(const DeviceScene &s, uint32_t n, uint32_t *workCoun
                 tr.postponeLeaf(s.triPos);
             } while (__any_sync(FULL, tr.atInternal() && !tr.hasLeaf()));
             tr.leafStep(s);
-            if (haveRay && tr.finished())
+            if (!drain)
             {
-                pending = true;
+                if (TR::kStats)
+                    dbgIters++;
+                if (haveRay && tr.finished())
+                {
+                    countVisits(tr.visits);
+                    pending = true;
+                    haveRay = false;
+                }
+                if (__popc(__ballot_sync(FULL, haveRay)) < PT_REFILL_LANES)
+                    break;
+                continue;
+            }
+            // ---- drain mode -----------------------------------------------------------------------
+            if (TR::kStats)
+            {
+                dbgIters++;
+                dbgDrainIters++;
+            }
+            // (1) helpers that are done hand their result to the owner lane
+            unsigned hm = __ballot_sync(FULL, haveRay && owner != lane && tr.finished());
+            while (hm != 0)
+            {
+                const int h = __ffs(hm) - 1;
+                hm &= hm - 1;
+                const unsigned o = __shfl_sync(FULL, owner, h);
+                const uint32_t tri = __shfl_sync(FULL, tr.hit.tri, h);
+                const float t = __shfl_sync(FULL, tr.hit.t, h);
+                const float b1 = __shfl_sync(FULL, tr.hit.b1, h), b2 = __shfl_sync(FULL, tr.hit.b2, h);
+                const uint32_t flat = __shfl_sync(FULL, tr.bestFlat, h);
+                const float dd = __shfl_sync(FULL, tr.decal.dist, h), dr = __shfl_sync(FULL, tr.decal.r, h);
+                const float dg = __shfl_sync(FULL, tr.decal.g, h), db = __shfl_sync(FULL, tr.decal.b, h);
+                const float da = __shfl_sync(FULL, tr.decal.a, h);
+                if ((int)lane == h)
+                    haveRay = false;
+                else if (haveRay && owner == o)
+                {
+                    // the owner takes the result; for occlusion rays every part of the ray stops on a hit
+                    if (lane == o || !TR::kClosest)
+                        tr.merge(tri, t, b1, b2, flat);
+                    if (lane == o && TR::kAlpha && TR::kClosest && dd != -1.0f && (tr.decal.dist == -1.0f || dd < tr.decal.dist))
+                    {
+                        tr.decal.dist = dd;
+                        tr.decal.r = dr, tr.decal.g = dg, tr.decal.b = db, tr.decal.a = da;
+                    }
+                }
+            }
+            // (2) owners whose ray is done in all its parts
+            const unsigned group = __match_any_sync(FULL, haveRay ? owner : 32u + lane);
+            if (haveRay && owner == lane && tr.finished() && group == (1u << lane))
+            {
+                countVisits(tr.visits);
+                commit(tr, slot);
                 haveRay = false;
             }
-            if (__popc(__ballot_sync(FULL, haveRay)) < keepGoing)
+            // (3) idle lanes take sub-trees off the deepest stacks
+            unsigned idleLanes = ~__ballot_sync(FULL, haveRay);
+            if (idleLanes == FULL)
                 break;
+            while (idleLanes != 0)
+            {
+                const unsigned key = (haveRay && tr.sp >= 1) ? (((unsigned)tr.sp << 5) | lane) : 0u;
+                const unsigned top = __reduce_max_sync(FULL, key);
+                if (top == 0)
+                    break;
+                const int donor = (int)(top & 31u);
+                const int helper = __ffs(idleLanes) - 1;
+                idleLanes &= idleLanes - 1;
+                unsigned long long e = 0;
+                if ((int)lane == donor)
+                    e = tr.stack[--tr.sp];
+                e = __shfl_sync(FULL, e, donor);
+                RaySetup r;
+                r.org.x = __shfl_sync(FULL, tr.r.org.x, donor), r.org.y = __shfl_sync(FULL, tr.r.org.y, donor);
+                r.org.z = __shfl_sync(FULL, tr.r.org.z, donor);
+                r.idx = __shfl_sync(FULL, tr.r.idx, donor), r.idy = __shfl_sync(FULL, tr.r.idy, donor);
+                r.idz = __shfl_sync(FULL, tr.r.idz, donor);
+                r.Sx = __shfl_sync(FULL, tr.r.Sx, donor), r.Sy = __shfl_sync(FULL, tr.r.Sy, donor);
+                r.Sz = __shfl_sync(FULL, tr.r.Sz, donor);
+                r.kx = __shfl_sync(FULL, tr.r.kx, donor), r.ky = __shfl_sync(FULL, tr.r.ky, donor);
+                r.kz = __shfl_sync(FULL, tr.r.kz, donor);
+                r.nearX = __shfl_sync(FULL, tr.r.nearX, donor), r.nearY = __shfl_sync(FULL, tr.r.nearY, donor);
+                r.nearZ = __shfl_sync(FULL, tr.r.nearZ, donor);
+                const float dTmin = __shfl_sync(FULL, tr.tmin, donor), dTmax = __shfl_sync(FULL, tr.tmax, donor);
+                const float dBest = __shfl_sync(FULL, tr.best, donor);
+                const uint32_t dFlat = __shfl_sync(FULL, tr.bestFlat, donor);
+                const uint32_t dSlot = __shfl_sync(FULL, slot, donor);
+                const unsigned dOwner = __shfl_sync(FULL, owner, donor);
+                if ((int)lane == helper)
+                {
+                    tr.r = r;
+                    tr.tmin = dTmin;
+                    tr.tmax = dTmax;
+                    tr.best = dBest;
+                    tr.bestFlat = dFlat;
+                    tr.hit.tri = 0xffffffffu;
+                    tr.hit.t = dTmax;
+                    tr.hit.b1 = tr.hit.b2 = 0.0f;
+                    tr.decal.dist = -1.0f;
+                    tr.cur = (int)(uint32_t)e;
+                    tr.leaf = PT_CHILD_EMPTY;
+                    tr.sp = 0;
+                    slot = dSlot;
+                    owner = dOwner;
+                    haveRay = true;
+                }
+            }
         }
     }
 }

@@ -110,13 +110,13 @@ __device__ __forceinline__ void generatePath(const RenderConst &rc, uint32_t slo
     }
     const PrimaryRays pr = constructPrimaryRay((float)px, (float)py, (float)rc.width, (float)rc.height, rc.cam, V2(ux, uy),
                                                u2, rc.lensRadius, rc.focalDistance);
-    rc.ps.rayO[slot] = make_float4(pr.origin.x, pr.origin.y, pr.origin.z, 0.0f); // MaxRoughness = 0
-    rc.ps.rayD[slot] = make_float4(pr.direction.x, pr.direction.y, pr.direction.z, __uint_as_float(rng));
-    rc.ps.thr[slot] = make_float4(1.0f, 1.0f, 1.0f, __uint_as_float(0u));
-    rc.ps.rad[slot] = make_float4(0.0f, 0.0f, 0.0f, __uint_as_float(restarts));
-    rc.ps.diff0[slot] = make_float4(pr.origin.x, pr.origin.y, pr.origin.z, pr.rxDirection.x);
-    rc.ps.diff1[slot] = make_float4(pr.rxDirection.y, pr.rxDirection.z, pr.origin.x, pr.origin.y);
-    rc.ps.diff2[slot] = make_float4(pr.origin.z, pr.ryDirection.x, pr.ryDirection.y, pr.ryDirection.z);
+    rc.ps.rec[slot].rayO = make_float4(pr.origin.x, pr.origin.y, pr.origin.z, 0.0f); // MaxRoughness = 0
+    rc.ps.rec[slot].rayD = make_float4(pr.direction.x, pr.direction.y, pr.direction.z, __uint_as_float(rng));
+    rc.ps.rec[slot].thr = make_float4(1.0f, 1.0f, 1.0f, __uint_as_float(0u));
+    rc.ps.rec[slot].rad = make_float4(0.0f, 0.0f, 0.0f, __uint_as_float(restarts));
+    rc.ps.rec[slot].diff0 = make_float4(pr.origin.x, pr.origin.y, pr.origin.z, pr.rxDirection.x);
+    rc.ps.rec[slot].diff1 = make_float4(pr.rxDirection.y, pr.rxDirection.z, pr.origin.x, pr.origin.y);
+    rc.ps.rec[slot].diff2 = make_float4(pr.origin.z, pr.ryDirection.x, pr.ryDirection.y, pr.ryDirection.z);
 }
 
 // work item -> (pixel, absolute sample index); starts the item's path in `slot`
@@ -125,7 +125,7 @@ __device__ __forceinline__ void startItem(const RenderConst &rc, uint32_t slot, 
     const uint32_t s = item / rc.pixelCount, pi = item - s * rc.pixelCount;
     const uint32_t pixel = __ldg(rc.pixelList + pi);
     const uint32_t py = pixel / rc.width, px = pixel - py * rc.width;
-    rc.ps.item[slot] = item;
+    rc.ps.rec[slot].item = item;
     generatePath(rc, slot, pixel, initRng(px, py, rc.width, rc.firstSample + rc.roundBase + s), 0);
 }
 
@@ -192,7 +192,7 @@ template <bool ALPHA, bool STATS> __global__ void __launch_bounds__(128, PT_TRAC
         [&](uint32_t slot) {
             RayPacket p;
             p.slot = slot;
-            const float4 o = rc.ps.rayO[p.slot], d = rc.ps.rayD[p.slot];
+            const float4 o = rc.ps.rec[p.slot].rayO, d = rc.ps.rec[p.slot].rayD;
             p.ox = o.x, p.oy = o.y, p.oz = o.z;
             p.dx = d.x, p.dy = d.y, p.dz = d.z;
             p.tmax = 10000.0f;
@@ -202,24 +202,26 @@ template <bool ALPHA, bool STATS> __global__ void __launch_bounds__(128, PT_TRAC
             if (t.hit.tri == 0xffffffffu)
             {
                 // miss.rmiss + raygen.rgen:71-75: the path ends with the sky radiance
-                const float4 thr4 = rc.ps.thr[slot], d = rc.ps.rayD[slot];
-                const float4 rad4 = rc.ps.rad[slot];
+                const float4 thr4 = rc.ps.rec[slot].thr, d = rc.ps.rec[slot].rayD;
+                const float4 rad4 = rc.ps.rec[slot].rad;
                 const vec3 radiance = V3(rad4) + V3(thr4) * skyRadiance(rc, V3(d));
-                rc.ps.rad[slot] = make_float4(radiance.x, radiance.y, radiance.z, rad4.w);
+                rc.ps.rec[slot].rad = make_float4(radiance.x, radiance.y, radiance.z, rad4.w);
                 rc.ps.doneQ[atomicAggInc(&rc.qc->done[cur])] = slot;
                 return;
             }
-            rc.ps.hit[slot] = make_float4(__uint_as_float(t.hit.tri), t.hit.t, t.hit.b1, t.hit.b2);
+            rc.ps.rec[slot].hit = make_float4(__uint_as_float(t.hit.tri), t.hit.t, t.hit.b1, t.hit.b2);
             if (ALPHA)
             {
-                rc.ps.decal[slot] = make_float4(t.decal.r, t.decal.g, t.decal.b, t.decal.dist);
-                rc.ps.decalA[slot] = t.decal.a;
+                rc.ps.rec[slot].decal = make_float4(t.decal.r, t.decal.g, t.decal.b, t.decal.dist);
+                rc.ps.rec[slot].decalA = t.decal.a;
             }
             const uint32_t pos = atomicAggInc(&rc.qc->hit);
             rc.ps.hitQ[pos] = slot;
             rc.ps.hitKey[pos] = t.hit.tri >> rc.hitKeyShift;
             hits++;
-        });
+        },
+        TailStats { rc.counters->visitHist, &rc.counters->warpIters, &rc.counters->warpDrainIters,
+                    &rc.counters->maxWarpDrainIters });
     warpAdd(&rc.counters->hits, hits);
     if (STATS)
     {
@@ -349,10 +351,10 @@ template <bool ALPHA, bool STATS> __global__ void __launch_bounds__(128, PT_SHAD
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
     {
         const uint32_t slot = (rc.sortHits ? rc.ps.hitQSorted : rc.ps.hitQ)[i];
-        const float4 hitv = rc.ps.hit[slot];
-        const float4 rayO = rc.ps.rayO[slot], rayD = rc.ps.rayD[slot];
-        float4 thr4 = rc.ps.thr[slot];
-        float4 rad4 = rc.ps.rad[slot];
+        const float4 hitv = rc.ps.rec[slot].hit;
+        const float4 rayO = rc.ps.rec[slot].rayO, rayD = rc.ps.rec[slot].rayD;
+        float4 thr4 = rc.ps.rec[slot].thr;
+        float4 rad4 = rc.ps.rec[slot].rad;
         vec3 throughput = V3(thr4), radiance = V3(rad4);
         uint32_t state = __float_as_uint(thr4.w);
         const vec3 rayDir = V3(rayD);
@@ -417,7 +419,7 @@ template <bool ALPHA, bool STATS> __global__ void __launch_bounds__(128, PT_SHAD
                 dndv = (-duv2.x * en1 + duv1.x * en2) * invDet;
             }
         }
-        const float4 d0 = rc.ps.diff0[slot], d1 = rc.ps.diff1[slot], d2 = rc.ps.diff2[slot];
+        const float4 d0 = rc.ps.rec[slot].diff0, d1 = rc.ps.rec[slot].diff1, d2 = rc.ps.rec[slot].diff2;
         RayDifferentials rd;
         rd.rxOrigin = V3(d0.x, d0.y, d0.z);
         rd.rxDirection = V3(d0.w, d1.x, d1.y);
@@ -440,9 +442,9 @@ template <bool ALPHA, bool STATS> __global__ void __launch_bounds__(128, PT_SHAD
                                                  STATS ? &texels : nullptr);
         if (ALPHA)
         {
-            const float4 dec = rc.ps.decal[slot];
+            const float4 dec = rc.ps.rec[slot].decal;
             if (dec.w != -1.0f && rayTmax > dec.w)
-                material.Color = mix(material.Color, V3(dec), rc.ps.decalA[slot]);
+                material.Color = mix(material.Color, V3(dec), rc.ps.rec[slot].decalA);
         }
         maxRoughness = fmaxf(material.Roughness, maxRoughness);
         material.Roughness = fmaxf(maxRoughness, 0.01f);
@@ -493,9 +495,9 @@ template <bool ALPHA, bool STATS> __global__ void __launch_bounds__(128, PT_SHAD
                 if (!(c.x == 0.0f && c.y == 0.0f && c.z == 0.0f))
                 {
                     const vec3 sd = -normalize(light.Direction);
-                    rc.ps.shO[slot] = make_float4(newPos.x, newPos.y, newPos.z, light.Distance);
-                    rc.ps.shD[slot] = make_float4(sd.x, sd.y, sd.z, 0.0f);
-                    rc.ps.shC[slot] = make_float4(c.x, c.y, c.z, 0.0f);
+                    rc.ps.rec[slot].shO = make_float4(newPos.x, newPos.y, newPos.z, light.Distance);
+                    rc.ps.rec[slot].shD = make_float4(sd.x, sd.y, sd.z, 0.0f);
+                    rc.ps.rec[slot].shC = make_float4(c.x, c.y, c.z, 0.0f);
                     rc.ps.shadowQueue[atomicAggInc(&rc.qc->shadow)] = slot;
                 }
             }
@@ -520,16 +522,16 @@ template <bool ALPHA, bool STATS> __global__ void __launch_bounds__(128, PT_SHAD
         else
             (cur ? rc.ps.contQ[0] : rc.ps.contQ[1])[atomicAggInc(&rc.qc->cont[cur ^ 1])] = slot;
 
-        rc.ps.rad[slot] = make_float4(radiance.x, radiance.y, radiance.z, rad4.w);
+        rc.ps.rec[slot].rad = make_float4(radiance.x, radiance.y, radiance.z, rad4.w);
         // the rng state outlives the path (a NaN/Inf restart continues the stream, raygen.rgen:99-112)
-        rc.ps.rayD[slot] = make_float4(newDir.x, newDir.y, newDir.z, __uint_as_float(rng));
+        rc.ps.rec[slot].rayD = make_float4(newDir.x, newDir.y, newDir.z, __uint_as_float(rng));
         if (!done)
         {
-            rc.ps.thr[slot] = make_float4(throughput.x, throughput.y, throughput.z, __uint_as_float(state));
-            rc.ps.rayO[slot] = make_float4(newPos.x, newPos.y, newPos.z, maxRoughness);
-            rc.ps.diff0[slot] = make_float4(rd.rxOrigin.x, rd.rxOrigin.y, rd.rxOrigin.z, rd.rxDirection.x);
-            rc.ps.diff1[slot] = make_float4(rd.rxDirection.y, rd.rxDirection.z, rd.ryOrigin.x, rd.ryOrigin.y);
-            rc.ps.diff2[slot] = make_float4(rd.ryOrigin.z, rd.ryDirection.x, rd.ryDirection.y, rd.ryDirection.z);
+            rc.ps.rec[slot].thr = make_float4(throughput.x, throughput.y, throughput.z, __uint_as_float(state));
+            rc.ps.rec[slot].rayO = make_float4(newPos.x, newPos.y, newPos.z, maxRoughness);
+            rc.ps.rec[slot].diff0 = make_float4(rd.rxOrigin.x, rd.rxOrigin.y, rd.rxOrigin.z, rd.rxDirection.x);
+            rc.ps.rec[slot].diff1 = make_float4(rd.rxDirection.y, rd.rxDirection.z, rd.ryOrigin.x, rd.ryOrigin.y);
+            rc.ps.rec[slot].diff2 = make_float4(rd.ryOrigin.z, rd.ryDirection.x, rd.ryDirection.y, rd.ryDirection.z);
         }
     }
     if (STATS)
@@ -552,7 +554,7 @@ template <bool ALPHA, bool STATS> __global__ void __launch_bounds__(128, PT_TRAC
         [&](uint32_t slot) {
             RayPacket p;
             p.slot = slot;
-            const float4 o = rc.ps.shO[p.slot], d = rc.ps.shD[p.slot];
+            const float4 o = rc.ps.rec[p.slot].shO, d = rc.ps.rec[p.slot].shD;
             p.ox = o.x, p.oy = o.y, p.oz = o.z;
             p.dx = d.x, p.dy = d.y, p.dz = d.z;
             p.tmax = o.w;
@@ -561,14 +563,16 @@ template <bool ALPHA, bool STATS> __global__ void __launch_bounds__(128, PT_TRAC
         [&](Traverser<false, ALPHA, STATS> &t, uint32_t slot) {
             if (t.hit.tri == 0xffffffffu)
             {
-                const float4 c = rc.ps.shC[slot];
-                float4 r = rc.ps.rad[slot];
+                const float4 c = rc.ps.rec[slot].shC;
+                float4 r = rc.ps.rec[slot].rad;
                 r.x += c.x;
                 r.y += c.y;
                 r.z += c.z;
-                rc.ps.rad[slot] = r;
+                rc.ps.rec[slot].rad = r;
             }
-        });
+        },
+        TailStats { rc.counters->visitHist, &rc.counters->warpIters, &rc.counters->warpDrainIters,
+                    &rc.counters->maxWarpDrainIters });
     if (STATS)
     {
         warpAdd(&rc.counters->boxShadow, tr.st.boxTests);
@@ -582,39 +586,50 @@ template <bool ALPHA, bool STATS> __global__ void __launch_bounds__(128, PT_TRAC
 // ---------------------------------------------------------------------------------------------
 // finish: raygen.rgen:99-117 for finished paths, then the next work item
 // ---------------------------------------------------------------------------------------------
-// Block-aggregated queue reservation: every thread of the block calls it (uniform control flow);
-// threads with want = true get consecutive positions, the whole block costs ONE atomic.  Hot
-// same-address atomics are serialised by the L2 (a few ns each), so per-warp reservations made
-// k_finish atomic-bound.
-template <int WARPS> __device__ __forceinline__ uint32_t blockReserve(bool want, uint32_t *counter, uint32_t *scratch)
+// Block-aggregated queue reservation: every thread of the block calls it (uniform control flow)
+// with the number of entries it wants; it gets the first of its consecutive positions, and the
+// whole block costs ONE atomic.  Hot same-address atomics are serialised by the L2 (a few ns
+// each), so per-warp reservations made k_finish atomic-bound.
+template <int WARPS> __device__ __forceinline__ uint32_t blockReserve(uint32_t count, uint32_t *counter, uint32_t *scratch)
 {
     const unsigned lane = laneId(), warp = threadIdx.x >> 5;
-    const unsigned mask = __ballot_sync(0xffffffffu, want);
-    if (lane == 0)
-        scratch[warp] = __popc(mask);
+    uint32_t incl = count;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1)
+    {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+        if ((int)lane >= o)
+            incl += t;
+    }
+    if (lane == 31)
+        scratch[warp] = incl;
     __syncthreads();
     if (warp == 0)
     {
         const uint32_t v = lane < WARPS ? scratch[lane] : 0;
-        uint32_t incl = v;
+        uint32_t wIncl = v;
 #pragma unroll
         for (int o = 1; o < WARPS; o <<= 1)
         {
-            const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+            const uint32_t t = __shfl_up_sync(0xffffffffu, wIncl, o);
             if ((int)lane >= o)
-                incl += t;
+                wIncl += t;
         }
-        const uint32_t total = __shfl_sync(0xffffffffu, incl, WARPS - 1);
+        const uint32_t total = __shfl_sync(0xffffffffu, wIncl, WARPS - 1);
         uint32_t base = 0;
         if (lane == 0 && total)
             base = atomicAdd(counter, total);
         base = __shfl_sync(0xffffffffu, base, 0);
         if (lane < WARPS)
-            scratch[WARPS + lane] = base + incl - v;
+            scratch[WARPS + lane] = base + wIncl - v;
     }
     __syncthreads();
-    return scratch[WARPS + warp] + __popc(mask & ((1u << lane) - 1u));
+    return scratch[WARPS + warp] + incl - count;
 }
+
+// Each thread handles PT_FINISH_ITEMS finished paths per block iteration: their loads are in
+// flight together and the two block-wide reservations are amortised over four times the work.
+#define PT_FINISH_ITEMS 4
 
 __global__ void __launch_bounds__(256) k_finish(RenderConst rc, int cur)
 {
@@ -632,47 +647,83 @@ __global__ void __launch_bounds__(256) k_finish(RenderConst rc, int cur)
         rc.qc->shadowWork = 0;
         rc.qc->done[cur ^ 1] = 0;
     }
-    const uint32_t stride = gridDim.x * blockDim.x;
+    constexpr uint32_t K = PT_FINISH_ITEMS, TILE = 256 * K;
     uint32_t samples = 0, restarts = 0;
     uint32_t *freshOut = cur ? rc.ps.freshQ[0] : rc.ps.freshQ[1];
     // uniform trip count: every thread of the block takes part in the block-wide reservations
-    for (uint32_t first = blockIdx.x * blockDim.x; first < n; first += stride)
+    for (uint32_t first = blockIdx.x * TILE; first < n; first += gridDim.x * TILE)
     {
-        const uint32_t i = first + threadIdx.x;
-        const bool valid = i < n;
-        uint32_t slot = 0, item = 0, restartCount = 0;
-        bool restart = false, park = false;
-        if (valid)
+        uint32_t slot[K], item[K], restartCount[K];
+        float4 r[K];
+        bool valid[K], restart[K], park[K];
+#pragma unroll
+        for (uint32_t k = 0; k < K; k++)
         {
-            slot = rc.ps.doneQ[i];
-            const float4 r = rc.ps.rad[slot];
-            item = rc.ps.item[slot];
-            restartCount = __float_as_uint(r.w);
-            samples++;
-            const bool isBad = bad(r.x) || bad(r.y) || bad(r.z);
-            // radiance = 0; smpl = -1: the sample is redone with the ADVANCED rng state
-            restart = isBad && restartCount < kMaxRestarts;
-            park = !restart;
-            // park the sample; k_resolve adds the round's samples to the image in sample order
-            if (park)
-                rc.sbuf[item] = isBad ? make_float4(0.0f, 0.0f, 0.0f, 0.0f) : r;
+            const uint32_t i = first + threadIdx.x * K + k;
+            valid[k] = i < n;
+            slot[k] = valid[k] ? rc.ps.doneQ[i] : 0u;
         }
-        // pull the next work items: the threads of a block that finish together take consecutive
+#pragma unroll
+        for (uint32_t k = 0; k < K; k++)
+            if (valid[k])
+            {
+                r[k] = rc.ps.rec[slot[k]].rad;
+                item[k] = rc.ps.rec[slot[k]].item;
+            }
+        uint32_t parks = 0;
+#pragma unroll
+        for (uint32_t k = 0; k < K; k++)
+        {
+            restart[k] = park[k] = false;
+            if (valid[k])
+            {
+                restartCount[k] = __float_as_uint(r[k].w);
+                samples++;
+                const bool isBad = bad(r[k].x) || bad(r[k].y) || bad(r[k].z);
+                // radiance = 0; smpl = -1: the sample is redone with the ADVANCED rng state
+                restart[k] = isBad && restartCount[k] < kMaxRestarts;
+                park[k] = !restart[k];
+                // park the sample; k_resolve adds the round's samples to the image in sample order
+                if (park[k])
+                {
+                    rc.sbuf[item[k]] = isBad ? make_float4(0.0f, 0.0f, 0.0f, 0.0f) : r[k];
+                    parks++;
+                }
+            }
+        }
+        // pull the next work items: the paths of a block that finish together take consecutive
         // items (= neighbouring pixels, 8x4 blocks) and consecutive positions of the fresh queue
-        const uint32_t next = blockReserve<8>(park, rc.nextItem, scratch[0]);
-        const bool regenerate = park && next < rc.itemCount;
-        const uint32_t pos = blockReserve<8>(restart || regenerate, &rc.qc->fresh[cur ^ 1], scratch[1]);
-        if (restart)
+        uint32_t next = blockReserve<8>(parks, rc.nextItem, scratch[0]);
+        uint32_t fresh = 0;
+        bool regenerate[K];
+#pragma unroll
+        for (uint32_t k = 0; k < K; k++)
         {
-            restarts++;
-            const uint32_t s = item / rc.pixelCount, pi = item - s * rc.pixelCount;
-            generatePath(rc, slot, __ldg(rc.pixelList + pi), __float_as_uint(rc.ps.rayD[slot].w), restartCount + 1);
-            freshOut[pos] = slot;
+            regenerate[k] = false;
+            if (park[k])
+            {
+                regenerate[k] = next < rc.itemCount;
+                item[k] = next++;
+            }
+            fresh += (restart[k] || regenerate[k]) ? 1u : 0u;
         }
-        else if (regenerate)
+        uint32_t pos = blockReserve<8>(fresh, &rc.qc->fresh[cur ^ 1], scratch[1]);
+#pragma unroll
+        for (uint32_t k = 0; k < K; k++)
         {
-            startItem(rc, slot, next);
-            freshOut[pos] = slot;
+            if (restart[k])
+            {
+                restarts++;
+                const uint32_t s = item[k] / rc.pixelCount, pi = item[k] - s * rc.pixelCount;
+                generatePath(rc, slot[k], __ldg(rc.pixelList + pi), __float_as_uint(rc.ps.rec[slot[k]].rayD.w),
+                             restartCount[k] + 1);
+                freshOut[pos++] = slot[k];
+            }
+            else if (regenerate[k])
+            {
+                startItem(rc, slot[k], item[k]);
+                freshOut[pos++] = slot[k];
+            }
         }
     }
     warpAdd(&rc.counters->samples, samples);
@@ -942,7 +993,7 @@ pt_status renderSamples(Context *ctx, const pt_render_params *params, uint32_t f
         // thousands of nodes); with one wavefront the whole GPU waits for them every iteration.
         // Several smaller wavefronts on separate streams fill those tails with each other's kernels.
         const uint32_t slotsTotal = std::min(ctx->slotCapacity, base.itemCount);
-        uint32_t poolCount = std::max(1u, std::min(ctx->poolCount, slotsTotal / 65536u));
+        uint32_t poolCount = std::max(1u, std::min(ctx->poolCount, slotsTotal / 16384u));
         const uint32_t poolSlots = slotsTotal / poolCount; // the last pool takes the remainder
         struct Pool
         {
@@ -950,7 +1001,7 @@ pt_status renderSamples(Context *ctx, const pt_render_params *params, uint32_t f
             cudaStream_t stream;
             QueueCounts *hq;
             void *sortTemp;
-            uint32_t gridExtend, gridShadow, gridShade, gridWide;
+            uint32_t gridExtend, gridShadow, gridShade, gridWide, gridFinish;
             int cur;
             bool active;
         };
@@ -998,6 +1049,7 @@ pt_status renderSamples(Context *ctx, const pt_render_params *params, uint32_t f
             else
                 pl.gridExtend = residentGrid(k_extend<false, false>), pl.gridShadow = residentGrid(k_shadow<false, false>);
             pl.gridWide = std::min((slots + 255) / 256, (uint32_t)ctx->smCount * 8);
+            pl.gridFinish = std::min((slots + 256 * PT_FINISH_ITEMS - 1) / (256 * PT_FINISH_ITEMS), (uint32_t)ctx->smCount * 8);
             if (pl.stream != ctx->stream)
                 PT_CUDA_CHECK(ctx, cudaStreamWaitEvent(pl.stream, ctx->evRound, 0));
             k_init<<<pl.gridWide, 256, 0, pl.stream>>>(pl.rc);
@@ -1040,7 +1092,7 @@ pt_status renderSamples(Context *ctx, const pt_render_params *params, uint32_t f
             PT_DISPATCH(k_shadow, pl.gridShadow, 128, rc);
             end(st);
             begin(PT_KERNEL_FINISH, st);
-            k_finish<<<pl.gridWide, 256, 0, st>>>(rc, cur);
+            k_finish<<<pl.gridFinish, 256, 0, st>>>(rc, cur);
             end(st);
 #undef PT_DISPATCH
             ctx->stats.kernel_launches += 4;

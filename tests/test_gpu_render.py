@@ -138,6 +138,35 @@ def test_traversal_stats_toggle(feature):
     assert r.stats()["box_tests_closest"] == 0
 
 
+def test_scheduling_knobs_do_not_change_the_image(oracle_mod):
+    """Pools, slot count, hit sorting and the per-round sample budget only change scheduling: the
+    accumulated image is bit-identical (samples are parked and summed in sample order)."""
+    s = scenes.chess_scene(320, 180, segments=24, rings=20, board_tess=32, texture_size=128)
+    p = s.default_params(bounce_count=6)
+    W, H, spp = 320, 180, 12
+    images = []
+    for knobs in ({}, {"pools": 1, "sort_hits": 0}, {"pools": 3, "slots": 200_000}, {"pools": 8, "slots": 140_000, "sbuf_mb": 4},
+                  {"pools": 2, "slots": 5000, "sbuf_mb": 1}):
+        r = conftest.core.Renderer(0)
+        try:
+            for k, v in knobs.items():
+                r.set_tuning(k, v)
+            r.update_scene_data(s)
+            r.on_resize(W, H)
+            r.render(spp, params=p)
+            images.append(r.read_accumulation().copy())
+            st = r.stats()
+            assert st["samples"] >= W * H * spp  # restarts count as samples too
+        finally:
+            r.close()
+    for img in images[1:]:
+        assert (img == images[0]).all()
+    # and the image is the oracle's
+    ref, _ = oracle_mod.OracleScene(s).render(p, W, H, 0, spp)
+    assert metrics.close_fraction(images[0], ref, 1e-3) > 0.97
+    assert metrics.rel_mse(images[0] / spp, ref / spp) <= 1e-3
+
+
 def test_kernel_timing(feature):
     s, r, _ = feature
     r.on_resize(64, 48)
