@@ -32,9 +32,9 @@ struct DeviceCounters
 struct QueueCounts
 {
     uint32_t cont[2];  // double-buffered queue sizes: continuing paths ...
-    uint32_t fresh[2]; // ... and freshly generated primary rays
+    uint32_t regen[2]; // ... and ended paths whose slot takes the next work item inside k_extend
     uint32_t hit;      // slots whose closest-hit query hit (input of k_shade)
-    uint32_t done[2];  // slots whose path ended in iteration parity [cur] (input of k_finish)
+    uint32_t pad2[2];
     uint32_t shadow;
     uint32_t extendWork; // ray-queue positions handed out to the persistent warps of k_extend ...
     uint32_t shadowWork; // ... and k_shadow
@@ -51,20 +51,19 @@ struct __align__(128) PathRecord
     // line A — the bounce state (k_extend reads rayO/rayD, k_shade reads and rewrites all of it)
     float4 rayO;  // origin.xyz, maxRoughness
     float4 rayD;  // direction.xyz, rng (bits)
-    float4 thr;   // throughput.xyz, bounce count (bits)
-    float4 rad;   // radiance.xyz, restarts (bits)
+    float4 thr;   // throughput.xyz, bits: bounce count | NaN/Inf restarts of the sample << 8
+    float4 rad;   // radiance.xyz, work item (bits): round-relative sample * pixelCount + pixel-list index
     float4 diff0; // rxOrigin.xyz, rxDirection.x
     float4 diff1; // rxDirection.yz, ryOrigin.xy
     float4 diff2; // ryOrigin.z, ryDirection.xyz
     float4 hit;   // tri (bits), t, b1, b2
-    // line B — the shadow ray, the decal record and the work item
+    // line B — the shadow ray and the decal record
     float4 shO;   // shadow origin.xyz, tmax
     float4 shD;   // shadow direction.xyz, -
     float4 shC;   // contribution.xyz (throughput * DirectLight / pdf), -
     float4 decal; // rgb, dist (scenes with alpha-tested geometry)
-    uint32_t item; // work item of the slot (round-relative sample * pixelCount + pixel-list index)
     float decalA;
-    uint32_t pad[2];
+    uint32_t pad[3];
     float4 spare[3];
 };
 static_assert(sizeof(PathRecord) == 256, "PathRecord must be two 128-byte lines");
@@ -73,8 +72,7 @@ struct PathState
 {
     PathRecord *rec;
     uint32_t *contQ[2];  // active slots with a continuing path, double buffered
-    uint32_t *freshQ[2]; // active slots with a fresh primary ray, double buffered
-    uint32_t *doneQ;     // slots whose path has ended (missed, terminated or out of bounces)
+    uint32_t *regenQ[2]; // slots whose path has ended (| PT_REGEN, | PT_REGEN_MISS if it left the scene), double buffered
     uint32_t *hitQ;      // slots to shade (k_extend order)
     uint32_t *hitKey;    // sort key of hitQ[i]: leaf-order triangle index >> hitKeyShift (0xffffffff = unused)
     uint32_t *hitQSorted, *hitKeySorted; // after the radix sort: coherent warps for k_shade

@@ -216,9 +216,8 @@ pt_status pt_render_begin(pt_context *ctx, uint32_t width, uint32_t height)
         PT_T(targetAlloc(ctx, &ps.rec, slots));
         PT_T(targetAlloc(ctx, &ps.contQ[0], slots));
         PT_T(targetAlloc(ctx, &ps.contQ[1], slots));
-        PT_T(targetAlloc(ctx, &ps.freshQ[0], slots));
-        PT_T(targetAlloc(ctx, &ps.freshQ[1], slots));
-        PT_T(targetAlloc(ctx, &ps.doneQ, slots));
+        PT_T(targetAlloc(ctx, &ps.regenQ[0], slots));
+        PT_T(targetAlloc(ctx, &ps.regenQ[1], slots));
         PT_T(targetAlloc(ctx, &ps.hitQ, slots));
         PT_T(targetAlloc(ctx, &ps.hitKey, slots));
         PT_T(targetAlloc(ctx, &ps.hitQSorted, slots));

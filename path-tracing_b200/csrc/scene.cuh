@@ -129,8 +129,11 @@ PT_DEV float4 sampleBilinear(const DeviceScene &s, const DevTexture &t, uint32_t
     const float fx0 = floorf(x), fy0 = floorf(y);
     const float fx = x - fx0, fy = y - fy0;
     const int W = (int)lw, H = (int)lh;
-    const int x0 = (((int)fx0 % W) + W) % W, x1 = (x0 + 1) % W;
-    const int y0 = (((int)fy0 % H) + H) % H, y1 = (y0 + 1) % H;
+    // repeat wrap: u, v are in [0, 1] here, so floor(x) is in [-1, W - 1] and one conditional
+    // replaces the oracle's ((i % W) + W) % W (same integers, no integer divisions)
+    const int ix = (int)fx0, iy = (int)fy0;
+    const int x0 = ix < 0 ? W - 1 : ix, x1 = x0 + 1 == W ? 0 : x0 + 1;
+    const int y0 = iy < 0 ? H - 1 : iy, y1 = y0 + 1 == H ? 0 : y0 + 1;
     const float4 t00 = fetchTexel(s, t, level, x0, y0, lw), t10 = fetchTexel(s, t, level, x1, y0, lw);
     const float4 t01 = fetchTexel(s, t, level, x0, y1, lw), t11 = fetchTexel(s, t, level, x1, y1, lw);
     return lerp4(lerp4(t00, t10, fx), lerp4(t01, t11, fx), fy);

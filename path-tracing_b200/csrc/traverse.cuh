@@ -433,8 +433,9 @@ PT_DEV void traverse(const DeviceScene &s, vec3 org, vec3 dir, float tmin, float
 // still traversing.  Queue positions are handed out to warps in chunks of PT_FETCH_CHUNK through
 // one atomic per chunk; inside a chunk lanes take positions by ballot arithmetic.
 //
-//   loadSlot(i)        : issue the load of queue entry i (the slot index)
-//   loadRay(slot)      : issue the loads of that slot's ray, return them as a RayPacket
+//   loadSlot(i)        : issue the load of queue entry i (the slot index, possibly with flag bits)
+//   loadRay(entry)     : issue the loads of that entry's ray, return them as a RayPacket (k_extend also
+//                        regenerates ended paths here; slot 0xffffffff = no ray)
 //   commit(tr, slot)   : ray finished — write the result
 //
 // Two details matter as much as the refill itself:
@@ -550,7 +551,8 @@ PT_DEV void tracePersistent(const DeviceScene &s, uint32_t n, uint32_t *workCoun
             p.dy = __shfl_sync(FULL, pf.dy, src);
             p.dz = __shfl_sync(FULL, pf.dz, src);
             p.tmax = __shfl_sync(FULL, pf.tmax, src);
-            if (!haveRay && rank < take)
+            // (a packet with slot 0xffffffff carries no ray: the lane stays idle and is offered the next one)
+            if (!haveRay && rank < take && p.slot != 0xffffffffu)
             {
                 slot = p.slot;
                 owner = lane;

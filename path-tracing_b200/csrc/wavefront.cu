@@ -9,17 +9,19 @@
 // on scheduling, slot count or tile partition, bit for bit.  Per iteration:
 //
 //   k_extend   closest-hit traversal of every active slot's ray          (raygen.rgen:68)
-//   k_shade    miss.rmiss / closestHit.rchit + the raygen bounce logic     (raygen.rgen:71-96)
+//              PATH REGENERATION happens here too: a slot whose path ended in the previous
+//              iteration (regen queue) is finished while its ray would be fetched — miss.rmiss,
+//              NaN/Inf restart or park the sample and pull the next work item, generate the primary
+//              ray (raygen.rgen:38-58, 71-75, 99-117) — and the new ray is traversed right away
+//   k_shade    closestHit.rchit + the raygen bounce logic                  (raygen.rgen:76-96)
 //              emits a shadow ray into a compacted queue when NEE can contribute
 //   k_shadow   occlusion traversal, adds the direct-light contribution    (raygen.rgen:79-81)
-//   k_finish   finished paths: NaN/Inf restart or park the sample and pull the next work item
-//              (raygen.rgen:38-58, 99-117); builds the next compacted queues
 //
-// Path state is SoA float4 streams indexed by slot (coalesced 16-byte accesses); queues hold slot
-// indices and are compacted with warp-aggregated atomics.  Continuing (incoherent) paths and
-// freshly generated (coherent, consecutive pixels of an 8x4 block) primary rays go to separate
-// queues so that warps of k_extend are not a mix of both.  Queue order never influences a
-// slot's arithmetic, so results are deterministic.
+// Path state is one 256-byte record per slot (core_internal.h); queues hold slot indices and are
+// compacted with warp-aggregated atomics.  Continuing (incoherent) paths and ended paths (whose
+// successors are coherent primary rays: consecutive pixels of an 8x4 block) go to separate queues
+// so that warps of k_extend are not a mix of both.  Queue order never influences a slot's
+// arithmetic, so results are deterministic.
 #include "core_internal.h"
 #include "shading.cuh"
 #include "traverse.cuh"
@@ -93,11 +95,17 @@ __device__ __forceinline__ void warpAdd(unsigned long long *counter, uint32_t va
         atomicAdd(counter, (unsigned long long)value);
 }
 
+// queue entry flags (slot indices need 24 bits at most)
+constexpr uint32_t kRegen = 0x40000000u;     // regen queue entry: the slot's path has ended
+constexpr uint32_t kRegenMiss = 0x80000000u; // ... by leaving the scene: throughput * sky is still to be added
+constexpr uint32_t kSlotMask = 0x3fffffffu;
+constexpr uint32_t kDeadSlot = 0xffffffffu;  // RayPacket::slot of a regen entry that found no work item left
+
 // ---------------------------------------------------------------------------------------------
-// raygen.rgen:44-60 — start one sample of a slot's pixel
+// raygen.rgen:44-60 — start one sample of a slot's pixel; returns the primary ray
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ void generatePath(const RenderConst &rc, uint32_t slot, uint32_t pixel, uint32_t rng,
-                                             uint32_t restarts)
+__device__ __forceinline__ PrimaryRays generatePath(const RenderConst &rc, uint32_t slot, uint32_t pixel, uint32_t item,
+                                                    uint32_t rng, uint32_t restarts)
 {
     const uint32_t py = pixel / rc.width, px = pixel - py * rc.width;
     const float ux = rnd(rng);
@@ -110,23 +118,24 @@ __device__ __forceinline__ void generatePath(const RenderConst &rc, uint32_t slo
     }
     const PrimaryRays pr = constructPrimaryRay((float)px, (float)py, (float)rc.width, (float)rc.height, rc.cam, V2(ux, uy),
                                                u2, rc.lensRadius, rc.focalDistance);
-    rc.ps.rec[slot].rayO = make_float4(pr.origin.x, pr.origin.y, pr.origin.z, 0.0f); // MaxRoughness = 0
-    rc.ps.rec[slot].rayD = make_float4(pr.direction.x, pr.direction.y, pr.direction.z, __uint_as_float(rng));
-    rc.ps.rec[slot].thr = make_float4(1.0f, 1.0f, 1.0f, __uint_as_float(0u));
-    rc.ps.rec[slot].rad = make_float4(0.0f, 0.0f, 0.0f, __uint_as_float(restarts));
-    rc.ps.rec[slot].diff0 = make_float4(pr.origin.x, pr.origin.y, pr.origin.z, pr.rxDirection.x);
-    rc.ps.rec[slot].diff1 = make_float4(pr.rxDirection.y, pr.rxDirection.z, pr.origin.x, pr.origin.y);
-    rc.ps.rec[slot].diff2 = make_float4(pr.origin.z, pr.ryDirection.x, pr.ryDirection.y, pr.ryDirection.z);
+    PathRecord &rec = rc.ps.rec[slot];
+    rec.rayO = make_float4(pr.origin.x, pr.origin.y, pr.origin.z, 0.0f); // MaxRoughness = 0
+    rec.rayD = make_float4(pr.direction.x, pr.direction.y, pr.direction.z, __uint_as_float(rng));
+    rec.thr = make_float4(1.0f, 1.0f, 1.0f, __uint_as_float(restarts << 8)); // bounce 0
+    rec.rad = make_float4(0.0f, 0.0f, 0.0f, __uint_as_float(item));
+    rec.diff0 = make_float4(pr.origin.x, pr.origin.y, pr.origin.z, pr.rxDirection.x);
+    rec.diff1 = make_float4(pr.rxDirection.y, pr.rxDirection.z, pr.origin.x, pr.origin.y);
+    rec.diff2 = make_float4(pr.origin.z, pr.ryDirection.x, pr.ryDirection.y, pr.ryDirection.z);
+    return pr;
 }
 
 // work item -> (pixel, absolute sample index); starts the item's path in `slot`
-__device__ __forceinline__ void startItem(const RenderConst &rc, uint32_t slot, uint32_t item)
+__device__ __forceinline__ PrimaryRays startItem(const RenderConst &rc, uint32_t slot, uint32_t item)
 {
     const uint32_t s = item / rc.pixelCount, pi = item - s * rc.pixelCount;
     const uint32_t pixel = __ldg(rc.pixelList + pi);
     const uint32_t py = pixel / rc.width, px = pixel - py * rc.width;
-    rc.ps.rec[slot].item = item;
-    generatePath(rc, slot, pixel, initRng(px, py, rc.width, rc.firstSample + rc.roundBase + s), 0);
+    return generatePath(rc, slot, pixel, item, initRng(px, py, rc.width, rc.firstSample + rc.roundBase + s), 0);
 }
 
 // slot i (of all pools together) starts with work item i of the round
@@ -136,28 +145,26 @@ __global__ void __launch_bounds__(256) k_init(RenderConst rc)
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < rc.slotCount; i += stride)
     {
         const uint32_t slot = rc.slotBase + i;
-        rc.ps.freshQ[0][i] = slot;
+        rc.ps.contQ[0][i] = slot;
         startItem(rc, slot, slot);
     }
     if (blockIdx.x == 0 && threadIdx.x == 0)
     {
-        rc.qc->cont[0] = 0;
-        rc.qc->fresh[0] = rc.slotCount;
+        rc.qc->cont[0] = rc.slotCount;
+        rc.qc->regen[0] = 0;
         rc.qc->cont[1] = 0;
-        rc.qc->fresh[1] = 0;
+        rc.qc->regen[1] = 0;
         rc.qc->shadow = 0;
         rc.qc->hit = 0;
-        rc.qc->done[0] = 0;
-        rc.qc->done[1] = 0;
         rc.qc->extendWork = 0;
         rc.qc->shadowWork = 0;
     }
 }
 
-// i-th active slot of queue pair `cur`: continuing paths first, then fresh primary rays
+// i-th entry of queue pair `cur`: continuing paths first, then the ended ones
 __device__ __forceinline__ uint32_t activeSlot(const RenderConst &rc, int cur, uint32_t i, uint32_t nCont)
 {
-    return i < nCont ? (cur ? rc.ps.contQ[1] : rc.ps.contQ[0])[i] : (cur ? rc.ps.freshQ[1] : rc.ps.freshQ[0])[i - nCont];
+    return i < nCont ? (cur ? rc.ps.contQ[1] : rc.ps.contQ[0])[i] : (cur ? rc.ps.regenQ[1] : rc.ps.regenQ[0])[i - nCont];
 }
 
 // miss.rmiss:16-39
@@ -177,11 +184,60 @@ __device__ __forceinline__ vec3 skyRadiance(const RenderConst &rc, vec3 dir)
 // ---------------------------------------------------------------------------------------------
 // extend
 // ---------------------------------------------------------------------------------------------
+// raygen.rgen:71-75, 99-117 and 38-58 for one ended path: finish its sample and start the slot's next
+// one.  Called where k_extend would load the slot's ray, by a converged batch of regen-queue entries,
+// so the lanes of a warp take consecutive work items (neighbouring pixels) with one atomic.
+__device__ __forceinline__ RayPacket regeneratePath(const RenderConst &rc, uint32_t entry, uint32_t &samples, uint32_t &restarts)
+{
+    const uint32_t slot = entry & kSlotMask;
+    const PathRecord &rec = rc.ps.rec[slot];
+    const float4 rad4 = rec.rad, thr4 = rec.thr, d4 = rec.rayD;
+    vec3 radiance = V3(rad4);
+    if (entry & kRegenMiss) // miss.rmiss + raygen.rgen:71-75: the path ended with the sky radiance
+        radiance = radiance + V3(thr4) * skyRadiance(rc, V3(d4));
+    uint32_t item = __float_as_uint(rad4.w);
+    uint32_t restartCount = __float_as_uint(thr4.w) >> 8;
+    const bool isBad = bad(radiance.x) || bad(radiance.y) || bad(radiance.z);
+    // raygen.rgen:99-112: radiance = 0; smpl = -1 — the sample is redone with the ADVANCED rng state
+    const bool restart = isBad && restartCount < kMaxRestarts;
+    RayPacket p;
+    p.slot = kDeadSlot;
+    p.ox = p.oy = p.oz = p.dx = p.dy = p.dz = p.tmax = 0.0f;
+    PrimaryRays pr;
+    if (restart)
+    {
+        restarts++;
+        const uint32_t s = item / rc.pixelCount, pi = item - s * rc.pixelCount;
+        pr = generatePath(rc, slot, __ldg(rc.pixelList + pi), item, __float_as_uint(d4.w), restartCount + 1);
+    }
+    else
+    {
+        // park the sample; k_resolve adds the round's samples to the image in sample order
+        rc.sbuf[item] = isBad ? make_float4(0.0f, 0.0f, 0.0f, 0.0f) : make_float4(radiance.x, radiance.y, radiance.z, 1.0f);
+        samples++;
+        item = atomicAggInc(rc.nextItem);
+        if (item >= rc.itemCount)
+            return p; // the round has no work left for this slot
+        pr = startItem(rc, slot, item);
+    }
+    p.slot = slot;
+    p.ox = pr.origin.x, p.oy = pr.origin.y, p.oz = pr.origin.z;
+    p.dx = pr.direction.x, p.dy = pr.direction.y, p.dz = pr.direction.z;
+    p.tmax = 10000.0f;
+    return p;
+}
+
 template <bool ALPHA, bool STATS> __global__ void __launch_bounds__(128, PT_TRACE_MIN_BLOCKS) k_extend(RenderConst rc, int cur)
 {
-    const uint32_t nCont = rc.qc->cont[cur], n = nCont + rc.qc->fresh[cur];
-    // (the counters of the queues this iteration fills were reset by k_init / the previous k_finish)
-    uint32_t hits = 0;
+    const uint32_t nCont = rc.qc->cont[cur], n = nCont + rc.qc->regen[cur];
+    // counters of k_shadow, which has completed (stream order) and is not running now
+    if (blockIdx.x == 0 && threadIdx.x == 0)
+    {
+        rc.qc->shadow = 0;
+        rc.qc->shadowWork = 0;
+    }
+    uint32_t hits = 0, rays = 0, samples = 0, restarts = 0;
+    uint32_t *regenOut = cur ? rc.ps.regenQ[0] : rc.ps.regenQ[1];
     unsigned long long stack[PT_STACK_SIZE];
     Traverser<true, ALPHA, STATS> tr;
     tr.stack = stack;
@@ -189,9 +245,11 @@ template <bool ALPHA, bool STATS> __global__ void __launch_bounds__(128, PT_TRAC
     tracePersistent(
         rc.scene, n, &rc.qc->extendWork, tr, 0.00001f,
         [&](uint32_t i) { return activeSlot(rc, cur, i, nCont); },
-        [&](uint32_t slot) {
+        [&](uint32_t entry) {
+            if (entry & kRegen)
+                return regeneratePath(rc, entry, samples, restarts);
             RayPacket p;
-            p.slot = slot;
+            p.slot = entry;
             const float4 o = rc.ps.rec[p.slot].rayO, d = rc.ps.rec[p.slot].rayD;
             p.ox = o.x, p.oy = o.y, p.oz = o.z;
             p.dx = d.x, p.dy = d.y, p.dz = d.z;
@@ -199,14 +257,11 @@ template <bool ALPHA, bool STATS> __global__ void __launch_bounds__(128, PT_TRAC
             return p;
         },
         [&](Traverser<true, ALPHA, STATS> &t, uint32_t slot) {
+            rays++;
             if (t.hit.tri == 0xffffffffu)
             {
-                // miss.rmiss + raygen.rgen:71-75: the path ends with the sky radiance
-                const float4 thr4 = rc.ps.rec[slot].thr, d = rc.ps.rec[slot].rayD;
-                const float4 rad4 = rc.ps.rec[slot].rad;
-                const vec3 radiance = V3(rad4) + V3(thr4) * skyRadiance(rc, V3(d));
-                rc.ps.rec[slot].rad = make_float4(radiance.x, radiance.y, radiance.z, rad4.w);
-                rc.ps.doneQ[atomicAggInc(&rc.qc->done[cur])] = slot;
+                // the path ends; its sample is finished by the next k_extend (regeneratePath)
+                regenOut[atomicAggInc(&rc.qc->regen[cur ^ 1])] = slot | kRegen | kRegenMiss;
                 return;
             }
             rc.ps.rec[slot].hit = make_float4(__uint_as_float(t.hit.tri), t.hit.t, t.hit.b1, t.hit.b2);
@@ -223,14 +278,15 @@ template <bool ALPHA, bool STATS> __global__ void __launch_bounds__(128, PT_TRAC
         TailStats { rc.counters->visitHist, &rc.counters->warpIters, &rc.counters->warpDrainIters,
                     &rc.counters->maxWarpDrainIters });
     warpAdd(&rc.counters->hits, hits);
+    warpAdd(&rc.counters->raysClosest, rays);
+    warpAdd(&rc.counters->samples, samples);
+    warpAdd(&rc.counters->restarts, restarts);
     if (STATS)
     {
         warpAdd(&rc.counters->boxClosest, tr.st.boxTests);
         warpAdd(&rc.counters->triClosest, tr.st.triTests);
         warpAdd(&rc.counters->alphaClosest, tr.st.alphaTests);
     }
-    if (blockIdx.x == 0 && threadIdx.x == 0)
-        atomicAdd(&rc.counters->raysClosest, (unsigned long long)n);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -348,9 +404,15 @@ template <bool ALPHA, bool STATS> __global__ void __launch_bounds__(128, PT_SHAD
     const uint32_t stride = gridDim.x * blockDim.x;
     const DeviceScene &s = rc.scene;
     uint32_t texels = 0;
+    // the queue positions of k_extend, which has completed (stream order)
+    if (blockIdx.x == 0 && threadIdx.x == 0)
+        rc.qc->extendWork = 0;
+    const uint32_t *hitQueue = rc.sortHits ? rc.ps.hitQSorted : rc.ps.hitQ;
+    // (requesting the next hit's path record into L2 one loop iteration ahead was measured: no gain,
+    // the kernel is bound by issue latency at 16 warps per SM, not by the record's DRAM latency)
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
     {
-        const uint32_t slot = (rc.sortHits ? rc.ps.hitQSorted : rc.ps.hitQ)[i];
+        const uint32_t slot = hitQueue[i];
         const float4 hitv = rc.ps.rec[slot].hit;
         const float4 rayO = rc.ps.rec[slot].rayO, rayD = rc.ps.rec[slot].rayD;
         float4 thr4 = rc.ps.rec[slot].thr;
@@ -511,14 +573,15 @@ template <bool ALPHA, bool STATS> __global__ void __launch_bounds__(128, PT_SHAD
             else
                 throughput = throughput / prob;
         }
-        uint32_t bounce = (state & 0xffu) + 1;
+        const uint32_t bounce = (state & 0xffu) + 1;
         if (bounce >= rc.bounceCount)
             done = true;
-        state = bounce;
+        state = (state & ~0xffu) | bounce;
         // continuing paths go straight to the next iteration's queue (in shading = triangle order, so
-        // the next extend starts from spatially coherent origins); finished ones to k_finish
+        // the next extend starts from spatially coherent origins); ended ones to its regen queue
+        // (their shadow ray, if any, is resolved by k_shadow before that)
         if (done)
-            rc.ps.doneQ[atomicAggInc(&rc.qc->done[cur])] = slot;
+            (cur ? rc.ps.regenQ[0] : rc.ps.regenQ[1])[atomicAggInc(&rc.qc->regen[cur ^ 1])] = slot | kRegen;
         else
             (cur ? rc.ps.contQ[0] : rc.ps.contQ[1])[atomicAggInc(&rc.qc->cont[cur ^ 1])] = slot;
 
@@ -541,9 +604,17 @@ template <bool ALPHA, bool STATS> __global__ void __launch_bounds__(128, PT_SHAD
 // ---------------------------------------------------------------------------------------------
 // shadow
 // ---------------------------------------------------------------------------------------------
-template <bool ALPHA, bool STATS> __global__ void __launch_bounds__(128, PT_TRACE_MIN_BLOCKS) k_shadow(RenderConst rc)
+template <bool ALPHA, bool STATS> __global__ void __launch_bounds__(128, PT_TRACE_MIN_BLOCKS) k_shadow(RenderConst rc, int cur)
 {
     const uint32_t n = rc.qc->shadow;
+    // Counters of the queues the NEXT iteration fills: this iteration's inputs.  Nothing in this
+    // kernel reads them, and everything that did has completed (stream order).
+    if (blockIdx.x == 0 && threadIdx.x == 0)
+    {
+        rc.qc->cont[cur] = 0;
+        rc.qc->regen[cur] = 0;
+        rc.qc->hit = 0;
+    }
     unsigned long long stack[PT_STACK_SIZE];
     Traverser<false, ALPHA, STATS> tr;
     tr.stack = stack;
@@ -581,153 +652,6 @@ template <bool ALPHA, bool STATS> __global__ void __launch_bounds__(128, PT_TRAC
     }
     if (blockIdx.x == 0 && threadIdx.x == 0)
         atomicAdd(&rc.counters->raysShadow, (unsigned long long)n);
-}
-
-// ---------------------------------------------------------------------------------------------
-// finish: raygen.rgen:99-117 for finished paths, then the next work item
-// ---------------------------------------------------------------------------------------------
-// Block-aggregated queue reservation: every thread of the block calls it (uniform control flow)
-// with the number of entries it wants; it gets the first of its consecutive positions, and the
-// whole block costs ONE atomic.  Hot same-address atomics are serialised by the L2 (a few ns
-// each), so per-warp reservations made k_finish atomic-bound.
-template <int WARPS> __device__ __forceinline__ uint32_t blockReserve(uint32_t count, uint32_t *counter, uint32_t *scratch)
-{
-    const unsigned lane = laneId(), warp = threadIdx.x >> 5;
-    uint32_t incl = count;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1)
-    {
-        const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
-        if ((int)lane >= o)
-            incl += t;
-    }
-    if (lane == 31)
-        scratch[warp] = incl;
-    __syncthreads();
-    if (warp == 0)
-    {
-        const uint32_t v = lane < WARPS ? scratch[lane] : 0;
-        uint32_t wIncl = v;
-#pragma unroll
-        for (int o = 1; o < WARPS; o <<= 1)
-        {
-            const uint32_t t = __shfl_up_sync(0xffffffffu, wIncl, o);
-            if ((int)lane >= o)
-                wIncl += t;
-        }
-        const uint32_t total = __shfl_sync(0xffffffffu, wIncl, WARPS - 1);
-        uint32_t base = 0;
-        if (lane == 0 && total)
-            base = atomicAdd(counter, total);
-        base = __shfl_sync(0xffffffffu, base, 0);
-        if (lane < WARPS)
-            scratch[WARPS + lane] = base + wIncl - v;
-    }
-    __syncthreads();
-    return scratch[WARPS + warp] + incl - count;
-}
-
-// Each thread handles PT_FINISH_ITEMS finished paths per block iteration: their loads are in
-// flight together and the two block-wide reservations are amortised over four times the work.
-#define PT_FINISH_ITEMS 4
-
-__global__ void __launch_bounds__(256) k_finish(RenderConst rc, int cur)
-{
-    __shared__ uint32_t scratch[2][16];
-    const uint32_t n = rc.qc->done[cur];
-    // Counters of the queues the NEXT iteration fills.  None of them is read by this kernel, and
-    // everything that read them in this iteration has completed (stream order).
-    if (blockIdx.x == 0 && threadIdx.x == 0)
-    {
-        rc.qc->cont[cur] = 0;
-        rc.qc->fresh[cur] = 0;
-        rc.qc->hit = 0;
-        rc.qc->shadow = 0;
-        rc.qc->extendWork = 0;
-        rc.qc->shadowWork = 0;
-        rc.qc->done[cur ^ 1] = 0;
-    }
-    constexpr uint32_t K = PT_FINISH_ITEMS, TILE = 256 * K;
-    uint32_t samples = 0, restarts = 0;
-    uint32_t *freshOut = cur ? rc.ps.freshQ[0] : rc.ps.freshQ[1];
-    // uniform trip count: every thread of the block takes part in the block-wide reservations
-    for (uint32_t first = blockIdx.x * TILE; first < n; first += gridDim.x * TILE)
-    {
-        uint32_t slot[K], item[K], restartCount[K];
-        float4 r[K];
-        bool valid[K], restart[K], park[K];
-#pragma unroll
-        for (uint32_t k = 0; k < K; k++)
-        {
-            const uint32_t i = first + threadIdx.x * K + k;
-            valid[k] = i < n;
-            slot[k] = valid[k] ? rc.ps.doneQ[i] : 0u;
-        }
-#pragma unroll
-        for (uint32_t k = 0; k < K; k++)
-            if (valid[k])
-            {
-                r[k] = rc.ps.rec[slot[k]].rad;
-                item[k] = rc.ps.rec[slot[k]].item;
-            }
-        uint32_t parks = 0;
-#pragma unroll
-        for (uint32_t k = 0; k < K; k++)
-        {
-            restart[k] = park[k] = false;
-            if (valid[k])
-            {
-                restartCount[k] = __float_as_uint(r[k].w);
-                samples++;
-                const bool isBad = bad(r[k].x) || bad(r[k].y) || bad(r[k].z);
-                // radiance = 0; smpl = -1: the sample is redone with the ADVANCED rng state
-                restart[k] = isBad && restartCount[k] < kMaxRestarts;
-                park[k] = !restart[k];
-                // park the sample; k_resolve adds the round's samples to the image in sample order
-                if (park[k])
-                {
-                    rc.sbuf[item[k]] = isBad ? make_float4(0.0f, 0.0f, 0.0f, 0.0f) : r[k];
-                    parks++;
-                }
-            }
-        }
-        // pull the next work items: the paths of a block that finish together take consecutive
-        // items (= neighbouring pixels, 8x4 blocks) and consecutive positions of the fresh queue
-        uint32_t next = blockReserve<8>(parks, rc.nextItem, scratch[0]);
-        uint32_t fresh = 0;
-        bool regenerate[K];
-#pragma unroll
-        for (uint32_t k = 0; k < K; k++)
-        {
-            regenerate[k] = false;
-            if (park[k])
-            {
-                regenerate[k] = next < rc.itemCount;
-                item[k] = next++;
-            }
-            fresh += (restart[k] || regenerate[k]) ? 1u : 0u;
-        }
-        uint32_t pos = blockReserve<8>(fresh, &rc.qc->fresh[cur ^ 1], scratch[1]);
-#pragma unroll
-        for (uint32_t k = 0; k < K; k++)
-        {
-            if (restart[k])
-            {
-                restarts++;
-                const uint32_t s = item[k] / rc.pixelCount, pi = item[k] - s * rc.pixelCount;
-                generatePath(rc, slot[k], __ldg(rc.pixelList + pi), __float_as_uint(rc.ps.rec[slot[k]].rayD.w),
-                             restartCount[k] + 1);
-                freshOut[pos++] = slot[k];
-            }
-            else if (regenerate[k])
-            {
-                startItem(rc, slot[k], item[k]);
-                freshOut[pos++] = slot[k];
-            }
-        }
-    }
-    warpAdd(&rc.counters->samples, samples);
-    warpAdd(&rc.counters->restarts, restarts);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1001,7 +925,7 @@ pt_status renderSamples(Context *ctx, const pt_render_params *params, uint32_t f
             cudaStream_t stream;
             QueueCounts *hq;
             void *sortTemp;
-            uint32_t gridExtend, gridShadow, gridShade, gridWide, gridFinish;
+            uint32_t gridExtend, gridShadow, gridShade, gridWide;
             int cur;
             bool active;
         };
@@ -1017,8 +941,8 @@ pt_status renderSamples(Context *ctx, const pt_render_params *params, uint32_t f
             pl.rc.ps = ctx->ps;
             // queues are private to the pool: its sub-range of the queue arrays
             pl.rc.ps.contQ[0] += first, pl.rc.ps.contQ[1] += first;
-            pl.rc.ps.freshQ[0] += first, pl.rc.ps.freshQ[1] += first;
-            pl.rc.ps.doneQ += first, pl.rc.ps.hitQ += first, pl.rc.ps.hitKey += first;
+            pl.rc.ps.regenQ[0] += first, pl.rc.ps.regenQ[1] += first;
+            pl.rc.ps.hitQ += first, pl.rc.ps.hitKey += first;
             pl.rc.ps.hitQSorted += first, pl.rc.ps.hitKeySorted += first, pl.rc.ps.shadowQueue += first;
             pl.rc.qc = ctx->dQueueCounts + p;
             pl.rc.slotBase = first;
@@ -1049,7 +973,6 @@ pt_status renderSamples(Context *ctx, const pt_render_params *params, uint32_t f
             else
                 pl.gridExtend = residentGrid(k_extend<false, false>), pl.gridShadow = residentGrid(k_shadow<false, false>);
             pl.gridWide = std::min((slots + 255) / 256, (uint32_t)ctx->smCount * 8);
-            pl.gridFinish = std::min((slots + 256 * PT_FINISH_ITEMS - 1) / (256 * PT_FINISH_ITEMS), (uint32_t)ctx->smCount * 8);
             if (pl.stream != ctx->stream)
                 PT_CUDA_CHECK(ctx, cudaStreamWaitEvent(pl.stream, ctx->evRound, 0));
             k_init<<<pl.gridWide, 256, 0, pl.stream>>>(pl.rc);
@@ -1089,13 +1012,10 @@ pt_status renderSamples(Context *ctx, const pt_render_params *params, uint32_t f
             PT_DISPATCH(k_shade, pl.gridShade, 128, rc, cur);
             end(st);
             begin(PT_KERNEL_SHADOW, st);
-            PT_DISPATCH(k_shadow, pl.gridShadow, 128, rc);
-            end(st);
-            begin(PT_KERNEL_FINISH, st);
-            k_finish<<<pl.gridFinish, 256, 0, st>>>(rc, cur);
+            PT_DISPATCH(k_shadow, pl.gridShadow, 128, rc, cur);
             end(st);
 #undef PT_DISPATCH
-            ctx->stats.kernel_launches += 4;
+            ctx->stats.kernel_launches += 3;
             pl.cur ^= 1;
             return PT_OK;
         };
@@ -1127,7 +1047,7 @@ pt_status renderSamples(Context *ctx, const pt_render_params *params, uint32_t f
                         PT_CUDA_CHECK(ctx, cudaMemcpyAsync(ctx->hNextItem, ctx->dNextItem, 4, cudaMemcpyDeviceToHost, pl.stream));
                     first = false;
                     PT_CUDA_CHECK(ctx, cudaStreamSynchronize(pl.stream));
-                    if (pl.hq->cont[pl.cur] + pl.hq->fresh[pl.cur] == 0)
+                    if (pl.hq->cont[pl.cur] + pl.hq->regen[pl.cur] == 0)
                     {
                         pl.active = false;
                         live--;

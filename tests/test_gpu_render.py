@@ -35,6 +35,25 @@ def test_default_scene_config0(default_renderer, default_oracle, default_scene):
     assert abs(st["hits"] - cnt["hits"]) <= 1e-4 * cnt["hits"]
 
 
+def test_large_frame_grid_stride_loops(default_renderer, default_oracle, default_scene):
+    """A frame with more hits per wavefront iteration than resident threads: the grid-stride loop of
+    k_shade (with its software-pipelined record prefetch) and every persistent warp of the traversal
+    kernels run several times.  (Smaller frames fit one pass and would not notice a broken loop.)"""
+    p = default_scene.default_params(bounce_count=8)
+    r = default_renderer
+    W, H, spp = 1536, 1024, 2
+    r.on_resize(W, H)
+    r.render(spp, params=p)
+    img = r.read_accumulation()
+    st = r.stats()
+    ref, cnt = default_oracle.render(p, W, H, 0, spp)
+    assert np.isfinite(img).all()
+    assert metrics.close_fraction(img, ref, 1e-4) > 0.995
+    assert st["samples"] == cnt["samples"] == W * H * spp
+    assert abs(st["rays_closest"] - cnt["rays_closest"]) <= 1e-4 * cnt["rays_closest"]
+    assert abs(st["hits"] - cnt["hits"]) <= 1e-4 * cnt["hits"]
+
+
 def test_incremental_equals_batch_and_is_deterministic(default_renderer, default_scene):
     """16 frames of 1 sample == one call of 16 samples; reruns are bit-identical."""
     p = default_scene.default_params()
