@@ -572,3 +572,268 @@ def chess_scene(width: int = 1920, height: int = 1080, segments: int = 192, ring
     eye = np.array([5.6, 4.2, -7.4])
     cam = camera_matrices(eye, np.array([0.2, 0.3, 0.2]) - eye, width, height, fov_deg=38)
     return b.build(cam, (width, height))
+
+
+# ---------------------------------------------------------------------------------------------
+# configs[2..4] stand-ins: every count below is declared by the builder
+# ---------------------------------------------------------------------------------------------
+def tube(center, radius, n_u: int, n_v: int, uv_scale=(1.0, 1.0)):
+    """Closed tube (torus topology) around the closed curve center(t), t in [0, 2 pi), with
+    radius(t, phi); seam vertices are duplicated so UVs run 0..uv_scale.  2 * n_u * n_v triangles."""
+    t = np.linspace(0, 2 * np.pi, n_u + 1)
+    phi = np.linspace(0, 2 * np.pi, n_v + 1)
+    c = center(t)  # (n_u + 1, 3)
+    e = 1e-4
+    tangent = center(t + e) - center(t - e)
+    tangent /= np.linalg.norm(tangent, axis=1, keepdims=True)
+    # frame from the curve's distance to the y axis: continuous and periodic for the knots used here
+    radial = c * np.array([1.0, 0.0, 1.0])
+    radial /= np.maximum(np.linalg.norm(radial, axis=1, keepdims=True), 1e-9)
+    side = np.cross(tangent, radial)
+    side /= np.linalg.norm(side, axis=1, keepdims=True)
+    up = np.cross(side, tangent)
+    T, P = np.meshgrid(t, phi, indexing="ij")
+    r = radius(T, P)
+
+    def surface(rr):
+        return c[:, None, :] + rr[..., None] * (np.cos(P)[..., None] * up[:, None, :] + np.sin(P)[..., None] * side[:, None, :])
+
+    pos = surface(r)
+    # normals from central differences of the parametric surface (radius varies along both directions)
+    du = np.roll(pos[:-1], -1, 0) - np.roll(pos[:-1], 1, 0)
+    du = np.concatenate([du, du[:1]], 0)
+    dv = np.roll(pos[:, :-1], -1, 1) - np.roll(pos[:, :-1], 1, 1)
+    dv = np.concatenate([dv, dv[:, :1]], 1)
+    nrm = np.cross(dv, du)
+    nrm /= np.maximum(np.linalg.norm(nrm, axis=-1, keepdims=True), 1e-12)
+    tan = du / np.maximum(np.linalg.norm(du, axis=-1, keepdims=True), 1e-12)
+    bit = np.cross(nrm, tan)
+    uv = np.stack([T / (2 * np.pi) * uv_scale[0], P / (2 * np.pi) * uv_scale[1]], -1)
+    i = (np.arange(n_u)[:, None] * (n_v + 1) + np.arange(n_v)[None, :]).reshape(-1)
+    idx = np.stack([i, i + n_v + 1, i + n_v + 2, i + n_v + 2, i + 1, i], -1).reshape(-1)
+    flat = lambda a: a.reshape(-1, a.shape[-1])
+    return _vertices(flat(pos), flat(uv), flat(nrm), flat(tan), flat(bit)), idx.astype(np.uint32)
+
+
+def torus_knot(p: int, q: int, big: float, small: float):
+    def center(t):
+        r = big + small * np.cos(q * t)
+        return np.stack([r * np.cos(p * t), small * np.sin(q * t), r * np.sin(p * t)], -1)
+
+    return center
+
+
+def dragon_scene(width: int = 1920, height: int = 1080, n_u: int = 4096, n_v: int = 64, cloth_tess: int = 256,
+                 texture_size: int = 1024, seed: int = 0xD2A60) -> sc.SceneData:
+    """BASELINE.json configs[2] stand-in ("DragonAttenuation-class"): one closed smooth transmissive
+    body — a (2,3) torus-knot tube with a scaly radius modulation, 2 * n_u * n_v triangles
+    (defaults: 524,288) — with Transmission 1, Ior 1.5, Roughness 0.02 and volume attenuation
+    (AttenuationColor (0.92, 0.55, 0.15), AttenuationDistance 0.35 = the tube's thickness scale), on a
+    displaced, textured cloth backdrop (2 * cloth_tess^2 triangles) and a floor quad; directional
+    sun + 2 point lights, constant sky.  Stresses the BTDF lobe, Beer-Lambert attenuation
+    (closestHit.rchit:123-128) and the TIR NaN restarts."""
+    rs = np.random.default_rng(seed)
+    b = SceneBuilder()
+    n = texture_size
+    weave = value_noise(rs, n, 6, 8)
+    stripes = 0.5 + 0.5 * np.sin(np.arange(n)[None, :] / n * 2 * np.pi * 24)
+    t_cloth = b.add_texture(rgba8(0.55 + 0.25 * stripes * weave, 0.12 + 0.1 * weave, 0.10 + 0.1 * weave), srgb=True)
+    t_cloth_n = b.add_texture(normal_map_from_height(weave + 0.2 * stripes, 5.0), srgb=False)
+    t_cloth_orm = b.add_texture(rgba8(np.ones_like(weave), 0.6 + 0.4 * weave, np.zeros_like(weave)), srgb=False)
+
+    m_body = b.add_material_mr(color=(1.0, 1.0, 1.0, 1), roughness=0.02, transmission=1.0, ior=1.5,
+                               attenuation_color=(0.92, 0.55, 0.15), attenuation_distance=0.35)
+    m_cloth = b.add_material_mr(roughness=0.9, color_idx=t_cloth, normal_idx=t_cloth_n, roughness_idx=t_cloth_orm)
+    m_floor = b.add_material_mr(color=(0.7, 0.7, 0.72, 1), roughness=0.6)
+
+    scales = lambda T, P: 0.30 * (1.0 + 0.06 * np.cos(64 * T) * np.cos(8 * P) + 0.15 * np.sin(3 * T))
+    g_body = b.add_geometry(*tube(torus_knot(2, 3, 1.6, 0.7), scales, n_u, n_v, uv_scale=(32.0, 2.0)))
+    g_cloth = b.add_geometry(*grid(cloth_tess, cloth_tess, 14, 14, uv_scale=4.0,
+                                   height=lambda x, z: 0.12 * np.sin(1.7 * x + 0.6 * np.sin(z)) * np.cos(1.1 * z)))
+    g_floor = b.add_geometry(*quad(80, 80, uv_scale=16))
+    b.add_instance(b.add_model([(g_body, m_body, None)]), translate(0, 1.45, 0) @ rotate_x(18))
+    b.add_instance(b.add_model([(g_cloth, m_cloth, None)]), translate(0, 0.0, 0))
+    b.add_instance(b.add_model([(g_cloth, m_cloth, None)]), translate(0, 5.0, 6.5) @ rotate_x(-78))
+    b.add_instance(b.add_model([(g_floor, m_floor, None)]), translate(0, -0.2, 0))
+    b.set_directional_light((4.0, 3.8, 3.4), (-0.35, -1.0, 0.45))
+    b.add_light((12.0, 10.0, 8.0), (-4.0, 4.5, -3.0), 1.0, 0.05, 0.1)
+    b.add_light((5.0, 7.0, 12.0), (4.5, 2.0, -4.0), 1.0, 0.05, 0.15)
+    eye = np.array([0.5, 3.4, -7.2])
+    cam = camera_matrices(eye, np.array([0.0, 1.3, 0.0]) - eye, width, height, fov_deg=40)
+    return b.build(cam, (width, height))
+
+
+def _leaf_texture(rs, n):
+    """RGBA8 colour texture with (mostly) binary alpha from thresholded noise, coverage ~ 50 %; RGB is
+    zeroed where alpha == 0 like the reference's importer does (TextureImporter.cpp:24-51)."""
+    noise = value_noise(rs, n, 5, 8)
+    alpha = np.clip((noise - np.median(noise)) * 24 + 0.5, 0, 1)
+    tex = rgba8(0.10 + 0.25 * noise, 0.35 + 0.5 * noise, 0.08 + 0.1 * noise, alpha)
+    tex[tex[..., 3] == 0, :3] = 0
+    return tex
+
+
+def atrium_scene(width: int = 3840, height: int = 2160, bays: int = 12, column_segments: int = 256, column_rings: int = 512,
+                 floor_tess: int = 1024, cards_per_branch: int = 512, branches: int = 12288, texture_size: int = 1024,
+                 seed: int = 0x5B0A2A) -> sc.SceneData:
+    """BASELINE.json configs[3] stand-in ("Sponza-scale"): a two-aisle atrium of `bays` bays — fluted
+    columns turned on a lathe (2 * column_segments * (column_rings - 1) triangles each, 4 rows),
+    lintel boxes, a displaced floor and a vault (2 * floor_tess^2 triangles each) — all opaque, plus
+    ALPHA-TESTED foliage: `branches` instances of a branch model holding `cards_per_branch` randomly
+    oriented leaf cards (2 triangles each, IsOpaque = false, RGBA colour texture with ~50 % coverage)
+    hanging as curtains between the columns.  Defaults:
+        columns  4 * 12 * 2 * 256 * 511      = 12,558,336   (instanced, flattened by the core)
+        floor + vault 2 * 2 * 1024^2         =  4,194,304
+        lintels                              =        576
+        foliage  12,288 * 512 * 2            = 12,582,912   (43 % of all triangles)
+        total                                = 29,336,128 instanced triangles
+    directional sun + constant sky + 6 point lights.  Stresses the any-hit stages (a4/a5)."""
+    rs = np.random.default_rng(seed)
+    b = SceneBuilder()
+    n = texture_size
+    stone = value_noise(rs, n, 7, 4)
+    t_stone = b.add_texture(rgba8(0.62 + 0.25 * stone, 0.58 + 0.25 * stone, 0.50 + 0.25 * stone), srgb=True)
+    t_stone_n = b.add_texture(normal_map_from_height(stone, 5.0), srgb=False)
+    t_stone_orm = b.add_texture(rgba8(np.ones_like(stone), 0.55 + 0.4 * stone, np.zeros_like(stone)), srgb=False)
+    t_leaf = b.add_texture(_leaf_texture(rs, n), srgb=True)
+    tiles = ((np.indices((n, n)) // (n // 16)).sum(0) % 2).astype(F)
+    t_floor = b.add_texture(rgba8(0.35 + 0.4 * tiles, 0.33 + 0.38 * tiles, 0.30 + 0.35 * tiles), srgb=True)
+
+    m_stone = b.add_material_mr(roughness=0.9, color_idx=t_stone, normal_idx=t_stone_n, roughness_idx=t_stone_orm)
+    m_floor = b.add_material_mr(roughness=0.35, color_idx=t_floor)
+    m_leaf = b.add_material_mr(roughness=0.7, color_idx=t_leaf)
+    m_curtain = b.add_material_mr(color=(0.9, 0.3, 0.25, 1), roughness=0.8, color_idx=t_leaf)
+
+    # fluted column: radius modulated around the axis is not a lathe, so flutes go into the profile's
+    # radius as fine rings (entasis + rings); base and capital included
+    y = np.linspace(0, 1, column_rings)
+    radius = 0.42 * (1 - 0.12 * y ** 2) * (1 + 0.015 * np.sin(y * 2 * np.pi * 40))
+    radius[: column_rings // 24] *= 1.45
+    radius[-column_rings // 24:] *= 1.5
+    profile = np.stack([radius, y * 6.0], -1)
+    g_column = b.add_geometry(*lathe(profile, column_segments, uv_scale=(3.0, 6.0)))
+    g_box = b.add_geometry(*box(1, 1, 1))
+    length = bays * 4.0
+    g_floor = b.add_geometry(*grid(floor_tess, floor_tess, 16.0, length + 4, uv_scale=8.0,
+                                   height=lambda x, z: 0.01 * np.sin(9 * x) * np.sin(9 * z)))
+    g_vault = b.add_geometry(*grid(floor_tess, floor_tess, 16.0, length + 4, uv_scale=6.0,
+                                   height=lambda x, z: -1.2 * np.cos(x * np.pi / 8) ** 2 - 0.05 * np.sin(3 * z)))
+    # branch: cards scattered in a flat slab (a hanging curtain of leaves), random orientation
+    cards_v, cards_i = [], []
+    qv, qi = quad(0.22, 0.22)
+    for k in range(cards_per_branch):
+        m = (translate(*(rs.uniform(-0.5, 0.5, 3) * np.array([1.0, 1.0, 0.25]))) @ rotate_y(rs.uniform(0, 360)) @
+             rotate_x(rs.uniform(40, 140)))
+        v = qv.copy()
+        p = np.concatenate([qv["position"], np.ones((4, 1), F)], 1) @ m.T
+        v["position"] = p[:, :3]
+        for f in ("normal", "tangent", "bitangent"):
+            v[f] = qv[f] @ m[:3, :3].T
+        cards_v.append(v)
+        cards_i.append(qi + 4 * k)
+    g_branch = b.add_geometry(np.concatenate(cards_v), np.concatenate(cards_i), is_opaque=False)
+
+    column = b.add_model([(g_column, m_stone, None)])
+    lintel = b.add_model([(g_box, m_stone, None)])
+    branch = [b.add_model([(g_branch, m_leaf, None)]), b.add_model([(g_branch, m_curtain, None)])]
+    rows = (-6.0, -2.5, 2.5, 6.0)
+    for bay in range(bays):
+        z = (bay + 0.5) * 4.0 - length / 2
+        for x in rows:
+            b.add_instance(column, translate(x, 0, z))
+    for x in rows:
+        b.add_instance(lintel, translate(x, 6.25, 0) @ scale(1.2, 0.5, length))
+    b.add_instance(b.add_model([(g_floor, m_floor, None)]))
+    b.add_instance(b.add_model([(g_vault, m_stone, None)]), translate(0, 8.6, 0) @ rotate_x(180))
+    # foliage curtains between neighbouring columns of every row, stacked vertically
+    per_gap = max(1, branches // (len(rows) * bays))
+    placed = 0
+    for bay in range(bays):
+        z = bay * 4.0 - length / 2 + 2.0
+        for x in rows:
+            for k in range(per_gap):
+                if placed >= branches:
+                    break
+                s = rs.uniform(0.8, 1.2)
+                b.add_instance(branch[placed & 1], translate(x + rs.uniform(-0.3, 0.3), rs.uniform(0.6, 5.8), z + 2.0 + rs.uniform(-1.4, 1.4)) @
+                               rotate_y(rs.uniform(-20, 20) + 90) @ scale(s * 2.4, s * 1.6, s))
+                placed += 1
+    b.set_directional_light((5.0, 4.6, 4.0), (-0.5, -1.0, 0.25))
+    for k in range(6):
+        b.add_light((8.0, 6.5, 4.5), (0.0, 5.0, (k + 0.5) / 6 * length - length / 2), 1.0, 0.05, 0.12)
+    eye = np.array([0.6, 2.0, -length / 2 + 1.0])
+    cam = camera_matrices(eye, np.array([-0.4, 2.6, 0.0]) - eye, width, height, fov_deg=60)
+    return b.build(cam, (width, height))
+
+
+def street_scene(width: int = 3840, height: int = 2160, blocks: int = 24, facade_tess: int = 192, road_tess: int = 768,
+                 lamps: int = 4096, lamp_segments: int = 32, texture_size: int = 1024, seed: int = 0xB157E0) -> sc.SceneData:
+    """BASELINE.json configs[4] stand-in ("Bistro-scale"): a street of 2 * blocks displaced, textured
+    facades (2 * facade_tess^2 triangles each), a displaced road, and `lamps` small emissive lamps
+    (an emissive quad under a lathe-turned shade) strung along the street, plus the reference's
+    maximum of 64 point lights and a dim directional light.  Reference semantics: emissive triangles
+    are found by BSDF sampling only; NEE runs over the 65 analytic lights.  Defaults:
+        facades 48 * 2 * 192^2 = 3,538,944; road 2 * 768^2 = 1,179,648;
+        lamps 4096 * (2 + 2 * 32 * 15) = 3,940,352; total 8,658,944 instanced triangles."""
+    rs = np.random.default_rng(seed)
+    b = SceneBuilder()
+    n = texture_size
+    brick_noise = value_noise(rs, n, 6, 8)
+    rows = (np.arange(n)[:, None] // (n // 32))
+    bricks = (((np.arange(n)[None, :] + (rows % 2) * (n // 32)) // (n // 16)) + rows) % 3 / 2.0
+    mortar = ((np.arange(n)[:, None] % (n // 32)) < 2) | (((np.arange(n)[None, :] + (rows % 2) * (n // 32)) % (n // 16)) < 2)
+    shade_ = np.where(mortar, 0.75, 0.35 + 0.3 * bricks) * (0.8 + 0.2 * brick_noise)
+    t_brick = b.add_texture(rgba8(shade_ * 1.1, shade_ * 0.62, shade_ * 0.5), srgb=True)
+    t_brick_n = b.add_texture(normal_map_from_height(np.where(mortar, 0.0, 1.0) * 0.5 + brick_noise * 0.5, 5.0), srgb=False)
+    windows = (((np.arange(n)[:, None] // (n // 8)) % 2 == 1) & ((np.arange(n)[None, :] // (n // 8)) % 2 == 1)).astype(F)
+    glow = windows * (value_noise(rs, n, 3, 8) > 0.5)
+    t_window_e = b.add_texture(rgba8(glow, 0.8 * glow, 0.45 * glow), srgb=True)
+    asphalt = value_noise(rs, n, 7, 16)
+    t_road = b.add_texture(rgba8(0.18 + 0.1 * asphalt, 0.18 + 0.1 * asphalt, 0.19 + 0.1 * asphalt), srgb=True)
+    t_road_orm = b.add_texture(rgba8(np.ones_like(asphalt), 0.3 + 0.6 * asphalt, np.zeros_like(asphalt)), srgb=False)
+
+    m_facade = b.add_material_mr(roughness=0.85, color_idx=t_brick, normal_idx=t_brick_n, emissive=(0, 0, 0),
+                                 emissive_intensity=2.5, emissive_idx=t_window_e)
+    m_road = b.add_material_mr(roughness=1.0, color_idx=t_road, roughness_idx=t_road_orm)
+    m_shade = b.add_material_mr(color=(0.2, 0.2, 0.22, 1), roughness=0.4, metalness=1.0)
+    lamp_colors = [(1.0, 0.85, 0.6), (1.0, 0.6, 0.3), (0.7, 0.85, 1.0), (1.0, 0.3, 0.3), (0.4, 1.0, 0.5)]
+    m_bulbs = [b.add_material_mr(color=(1, 1, 1, 1), emissive=c, emissive_intensity=40.0) for c in lamp_colors]
+
+    length = blocks * 6.0
+    g_facade = b.add_geometry(*grid(facade_tess, facade_tess, 6.0, 9.0, uv_scale=2.0,
+                                    height=lambda x, z: 0.04 * np.sin(7 * x) * np.sin(5 * z) + 0.1 * (np.abs(np.sin(2.1 * x)) > 0.93)))
+    g_road = b.add_geometry(*grid(road_tess, road_tess, 12.0, length, uv_scale=12.0,
+                                  height=lambda x, z: 0.015 * np.sin(5 * x) * np.sin(3 * z) - 0.03 * (x / 6) ** 2))
+    g_bulb = b.add_geometry(*quad(0.12, 0.12))
+    shade_profile = _refine_profile([(0.02, 0.0), (0.03, 0.05), (0.10, 0.08), (0.14, 0.16), (0.15, 0.18)], 16)
+    g_shade = b.add_geometry(*lathe(shade_profile, lamp_segments))
+
+    facade = b.add_model([(g_facade, m_facade, None)])
+    b.add_instance(b.add_model([(g_road, m_road, None)]))
+    for k in range(blocks):
+        z = (k + 0.5) * 6.0 - length / 2
+        b.add_instance(facade, translate(-6.0, 4.5, z) @ rotate_y(90) @ rotate_x(-90))   # facing +x
+        b.add_instance(facade, translate(6.0, 4.5, z) @ rotate_y(-90) @ rotate_x(-90))   # facing -x
+    lamp_models = [b.add_model([(g_bulb, m, translate(0, 0.17, 0) @ rotate_x(180)), (g_shade, m_shade, rotate_x(180) @ translate(0, -0.36, 0))])
+                   for m in m_bulbs]
+    for k in range(lamps):
+        z = rs.uniform(-length / 2, length / 2)
+        x = rs.uniform(-5.5, 5.5)
+        ysag = 4.2 + 0.8 * (x / 5.5) ** 2 + rs.uniform(-0.1, 0.1)
+        b.add_instance(lamp_models[k % len(lamp_models)], translate(x, ysag, z))
+    for k in range(64):
+        z = (k + 0.5) / 64 * length - length / 2
+        b.add_light(tuple(4.0 * np.array(lamp_colors[k % 5])), ((-4.5, 4.5)[k & 1], 3.5, z), 1.0, 0.1, 0.25)
+    b.set_directional_light((0.15, 0.17, 0.25), (-0.3, -1.0, 0.2))
+    eye = np.array([1.2, 1.7, -length / 2 + 2.0])
+    cam = camera_matrices(eye, np.array([-0.5, 2.4, 0.0]) - eye, width, height, fov_deg=62)
+    return b.build(cam, (width, height))
+
+
+WORKLOADS = {
+    # name: (builder, BASELINE.json config index, default width, height, spp, depth)
+    "chess": (chess_scene, 1, 1920, 1080, 256, 8),
+    "dragon": (dragon_scene, 2, 1920, 1080, 1024, 16),
+    "atrium": (atrium_scene, 3, 3840, 2160, 256, 8),
+    "street": (street_scene, 4, 3840, 2160, 1024, 8),
+}
