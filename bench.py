@@ -47,23 +47,42 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--spp", type=int, default=256, help="samples per pixel of one step (configs[1]: 256)")
-    ap.add_argument("--width", type=int, default=1920)
-    ap.add_argument("--height", type=int, default=1080)
-    ap.add_argument("--bounces", type=int, default=8)
+    ap.add_argument("--workload", default="chess", choices=["chess", "dragon", "atrium", "street"],
+                    help="chess = BASELINE.json configs[1] (the default and the headline); dragon / atrium / street = "
+                         "configs[2..4] stand-ins (extra lines, not the headline)")
+    ap.add_argument("--spp", type=int, default=None, help="samples per pixel of one step (default: the config's, chess 256)")
+    ap.add_argument("--width", type=int, default=None)
+    ap.add_argument("--height", type=int, default=None)
+    ap.add_argument("--bounces", type=int, default=None)
     ap.add_argument("--partition", default="samples", choices=["tiles", "samples"],
                     help="samples (default, weak scaling): rank g renders samples [g*spp, (g+1)*spp) of the whole frame; "
                          "tiles (strong scaling): the frame's row blocks are dealt to the ranks, spp is the total")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--small", action="store_true", help="reduced tessellation (debugging only; reported in config)")
-    return ap.parse_args()
+    args = ap.parse_args()
+    scenes = importlib.import_module("path-tracing_b200.scenes")
+    _, _, w, h, spp, depth = scenes.WORKLOADS[args.workload]
+    args.width, args.height = args.width or w, args.height or h
+    args.spp, args.bounces = args.spp or spp, args.bounces or depth
+    return args
+
+
+WORKLOAD_LABEL = {
+    "chess": "ABeautifulGame-class procedural stand-in",
+    "dragon": "DragonAttenuation-class procedural stand-in (transmission + volume attenuation)",
+    "atrium": "Sponza-scale procedural stand-in (alpha-tested foliage)",
+    "street": "Bistro-scale procedural stand-in (emissive lamps, 64 point lights)",
+}
 
 
 def build_scene(args):
     scenes = importlib.import_module("path-tracing_b200.scenes")
     if args.small:
-        return scenes.chess_scene(args.width, args.height, segments=48, rings=40, board_tess=32, texture_size=256), "chess_scene(small)"
-    return scenes.chess_scene(args.width, args.height), "chess_scene"
+        assert args.workload == "chess"
+        return (scenes.chess_scene(args.width, args.height, segments=48, rings=40, board_tess=32, texture_size=256),
+                "chess_scene(small): " + WORKLOAD_LABEL["chess"])
+    builder = scenes.WORKLOADS[args.workload][0]
+    return builder(args.width, args.height), f"{builder.__name__}: {WORKLOAD_LABEL[args.workload]}"
 
 
 class ClockSampler:
@@ -169,7 +188,7 @@ def cpu_baseline(scene, params, args, threads=None, tile=(0, 0, 1 << 30, 1 << 30
     o = oracle.OracleScene(scene)
     build_s = time.perf_counter() - t0
     x0, y0, x1, y1 = (min(tile[0], args.width), min(tile[1], args.height), min(tile[2], args.width), min(tile[3], args.height))
-    spp = max(1, min(spp, args.spp))
+    spp = max(1, min(int(round(spp * (1920 * 1080) / (args.width * args.height))), args.spp))
     tiles = np.array([(x0, y0, x1, y1)], importlib.import_module("path-tracing_b200.scene").TILE)
     t0 = time.perf_counter()
     _, cnt = o.render(params, args.width, args.height, 0, spp, tiles=tiles, threads=threads)
@@ -226,7 +245,7 @@ def run_reference(args):
         "vs_baseline": None,
         "dtype": "f32",
         "data": "synthetic",
-        "config": {"workload": f"{scene_name}: ABeautifulGame-class procedural stand-in, {args.width}x{args.height}, depth {args.bounces}; "
+        "config": {"workload": f"{scene_name}, {args.width}x{args.height}, depth {args.bounces}; "
                                f"each step = {step_spp} spp of the whole frame on the host CPU (bounded sample of the {args.spp}-spp step)",
                    "triangles": scene.instanced_triangle_count()},
         "cpu_baseline": {"value": value, "unit": "Mrays/s", "cores": threads, "kind": "port", "sample": base["sample"]},
@@ -391,7 +410,7 @@ def run_ours(args):
         "dtype": "f32",
         "data": "synthetic",
         "config": {
-            "workload": f"{scene_name}: ABeautifulGame-class procedural stand-in, {W}x{H}, "
+            "workload": f"{scene_name}, {W}x{H}, "
                         + (f"{spp} spp per GPU per step ({spp * world} spp per frame)" if args.partition == "samples" else f"{spp} spp per step")
                         + f", depth {args.bounces}",
             "triangles": int(build_stats["triangle_count"]),
@@ -400,8 +419,8 @@ def run_ours(args):
             "materials": int(len(scene.mr_materials)),
             "textures": len(scene.textures),
             "partition": "none" if world == 1 else args.partition,
-            "l2": "working set (path state of 8 M paths in flight 2 GB + sample buffer 8 GB + triangles/BVH 0.44 GB + textures) "
-                  "exceeds the 126 MB L2 many times over; no explicit flush",
+            "l2": f"working set (path state of 8 M paths in flight 2 GB + sample buffer up to 8 GB + triangles/BVH "
+                  f"{build_stats['bvh_bytes'] / 1e9:.2f} GB + textures) exceeds the 126 MB L2 many times over; no explicit flush",
             "scheduling": "8 M path slots in 8 wavefront pools on 8 CUDA streams, hits shaded in triangle order",
             "bvh_build_ms": build_stats["bvh_build_ms"],
             "scene_upload_ms": build_stats["scene_upload_ms"],

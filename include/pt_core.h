@@ -187,7 +187,7 @@ typedef struct pt_texture_desc {
 enum {
     PT_MISS_FLAGS_NONE = 0x0,      /* PT/Shaders/ShaderRendererTypes.incl:92-95 */
     PT_MISS_FLAGS_SKYBOX_2D = 0x1,
-    PT_MISS_FLAGS_SKYBOX_CUBE = 0x2 /* not implemented in this round: PT_ERR_UNSUPPORTED */
+    PT_MISS_FLAGS_SKYBOX_CUBE = 0x2
 };
 enum {
     PT_HIT_FLAGS_NONE = 0x0,       /* PT/Shaders/ShaderRendererTypes.incl:97-99 */
@@ -223,6 +223,11 @@ typedef struct pt_scene_desc {
     uint32_t point_light_count; /* <= PT_MAX_LIGHT_COUNT */
     pt_directional_light directional_light;
     const pt_texture_desc *skybox_2d; /* equirect sky for PT_MISS_FLAGS_SKYBOX_2D, or NULL */
+    /* Six equally sized faces for PT_MISS_FLAGS_SKYBOX_CUBE, or NULL, in the order
+     * TextureUploader::UploadSkyboxBlocking fills the cube image's layers
+     * (PT/Renderer/TextureUploader.cpp:232-236): Front, Back, Up, Down, Left, Right
+     * = Vulkan cube faces +X, -X, +Y, -Y, +Z, -Z. */
+    const pt_texture_desc *skybox_cube;
 } pt_scene_desc;
 
 /* Shaders::RaygenUniformData (PT/Shaders/ShaderRendererTypes.incl:26-34) plus the two

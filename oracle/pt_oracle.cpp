@@ -894,6 +894,8 @@ struct pto_scene
     pt_directional_light directional;
     bool hasSky2D = false;
     Texture sky2D;
+    bool hasSkyCube = false;
+    Texture skyCube[6]; /* Vulkan layer order +X, -X, +Y, -Y, +Z, -Z */
 
     std::vector<FlatTri> tris;      /* flattening order: instance, mesh-in-model, primitive */
     std::vector<uint32_t> triOrder; /* BVH leaf order -> index into tris */
@@ -1607,6 +1609,55 @@ struct Payload
     vec4 RayDifferentials0, RayDifferentials1, RayDifferentials2;
 };
 
+/* texture(samplerCube, dir) outside a fragment stage (miss.rmiss:31): level 0, linear filter.
+ * Face selection and (s, t) follow the Vulkan specification ("Cube Map Face Selection": the major
+ * axis is the largest |component|, z winning ties over y over x; table of sc / tc per face).
+ * PARITY UNPINNED (sampler hardware): the bilinear footprint is clamped to the face here, the
+ * hardware filters seamlessly across face edges — a sub-texel difference along the 12 seams. */
+vec4 sampleCube(const Texture faces[6], vec3 r)
+{
+    const float ax = std::fabs(r.x), ay = std::fabs(r.y), az = std::fabs(r.z);
+    int face;
+    float sc, tc, ma;
+    if (az >= ax && az >= ay)
+    {
+        face = r.z < 0.0f ? 5 : 4;
+        sc = r.z < 0.0f ? -r.x : r.x;
+        tc = -r.y;
+        ma = az;
+    }
+    else if (ay >= ax)
+    {
+        face = r.y < 0.0f ? 3 : 2;
+        sc = r.x;
+        tc = r.y < 0.0f ? -r.z : r.z;
+        ma = ay;
+    }
+    else
+    {
+        face = r.x < 0.0f ? 1 : 0;
+        sc = r.x < 0.0f ? r.z : -r.z;
+        tc = -r.y;
+        ma = ax;
+    }
+    const Texture &t = faces[face];
+    const TexLevel &l = t.levels[0];
+    float u = 0.5f * (sc / ma + 1.0f), v = 0.5f * (tc / ma + 1.0f);
+    u = std::isfinite(u) ? u : 0.5f;
+    v = std::isfinite(v) ? v : 0.5f;
+    const float x = u * (float)l.w - 0.5f, y = v * (float)l.h - 0.5f;
+    const float fx0 = std::floor(x), fy0 = std::floor(y);
+    const float fx = x - fx0, fy = y - fy0;
+    const int W = (int)l.w, H = (int)l.h;
+    const int x0 = std::min(std::max((int)fx0, 0), W - 1), x1 = std::min(std::max((int)fx0 + 1, 0), W - 1);
+    const int y0 = std::min(std::max((int)fy0, 0), H - 1), y1 = std::min(std::max((int)fy0 + 1, 0), H - 1);
+    const vec4 t00 = t.texel(0, x0, y0), t10 = t.texel(0, x1, y0);
+    const vec4 t01 = t.texel(0, x0, y1), t11 = t.texel(0, x1, y1);
+    const vec4 top = t00 * (1.0f - fx) + t10 * fx;
+    const vec4 bot = t01 * (1.0f - fx) + t11 * fx;
+    return top * (1.0f - fy) + bot * fy;
+}
+
 /* PT/Shaders/miss.rmiss:16-39 */
 void missShader(const pto_scene &s, const pt_render_params &p, vec3 rayDir, Payload &payload)
 {
@@ -1619,6 +1670,8 @@ void missShader(const pto_scene &s, const pt_render_params &p, vec3 rayDir, Payl
         payload.Emissive = xyz(textureLod0(s.sky2D, texCoords));
         payload.Emissive = hdrToLdr(payload.Emissive);
     }
+    else if ((p.miss_flags & PT_MISS_FLAGS_SKYBOX_CUBE) != 0 && s.hasSkyCube)
+        payload.Emissive = xyz(sampleCube(s.skyCube, rayDir));
     else
         payload.Emissive = V3(0.08f, 0.09f, 0.1f);
     payload.Pdf = -1.0f;
@@ -1954,6 +2007,12 @@ pto_scene *pto_scene_create(const pt_scene_desc *d)
     {
         s->hasSky2D = true;
         s->sky2D = makeTexture(*d->skybox_2d);
+    }
+    if (d->skybox_cube)
+    {
+        s->hasSkyCube = true;
+        for (int f = 0; f < 6; f++)
+            s->skyCube[f] = makeTexture(d->skybox_cube[f]);
     }
 
     /* flatten TLAS -> BLAS -> geometry into world-space triangles

@@ -700,11 +700,20 @@ pt_status uploadScene(Context *ctx, const pt_scene_desc *d)
         static const uint32_t kDefaults[9] = { 0xffffffffu, 0xffff8080u, 0xffffffffu, 0xffffffffu, 0x00000000u,
                                                0xffffffffu, 0x00000000u, 0x00000000u, 0xffffffffu };
         static const bool kSrgb[9] = { true, false, false, false, true, true, false, false, true };
-        ctx->hostTextures.resize(PT_SCENE_TEXTURE_OFFSET + d->texture_count);
+        // the six faces of a cube sky follow the scene's textures in the same table
+        const uint32_t sceneSlots = PT_SCENE_TEXTURE_OFFSET + d->texture_count;
+        if (d->skybox_cube)
+            for (int f = 1; f < 6; f++)
+                if (d->skybox_cube[f].width != d->skybox_cube[0].width || d->skybox_cube[f].height != d->skybox_cube[0].height ||
+                    d->skybox_cube[f].format != d->skybox_cube[0].format)
+                    return fail(ctx, PT_ERR_INVALID_ARGUMENT, "pt_scene_upload", "cube sky faces differ in size or format");
+        ctx->hostTextures.resize(sceneSlots + (d->skybox_cube ? 6 : 0));
+        s.skyCubeSlot = d->skybox_cube ? sceneSlots : 0;
         for (uint32_t i = 0; i < ctx->hostTextures.size(); i++)
         {
-            const pt_texture_desc desc =
-                i < PT_SCENE_TEXTURE_OFFSET ? defaultTexture(&kDefaults[i], kSrgb[i]) : d->textures[i - PT_SCENE_TEXTURE_OFFSET];
+            const pt_texture_desc desc = i < PT_SCENE_TEXTURE_OFFSET ? defaultTexture(&kDefaults[i], kSrgb[i])
+                                         : i < sceneSlots            ? d->textures[i - PT_SCENE_TEXTURE_OFFSET]
+                                                                     : d->skybox_cube[i - sceneSlots];
             void *mem = nullptr;
             PT_TRY(createTexture(ctx, desc, ctx->hostTextures[i], &mem));
             own.push_back(mem);
@@ -726,7 +735,7 @@ pt_status uploadScene(Context *ctx, const pt_scene_desc *d)
     }
     // material texture indices must address existing slots
     {
-        auto checkIdx = [&](uint32_t idx) { return idx < ctx->hostTextures.size(); };
+        auto checkIdx = [&](uint32_t idx) { return idx < PT_SCENE_TEXTURE_OFFSET + d->texture_count; };
         bool ok = true;
         for (uint32_t i = 0; i < d->mr_material_count; i++)
         {

@@ -95,6 +95,7 @@ struct DeviceScene
     uint32_t textureCount;
     uint32_t hasAlpha; // any non-opaque triangle
     uint32_t hasSky2D;
+    uint32_t skyCubeSlot; // first of six consecutive entries of textures[] (+X, -X, +Y, -Y, +Z, -Z); 0 = no cube sky
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -143,6 +144,49 @@ PT_DEV float4 sampleBilinear(const DeviceScene &s, const DevTexture &t, uint32_t
 PT_DEV float4 textureLod0(const DeviceScene &s, const DevTexture &t, float u, float v)
 {
     return sampleBilinear(s, t, 0, u, v);
+}
+
+// texture(samplerCube, dir) outside a fragment stage: level 0, linear; Vulkan face selection
+// (z wins ties over y over x), footprint clamped to the face — oracle/pt_oracle.cpp sampleCube
+PT_DEV float4 sampleCube(const DeviceScene &s, uint32_t firstSlot, vec3 r)
+{
+    const float ax = fabsf(r.x), ay = fabsf(r.y), az = fabsf(r.z);
+    uint32_t face;
+    float sc, tc, ma;
+    if (az >= ax && az >= ay)
+    {
+        face = r.z < 0.0f ? 5 : 4;
+        sc = r.z < 0.0f ? -r.x : r.x;
+        tc = -r.y;
+        ma = az;
+    }
+    else if (ay >= ax)
+    {
+        face = r.y < 0.0f ? 3 : 2;
+        sc = r.x;
+        tc = r.y < 0.0f ? -r.z : r.z;
+        ma = ay;
+    }
+    else
+    {
+        face = r.x < 0.0f ? 1 : 0;
+        sc = r.x < 0.0f ? r.z : -r.z;
+        tc = -r.y;
+        ma = ax;
+    }
+    const DevTexture &t = s.textures[firstSlot + face];
+    float u = 0.5f * (sc / ma + 1.0f), v = 0.5f * (tc / ma + 1.0f);
+    u = isfinite(u) ? u : 0.5f;
+    v = isfinite(v) ? v : 0.5f;
+    const float x = u * (float)t.width - 0.5f, y = v * (float)t.height - 0.5f;
+    const float fx0 = floorf(x), fy0 = floorf(y);
+    const float fx = x - fx0, fy = y - fy0;
+    const int W = (int)t.width, H = (int)t.height;
+    const int x0 = min(max((int)fx0, 0), W - 1), x1 = min(max((int)fx0 + 1, 0), W - 1);
+    const int y0 = min(max((int)fy0, 0), H - 1), y1 = min(max((int)fy0 + 1, 0), H - 1);
+    const float4 t00 = fetchTexel(s, t, 0, x0, y0, t.width), t10 = fetchTexel(s, t, 0, x1, y0, t.width);
+    const float4 t01 = fetchTexel(s, t, 0, x0, y1, t.width), t11 = fetchTexel(s, t, 0, x1, y1, t.width);
+    return lerp4(lerp4(t00, t10, fx), lerp4(t01, t11, fx), fy);
 }
 
 // textureGrad(): lambda = log2(max(|dPdx * size|, |dPdy * size|)); returns the lower level and the

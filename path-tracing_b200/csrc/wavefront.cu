@@ -178,6 +178,8 @@ __device__ __forceinline__ vec3 skyRadiance(const RenderConst &rc, vec3 dir)
         const vec3 rgb = V3(c);
         return rgb / (1.0f + maxComponent(rgb)); // hdrToLdr
     }
+    if ((rc.missFlags & PT_MISS_FLAGS_SKYBOX_CUBE) && rc.scene.skyCubeSlot)
+        return V3(sampleCube(rc.scene, rc.scene.skyCubeSlot, dir));
     return V3(0.08f, 0.09f, 0.1f);
 }
 
@@ -780,8 +782,6 @@ pt_status renderSamples(Context *ctx, const pt_render_params *params, uint32_t f
         return fail(ctx, PT_ERR_NO_SCENE, "pt_render_samples", "no scene uploaded");
     if (!ctx->accum)
         return fail(ctx, PT_ERR_NO_TARGET, "pt_render_samples", "pt_render_begin has not been called");
-    if (params->miss_flags & PT_MISS_FLAGS_SKYBOX_CUBE)
-        return fail(ctx, PT_ERR_UNSUPPORTED, "pt_render_samples", "cube skyboxes are not supported");
     if (params->bounce_count == 0 || params->bounce_count > 255)
         return fail(ctx, PT_ERR_INVALID_ARGUMENT, "pt_render_samples", "bounce_count must be in 1..255");
     if (tiles == nullptr)

@@ -87,8 +87,9 @@ void HeadlessRenderer::Render(uint32_t samples)
     params.lens_radius = m_PathTracing.LensRadius;
     params.focal_distance = m_PathTracing.FocalDistance;
     /* UpdateScenePipelineConfig: specialisation constants follow the scene (Renderer.cpp:711-754) */
-    params.miss_flags = std::holds_alternative<Skybox2D>(m_Scene->GetSkybox()) ? PT_MISS_FLAGS_SKYBOX_2D
-                                                                                : PT_MISS_FLAGS_NONE;
+    params.miss_flags = std::holds_alternative<Skybox2D>(m_Scene->GetSkybox())     ? PT_MISS_FLAGS_SKYBOX_2D
+                        : std::holds_alternative<SkyboxCube>(m_Scene->GetSkybox()) ? PT_MISS_FLAGS_SKYBOX_CUBE
+                                                                                   : PT_MISS_FLAGS_NONE;
     params.hit_flags = m_Scene->HasDxNormalTextures() ? PT_HIT_FLAGS_DX_NORMAL_TEXTURES : PT_HIT_FLAGS_NONE;
 
     Check(pt_render_samples(m_Context, &params, m_TotalSamples, samples, nullptr, 0), "pt_render_samples");

@@ -38,6 +38,8 @@ struct FlattenedScene
     std::vector<std::vector<std::byte>> TexturePixels;
     pt_texture_desc Skybox2D = {};
     std::vector<std::byte> SkyboxPixels;
+    pt_texture_desc SkyboxCube[6] = {};
+    std::vector<std::byte> SkyboxCubePixels[6];
     pt_scene_desc Desc = {};
 };
 

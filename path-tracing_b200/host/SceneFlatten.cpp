@@ -135,8 +135,14 @@ std::unique_ptr<FlattenedScene> FlattenScene(const Scene &scene, bool loadTextur
             flat->Skybox2D = LoadTexture(skybox->Content, flat->SkyboxPixels);
             desc.skybox_2d = &flat->Skybox2D;
         }
-        else if (std::holds_alternative<SkyboxCube>(scene.GetSkybox()))
-            throw error("Cube skyboxes are not supported by the headless renderer");
+        else if (const SkyboxCube *cube = std::get_if<SkyboxCube>(&scene.GetSkybox()))
+        {
+            /* layer order of TextureUploader::UploadSkyboxBlocking (TextureUploader.cpp:232-236) */
+            const TextureInfo *faces[6] = { &cube->Front, &cube->Back, &cube->Up, &cube->Down, &cube->Left, &cube->Right };
+            for (int i = 0; i < 6; i++)
+                flat->SkyboxCube[i] = LoadTexture(*faces[i], flat->SkyboxCubePixels[i]);
+            desc.skybox_cube = flat->SkyboxCube;
+        }
     }
 
     /* light UBO content (Renderer.cpp:1719-1726) */

@@ -89,7 +89,7 @@ SCENE_TEXTURE_OFFSET = 9
 NO_HIT = 0xFFFFFFFF
 TEXTURE_RGBA8, TEXTURE_RGBAF32 = 0, 1
 MATERIAL_TYPE_MR, MATERIAL_TYPE_SG, MATERIAL_TYPE_PHONG = 0, 1, 2
-MISS_FLAGS_NONE, MISS_FLAGS_SKYBOX_2D = 0, 1
+MISS_FLAGS_NONE, MISS_FLAGS_SKYBOX_2D, MISS_FLAGS_SKYBOX_CUBE = 0, 1, 2
 HIT_FLAGS_NONE, HIT_FLAGS_DX_NORMAL_TEXTURES = 0, 1
 
 # default texture slots, Path-Tracing/Shaders/ShaderTypes.incl:18-26
@@ -141,6 +141,7 @@ class CSceneDesc(C.Structure):
         ("point_light_count", C.c_uint32),
         ("directional_light", CDirectionalLight),
         ("skybox_2d", C.c_void_p),
+        ("skybox_cube", C.c_void_p),
     ]
 
 
@@ -223,6 +224,7 @@ class SceneData:
     point_lights: np.ndarray = field(default_factory=lambda: _empty(POINT_LIGHT))
     directional_light: np.ndarray = field(default_factory=lambda: np.zeros((), DIRECTIONAL_LIGHT))
     skybox_2d: Texture | None = None
+    skybox_cube: list | None = None  # six Textures: Front, Back, Up, Down, Left, Right (= +X -X +Y -Y +Z -Z)
     # default camera of the scene at `camera_extent` (not part of pt_scene_desc)
     camera_extent: tuple = (0, 0)
     view_inverse: np.ndarray | None = None
@@ -305,6 +307,11 @@ class SceneData:
             sky = tex_desc(self.skybox_2d)
             keep.append(sky)
             d.skybox_2d = C.cast(C.pointer(sky), C.c_void_p)
+        if self.skybox_cube is not None:
+            assert len(self.skybox_cube) == 6
+            faces = (CTextureDesc * 6)(*[tex_desc(t) for t in self.skybox_cube])
+            keep.append(faces)
+            d.skybox_cube = C.cast(faces, C.c_void_p)
         return d, keep
 
     # -- serialisation ----------------------------------------------------------------------
@@ -334,6 +341,9 @@ class SceneData:
         if self.skybox_2d is not None:
             items["skybox_2d"] = self.skybox_2d.pixels
             items["skybox_2d_srgb"] = np.asarray([self.skybox_2d.srgb], np.uint8)
+        if self.skybox_cube is not None:
+            items["skybox_cube"] = np.stack([t.pixels for t in self.skybox_cube])
+            items["skybox_cube_srgb"] = np.asarray([self.skybox_cube[0].srgb], np.uint8)
         np.savez_compressed(path, **items)
 
     @staticmethod
@@ -364,6 +374,8 @@ class SceneData:
         s.textures = [Texture(z[f"texture_{i}"], bool(srgb[i])) for i in range(len(srgb))]
         if "skybox_2d" in z:
             s.skybox_2d = Texture(z["skybox_2d"], bool(z["skybox_2d_srgb"][0]))
+        if "skybox_cube" in z:
+            s.skybox_cube = [Texture(f, bool(z["skybox_cube_srgb"][0])) for f in z["skybox_cube"]]
         return s
 
     @staticmethod

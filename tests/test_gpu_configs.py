@@ -1,0 +1,58 @@
+"""BASELINE.json configs[1..4] (reduced tessellation, same builders / materials / lights / cameras):
+the CUDA core against the oracle on the same seeded inputs — primary-hit ids bit-exact, images
+within the relMSE / FLIP bounds of BASELINE.md."""
+import numpy as np
+import pytest
+
+import conftest
+import metrics
+from scenes_small import SMALL, W, H
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module", params=sorted(SMALL))
+def config(request, oracle_mod):
+    build, bounces, _ = SMALL[request.param]
+    s = build()
+    r = conftest.core.Renderer(0)
+    r.update_scene_data(s)
+    yield request.param, s, r, oracle_mod.OracleScene(s), bounces
+    r.close()
+
+
+def test_first_hit_ids_bit_exact(config):
+    name, s, r, o, bounces = config
+    p = s.default_params(bounce_count=bounces)
+    got, ref = r.first_hit_aov(p, W, H), o.first_hit_aov(p, W, H)
+    for k in ("instance", "geometry", "primitive"):
+        assert (got[k] == ref[k]).all(), (name, k)
+    hit = ref["primitive"] != 0xFFFFFFFF
+    assert np.allclose(got["t"][hit], ref["t"][hit], rtol=1e-5, atol=0)
+    assert np.allclose(got["u"][hit], ref["u"][hit], rtol=1e-4, atol=1e-6)
+
+
+def test_image_parity(config):
+    name, s, r, o, bounces = config
+    p = s.default_params(bounce_count=bounces)
+    spp = 16
+    r.on_resize(W, H)
+    r.render(spp, params=p)
+    img, st = r.read_accumulation(), r.stats()
+    ref, cnt = o.render(p, W, H, 0, spp)
+    assert np.isfinite(img).all()
+    assert st["samples"] == cnt["samples"] == W * H * spp
+    # chaotic paths: a 1-ulp difference re-routes a path; transmissive / alpha-tested scenes have more of them
+    assert metrics.close_fraction(img, ref, 1e-3) > (0.93 if name == "dragon" else 0.96), name
+    assert metrics.rel_mse(img / spp, ref / spp) <= 1e-3, name
+    assert metrics.flip_lite(img / spp, ref / spp) <= 5e-3, name
+    assert abs(st["rays_closest"] - cnt["rays_closest"]) <= 3e-3 * cnt["rays_closest"]
+    assert abs(st["hits"] - cnt["hits"]) <= 3e-3 * cnt["hits"]
+    assert st["rays_shadow"] <= cnt["rays_shadow"]  # exactly-zero contributions are not traced
+    if name == "atrium":
+        r.set_traversal_stats(True)
+        r.on_resize(W, H)
+        r.render(1, params=p)
+        st = r.stats()
+        r.set_traversal_stats(False)
+        assert st["alpha_tests_closest"] > 0 and st["alpha_tests_shadow"] > 0

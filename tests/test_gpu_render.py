@@ -220,6 +220,41 @@ def test_skybox_2d(oracle_mod):
         assert metrics.rel_mse(img / 8, ref / 8) <= 1e-3
 
 
+def _cube_scene(rs, srgb):
+    b = scenes.SceneBuilder()
+    if srgb:
+        faces = [rs.integers(0, 256, (16, 16, 4), dtype=np.uint8) for _ in range(6)]
+    else:
+        faces = [rs.uniform(0, 3, (16, 16, 4)).astype(np.float32) for _ in range(6)]
+    b.set_skybox_cube(faces, srgb=srgb)
+    g = b.add_geometry(*scenes.sphere(1.0, 24, 12))
+    b.add_instance(b.add_model([(g, b.add_material_mr(color=(0.9, 0.9, 0.9, 1), roughness=0.1, metalness=1.0), None)]))
+    b.set_directional_light((0, 0, 0), (0, -1, 0))
+    return b.build(scenes.camera_matrices((0.3, 0.5, -4), (0, -0.1, 1), 96, 64, fov_deg=90), (96, 64))
+
+
+@pytest.mark.parametrize("srgb", [False, True])
+def test_skybox_cube(oracle_mod, srgb):
+    """miss.rmiss:29-32: cube sky, float and sRGB8 faces; the mirror ball reaches all six faces."""
+    s = _cube_scene(np.random.default_rng(37), srgb)
+    o = oracle_mod.OracleScene(s)
+    with conftest.core.Renderer(0) as r:
+        r.update_scene_data(s)
+        r.on_resize(96, 64)
+        p = s.default_params(4)
+        assert p.miss_flags == sc.MISS_FLAGS_SKYBOX_CUBE
+        r.render(8, params=p)
+        img = r.read_accumulation()
+        ref, _ = o.render(p, 96, 64, 0, 8)
+        assert metrics.close_fraction(img, ref, 1e-3) > 0.98
+        assert metrics.rel_mse(img / 8, ref / 8) <= 1e-3
+        # without the flag the constant sky is used (Renderer.cpp:679-690 sets the flag from the scene)
+        p.miss_flags = sc.MISS_FLAGS_NONE
+        r.on_resize(96, 64)
+        r.render(1, params=p)
+        assert np.allclose(r.read_accumulation()[0, 0, :3], (0.08, 0.09, 0.1))
+
+
 def test_errors(default_scene):
     core = conftest.core
     with core.Renderer(0) as r:
