@@ -21,6 +21,10 @@ namespace pt
 #define PT_PREFETCH_PUSH 0 // prefetch the nearest pushed child node into L1
 #endif
 
+#ifndef PT_BOX_FMA
+#define PT_BOX_FMA 0 // slab distances as one FMA per plane (precomputed org / dir, error folded into the planes)
+#endif
+
 PT_DEV void prefetchL1(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 
 struct Hit
@@ -57,6 +61,12 @@ struct RaySetup
     // float4 index (0 = lo planes, 3 = hi planes) of the slab planes the ray enters through, per axis:
     // chosen by the SIGN BIT of the direction (so that -0 pairs with idx = -inf)
     int nearX, nearY, nearZ;
+#if PT_BOX_FMA
+    // rn(org * idir) pushed outwards by its own rounding error (and one more ulp for the FMA's), per
+    // axis, for the entry (N) and exit (F) planes: fma(plane, idir, -oidN) <= true entry distance and
+    // fma(plane, idir, -oidF) >= true exit distance, so the box test stays conservative
+    float oidNx, oidNy, oidNz, oidFx, oidFy, oidFz;
+#endif
 };
 
 PT_DEV float comp(vec3 v, int k) { return k == 0 ? v.x : (k == 1 ? v.y : v.z); }
@@ -85,6 +95,16 @@ PT_DEV RaySetup setupRay(vec3 o, vec3 d)
     r.nearX = __float_as_int(d.x) < 0 ? 3 : 0;
     r.nearY = __float_as_int(d.y) < 0 ? 3 : 0;
     r.nearZ = __float_as_int(d.z) < 0 ? 3 : 0;
+#if PT_BOX_FMA
+    {
+        // |error| of fma(p, id, -rn(o * id)) against (p - o) * id is at most ulp(o * id) / 2 + ulp(result) / 2;
+        // the second term is covered by the relative factor of the test, the first by e below
+        const float ox = o.x * r.idx, oy = o.y * r.idy, oz = o.z * r.idz;
+        const float ex = fabsf(ox) * 1.8e-7f, ey = fabsf(oy) * 1.8e-7f, ez = fabsf(oz) * 1.8e-7f;
+        r.oidNx = ox + ex, r.oidNy = oy + ey, r.oidNz = oz + ez;
+        r.oidFx = ox - ex, r.oidFy = oy - ey, r.oidFz = oz - ez;
+    }
+#endif
     return r;
 }
 
@@ -159,9 +179,15 @@ PT_DEV void intersectNode(const BvhNode *__restrict__ node, const RaySetup &r, f
 #pragma unroll
     for (int i = 0; i < 4; i++)
     {
+#if PT_BOX_FMA
+        const float ax = fmaf(nx[i], r.idx, -r.oidNx), bx = fmaf(fx[i], r.idx, -r.oidFx);
+        const float ay = fmaf(ny[i], r.idy, -r.oidNy), by = fmaf(fy[i], r.idy, -r.oidFy);
+        const float az = fmaf(nz[i], r.idz, -r.oidNz), bz = fmaf(fz[i], r.idz, -r.oidFz);
+#else
         const float ax = (nx[i] - r.org.x) * r.idx, bx = (fx[i] - r.org.x) * r.idx;
         const float ay = (ny[i] - r.org.y) * r.idy, by = (fy[i] - r.org.y) * r.idy;
         const float az = (nz[i] - r.org.z) * r.idz, bz = (fz[i] - r.org.z) * r.idz;
+#endif
         // fminf/fmaxf drop NaNs (0 * inf when the origin lies in a slab plane of an axis-parallel ray)
         const float t0 = fmaxf(fmaxf(ax, ay), fmaxf(az, tmin));
         const float t1 = fminf(fminf(bx, by), fminf(bz, tmax));
@@ -665,6 +691,11 @@ PT_DEV void tracePersistent(const DeviceScene &s, uint32_t n, uint32_t *workCoun
                 r.org.z = __shfl_sync(FULL, tr.r.org.z, donor);
                 r.idx = __shfl_sync(FULL, tr.r.idx, donor), r.idy = __shfl_sync(FULL, tr.r.idy, donor);
                 r.idz = __shfl_sync(FULL, tr.r.idz, donor);
+#if PT_BOX_FMA
+                r.oidNx = __shfl_sync(FULL, tr.r.oidNx, donor), r.oidNy = __shfl_sync(FULL, tr.r.oidNy, donor);
+                r.oidNz = __shfl_sync(FULL, tr.r.oidNz, donor), r.oidFx = __shfl_sync(FULL, tr.r.oidFx, donor);
+                r.oidFy = __shfl_sync(FULL, tr.r.oidFy, donor), r.oidFz = __shfl_sync(FULL, tr.r.oidFz, donor);
+#endif
                 r.Sx = __shfl_sync(FULL, tr.r.Sx, donor), r.Sy = __shfl_sync(FULL, tr.r.Sy, donor);
                 r.Sz = __shfl_sync(FULL, tr.r.Sz, donor);
                 r.kx = __shfl_sync(FULL, tr.r.kx, donor), r.ky = __shfl_sync(FULL, tr.r.ky, donor);
