@@ -6,12 +6,16 @@
 // code.  Pipeline, all on the GPU:
 //   bake (instance x mesh transforms -> world-space triangles + shading records)
 //   -> centroid bounds -> 63-bit Morton codes -> radix sort (CUB)
-//   -> LBVH hierarchy (Karras 2012) -> bottom-up refit
-//   -> surface-area-guided collapse into 4-wide 128-byte nodes with <= 4-triangle leaves
+//   -> binary hierarchy: PLOC (Meister & Bittner 2018: repeated merging of mutually nearest clusters
+//      inside a Morton-order window, nearest = smallest surface area of the union — the default) or
+//      LBVH (Karras 2012, + bottom-up refit; tuning key "bvh_builder" = 0)
+//   -> surface-area-guided collapse into 4-wide 128-byte nodes with <= 4-triangle leaves, which also
+//      lays the triangles out in depth-first leaf order
 //   -> gather triangles into leaf order.
 #include "core_internal.h"
 
 #include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
 
 #include <algorithm>
 #include <cmath>
@@ -166,7 +170,8 @@ __global__ void k_morton(const Aabb *__restrict__ boxes, uint32_t n, const uint3
 struct Bvh2
 {
     int *left, *right, *parent;
-    uint32_t *first, *last; // covered range of sorted primitives
+    uint32_t *first, *last; // covered range of sorted primitives (LBVH only)
+    uint32_t *count;        // primitives below the node
     Aabb *box;
     uint32_t *visit;
 };
@@ -215,6 +220,7 @@ __global__ void k_hierarchy(const uint64_t *__restrict__ keys, int n, Bvh2 t)
     t.parent[rightIdx] = i;
     t.first[i] = lo;
     t.last[i] = hi;
+    t.count[i] = (uint32_t)(hi - lo + 1);
     if (i == 0)
         t.parent[0] = -1;
 }
@@ -228,6 +234,7 @@ __global__ void k_refit(const Aabb *__restrict__ primBoxes, const uint32_t *__re
     t.box[leaf] = primBoxes[sortedIdx[k]];
     t.first[leaf] = k;
     t.last[leaf] = k;
+    t.count[leaf] = 1;
     int node = t.parent[leaf];
     while (node >= 0)
     {
@@ -253,21 +260,167 @@ __device__ __forceinline__ float halfArea(const Aabb &b)
     return dx * dy + dy * dz + dz * dx;
 }
 
-// One work item = (BVH2 internal node, wide node index).  Children are opened largest-area first
-// until the node is 4 wide; sub-trees of <= PT_MAX_LEAF_TRIS primitives become leaves.
-__global__ void k_collapse(Bvh2 t, int n, const uint2 *__restrict__ work, uint32_t workCount, uint2 *__restrict__ next,
-                           uint32_t *__restrict__ nextCount, BvhNode *__restrict__ nodes, uint32_t *__restrict__ nodeCount)
+// ---------------------------------------------------------------------------------------------
+// PLOC — parallel locally-ordered clustering (Meister & Bittner, TVCG 2018).  The clusters (at first
+// the triangles, in Morton order) are merged bottom-up: every cluster looks for its nearest
+// neighbour among the PT_PLOC radius clusters on either side of it in the array, "nearest" meaning
+// the smallest surface area of the merged box; pairs that chose each other are merged into a new
+// BVH2 node, the array is compacted, repeat until one cluster is left.  The result is close to a
+// full-sweep SAH build in ray-tracing cost at a few ms per million triangles.
+//
+// Pairs are compared by the key (area, index distance, parity of the left index, left index): a
+// total order both ends of a pair evaluate identically, so the globally smallest pair is always
+// mutual (progress), and runs of identical boxes pair up as (0,1)(2,3)... instead of merging one
+// pair per pass.
+// ---------------------------------------------------------------------------------------------
+#define PT_PLOC_BLOCK 256
+#define PT_PLOC_MAX_RADIUS 64
+
+__global__ void k_ploc_leaves(const Aabb *__restrict__ primBoxes, const uint32_t *__restrict__ sortedIdx, uint32_t n, Bvh2 t,
+                              int *__restrict__ clusters)
+{
+    const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n)
+        return;
+    const uint32_t leaf = n - 1 + k;
+    t.box[leaf] = primBoxes[sortedIdx[k]];
+    t.count[leaf] = 1;
+    clusters[k] = (int)leaf;
+}
+
+__global__ void __launch_bounds__(PT_PLOC_BLOCK)
+    k_ploc_nearest(const int *__restrict__ clusters, uint32_t m, const Aabb *__restrict__ boxes, int radius,
+                   uint32_t *__restrict__ nearest)
+{
+    __shared__ float sb[6][PT_PLOC_BLOCK + 2 * PT_PLOC_MAX_RADIUS];
+    const int base = (int)(blockIdx.x * PT_PLOC_BLOCK) - radius;
+    for (int k = threadIdx.x; k < PT_PLOC_BLOCK + 2 * radius; k += PT_PLOC_BLOCK)
+    {
+        const int j = base + k;
+        if (j >= 0 && j < (int)m)
+        {
+            const Aabb b = boxes[clusters[j]];
+            sb[0][k] = b.lo[0], sb[1][k] = b.lo[1], sb[2][k] = b.lo[2];
+            sb[3][k] = b.hi[0], sb[4][k] = b.hi[1], sb[5][k] = b.hi[2];
+        }
+    }
+    __syncthreads();
+    const int i = (int)(blockIdx.x * PT_PLOC_BLOCK + threadIdx.x);
+    if (i >= (int)m)
+        return;
+    const int li = (int)threadIdx.x + radius;
+    const float lx = sb[0][li], ly = sb[1][li], lz = sb[2][li], hx = sb[3][li], hy = sb[4][li], hz = sb[5][li];
+    float bestArea = INFINITY;
+    int bestDist = 0x7fffffff, bestLeft = 0x7fffffff, bestJ = -1;
+    const int j0 = max(0, i - radius), j1 = min((int)m - 1, i + radius);
+    for (int j = j0; j <= j1; j++)
+    {
+        if (j == i)
+            continue;
+        const int lj = j - base;
+        const float dx = fmaxf(hx, sb[3][lj]) - fminf(lx, sb[0][lj]);
+        const float dy = fmaxf(hy, sb[4][lj]) - fminf(ly, sb[1][lj]);
+        const float dz = fmaxf(hz, sb[5][lj]) - fminf(lz, sb[2][lj]);
+        float area = dx * dy + dy * dz + dz * dx;
+        if (!(area < INFINITY))
+            area = INFINITY; // NaN / overflow: still a valid, symmetric key
+        const int dist = abs(i - j), left = min(i, j);
+        bool better = area < bestArea;
+        if (area == bestArea)
+        {
+            if (dist != bestDist)
+                better = dist < bestDist;
+            else if ((left & 1) != (bestLeft & 1))
+                better = (left & 1) == 0;
+            else
+                better = left < bestLeft;
+        }
+        if (better)
+        {
+            bestArea = area;
+            bestDist = dist;
+            bestLeft = left;
+            bestJ = j;
+        }
+    }
+    nearest[i] = (uint32_t)bestJ;
+}
+
+// flags[i] = (cluster i stays in the array) | (cluster i is the left end of a merging pair) << 32
+__global__ void k_ploc_flags(const uint32_t *__restrict__ nearest, uint32_t m, unsigned long long *__restrict__ flags)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= m)
+        return;
+    const uint32_t j = nearest[i];
+    const bool mutual = nearest[j] == i;
+    const unsigned long long keep = !(mutual && i > j), merger = mutual && i < j;
+    flags[i] = keep | (merger << 32);
+}
+
+// scan[i] = exclusive prefix sum of flags: low word = position after compaction, high word = rank
+// among this pass's merges.  Merge number q (counted over all passes) creates node n - 2 - q, so that
+// the last merge creates the root, node 0.
+__global__ void k_ploc_merge(const int *__restrict__ clusters, uint32_t m, const uint32_t *__restrict__ nearest,
+                             const unsigned long long *__restrict__ flags, const unsigned long long *__restrict__ scan,
+                             uint32_t n, uint32_t mergesBefore, Bvh2 t, int *__restrict__ clustersOut,
+                             uint32_t *__restrict__ totals)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= m)
+        return;
+    const unsigned long long f = flags[i], sc = scan[i];
+    const uint32_t keep = (uint32_t)f & 1u, merger = (uint32_t)(f >> 32);
+    const uint32_t pos = (uint32_t)sc, rank = (uint32_t)(sc >> 32);
+    if (i == m - 1)
+    {
+        totals[0] = pos + keep;    // clusters left
+        totals[1] = rank + merger; // merges of this pass
+    }
+    if (!keep)
+        return;
+    int node = clusters[i];
+    if (merger)
+    {
+        const int other = clusters[nearest[i]];
+        const int id = (int)(n - 2u - (mergesBefore + rank));
+        const Aabb a = t.box[node], b = t.box[other];
+        Aabb u;
+#pragma unroll
+        for (int j = 0; j < 3; j++)
+        {
+            u.lo[j] = fminf(a.lo[j], b.lo[j]);
+            u.hi[j] = fmaxf(a.hi[j], b.hi[j]);
+        }
+        t.box[id] = u;
+        t.left[id] = node;
+        t.right[id] = other;
+        t.count[id] = t.count[node] + t.count[other];
+        node = id;
+    }
+    clustersOut[pos] = node;
+}
+
+// One work item = (BVH2 internal node, wide node index, first triangle of the node's range in the
+// final order).  Children are opened largest-area first until the node is 4 wide; sub-trees of
+// <= PT_MAX_LEAF_TRIS primitives become leaves.  The triangles are laid out depth first: child k
+// starts where child k - 1 ends, and a leaf writes the source indices of its triangles to
+// order[first ...] (k_gather moves the triangle data afterwards).
+__global__ void k_collapse(Bvh2 t, int n, const uint4 *__restrict__ work, uint32_t workCount, uint4 *__restrict__ next,
+                           uint32_t *__restrict__ nextCount, BvhNode *__restrict__ nodes, uint32_t *__restrict__ nodeCount,
+                           const uint32_t *__restrict__ sortedIdx, uint32_t *__restrict__ order)
 {
     const uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;
     if (w >= workCount)
         return;
     const int src = (int)work[w].x;
     const uint32_t dst = work[w].y;
+    uint32_t first = work[w].z;
     int c[4];
     int cc = 2;
     c[0] = t.left[src];
     c[1] = t.right[src];
-    auto isLeaf = [&](int node) { return t.last[node] - t.first[node] + 1 <= PT_MAX_LEAF_TRIS; };
+    auto isLeaf = [&](int node) { return t.count[node] <= PT_MAX_LEAF_TRIS; };
     while (cc < 4)
     {
         int bestSlot = -1;
@@ -308,14 +461,37 @@ __global__ void k_collapse(Bvh2 t, int n, const uint2 *__restrict__ work, uint32
             lo[j][i] = b.lo[j];
             hi[j][i] = b.hi[j];
         }
+        const uint32_t count = t.count[c[i]];
         if (isLeaf(c[i]))
-            ref[i] = encodeLeaf(t.first[c[i]], t.last[c[i]] - t.first[c[i]] + 1);
+        {
+            ref[i] = encodeLeaf(first, count);
+            // the (at most PT_MAX_LEAF_TRIS) triangles below c[i], left to right
+            int stack[PT_MAX_LEAF_TRIS];
+            int sp = 0, node = c[i];
+            uint32_t out = first;
+            for (;;)
+            {
+                if (node >= n - 1)
+                {
+                    order[out++] = sortedIdx[node - (n - 1)];
+                    if (sp == 0)
+                        break;
+                    node = stack[--sp];
+                }
+                else
+                {
+                    stack[sp++] = t.right[node];
+                    node = t.left[node];
+                }
+            }
+        }
         else
         {
             const uint32_t idx = atomicAdd(nodeCount, 1u);
             ref[i] = (int)idx;
-            next[atomicAdd(nextCount, 1u)] = make_uint2((uint32_t)c[i], idx);
+            next[atomicAdd(nextCount, 1u)] = make_uint4((uint32_t)c[i], idx, first, 0u);
         }
+        first += count;
     }
     BvhNode out;
     out.lox = make_float4(lo[0][0], lo[0][1], lo[0][2], lo[0][3]);
@@ -807,20 +983,12 @@ pt_status uploadScene(Context *ctx, const pt_scene_desc *d)
         PT_CUDA_CHECK(ctx, cub::DeviceRadixSort::SortPairs(sortTemp, sortBytes, keysIn, keysOut, valsIn, valsOut, (int)n, 0,
                                                            63, ctx->stream));
 
-        // ---- final triangle streams ---------------------------------------------------------
-        float4 *triPos;
-        TriShade *triShade;
-        PT_TRY(devAlloc(ctx, &triPos, (size_t)n * 3, own));
-        PT_TRY(devAlloc(ctx, &triShade, (size_t)n, own));
-        k_gather<<<G, T, 0, ctx->stream>>>(valsOut, n, posUnsorted, shadeUnsorted, triPos, triShade);
-        s.triPos = triPos;
-        s.triShade = triShade;
-
         // ---- hierarchy ------------------------------------------------------------------------
         BvhNode *wide;
         const uint32_t wideCapacity = std::max(1u, n); // <= n - 1 internal nodes (+ 1 for tiny scenes)
         PT_TRY(devAlloc(ctx, &wide, (size_t)wideCapacity, temp));
         uint32_t wideCount = 1;
+        uint32_t *order = valsOut; // source index of the triangle at every position of the final order
         if (n <= PT_MAX_LEAF_TRIS)
             k_single_leaf_root<<<1, 1, 0, ctx->stream>>>(primBoxes, valsOut, n, wide);
         else
@@ -829,21 +997,70 @@ pt_status uploadScene(Context *ctx, const pt_scene_desc *d)
             const size_t nodes2 = 2 * (size_t)n - 1;
             PT_TRY(devAlloc(ctx, &t.left, (size_t)n, temp));
             PT_TRY(devAlloc(ctx, &t.right, (size_t)n, temp));
-            PT_TRY(devAlloc(ctx, &t.parent, nodes2, temp));
-            PT_TRY(devAlloc(ctx, &t.first, nodes2, temp));
-            PT_TRY(devAlloc(ctx, &t.last, nodes2, temp));
+            PT_TRY(devAlloc(ctx, &t.count, nodes2, temp));
             PT_TRY(devAlloc(ctx, &t.box, nodes2, temp));
-            PT_TRY(devAlloc(ctx, &t.visit, (size_t)n, temp));
-            PT_CUDA_CHECK(ctx, cudaMemsetAsync(t.visit, 0, (size_t)n * 4, ctx->stream));
-            k_hierarchy<<<G, T, 0, ctx->stream>>>(keysOut, (int)n, t);
-            k_refit<<<G, T, 0, ctx->stream>>>(primBoxes, valsOut, (int)n, t);
+            if (ctx->bvhBuilder == 0)
+            {
+                PT_TRY(devAlloc(ctx, &t.parent, nodes2, temp));
+                PT_TRY(devAlloc(ctx, &t.first, nodes2, temp));
+                PT_TRY(devAlloc(ctx, &t.last, nodes2, temp));
+                PT_TRY(devAlloc(ctx, &t.visit, (size_t)n, temp));
+                PT_CUDA_CHECK(ctx, cudaMemsetAsync(t.visit, 0, (size_t)n * 4, ctx->stream));
+                k_hierarchy<<<G, T, 0, ctx->stream>>>(keysOut, (int)n, t);
+                k_refit<<<G, T, 0, ctx->stream>>>(primBoxes, valsOut, (int)n, t);
+            }
+            else
+            {
+                t.parent = nullptr;
+                t.first = t.last = t.visit = nullptr;
+                const int radius = (int)std::min<uint32_t>(PT_PLOC_MAX_RADIUS, std::max<uint32_t>(1u, ctx->plocRadius));
+                int *clusters[2];
+                uint32_t *nearest, *totals;
+                unsigned long long *flags, *scan;
+                PT_TRY(devAlloc(ctx, &clusters[0], (size_t)n, temp));
+                PT_TRY(devAlloc(ctx, &clusters[1], (size_t)n, temp));
+                PT_TRY(devAlloc(ctx, &nearest, (size_t)n, temp));
+                PT_TRY(devAlloc(ctx, &flags, (size_t)n, temp));
+                PT_TRY(devAlloc(ctx, &scan, (size_t)n, temp));
+                PT_TRY(devAlloc(ctx, &totals, 2, temp));
+                size_t scanBytes = 0;
+                cub::DeviceScan::ExclusiveSum(nullptr, scanBytes, flags, scan, (int)n, ctx->stream);
+                uint8_t *scanTemp;
+                PT_TRY(devAlloc(ctx, &scanTemp, scanBytes, temp));
+                k_ploc_leaves<<<G, T, 0, ctx->stream>>>(primBoxes, valsOut, n, t, clusters[0]);
+                uint32_t m = n, merges = 0, passes = 0;
+                int cur = 0;
+                while (m > 1)
+                {
+                    const uint32_t gb = (m + PT_PLOC_BLOCK - 1) / PT_PLOC_BLOCK;
+                    k_ploc_nearest<<<gb, PT_PLOC_BLOCK, 0, ctx->stream>>>(clusters[cur], m, t.box, radius, nearest);
+                    k_ploc_flags<<<gb, PT_PLOC_BLOCK, 0, ctx->stream>>>(nearest, m, flags);
+                    PT_CUDA_CHECK(ctx, cub::DeviceScan::ExclusiveSum(scanTemp, scanBytes, flags, scan, (int)m, ctx->stream));
+                    k_ploc_merge<<<gb, PT_PLOC_BLOCK, 0, ctx->stream>>>(clusters[cur], m, nearest, flags, scan, n, merges, t,
+                                                                        clusters[cur ^ 1], totals);
+                    uint32_t h[2] = { 0, 0 };
+                    PT_CUDA_CHECK(ctx, cudaMemcpyAsync(h, totals, 8, cudaMemcpyDeviceToHost, ctx->stream));
+                    PT_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+                    if (h[1] == 0 || h[0] + h[1] != m || ++passes > 100000)
+                    {
+                        freeTemp();
+                        freeScene(ctx);
+                        return fail(ctx, PT_ERR_CUDA, "pt_scene_upload", "PLOC made no progress (internal error)");
+                    }
+                    m = h[0];
+                    merges += h[1];
+                    cur ^= 1;
+                }
+                ctx->bvhBuildPasses = passes;
+            }
 
-            uint2 *work[2];
+            uint4 *work[2];
             uint32_t *counters; // [0] node count, [1], [2] work counts
             PT_TRY(devAlloc(ctx, &work[0], (size_t)n, temp));
             PT_TRY(devAlloc(ctx, &work[1], (size_t)n, temp));
             PT_TRY(devAlloc(ctx, &counters, 3, temp));
-            const uint2 rootItem = make_uint2(0u, 0u);
+            PT_TRY(devAlloc(ctx, &order, (size_t)n, temp));
+            const uint4 rootItem = make_uint4(0u, 0u, 0u, 0u);
             const uint32_t initCounters[3] = { 1u, 0u, 0u };
             PT_CUDA_CHECK(ctx, cudaMemcpyAsync(work[0], &rootItem, sizeof(rootItem), cudaMemcpyHostToDevice, ctx->stream));
             PT_CUDA_CHECK(ctx, cudaMemcpyAsync(counters, initCounters, sizeof(initCounters), cudaMemcpyHostToDevice, ctx->stream));
@@ -854,7 +1071,8 @@ pt_status uploadScene(Context *ctx, const pt_scene_desc *d)
             {
                 PT_CUDA_CHECK(ctx, cudaMemsetAsync(counters + 1 + (cur ^ 1), 0, 4, ctx->stream));
                 k_collapse<<<(workCount + 127) / 128, 128, 0, ctx->stream>>>(t, (int)n, work[cur], workCount, work[cur ^ 1],
-                                                                             counters + 1 + (cur ^ 1), wide, counters);
+                                                                             counters + 1 + (cur ^ 1), wide, counters, valsOut,
+                                                                             order);
                 PT_CUDA_CHECK(ctx, cudaMemcpyAsync(&workCount, counters + 1 + (cur ^ 1), 4, cudaMemcpyDeviceToHost, ctx->stream));
                 PT_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
                 cur ^= 1;
@@ -862,6 +1080,15 @@ pt_status uploadScene(Context *ctx, const pt_scene_desc *d)
             PT_CUDA_CHECK(ctx, cudaMemcpyAsync(&wideCount, counters, 4, cudaMemcpyDeviceToHost, ctx->stream));
             PT_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
         }
+
+        // ---- final triangle streams, in leaf order ------------------------------------------------
+        float4 *triPos;
+        TriShade *triShade;
+        PT_TRY(devAlloc(ctx, &triPos, (size_t)n * 3, own));
+        PT_TRY(devAlloc(ctx, &triShade, (size_t)n, own));
+        k_gather<<<G, T, 0, ctx->stream>>>(order, n, posUnsorted, shadeUnsorted, triPos, triShade);
+        s.triPos = triPos;
+        s.triShade = triShade;
         BvhNode *nodes;
         PT_TRY(devAlloc(ctx, &nodes, (size_t)wideCount, own));
         PT_CUDA_CHECK(ctx, cudaMemcpyAsync(nodes, wide, (size_t)wideCount * sizeof(BvhNode), cudaMemcpyDeviceToDevice, ctx->stream));

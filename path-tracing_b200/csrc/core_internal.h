@@ -97,6 +97,9 @@ struct Context
     uint64_t texelArenaBytes = 0;
     uint64_t nodeCount = 0, bvhBytes = 0;
     float bvhBuildMs = 0, sceneUploadMs = 0;
+    uint32_t bvhBuilder = 1;  // 1 = PLOC (default), 0 = LBVH; PT_BVH / tuning key "bvh_builder"
+    uint32_t plocRadius = 8;  // PLOC search window on either side; PT_PLOC_RADIUS / "ploc_radius"
+    uint32_t bvhBuildPasses = 0;
 
     // target
     uint32_t width = 0, height = 0;

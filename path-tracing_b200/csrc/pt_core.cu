@@ -94,6 +94,10 @@ pt_status pt_context_create(int32_t cuda_device, pt_context **out_ctx)
         ctx->poolCount = (uint32_t)std::min(PT_MAX_POOLS, std::max(1, std::atoi(e)));
     if (const char *e = std::getenv("PT_SORT_HITS"))
         ctx->sortHits = std::atoi(e) != 0;
+    if (const char *e = std::getenv("PT_BVH"))
+        ctx->bvhBuilder = std::atoi(e) != 0;
+    if (const char *e = std::getenv("PT_PLOC_RADIUS"))
+        ctx->plocRadius = (uint32_t)std::max(1, std::atoi(e));
     if (const char *e = std::getenv("PT_SBUF_MB"))
         ctx->sbufBudgetBytes = std::max<size_t>(1, std::strtoull(e, nullptr, 10)) << 20;
 #define PT_CREATE_CHECK(expr)                                                                                         \
@@ -386,6 +390,10 @@ pt_status pt_set_tuning(pt_context *ctx, const char *key, uint64_t value)
     }
     else if (k == "sort_hits")
         ctx->sortHits = value != 0;
+    else if (k == "bvh_builder") // takes effect at the next pt_scene_upload
+        ctx->bvhBuilder = value != 0;
+    else if (k == "ploc_radius")
+        ctx->plocRadius = (uint32_t)std::max<uint64_t>(1, value);
     else if (k == "sbuf_mb")
         ctx->sbufBudgetBytes = std::max<uint64_t>(1, value) << 20;
     else
