@@ -366,6 +366,38 @@ PT_API pt_status pt_accum_device_ptr(pt_context *ctx, void **out_float4_device_p
  * float4 sum image: copies width*height*4 floats (RGB = sum of samples, A = 1) to host. */
 PT_API pt_status pt_readback(pt_context *ctx, float *out_rgba, size_t out_bytes);
 
+/* ---- post-processing and output conversion ---------- */
+
+/* Renderer::PostProcessSettings (PT/Renderer/Renderer.h:68-73) + the tone-mapping
+ * specialisation constant (PT/Shaders/ShaderRendererTypes.incl:70-72). */
+typedef struct pt_postprocess_params {
+    float exposure;        /* default 1.0 */
+    float bloom_threshold; /* default 1.0 */
+    float bloom_intensity; /* default 0.1 */
+    uint32_t tone_mapping; /* PT_TONE_MAPPING_SDR: 1 - exp(-c); PT_TONE_MAPPING_HDR: identity */
+} pt_postprocess_params;
+
+enum { PT_TONE_MAPPING_SDR = 0, PT_TONE_MAPPING_HDR = 1 };
+
+/* OutputSaver::SelectImageFormat (PT/Renderer/OutputSaver.cpp:255-273): png/jpg/tga/mp4 outputs
+ * are R8G8B8A8_SRGB, hdr outputs R32G32B32A32_SFLOAT. */
+enum { PT_OUTPUT_RGBA8_SRGB = 0, PT_OUTPUT_RGBAF32 = 1 };
+
+/* Replaces Renderer::RecordPostProcessCommands + RecordSaveOutputCommands
+ * (PT/Renderer/Renderer.cpp:928-1060, 1205-1250) and OutputSaver's blit + read-back
+ * (PT/Renderer/OutputSaver.cpp:113-181) for the accumulated image:
+ *   postprocess.comp:16-40   colour = sum / total_samples * exposure (NaN -> red, Inf -> green
+ *                            markers), soft-knee bloom prefilter; both stored as RGBA16F
+ *   bloomDownsample.comp / bloomUpsample.comp over mip levels 0 .. min(levels - 3, 12) - 1
+ *                            of the RGBA16F bloom image (bilinear, clamp-to-edge sampler)
+ *   composition.comp:15-25   colour += bloom_intensity * 0.1 * bloom
+ *   toneMapping.comp:13-24   in place on the RGBA16F "linear output image"
+ *   blit to the output format (sRGB encode + 8-bit quantisation, or float widening).
+ * Writes width*height*4 bytes (RGBA8) or width*height*16 bytes (RGBAF32) to host memory;
+ * alpha is 1.  The accumulation buffer is not modified. */
+PT_API pt_status pt_postprocess(pt_context *ctx, const pt_postprocess_params *params, uint32_t total_samples,
+                                uint32_t output_format, void *out_pixels, size_t out_bytes);
+
 /* Waits for all queued work of the context. */
 PT_API pt_status pt_synchronize(pt_context *ctx);
 

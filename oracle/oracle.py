@@ -40,7 +40,7 @@ class Counters(C.Structure):
 
 def build(force: bool = False) -> str:
     """Compiles the oracle with the committed Makefile (gcc only, no CUDA)."""
-    src = [os.path.join(_HERE, f) for f in ("pt_oracle.cpp", "pt_oracle.h", "glsl_math.h")]
+    src = [os.path.join(_HERE, f) for f in ("pt_oracle.cpp", "pt_oracle_post.cpp", "pt_oracle.h", "glsl_math.h")]
     if force or not os.path.exists(_LIB_PATH) or any(os.path.getmtime(s) > os.path.getmtime(_LIB_PATH) for s in src):
         subprocess.check_call(["make", "-C", _HERE, "libpt_oracle.so"], stdout=subprocess.DEVNULL)
     return _LIB_PATH
@@ -81,8 +81,34 @@ def lib():
         L.pto_texture_info.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p]
         L.pto_texture_level.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p]
         L.pto_texture_sample.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint32, C.c_int32]
+        L.pto_postprocess.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p]
+        L.pto_round_half.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64]
         _lib = L
     return _lib
+
+
+def postprocess(accum: np.ndarray, total_samples: int, exposure=1.0, bloom_threshold=1.0, bloom_intensity=0.1,
+                hdr: bool = False) -> np.ndarray:
+    """The reference's post-process + output chain (pt_oracle_post.cpp) on a host (H, W, 4) float32 sum image:
+    (H, W, 4) uint8 sRGB (png / jpg / tga outputs) or, with hdr, (H, W, 4) float32 (the .hdr output)."""
+    from importlib import import_module
+
+    core = import_module("path-tracing_b200.core")
+    accum = np.ascontiguousarray(accum, np.float32)
+    h, w = accum.shape[:2]
+    p = core.PostProcessParams(exposure, bloom_threshold, bloom_intensity, 1 if hdr else 0)
+    out = np.zeros((h, w, 4), np.float32 if hdr else np.uint8)
+    rc = lib().pto_postprocess(accum.ctypes.data, w, h, C.addressof(p), int(total_samples), 1 if hdr else 0, out.ctypes.data)
+    assert rc == 0, rc
+    return out
+
+
+def round_half(values: np.ndarray) -> np.ndarray:
+    a = np.ascontiguousarray(values, np.float32)
+    out = np.empty_like(a)
+    rc = lib().pto_round_half(a.ctypes.data, out.ctypes.data, a.size)
+    assert rc == 0, rc
+    return out
 
 
 # record strides of pt(o)_test_shading, include/pt_core.h

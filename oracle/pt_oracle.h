@@ -77,6 +77,13 @@ PT_API int32_t pto_texture_level(const pto_scene *scene, uint32_t slot, uint32_t
 PT_API int32_t pto_texture_sample(const pto_scene *scene, uint32_t slot, const float *in6, float *out4,
                                   uint32_t count, int32_t use_grad);
 
+/* Post-processing + output chain (pt_oracle_post.cpp; same parameters and formats as pt_postprocess)
+ * applied to a host accumulation image of width*height float4 sums. */
+PT_API int32_t pto_postprocess(const float *accum, uint32_t width, uint32_t height, const pt_postprocess_params *params,
+                               uint32_t total_samples, uint32_t output_format, void *out_pixels);
+/* binary32 -> binary16 -> binary32 (round to nearest even) of n values */
+PT_API int32_t pto_round_half(const float *in, float *out, uint64_t n);
+
 #ifdef __cplusplus
 }
 #endif

@@ -31,6 +31,7 @@ ABI_SYMBOLS = [
     "pt_render_samples",
     "pt_accum_device_ptr",
     "pt_readback",
+    "pt_postprocess",
     "pt_synchronize",
     "pt_first_hit_aov",
     "pt_trace_closest",
@@ -54,6 +55,16 @@ class PtError(RuntimeError):
 
 
 KERNEL_CLASSES = ("extend", "shade", "shadow", "finish")
+
+
+class PostProcessParams(C.Structure):
+    """pt_postprocess_params = Renderer::PostProcessSettings (Path-Tracing/Renderer/Renderer.h:68-73) + tone-mapping mode."""
+
+    _fields_ = [("exposure", C.c_float), ("bloom_threshold", C.c_float), ("bloom_intensity", C.c_float), ("tone_mapping", C.c_uint32)]
+
+
+TONE_MAPPING_SDR, TONE_MAPPING_HDR = 0, 1
+OUTPUT_RGBA8_SRGB, OUTPUT_RGBAF32 = 0, 1
 
 
 class Stats(C.Structure):
@@ -100,6 +111,22 @@ def build(verbose: bool = False) -> str:
     return LIB_PATH
 
 
+def write_png(path: str, rgba8: np.ndarray):
+    """Minimal PNG writer (8-bit RGBA, zlib, no filtering) — the reference uses stb_image_write."""
+    import struct
+    import zlib
+
+    h, w = rgba8.shape[:2]
+    raw = np.concatenate([np.zeros((h, 1), np.uint8), np.ascontiguousarray(rgba8, np.uint8).reshape(h, w * 4)], 1).tobytes()
+
+    def chunk(tag: bytes, data: bytes) -> bytes:
+        return struct.pack(">I", len(data)) + tag + data + struct.pack(">I", zlib.crc32(tag + data) & 0xFFFFFFFF)
+
+    with open(path, "wb") as f:
+        f.write(b"\x89PNG\r\n\x1a\n" + chunk(b"IHDR", struct.pack(">IIBBBBB", w, h, 8, 6, 0, 0, 0)) +
+                chunk(b"IDAT", zlib.compress(raw, 6)) + chunk(b"IEND", b""))
+
+
 _lib = None
 
 
@@ -123,6 +150,7 @@ def lib():
     L.pt_render_samples.argtypes = [vp, vp, u32, u32, vp, u32]
     L.pt_accum_device_ptr.argtypes = [vp, C.POINTER(vp), C.POINTER(C.c_size_t), C.POINTER(vp)]
     L.pt_readback.argtypes = [vp, vp, C.c_size_t]
+    L.pt_postprocess.argtypes = [vp, vp, u32, u32, vp, C.c_size_t]
     L.pt_synchronize.argtypes = [vp]
     L.pt_first_hit_aov.argtypes = [vp, vp, u32, u32, vp]
     L.pt_trace_closest.argtypes = [vp, vp, u64, vp]
@@ -217,6 +245,24 @@ class Renderer:
         assert out.dtype == np.float32 and out.flags.c_contiguous and out.size == self.width * self.height * 4
         self._check(self._L.pt_readback(self._h, out.ctypes.data, out.nbytes))
         return out
+
+    def postprocess(self, exposure: float = 1.0, bloom_threshold: float = 1.0, bloom_intensity: float = 0.1, hdr: bool = False,
+                    total_samples: int | None = None) -> np.ndarray:
+        """What the reference's "Render" button writes (Renderer::RecordPostProcessCommands +
+        RecordSaveOutputCommands + OutputSaver): exposure, bloom, tone mapping and the output-format
+        conversion of the accumulated image.  (H, W, 4) uint8 sRGB, or float32 with hdr (the .hdr output,
+        not tone-mapped)."""
+        p = PostProcessParams(exposure, bloom_threshold, bloom_intensity, TONE_MAPPING_HDR if hdr else TONE_MAPPING_SDR)
+        out = np.empty((self.height, self.width, 4), np.float32 if hdr else np.uint8)
+        n = self.total_samples if total_samples is None else total_samples
+        self._check(self._L.pt_postprocess(self._h, C.addressof(p), int(n), OUTPUT_RGBAF32 if hdr else OUTPUT_RGBA8_SRGB,
+                                           out.ctypes.data, out.nbytes))
+        return out
+
+    def save_png(self, path: str, **postprocess_args):
+        """OutputSaver::WriteImage for OutputFormat::Png (Path-Tracing/Renderer/OutputSaver.cpp:227-253):
+        8-bit RGBA, rows top to bottom."""
+        write_png(path, self.postprocess(hdr=False, **postprocess_args))
 
     def readback_into(self, host_ptr: int, nbytes: int):
         """pt_readback into caller-owned (e.g. pinned) host memory."""

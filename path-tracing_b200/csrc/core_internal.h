@@ -155,6 +155,10 @@ pt_status firstHitAov(Context *ctx, const pt_render_params *params, uint32_t wid
 pt_status traceClosest(Context *ctx, const pt_ray *rays, uint64_t n, pt_hit *out);
 pt_status traceOcclusion(Context *ctx, const pt_ray *rays, uint64_t n, uint8_t *out);
 
+// postprocess.cu
+pt_status postProcess(Context *ctx, const pt_postprocess_params *params, uint32_t totalSamples, uint32_t outputFormat,
+                      void *out, size_t outBytes);
+
 // unit_kernels.cu
 pt_status testShading(Context *ctx, uint32_t mode, const float *input, float *output, uint32_t count);
 uint32_t testInputStride(uint32_t mode);

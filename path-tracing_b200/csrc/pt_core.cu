@@ -283,6 +283,15 @@ pt_status pt_readback(pt_context *ctx, float *out_rgba, size_t out_bytes)
     return PT_OK;
 }
 
+pt_status pt_postprocess(pt_context *ctx, const pt_postprocess_params *params, uint32_t total_samples,
+                         uint32_t output_format, void *out_pixels, size_t out_bytes)
+{
+    if (!ctx)
+        return PT_ERR_INVALID_ARGUMENT;
+    cudaSetDevice(ctx->device);
+    return postProcess(ctx, params, total_samples, output_format, out_pixels, out_bytes);
+}
+
 pt_status pt_synchronize(pt_context *ctx)
 {
     if (!ctx)

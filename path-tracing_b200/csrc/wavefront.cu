@@ -39,7 +39,7 @@ namespace
 
 // resident 128-thread blocks per SM the register allocation must allow (tuned on the B200)
 #ifndef PT_TRACE_MIN_BLOCKS
-#define PT_TRACE_MIN_BLOCKS 6
+#define PT_TRACE_MIN_BLOCKS 8
 #endif
 #ifndef PT_SHADE_MIN_BLOCKS
 #define PT_SHADE_MIN_BLOCKS 4

@@ -103,34 +103,28 @@ std::vector<float> HeadlessRenderer::ReadAccumulation()
     return pixels;
 }
 
+/* Renderer::RecordPostProcessCommands + RecordSaveOutputCommands + OutputSaver::WriteImage
+ * (Renderer.cpp:928-1060, 1205-1250; OutputSaver.cpp:227-253): the whole chain runs in the core. */
 void HeadlessRenderer::SavePng(const std::string &path)
 {
-    const std::vector<float> sum = ReadAccumulation();
+    const pt_postprocess_params params = { m_PostProcess.Exposure, m_PostProcess.BloomThreshold,
+                                           m_PostProcess.BloomIntensity, PT_TONE_MAPPING_SDR };
     std::vector<uint8_t> out(static_cast<size_t>(m_Width) * m_Height * 4);
-    const float scale = m_PostProcess.Exposure / static_cast<float>(std::max(1u, m_TotalSamples));
-    for (size_t i = 0; i < out.size(); i += 4)
-    {
-        for (int c = 0; c < 3; c++)
-        {
-            const float linear = 1.0f - std::exp(-sum[i + c] * scale);
-            const float srgb =
-                linear <= 0.0031308f ? 12.92f * linear : 1.055f * std::pow(linear, 1.0f / 2.4f) - 0.055f;
-            out[i + c] = static_cast<uint8_t>(std::clamp(srgb, 0.0f, 1.0f) * 255.0f + 0.5f);
-        }
-        out[i + 3] = 255;
-    }
-    if (stbi_write_png(path.c_str(), m_Width, m_Height, 4, out.data(), m_Width * 4) == 0)
+    Check(pt_postprocess(m_Context, &params, std::max(1u, m_TotalSamples), PT_OUTPUT_RGBA8_SRGB, out.data(), out.size()),
+          "pt_postprocess");
+    if (stbi_write_png(path.c_str(), m_Width, m_Height, 4, out.data(), 0) == 0)
         throw error(std::format("Could not write {}", path));
 }
 
 void HeadlessRenderer::SaveHdr(const std::string &path)
 {
-    std::vector<float> sum = ReadAccumulation();
-    const float scale = m_PostProcess.Exposure / static_cast<float>(std::max(1u, m_TotalSamples));
-    for (size_t i = 0; i < sum.size(); i += 4)
-        for (int c = 0; c < 3; c++)
-            sum[i + c] *= scale;
-    if (stbi_write_hdr(path.c_str(), m_Width, m_Height, 4, sum.data()) == 0)
+    const pt_postprocess_params params = { m_PostProcess.Exposure, m_PostProcess.BloomThreshold,
+                                           m_PostProcess.BloomIntensity, PT_TONE_MAPPING_HDR };
+    std::vector<float> out(static_cast<size_t>(m_Width) * m_Height * 4);
+    Check(pt_postprocess(m_Context, &params, std::max(1u, m_TotalSamples), PT_OUTPUT_RGBAF32, out.data(),
+                         out.size() * sizeof(float)),
+          "pt_postprocess");
+    if (stbi_write_hdr(path.c_str(), m_Width, m_Height, 4, out.data()) == 0)
         throw error(std::format("Could not write {}", path));
 }
 

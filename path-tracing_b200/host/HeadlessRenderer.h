@@ -59,7 +59,7 @@ public:
         float FocalDistance = 10.0f;
     };
 
-    /* Renderer::PostProcessSettings, Renderer.h:62-67 (only Exposure is used headless) */
+    /* Renderer::PostProcessSettings, Renderer.h:68-73 */
     struct PostProcessSettings
     {
         float Exposure = 1.0f;
@@ -86,9 +86,9 @@ public:
     [[nodiscard]] uint32_t GetTotalSamples() const { return m_TotalSamples; }
     /* raw sum image, RGBA float, width*height*4 */
     [[nodiscard]] std::vector<float> ReadAccumulation();
-    /* postprocess.comp:22 (sum / TotalSamples * exposure), toneMapping.comp:21 (1 - exp(-c)), sRGB8 */
+    /* exposure + bloom + composition + SDR tone mapping + sRGB8 (pt_postprocess), written with stb like OutputSaver */
     void SavePng(const std::string &path);
-    /* linear float image (sum / TotalSamples * exposure) as Radiance .hdr */
+    /* OutputFormat::Hdr: same chain without the tone curve, as Radiance .hdr */
     void SaveHdr(const std::string &path);
 
     [[nodiscard]] pt_stats GetStats();
