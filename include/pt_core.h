@@ -334,6 +334,27 @@ PT_API const char *pt_last_error(const pt_context *ctx);
  * the GPU, builds texture mip chains.  Blocking. */
 PT_API pt_status pt_scene_upload(pt_context *ctx, const pt_scene_desc *scene);
 
+/* What Scene::Update changes from frame to frame in an animated scene (PT/Scene.cpp:52-83).
+ * A NULL pointer leaves that part of the scene as it is. */
+typedef struct pt_scene_update_desc {
+    const float *instance_transforms; /* instance_count x 12 floats, the pt_instance::transform of every
+                                         instance in upload order (ModelInstance::Transform, Scene.cpp:69-70) */
+    uint32_t instance_count;          /* must equal the uploaded scene's instance_count */
+    const pt_point_light *point_lights; /* the whole light array (positions follow their nodes, Scene.cpp:75-77) */
+    uint32_t point_light_count;       /* <= PT_MAX_LIGHT_COUNT */
+    const pt_directional_light *directional_light; /* Scene.cpp:79-80 */
+} pt_scene_update_desc;
+
+/* Replaces the per-frame half of Renderer::UpdateSceneData / Renderer::Render for animated scenes:
+ * the light uniform rewrite (PT/Renderer/Renderer.cpp:1719-1726) and
+ * AccelerationStructure::RecordUpdateCommands (PT/Renderer/AccelerationStructure.cpp:48-57, called
+ * from Renderer.cpp:1753-1754).  Where the reference refits BLAS + TLAS, the core re-bakes the
+ * instances and rebuilds its BVH on the GPU.  Geometry, materials and textures are unchanged.
+ * Skeletal animation (skinning.comp) is not covered: PT_ERR_UNSUPPORTED at upload (IsAnimated).
+ * The accumulation buffer is NOT reset — the caller does that (Renderer::UpdateSceneData's
+ * `updated` flag, Renderer.cpp:240-241) with pt_render_begin.  Blocking. */
+PT_API pt_status pt_scene_update(pt_context *ctx, const pt_scene_update_desc *desc);
+
 /* Replaces Renderer::UpdateTexture(index) (PT/Renderer/Renderer.cpp:441-471): replace the
  * content of one texture slot (slot = PT_SCENE_TEXTURE_OFFSET + scene texture index). */
 PT_API pt_status pt_texture_upload(pt_context *ctx, uint32_t slot, const pt_texture_desc *texture);

@@ -26,6 +26,7 @@ ABI_SYMBOLS = [
     "pt_context_destroy",
     "pt_last_error",
     "pt_scene_upload",
+    "pt_scene_update",
     "pt_texture_upload",
     "pt_render_begin",
     "pt_render_samples",
@@ -61,6 +62,13 @@ class PostProcessParams(C.Structure):
     """pt_postprocess_params = Renderer::PostProcessSettings (Path-Tracing/Renderer/Renderer.h:68-73) + tone-mapping mode."""
 
     _fields_ = [("exposure", C.c_float), ("bloom_threshold", C.c_float), ("bloom_intensity", C.c_float), ("tone_mapping", C.c_uint32)]
+
+
+class SceneUpdateDesc(C.Structure):
+    """pt_scene_update_desc."""
+
+    _fields_ = [("instance_transforms", C.c_void_p), ("instance_count", C.c_uint32), ("point_lights", C.c_void_p),
+                ("point_light_count", C.c_uint32), ("directional_light", C.c_void_p)]
 
 
 TONE_MAPPING_SDR, TONE_MAPPING_HDR = 0, 1
@@ -145,6 +153,7 @@ def lib():
     L.pt_last_error.argtypes = [vp]
     L.pt_last_error.restype = C.c_char_p
     L.pt_scene_upload.argtypes = [vp, vp]
+    L.pt_scene_update.argtypes = [vp, vp]
     L.pt_texture_upload.argtypes = [vp, u32, vp]
     L.pt_render_begin.argtypes = [vp, u32, u32]
     L.pt_render_samples.argtypes = [vp, vp, u32, u32, vp, u32]
@@ -211,6 +220,27 @@ class Renderer:
         self.total_samples = 0
         if self.width:
             self.on_resize(self.width, self.height)
+
+    def update_scene(self, instance_transforms=None, point_lights=None, directional_light=None):
+        """The per-frame half of Renderer::UpdateSceneData for animated scenes (Scene::Update's outputs):
+        new instance transforms ((N, 12) float32, 3x4 row-major) re-bake the instances and rebuild the BVH;
+        point_lights (sc.POINT_LIGHT records) / directional_light (sc.DIRECTIONAL_LIGHT record) rewrite the
+        light block.  The accumulation is not reset — call on_resize() like the reference's `updated` flag."""
+        d = SceneUpdateDesc()
+        keep = []
+        if instance_transforms is not None:
+            t = np.ascontiguousarray(instance_transforms, np.float32).reshape(-1, 12)
+            keep.append(t)
+            d.instance_transforms, d.instance_count = t.ctypes.data, len(t)
+        if point_lights is not None:
+            pl = np.ascontiguousarray(point_lights, sc.POINT_LIGHT)
+            keep.append(pl)
+            d.point_lights, d.point_light_count = pl.ctypes.data, len(pl)
+        if directional_light is not None:
+            dl = np.ascontiguousarray(directional_light, sc.DIRECTIONAL_LIGHT).reshape(1)
+            keep.append(dl)
+            d.directional_light = dl.ctypes.data
+        self._check(self._L.pt_scene_update(self._h, C.addressof(d)))
 
     def upload_texture(self, slot: int, tex: sc.Texture):
         px = np.ascontiguousarray(tex.pixels)

@@ -700,65 +700,29 @@ void invert3x3(const double m[9], double out[9])
     out[8] = (m[0] * m[4] - m[1] * m[3]) * inv;
 }
 
-} // namespace
-
-void freeScene(Context *ctx)
+void freeAccel(Context *ctx)
 {
-    for (void *p : ctx->sceneAllocs)
+    for (void *p : ctx->accelAllocs)
         cudaFree(p);
-    ctx->sceneAllocs.clear();
-    ctx->hostTextures.clear();
-    ctx->hasScene = false;
-    ctx->scene = DeviceScene {};
+    ctx->accelAllocs.clear();
+    ctx->scene.nodes = nullptr;
+    ctx->scene.triPos = nullptr;
+    ctx->scene.triShade = nullptr;
 }
 
-pt_status uploadTextureSlot(Context *ctx, uint32_t slot, const pt_texture_desc *tex)
+// Bakes the flattened mesh instances into world-space triangles and builds the BVH over them, all
+// on the GPU, from the device-resident vertex / index buffers.  Replaces the previous triangle
+// streams and nodes of the scene (pt_scene_upload calls it once, pt_scene_update per changed frame).
+pt_status buildAccel(Context *ctx, const std::vector<MeshInstance> &mis, uint32_t n)
 {
-    if (!ctx->hasScene)
-        return fail(ctx, PT_ERR_NO_SCENE, "pt_texture_upload", "no scene uploaded");
-    if (!tex || slot >= ctx->hostTextures.size())
-        return fail(ctx, PT_ERR_INVALID_ARGUMENT, "pt_texture_upload", "slot out of range");
-    DevTexture t;
-    void *mem = nullptr;
-    const pt_status st = createTexture(ctx, *tex, t, &mem);
-    if (st != PT_OK)
-        return st;
-    // the old allocation stays owned by the scene until the next scene upload
-    ctx->sceneAllocs.push_back(mem);
-    ctx->hostTextures[slot] = t;
-    PT_CUDA_CHECK(ctx, cudaMemcpyAsync(const_cast<DevTexture *>(ctx->scene.textures) + slot, &t, sizeof(t),
-                                       cudaMemcpyHostToDevice, ctx->stream));
-    PT_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
-    return PT_OK;
-}
-
-pt_status uploadScene(Context *ctx, const pt_scene_desc *d)
-{
-    if (!d)
-        return fail(ctx, PT_ERR_INVALID_ARGUMENT, "pt_scene_upload", "scene is NULL");
-    if (d->point_light_count > PT_MAX_LIGHT_COUNT)
-        return fail(ctx, PT_ERR_INVALID_ARGUMENT, "pt_scene_upload", "more than 64 point lights");
-    if (d->transform_count == 0 || !d->transforms)
-        return fail(ctx, PT_ERR_INVALID_ARGUMENT, "pt_scene_upload", "transforms[0] (identity) is required");
-    if ((d->vertex_count && !d->vertices) || (d->index_count && !d->indices) || (d->geometry_count && !d->geometries) ||
-        (d->mesh_record_count && !d->mesh_records) || (d->model_count && !d->models) ||
-        (d->instance_count && !d->instances) || (d->texture_count && !d->textures))
-        return fail(ctx, PT_ERR_INVALID_ARGUMENT, "pt_scene_upload", "array pointer is NULL with a non-zero count");
-
-    freeScene(ctx);
-    std::vector<void *> &own = ctx->sceneAllocs;
+    freeAccel(ctx);
+    DeviceScene &s = ctx->scene;
     std::vector<void *> temp;
     auto freeTemp = [&]() {
         for (void *p : temp)
             cudaFree(p);
         temp.clear();
     };
-    cudaEvent_t ev0, ev1, ev2;
-    cudaEventCreate(&ev0);
-    cudaEventCreate(&ev1);
-    cudaEventCreate(&ev2);
-    cudaEventRecord(ev0, ctx->stream);
-
 #define PT_TRY(expr)                                                                                                  \
     do                                                                                                                \
     {                                                                                                                 \
@@ -766,200 +730,27 @@ pt_status uploadScene(Context *ctx, const pt_scene_desc *d)
         if (st__ != PT_OK)                                                                                            \
         {                                                                                                             \
             freeTemp();                                                                                               \
-            freeScene(ctx);                                                                                           \
             return st__;                                                                                              \
         }                                                                                                             \
     } while (0)
-
-    // ---- flatten instances x meshes (host, tiny) ------------------------------------------
-    std::vector<MeshInstance> mis;
-    uint64_t triTotal = 0;
-    bool hasAlpha = false;
-    for (uint32_t ii = 0; ii < d->instance_count; ii++)
-    {
-        const pt_instance &inst = d->instances[ii];
-        if (inst.model_index >= d->model_count)
-        {
-            freeTemp();
-            return fail(ctx, PT_ERR_INVALID_ARGUMENT, "pt_scene_upload", "instance.model_index out of range");
-        }
-        const pt_model &model = d->models[inst.model_index];
-        for (uint32_t mi = 0; mi < model.mesh_count; mi++)
-        {
-            if (model.mesh_offset + mi >= d->mesh_record_count)
-                return fail(ctx, PT_ERR_INVALID_ARGUMENT, "pt_scene_upload", "model mesh range out of range");
-            const pt_mesh_record &rec = d->mesh_records[model.mesh_offset + mi];
-            if (rec.geometry_index >= d->geometry_count || rec.transform_index >= d->transform_count)
-                return fail(ctx, PT_ERR_INVALID_ARGUMENT, "pt_scene_upload", "mesh record index out of range");
-            const pt_geometry &g = d->geometries[rec.geometry_index];
-            if ((uint64_t)g.index_offset + g.index_length > d->index_count ||
-                (uint64_t)g.vertex_offset + g.vertex_length > d->vertex_count)
-                return fail(ctx, PT_ERR_INVALID_ARGUMENT, "pt_scene_upload", "geometry range out of range");
-            const uint32_t type = rec.material_id & 0xffu, index = rec.material_id >> 8;
-            const uint32_t limit = type == 0 ? d->mr_material_count : type == 1 ? d->sg_material_count
-                                                                  : type == 2   ? d->phong_material_count
-                                                                                : 0xffffffffu;
-            if (index >= limit)
-                return fail(ctx, PT_ERR_INVALID_ARGUMENT, "pt_scene_upload", "material index out of range");
-            MeshInstance m = {};
-            // P = Instance * Mesh with the evaluation order of
-            // `mat4(transforms[i]) * gl_ObjectToWorld3x4EXT` (PT/Shaders/sampling.glsl:7)
-            const float *A = d->transforms + 12 * (size_t)rec.transform_index; // mesh, rows
-            const float *B = inst.transform;                                   // instance, rows
-            for (int j = 0; j < 3; j++)
-                for (int c = 0; c < 4; c++)
-                {
-                    float v = A[0 * 4 + c] * B[j * 4 + 0] + A[1 * 4 + c] * B[j * 4 + 1];
-                    v = v + A[2 * 4 + c] * B[j * 4 + 2];
-                    if (c == 3)
-                        v = v + 1.0f * B[j * 4 + 3];
-                    m.P[j * 4 + c] = v;
-                }
-            double R[9], Ri[9];
-            for (int j = 0; j < 3; j++)
-                for (int c = 0; c < 3; c++)
-                    R[j * 3 + c] = m.P[j * 4 + c];
-            invert3x3(R, Ri);
-            for (int j = 0; j < 3; j++)
-                for (int c = 0; c < 3; c++)
-                    m.N[j * 3 + c] = (float)Ri[c * 3 + j]; // inverse transpose
-            m.triOffset = (uint32_t)triTotal;
-            m.triCount = g.index_length / 3;
-            m.vertexOffset = g.vertex_offset;
-            m.indexOffset = g.index_offset;
-            m.instance = ii;
-            m.geometry = mi;
-            m.materialId = rec.material_id;
-            m.flags = g.is_opaque ? PT_TRI_FLAG_OPAQUE : 0u;
-            hasAlpha |= !g.is_opaque;
-            if (m.triCount == 0)
-                continue;
-            triTotal += m.triCount;
-            mis.push_back(m);
-        }
-    }
-    if (triTotal >= (1ull << 29))
-        return fail(ctx, PT_ERR_UNSUPPORTED, "pt_scene_upload", "more than 2^29 instanced triangles");
-    const uint32_t n = (uint32_t)triTotal;
-
-    // ---- materials, lights, LUT, textures -------------------------------------------------
-    DeviceScene &s = ctx->scene;
-    {
-        MaterialRaw *dm[3];
-        const void *src[3] = { d->mr_materials, d->sg_materials, d->phong_materials };
-        const uint32_t cnt[3] = { d->mr_material_count, d->sg_material_count, d->phong_material_count };
-        for (int k = 0; k < 3; k++)
-        {
-            PT_TRY(devAlloc(ctx, &dm[k], cnt[k], own));
-            if (cnt[k])
-                PT_CUDA_CHECK(ctx, cudaMemcpyAsync(dm[k], src[k], (size_t)cnt[k] * 96, cudaMemcpyHostToDevice, ctx->stream));
-            s.materials[k] = dm[k];
-        }
-        LightBlock lb = {};
-        lb.count = d->point_light_count;
-        lb.dirColor = make_float4(d->directional_light.color[0], d->directional_light.color[1], d->directional_light.color[2], 0);
-        lb.dirDirection = make_float4(d->directional_light.direction[0], d->directional_light.direction[1],
-                                      d->directional_light.direction[2], 0);
-        if (d->point_light_count)
-            std::memcpy(lb.point, d->point_lights, (size_t)d->point_light_count * 48);
-        LightBlock *dl;
-        PT_TRY(devAlloc(ctx, &dl, 1, own));
-        PT_CUDA_CHECK(ctx, cudaMemcpyAsync(dl, &lb, sizeof(lb), cudaMemcpyHostToDevice, ctx->stream));
-        PT_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream)); // lb is a stack object
-        s.lights = dl;
-        s.lut = ctx->dLut;
-    }
-    {
-        // built-in 1x1 textures, slots 0-8 (PT/Renderer/Renderer.cpp:127-173; texel values
-        // PT/Shaders/ShaderRendererTypes.incl:49-56; colour space per texture type).  Slot 8 is the
-        // reference's "placeholder" shown while uploads are pending; uploads here are synchronous.
-        static const uint32_t kDefaults[9] = { 0xffffffffu, 0xffff8080u, 0xffffffffu, 0xffffffffu, 0x00000000u,
-                                               0xffffffffu, 0x00000000u, 0x00000000u, 0xffffffffu };
-        static const bool kSrgb[9] = { true, false, false, false, true, true, false, false, true };
-        // the six faces of a cube sky follow the scene's textures in the same table
-        const uint32_t sceneSlots = PT_SCENE_TEXTURE_OFFSET + d->texture_count;
-        if (d->skybox_cube)
-            for (int f = 1; f < 6; f++)
-                if (d->skybox_cube[f].width != d->skybox_cube[0].width || d->skybox_cube[f].height != d->skybox_cube[0].height ||
-                    d->skybox_cube[f].format != d->skybox_cube[0].format)
-                    return fail(ctx, PT_ERR_INVALID_ARGUMENT, "pt_scene_upload", "cube sky faces differ in size or format");
-        ctx->hostTextures.resize(sceneSlots + (d->skybox_cube ? 6 : 0));
-        s.skyCubeSlot = d->skybox_cube ? sceneSlots : 0;
-        for (uint32_t i = 0; i < ctx->hostTextures.size(); i++)
-        {
-            const pt_texture_desc desc = i < PT_SCENE_TEXTURE_OFFSET ? defaultTexture(&kDefaults[i], kSrgb[i])
-                                         : i < sceneSlots            ? d->textures[i - PT_SCENE_TEXTURE_OFFSET]
-                                                                     : d->skybox_cube[i - sceneSlots];
-            void *mem = nullptr;
-            PT_TRY(createTexture(ctx, desc, ctx->hostTextures[i], &mem));
-            own.push_back(mem);
-        }
-        DevTexture *dt;
-        PT_TRY(devAlloc(ctx, &dt, ctx->hostTextures.size(), own));
-        PT_CUDA_CHECK(ctx, cudaMemcpyAsync(dt, ctx->hostTextures.data(), ctx->hostTextures.size() * sizeof(DevTexture),
-                                           cudaMemcpyHostToDevice, ctx->stream));
-        s.textures = dt;
-        s.textureCount = (uint32_t)ctx->hostTextures.size();
-        s.hasSky2D = 0;
-        if (d->skybox_2d)
-        {
-            void *mem = nullptr;
-            PT_TRY(createTexture(ctx, *d->skybox_2d, s.sky2D, &mem));
-            own.push_back(mem);
-            s.hasSky2D = 1;
-        }
-    }
-    // material texture indices must address existing slots
-    {
-        auto checkIdx = [&](uint32_t idx) { return idx < PT_SCENE_TEXTURE_OFFSET + d->texture_count; };
-        bool ok = true;
-        for (uint32_t i = 0; i < d->mr_material_count; i++)
-        {
-            const pt_material_mr &m = d->mr_materials[i];
-            ok &= checkIdx(m.emissive_idx) && checkIdx(m.color_idx) && checkIdx(m.normal_idx) && checkIdx(m.roughness_idx) &&
-                  checkIdx(m.metallic_idx);
-        }
-        for (int k = 0; k < 2; k++)
-        {
-            const pt_material_sg *arr = k == 0 ? d->sg_materials : d->phong_materials;
-            const uint32_t cnt = k == 0 ? d->sg_material_count : d->phong_material_count;
-            for (uint32_t i = 0; i < cnt; i++)
-                ok &= checkIdx(arr[i].emissive_idx) && checkIdx(arr[i].color_idx) && checkIdx(arr[i].normal_idx) &&
-                      checkIdx(arr[i].specular_idx) && checkIdx(arr[i].glossiness_idx);
-        }
-        if (!ok)
-        {
-            freeTemp();
-            freeScene(ctx);
-            return fail(ctx, PT_ERR_INVALID_ARGUMENT, "pt_scene_upload", "material texture index out of range");
-        }
-    }
-
     s.triCount = n;
-    s.hasAlpha = hasAlpha ? 1u : 0u;
     ctx->nodeCount = 0;
     ctx->bvhBytes = 0;
-    cudaEventRecord(ev1, ctx->stream);
-
     if (n > 0)
     {
         // ---- bake -------------------------------------------------------------------------
-        float *dVertices;
-        uint32_t *dIndices;
+        const float *dVertices = ctx->dVertices;
+        const uint32_t *dIndices = ctx->dIndices;
         MeshInstance *dMis;
         float4 *posUnsorted;
         TriShade *shadeUnsorted;
         Aabb *primBoxes;
         uint32_t *sceneBounds;
-        PT_TRY(devAlloc(ctx, &dVertices, (size_t)d->vertex_count * 14, temp));
-        PT_TRY(devAlloc(ctx, &dIndices, (size_t)d->index_count, temp));
         PT_TRY(devAlloc(ctx, &dMis, mis.size(), temp));
         PT_TRY(devAlloc(ctx, &posUnsorted, (size_t)n * 3, temp));
         PT_TRY(devAlloc(ctx, &shadeUnsorted, (size_t)n, temp));
         PT_TRY(devAlloc(ctx, &primBoxes, (size_t)n, temp));
         PT_TRY(devAlloc(ctx, &sceneBounds, 6, temp));
-        PT_CUDA_CHECK(ctx, cudaMemcpyAsync(dVertices, d->vertices, (size_t)d->vertex_count * 56, cudaMemcpyHostToDevice, ctx->stream));
-        PT_CUDA_CHECK(ctx, cudaMemcpyAsync(dIndices, d->indices, (size_t)d->index_count * 4, cudaMemcpyHostToDevice, ctx->stream));
         PT_CUDA_CHECK(ctx, cudaMemcpyAsync(dMis, mis.data(), mis.size() * sizeof(MeshInstance), cudaMemcpyHostToDevice, ctx->stream));
         const uint32_t boundsInit[6] = { 0xffffffffu, 0xffffffffu, 0xffffffffu, 0u, 0u, 0u };
         PT_CUDA_CHECK(ctx, cudaMemcpyAsync(sceneBounds, boundsInit, sizeof(boundsInit), cudaMemcpyHostToDevice, ctx->stream));
@@ -1044,7 +835,6 @@ pt_status uploadScene(Context *ctx, const pt_scene_desc *d)
                     if (h[1] == 0 || h[0] + h[1] != m || ++passes > 100000)
                     {
                         freeTemp();
-                        freeScene(ctx);
                         return fail(ctx, PT_ERR_CUDA, "pt_scene_upload", "PLOC made no progress (internal error)");
                     }
                     m = h[0];
@@ -1084,18 +874,299 @@ pt_status uploadScene(Context *ctx, const pt_scene_desc *d)
         // ---- final triangle streams, in leaf order ------------------------------------------------
         float4 *triPos;
         TriShade *triShade;
-        PT_TRY(devAlloc(ctx, &triPos, (size_t)n * 3, own));
-        PT_TRY(devAlloc(ctx, &triShade, (size_t)n, own));
+        PT_TRY(devAlloc(ctx, &triPos, (size_t)n * 3, ctx->accelAllocs));
+        PT_TRY(devAlloc(ctx, &triShade, (size_t)n, ctx->accelAllocs));
         k_gather<<<G, T, 0, ctx->stream>>>(order, n, posUnsorted, shadeUnsorted, triPos, triShade);
         s.triPos = triPos;
         s.triShade = triShade;
         BvhNode *nodes;
-        PT_TRY(devAlloc(ctx, &nodes, (size_t)wideCount, own));
+        PT_TRY(devAlloc(ctx, &nodes, (size_t)wideCount, ctx->accelAllocs));
         PT_CUDA_CHECK(ctx, cudaMemcpyAsync(nodes, wide, (size_t)wideCount * sizeof(BvhNode), cudaMemcpyDeviceToDevice, ctx->stream));
         s.nodes = nodes;
         ctx->nodeCount = wideCount;
         ctx->bvhBytes = (uint64_t)wideCount * sizeof(BvhNode) + (uint64_t)n * (48 + 144);
     }
+    PT_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+    PT_CUDA_CHECK(ctx, cudaGetLastError());
+    freeTemp();
+    return PT_OK;
+#undef PT_TRY
+}
+
+// Flattens instances x meshes into one MeshInstance per (instance, mesh) pair with its baked
+// object-to-world and normal matrices (host, tiny).
+pt_status flattenInstances(Context *ctx, const SceneTopology &t, std::vector<MeshInstance> &mis, bool &hasAlpha)
+{
+    mis.clear();
+    uint64_t triTotal = 0;
+    hasAlpha = false;
+    for (uint32_t ii = 0; ii < (uint32_t)t.instances.size(); ii++)
+    {
+        const pt_instance &inst = t.instances[ii];
+        if (inst.model_index >= t.models.size())
+            return fail(ctx, PT_ERR_INVALID_ARGUMENT, "pt_scene_upload", "instance.model_index out of range");
+        const pt_model &model = t.models[inst.model_index];
+        for (uint32_t mi = 0; mi < model.mesh_count; mi++)
+        {
+            if (model.mesh_offset + mi >= t.meshRecords.size())
+                return fail(ctx, PT_ERR_INVALID_ARGUMENT, "pt_scene_upload", "model mesh range out of range");
+            const pt_mesh_record &rec = t.meshRecords[model.mesh_offset + mi];
+            if (rec.geometry_index >= t.geometries.size() || rec.transform_index >= t.transforms.size() / 12)
+                return fail(ctx, PT_ERR_INVALID_ARGUMENT, "pt_scene_upload", "mesh record index out of range");
+            const pt_geometry &g = t.geometries[rec.geometry_index];
+            if ((uint64_t)g.index_offset + g.index_length > t.indexCount ||
+                (uint64_t)g.vertex_offset + g.vertex_length > t.vertexCount)
+                return fail(ctx, PT_ERR_INVALID_ARGUMENT, "pt_scene_upload", "geometry range out of range");
+            const uint32_t type = rec.material_id & 0xffu, index = rec.material_id >> 8;
+            const uint32_t limit = type == 0 ? t.materialCount[0] : type == 1 ? t.materialCount[1]
+                                                                  : type == 2   ? t.materialCount[2]
+                                                                                : 0xffffffffu;
+            if (index >= limit)
+                return fail(ctx, PT_ERR_INVALID_ARGUMENT, "pt_scene_upload", "material index out of range");
+            MeshInstance m = {};
+            // P = Instance * Mesh with the evaluation order of
+            // `mat4(transforms[i]) * gl_ObjectToWorld3x4EXT` (PT/Shaders/sampling.glsl:7)
+            const float *A = t.transforms.data() + 12 * (size_t)rec.transform_index; // mesh, rows
+            const float *B = inst.transform;                                   // instance, rows
+            for (int j = 0; j < 3; j++)
+                for (int c = 0; c < 4; c++)
+                {
+                    float v = A[0 * 4 + c] * B[j * 4 + 0] + A[1 * 4 + c] * B[j * 4 + 1];
+                    v = v + A[2 * 4 + c] * B[j * 4 + 2];
+                    if (c == 3)
+                        v = v + 1.0f * B[j * 4 + 3];
+                    m.P[j * 4 + c] = v;
+                }
+            double R[9], Ri[9];
+            for (int j = 0; j < 3; j++)
+                for (int c = 0; c < 3; c++)
+                    R[j * 3 + c] = m.P[j * 4 + c];
+            invert3x3(R, Ri);
+            for (int j = 0; j < 3; j++)
+                for (int c = 0; c < 3; c++)
+                    m.N[j * 3 + c] = (float)Ri[c * 3 + j]; // inverse transpose
+            m.triOffset = (uint32_t)triTotal;
+            m.triCount = g.index_length / 3;
+            m.vertexOffset = g.vertex_offset;
+            m.indexOffset = g.index_offset;
+            m.instance = ii;
+            m.geometry = mi;
+            m.materialId = rec.material_id;
+            m.flags = g.is_opaque ? PT_TRI_FLAG_OPAQUE : 0u;
+            hasAlpha |= !g.is_opaque;
+            if (m.triCount == 0)
+                continue;
+            triTotal += m.triCount;
+            mis.push_back(m);
+        }
+    }
+    if (triTotal >= (1ull << 29))
+        return fail(ctx, PT_ERR_UNSUPPORTED, "pt_scene_upload", "more than 2^29 instanced triangles");
+    return PT_OK;
+
+}
+
+} // namespace
+
+void freeScene(Context *ctx)
+{
+    freeAccel(ctx);
+    for (void *p : ctx->sceneAllocs)
+        cudaFree(p);
+    ctx->sceneAllocs.clear();
+    ctx->hostTextures.clear();
+    ctx->hasScene = false;
+    ctx->scene = DeviceScene {};
+}
+
+pt_status uploadTextureSlot(Context *ctx, uint32_t slot, const pt_texture_desc *tex)
+{
+    if (!ctx->hasScene)
+        return fail(ctx, PT_ERR_NO_SCENE, "pt_texture_upload", "no scene uploaded");
+    if (!tex || slot >= ctx->hostTextures.size())
+        return fail(ctx, PT_ERR_INVALID_ARGUMENT, "pt_texture_upload", "slot out of range");
+    DevTexture t;
+    void *mem = nullptr;
+    const pt_status st = createTexture(ctx, *tex, t, &mem);
+    if (st != PT_OK)
+        return st;
+    // the old allocation stays owned by the scene until the next scene upload
+    ctx->sceneAllocs.push_back(mem);
+    ctx->hostTextures[slot] = t;
+    PT_CUDA_CHECK(ctx, cudaMemcpyAsync(const_cast<DevTexture *>(ctx->scene.textures) + slot, &t, sizeof(t),
+                                       cudaMemcpyHostToDevice, ctx->stream));
+    PT_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+    return PT_OK;
+}
+
+pt_status uploadScene(Context *ctx, const pt_scene_desc *d)
+{
+    if (!d)
+        return fail(ctx, PT_ERR_INVALID_ARGUMENT, "pt_scene_upload", "scene is NULL");
+    if (d->point_light_count > PT_MAX_LIGHT_COUNT)
+        return fail(ctx, PT_ERR_INVALID_ARGUMENT, "pt_scene_upload", "more than 64 point lights");
+    if (d->transform_count == 0 || !d->transforms)
+        return fail(ctx, PT_ERR_INVALID_ARGUMENT, "pt_scene_upload", "transforms[0] (identity) is required");
+    if ((d->vertex_count && !d->vertices) || (d->index_count && !d->indices) || (d->geometry_count && !d->geometries) ||
+        (d->mesh_record_count && !d->mesh_records) || (d->model_count && !d->models) ||
+        (d->instance_count && !d->instances) || (d->texture_count && !d->textures))
+        return fail(ctx, PT_ERR_INVALID_ARGUMENT, "pt_scene_upload", "array pointer is NULL with a non-zero count");
+
+    freeScene(ctx);
+    std::vector<void *> &own = ctx->sceneAllocs;
+    std::vector<void *> temp;
+    auto freeTemp = [&]() {
+        for (void *p : temp)
+            cudaFree(p);
+        temp.clear();
+    };
+    cudaEvent_t ev0, ev1, ev2;
+    cudaEventCreate(&ev0);
+    cudaEventCreate(&ev1);
+    cudaEventCreate(&ev2);
+    cudaEventRecord(ev0, ctx->stream);
+
+#define PT_TRY(expr)                                                                                                  \
+    do                                                                                                                \
+    {                                                                                                                 \
+        const pt_status st__ = (expr);                                                                                \
+        if (st__ != PT_OK)                                                                                            \
+        {                                                                                                             \
+            freeTemp();                                                                                               \
+            freeScene(ctx);                                                                                           \
+            return st__;                                                                                              \
+        }                                                                                                             \
+    } while (0)
+
+    // ---- host copy of the instance / model / mesh tables (pt_scene_update re-flattens from them) ----
+    SceneTopology &topo = ctx->topo;
+    topo.instances.assign(d->instances, d->instances + d->instance_count);
+    topo.models.assign(d->models, d->models + d->model_count);
+    topo.meshRecords.assign(d->mesh_records, d->mesh_records + d->mesh_record_count);
+    topo.geometries.assign(d->geometries, d->geometries + d->geometry_count);
+    topo.transforms.assign(d->transforms, d->transforms + 12 * (size_t)d->transform_count);
+    topo.vertexCount = d->vertex_count;
+    topo.indexCount = d->index_count;
+    topo.materialCount[0] = d->mr_material_count;
+    topo.materialCount[1] = d->sg_material_count;
+    topo.materialCount[2] = d->phong_material_count;
+    std::vector<MeshInstance> mis;
+    bool hasAlpha = false;
+    PT_TRY(flattenInstances(ctx, topo, mis, hasAlpha));
+    const uint32_t n = mis.empty() ? 0u : mis.back().triOffset + mis.back().triCount;
+
+    // ---- materials, lights, LUT, textures -------------------------------------------------
+    DeviceScene &s = ctx->scene;
+    {
+        MaterialRaw *dm[3];
+        const void *src[3] = { d->mr_materials, d->sg_materials, d->phong_materials };
+        const uint32_t cnt[3] = { d->mr_material_count, d->sg_material_count, d->phong_material_count };
+        for (int k = 0; k < 3; k++)
+        {
+            PT_TRY(devAlloc(ctx, &dm[k], cnt[k], own));
+            if (cnt[k])
+                PT_CUDA_CHECK(ctx, cudaMemcpyAsync(dm[k], src[k], (size_t)cnt[k] * 96, cudaMemcpyHostToDevice, ctx->stream));
+            s.materials[k] = dm[k];
+        }
+        LightBlock &lb = ctx->hostLights;
+        lb = LightBlock {};
+        lb.count = d->point_light_count;
+        lb.dirColor = make_float4(d->directional_light.color[0], d->directional_light.color[1], d->directional_light.color[2], 0);
+        lb.dirDirection = make_float4(d->directional_light.direction[0], d->directional_light.direction[1],
+                                      d->directional_light.direction[2], 0);
+        if (d->point_light_count)
+            std::memcpy(lb.point, d->point_lights, (size_t)d->point_light_count * 48);
+        LightBlock *dl;
+        PT_TRY(devAlloc(ctx, &dl, 1, own));
+        PT_CUDA_CHECK(ctx, cudaMemcpyAsync(dl, &lb, sizeof(lb), cudaMemcpyHostToDevice, ctx->stream));
+        PT_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+        s.lights = dl;
+        s.lut = ctx->dLut;
+    }
+    {
+        // built-in 1x1 textures, slots 0-8 (PT/Renderer/Renderer.cpp:127-173; texel values
+        // PT/Shaders/ShaderRendererTypes.incl:49-56; colour space per texture type).  Slot 8 is the
+        // reference's "placeholder" shown while uploads are pending; uploads here are synchronous.
+        static const uint32_t kDefaults[9] = { 0xffffffffu, 0xffff8080u, 0xffffffffu, 0xffffffffu, 0x00000000u,
+                                               0xffffffffu, 0x00000000u, 0x00000000u, 0xffffffffu };
+        static const bool kSrgb[9] = { true, false, false, false, true, true, false, false, true };
+        // the six faces of a cube sky follow the scene's textures in the same table
+        const uint32_t sceneSlots = PT_SCENE_TEXTURE_OFFSET + d->texture_count;
+        if (d->skybox_cube)
+            for (int f = 1; f < 6; f++)
+                if (d->skybox_cube[f].width != d->skybox_cube[0].width || d->skybox_cube[f].height != d->skybox_cube[0].height ||
+                    d->skybox_cube[f].format != d->skybox_cube[0].format)
+                    return fail(ctx, PT_ERR_INVALID_ARGUMENT, "pt_scene_upload", "cube sky faces differ in size or format");
+        ctx->hostTextures.resize(sceneSlots + (d->skybox_cube ? 6 : 0));
+        s.skyCubeSlot = d->skybox_cube ? sceneSlots : 0;
+        for (uint32_t i = 0; i < ctx->hostTextures.size(); i++)
+        {
+            const pt_texture_desc desc = i < PT_SCENE_TEXTURE_OFFSET ? defaultTexture(&kDefaults[i], kSrgb[i])
+                                         : i < sceneSlots            ? d->textures[i - PT_SCENE_TEXTURE_OFFSET]
+                                                                     : d->skybox_cube[i - sceneSlots];
+            void *mem = nullptr;
+            PT_TRY(createTexture(ctx, desc, ctx->hostTextures[i], &mem));
+            own.push_back(mem);
+        }
+        DevTexture *dt;
+        PT_TRY(devAlloc(ctx, &dt, ctx->hostTextures.size(), own));
+        PT_CUDA_CHECK(ctx, cudaMemcpyAsync(dt, ctx->hostTextures.data(), ctx->hostTextures.size() * sizeof(DevTexture),
+                                           cudaMemcpyHostToDevice, ctx->stream));
+        s.textures = dt;
+        s.textureCount = (uint32_t)ctx->hostTextures.size();
+        s.hasSky2D = 0;
+        if (d->skybox_2d)
+        {
+            void *mem = nullptr;
+            PT_TRY(createTexture(ctx, *d->skybox_2d, s.sky2D, &mem));
+            own.push_back(mem);
+            s.hasSky2D = 1;
+        }
+    }
+    // material texture indices must address existing slots
+    {
+        auto checkIdx = [&](uint32_t idx) { return idx < PT_SCENE_TEXTURE_OFFSET + d->texture_count; };
+        bool ok = true;
+        for (uint32_t i = 0; i < d->mr_material_count; i++)
+        {
+            const pt_material_mr &m = d->mr_materials[i];
+            ok &= checkIdx(m.emissive_idx) && checkIdx(m.color_idx) && checkIdx(m.normal_idx) && checkIdx(m.roughness_idx) &&
+                  checkIdx(m.metallic_idx);
+        }
+        for (int k = 0; k < 2; k++)
+        {
+            const pt_material_sg *arr = k == 0 ? d->sg_materials : d->phong_materials;
+            const uint32_t cnt = k == 0 ? d->sg_material_count : d->phong_material_count;
+            for (uint32_t i = 0; i < cnt; i++)
+                ok &= checkIdx(arr[i].emissive_idx) && checkIdx(arr[i].color_idx) && checkIdx(arr[i].normal_idx) &&
+                      checkIdx(arr[i].specular_idx) && checkIdx(arr[i].glossiness_idx);
+        }
+        if (!ok)
+        {
+            freeTemp();
+            freeScene(ctx);
+            return fail(ctx, PT_ERR_INVALID_ARGUMENT, "pt_scene_upload", "material texture index out of range");
+        }
+    }
+
+    s.triCount = n;
+    s.hasAlpha = hasAlpha ? 1u : 0u;
+    // vertices and indices stay on the device: pt_scene_update re-bakes from them
+    {
+        float *dVertices;
+        uint32_t *dIndices;
+        PT_TRY(devAlloc(ctx, &dVertices, (size_t)d->vertex_count * 14, own));
+        PT_TRY(devAlloc(ctx, &dIndices, (size_t)d->index_count, own));
+        if (d->vertex_count)
+            PT_CUDA_CHECK(ctx, cudaMemcpyAsync(dVertices, d->vertices, (size_t)d->vertex_count * 56, cudaMemcpyHostToDevice, ctx->stream));
+        if (d->index_count)
+            PT_CUDA_CHECK(ctx, cudaMemcpyAsync(dIndices, d->indices, (size_t)d->index_count * 4, cudaMemcpyHostToDevice, ctx->stream));
+        PT_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+        ctx->dVertices = dVertices;
+        ctx->dIndices = dIndices;
+    }
+    cudaEventRecord(ev1, ctx->stream);
+    PT_TRY(buildAccel(ctx, mis, n));
     cudaEventRecord(ev2, ctx->stream);
     PT_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
     PT_CUDA_CHECK(ctx, cudaGetLastError());
@@ -1106,8 +1177,75 @@ pt_status uploadScene(Context *ctx, const pt_scene_desc *d)
     cudaEventDestroy(ev1);
     cudaEventDestroy(ev2);
     ctx->hasScene = true;
+    ctx->sceneUpdates = 0;
     return PT_OK;
 #undef PT_TRY
+}
+
+// Scene::Update's per-frame outputs (PT/Scene.cpp:52-83: instance transforms, point-light positions,
+// directional-light direction) applied to the uploaded scene.  The reference refits its BLASes and
+// TLAS in place (AccelerationStructure::RecordUpdateCommands, AccelerationStructure.cpp:48-57); here
+// the instances are re-baked and the BVH is REBUILT on the GPU — a full PLOC build of a few million
+// triangles costs about as much as one sample per pixel, and a fresh tree keeps its quality however
+// far the instances move.
+pt_status updateScene(Context *ctx, const pt_scene_update_desc *d)
+{
+    if (!d)
+        return fail(ctx, PT_ERR_INVALID_ARGUMENT, "pt_scene_update", "desc is NULL");
+    if (!ctx->hasScene)
+        return fail(ctx, PT_ERR_NO_SCENE, "pt_scene_update", "no scene uploaded");
+    if (d->instance_transforms && d->instance_count != ctx->topo.instances.size())
+        return fail(ctx, PT_ERR_INVALID_ARGUMENT, "pt_scene_update", "instance_count differs from the uploaded scene");
+    if (d->point_lights && d->point_light_count > PT_MAX_LIGHT_COUNT)
+        return fail(ctx, PT_ERR_INVALID_ARGUMENT, "pt_scene_update", "more than 64 point lights");
+    PT_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+    if (d->point_lights || d->directional_light)
+    {
+        LightBlock &lb = ctx->hostLights;
+        if (d->point_lights)
+        {
+            lb.count = d->point_light_count;
+            if (d->point_light_count)
+                std::memcpy(lb.point, d->point_lights, (size_t)d->point_light_count * 48);
+        }
+        if (d->directional_light)
+        {
+            lb.dirColor = make_float4(d->directional_light->color[0], d->directional_light->color[1], d->directional_light->color[2], 0);
+            lb.dirDirection = make_float4(d->directional_light->direction[0], d->directional_light->direction[1],
+                                          d->directional_light->direction[2], 0);
+        }
+        PT_CUDA_CHECK(ctx, cudaMemcpyAsync(const_cast<LightBlock *>(ctx->scene.lights), &lb, sizeof(lb), cudaMemcpyHostToDevice, ctx->stream));
+        PT_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    if (d->instance_transforms)
+    {
+        for (uint32_t i = 0; i < d->instance_count; i++)
+            std::memcpy(ctx->topo.instances[i].transform, d->instance_transforms + 12 * (size_t)i, 48);
+        std::vector<MeshInstance> mis;
+        bool hasAlpha = false;
+        pt_status st = flattenInstances(ctx, ctx->topo, mis, hasAlpha);
+        if (st != PT_OK)
+            return st;
+        const uint32_t n = mis.empty() ? 0u : mis.back().triOffset + mis.back().triCount;
+        cudaEvent_t ev0, ev1;
+        cudaEventCreate(&ev0);
+        cudaEventCreate(&ev1);
+        cudaEventRecord(ev0, ctx->stream);
+        st = buildAccel(ctx, mis, n);
+        cudaEventRecord(ev1, ctx->stream);
+        cudaEventSynchronize(ev1);
+        if (st == PT_OK)
+            cudaEventElapsedTime(&ctx->bvhBuildMs, ev0, ev1);
+        cudaEventDestroy(ev0);
+        cudaEventDestroy(ev1);
+        if (st != PT_OK)
+        {
+            freeScene(ctx); // the old tree is gone and the new one failed: nothing left to render
+            return st;
+        }
+    }
+    ctx->sceneUpdates++;
+    return PT_OK;
 }
 
 } // namespace pt

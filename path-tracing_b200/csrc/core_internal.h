@@ -81,6 +81,18 @@ struct PathState
 
 #define PT_MAX_POOLS 8
 
+// host copy of the tables instances are flattened from (kept for pt_scene_update)
+struct SceneTopology
+{
+    std::vector<pt_instance> instances;
+    std::vector<pt_model> models;
+    std::vector<pt_mesh_record> meshRecords;
+    std::vector<pt_geometry> geometries;
+    std::vector<float> transforms; // 12 per mesh transform
+    uint64_t vertexCount = 0, indexCount = 0;
+    uint32_t materialCount[3] = { 0, 0, 0 };
+};
+
 struct Context
 {
     int device = 0;
@@ -92,7 +104,13 @@ struct Context
     // scene
     bool hasScene = false;
     DeviceScene scene = {};
-    std::vector<void *> sceneAllocs; // everything cudaMalloc'ed for the scene
+    std::vector<void *> sceneAllocs; // everything cudaMalloc'ed for the scene ...
+    std::vector<void *> accelAllocs; // ... except the triangle streams + BVH, which pt_scene_update rebuilds
+    SceneTopology topo;
+    const float *dVertices = nullptr;    // the reference's vertex buffer, 14 floats per vertex
+    const uint32_t *dIndices = nullptr;
+    LightBlock hostLights = {};
+    uint32_t sceneUpdates = 0;
     std::vector<DevTexture> hostTextures;
     uint64_t texelArenaBytes = 0;
     uint64_t nodeCount = 0, bvhBytes = 0;
@@ -146,6 +164,7 @@ pt_status fail(Context *ctx, pt_status code, const char *what, const char *detai
 pt_status uploadScene(Context *ctx, const pt_scene_desc *desc);
 void freeScene(Context *ctx);
 pt_status uploadTextureSlot(Context *ctx, uint32_t slot, const pt_texture_desc *tex);
+pt_status updateScene(Context *ctx, const pt_scene_update_desc *desc);
 
 // wavefront.cu
 pt_status allocSortTemp(Context *ctx, size_t slots);

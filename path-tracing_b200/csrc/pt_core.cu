@@ -283,6 +283,14 @@ pt_status pt_readback(pt_context *ctx, float *out_rgba, size_t out_bytes)
     return PT_OK;
 }
 
+pt_status pt_scene_update(pt_context *ctx, const pt_scene_update_desc *desc)
+{
+    if (!ctx)
+        return PT_ERR_INVALID_ARGUMENT;
+    cudaSetDevice(ctx->device);
+    return updateScene(ctx, desc);
+}
+
 pt_status pt_postprocess(pt_context *ctx, const pt_postprocess_params *params, uint32_t total_samples,
                          uint32_t output_format, void *out_pixels, size_t out_bytes)
 {

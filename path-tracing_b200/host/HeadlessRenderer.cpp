@@ -43,7 +43,30 @@ void HeadlessRenderer::UpdateSceneData(const std::shared_ptr<Scene> &scene, bool
         ResetAccumulation();
 
     if (m_Scene == scene)
+    {
+        /* Renderer::Render's per-frame work for animated scenes: the light uniform rewrite
+         * (Renderer.cpp:1719-1726) and AccelerationStructure::RecordUpdateCommands (:1753-1754),
+         * fed by what Scene::Update moved (Scene.cpp:52-83). */
+        if (updated && scene->HasAnimations())
+        {
+            std::vector<float> transforms;
+            for (const ModelInstance &instance : scene->GetModelInstances())
+            {
+                const float *m = reinterpret_cast<const float *>(&instance.Transform);
+                transforms.insert(transforms.end(), m, m + 12);
+            }
+            const auto lights = scene->GetPointLights();
+            const Shaders::DirectionalLight directional = scene->GetDirectionalLight();
+            pt_scene_update_desc update = {};
+            update.instance_transforms = transforms.data();
+            update.instance_count = static_cast<uint32_t>(transforms.size() / 12);
+            update.point_lights = reinterpret_cast<const pt_point_light *>(lights.data());
+            update.point_light_count = static_cast<uint32_t>(lights.size());
+            update.directional_light = reinterpret_cast<const pt_directional_light *>(&directional);
+            Check(pt_scene_update(m_Context, &update), "pt_scene_update");
+        }
         return;
+    }
 
     m_Scene = scene;
     const auto flat = FlattenScene(*scene);
