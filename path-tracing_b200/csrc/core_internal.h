@@ -142,7 +142,7 @@ struct Context
     void *sortTemp = nullptr;   // CUB radix-sort scratch for slotCapacity pairs
     size_t sortTempBytes = 0;
 
-    uint32_t poolCount = 8;     // independent sub-wavefronts (PT_POOLS)
+    uint32_t poolCount = 2;     // independent sub-wavefronts (PT_POOLS); 2 measured best once k_extend regenerates paths
     cudaStream_t poolStreams[PT_MAX_POOLS] = {};
     cudaEvent_t evRound = nullptr;
 

@@ -207,8 +207,13 @@ PT_DEV void intersectNode(const BvhNode *__restrict__ node, const RaySetup &r, f
         c[j] = tc;                                                                                                    \
     }
 
+// cur value "take the next entry off the stack": popping is a step of the state machine of its own
+// (popStep), executed by all lanes of a warp together, instead of a loop inside whichever lane
+// runs dry — that loop ran with 4 of 32 lanes active and a dependent local-memory load per trip.
+#define PT_CHILD_POP 0x7ffffffe
+
 // Per-lane traversal state machine.  `cur` is the next thing to do: an internal node (>= 0), a
-// leaf (< 0) or PT_CHILD_EMPTY = finished.  The kernels drive it either as a plain per-thread
+// leaf (< 0), PT_CHILD_POP = fetch the next stack entry, or PT_CHILD_EMPTY = finished.  The kernels drive it either as a plain per-thread
 // loop (traverse(), standalone queries) or warp-synchronously with dynamic ray fetch (wavefront).
 //   CLOSEST = true : nearest hit (+ decal record if ALPHA)
 //   CLOSEST = false: any hit in (tmin, tmax) with alpha >= 1 -> hit.tri != miss
@@ -231,7 +236,8 @@ template <bool CLOSEST, bool ALPHA, bool STATS> struct Traverser
 
     PT_DEV bool finished() const { return cur == PT_CHILD_EMPTY && leaf == PT_CHILD_EMPTY; }
     PT_DEV bool hasLeaf() const { return leaf != PT_CHILD_EMPTY; }
-    PT_DEV bool atInternal() const { return (unsigned)cur < (unsigned)PT_CHILD_EMPTY; }
+    PT_DEV bool atInternal() const { return (unsigned)cur < (unsigned)PT_CHILD_POP; }
+    PT_DEV bool needsPop() const { return cur == PT_CHILD_POP; }
 
     PT_DEV void begin(const DeviceScene &s, vec3 org, vec3 dir, float tmin_, float tmax_)
     {
@@ -258,21 +264,20 @@ template <bool CLOSEST, bool ALPHA, bool STATS> struct Traverser
         r = setupRay(org, dir);
     }
 
-    // pop, skipping sub-trees that start beyond the current best (ties are kept)
-    PT_DEV void pop()
+    // One stack entry, if the lane asked for it: sub-trees that start beyond the current best are
+    // dropped (ties are kept) and the lane asks again.
+    PT_DEV void popStep()
     {
-        for (;;)
+        if (cur != PT_CHILD_POP)
+            return;
+        if (sp == 0)
         {
-            if (sp == 0)
-            {
-                cur = PT_CHILD_EMPTY;
-                return;
-            }
-            const unsigned long long e = stack[--sp];
-            cur = (int)(uint32_t)e;
-            if (!CLOSEST || __uint_as_float((uint32_t)(e >> 32)) <= best)
-                return;
+            cur = PT_CHILD_EMPTY;
+            return;
         }
+        const unsigned long long e = stack[--sp];
+        if (!CLOSEST || __uint_as_float((uint32_t)(e >> 32)) <= best)
+            cur = (int)(uint32_t)e;
     }
 
     PT_DEV void push(int node, float dist)
@@ -300,7 +305,7 @@ template <bool CLOSEST, bool ALPHA, bool STATS> struct Traverser
         PT_CSWAP(1, 2)
         if (d[0] == INFINITY)
         {
-            pop();
+            cur = PT_CHILD_POP;
             return;
         }
         cur = c[0];
@@ -352,7 +357,7 @@ template <bool CLOSEST, bool ALPHA, bool STATS> struct Traverser
 #if PT_PREFETCH_LEAF
             prefetchL1(sPrefetchTri + 3 * (size_t)(((uint32_t)~cur) >> 2));
 #endif
-            pop();
+            cur = PT_CHILD_POP;
         }
     }
 
@@ -422,7 +427,7 @@ template <bool CLOSEST, bool ALPHA, bool STATS> struct Traverser
             if (cur < 0)
             {
                 leaf = cur;
-                pop();
+                cur = PT_CHILD_POP;
             }
         }
     }
@@ -440,9 +445,14 @@ PT_DEV void traverse(const DeviceScene &s, vec3 org, vec3 dir, float tmin, float
     tr.begin(s, org, dir, tmin, tmax);
     while (!tr.finished())
     {
-        while (tr.atInternal())
-            tr.nodeStep(s);
+        while (tr.atInternal() || tr.needsPop())
+        {
+            if (tr.atInternal())
+                tr.nodeStep(s);
+            tr.popStep();
+        }
         tr.postponeLeaf(s.triPos);
+        tr.popStep();
         tr.leafStep(s);
     }
     hit = tr.hit;
@@ -611,7 +621,8 @@ PT_DEV void tracePersistent(const DeviceScene &s, uint32_t n, uint32_t *workCoun
                 if (tr.atInternal())
                     tr.nodeStep(s);
                 tr.postponeLeaf(s.triPos);
-            } while (__any_sync(FULL, tr.atInternal() && !tr.hasLeaf()));
+                tr.popStep();
+            } while (__any_sync(FULL, (tr.atInternal() || tr.needsPop()) && !tr.hasLeaf()));
             tr.leafStep(s);
             if (!drain)
             {
