@@ -12,6 +12,16 @@ namespace pt
 {
 
 #define PT_STACK_SIZE 64
+// PT_SMEM_STACK > 0 puts the first PT_SMEM_STACK entries of a wavefront lane's traversal stack in SHARED
+// memory, laid out [entry][thread] (64-bit words: conflict-free whatever the lanes' depths), deeper
+// entries in the local-memory array.  Measured on the B200 (chess / street / atrium, 8 blocks per SM):
+// 8 entries = no change, 16 entries = 1-3 % SLOWER, 24 entries = 8 % slower in k_extend — the hot top of
+// a local-memory stack already sits in L1, and the shared-memory carve-out takes that L1 away from
+// the BVH nodes.  Off by default.
+#ifndef PT_SMEM_STACK
+#define PT_SMEM_STACK 0
+#endif
+#define PT_TRACE_THREADS 128
 
 // tuning switches (A/B-tested on the B200)
 #ifndef PT_PREFETCH_LEAF
@@ -217,9 +227,10 @@ PT_DEV void intersectNode(const BvhNode *__restrict__ node, const RaySetup &r, f
 // loop (traverse(), standalone queries) or warp-synchronously with dynamic ray fetch (wavefront).
 //   CLOSEST = true : nearest hit (+ decal record if ALPHA)
 //   CLOSEST = false: any hit in (tmin, tmax) with alpha >= 1 -> hit.tri != miss
-template <bool CLOSEST, bool ALPHA, bool STATS> struct Traverser
+template <bool CLOSEST, bool ALPHA, bool STATS, int SMEM = 0> struct Traverser
 {
     static constexpr bool kClosest = CLOSEST, kAlpha = ALPHA, kStats = STATS;
+    unsigned long long *sstack; // this thread's column of the block's shared stack (SMEM > 0)
     RaySetup r;
     float tmin, tmax, best;
     uint32_t bestFlat;
@@ -275,15 +286,30 @@ template <bool CLOSEST, bool ALPHA, bool STATS> struct Traverser
             cur = PT_CHILD_EMPTY;
             return;
         }
-        const unsigned long long e = stack[--sp];
+        const unsigned long long e = take();
         if (!CLOSEST || __uint_as_float((uint32_t)(e >> 32)) <= best)
             cur = (int)(uint32_t)e;
     }
 
+    // removes and returns the top entry (sp > 0)
+    PT_DEV unsigned long long take()
+    {
+        --sp;
+        if (SMEM > 0 && sp < SMEM)
+            return sstack[sp * PT_TRACE_THREADS];
+        return stack[sp - SMEM];
+    }
+
     PT_DEV void push(int node, float dist)
     {
-        if (sp < PT_STACK_SIZE)
-            stack[sp++] = ((unsigned long long)__float_as_uint(dist) << 32) | (uint32_t)node;
+        const unsigned long long e = ((unsigned long long)__float_as_uint(dist) << 32) | (uint32_t)node;
+        if (SMEM > 0 && sp < SMEM)
+            sstack[sp++ * PT_TRACE_THREADS] = e;
+        else if (sp < PT_STACK_SIZE + SMEM)
+        {
+            stack[sp - SMEM] = e;
+            sp++;
+        }
     }
 
     // cur is an internal node: test its children, descend into the nearest, push the others
@@ -695,7 +721,7 @@ PT_DEV void tracePersistent(const DeviceScene &s, uint32_t n, uint32_t *workCoun
                 idleLanes &= idleLanes - 1;
                 unsigned long long e = 0;
                 if ((int)lane == donor)
-                    e = tr.stack[--tr.sp];
+                    e = tr.take();
                 e = __shfl_sync(FULL, e, donor);
                 RaySetup r;
                 r.org.x = __shfl_sync(FULL, tr.r.org.x, donor), r.org.y = __shfl_sync(FULL, tr.r.org.y, donor);

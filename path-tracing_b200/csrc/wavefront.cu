@@ -241,8 +241,10 @@ template <bool ALPHA, bool STATS> __global__ void __launch_bounds__(128, PT_TRAC
     uint32_t hits = 0, rays = 0, samples = 0, restarts = 0;
     uint32_t *regenOut = cur ? rc.ps.regenQ[0] : rc.ps.regenQ[1];
     unsigned long long stack[PT_STACK_SIZE];
-    Traverser<true, ALPHA, STATS> tr;
+    __shared__ unsigned long long sharedStack[(PT_SMEM_STACK > 0 ? PT_SMEM_STACK : 1) * PT_TRACE_THREADS];
+    Traverser<true, ALPHA, STATS, PT_SMEM_STACK> tr;
     tr.stack = stack;
+    tr.sstack = sharedStack + threadIdx.x;
     tr.st = TraversalStats { 0, 0, 0 };
     tracePersistent(
         rc.scene, n, &rc.qc->extendWork, tr, 0.00001f,
@@ -258,7 +260,7 @@ template <bool ALPHA, bool STATS> __global__ void __launch_bounds__(128, PT_TRAC
             p.tmax = 10000.0f;
             return p;
         },
-        [&](Traverser<true, ALPHA, STATS> &t, uint32_t slot) {
+        [&](Traverser<true, ALPHA, STATS, PT_SMEM_STACK> &t, uint32_t slot) {
             rays++;
             if (t.hit.tri == 0xffffffffu)
             {
@@ -618,8 +620,10 @@ template <bool ALPHA, bool STATS> __global__ void __launch_bounds__(128, PT_TRAC
         rc.qc->hit = 0;
     }
     unsigned long long stack[PT_STACK_SIZE];
-    Traverser<false, ALPHA, STATS> tr;
+    __shared__ unsigned long long sharedStack[(PT_SMEM_STACK > 0 ? PT_SMEM_STACK : 1) * PT_TRACE_THREADS];
+    Traverser<false, ALPHA, STATS, PT_SMEM_STACK> tr;
     tr.stack = stack;
+    tr.sstack = sharedStack + threadIdx.x;
     tr.st = TraversalStats { 0, 0, 0 };
     tracePersistent(
         rc.scene, n, &rc.qc->shadowWork, tr, 0.00001f,
@@ -633,7 +637,7 @@ template <bool ALPHA, bool STATS> __global__ void __launch_bounds__(128, PT_TRAC
             p.tmax = o.w;
             return p;
         },
-        [&](Traverser<false, ALPHA, STATS> &t, uint32_t slot) {
+        [&](Traverser<false, ALPHA, STATS, PT_SMEM_STACK> &t, uint32_t slot) {
             if (t.hit.tri == 0xffffffffu)
             {
                 const float4 c = rc.ps.rec[slot].shC;
