@@ -38,6 +38,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+POOLS = int(os.environ.get("PT_POOLS", "2"))  # the library's default (core_internal.h: Context::poolCount)
 METRIC = "Mrays/s (closest-hit + occlusion rays; path samples/s alongside), 1080p, depth 8"
 
 
@@ -421,7 +422,8 @@ def run_ours(args):
             "partition": "none" if world == 1 else args.partition,
             "l2": f"working set (path state of 8 M paths in flight 2 GB + sample buffer up to 8 GB + triangles/BVH "
                   f"{build_stats['bvh_bytes'] / 1e9:.2f} GB + textures) exceeds the 126 MB L2 many times over; no explicit flush",
-            "scheduling": "8 M path slots in 8 wavefront pools on 8 CUDA streams, hits shaded in triangle order",
+            "scheduling": f"8 M path slots in {POOLS} wavefront pools on {POOLS} CUDA streams, paths regenerated inside k_extend, "
+                          "hits shaded in triangle order",
             "bvh_build_ms": build_stats["bvh_build_ms"],
             "scene_upload_ms": build_stats["scene_upload_ms"],
         },
@@ -430,7 +432,7 @@ def run_ours(args):
             "bound": "hbm",
             "kernel": f"k_{dominant}",
             "timing": "CUDA events on the launching stream around every launch of a separate, identical render with ONE "
-                      "wavefront pool (kernels of different pools overlap otherwise); value/ms_per_step come from the 8-pool runs",
+                      f"wavefront pool (kernels of different pools overlap otherwise); value/ms_per_step come from the {POOLS}-pool runs",
             "achieved": kernels[dominant]["achieved_gbs"],
             "peak": peak,
             "unit": "GB/s",
