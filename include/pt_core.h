@@ -168,20 +168,29 @@ typedef struct pt_point_light {
 #define PT_SCENE_TEXTURE_OFFSET 9u   /* PT/Shaders/ShaderTypes.incl:27; slots 0-8 are built in */
 
 enum {
-    PT_TEXTURE_RGBA8 = 0,  /* TextureFormat::RGBAU8,  PT/Scene.h:35-42 */
-    PT_TEXTURE_RGBAF32 = 1 /* TextureFormat::RGBAF32 */
+    PT_TEXTURE_RGBA8 = 0,   /* TextureFormat::RGBAU8,  PT/Scene.h:35-42 */
+    PT_TEXTURE_RGBAF32 = 1, /* TextureFormat::RGBAF32 */
+    PT_TEXTURE_BC1 = 2,     /* TextureFormat::BC1: DXT1 blocks (8 B per 4x4), 1-bit alpha          */
+    PT_TEXTURE_BC3 = 3,     /* TextureFormat::BC3: DXT5 blocks (16 B), always sampled as sRGB       */
+    PT_TEXTURE_BC5 = 4      /* TextureFormat::BC5: ATI2N blocks (16 B), two channels, sampled (r, g, 0, 1) */
 };
 
 /* One decoded level-0 image (what TextureImporter::LoadTextureData returns,
  * PT/TextureImporter.cpp:413-424).  The core builds the full mip chain itself
- * (PT/Renderer/Image.cpp:14-17,264-305).  srgb follows the reference's rule
+ * (PT/Renderer/Image.cpp:14-17,264-305); block-compressed images are decoded to
+ * RGBA8 on the GPU at upload, level by level.  srgb follows the reference's rule
  * Color/Specular/Emissive/Skybox => sRGB (PT/Renderer/TextureUploader.cpp:571-595). */
 typedef struct pt_texture_desc {
     uint32_t width;
     uint32_t height;
     uint32_t format; /* PT_TEXTURE_* */
-    uint32_t srgb;   /* RGBA8 only */
+    uint32_t srgb;   /* RGBA8 and BC1 (BC3 is always sRGB, BC5 and float never: TextureUploader.cpp:571-595) */
     const void *pixels;
+    /* Block-compressed formats only: number of mip levels stored in `pixels`, level 0 first, tightly
+     * packed, exactly as TextureImporter's gli loader concatenates a .dds file
+     * (PT/TextureImporter.cpp:311-343).  Mips of compressed textures are never generated
+     * (TextureUploader.cpp:420-456): the sampler clamps to the last stored level.  0 means 1. */
+    uint32_t levels;
 } pt_texture_desc;
 
 enum {

@@ -763,8 +763,121 @@ void buildMips(Texture &t)
     }
 }
 
+/* Block-compressed formats (TextureFormat::BC1 / BC3 / BC5, PT/Scene.h:35-42; VK_FORMAT_BC1_RGBA /
+ * BC3 / BC5 in PT/Renderer/TextureUploader.cpp:586-591), decoded per the format definition: 565
+ * endpoints expanded by bit replication, interpolated palette entries = the exact rationals rounded
+ * to the nearest 8-bit value.  PARITY UNPINNED: the reference leaves decoding to the sampler
+ * hardware, whose interpolation precision is implementation-defined. */
+void bcAlphaBlock(const uint8_t *b, uint8_t out[16])
+{
+    uint8_t pal[8];
+    const uint32_t a0 = b[0], a1 = b[1];
+    pal[0] = (uint8_t)a0;
+    pal[1] = (uint8_t)a1;
+    if (a0 > a1)
+        for (uint32_t i = 1; i < 7; i++)
+            pal[1 + i] = (uint8_t)(((7 - i) * a0 + i * a1 + 3) / 7);
+    else
+    {
+        for (uint32_t i = 1; i < 5; i++)
+            pal[1 + i] = (uint8_t)(((5 - i) * a0 + i * a1 + 2) / 5);
+        pal[6] = 0;
+        pal[7] = 255;
+    }
+    uint64_t bits = 0;
+    for (int k = 0; k < 6; k++)
+        bits |= (uint64_t)b[2 + k] << (8 * k);
+    for (int t = 0; t < 16; t++)
+        out[t] = pal[(bits >> (3 * t)) & 7u];
+}
+
+void bcColorBlock(const uint8_t *b, bool punchThrough, uint8_t out[16][4])
+{
+    const uint32_t c0 = b[0] | (b[1] << 8), c1 = b[2] | (b[3] << 8);
+    uint32_t pal[4][4];
+    auto expand = [](uint32_t c, uint32_t *o) {
+        const uint32_t r = c >> 11, g = (c >> 5) & 63u, bl = c & 31u;
+        o[0] = (r << 3) | (r >> 2);
+        o[1] = (g << 2) | (g >> 4);
+        o[2] = (bl << 3) | (bl >> 2);
+        o[3] = 255;
+    };
+    expand(c0, pal[0]);
+    expand(c1, pal[1]);
+    for (int k = 0; k < 3; k++)
+    {
+        if (c0 > c1 || !punchThrough)
+        {
+            pal[2][k] = (2 * pal[0][k] + pal[1][k] + 1) / 3;
+            pal[3][k] = (pal[0][k] + 2 * pal[1][k] + 1) / 3;
+        }
+        else
+        {
+            pal[2][k] = (pal[0][k] + pal[1][k] + 1) / 2;
+            pal[3][k] = 0;
+        }
+    }
+    pal[2][3] = 255;
+    pal[3][3] = (c0 > c1 || !punchThrough) ? 255 : 0;
+    const uint32_t idx = b[4] | (b[5] << 8) | (b[6] << 16) | ((uint32_t)b[7] << 24);
+    for (int t = 0; t < 16; t++)
+        for (int k = 0; k < 4; k++)
+            out[t][k] = (uint8_t)pal[(idx >> (2 * t)) & 3u][k];
+}
+
+Texture makeBlockCompressedTexture(const pt_texture_desc &d)
+{
+    Texture t;
+    t.isFloat = false;
+    t.srgb = d.format == PT_TEXTURE_BC3 || (d.format == PT_TEXTURE_BC1 && d.srgb != 0);
+    const uint8_t *src = (const uint8_t *)d.pixels;
+    const uint32_t levels = d.levels ? d.levels : 1u;
+    const size_t blockBytes = d.format == PT_TEXTURE_BC1 ? 8 : 16;
+    for (uint32_t level = 0; level < levels; level++)
+    {
+        TexLevel l;
+        l.w = std::max(1u, d.width >> level);
+        l.h = std::max(1u, d.height >> level);
+        l.rgba8.assign((size_t)l.w * l.h * 4, 0);
+        const uint32_t bw = (l.w + 3) / 4, bh = (l.h + 3) / 4;
+        for (uint32_t by = 0; by < bh; by++)
+            for (uint32_t bx = 0; bx < bw; bx++, src += blockBytes)
+            {
+                uint8_t texel[16][4];
+                if (d.format == PT_TEXTURE_BC5)
+                {
+                    uint8_t r[16], g[16];
+                    bcAlphaBlock(src, r);
+                    bcAlphaBlock(src + 8, g);
+                    for (int k = 0; k < 16; k++)
+                        texel[k][0] = r[k], texel[k][1] = g[k], texel[k][2] = 0, texel[k][3] = 255;
+                }
+                else if (d.format == PT_TEXTURE_BC3)
+                {
+                    uint8_t a[16];
+                    bcAlphaBlock(src, a);
+                    bcColorBlock(src + 8, false, texel);
+                    for (int k = 0; k < 16; k++)
+                        texel[k][3] = a[k];
+                }
+                else
+                    bcColorBlock(src, true, texel);
+                for (int k = 0; k < 16; k++)
+                {
+                    const uint32_t x = bx * 4 + (k & 3), y = by * 4 + (k >> 2);
+                    if (x < l.w && y < l.h)
+                        std::memcpy(&l.rgba8[((size_t)y * l.w + x) * 4], texel[k], 4);
+                }
+            }
+        t.levels.push_back(std::move(l));
+    }
+    return t;
+}
+
 Texture makeTexture(const pt_texture_desc &d)
 {
+    if (d.format >= PT_TEXTURE_BC1)
+        return makeBlockCompressedTexture(d);
     Texture t;
     t.isFloat = d.format == PT_TEXTURE_RGBAF32;
     t.srgb = !t.isFloat && d.srgb != 0;
@@ -784,7 +897,7 @@ Texture makeTexture(const pt_texture_desc &d)
 Texture makeDefaultTexture(uint32_t rgba, bool srgb)
 {
     /* PT/Renderer/Renderer.cpp:127-173: 1x1 RGBA8 from a little-endian uint */
-    pt_texture_desc d;
+    pt_texture_desc d = {};
     d.width = d.height = 1;
     d.format = PT_TEXTURE_RGBA8;
     d.srgb = srgb;

@@ -244,7 +244,7 @@ class Renderer:
 
     def upload_texture(self, slot: int, tex: sc.Texture):
         px = np.ascontiguousarray(tex.pixels)
-        d = sc.CTextureDesc(tex.width, tex.height, tex.format, 1 if tex.srgb else 0, px.ctypes.data)
+        d = sc.CTextureDesc(tex.width, tex.height, tex.format, 1 if tex.srgb else 0, px.ctypes.data, tex.levels)
         self._check(self._L.pt_texture_upload(self._h, slot, C.addressof(d)))
 
     def on_resize(self, width: int, height: int):

@@ -623,12 +623,163 @@ __global__ void k_mip(DevTexture t, const float *__restrict__ lut, uint32_t leve
     reinterpret_cast<uchar4 *>(t.base)[idx] = o;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Block-compressed textures (TextureFormat::BC1 / BC3 / BC5, PT/Scene.h:35-42; the reference hands
+// the blocks to the sampler hardware, VK_FORMAT_BC1_RGBA / BC3 / BC5, TextureUploader.cpp:586-591).
+// Decoded here once, at upload, into the RGBA8 texels every other texture uses: one thread per 4x4
+// block.  Interpolated palette entries are the exact rationals of the format definition rounded to
+// the nearest 8-bit value (halves up).
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void bcColorPalette(const uint8_t *b, bool allowPunchThrough, uchar4 pal[4])
+{
+    const uint32_t c0 = b[0] | (b[1] << 8), c1 = b[2] | (b[3] << 8);
+    auto expand = [](uint32_t c) {
+        const uint32_t r = c >> 11, g = (c >> 5) & 63u, bl = c & 31u;
+        return make_uchar4((uint8_t)((r << 3) | (r >> 2)), (uint8_t)((g << 2) | (g >> 4)), (uint8_t)((bl << 3) | (bl >> 2)), 255);
+    };
+    pal[0] = expand(c0);
+    pal[1] = expand(c1);
+    if (c0 > c1 || !allowPunchThrough)
+    {
+        pal[2] = make_uchar4((uint8_t)((2 * pal[0].x + pal[1].x + 1) / 3), (uint8_t)((2 * pal[0].y + pal[1].y + 1) / 3),
+                             (uint8_t)((2 * pal[0].z + pal[1].z + 1) / 3), 255);
+        pal[3] = make_uchar4((uint8_t)((pal[0].x + 2 * pal[1].x + 1) / 3), (uint8_t)((pal[0].y + 2 * pal[1].y + 1) / 3),
+                             (uint8_t)((pal[0].z + 2 * pal[1].z + 1) / 3), 255);
+    }
+    else
+    {
+        pal[2] = make_uchar4((uint8_t)((pal[0].x + pal[1].x + 1) / 2), (uint8_t)((pal[0].y + pal[1].y + 1) / 2),
+                             (uint8_t)((pal[0].z + pal[1].z + 1) / 2), 255);
+        pal[3] = make_uchar4(0, 0, 0, 0); // BC1_RGBA: transparent black
+    }
+}
+
+// the 8-byte single-channel block of BC3's alpha and BC5's two channels
+__device__ __forceinline__ void bcAlphaPalette(const uint8_t *b, uint8_t pal[8])
+{
+    const uint32_t a0 = b[0], a1 = b[1];
+    pal[0] = (uint8_t)a0;
+    pal[1] = (uint8_t)a1;
+    if (a0 > a1)
+        for (uint32_t i = 1; i < 7; i++)
+            pal[1 + i] = (uint8_t)(((7 - i) * a0 + i * a1 + 3) / 7);
+    else
+    {
+        for (uint32_t i = 1; i < 5; i++)
+            pal[1 + i] = (uint8_t)(((5 - i) * a0 + i * a1 + 2) / 5);
+        pal[6] = 0;
+        pal[7] = 255;
+    }
+}
+
+__global__ void k_bc_decode(const uint8_t *__restrict__ blocks, uint32_t format, uint32_t w, uint32_t h, uchar4 *__restrict__ out)
+{
+    const uint32_t bw = (w + 3) / 4, bh = (h + 3) / 4;
+    const uint32_t bi = blockIdx.x * blockDim.x + threadIdx.x;
+    if (bi >= bw * bh)
+        return;
+    const uint32_t bx = bi % bw, by = bi / bw;
+    const uint8_t *b = blocks + (size_t)bi * (format == PT_TEXTURE_BC1 ? 8 : 16);
+    uchar4 texel[16];
+    if (format == PT_TEXTURE_BC5)
+    {
+        uint8_t pr[8], pg[8];
+        bcAlphaPalette(b, pr);
+        bcAlphaPalette(b + 8, pg);
+        unsigned long long ir = 0, ig = 0;
+        for (int k = 0; k < 6; k++)
+        {
+            ir |= (unsigned long long)b[2 + k] << (8 * k);
+            ig |= (unsigned long long)b[10 + k] << (8 * k);
+        }
+        for (int t = 0; t < 16; t++)
+            texel[t] = make_uchar4(pr[(ir >> (3 * t)) & 7u], pg[(ig >> (3 * t)) & 7u], 0, 255);
+    }
+    else
+    {
+        const uint8_t *color = format == PT_TEXTURE_BC3 ? b + 8 : b;
+        uchar4 pal[4];
+        bcColorPalette(color, format == PT_TEXTURE_BC1, pal);
+        const uint32_t idx = color[4] | (color[5] << 8) | (color[6] << 16) | ((uint32_t)color[7] << 24);
+        for (int t = 0; t < 16; t++)
+            texel[t] = pal[(idx >> (2 * t)) & 3u];
+        if (format == PT_TEXTURE_BC3)
+        {
+            uint8_t pa[8];
+            bcAlphaPalette(b, pa);
+            unsigned long long ia = 0;
+            for (int k = 0; k < 6; k++)
+                ia |= (unsigned long long)b[2 + k] << (8 * k);
+            for (int t = 0; t < 16; t++)
+                texel[t].w = pa[(ia >> (3 * t)) & 7u];
+        }
+    }
+    for (int t = 0; t < 16; t++)
+    {
+        const uint32_t x = bx * 4 + (t & 3), y = by * 4 + (t >> 2);
+        if (x < w && y < h)
+            out[(size_t)y * w + x] = texel[t];
+    }
+}
+
 pt_status createTexture(Context *ctx, const pt_texture_desc &d, DevTexture &out, void **outAlloc)
 {
     if (d.width == 0 || d.height == 0 || !d.pixels)
         return fail(ctx, PT_ERR_INVALID_ARGUMENT, "texture", "empty texture");
-    if (d.format != PT_TEXTURE_RGBA8 && d.format != PT_TEXTURE_RGBAF32)
-        return fail(ctx, PT_ERR_UNSUPPORTED, "texture", "only RGBA8 and RGBAF32 textures are supported");
+    if (d.format > PT_TEXTURE_BC5)
+        return fail(ctx, PT_ERR_UNSUPPORTED, "texture", "unknown texture format");
+    if (d.format >= PT_TEXTURE_BC1)
+    {
+        // stored mip chain, decoded level by level; no mips are generated (TextureUploader.cpp:420-456)
+        DevTexture t = {};
+        t.width = d.width;
+        t.height = d.height;
+        t.flags = (d.format == PT_TEXTURE_BC3 || (d.format == PT_TEXTURE_BC1 && d.srgb)) ? PT_TEX_FLAG_SRGB : 0u;
+        uint32_t full = 1;
+        for (uint32_t m = std::max(d.width, d.height); m > 1; m >>= 1)
+            full++;
+        const uint32_t levels = std::max(1u, d.levels);
+        if (levels > full || levels > PT_MAX_TEX_LEVELS)
+            return fail(ctx, PT_ERR_INVALID_ARGUMENT, "texture", "more mip levels than the extent allows");
+        t.levels = levels;
+        const uint64_t blockBytes = d.format == PT_TEXTURE_BC1 ? 8 : 16;
+        uint64_t texels = 0, bytes = 0;
+        std::vector<uint64_t> blockOffset(levels);
+        for (uint32_t l = 0; l < levels; l++)
+        {
+            const uint32_t lw = std::max(1u, d.width >> l), lh = std::max(1u, d.height >> l);
+            t.levelOffset[l] = (uint32_t)texels;
+            texels += (uint64_t)lw * lh;
+            blockOffset[l] = bytes;
+            bytes += (uint64_t)((lw + 3) / 4) * ((lh + 3) / 4) * blockBytes;
+        }
+        void *mem = nullptr;
+        uint8_t *dBlocks = nullptr;
+        PT_CUDA_CHECK(ctx, cudaMalloc(&mem, texels * 4));
+        cudaError_t err = cudaMalloc((void **)&dBlocks, bytes);
+        if (err == cudaSuccess)
+            err = cudaMemcpyAsync(dBlocks, d.pixels, bytes, cudaMemcpyHostToDevice, ctx->stream);
+        for (uint32_t l = 0; l < levels && err == cudaSuccess; l++)
+        {
+            const uint32_t lw = std::max(1u, d.width >> l), lh = std::max(1u, d.height >> l);
+            const uint32_t nBlocks = ((lw + 3) / 4) * ((lh + 3) / 4);
+            k_bc_decode<<<(nBlocks + 127) / 128, 128, 0, ctx->stream>>>(dBlocks + blockOffset[l], d.format, lw, lh,
+                                                                        reinterpret_cast<uchar4 *>(mem) + t.levelOffset[l]);
+            err = cudaGetLastError();
+        }
+        if (err == cudaSuccess)
+            err = cudaStreamSynchronize(ctx->stream);
+        cudaFree(dBlocks);
+        if (err != cudaSuccess)
+        {
+            cudaFree(mem);
+            PT_CUDA_CHECK(ctx, err);
+        }
+        t.base = (uint64_t)mem;
+        out = t;
+        *outAlloc = mem;
+        return PT_OK;
+    }
     DevTexture t = {};
     t.width = d.width;
     t.height = d.height;

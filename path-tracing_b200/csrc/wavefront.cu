@@ -41,6 +41,11 @@ namespace
 #ifndef PT_TRACE_MIN_BLOCKS
 #define PT_TRACE_MIN_BLOCKS 8
 #endif
+// bits of the leaf-order triangle index the hit queue is sorted by; one more bit sends unused entries
+// to the end, and CUB's onesweep sort takes one pass per 8 bits: 15 + 1 = two passes
+#ifndef PT_HIT_KEY_BITS
+#define PT_HIT_KEY_BITS 15
+#endif
 #ifndef PT_SHADE_MIN_BLOCKS
 #define PT_SHADE_MIN_BLOCKS 4
 #endif
@@ -885,11 +890,11 @@ pt_status renderSamples(Context *ctx, const pt_render_params *params, uint32_t f
     // Hits are shaded in triangle order (radix sort of the hit queue on the upper bits of the
     // leaf-order = Morton-order triangle index): neighbouring lanes then shade neighbouring
     // triangles — same material branch, same texture region, shared cache lines.  16 key bits
-    // (two 8-bit passes) are plenty for that.
+    // are plenty for that.
     uint32_t triBits = 1;
     while (triBits < 32 && (ctx->scene.triCount >> triBits) != 0)
         triBits++;
-    const uint32_t keyBits = std::min(triBits, 16u);
+    const uint32_t keyBits = std::min(triBits, (uint32_t)PT_HIT_KEY_BITS);
 
     for (uint32_t roundBase = 0; roundMax > 0 && roundBase < sampleCount; roundBase += roundMax)
     {

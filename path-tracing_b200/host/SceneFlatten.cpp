@@ -31,9 +31,6 @@ bool IsSrgbTexture(TextureType type)
 
 pt_texture_desc LoadTexture(const TextureInfo &info, std::vector<std::byte> &pixels)
 {
-    if (info.Format != TextureFormat::RGBAU8 && info.Format != TextureFormat::RGBAF32)
-        throw error(std::format("Texture {}: block-compressed formats are not supported headless", info.Name));
-
     TextureData data = TextureImporter::LoadTextureData(info);
     pixels.assign(data.begin(), data.end());
     TextureImporter::ReleaseTextureData(info, data);
@@ -41,8 +38,18 @@ pt_texture_desc LoadTexture(const TextureInfo &info, std::vector<std::byte> &pix
     pt_texture_desc desc = {};
     desc.width = info.Width;
     desc.height = info.Height;
-    desc.format = info.Format == TextureFormat::RGBAF32 ? PT_TEXTURE_RGBAF32 : PT_TEXTURE_RGBA8;
-    desc.srgb = info.Format == TextureFormat::RGBAU8 && IsSrgbTexture(info.Type);
+    switch (info.Format)
+    {
+    case TextureFormat::RGBAU8: desc.format = PT_TEXTURE_RGBA8; break;
+    case TextureFormat::RGBAF32: desc.format = PT_TEXTURE_RGBAF32; break;
+    /* .dds files: the gli loader returns every stored level, level 0 first (TextureImporter.cpp:311-343) */
+    case TextureFormat::BC1: desc.format = PT_TEXTURE_BC1; break;
+    case TextureFormat::BC3: desc.format = PT_TEXTURE_BC3; break;
+    case TextureFormat::BC5: desc.format = PT_TEXTURE_BC5; break;
+    default: throw error(std::format("Texture {}: unsupported texture format", info.Name));
+    }
+    desc.srgb = (info.Format == TextureFormat::RGBAU8 || info.Format == TextureFormat::BC1) && IsSrgbTexture(info.Type);
+    desc.levels = info.Levels;
     desc.pixels = pixels.data();
     return desc;
 }

@@ -87,7 +87,7 @@ assert HIT.itemsize == 24 and RAY.itemsize == 32
 
 SCENE_TEXTURE_OFFSET = 9
 NO_HIT = 0xFFFFFFFF
-TEXTURE_RGBA8, TEXTURE_RGBAF32 = 0, 1
+TEXTURE_RGBA8, TEXTURE_RGBAF32, TEXTURE_BC1, TEXTURE_BC3, TEXTURE_BC5 = 0, 1, 2, 3, 4
 MATERIAL_TYPE_MR, MATERIAL_TYPE_SG, MATERIAL_TYPE_PHONG = 0, 1, 2
 MISS_FLAGS_NONE, MISS_FLAGS_SKYBOX_2D, MISS_FLAGS_SKYBOX_CUBE = 0, 1, 2
 HIT_FLAGS_NONE, HIT_FLAGS_DX_NORMAL_TEXTURES = 0, 1
@@ -106,7 +106,8 @@ def material_id(index: int, material_type: int = MATERIAL_TYPE_MR) -> int:
 
 
 class CTextureDesc(C.Structure):
-    _fields_ = [("width", C.c_uint32), ("height", C.c_uint32), ("format", C.c_uint32), ("srgb", C.c_uint32), ("pixels", C.c_void_p)]
+    _fields_ = [("width", C.c_uint32), ("height", C.c_uint32), ("format", C.c_uint32), ("srgb", C.c_uint32), ("pixels", C.c_void_p),
+                ("levels", C.c_uint32)]
 
 
 class CDirectionalLight(C.Structure):
@@ -159,21 +160,27 @@ class CRenderParams(C.Structure):
 
 @dataclass
 class Texture:
-    """One decoded level-0 image (pt_texture_desc)."""
+    """One decoded level-0 image (pt_texture_desc), or — with bc_format set — the block-compressed mip
+    chain of a .dds file: pixels is then the flat uint8 block data of `levels` levels, level 0 first."""
 
-    pixels: np.ndarray  # (h, w, 4) uint8 or float32
+    pixels: np.ndarray  # (h, w, 4) uint8 or float32; BC: flat uint8 blocks
     srgb: bool = False
+    bc_format: int = 0  # TEXTURE_BC1 / BC3 / BC5, 0 = uncompressed
+    bc_extent: tuple = (0, 0)  # (width, height) of level 0 of a BC texture
+    levels: int = 1
 
     @property
     def width(self) -> int:
-        return int(self.pixels.shape[1])
+        return int(self.bc_extent[0]) if self.bc_format else int(self.pixels.shape[1])
 
     @property
     def height(self) -> int:
-        return int(self.pixels.shape[0])
+        return int(self.bc_extent[1]) if self.bc_format else int(self.pixels.shape[0])
 
     @property
     def format(self) -> int:
+        if self.bc_format:
+            return self.bc_format
         return TEXTURE_RGBAF32 if self.pixels.dtype == np.float32 else TEXTURE_RGBA8
 
 
@@ -296,7 +303,7 @@ class SceneData:
         def tex_desc(tex: Texture) -> CTextureDesc:
             px = np.ascontiguousarray(tex.pixels)
             keep.append(px)
-            return CTextureDesc(tex.width, tex.height, tex.format, 1 if tex.srgb else 0, px.ctypes.data)
+            return CTextureDesc(tex.width, tex.height, tex.format, 1 if tex.srgb else 0, px.ctypes.data, tex.levels)
 
         if self.textures:
             descs = (CTextureDesc * len(self.textures))(*[tex_desc(t) for t in self.textures])

@@ -19,7 +19,7 @@ def test_sizes():
     assert sc.GEOMETRY.itemsize == 20 and sc.MESH_RECORD.itemsize == 12 and sc.MODEL.itemsize == 8
     assert sc.INSTANCE.itemsize == 52 and sc.RAY.itemsize == 32 and sc.HIT.itemsize == 24
     assert C.sizeof(sc.CRenderParams) == 148  # 2 mat4 + bounce, lens, focal + the two specialisation constants
-    assert C.sizeof(sc.CTextureDesc) == 24
+    assert C.sizeof(sc.CTextureDesc) == 32  # + levels (block-compressed mip chains), padded to the pointer alignment
 
 
 def test_metallic_roughness_padding_literals():
