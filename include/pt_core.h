@@ -67,7 +67,20 @@ typedef struct pt_vertex {
     float bitangent[3];
 } pt_vertex;
 
-/* PathTracing::Geometry, PT/Scene.h:63-71 (bools widened to u32; IsAnimated must be 0). */
+/* Shaders::AnimatedVertex, PT/Shaders/ShaderTypes.incl:50-59 (88 bytes): a Vertex + 4 bone indices
+ * and weights (MaxBonesPerVertex = 4, ShaderTypes.incl:31). */
+typedef struct pt_animated_vertex {
+    float position[3];
+    float texcoords[2];
+    float normal[3];
+    float tangent[3];
+    float bitangent[3];
+    uint32_t bone_indices[4];
+    float bone_weights[4];
+} pt_animated_vertex;
+
+/* PathTracing::Geometry, PT/Scene.h:63-71 (bools widened to u32; IsAnimated travels separately in
+ * pt_scene_desc::geometry_is_animated so that this struct keeps its 20 bytes). */
 typedef struct pt_geometry {
     uint32_t vertex_offset; /* first vertex; indices are relative to it (PT/Shaders/common.glsl:27-34) */
     uint32_t vertex_length;
@@ -237,6 +250,20 @@ typedef struct pt_scene_desc {
      * (PT/Renderer/TextureUploader.cpp:232-236): Front, Back, Up, Down, Left, Right
      * = Vulkan cube faces +X, -X, +Y, -Y, +Z, -Z. */
     const pt_texture_desc *skybox_cube;
+    /* Skeletal animation (Scene::GetAnimatedVertices / GetAnimatedIndices /
+     * GetBoneTransforms, PT/Scene.h:183-196).  geometry_is_animated[i] != 0 marks geometry i as
+     * Geometry::IsAnimated: its vertex_offset / index_offset then address animated_vertices /
+     * animated_indices instead of vertices / indices (PT/Renderer/Renderer.cpp:286-372).  The core
+     * skins them with bone_transforms (skinning.comp:21-50) before it bakes and builds.  All NULL / 0
+     * for a scene without skeletal animation. */
+    const uint32_t *geometry_is_animated; /* geometry_count entries, or NULL */
+    const pt_animated_vertex *animated_vertices;
+    uint64_t animated_vertex_count;
+    const uint32_t *animated_indices;
+    uint64_t animated_index_count;
+    const float *bone_transforms; /* bone_count x 12 floats: glm::mat3x4 = three vec4 columns = the rows of
+                                     the 3x4 bone matrix (Bone::Offset * node transform, Scene.cpp:72-73) */
+    uint32_t bone_count;
 } pt_scene_desc;
 
 /* Shaders::RaygenUniformData (PT/Shaders/ShaderRendererTypes.incl:26-34) plus the two
@@ -352,14 +379,18 @@ typedef struct pt_scene_update_desc {
     const pt_point_light *point_lights; /* the whole light array (positions follow their nodes, Scene.cpp:75-77) */
     uint32_t point_light_count;       /* <= PT_MAX_LIGHT_COUNT */
     const pt_directional_light *directional_light; /* Scene.cpp:79-80 */
+    const float *bone_transforms;     /* bone_count x 12 floats (Scene::GetBoneTransforms, Scene.cpp:72-73):
+                                         re-skins the animated geometries (RecordSkinningCommands) */
+    uint32_t bone_count;              /* must equal the uploaded scene's bone_count */
 } pt_scene_update_desc;
 
 /* Replaces the per-frame half of Renderer::UpdateSceneData / Renderer::Render for animated scenes:
  * the light uniform rewrite (PT/Renderer/Renderer.cpp:1719-1726) and
  * AccelerationStructure::RecordUpdateCommands (PT/Renderer/AccelerationStructure.cpp:48-57, called
  * from Renderer.cpp:1753-1754).  Where the reference refits BLAS + TLAS, the core re-bakes the
- * instances and rebuilds its BVH on the GPU.  Geometry, materials and textures are unchanged.
- * Skeletal animation (skinning.comp) is not covered: PT_ERR_UNSUPPORTED at upload (IsAnimated).
+ * instances and rebuilds its BVH on the GPU; new bone transforms first re-skin the animated
+ * geometries (Renderer::RecordSkinningCommands, Renderer.cpp:854-890 = skinning.comp).  Static
+ * geometry, materials and textures are unchanged.
  * The accumulation buffer is NOT reset — the caller does that (Renderer::UpdateSceneData's
  * `updated` flag, Renderer.cpp:240-241) with pt_render_begin.  Blocking. */
 PT_API pt_status pt_scene_update(pt_context *ctx, const pt_scene_update_desc *desc);

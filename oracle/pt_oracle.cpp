@@ -1043,6 +1043,38 @@ Vertex getVertex(const pto_scene &s, const pt_geometry &g, uint32_t offset)
     return toVertex(s.vertices[g.vertex_offset + index]);
 }
 
+/* skinning.comp:21-50 — one animated vertex through its (at most MaxBonesPerVertex = 4) bones.
+ * boneTransforms[b] = GLSL mat3x4 (three vec4 columns). */
+pt_vertex skinVertex(const pt_animated_vertex &a, const float *boneTransforms, uint32_t boneCount)
+{
+    const vec3 P = V3(a.position[0], a.position[1], a.position[2]);
+    const vec3 N = V3(a.normal[0], a.normal[1], a.normal[2]);
+    const vec3 T = V3(a.tangent[0], a.tangent[1], a.tangent[2]);
+    const vec3 B = V3(a.bitangent[0], a.bitangent[1], a.bitangent[2]);
+    vec3 position = V3(0.0f, 0.0f, 0.0f), normal = position, tangent = position, bitangent = position;
+    float totalWeight = 0;
+    for (int i = 0; i < 4 && totalWeight < 1.0f; i++)
+    {
+        const uint32_t boneIndex = std::min(a.bone_indices[i], boneCount - 1);
+        const float boneWeight = a.bone_weights[i];
+        const float *m = boneTransforms + 12 * (size_t)boneIndex;
+        const mat3x4 transform = { { V4(m[0], m[1], m[2], m[3]), V4(m[4], m[5], m[6], m[7]), V4(m[8], m[9], m[10], m[11]) } };
+        position = position + (V4(P, 1.0f) * transform) * boneWeight;
+        tangent = tangent + normalize(V4(T, 0.0f) * transform) * boneWeight;
+        bitangent = bitangent + normalize(V4(B, 0.0f) * transform) * boneWeight;
+        const vec4 n4 = V4(N, 0.0f) * transpose(inverse(M4(transform)));
+        normal = normal + normalize(V3(n4.x, n4.y, n4.z)) * boneWeight;
+        totalWeight += boneWeight;
+    }
+    pt_vertex v = {};
+    v.position[0] = position.x, v.position[1] = position.y, v.position[2] = position.z;
+    v.texcoords[0] = a.texcoords[0], v.texcoords[1] = a.texcoords[1];
+    v.normal[0] = normal.x, v.normal[1] = normal.y, v.normal[2] = normal.z;
+    v.tangent[0] = tangent.x, v.tangent[1] = tangent.y, v.tangent[2] = tangent.z;
+    v.bitangent[0] = bitangent.x, v.bitangent[1] = bitangent.y, v.bitangent[2] = bitangent.z;
+    return v;
+}
+
 /* ------------------------------------------------------------------------- */
 /* BVH2, binned SAH (the reference has no BVH code: the Vulkan driver builds it) */
 /* ------------------------------------------------------------------------- */
@@ -2090,6 +2122,21 @@ pto_scene *pto_scene_create(const pt_scene_desc *d)
             mat3x4 { { V4(m[0], m[1], m[2], m[3]), V4(m[4], m[5], m[6], m[7]), V4(m[8], m[9], m[10], m[11]) } });
     }
     s->geometries.assign(d->geometries, d->geometries + d->geometry_count);
+    if (d->geometry_is_animated)
+    {
+        /* Renderer::RecordSkinningCommands (PT/Renderer/Renderer.cpp:854-890): the animated geometries'
+         * vertices are skinned into an out-buffer the geometry table then points at (:353-372); here they
+         * are appended to the static buffers and the animated geometries' offsets moved behind them */
+        for (uint64_t i = 0; i < d->animated_vertex_count; i++)
+            s->vertices.push_back(skinVertex(d->animated_vertices[i], d->bone_transforms, d->bone_count));
+        s->indices.insert(s->indices.end(), d->animated_indices, d->animated_indices + d->animated_index_count);
+        for (uint32_t g = 0; g < d->geometry_count; g++)
+            if (d->geometry_is_animated[g])
+            {
+                s->geometries[g].vertex_offset += (uint32_t)d->vertex_count;
+                s->geometries[g].index_offset += (uint32_t)d->index_count;
+            }
+    }
     s->meshRecords.assign(d->mesh_records, d->mesh_records + d->mesh_record_count);
     s->models.assign(d->models, d->models + d->model_count);
     s->instances.assign(d->instances, d->instances + d->instance_count);

@@ -68,7 +68,8 @@ class SceneUpdateDesc(C.Structure):
     """pt_scene_update_desc."""
 
     _fields_ = [("instance_transforms", C.c_void_p), ("instance_count", C.c_uint32), ("point_lights", C.c_void_p),
-                ("point_light_count", C.c_uint32), ("directional_light", C.c_void_p)]
+                ("point_light_count", C.c_uint32), ("directional_light", C.c_void_p), ("bone_transforms", C.c_void_p),
+                ("bone_count", C.c_uint32)]
 
 
 TONE_MAPPING_SDR, TONE_MAPPING_HDR = 0, 1
@@ -221,11 +222,12 @@ class Renderer:
         if self.width:
             self.on_resize(self.width, self.height)
 
-    def update_scene(self, instance_transforms=None, point_lights=None, directional_light=None):
+    def update_scene(self, instance_transforms=None, point_lights=None, directional_light=None, bone_transforms=None):
         """The per-frame half of Renderer::UpdateSceneData for animated scenes (Scene::Update's outputs):
         new instance transforms ((N, 12) float32, 3x4 row-major) re-bake the instances and rebuild the BVH;
         point_lights (sc.POINT_LIGHT records) / directional_light (sc.DIRECTIONAL_LIGHT record) rewrite the
-        light block.  The accumulation is not reset — call on_resize() like the reference's `updated` flag."""
+        light block; bone_transforms ((B, 12) float32) re-skin the animated geometries (skinning.comp) before the
+        rebuild.  The accumulation is not reset — call on_resize() like the reference's `updated` flag."""
         d = SceneUpdateDesc()
         keep = []
         if instance_transforms is not None:
@@ -240,6 +242,10 @@ class Renderer:
             dl = np.ascontiguousarray(directional_light, sc.DIRECTIONAL_LIGHT).reshape(1)
             keep.append(dl)
             d.directional_light = dl.ctypes.data
+        if bone_transforms is not None:
+            bt = np.ascontiguousarray(bone_transforms, np.float32).reshape(-1, 12)
+            keep.append(bt)
+            d.bone_transforms, d.bone_count = bt.ctypes.data, len(bt)
         self._check(self._L.pt_scene_update(self._h, C.addressof(d)))
 
     def upload_texture(self, slot: int, tex: sc.Texture):

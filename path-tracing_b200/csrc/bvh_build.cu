@@ -132,6 +132,57 @@ __global__ void k_bake(const MeshInstance *__restrict__ mis, uint32_t miCount, c
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// skinning.comp:21-50 — Renderer::RecordSkinningCommands (PT/Renderer/Renderer.cpp:854-890).
+// One thread per animated vertex: blends the bone-transformed position / tangent frame with up to
+// MaxBonesPerVertex = 4 weights (the loop stops once the weights reach 1).  bones[b] = the 12 floats
+// of the bone's mat3x4 (three vec4 columns = rows of the 3x4 matrix) followed by the 9 of its normal
+// matrix (inverse transpose of the linear part, precomputed on the host like the instances').
+// The reference writes into a separate "out animated vertex" buffer per frame in flight; here the
+// skinned vertices live behind the static ones in the one vertex buffer k_bake reads.
+// ---------------------------------------------------------------------------------------------
+#define PT_BONE_STRIDE 21
+__global__ void k_skin(const float *__restrict__ animated, uint32_t count, const float *__restrict__ bones, uint32_t boneCount,
+                       float *__restrict__ out)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count)
+        return;
+    const float *a = animated + (size_t)i * 22;
+    const vec3 P = V3(a[0], a[1], a[2]), N = V3(a[5], a[6], a[7]), T = V3(a[8], a[9], a[10]), B = V3(a[11], a[12], a[13]);
+    vec3 pos = V3(0.0f), nrm = V3(0.0f), tan = V3(0.0f), bit = V3(0.0f);
+    float totalWeight = 0.0f;
+    for (int k = 0; k < 4 && totalWeight < 1.0f; k++)
+    {
+        const uint32_t bone = min(__float_as_uint(a[14 + k]), boneCount - 1); // (an index past the UBO is undefined in GLSL)
+        const float w = a[18 + k];
+        const float *m = bones + (size_t)bone * PT_BONE_STRIDE;
+        // vec4(v, 1 | 0) * mat3x4: component j = dot(v4, column j)
+        auto xformPoint = [&](vec3 v) {
+            return V3(((v.x * m[0] + v.y * m[1]) + v.z * m[2]) + 1.0f * m[3], ((v.x * m[4] + v.y * m[5]) + v.z * m[6]) + 1.0f * m[7],
+                      ((v.x * m[8] + v.y * m[9]) + v.z * m[10]) + 1.0f * m[11]);
+        };
+        auto xformDir = [&](vec3 v) {
+            return V3(((v.x * m[0] + v.y * m[1]) + v.z * m[2]) + 0.0f * m[3], ((v.x * m[4] + v.y * m[5]) + v.z * m[6]) + 0.0f * m[7],
+                      ((v.x * m[8] + v.y * m[9]) + v.z * m[10]) + 0.0f * m[11]);
+        };
+        const float *nm = m + 12;
+        const vec3 nn = V3((N.x * nm[0] + N.y * nm[1]) + N.z * nm[2], (N.x * nm[3] + N.y * nm[4]) + N.z * nm[5],
+                           (N.x * nm[6] + N.y * nm[7]) + N.z * nm[8]);
+        pos = pos + w * xformPoint(P);
+        tan = tan + w * normalize(xformDir(T));
+        bit = bit + w * normalize(xformDir(B));
+        nrm = nrm + w * normalize(nn);
+        totalWeight += w;
+    }
+    float *o = out + (size_t)i * 14;
+    o[0] = pos.x, o[1] = pos.y, o[2] = pos.z;
+    o[3] = a[3], o[4] = a[4];
+    o[5] = nrm.x, o[6] = nrm.y, o[7] = nrm.z;
+    o[8] = tan.x, o[9] = tan.y, o[10] = tan.z;
+    o[11] = bit.x, o[12] = bit.y, o[13] = bit.z;
+}
+
 __device__ __forceinline__ uint64_t expandBits21(uint64_t v)
 {
     v &= 0x1fffffull;
@@ -1044,6 +1095,35 @@ pt_status buildAccel(Context *ctx, const std::vector<MeshInstance> &mis, uint32_
 #undef PT_TRY
 }
 
+// Uploads the bone matrices (+ their normal matrices) and re-skins every animated vertex into its
+// place behind the static vertices (Renderer::RecordSkinningCommands).
+pt_status skinAnimatedVertices(Context *ctx, const float *boneTransforms)
+{
+    const SceneTopology &t = ctx->topo;
+    std::vector<float> bones((size_t)t.boneCount * PT_BONE_STRIDE);
+    for (uint32_t b = 0; b < t.boneCount; b++)
+    {
+        const float *m = boneTransforms + 12 * (size_t)b;
+        float *o = bones.data() + (size_t)b * PT_BONE_STRIDE;
+        std::memcpy(o, m, 48);
+        double R[9], Ri[9];
+        for (int j = 0; j < 3; j++)
+            for (int c = 0; c < 3; c++)
+                R[j * 3 + c] = m[j * 4 + c];
+        invert3x3(R, Ri);
+        for (int j = 0; j < 3; j++)
+            for (int c = 0; c < 3; c++)
+                o[12 + j * 3 + c] = (float)Ri[c * 3 + j]; // inverse transpose
+    }
+    PT_CUDA_CHECK(ctx, cudaMemcpyAsync(ctx->dBones, bones.data(), bones.size() * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    const uint32_t n = (uint32_t)t.animatedVertexCount;
+    k_skin<<<(n + 255) / 256, 256, 0, ctx->stream>>>(ctx->dAnimatedVertices, n, ctx->dBones, t.boneCount,
+                                                     const_cast<float *>(ctx->dVertices) + (size_t)t.vertexCount * 14);
+    PT_CUDA_CHECK(ctx, cudaGetLastError());
+    PT_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream)); // `bones` is a local
+    return PT_OK;
+}
+
 // Flattens instances x meshes into one MeshInstance per (instance, mesh) pair with its baked
 // object-to-world and normal matrices (host, tiny).
 pt_status flattenInstances(Context *ctx, const SceneTopology &t, std::vector<MeshInstance> &mis, bool &hasAlpha)
@@ -1065,8 +1145,9 @@ pt_status flattenInstances(Context *ctx, const SceneTopology &t, std::vector<Mes
             if (rec.geometry_index >= t.geometries.size() || rec.transform_index >= t.transforms.size() / 12)
                 return fail(ctx, PT_ERR_INVALID_ARGUMENT, "pt_scene_upload", "mesh record index out of range");
             const pt_geometry &g = t.geometries[rec.geometry_index];
-            if ((uint64_t)g.index_offset + g.index_length > t.indexCount ||
-                (uint64_t)g.vertex_offset + g.vertex_length > t.vertexCount)
+            const bool animated = !t.geometryIsAnimated.empty() && t.geometryIsAnimated[rec.geometry_index] != 0;
+            if ((uint64_t)g.index_offset + g.index_length > (animated ? t.animatedIndexCount : t.indexCount) ||
+                (uint64_t)g.vertex_offset + g.vertex_length > (animated ? t.animatedVertexCount : t.vertexCount))
                 return fail(ctx, PT_ERR_INVALID_ARGUMENT, "pt_scene_upload", "geometry range out of range");
             const uint32_t type = rec.material_id & 0xffu, index = rec.material_id >> 8;
             const uint32_t limit = type == 0 ? t.materialCount[0] : type == 1 ? t.materialCount[1]
@@ -1098,8 +1179,9 @@ pt_status flattenInstances(Context *ctx, const SceneTopology &t, std::vector<Mes
                     m.N[j * 3 + c] = (float)Ri[c * 3 + j]; // inverse transpose
             m.triOffset = (uint32_t)triTotal;
             m.triCount = g.index_length / 3;
-            m.vertexOffset = g.vertex_offset;
-            m.indexOffset = g.index_offset;
+            // skinned vertices / animated indices sit behind the static ones in the device buffers
+            m.vertexOffset = g.vertex_offset + (animated ? (uint32_t)t.vertexCount : 0u);
+            m.indexOffset = g.index_offset + (animated ? (uint32_t)t.indexCount : 0u);
             m.instance = ii;
             m.geometry = mi;
             m.materialId = rec.material_id;
@@ -1163,6 +1245,14 @@ pt_status uploadScene(Context *ctx, const pt_scene_desc *d)
         (d->instance_count && !d->instances) || (d->texture_count && !d->textures))
         return fail(ctx, PT_ERR_INVALID_ARGUMENT, "pt_scene_upload", "array pointer is NULL with a non-zero count");
 
+    if (d->geometry_is_animated &&
+        ((d->animated_vertex_count && !d->animated_vertices) || (d->animated_index_count && !d->animated_indices) ||
+         d->bone_count == 0 || !d->bone_transforms))
+        return fail(ctx, PT_ERR_INVALID_ARGUMENT, "pt_scene_upload", "animated geometries need animated vertices, indices and bone transforms");
+    if (d->vertex_count + (d->geometry_is_animated ? d->animated_vertex_count : 0) >= (1ull << 32) ||
+        d->index_count + (d->geometry_is_animated ? d->animated_index_count : 0) >= (1ull << 32))
+        return fail(ctx, PT_ERR_UNSUPPORTED, "pt_scene_upload", "more than 2^32 vertices or indices");
+
     freeScene(ctx);
     std::vector<void *> &own = ctx->sceneAllocs;
     std::vector<void *> temp;
@@ -1201,6 +1291,16 @@ pt_status uploadScene(Context *ctx, const pt_scene_desc *d)
     topo.materialCount[0] = d->mr_material_count;
     topo.materialCount[1] = d->sg_material_count;
     topo.materialCount[2] = d->phong_material_count;
+    topo.geometryIsAnimated.clear();
+    topo.animatedVertexCount = topo.animatedIndexCount = 0;
+    topo.boneCount = 0;
+    if (d->geometry_is_animated)
+    {
+        topo.geometryIsAnimated.assign(d->geometry_is_animated, d->geometry_is_animated + d->geometry_count);
+        topo.animatedVertexCount = d->animated_vertex_count;
+        topo.animatedIndexCount = d->animated_index_count;
+        topo.boneCount = d->bone_count;
+    }
     std::vector<MeshInstance> mis;
     bool hasAlpha = false;
     PT_TRY(flattenInstances(ctx, topo, mis, hasAlpha));
@@ -1302,19 +1402,35 @@ pt_status uploadScene(Context *ctx, const pt_scene_desc *d)
 
     s.triCount = n;
     s.hasAlpha = hasAlpha ? 1u : 0u;
-    // vertices and indices stay on the device: pt_scene_update re-bakes from them
+    // vertices and indices stay on the device: pt_scene_update re-bakes from them.  Skinned vertices and
+    // animated indices follow the static ones in the same buffers.
     {
         float *dVertices;
         uint32_t *dIndices;
-        PT_TRY(devAlloc(ctx, &dVertices, (size_t)d->vertex_count * 14, own));
-        PT_TRY(devAlloc(ctx, &dIndices, (size_t)d->index_count, own));
+        const uint64_t av = topo.animatedVertexCount, ai = topo.animatedIndexCount;
+        PT_TRY(devAlloc(ctx, &dVertices, (size_t)(d->vertex_count + av) * 14, own));
+        PT_TRY(devAlloc(ctx, &dIndices, (size_t)(d->index_count + ai), own));
         if (d->vertex_count)
             PT_CUDA_CHECK(ctx, cudaMemcpyAsync(dVertices, d->vertices, (size_t)d->vertex_count * 56, cudaMemcpyHostToDevice, ctx->stream));
         if (d->index_count)
             PT_CUDA_CHECK(ctx, cudaMemcpyAsync(dIndices, d->indices, (size_t)d->index_count * 4, cudaMemcpyHostToDevice, ctx->stream));
-        PT_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+        if (ai)
+            PT_CUDA_CHECK(ctx, cudaMemcpyAsync(dIndices + d->index_count, d->animated_indices, (size_t)ai * 4, cudaMemcpyHostToDevice, ctx->stream));
         ctx->dVertices = dVertices;
         ctx->dIndices = dIndices;
+        ctx->dAnimatedVertices = nullptr;
+        ctx->dBones = nullptr;
+        if (av)
+        {
+            float *dAnimated;
+            PT_TRY(devAlloc(ctx, &dAnimated, (size_t)av * 22, own));
+            PT_TRY(devAlloc(ctx, &ctx->dBones, (size_t)topo.boneCount * PT_BONE_STRIDE, own));
+            PT_CUDA_CHECK(ctx, cudaMemcpyAsync(dAnimated, d->animated_vertices, (size_t)av * 88, cudaMemcpyHostToDevice, ctx->stream));
+            ctx->dAnimatedVertices = dAnimated;
+        }
+        PT_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+        if (av)
+            PT_TRY(skinAnimatedVertices(ctx, d->bone_transforms));
     }
     cudaEventRecord(ev1, ctx->stream);
     PT_TRY(buildAccel(ctx, mis, n));
@@ -1349,6 +1465,8 @@ pt_status updateScene(Context *ctx, const pt_scene_update_desc *d)
         return fail(ctx, PT_ERR_INVALID_ARGUMENT, "pt_scene_update", "instance_count differs from the uploaded scene");
     if (d->point_lights && d->point_light_count > PT_MAX_LIGHT_COUNT)
         return fail(ctx, PT_ERR_INVALID_ARGUMENT, "pt_scene_update", "more than 64 point lights");
+    if (d->bone_transforms && (d->bone_count != ctx->topo.boneCount || ctx->topo.animatedVertexCount == 0))
+        return fail(ctx, PT_ERR_INVALID_ARGUMENT, "pt_scene_update", "bone_count differs from the uploaded scene");
     PT_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
     if (d->point_lights || d->directional_light)
     {
@@ -1368,10 +1486,17 @@ pt_status updateScene(Context *ctx, const pt_scene_update_desc *d)
         PT_CUDA_CHECK(ctx, cudaMemcpyAsync(const_cast<LightBlock *>(ctx->scene.lights), &lb, sizeof(lb), cudaMemcpyHostToDevice, ctx->stream));
         PT_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
     }
-    if (d->instance_transforms)
+    if (d->bone_transforms)
     {
-        for (uint32_t i = 0; i < d->instance_count; i++)
-            std::memcpy(ctx->topo.instances[i].transform, d->instance_transforms + 12 * (size_t)i, 48);
+        const pt_status st = skinAnimatedVertices(ctx, d->bone_transforms);
+        if (st != PT_OK)
+            return st;
+    }
+    if (d->instance_transforms || d->bone_transforms)
+    {
+        if (d->instance_transforms)
+            for (uint32_t i = 0; i < d->instance_count; i++)
+                std::memcpy(ctx->topo.instances[i].transform, d->instance_transforms + 12 * (size_t)i, 48);
         std::vector<MeshInstance> mis;
         bool hasAlpha = false;
         pt_status st = flattenInstances(ctx, ctx->topo, mis, hasAlpha);

@@ -91,6 +91,11 @@ struct SceneTopology
     std::vector<float> transforms; // 12 per mesh transform
     uint64_t vertexCount = 0, indexCount = 0;
     uint32_t materialCount[3] = { 0, 0, 0 };
+    // skeletal animation: animated geometries address the animated buffers, which the core keeps
+    // BEHIND the static ones (skinned vertices at vertexCount + i, animated indices at indexCount + i)
+    std::vector<uint32_t> geometryIsAnimated;
+    uint64_t animatedVertexCount = 0, animatedIndexCount = 0;
+    uint32_t boneCount = 0;
 };
 
 struct Context
@@ -107,8 +112,10 @@ struct Context
     std::vector<void *> sceneAllocs; // everything cudaMalloc'ed for the scene ...
     std::vector<void *> accelAllocs; // ... except the triangle streams + BVH, which pt_scene_update rebuilds
     SceneTopology topo;
-    const float *dVertices = nullptr;    // the reference's vertex buffer, 14 floats per vertex
+    const float *dVertices = nullptr;    // the reference's vertex buffer, 14 floats per vertex (+ the skinned vertices)
     const uint32_t *dIndices = nullptr;
+    const float *dAnimatedVertices = nullptr; // Shaders::AnimatedVertex, 22 words per vertex (bind pose)
+    float *dBones = nullptr;                  // per bone: 12 floats of the matrix + 9 of its normal matrix
     LightBlock hostLights = {};
     uint32_t sceneUpdates = 0;
     std::vector<DevTexture> hostTextures;

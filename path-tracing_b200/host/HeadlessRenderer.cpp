@@ -63,6 +63,13 @@ void HeadlessRenderer::UpdateSceneData(const std::shared_ptr<Scene> &scene, bool
             update.point_lights = reinterpret_cast<const pt_point_light *>(lights.data());
             update.point_light_count = static_cast<uint32_t>(lights.size());
             update.directional_light = reinterpret_cast<const pt_directional_light *>(&directional);
+            /* Renderer::RecordSkinningCommands (Renderer.cpp:1750-1751) */
+            const auto bones = scene->GetBoneTransforms();
+            if (scene->HasSkeletalAnimations())
+            {
+                update.bone_transforms = reinterpret_cast<const float *>(bones.data());
+                update.bone_count = static_cast<uint32_t>(bones.size());
+            }
             Check(pt_scene_update(m_Context, &update), "pt_scene_update");
         }
         return;

@@ -31,6 +31,7 @@ struct FlattenedScene
 {
     std::vector<float> Transforms; /* 12 per transform */
     std::vector<pt_geometry> Geometries;
+    std::vector<uint32_t> GeometryIsAnimated;
     std::vector<pt_mesh_record> MeshRecords;
     std::vector<pt_model> Models;
     std::vector<pt_instance> Instances;

@@ -76,21 +76,38 @@ std::unique_ptr<FlattenedScene> FlattenScene(const Scene &scene, bool loadTextur
     desc.transforms = flat->Transforms.data();
     desc.transform_count = static_cast<uint32_t>(transforms.size());
 
-    /* Geometries[] holds only non-animated geometries, addressed through geometryIndexMap
-     * (Renderer.cpp:333-350) */
+    /* The reference keeps non-animated geometries first and appends one entry per animated mesh
+     * instance, addressed through geometryIndexMap (Renderer.cpp:333-372).  The C ABI takes the scene's
+     * geometry list as it is plus the IsAnimated flags: an animated geometry's offsets address the
+     * animated vertex / index buffers, and the core skins it (skinning.comp) before baking. */
     const auto geometries = scene.GetGeometries();
     std::vector<uint32_t> geometryIndexMap(geometries.size(), 0);
+    bool anyAnimated = false;
     for (size_t i = 0; i < geometries.size(); i++)
     {
         const Geometry &geometry = geometries[i];
-        if (geometry.IsAnimated)
-            throw error("Animated geometry is not supported by the headless renderer");
         geometryIndexMap[i] = static_cast<uint32_t>(flat->Geometries.size());
         flat->Geometries.push_back(pt_geometry { geometry.VertexOffset, geometry.VertexLength, geometry.IndexOffset,
                                                  geometry.IndexLength, geometry.IsOpaque ? 1u : 0u });
+        flat->GeometryIsAnimated.push_back(geometry.IsAnimated ? 1u : 0u);
+        anyAnimated |= geometry.IsAnimated;
     }
     desc.geometries = flat->Geometries.data();
     desc.geometry_count = static_cast<uint32_t>(flat->Geometries.size());
+    if (anyAnimated)
+    {
+        static_assert(sizeof(pt_animated_vertex) == sizeof(Shaders::AnimatedVertex));
+        const auto animatedVertices = scene.GetAnimatedVertices();
+        const auto animatedIndices = scene.GetAnimatedIndices();
+        const auto bones = scene.GetBoneTransforms();
+        desc.geometry_is_animated = flat->GeometryIsAnimated.data();
+        desc.animated_vertices = reinterpret_cast<const pt_animated_vertex *>(animatedVertices.data());
+        desc.animated_vertex_count = animatedVertices.size();
+        desc.animated_indices = animatedIndices.data();
+        desc.animated_index_count = animatedIndices.size();
+        desc.bone_transforms = reinterpret_cast<const float *>(bones.data());
+        desc.bone_count = static_cast<uint32_t>(bones.size());
+    }
 
     /* one record per (model, mesh) in model order (Renderer.cpp:381-399) */
     const auto models = scene.GetModels();

@@ -20,6 +20,10 @@ import numpy as np
 VERTEX = np.dtype(
     [("position", "<f4", 3), ("texcoords", "<f4", 2), ("normal", "<f4", 3), ("tangent", "<f4", 3), ("bitangent", "<f4", 3)]
 )
+ANIMATED_VERTEX = np.dtype(
+    [("position", "<f4", 3), ("texcoords", "<f4", 2), ("normal", "<f4", 3), ("tangent", "<f4", 3), ("bitangent", "<f4", 3),
+     ("bone_indices", "<u4", 4), ("bone_weights", "<f4", 4)]
+)
 GEOMETRY = np.dtype(
     [("vertex_offset", "<u4"), ("vertex_length", "<u4"), ("index_offset", "<u4"), ("index_length", "<u4"), ("is_opaque", "<u4")]
 )
@@ -82,7 +86,7 @@ HIT = np.dtype([("instance", "<u4"), ("geometry", "<u4"), ("primitive", "<u4"), 
 TILE = np.dtype([("x0", "<u4"), ("y0", "<u4"), ("x1", "<u4"), ("y1", "<u4")])
 
 assert VERTEX.itemsize == 56 and MATERIAL_MR.itemsize == 96 and MATERIAL_SG.itemsize == 96
-assert POINT_LIGHT.itemsize == 48 and DIRECTIONAL_LIGHT.itemsize == 32 and INSTANCE.itemsize == 52
+assert ANIMATED_VERTEX.itemsize == 88 and POINT_LIGHT.itemsize == 48 and DIRECTIONAL_LIGHT.itemsize == 32 and INSTANCE.itemsize == 52
 assert HIT.itemsize == 24 and RAY.itemsize == 32
 
 SCENE_TEXTURE_OFFSET = 9
@@ -143,6 +147,13 @@ class CSceneDesc(C.Structure):
         ("directional_light", CDirectionalLight),
         ("skybox_2d", C.c_void_p),
         ("skybox_cube", C.c_void_p),
+        ("geometry_is_animated", C.c_void_p),
+        ("animated_vertices", C.c_void_p),
+        ("animated_vertex_count", C.c_uint64),
+        ("animated_indices", C.c_void_p),
+        ("animated_index_count", C.c_uint64),
+        ("bone_transforms", C.c_void_p),
+        ("bone_count", C.c_uint32),
     ]
 
 
@@ -232,6 +243,11 @@ class SceneData:
     directional_light: np.ndarray = field(default_factory=lambda: np.zeros((), DIRECTIONAL_LIGHT))
     skybox_2d: Texture | None = None
     skybox_cube: list | None = None  # six Textures: Front, Back, Up, Down, Left, Right (= +X -X +Y -Y +Z -Z)
+    # skeletal animation: geometries flagged in geometry_is_animated address these buffers
+    geometry_is_animated: np.ndarray | None = None  # (geometry_count,) uint32 or None
+    animated_vertices: np.ndarray = field(default_factory=lambda: _empty(ANIMATED_VERTEX))
+    animated_indices: np.ndarray = field(default_factory=lambda: _empty(np.uint32))
+    bone_transforms: np.ndarray = field(default_factory=lambda: np.zeros((0, 12), np.float32))
     # default camera of the scene at `camera_extent` (not part of pt_scene_desc)
     camera_extent: tuple = (0, 0)
     view_inverse: np.ndarray | None = None
@@ -297,6 +313,13 @@ class SceneData:
         d.sg_materials, d.sg_material_count = arr(self.sg_materials, MATERIAL_SG)
         d.phong_materials, d.phong_material_count = arr(self.phong_materials, MATERIAL_SG)
         d.point_lights, d.point_light_count = arr(self.point_lights, POINT_LIGHT)
+        if self.geometry_is_animated is not None and np.any(self.geometry_is_animated):
+            assert len(self.geometry_is_animated) == len(self.geometries)
+            d.geometry_is_animated, _ = arr(self.geometry_is_animated, np.uint32)
+            d.animated_vertices, d.animated_vertex_count = arr(self.animated_vertices, ANIMATED_VERTEX)
+            d.animated_indices, d.animated_index_count = arr(self.animated_indices, np.uint32)
+            bt = np.ascontiguousarray(self.bone_transforms, np.float32).reshape(-1, 12)
+            d.bone_transforms, d.bone_count = arr(bt, np.float32)
         dl = np.ascontiguousarray(self.directional_light, DIRECTIONAL_LIGHT).reshape(())
         C.memmove(C.byref(d.directional_light), dl.tobytes(), 32)
 

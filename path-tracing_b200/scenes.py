@@ -124,6 +124,27 @@ class SceneBuilder:
         self.index_count += len(indices)
         return len(self.geometries) - 1
 
+    def add_animated_geometry(self, vertices: np.ndarray, indices: np.ndarray, bone_indices: np.ndarray,
+                              bone_weights: np.ndarray, is_opaque: bool = True) -> int:
+        """A skinned geometry (Geometry::IsAnimated): its offsets address the animated vertex / index buffers
+        (SceneBuilder::AddGeometry's animated overload, Scene.cpp:100-123)."""
+        vertices = np.ascontiguousarray(vertices, sc.VERTEX)
+        indices = np.ascontiguousarray(indices, np.uint32).reshape(-1)
+        assert len(indices) % 3 == 0 and indices.max() < len(vertices)
+        av = np.zeros(len(vertices), sc.ANIMATED_VERTEX)
+        for f in ("position", "texcoords", "normal", "tangent", "bitangent"):
+            av[f] = vertices[f]
+        av["bone_indices"], av["bone_weights"] = bone_indices, bone_weights
+        if not hasattr(self, "animated_vertices"):
+            self.animated_vertices, self.animated_indices, self.animated_flags = [], [], {}
+        a_v = sum(len(v) for v in self.animated_vertices)
+        a_i = sum(len(i) for i in self.animated_indices)
+        self.geometries.append((a_v, len(vertices), a_i, len(indices), 1 if is_opaque else 0))
+        self.animated_flags[len(self.geometries) - 1] = 1
+        self.animated_vertices.append(av)
+        self.animated_indices.append(indices)
+        return len(self.geometries) - 1
+
     def add_texture(self, pixels: np.ndarray, srgb: bool) -> int:
         """Returns the bindless slot, SceneTextureOffset + i (Scene.cpp:125-140)."""
         self.textures.append(sc.Texture(np.ascontiguousarray(pixels), srgb))
@@ -231,6 +252,13 @@ class SceneBuilder:
             s.skybox_2d = self.skybox
             s.miss_flags = sc.MISS_FLAGS_SKYBOX_2D if self.skybox is not None else sc.MISS_FLAGS_NONE
         s.hit_flags = self.hit_flags
+        if getattr(self, "animated_vertices", None):
+            s.animated_vertices = np.concatenate(self.animated_vertices)
+            s.animated_indices = np.concatenate(self.animated_indices)
+            flags = np.zeros(len(self.geometries), np.uint32)
+            flags[list(self.animated_flags)] = 1
+            s.geometry_is_animated = flags
+            s.bone_transforms = np.tile(np.array([1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0], F), (int(s.animated_vertices["bone_indices"].max()) + 1, 1))
         if camera is not None:
             s.view_inverse, s.proj_inverse = camera
             s.camera_extent = tuple(extent)
@@ -837,6 +865,63 @@ def street_scene(width: int = 3840, height: int = 2160, blocks: int = 24, facade
     eye = np.array([1.2, 1.7, -length / 2 + 2.0])
     cam = camera_matrices(eye, np.array([-0.5, 2.4, 0.0]) - eye, width, height, fov_deg=62)
     return b.build(cam, (width, height))
+
+
+def skinned_scene(width: int = 160, height: int = 120, segments: int = 24, rings: int = 40, bones: int = 4,
+                  texture_size: int = 64, seed: int = 77) -> sc.SceneData:
+    """A skinned column (a lathe-turned tube with `bones` bones along its axis, linear weights between
+    neighbouring joints, up to 3 influences per vertex) bending over a static textured floor, next to a
+    static sphere — the smallest scene that exercises skinning.comp's bone loop, the mixed static /
+    animated buffers and the per-frame re-skin + rebuild.  Bone matrices come from bend_bones()."""
+    rs = np.random.default_rng(seed)
+    b = SceneBuilder()
+    n = texture_size
+    noise = value_noise(rs, n, 4)
+    t_color = b.add_texture(rgba8(0.3 + 0.6 * noise, 0.5 + 0.3 * noise, 0.7 - 0.4 * noise), srgb=True)
+    m_floor = b.add_material_mr(color=(0.8, 0.8, 0.8, 1), roughness=0.6, color_idx=t_color)
+    m_skin = b.add_material_mr(color=(0.9, 0.5, 0.3, 1), roughness=0.35, metalness=0.2, color_idx=t_color)
+    m_ball = b.add_material_mr(color=(0.9, 0.9, 1.0, 1), roughness=0.1, metalness=1.0)
+    y = np.linspace(0, 2.0, rings)
+    profile = np.stack([0.18 + 0.04 * np.sin(y * 9), y], -1)
+    v, i = lathe(profile, segments, uv_scale=(2.0, 2.0))
+    # weights: joint k sits at height k * 2 / bones; a vertex is bound to the joints around it (hat functions)
+    h = v["position"][:, 1] / 2.0 * bones
+    idx = np.zeros((len(v), 4), np.uint32)
+    wgt = np.zeros((len(v), 4), F)
+    k0 = np.clip(np.floor(h - 0.5).astype(int), 0, bones - 1)
+    for slot, dk in enumerate((0, 1, 2)):
+        k = np.clip(k0 + dk, 0, bones - 1)
+        idx[:, slot] = k
+        wgt[:, slot] = np.clip(1.0 - np.abs(h - 0.5 - k) , 0.0, 1.0)
+    wgt[:, 0] += (wgt.sum(1) == 0)
+    wgt /= wgt.sum(1, keepdims=True)
+    g_tube = b.add_animated_geometry(v, i, idx, wgt)
+    g_floor = b.add_geometry(*grid(8, 8, 6.0, 6.0, uv_scale=3.0))
+    g_ball = b.add_geometry(*sphere(0.4, 16, 12))
+    b.add_instance(b.add_model([(g_floor, m_floor, None)]))
+    b.add_instance(b.add_model([(g_tube, m_skin, None)]), translate(-0.3, 0.0, 0.0))
+    b.add_instance(b.add_model([(g_ball, m_ball, None)]), translate(0.9, 0.4, 0.3))
+    b.set_directional_light((3.0, 2.8, 2.5), (-0.4, -1.0, -0.3))
+    b.add_light((6.0, 5.0, 4.0), (1.5, 2.5, 1.5), 1.0, 0.1, 0.2)
+    eye = np.array([0.4, 1.3, 3.2])
+    cam = camera_matrices(eye, np.array([0.0, 0.9, 0.0]) - eye, width, height, fov_deg=50)
+    s = b.build(cam, (width, height))
+    s.bone_transforms = bend_bones(bones, 0.0)
+    return s
+
+
+def bend_bones(bones: int, angle_deg: float, length: float = 2.0) -> np.ndarray:
+    """(bones, 12) bone matrices (3x4 row-major = glm::mat3x4 columns) of a chain along +y whose joint k rotates
+    by angle_deg about z relative to its parent, joint k at height k * length / bones in the bind pose."""
+    out = np.zeros((bones, 12), F)
+    m = np.eye(4)
+    for k in range(bones):
+        pivot = translate(0.0, k * length / bones, 0.0).astype(np.float64)
+        a = np.radians(angle_deg)
+        rz = np.array([[np.cos(a), -np.sin(a), 0, 0], [np.sin(a), np.cos(a), 0, 0], [0, 0, 1, 0], [0, 0, 0, 1]])
+        m = m @ pivot @ rz @ np.linalg.inv(pivot)
+        out[k] = m[:3, :].astype(F).reshape(12)
+    return out
 
 
 WORKLOADS = {
