@@ -44,7 +44,22 @@ compile() { # src obj
     fi
 }
 
+# with the vendored assimp built (build_assimp.sh), the reference's own
+# SceneImporter.cpp joins the overlay instead of the stub
+ASSIMP_LIB="$OUT/assimp/libassimp.a"
+EXTRA_LIBS=()
+if [ -f "$ASSIMP_LIB" ]; then
+    link SceneImporter.cpp
+    INC+=(-I"$OUT/assimp/gen" -I"$REF/vendor/assimp/include")
+    FLAGS+=(-DPT_OVERLAY_HAS_ASSIMP)
+    EXTRA_LIBS=("$ASSIMP_LIB")
+fi
+
 REF_OBJS=()
+if [ -f "$ASSIMP_LIB" ]; then
+    compile "$OV/SceneImporter.cpp" "$OBJ/ref_SceneImporter.o"
+    REF_OBJS+=("$OBJ/ref_SceneImporter.o")
+fi
 for f in Scene SceneGraph SceneManager ExampleScenes TextureImporter Resources Core/Core Core/Config Core/Camera; do
     o="$OBJ/ref_$(echo "$f" | tr / _).o"
     compile "$OV/$f.cpp" "$o"
@@ -59,13 +74,13 @@ compile "$HERE/pt_headless.cpp" "$OBJ/pt_headless.o"
 
 echo "  LD  scene_dump"
 "$CXX" -o "$OUT/scene_dump" "$OBJ/scene_dump.o" "$OBJ/SceneFlatten.o" "$OBJ/stubs.o" "$OBJ/stb_impl.o" \
-    "${REF_OBJS[@]}" -pthread
+    "${REF_OBJS[@]}" "${EXTRA_LIBS[@]}" -pthread
 
 CORE="$REPO/path-tracing_b200/csrc/libpt_core.so"
 if [ -f "$CORE" ]; then
     echo "  LD  pt_headless"
     "$CXX" -o "$OUT/pt_headless" "$OBJ/pt_headless.o" "$OBJ/HeadlessRenderer.o" "$OBJ/SceneFlatten.o" \
-        "$OBJ/stubs.o" "$OBJ/stb_impl.o" "${REF_OBJS[@]}" "$CORE" -Wl,-rpath,'$ORIGIN/../../path-tracing_b200/csrc' -pthread
+        "$OBJ/stubs.o" "$OBJ/stb_impl.o" "${REF_OBJS[@]}" "${EXTRA_LIBS[@]}" "$CORE" -Wl,-rpath,'$ORIGIN/../../path-tracing_b200/csrc' -pthread
 else
     echo "  (libpt_core.so not built yet: skipping pt_headless)"
 fi

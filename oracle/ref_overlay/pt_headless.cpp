@@ -5,12 +5,14 @@
  * (Path-Tracing/UserInterface.cpp:1074-1092) without a window.
  *
  *   pt_headless <group> <scene> <width> <height> <spp> <bounces> <out.png>
+ *   pt_headless --file <model.gltf|.glb|.obj> <width> <height> <spp> <bounces> <out.png>   (assimp overlay)
  */
 #include <cstdio>
 
 #include "Core/Core.h"
 
 #include "HeadlessRenderer.h"
+#include "SceneImporter.h"
 #include "SceneManager.h"
 
 using namespace PathTracing;
@@ -24,10 +26,24 @@ int main(int argc, char **argv)
     }
     try
     {
-        SceneManager::Init();
-        if (std::string(argv[1]) != "Test Scenes" || std::string(argv[2]) != "Default")
-            SceneManager::SetActiveScene(argv[1], argv[2]);
-        std::shared_ptr<Scene> scene = SceneManager::GetActiveScene();
+        const bool fromFile = std::string(argv[1]) == "--file";
+        std::shared_ptr<Scene> scene;
+        if (fromFile)
+        {
+            SceneImporter::Init();
+            SceneBuilder builder;
+            SceneImporter::AddFile(builder, argv[2]);
+            scene = builder.CreateSceneShared(std::filesystem::path(argv[2]).stem().string());
+        if (scene->GetSceneCamerasCount() > 0)
+            scene->SetActiveCamera(0); /* the file's own first camera instead of the input camera */
+        }
+        else
+        {
+            SceneManager::Init();
+            if (std::string(argv[1]) != "Test Scenes" || std::string(argv[2]) != "Default")
+                SceneManager::SetActiveScene(argv[1], argv[2]);
+            scene = SceneManager::GetActiveScene();
+        }
         InputCamera::DisableInput();
 
         HeadlessRenderer renderer(0);
@@ -48,7 +64,8 @@ int main(int argc, char **argv)
             (unsigned long long)stats.rays_closest, (unsigned long long)stats.rays_shadow,
             (unsigned long long)stats.triangle_count, stats.bvh_build_ms
         );
-        SceneManager::Shutdown();
+        if (!fromFile)
+            SceneManager::Shutdown();
     }
     catch (const std::exception &e)
     {

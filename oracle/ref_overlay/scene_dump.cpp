@@ -5,6 +5,8 @@
  * turns into the committed fixture.  Built only where /root/reference exists.
  *
  *   scene_dump <group> <scene> <width> <height> <out.ptscene>
+ *   scene_dump --file <model.gltf|.glb|.obj> <width> <height> <out.ptscene>     (needs the assimp overlay:
+ *       the reference's own SceneImporter::AddFile, like SceneManager's file loaders, SceneManager.cpp:43-52)
  */
 #include <cstdio>
 #include <cstring>
@@ -13,6 +15,7 @@
 #include "Core/Core.h"
 
 #include "HeadlessRenderer.h"
+#include "SceneImporter.h"
 #include "SceneManager.h"
 
 using namespace PathTracing;
@@ -35,10 +38,23 @@ int main(int argc, char **argv)
     }
     const uint32_t width = std::atoi(argv[3]), height = std::atoi(argv[4]);
 
-    SceneManager::Init(); /* loads "Test Scenes"/"Default" like Application::Init */
-    if (std::string(argv[1]) != "Test Scenes" || std::string(argv[2]) != "Default")
-        SceneManager::SetActiveScene(argv[1], argv[2]);
-    std::shared_ptr<Scene> scene = SceneManager::GetActiveScene();
+    std::shared_ptr<Scene> scene;
+    if (std::string(argv[1]) == "--file")
+    {
+        SceneImporter::Init();
+        SceneBuilder builder;
+        SceneImporter::AddFile(builder, argv[2]);
+        scene = builder.CreateSceneShared(std::filesystem::path(argv[2]).stem().string());
+        if (scene->GetSceneCamerasCount() > 0)
+            scene->SetActiveCamera(0); /* the file's own first camera instead of the input camera */
+    }
+    else
+    {
+        SceneManager::Init(); /* loads "Test Scenes"/"Default" like Application::Init */
+        if (std::string(argv[1]) != "Test Scenes" || std::string(argv[2]) != "Default")
+            SceneManager::SetActiveScene(argv[1], argv[2]);
+        scene = SceneManager::GetActiveScene();
+    }
     InputCamera::DisableInput();
     scene->Update(0.0f); /* instance transforms become final (Scene.cpp:65-70) */
 
@@ -64,11 +80,20 @@ int main(int argc, char **argv)
     WriteChunk(out, "phong_materials", d.phong_materials, d.phong_material_count * sizeof(pt_material_phong));
     WriteChunk(out, "point_lights", d.point_lights, d.point_light_count * sizeof(pt_point_light));
     WriteChunk(out, "directional_light", &d.directional_light, sizeof(pt_directional_light));
+    if (d.geometry_is_animated)
+    {
+        WriteChunk(out, "geometry_is_animated", d.geometry_is_animated, d.geometry_count * sizeof(uint32_t));
+        WriteChunk(out, "animated_vertices", d.animated_vertices, d.animated_vertex_count * sizeof(pt_animated_vertex));
+        WriteChunk(out, "animated_indices", d.animated_indices, d.animated_index_count * sizeof(uint32_t));
+        WriteChunk(out, "bone_transforms", d.bone_transforms, d.bone_count * 48ull);
+    }
     for (uint32_t i = 0; i < d.texture_count; i++)
     {
         const pt_texture_desc &t = d.textures[i];
         const uint32_t info[4] = { t.width, t.height, t.format, t.srgb };
         WriteChunk(out, "texture_info", info, sizeof(info));
+        if (t.format >= PT_TEXTURE_BC1)
+            throw error("scene_dump: block-compressed textures are not written to fixtures");
         const uint64_t bpp = t.format == PT_TEXTURE_RGBAF32 ? 16 : 4;
         WriteChunk(out, "texture_pixels", t.pixels, bpp * t.width * t.height);
     }
@@ -88,6 +113,7 @@ int main(int argc, char **argv)
         d.transform_count, d.mesh_record_count, d.model_count, d.instance_count, d.mr_material_count,
         d.texture_count, d.point_light_count
     );
-    SceneManager::Shutdown();
+    if (std::string(argv[1]) != "--file")
+        SceneManager::Shutdown();
     return 0;
 }

@@ -30,11 +30,13 @@ bool Input::IsKeyPressed(Key) { return false; }
 bool Input::IsMouseButtonPressed(MouseButton) { return false; }
 glm::vec2 Input::GetMousePosition() { return glm::vec2(0.0f); }
 
+#ifndef PT_OVERLAY_HAS_ASSIMP
 void SceneImporter::Init() {}
 void SceneImporter::Shutdown() {}
 SceneBuilder &SceneImporter::AddFile(SceneBuilder &, const std::filesystem::path &path, TextureMapping)
 {
     throw error("SceneImporter (assimp) is not part of the overlay build: " + path.string());
 }
+#endif
 
 }

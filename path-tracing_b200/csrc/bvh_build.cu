@@ -887,20 +887,44 @@ template <typename T> pt_status devAlloc(Context *ctx, T **ptr, size_t count, st
     return PT_OK;
 }
 
-void invert3x3(const double m[9], double out[9])
+// The normal matrix of sampling.glsl:12 / skinning.comp:44, `transpose(inverse(mat4(transform)))`, for
+// a 3x4 row-major affine matrix P — evaluated the way the GLSL evaluates it: fp32 throughout, the
+// 4x4 inverse by cofactors over 2x2 sub-determinants.  (A double-precision 3x3 inverse is more
+// accurate but rounds differently from the shader in the last bit; on scenes modelled in millimetres
+// that last bit decides whether a shadow ray leaves its own triangle, i.e. whole pixels.)
+// N[j*3 + i] = inverse(A)(i, j): world normal_j = sum_i N[j*3 + i] * n_i.
+void normalMatrix(const float P[12], float N[9])
 {
-    const double det = m[0] * (m[4] * m[8] - m[5] * m[7]) - m[1] * (m[3] * m[8] - m[5] * m[6]) + m[2] * (m[3] * m[7] - m[4] * m[6]);
-    const double inv = 1.0 / det;
-    out[0] = (m[4] * m[8] - m[5] * m[7]) * inv;
-    out[1] = (m[2] * m[7] - m[1] * m[8]) * inv;
-    out[2] = (m[1] * m[5] - m[2] * m[4]) * inv;
-    out[3] = (m[5] * m[6] - m[3] * m[8]) * inv;
-    out[4] = (m[0] * m[8] - m[2] * m[6]) * inv;
-    out[5] = (m[2] * m[3] - m[0] * m[5]) * inv;
-    out[6] = (m[3] * m[7] - m[4] * m[6]) * inv;
-    out[7] = (m[1] * m[6] - m[0] * m[7]) * inv;
-    out[8] = (m[0] * m[4] - m[1] * m[3]) * inv;
+    const float A[4][4] = { { P[0], P[1], P[2], P[3] }, { P[4], P[5], P[6], P[7] }, { P[8], P[9], P[10], P[11] }, { 0.0f, 0.0f, 0.0f, 1.0f } };
+    const volatile float s0 = A[0][0] * A[1][1] - A[1][0] * A[0][1];
+    const volatile float s1 = A[0][0] * A[1][2] - A[1][0] * A[0][2];
+    const volatile float s2 = A[0][0] * A[1][3] - A[1][0] * A[0][3];
+    const volatile float s3 = A[0][1] * A[1][2] - A[1][1] * A[0][2];
+    const volatile float s4 = A[0][1] * A[1][3] - A[1][1] * A[0][3];
+    const volatile float s5 = A[0][2] * A[1][3] - A[1][2] * A[0][3];
+    const volatile float c5 = A[2][2] * A[3][3] - A[3][2] * A[2][3];
+    const volatile float c4 = A[2][1] * A[3][3] - A[3][1] * A[2][3];
+    const volatile float c3 = A[2][1] * A[3][2] - A[3][1] * A[2][2];
+    const volatile float c2 = A[2][0] * A[3][3] - A[3][0] * A[2][3];
+    const volatile float c1 = A[2][0] * A[3][2] - A[3][0] * A[2][2];
+    const volatile float c0 = A[2][0] * A[3][1] - A[3][0] * A[2][1];
+    const volatile float det = s0 * c5 - s1 * c4 + s2 * c3 + s3 * c2 - s4 * c1 + s5 * c0;
+    const float inv = 1.0f / det;
+    float B[3][3]; // rows 0-2, columns 0-2 of the inverse
+    B[0][0] = (A[1][1] * c5 - A[1][2] * c4 + A[1][3] * c3) * inv;
+    B[0][1] = (-A[0][1] * c5 + A[0][2] * c4 - A[0][3] * c3) * inv;
+    B[0][2] = (A[3][1] * s5 - A[3][2] * s4 + A[3][3] * s3) * inv;
+    B[1][0] = (-A[1][0] * c5 + A[1][2] * c2 - A[1][3] * c1) * inv;
+    B[1][1] = (A[0][0] * c5 - A[0][2] * c2 + A[0][3] * c1) * inv;
+    B[1][2] = (-A[3][0] * s5 + A[3][2] * s2 - A[3][3] * s1) * inv;
+    B[2][0] = (A[1][0] * c4 - A[1][1] * c2 + A[1][3] * c0) * inv;
+    B[2][1] = (-A[0][0] * c4 + A[0][1] * c2 - A[0][3] * c0) * inv;
+    B[2][2] = (A[3][0] * s4 - A[3][1] * s2 + A[3][3] * s0) * inv;
+    for (int j = 0; j < 3; j++)
+        for (int i = 0; i < 3; i++)
+            N[j * 3 + i] = B[i][j];
 }
+
 
 void freeAccel(Context *ctx)
 {
@@ -1106,14 +1130,7 @@ pt_status skinAnimatedVertices(Context *ctx, const float *boneTransforms)
         const float *m = boneTransforms + 12 * (size_t)b;
         float *o = bones.data() + (size_t)b * PT_BONE_STRIDE;
         std::memcpy(o, m, 48);
-        double R[9], Ri[9];
-        for (int j = 0; j < 3; j++)
-            for (int c = 0; c < 3; c++)
-                R[j * 3 + c] = m[j * 4 + c];
-        invert3x3(R, Ri);
-        for (int j = 0; j < 3; j++)
-            for (int c = 0; c < 3; c++)
-                o[12 + j * 3 + c] = (float)Ri[c * 3 + j]; // inverse transpose
+        normalMatrix(m, o + 12);
     }
     PT_CUDA_CHECK(ctx, cudaMemcpyAsync(ctx->dBones, bones.data(), bones.size() * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
     const uint32_t n = (uint32_t)t.animatedVertexCount;
@@ -1169,14 +1186,7 @@ pt_status flattenInstances(Context *ctx, const SceneTopology &t, std::vector<Mes
                         v = v + 1.0f * B[j * 4 + 3];
                     m.P[j * 4 + c] = v;
                 }
-            double R[9], Ri[9];
-            for (int j = 0; j < 3; j++)
-                for (int c = 0; c < 3; c++)
-                    R[j * 3 + c] = m.P[j * 4 + c];
-            invert3x3(R, Ri);
-            for (int j = 0; j < 3; j++)
-                for (int c = 0; c < 3; c++)
-                    m.N[j * 3 + c] = (float)Ri[c * 3 + j]; // inverse transpose
+            normalMatrix(m.P, m.N);
             m.triOffset = (uint32_t)triTotal;
             m.triCount = g.index_length / 3;
             // skinned vertices / animated indices sit behind the static ones in the device buffers

@@ -363,6 +363,11 @@ class SceneData:
             "flags": np.asarray([self.miss_flags, self.hit_flags], np.uint32),
             "texture_srgb": np.asarray([t.srgb for t in self.textures], np.uint8),
         }
+        if self.geometry_is_animated is not None:
+            items["geometry_is_animated"] = np.asarray(self.geometry_is_animated, np.uint32)
+            items["animated_vertices"] = self.animated_vertices
+            items["animated_indices"] = self.animated_indices
+            items["bone_transforms"] = np.asarray(self.bone_transforms, np.float32).reshape(-1, 12)
         if self.view_inverse is not None:
             items["view_inverse"] = np.asarray(self.view_inverse, np.float32)
             items["proj_inverse"] = np.asarray(self.proj_inverse, np.float32)
@@ -395,6 +400,9 @@ class SceneData:
             "directional_light",
         ):
             setattr(s, k, z[k])
+        if "geometry_is_animated" in z:
+            for k in ("geometry_is_animated", "animated_vertices", "animated_indices", "bone_transforms"):
+                setattr(s, k, z[k])
         s.camera_extent = tuple(int(x) for x in z["camera_extent"])
         s.miss_flags, s.hit_flags = (int(x) for x in z["flags"])
         if "view_inverse" in z:
@@ -427,6 +435,9 @@ class SceneData:
             "sg_materials": MATERIAL_SG,
             "phong_materials": MATERIAL_SG,
             "point_lights": POINT_LIGHT,
+            "geometry_is_animated": np.uint32,
+            "animated_vertices": ANIMATED_VERTEX,
+            "animated_indices": np.uint32,
         }
         while True:
             tag = f.read(24)
@@ -439,6 +450,8 @@ class SceneData:
                 setattr(s, name, np.frombuffer(payload, dtype=dtypes[name]).copy())
             elif name == "transforms":
                 s.transforms = np.frombuffer(payload, np.float32).reshape(-1, 12).copy()
+            elif name == "bone_transforms":
+                s.bone_transforms = np.frombuffer(payload, np.float32).reshape(-1, 12).copy()
             elif name == "directional_light":
                 s.directional_light = np.frombuffer(payload, DIRECTIONAL_LIGHT)[0].copy()
             elif name == "texture_info":
