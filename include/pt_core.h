@@ -537,6 +537,15 @@ PT_API uint32_t pt_test_output_stride(uint32_t mode);
 PT_API pt_status pt_test_shading(pt_context *ctx, uint32_t mode, const float *input, float *output,
                                  uint32_t count);
 
+/* Sampler probe: the production texture fetch of one bindless slot (0-8 built in, 9+ scene textures)
+ * for `count` records of (uv.xy, dPdx.xy, dPdy.xy).  use_grad = 1: textureGrad as the material
+ * fetches use it (PT/Shaders/material.glsl:62-171; sampler of PT/Renderer/Renderer.cpp:103-112:
+ * linear / linear-mip / repeat); use_grad = 0: texture() at level 0 as the any-hit and miss stages use
+ * it (anyhit.rahit:51, miss.rmiss:27).  Writes count RGBA float4.  The reference has no counterpart
+ * (its sampler is hardware); this is the parity hook for the software sampler. */
+PT_API pt_status pt_test_texture(pt_context *ctx, uint32_t slot, const float *in6, float *out4, uint32_t count,
+                                 int32_t use_grad);
+
 #ifdef __cplusplus
 }
 #endif

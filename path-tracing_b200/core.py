@@ -44,6 +44,7 @@ ABI_SYMBOLS = [
     "pt_test_input_stride",
     "pt_test_output_stride",
     "pt_test_shading",
+    "pt_test_texture",
 ]
 
 
@@ -174,6 +175,7 @@ def lib():
     L.pt_test_output_stride.argtypes = [u32]
     L.pt_test_output_stride.restype = u32
     L.pt_test_shading.argtypes = [vp, u32, vp, vp, u32]
+    L.pt_test_texture.argtypes = [vp, u32, vp, vp, u32, i32]
     _lib = L
     return L
 
@@ -345,6 +347,13 @@ class Renderer:
 
     def set_kernel_timing(self, enable: bool):
         self._check(self._L.pt_set_kernel_timing(self._h, 1 if enable else 0))
+
+    def texture_sample(self, slot: int, uv_ddx_ddy: np.ndarray, use_grad: bool = True) -> np.ndarray:
+        """The production sampler on (N, 6) records of uv, dPdx, dPdy -> (N, 4) RGBA (pt_test_texture)."""
+        a = np.ascontiguousarray(uv_ddx_ddy, np.float32).reshape(-1, 6)
+        out = np.zeros((a.shape[0], 4), np.float32)
+        self._check(self._L.pt_test_texture(self._h, slot, a.ctypes.data, out.ctypes.data, a.shape[0], 1 if use_grad else 0))
+        return out
 
     def test_shading(self, mode: int, inputs: np.ndarray) -> np.ndarray:
         """TestRenderer::ExecutePipeline equivalent (Path-Tracing-Tests/TestRenderer.cpp:79-106)."""

@@ -187,6 +187,7 @@ pt_status postProcess(Context *ctx, const pt_postprocess_params *params, uint32_
 
 // unit_kernels.cu
 pt_status testShading(Context *ctx, uint32_t mode, const float *input, float *output, uint32_t count);
+pt_status testTexture(Context *ctx, uint32_t slot, const float *in6, float *out4, uint32_t count, int32_t useGrad);
 uint32_t testInputStride(uint32_t mode);
 uint32_t testOutputStride(uint32_t mode);
 

@@ -418,6 +418,14 @@ pt_status pt_set_tuning(pt_context *ctx, const char *key, uint64_t value)
     return PT_OK;
 }
 
+pt_status pt_test_texture(pt_context *ctx, uint32_t slot, const float *in6, float *out4, uint32_t count, int32_t use_grad)
+{
+    if (!ctx)
+        return PT_ERR_INVALID_ARGUMENT;
+    cudaSetDevice(ctx->device);
+    return testTexture(ctx, slot, in6, out4, count, use_grad);
+}
+
 uint32_t pt_test_input_stride(uint32_t mode) { return testInputStride(mode); }
 uint32_t pt_test_output_stride(uint32_t mode) { return testOutputStride(mode); }
 

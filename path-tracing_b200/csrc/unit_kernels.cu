@@ -141,7 +141,47 @@ __global__ void k_test(uint32_t mode, const float *__restrict__ in, float *__res
     }
 }
 
+// texture(sampler, uv) (level 0: anyhit.rahit:51, miss.rmiss:27) / textureGrad(sampler, uv, ddx, ddy)
+// (material.glsl:62-171) of one bindless slot, one record per thread
+__global__ void k_test_texture(DeviceScene s, uint32_t slot, const float *__restrict__ in, float *__restrict__ out, uint32_t count,
+                               int useGrad)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count)
+        return;
+    const float *a = in + (size_t)i * 6;
+    const float4 r = useGrad ? textureGrad(s, slot, a[0], a[1], make_float4(a[2], a[3], a[4], a[5]))
+                             : textureLod0(s, s.textures[slot], a[0], a[1]);
+    out[(size_t)i * 4 + 0] = r.x, out[(size_t)i * 4 + 1] = r.y, out[(size_t)i * 4 + 2] = r.z, out[(size_t)i * 4 + 3] = r.w;
+}
+
 } // namespace
+
+pt_status testTexture(Context *ctx, uint32_t slot, const float *in6, float *out4, uint32_t count, int32_t useGrad)
+{
+    if (!ctx->hasScene)
+        return fail(ctx, PT_ERR_NO_SCENE, "pt_test_texture", "no scene uploaded");
+    if (slot >= ctx->scene.textureCount || (count && (!in6 || !out4)))
+        return fail(ctx, PT_ERR_INVALID_ARGUMENT, "pt_test_texture", "slot out of range or NULL buffer");
+    if (count == 0)
+        return PT_OK;
+    float *dIn = nullptr, *dOut = nullptr;
+    PT_CUDA_CHECK(ctx, cudaMalloc((void **)&dIn, (size_t)count * 24));
+    cudaError_t err = cudaMalloc((void **)&dOut, (size_t)count * 16);
+    if (err == cudaSuccess)
+        err = cudaMemcpyAsync(dIn, in6, (size_t)count * 24, cudaMemcpyHostToDevice, ctx->stream);
+    if (err == cudaSuccess)
+    {
+        k_test_texture<<<(count + 127) / 128, 128, 0, ctx->stream>>>(ctx->scene, slot, dIn, dOut, count, useGrad);
+        err = cudaMemcpyAsync(out4, dOut, (size_t)count * 16, cudaMemcpyDeviceToHost, ctx->stream);
+    }
+    if (err == cudaSuccess)
+        err = cudaStreamSynchronize(ctx->stream);
+    cudaFree(dIn);
+    cudaFree(dOut);
+    PT_CUDA_CHECK(ctx, err);
+    return PT_OK;
+}
 
 uint32_t testInputStride(uint32_t mode) { return mode < PT_TEST_MODE_COUNT ? h_in[mode] : 0; }
 uint32_t testOutputStride(uint32_t mode) { return mode < PT_TEST_MODE_COUNT ? h_out[mode] : 0; }
