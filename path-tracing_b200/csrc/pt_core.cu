@@ -112,6 +112,13 @@ pt_status pt_context_create(int32_t cuda_device, pt_context **out_ctx)
         }                                                                                                             \
     } while (0)
     PT_CREATE_CHECK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    {
+        // keep freed blocks of the stream-ordered allocator cached (bvh_build.cu: buildAccel)
+        cudaMemPool_t pool;
+        PT_CREATE_CHECK(cudaDeviceGetDefaultMemPool(&pool, cuda_device));
+        uint64_t threshold = UINT64_MAX;
+        PT_CREATE_CHECK(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &threshold));
+    }
     PT_CREATE_CHECK(cudaEventCreate(&ctx->evStart));
     PT_CREATE_CHECK(cudaEventCreate(&ctx->evStop));
     PT_CREATE_CHECK(cudaMalloc((void **)&ctx->dCounters, sizeof(DeviceCounters)));

@@ -112,6 +112,7 @@ class SceneBuilder:
         self.directional["direction"] = (-0.4, -1.0, -0.2)
         self.skybox = None
         self.hit_flags = sc.HIT_FLAGS_NONE
+        self.animated_vertices, self.animated_indices, self.animated_flags = [], [], {}
 
     def add_geometry(self, vertices: np.ndarray, indices: np.ndarray, is_opaque: bool = True) -> int:
         vertices = np.ascontiguousarray(vertices, sc.VERTEX)
@@ -135,8 +136,6 @@ class SceneBuilder:
         for f in ("position", "texcoords", "normal", "tangent", "bitangent"):
             av[f] = vertices[f]
         av["bone_indices"], av["bone_weights"] = bone_indices, bone_weights
-        if not hasattr(self, "animated_vertices"):
-            self.animated_vertices, self.animated_indices, self.animated_flags = [], [], {}
         a_v = sum(len(v) for v in self.animated_vertices)
         a_i = sum(len(i) for i in self.animated_indices)
         self.geometries.append((a_v, len(vertices), a_i, len(indices), 1 if is_opaque else 0))
@@ -252,7 +251,7 @@ class SceneBuilder:
             s.skybox_2d = self.skybox
             s.miss_flags = sc.MISS_FLAGS_SKYBOX_2D if self.skybox is not None else sc.MISS_FLAGS_NONE
         s.hit_flags = self.hit_flags
-        if getattr(self, "animated_vertices", None):
+        if self.animated_vertices:
             s.animated_vertices = np.concatenate(self.animated_vertices)
             s.animated_indices = np.concatenate(self.animated_indices)
             flags = np.zeros(len(self.geometries), np.uint32)
