@@ -197,11 +197,13 @@ pt_status postProcess(Context *ctx, const pt_postprocess_params *p, uint32_t tot
     }
     uint2 *mem = nullptr;
     void *dOut = nullptr;
-    PT_CUDA_CHECK(ctx, cudaMalloc((void **)&mem, (n + texels) * sizeof(uint2)));
-    cudaError_t err = cudaMalloc(&dOut, need);
+    // stream-ordered pool (see bvh_build.cu): repeated calls at one extent make no driver allocation
+    cudaStream_t st = ctx->stream;
+    PT_CUDA_CHECK(ctx, cudaMallocAsync((void **)&mem, (n + texels) * sizeof(uint2), st));
+    cudaError_t err = cudaMallocAsync(&dOut, need, st);
     if (err != cudaSuccess)
     {
-        cudaFree(mem);
+        cudaFreeAsync(mem, st);
         PT_CUDA_CHECK(ctx, err);
     }
     uint2 *color = mem, *cursor = mem + n;
@@ -210,7 +212,6 @@ pt_status postProcess(Context *ctx, const pt_postprocess_params *p, uint32_t tot
         bloom[l].px = cursor;
         cursor += (size_t)bloom[l].w * bloom[l].h;
     }
-    cudaStream_t st = ctx->stream;
     const uint32_t wide = (uint32_t)std::min<size_t>((n + 255) / 256, (size_t)ctx->smCount * 8);
     k_post_prefilter<<<wide, 256, 0, st>>>(ctx->accum, (uint32_t)n, (float)totalSamples, p->exposure, p->bloom_threshold, color,
                                            bloom[0].px);
@@ -231,8 +232,8 @@ pt_status postProcess(Context *ctx, const pt_postprocess_params *p, uint32_t tot
         err = cudaMemcpyAsync(out, dOut, need, cudaMemcpyDeviceToHost, st);
     if (err == cudaSuccess)
         err = cudaStreamSynchronize(st);
-    cudaFree(mem);
-    cudaFree(dOut);
+    cudaFreeAsync(mem, st);
+    cudaFreeAsync(dOut, st);
     PT_CUDA_CHECK(ctx, err);
     ctx->stats.kernel_launches = 2 + 2 * (uint64_t)(maxMip - 1);
     return PT_OK;
