@@ -158,14 +158,16 @@ def test_traversal_stats_toggle(feature):
 
 
 def test_scheduling_knobs_do_not_change_the_image(oracle_mod):
-    """Pools, slot count, hit sorting and the per-round sample budget only change scheduling: the
-    accumulated image is bit-identical (samples are parked and summed in sample order)."""
+    """Pools, slot count, hit sorting and the per-round sample budget only change scheduling, the BVH builder
+    (LBVH / PLOC at any radius) only the tree: the accumulated image is bit-identical (closest hits are
+    BVH-independent — ties in t go to the smaller triangle id — and samples are summed in sample order)."""
     s = scenes.chess_scene(320, 180, segments=24, rings=20, board_tess=32, texture_size=128)
     p = s.default_params(bounce_count=6)
     W, H, spp = 320, 180, 12
     images = []
     for knobs in ({}, {"pools": 1, "sort_hits": 0}, {"pools": 3, "slots": 200_000}, {"pools": 8, "slots": 140_000, "sbuf_mb": 4},
-                  {"pools": 2, "slots": 5000, "sbuf_mb": 1}):
+                  {"pools": 2, "slots": 5000, "sbuf_mb": 1}, {"bvh_builder": 0}, {"bvh_builder": 1, "ploc_radius": 3},
+                  {"bvh_builder": 1, "ploc_radius": 40, "pools": 1}):
         r = conftest.core.Renderer(0)
         try:
             for k, v in knobs.items():
