@@ -31,6 +31,11 @@ namespace pt
 #define PT_PREFETCH_PUSH 0 // prefetch the nearest pushed child node into L1
 #endif
 
+#ifndef PT_SHADOW_NOSORT
+#define PT_SHADOW_NOSORT 0 // occlusion rays: skip the front-to-back sort of a node's children (measured: k_shadow -3 % on
+                           // chess, -1 % dragon, +8 % street: near-first order finds occluders sooner; off)
+#endif
+
 #ifndef PT_BOX_FMA
 #define PT_BOX_FMA 0 // slab distances as one FMA per plane (precomputed org / dir, error folded into the planes)
 #endif
@@ -323,6 +328,23 @@ template <bool CLOSEST, bool ALPHA, bool STATS, int SMEM = 0> struct Traverser
             st.boxTests += 4;
             visits++;
         }
+#if PT_SHADOW_NOSORT
+        if (!CLOSEST)
+        {
+            // any hit will do: no front-to-back order, take the hit children as they are stored
+            int next = PT_CHILD_POP;
+#pragma unroll
+            for (int i = 3; i >= 0; i--)
+                if (d[i] != INFINITY)
+                {
+                    if (next != PT_CHILD_POP)
+                        push(next, 0.0f);
+                    next = c[i];
+                }
+            cur = next;
+            return;
+        }
+#endif
         // sorting network, ascending by distance (missed children carry INF)
         PT_CSWAP(0, 1)
         PT_CSWAP(2, 3)
