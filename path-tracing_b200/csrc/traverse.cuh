@@ -31,6 +31,21 @@ namespace pt
 #define PT_PREFETCH_PUSH 0 // prefetch the nearest pushed child node into L1
 #endif
 
+// the node phase of a warp goes on while more than this many lanes still look for their first leaf
+// (0 = until every lane has one; lanes cut short idle through the triangle phase)
+#ifndef PT_NODE_LOOP_LANES
+#define PT_NODE_LOOP_LANES 4 // measured on chess: 0 -> 4 = k_extend -1.5 %, k_shadow -6 %; 8 = no further gain
+#endif
+// leafStep also tests a second leaf the lane found while the first was postponed (1) or leaves it
+// to the next round of the warp (0)
+#ifndef PT_LEAF_SECOND
+#define PT_LEAF_SECOND 0 // measured: 1 -> 0 = +2.3 % chess, +2.5 % street, +2.4 % dragon
+#endif
+// the leaf phase tests ONE triangle per lane and trip of the warp instead of the whole leaf
+#ifndef PT_LEAF_ONE
+#define PT_LEAF_ONE 0
+#endif
+
 #ifndef PT_SHADOW_NOSORT
 #define PT_SHADOW_NOSORT 0 // occlusion rays: skip the front-to-back sort of a node's children (measured: k_shadow -3 % on
                            // chess, -1 % dragon, +8 % street: near-first order finds occluders sooner; off)
@@ -416,8 +431,15 @@ template <bool CLOSEST, bool ALPHA, bool STATS, int SMEM = 0> struct Traverser
         {
             const uint32_t code = (uint32_t)~leaf;
             const uint32_t first = code >> 2, count = (code & 3u) + 1;
+#if PT_LEAF_ONE
+            // one triangle per trip of the warp: the rest of the leaf waits for the next leaf phase
+            leaf = count > 1 ? encodeLeaf(first + 1, count - 1) : PT_CHILD_EMPTY;
+            const uint32_t trips = 1;
+#else
             leaf = PT_CHILD_EMPTY;
-            for (uint32_t i = 0; i < count; i++)
+            const uint32_t trips = count;
+#endif
+            for (uint32_t i = 0; i < trips; i++)
             {
                 const uint32_t tri = first + i;
                 const float4 q0 = __ldg(s.triPos + 3 * (size_t)tri);
@@ -464,19 +486,23 @@ template <bool CLOSEST, bool ALPHA, bool STATS, int SMEM = 0> struct Traverser
                 hit.b2 = b2;
                 if (!CLOSEST)
                 {
-                    cur = PT_CHILD_EMPTY; // gl_RayFlagsTerminateOnFirstHitEXT
+                    cur = leaf = PT_CHILD_EMPTY; // gl_RayFlagsTerminateOnFirstHitEXT
                     sp = 0;
                     return;
                 }
                 best = t;
                 bestFlat = flat;
             }
+#if PT_LEAF_ONE
+            return;
+#elif PT_LEAF_SECOND
             // a second leaf found while this one was postponed
             if (cur < 0)
             {
                 leaf = cur;
                 cur = PT_CHILD_POP;
             }
+#endif
         }
     }
 };
@@ -670,7 +696,7 @@ PT_DEV void tracePersistent(const DeviceScene &s, uint32_t n, uint32_t *workCoun
                     tr.nodeStep(s);
                 tr.postponeLeaf(s.triPos);
                 tr.popStep();
-            } while (__any_sync(FULL, (tr.atInternal() || tr.needsPop()) && !tr.hasLeaf()));
+            } while (__popc(__ballot_sync(FULL, (tr.atInternal() || tr.needsPop()) && !tr.hasLeaf())) > PT_NODE_LOOP_LANES);
             tr.leafStep(s);
             if (!drain)
             {
