@@ -42,6 +42,9 @@ namespace pt
 #define PT_LEAF_SECOND 0 // measured: 1 -> 0 = +2.3 % chess, +2.5 % street, +2.4 % dragon
 #endif
 // the leaf phase tests ONE triangle per lane and trip of the warp instead of the whole leaf
+#ifndef PT_POP_TWICE
+#define PT_POP_TWICE 0
+#endif
 #ifndef PT_LEAF_ONE
 #define PT_LEAF_ONE 0
 #endif
@@ -696,6 +699,9 @@ PT_DEV void tracePersistent(const DeviceScene &s, uint32_t n, uint32_t *workCoun
                     tr.nodeStep(s);
                 tr.postponeLeaf(s.triPos);
                 tr.popStep();
+#if PT_POP_TWICE
+                tr.popStep(); // an entry culled by the current best costs no extra trip
+#endif
             } while (__popc(__ballot_sync(FULL, (tr.atInternal() || tr.needsPop()) && !tr.hasLeaf())) > PT_NODE_LOOP_LANES);
             tr.leafStep(s);
             if (!drain)

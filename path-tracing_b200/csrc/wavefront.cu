@@ -29,6 +29,7 @@
 #include <cub/device/device_radix_sort.cuh>
 
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 
 namespace pt
