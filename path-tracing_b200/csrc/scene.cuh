@@ -33,7 +33,9 @@ struct __align__(16) BvhNode
 static_assert(sizeof(BvhNode) == 128, "BvhNode must be one 128-byte line");
 
 #define PT_CHILD_EMPTY 0x7fffffff
-#define PT_MAX_LEAF_TRIS 4
+#ifndef PT_MAX_LEAF_TRIS
+#define PT_MAX_LEAF_TRIS 4 // the leaf code has two bits for the count
+#endif
 
 PT_HD int encodeLeaf(uint32_t first, uint32_t count) { return ~(int)((first << 2) | (count - 1)); }
 
