@@ -537,6 +537,45 @@ PT_API uint32_t pt_test_output_stride(uint32_t mode);
 PT_API pt_status pt_test_shading(pt_context *ctx, uint32_t mode, const float *input, float *output,
                                  uint32_t count);
 
+/* ------------------------------------------------------------------------- */
+/* debug view                                            */
+/* ------------------------------------------------------------------------- */
+
+/* PT/Shaders/Debug/DebugShaderTypes.incl:18-42: the specialisation constants of the debug pipeline
+ * (Renderer::SetDebugRenderMode / SetDebugRaygenFlags / SetDebugHitGroupFlags). */
+enum {
+    PT_DEBUG_MODE_COLOR = 0, /* ambient + emissive + raster-style Cook-Torrance direct light with shadow rays */
+    PT_DEBUG_MODE_WORLD_POSITION = 1,
+    PT_DEBUG_MODE_NORMAL = 2, /* shading normal incl. the normal map */
+    PT_DEBUG_MODE_TEXTURE_COORDS = 3,
+    PT_DEBUG_MODE_MIPS = 4,   /* 0.1 * lod + 1 */
+    PT_DEBUG_MODE_GEOMETRY = 5, /* hashed colours of gl_GeometryIndexEXT / gl_PrimitiveID / gl_InstanceID */
+    PT_DEBUG_MODE_PRIMITIVE = 6,
+    PT_DEBUG_MODE_INSTANCE = 7
+};
+enum { PT_DEBUG_RAYGEN_FORCE_OPAQUE = 0x1, PT_DEBUG_RAYGEN_CULL_BACK_FACES = 0x2 /* PT_ERR_UNSUPPORTED */ };
+enum {
+    PT_DEBUG_HIT_DISABLE_COLOR_TEXTURE = 0x01,
+    PT_DEBUG_HIT_DISABLE_NORMAL_TEXTURE = 0x02,
+    PT_DEBUG_HIT_DISABLE_MIP_MAPS = 0x04,
+    PT_DEBUG_HIT_DISABLE_SHADOWS = 0x08,
+    PT_DEBUG_HIT_DX_NORMAL_TEXTURES = 0x10
+};
+typedef struct pt_debug_params {
+    uint32_t render_mode;     /* PT_DEBUG_MODE_* */
+    uint32_t raygen_flags;    /* PT_DEBUG_RAYGEN_* */
+    uint32_t hit_group_flags; /* PT_DEBUG_HIT_* */
+} pt_debug_params;
+
+/* Replaces one dispatch of the reference's debug ray-tracing pipeline (Renderer::SetPathTracingPipeline
+ * with a debug config; PT/Shaders/Debug/debugRaygen.rgen, debugClosestHit.rchit, debugAnyhit.rahit,
+ * debugMiss.rmiss): one pixel-centre ray per pixel, the selected view of the first hit, written as
+ * width*height RGBA floats (what the pipeline stores into its rgba32f image) to host memory.
+ * params->miss_flags selects the sky like in the path tracer; its other fields besides the camera
+ * are unused. */
+PT_API pt_status pt_debug_render(pt_context *ctx, const pt_render_params *params, const pt_debug_params *debug,
+                                 uint32_t width, uint32_t height, float *out_rgba);
+
 /* Sampler probe: the production texture fetch of one bindless slot (0-8 built in, 9+ scene textures)
  * for `count` records of (uv.xy, dPdx.xy, dPdy.xy).  use_grad = 1: textureGrad as the material
  * fetches use it (PT/Shaders/material.glsl:62-171; sampler of PT/Renderer/Renderer.cpp:103-112:

@@ -82,6 +82,7 @@ def lib():
         L.pto_texture_level.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p]
         L.pto_texture_sample.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint32, C.c_int32]
         L.pto_postprocess.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p]
+        L.pto_debug_render.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p]
         L.pto_round_half.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64]
         _lib = L
     return _lib
@@ -178,6 +179,17 @@ class OracleScene:
         rc = lib().pto_first_hit_aov(self._h, C.addressof(p), width, height, out.ctypes.data)
         assert rc == 0, rc
         return out.reshape(height, width)
+
+    def debug_render(self, params, width, height, mode="color", raygen_flags=0, hit_group_flags=0):
+        from importlib import import_module
+
+        core = import_module("path-tracing_b200.core")
+        d = core.DebugParams(core.DEBUG_MODES.index(mode) if isinstance(mode, str) else int(mode), raygen_flags, hit_group_flags)
+        p = params.to_c()
+        out = np.zeros((height, width, 4), np.float32)
+        rc = lib().pto_debug_render(self._h, C.addressof(p), C.addressof(d), width, height, out.ctypes.data)
+        assert rc == 0, rc
+        return out
 
     def trace_closest(self, rays):
         rays = np.ascontiguousarray(rays, self._sc.RAY)

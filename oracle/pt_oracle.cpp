@@ -1464,7 +1464,7 @@ bool rayCanHit(vec3 org, vec3 dir)
 /* closest hit with the primary any-hit shader.  Ties in t are broken towards the smaller flattened
  * triangle index so that the result does not depend on the BVH (the hardware's choice is
  * implementation-defined). */
-HitInfo traceClosest(const pto_scene &s, vec3 org, vec3 dir, float tmin, float tmax, Counters &c)
+HitInfo traceClosest(const pto_scene &s, vec3 org, vec3 dir, float tmin, float tmax, Counters &c, bool forceOpaque = false)
 {
     HitInfo hit;
     c.rays_closest++;
@@ -1519,7 +1519,7 @@ HitInfo traceClosest(const pto_scene &s, vec3 org, vec3 dir, float tmin, float t
                 continue;
             if (!(t < best || (t == best && hit.tri != PT_NO_HIT && ti < hit.tri)))
                 continue;
-            if (!tri.opaque)
+            if (!tri.opaque && !forceOpaque) /* gl_RayFlagsOpaqueEXT skips the any-hit stage */
             {
                 /* anyhit.rahit:36-65 */
                 c.alpha_c++;
@@ -1616,13 +1616,16 @@ struct TexCtx
 };
 
 /* PT/Shaders/material.glsl:62-84 */
-MaterialSample sampleMaterialMR(const pt_material_mr &m, TexCtx &tx, bool isHitFromInside)
+MaterialSample sampleMaterialMR(const pt_material_mr &m, TexCtx &tx, bool isHitFromInside, uint32_t flags = 0)
 {
     MaterialSample ret;
+    /* sampleValue(flags, HitGroupFlagsDisable*Texture, idx, Default*TextureIndex), material.glsl:4-23, 69-70 */
+    const uint32_t colorIdx = (flags & PT_DEBUG_HIT_DISABLE_COLOR_TEXTURE) ? 0u : m.color_idx;
+    const uint32_t normalIdx = (flags & PT_DEBUG_HIT_DISABLE_NORMAL_TEXTURE) ? 1u : m.normal_idx;
     const vec3 EmissiveColor = V3(m.emissive_color[0], m.emissive_color[1], m.emissive_color[2]);
     ret.EmissiveColor = (xyz(tx.grad(m.emissive_idx)) + EmissiveColor) * m.emissive_intensity;
-    ret.Color = xyz(tx.grad(m.color_idx)) * V3(m.color[0], m.color[1], m.color[2]);
-    ret.Normal = ReconstructNormalFromXY(xyz(tx.grad(m.normal_idx)));
+    ret.Color = xyz(tx.grad(colorIdx)) * V3(m.color[0], m.color[1], m.color[2]);
+    ret.Normal = ReconstructNormalFromXY(xyz(tx.grad(normalIdx)));
     ret.Roughness = tx.grad(m.roughness_idx).y * m.roughness;
     ret.Metalness = tx.grad(m.metallic_idx).z * m.metalness;
     ret.Transmission = m.transmission;
@@ -1634,13 +1637,15 @@ MaterialSample sampleMaterialMR(const pt_material_mr &m, TexCtx &tx, bool isHitF
 
 /* PT/Shaders/material.glsl:86-113 (specular-glossiness) and :115-142 (Phong: same code with
  * Shininess / ShininessIdx in the Glossiness slots — identical struct layout) */
-MaterialSample sampleMaterialSG(const pt_material_sg &m, TexCtx &tx, bool isHitFromInside)
+MaterialSample sampleMaterialSG(const pt_material_sg &m, TexCtx &tx, bool isHitFromInside, uint32_t flags = 0)
 {
     MaterialSample ret;
+    const uint32_t colorIdx = (flags & PT_DEBUG_HIT_DISABLE_COLOR_TEXTURE) ? 0u : m.color_idx;
+    const uint32_t normalIdx = (flags & PT_DEBUG_HIT_DISABLE_NORMAL_TEXTURE) ? 1u : m.normal_idx;
     const vec3 EmissiveColor = V3(m.emissive_color[0], m.emissive_color[1], m.emissive_color[2]);
     ret.EmissiveColor = (xyz(tx.grad(m.emissive_idx)) + EmissiveColor) * m.emissive_intensity;
-    ret.Color = xyz(tx.grad(m.color_idx)) * V3(m.color[0], m.color[1], m.color[2]);
-    ret.Normal = ReconstructNormalFromXY(xyz(tx.grad(m.normal_idx)));
+    ret.Color = xyz(tx.grad(colorIdx)) * V3(m.color[0], m.color[1], m.color[2]);
+    ret.Normal = ReconstructNormalFromXY(xyz(tx.grad(normalIdx)));
     ret.Transmission = m.transmission;
     ret.AttenuationColor = V3(m.attenuation_color[0], m.attenuation_color[1], m.attenuation_color[2]);
     ret.AttenuationDistance = m.attenuation_distance;
@@ -1655,7 +1660,7 @@ MaterialSample sampleMaterialSG(const pt_material_sg &m, TexCtx &tx, bool isHitF
 
 /* PT/Shaders/material.glsl:144-171 (flags is always 0 in closestHit.rchit:102) */
 MaterialSample sampleMaterial(const pto_scene &s, uint32_t materialId, vec2 texCoords, vec4 derivatives,
-                              bool isHitFromInside, bool flipNormalY, Counters &c)
+                              bool isHitFromInside, bool flipNormalY, Counters &c, uint32_t flags = 0)
 {
     uint32_t materialType;
     const uint32_t materialIndex = unpackMaterialId(materialId, materialType);
@@ -1664,13 +1669,13 @@ MaterialSample sampleMaterial(const pto_scene &s, uint32_t materialId, vec2 texC
     switch (materialType)
     {
     case PT_MATERIAL_METALLIC_ROUGHNESS:
-        ret = sampleMaterialMR(s.mr[materialIndex], tx, isHitFromInside);
+        ret = sampleMaterialMR(s.mr[materialIndex], tx, isHitFromInside, flags);
         break;
     case PT_MATERIAL_SPECULAR_GLOSSINESS:
-        ret = sampleMaterialSG(s.sg[materialIndex], tx, isHitFromInside);
+        ret = sampleMaterialSG(s.sg[materialIndex], tx, isHitFromInside, flags);
         break;
     case PT_MATERIAL_PHONG:
-        ret = sampleMaterialSG(s.phong[materialIndex], tx, isHitFromInside);
+        ret = sampleMaterialSG(s.phong[materialIndex], tx, isHitFromInside, flags);
         break;
     default:
         /* the GLSL leaves the other members undefined; zero them here */
@@ -2101,6 +2106,154 @@ const uint32_t kTestIn[PT_TEST_MODE_COUNT] = { 4, 4, 4, 2, 1, 10, 11, 6, 3, 23, 
 const uint32_t kTestOut[PT_TEST_MODE_COUNT] = { 1, 1, 1, 1, 1, 4, 4, 3, 4, 4, 8, 9, 18, 3, 2, 9 };
 
 } // namespace
+
+/* ========================================================================= */
+/* Debug pipeline: Debug/debugRaygen.rgen, debugClosestHit.rchit,            */
+/* debugAnyhit.rahit, debugMiss.rmiss                     */
+/* ========================================================================= */
+
+/* tracing.glsl:151-161 */
+float computeLod(vec4 derivatives)
+{
+    const float dudx = derivatives.x, dvdx = derivatives.y, dudy = derivatives.z, dvdy = derivatives.w;
+    const float sx = std::sqrt(dudx * dudx + dvdx * dvdx);
+    const float sy = std::sqrt(dudy * dudy + dvdy * dvdy);
+    const float smax = max(sx, sy);
+    return smax == 0.0f ? 0.0f : std::log2(smax);
+}
+
+/* debugClosestHit.rchit:141-161 */
+vec3 getRandomColor(uint32_t x)
+{
+    x *= 0x1eca7d79u;
+    x ^= x >> 20;
+    x = (x << 8) | (x >> 24);
+    x = ~x;
+    x ^= x << 5;
+    x += 0x10afe4e7u;
+    return V3((float)((x & 0xff000000u) >> 24) / 255.0f, (float)((x & 0x00ff0000u) >> 16) / 255.0f,
+              (float)((x & 0x0000ff00u) >> 8) / 255.0f);
+}
+
+/* debugClosestHit.rchit:70-139: the raster-style Cook-Torrance term of the debug view */
+vec3 debugLightContribution(vec3 lightDir, vec3 lightColor, float attenuation, vec3 V, vec3 N, vec3 color, float roughness,
+                            float metalness)
+{
+    const vec3 L = -normalize(lightDir);
+    const vec3 H = normalize(V + L);
+    const vec3 radiance = lightColor * attenuation;
+    vec3 F0 = V3(0.04f, 0.04f, 0.04f);
+    F0 = mix(F0, color, metalness);
+    /* DDDDistributionGGX */
+    const float a = roughness * roughness, a2 = a * a;
+    const float NdotH = max(dot(N, H), 0.0f), NdotH2 = NdotH * NdotH;
+    float denomD = NdotH2 * (a2 - 1.0f) + 1.0f;
+    denomD = PI * denomD * denomD;
+    const float NDF = a2 / max(denomD, 0.0001f);
+    /* DDDGeometrySmith */
+    const float NdotV = max(dot(N, V), 0.0f), NdotL = max(dot(N, L), 0.0f);
+    const float rr = roughness + 1.0f, k = (rr * rr) / 8.0f;
+    const float ggx2 = NdotV / (NdotV * (1.0f - k) + k), ggx1 = NdotL / (NdotL * (1.0f - k) + k);
+    const float G = ggx1 * ggx2;
+    /* DDDfresnelSchlick */
+    const float cosTheta = max(dot(H, V), 0.0f);
+    const vec3 F = F0 + (V3(1.0f, 1.0f, 1.0f) - F0) * std::pow(clamp(1.0f - cosTheta, 0.0f, 1.0f), 5.0f);
+    const vec3 numerator = F * (NDF * G);
+    const float denominator = 4.0f * max(dot(N, V), 0.0f) * max(dot(N, L), 0.0f);
+    const vec3 specular = numerator / max(denominator, 0.0001f);
+    vec3 kD = V3(1.0f, 1.0f, 1.0f) - F;
+    kD = kD * (1.0f - metalness);
+    return (kD * color / PI + specular) * radiance * NdotL;
+}
+
+vec4 debugPixel(const pto_scene &s, const pt_render_params &p, const pt_debug_params &dbg, uint32_t x, uint32_t y,
+                uint32_t width, uint32_t height, Counters &c)
+{
+    Ray rx, ry;
+    const Ray ray = constructPrimaryRay(V2((float)x, (float)y), V2((float)width, (float)height), toMat4(p.view_inverse),
+                                        toMat4(p.proj_inverse), V2(0.5f, 0.5f), rx, ry);
+    const bool forceOpaque = (dbg.raygen_flags & PT_DEBUG_RAYGEN_FORCE_OPAQUE) != 0;
+    const HitInfo hit = traceClosest(s, ray.Origin, ray.Direction, ray.tmin, ray.tmax, c, forceOpaque);
+    if (hit.tri == PT_NO_HIT)
+    {
+        /* debugMiss.rmiss:17-36 (no hdrToLdr here) */
+        if ((p.miss_flags & PT_MISS_FLAGS_SKYBOX_2D) != 0 && s.hasSky2D)
+        {
+            const vec3 dir = ray.Direction;
+            const float longitude = std::atan2(dir.z, dir.x), latitude = std::asin(-dir.y);
+            return V4(xyz(textureLod0(s.sky2D, V2(longitude / 2.0f / PI + 0.5f, latitude / PI + 0.5f))), 1.0f);
+        }
+        if ((p.miss_flags & PT_MISS_FLAGS_SKYBOX_CUBE) != 0 && s.hasSkyCube)
+            return V4(xyz(sampleCube(s.skyCube, ray.Direction)), 1.0f);
+        return V4(0.2f, 0.2f, 0.2f, 1.0f);
+    }
+
+    /* debugClosestHit.rchit:163-265 */
+    const FlatTri &ft = s.tris[hit.tri];
+    const pt_mesh_record &sbt = meshRecordOf(s, ft);
+    const pt_geometry &geom = s.geometries[sbt.geometry_index];
+    const mat3x4 objectToWorld = objectToWorld3x4(s.instances[ft.instance]);
+    const vec3 barycentricCoords = computeBarycentricCoords(V2(hit.b1, hit.b2));
+    Vertex v0 = getVertex(s, geom, ft.primitive * 3), v1 = getVertex(s, geom, ft.primitive * 3 + 1);
+    Vertex v2 = getVertex(s, geom, ft.primitive * 3 + 2);
+    const Vertex vertex = transformVertex(s, interpolate(v0, v1, v2, barycentricCoords), sbt.transform_index, objectToWorld);
+    const vec3 origin = ray.Origin, viewDir = ray.Direction;
+    v0 = transformVertex(s, v0, sbt.transform_index, objectToWorld);
+    v1 = transformVertex(s, v1, sbt.transform_index, objectToWorld);
+    v2 = transformVertex(s, v2, sbt.transform_index, objectToWorld);
+    vec3 dpdu, dpdv, dndu, dndv;
+    computeDpnDuv(v0, v1, v2, vertex, dpdu, dpdv, dndu, dndv);
+    vec3 dpdx, dpdy;
+    computeDpDxy(vertex.Position, origin, rx.Direction, origin, ry.Direction, vertex.Normal, dpdx, dpdy);
+    const uint32_t flags = dbg.hit_group_flags;
+    const vec4 derivatives = (flags & PT_DEBUG_HIT_DISABLE_MIP_MAPS) ? V4(0.0f, 0.0f, 0.0f, 0.0f) : computeDerivatives(dpdx, dpdy, dpdu, dpdv);
+    const bool flipYNormal = (flags & PT_DEBUG_HIT_DX_NORMAL_TEXTURES) != 0;
+    MaterialSample material = sampleMaterial(s, sbt.material_id, vertex.TexCoords, derivatives, false, flipYNormal, c, flags);
+    if (hit.decalDist != -1.0f && hit.t > hit.decalDist)
+        material.Color = mix(material.Color, hit.decalColor, hit.decalAlpha);
+    const vec3 V = -normalize(viewDir);
+    const mat3 TBN = M3(vertex.Tangent, vertex.Bitangent, vertex.Normal);
+    const vec3 N = normalize(vertex.Normal + TBN * material.Normal);
+
+    const float ambient = 0.1f;
+    vec3 totalLight = material.Color * ambient + material.EmissiveColor;
+    vec3 tmpu = vertex.Position - v0.Position, tmpv = vertex.Position - v1.Position, tmpw = vertex.Position - v2.Position;
+    const float dotu = min(0.0f, dot(tmpu, v0.Normal)), dotv = min(0.0f, dot(tmpv, v1.Normal));
+    const float dotw = min(0.0f, dot(tmpw, v2.Normal));
+    tmpu = tmpu - v0.Normal * dotu;
+    tmpv = tmpv - v1.Normal * dotv;
+    tmpw = tmpw - v2.Normal * dotw;
+    const vec3 Pp = vertex.Position + tmpu * barycentricCoords.x + tmpv * barycentricCoords.y + tmpw * barycentricCoords.z;
+    const bool shadowsDisabled = (flags & PT_DEBUG_HIT_DISABLE_SHADOWS) != 0;
+    auto checkOccluded = [&](vec3 lightDir, float dist) { return traceOccluded(s, Pp, -normalize(lightDir), 0.00001f, dist, c); };
+    const vec3 dirDirection = V3(s.directional.direction[0], s.directional.direction[1], s.directional.direction[2]);
+    const vec3 dirColor = V3(s.directional.color[0], s.directional.color[1], s.directional.color[2]);
+    if (shadowsDisabled || !checkOccluded(dirDirection, DirectionalLightDistance))
+        totalLight = totalLight + debugLightContribution(dirDirection, dirColor, 1.0f, V, N, material.Color, material.Roughness, material.Metalness);
+    for (const pt_point_light &light : s.pointLights)
+    {
+        const vec3 lightDirection = Pp - V3(light.position[0], light.position[1], light.position[2]);
+        const float dist = length(lightDirection);
+        const float attenuation = 1.0f / (light.attenuation_constant + dist * light.attenuation_linear + dist * dist * light.attenuation_quadratic);
+        if (shadowsDisabled || !checkOccluded(lightDirection, dist))
+            totalLight = totalLight + debugLightContribution(lightDirection, V3(light.color[0], light.color[1], light.color[2]), attenuation, V, N,
+                                                             material.Color, material.Roughness, material.Metalness);
+    }
+    switch (dbg.render_mode)
+    {
+    case PT_DEBUG_MODE_COLOR: return V4(totalLight, 1.0f);
+    case PT_DEBUG_MODE_WORLD_POSITION: return V4(vertex.Position, 1.0f);
+    case PT_DEBUG_MODE_NORMAL: return V4(N, 1.0f);
+    case PT_DEBUG_MODE_TEXTURE_COORDS: return V4(vertex.TexCoords.x, vertex.TexCoords.y, 0.0f, 1.0f);
+    case PT_DEBUG_MODE_MIPS: {
+        const float v = 0.1f * computeLod(derivatives) + 1.0f;
+        return V4(v, v, v, 1.0f);
+    }
+    case PT_DEBUG_MODE_GEOMETRY: return V4(getRandomColor(ft.geometry), 1.0f);
+    case PT_DEBUG_MODE_PRIMITIVE: return V4(getRandomColor(ft.primitive), 1.0f);
+    default: return V4(getRandomColor(ft.instance), 1.0f);
+    }
+}
 
 /* ========================================================================= */
 /* C ABI                                                                     */
@@ -2539,6 +2692,24 @@ int32_t pto_texture_sample(const pto_scene *s, uint32_t slot, const float *in6, 
                                 : textureLod0(t, V2(a[0], a[1]));
         out4[i * 4] = r.x, out4[i * 4 + 1] = r.y, out4[i * 4 + 2] = r.z, out4[i * 4 + 3] = r.w;
     }
+    return PT_OK;
+}
+
+int32_t pto_debug_render(const pto_scene *s, const pt_render_params *p, const pt_debug_params *dbg, uint32_t width,
+                         uint32_t height, float *out_rgba)
+{
+    if (!s || !p || !dbg || !out_rgba || dbg->render_mode > PT_DEBUG_MODE_INSTANCE)
+        return PT_ERR_INVALID_ARGUMENT;
+    if (dbg->raygen_flags & PT_DEBUG_RAYGEN_CULL_BACK_FACES)
+        return PT_ERR_UNSUPPORTED;
+    Counters c;
+    for (uint32_t y = 0; y < height; y++)
+        for (uint32_t x = 0; x < width; x++)
+        {
+            const vec4 v = debugPixel(*s, *p, *dbg, x, y, width, height, c);
+            float *o = out_rgba + 4 * ((size_t)y * width + x);
+            o[0] = v.x, o[1] = v.y, o[2] = v.z, o[3] = v.w;
+        }
     return PT_OK;
 }
 

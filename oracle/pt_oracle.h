@@ -81,6 +81,9 @@ PT_API int32_t pto_texture_sample(const pto_scene *scene, uint32_t slot, const f
  * applied to a host accumulation image of width*height float4 sums. */
 PT_API int32_t pto_postprocess(const float *accum, uint32_t width, uint32_t height, const pt_postprocess_params *params,
                                uint32_t total_samples, uint32_t output_format, void *out_pixels);
+/* The debug pipeline (same parameters as pt_debug_render): width*height RGBA floats. */
+PT_API int32_t pto_debug_render(const pto_scene *scene, const pt_render_params *params, const pt_debug_params *debug,
+                                uint32_t width, uint32_t height, float *out_rgba);
 /* binary32 -> binary16 -> binary32 (round to nearest even) of n values */
 PT_API int32_t pto_round_half(const float *in, float *out, uint64_t n);
 

@@ -45,6 +45,7 @@ ABI_SYMBOLS = [
     "pt_test_output_stride",
     "pt_test_shading",
     "pt_test_texture",
+    "pt_debug_render",
 ]
 
 
@@ -73,6 +74,13 @@ class SceneUpdateDesc(C.Structure):
                 ("bone_count", C.c_uint32)]
 
 
+class DebugParams(C.Structure):
+    """pt_debug_params: render mode + raygen / hit-group flags of the reference's debug pipeline."""
+
+    _fields_ = [("render_mode", C.c_uint32), ("raygen_flags", C.c_uint32), ("hit_group_flags", C.c_uint32)]
+
+
+DEBUG_MODES = ("color", "world_position", "normal", "texture_coords", "mips", "geometry", "primitive", "instance")
 TONE_MAPPING_SDR, TONE_MAPPING_HDR = 0, 1
 OUTPUT_RGBA8_SRGB, OUTPUT_RGBAF32 = 0, 1
 
@@ -176,6 +184,7 @@ def lib():
     L.pt_test_output_stride.restype = u32
     L.pt_test_shading.argtypes = [vp, u32, vp, vp, u32]
     L.pt_test_texture.argtypes = [vp, u32, vp, vp, u32, i32]
+    L.pt_debug_render.argtypes = [vp, vp, vp, u32, u32, vp]
     _lib = L
     return L
 
@@ -347,6 +356,15 @@ class Renderer:
 
     def set_kernel_timing(self, enable: bool):
         self._check(self._L.pt_set_kernel_timing(self._h, 1 if enable else 0))
+
+    def debug_render(self, params: sc.RenderParams, width: int, height: int, mode="color", raygen_flags: int = 0,
+                     hit_group_flags: int = 0) -> np.ndarray:
+        """One frame of the reference's debug pipeline (Debug/debug*.r*): (H, W, 4) float32."""
+        d = DebugParams(DEBUG_MODES.index(mode) if isinstance(mode, str) else int(mode), raygen_flags, hit_group_flags)
+        p = params.to_c()
+        out = np.zeros((height, width, 4), np.float32)
+        self._check(self._L.pt_debug_render(self._h, C.addressof(p), C.addressof(d), width, height, out.ctypes.data))
+        return out
 
     def texture_sample(self, slot: int, uv_ddx_ddy: np.ndarray, use_grad: bool = True) -> np.ndarray:
         """The production sampler on (N, 6) records of uv, dPdx, dPdy -> (N, 4) RGBA (pt_test_texture)."""

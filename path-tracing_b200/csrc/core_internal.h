@@ -178,6 +178,8 @@ pt_status allocSortTemp(Context *ctx, size_t slots);
 pt_status renderSamples(Context *ctx, const pt_render_params *params, uint32_t firstSample, uint32_t sampleCount,
                         const pt_tile *tiles, uint32_t tileCount);
 pt_status firstHitAov(Context *ctx, const pt_render_params *params, uint32_t width, uint32_t height, pt_hit *out);
+pt_status debugRender(Context *ctx, const pt_render_params *params, const pt_debug_params *debug, uint32_t width, uint32_t height,
+                      float *out);
 pt_status traceClosest(Context *ctx, const pt_ray *rays, uint64_t n, pt_hit *out);
 pt_status traceOcclusion(Context *ctx, const pt_ray *rays, uint64_t n, uint8_t *out);
 

@@ -425,6 +425,15 @@ pt_status pt_set_tuning(pt_context *ctx, const char *key, uint64_t value)
     return PT_OK;
 }
 
+pt_status pt_debug_render(pt_context *ctx, const pt_render_params *params, const pt_debug_params *debug, uint32_t width,
+                          uint32_t height, float *out_rgba)
+{
+    if (!ctx)
+        return PT_ERR_INVALID_ARGUMENT;
+    cudaSetDevice(ctx->device);
+    return debugRender(ctx, params, debug, width, height, out_rgba);
+}
+
 pt_status pt_test_texture(pt_context *ctx, uint32_t slot, const float *in6, float *out4, uint32_t count, int32_t use_grad)
 {
     if (!ctx)

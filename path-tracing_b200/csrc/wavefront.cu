@@ -309,7 +309,8 @@ __device__ __forceinline__ vec3 reconstructNormalFromXY(float4 t)
 }
 
 __device__ __forceinline__ MaterialSample sampleMaterial(const DeviceScene &s, uint32_t materialId, float u, float v,
-                                                         float4 deriv, bool inside, bool flipNormalY, uint32_t *texels)
+                                                         float4 deriv, bool inside, bool flipNormalY, uint32_t *texels,
+                                                         uint32_t debugFlags = 0)
 {
     const uint32_t type = materialId & 0xffu, index = materialId >> 8;
     MaterialSample r;
@@ -335,7 +336,10 @@ __device__ __forceinline__ MaterialSample sampleMaterial(const DeviceScene &s, u
     if (type == 0)
     {
         // material.glsl:62-84
-        const float4 e = tex(q4.w), c = tex(q5.x), nm = tex(q5.y);
+        // (debug view only: sampleValue(flags, HitGroupFlagsDisable*Texture, ...), material.glsl:69-70)
+        const float colorSlot = (debugFlags & PT_DEBUG_HIT_DISABLE_COLOR_TEXTURE) ? __uint_as_float(0u) : q5.x;
+        const float normalSlot = (debugFlags & PT_DEBUG_HIT_DISABLE_NORMAL_TEXTURE) ? __uint_as_float(1u) : q5.y;
+        const float4 e = tex(q4.w), c = tex(colorSlot), nm = tex(normalSlot);
         r.EmissiveColor = (V3(e) + V3(q0)) * q0.w;
         r.Color = V3(c) * V3(q1);
         r.Normal = reconstructNormalFromXY(nm);
@@ -347,7 +351,9 @@ __device__ __forceinline__ MaterialSample sampleMaterial(const DeviceScene &s, u
     else
     {
         // material.glsl:86-113 / 115-142 (specular-glossiness and Phong share the layout)
-        const float4 e = tex(q4.z), c = tex(q4.w), nm = tex(q5.x);
+        const float colorSlot = (debugFlags & PT_DEBUG_HIT_DISABLE_COLOR_TEXTURE) ? __uint_as_float(0u) : q4.w;
+        const float normalSlot = (debugFlags & PT_DEBUG_HIT_DISABLE_NORMAL_TEXTURE) ? __uint_as_float(1u) : q5.x;
+        const float4 e = tex(q4.z), c = tex(colorSlot), nm = tex(normalSlot);
         r.EmissiveColor = (V3(e) + V3(q0)) * q0.w;
         r.Color = V3(c) * V3(q1);
         r.Normal = reconstructNormalFromXY(nm);
@@ -724,6 +730,195 @@ template <bool ALPHA> __global__ void k_first_hit(DeviceScene s, CameraMatrices 
     TraversalStats st;
     traverse<true, ALPHA, false>(s, pr.origin, pr.direction, 0.00001f, 10000.0f, hit, decal, st);
     out[i] = toPtHit(s, hit);
+}
+
+// ---------------------------------------------------------------------------------------------
+// The reference's debug pipeline (Debug/debugRaygen.rgen, debugClosestHit.rchit, debugAnyhit.rahit,
+// debugMiss.rmiss): one pixel-centre ray per pixel, a view of the first hit.  A diagnostics path,
+// one thread per pixel with the plain per-thread traversal.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ vec3 debugRandomColor(uint32_t x) // debugClosestHit.rchit:141-161
+{
+    x *= 0x1eca7d79u;
+    x ^= x >> 20;
+    x = (x << 8) | (x >> 24);
+    x = ~x;
+    x ^= x << 5;
+    x += 0x10afe4e7u;
+    return V3((float)((x & 0xff000000u) >> 24) / 255.0f, (float)((x & 0x00ff0000u) >> 16) / 255.0f,
+              (float)((x & 0x0000ff00u) >> 8) / 255.0f);
+}
+
+// debugClosestHit.rchit:70-139
+__device__ __forceinline__ vec3 debugLightContribution(vec3 lightDir, vec3 lightColor, float attenuation, vec3 V, vec3 N, vec3 color,
+                                                       float roughness, float metalness)
+{
+    const vec3 L = -normalize(lightDir);
+    const vec3 H = normalize(V + L);
+    const vec3 radiance = lightColor * attenuation;
+    const vec3 F0 = mix(V3(0.04f), color, metalness);
+    const float a = roughness * roughness, a2 = a * a;
+    const float NdotH = fmaxf(dot(N, H), 0.0f), NdotH2 = NdotH * NdotH;
+    float denomD = NdotH2 * (a2 - 1.0f) + 1.0f;
+    denomD = PT_PI * denomD * denomD;
+    const float NDF = a2 / fmaxf(denomD, 0.0001f);
+    const float NdotV = fmaxf(dot(N, V), 0.0f), NdotL = fmaxf(dot(N, L), 0.0f);
+    const float rr = roughness + 1.0f, k = (rr * rr) / 8.0f;
+    const float ggx2 = NdotV / (NdotV * (1.0f - k) + k), ggx1 = NdotL / (NdotL * (1.0f - k) + k);
+    const float G = ggx1 * ggx2;
+    const float cosTheta = fmaxf(dot(H, V), 0.0f);
+    const vec3 F = F0 + (V3(1.0f) - F0) * powf(clampf(1.0f - cosTheta, 0.0f, 1.0f), 5.0f);
+    const vec3 numerator = F * (NDF * G);
+    const float denominator = 4.0f * fmaxf(dot(N, V), 0.0f) * fmaxf(dot(N, L), 0.0f);
+    const vec3 specular = numerator / fmaxf(denominator, 0.0001f);
+    vec3 kD = V3(1.0f) - F;
+    kD = kD * (1.0f - metalness);
+    return (kD * color / PT_PI + specular) * radiance * NdotL;
+}
+
+template <bool ALPHA_PRIMARY, bool ALPHA_SHADOW>
+__global__ void k_debug(DeviceScene s, CameraMatrices cam, uint32_t width, uint32_t height, uint32_t missFlags, pt_debug_params dbg,
+                        float4 *out)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= width * height)
+        return;
+    const uint32_t px = i % width, py = i / width;
+    const PrimaryRays pr = constructPrimaryRay((float)px, (float)py, (float)width, (float)height, cam, V2(0.5f, 0.5f),
+                                               V2(0.0f, 0.0f), 0.0f, 0.0f);
+    Hit hit;
+    Decal decal;
+    TraversalStats st;
+    traverse<true, ALPHA_PRIMARY, false>(s, pr.origin, pr.direction, 0.00001f, 10000.0f, hit, decal, st);
+    if (hit.tri == 0xffffffffu)
+    {
+        // debugMiss.rmiss:17-36 (no hdrToLdr here)
+        vec3 c = V3(0.2f, 0.2f, 0.2f);
+        if ((missFlags & PT_MISS_FLAGS_SKYBOX_2D) && s.hasSky2D)
+        {
+            const float longitude = atan2f(pr.direction.z, pr.direction.x), latitude = asinf(-pr.direction.y);
+            c = V3(textureLod0(s, s.sky2D, longitude / 2.0f / PT_PI + 0.5f, latitude / PT_PI + 0.5f));
+        }
+        else if ((missFlags & PT_MISS_FLAGS_SKYBOX_CUBE) && s.skyCubeSlot)
+            c = V3(sampleCube(s, s.skyCubeSlot, pr.direction));
+        out[i] = make_float4(c.x, c.y, c.z, 1.0f);
+        return;
+    }
+
+    // debugClosestHit.rchit:163-265 on the baked world-space triangle
+    const uint32_t tri = hit.tri;
+    const vec3 bary = V3(1.0f - hit.b1 - hit.b2, hit.b1, hit.b2);
+    const float4 q0 = __ldg(s.triPos + 3 * (size_t)tri), q1 = __ldg(s.triPos + 3 * (size_t)tri + 1);
+    const float4 q2 = __ldg(s.triPos + 3 * (size_t)tri + 2);
+    const TriShade &ts = s.triShade[tri];
+    const float4 a0 = __ldg(&ts.a[0]), a1 = __ldg(&ts.a[1]), a2 = __ldg(&ts.a[2]), a3 = __ldg(&ts.a[3]);
+    const float4 a4 = __ldg(&ts.a[4]), a5 = __ldg(&ts.a[5]), a6 = __ldg(&ts.a[6]), a7 = __ldg(&ts.a[7]);
+    const float4 a8 = __ldg(&ts.a[8]);
+    const uint32_t materialId = __float_as_uint(q2.w);
+    const vec3 p0 = V3(q0), p1 = V3(q1), p2 = V3(q2);
+    const vec3 n0r = V3(a0.x, a0.y, a0.z), n1r = V3(a0.w, a1.x, a1.y), n2r = V3(a1.z, a1.w, a2.x);
+    const vec3 t0r = V3(a2.y, a2.z, a2.w), t1r = V3(a3.x, a3.y, a3.z), t2r = V3(a3.w, a4.x, a4.y);
+    const vec3 b0r = V3(a4.z, a4.w, a5.x), b1r = V3(a5.y, a5.z, a5.w), b2r = V3(a6.x, a6.y, a6.z);
+    const vec2 uv0 = V2(a6.w, a7.x), uv1 = V2(a7.y, a7.z), uv2 = V2(a7.w, a8.x);
+    const vec3 position = p0 * bary.x + p1 * bary.y + p2 * bary.z;
+    const vec2 texCoords = uv0 * bary.x + uv1 * bary.y + uv2 * bary.z;
+    const vec3 normal = normalize(n0r * bary.x + n1r * bary.y + n2r * bary.z);
+    const vec3 tangent = normalize(t0r * bary.x + t1r * bary.y + t2r * bary.z);
+    const vec3 bitangent = normalize(b0r * bary.x + b1r * bary.y + b2r * bary.z);
+    const vec3 n0 = normalize(n0r), n1 = normalize(n1r), n2 = normalize(n2r);
+
+    // tracing.glsl:2-28
+    vec3 dpdu, dpdv;
+    {
+        const vec3 edge1 = p1 - p0, edge2 = p2 - p0;
+        const vec2 duv1 = uv1 - uv0, duv2 = uv2 - uv0;
+        const float det = duv1.x * duv2.y - duv2.x * duv1.y;
+        if (fabsf(det) < 1e-8f)
+        {
+            dpdu = tangent;
+            dpdv = bitangent;
+        }
+        else
+        {
+            const float invDet = 1.0f / det;
+            dpdu = (duv2.y * edge1 - duv1.y * edge2) * invDet;
+            dpdv = (-duv2.x * edge1 + duv1.x * edge2) * invDet;
+        }
+    }
+    // tracing.glsl:31-41 with both offset rays starting at the camera
+    vec3 dpdx, dpdy;
+    {
+        const float d = -dot(normal, position);
+        const float tx = (-dot(normal, pr.origin) - d) / dot(normal, pr.rxDirection);
+        const float ty = (-dot(normal, pr.origin) - d) / dot(normal, pr.ryDirection);
+        dpdx = (pr.origin + tx * pr.rxDirection) - position;
+        dpdy = (pr.origin + ty * pr.ryDirection) - position;
+    }
+    const uint32_t flags = dbg.hit_group_flags;
+    const float4 derivatives =
+        (flags & PT_DEBUG_HIT_DISABLE_MIP_MAPS) ? make_float4(0.0f, 0.0f, 0.0f, 0.0f) : computeDerivatives(dpdx, dpdy, dpdu, dpdv);
+    MaterialSample material = sampleMaterial(s, materialId, texCoords.x, texCoords.y, derivatives, false,
+                                             (flags & PT_DEBUG_HIT_DX_NORMAL_TEXTURES) != 0, nullptr, flags);
+    if (ALPHA_PRIMARY && decal.dist != -1.0f && hit.t > decal.dist)
+        material.Color = mix(material.Color, V3(decal.r, decal.g, decal.b), decal.a);
+    const vec3 V = -normalize(pr.direction);
+    const mat3 TBN = mat3 { tangent, bitangent, normal };
+    const vec3 N = normalize(normal + mul(TBN, material.Normal));
+
+    vec3 result;
+    switch (dbg.render_mode)
+    {
+    case PT_DEBUG_MODE_WORLD_POSITION: result = position; break;
+    case PT_DEBUG_MODE_NORMAL: result = N; break;
+    case PT_DEBUG_MODE_TEXTURE_COORDS: result = V3(texCoords.x, texCoords.y, 0.0f); break;
+    case PT_DEBUG_MODE_MIPS: {
+        // tracing.glsl:151-161
+        const float sx = sqrtf(derivatives.x * derivatives.x + derivatives.y * derivatives.y);
+        const float sy = sqrtf(derivatives.z * derivatives.z + derivatives.w * derivatives.w);
+        const float smax = fmaxf(sx, sy);
+        result = V3(0.1f * (smax == 0.0f ? 0.0f : log2f(smax)) + 1.0f);
+        break;
+    }
+    case PT_DEBUG_MODE_GEOMETRY: result = debugRandomColor(__float_as_uint(a8.z)); break;
+    case PT_DEBUG_MODE_PRIMITIVE: result = debugRandomColor(__float_as_uint(a8.w)); break;
+    case PT_DEBUG_MODE_INSTANCE: result = debugRandomColor(__float_as_uint(a8.y)); break;
+    default: {
+        const float ambient = 0.1f;
+        vec3 totalLight = material.Color * ambient + material.EmissiveColor;
+        vec3 tmpu = position - p0, tmpv = position - p1, tmpw = position - p2;
+        const float dotu = fminf(0.0f, dot(tmpu, n0)), dotv = fminf(0.0f, dot(tmpv, n1)), dotw = fminf(0.0f, dot(tmpw, n2));
+        tmpu = tmpu - n0 * dotu;
+        tmpv = tmpv - n1 * dotv;
+        tmpw = tmpw - n2 * dotw;
+        const vec3 Pp = position + tmpu * bary.x + tmpv * bary.y + tmpw * bary.z;
+        const bool shadowsDisabled = (flags & PT_DEBUG_HIT_DISABLE_SHADOWS) != 0;
+        auto occluded = [&](vec3 lightDir, float dist) {
+            Hit h;
+            Decal dd;
+            TraversalStats st2;
+            traverse<false, ALPHA_SHADOW, false>(s, Pp, -normalize(lightDir), 0.00001f, dist, h, dd, st2);
+            return h.tri != 0xffffffffu;
+        };
+        const LightBlock *lb = s.lights;
+        const vec3 dirDirection = V3(__ldg(&lb->dirDirection)), dirColor = V3(__ldg(&lb->dirColor));
+        if (shadowsDisabled || !occluded(dirDirection, 100000.0f))
+            totalLight = totalLight + debugLightContribution(dirDirection, dirColor, 1.0f, V, N, material.Color, material.Roughness,
+                                                             material.Metalness);
+        const uint32_t count = __ldg(&lb->count);
+        for (uint32_t li = 0; li < count; li++)
+        {
+            const float4 lc = __ldg(&lb->point[li * 3]), lp = __ldg(&lb->point[li * 3 + 1]), la = __ldg(&lb->point[li * 3 + 2]);
+            const vec3 lightDirection = Pp - V3(lp);
+            const float dist = length(lightDirection);
+            const float attenuation = 1.0f / (la.x + dist * la.y + dist * dist * la.z);
+            if (shadowsDisabled || !occluded(lightDirection, dist))
+                totalLight = totalLight + debugLightContribution(lightDirection, V3(lc), attenuation, V, N, material.Color,
+                                                                 material.Roughness, material.Metalness);
+        }
+        result = totalLight;
+    }
+    }
+    out[i] = make_float4(result.x, result.y, result.z, 1.0f);
 }
 
 template <bool ALPHA> __global__ void k_trace_closest(DeviceScene s, const pt_ray *rays, uint64_t n, pt_hit *out)
@@ -1111,6 +1306,38 @@ pt_status firstHitAov(Context *ctx, const pt_render_params *params, uint32_t wid
     if (err == cudaSuccess)
         err = cudaStreamSynchronize(ctx->stream);
     cudaFree(dOut);
+    PT_CUDA_CHECK(ctx, err);
+    return PT_OK;
+}
+
+pt_status debugRender(Context *ctx, const pt_render_params *params, const pt_debug_params *dbg, uint32_t width, uint32_t height,
+                      float *out)
+{
+    if (!params || !dbg || !out || width == 0 || height == 0 || dbg->render_mode > PT_DEBUG_MODE_INSTANCE)
+        return fail(ctx, PT_ERR_INVALID_ARGUMENT, "pt_debug_render", "bad argument");
+    if (dbg->raygen_flags & PT_DEBUG_RAYGEN_CULL_BACK_FACES)
+        return fail(ctx, PT_ERR_UNSUPPORTED, "pt_debug_render", "back-face culling (gl_RayFlagsCullBackFacingTrianglesEXT) is not supported");
+    if (!ctx->hasScene)
+        return fail(ctx, PT_ERR_NO_SCENE, "pt_debug_render", "no scene uploaded");
+    const size_t n = (size_t)width * height;
+    float4 *dOut = nullptr;
+    PT_CUDA_CHECK(ctx, cudaMallocAsync((void **)&dOut, n * sizeof(float4), ctx->stream));
+    const uint32_t grid = (uint32_t)((n + 127) / 128);
+    const bool alphaScene = ctx->scene.hasAlpha != 0;
+    const bool alphaPrimary = alphaScene && !(dbg->raygen_flags & PT_DEBUG_RAYGEN_FORCE_OPAQUE);
+    const CameraMatrices cam = toCamera(params);
+    if (alphaPrimary)
+        k_debug<true, true><<<grid, 128, 0, ctx->stream>>>(ctx->scene, cam, width, height, params->miss_flags, *dbg, dOut);
+    else if (alphaScene)
+        k_debug<false, true><<<grid, 128, 0, ctx->stream>>>(ctx->scene, cam, width, height, params->miss_flags, *dbg, dOut);
+    else
+        k_debug<false, false><<<grid, 128, 0, ctx->stream>>>(ctx->scene, cam, width, height, params->miss_flags, *dbg, dOut);
+    cudaError_t err = cudaGetLastError();
+    if (err == cudaSuccess)
+        err = cudaMemcpyAsync(out, dOut, n * sizeof(float4), cudaMemcpyDeviceToHost, ctx->stream);
+    if (err == cudaSuccess)
+        err = cudaStreamSynchronize(ctx->stream);
+    cudaFreeAsync(dOut, ctx->stream);
     PT_CUDA_CHECK(ctx, err);
     return PT_OK;
 }
