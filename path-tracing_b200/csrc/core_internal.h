@@ -173,6 +173,10 @@ void freeScene(Context *ctx);
 pt_status uploadTextureSlot(Context *ctx, uint32_t slot, const pt_texture_desc *tex);
 pt_status updateScene(Context *ctx, const pt_scene_update_desc *desc);
 
+// textures.cu
+pt_status createTexture(Context *ctx, const pt_texture_desc &desc, DevTexture &out, void **outAlloc);
+pt_texture_desc defaultTexture(const uint32_t *rgba, bool srgb);
+
 // wavefront.cu
 pt_status allocSortTemp(Context *ctx, size_t slots);
 pt_status renderSamples(Context *ctx, const pt_render_params *params, uint32_t firstSample, uint32_t sampleCount,

@@ -7,7 +7,7 @@ root=$(cd "$(dirname "$0")/.." && pwd)
 out=$root/scratch/variants/$name
 mkdir -p "$out"
 cd "$root/path-tracing_b200/csrc"
-for f in pt_core bvh_build wavefront postprocess unit_kernels; do
+for f in pt_core bvh_build textures wavefront postprocess unit_kernels; do
   nvcc -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -lineinfo -fmad=false \
        -Xcompiler -fPIC,-fvisibility=hidden --expt-relaxed-constexpr -Wno-deprecated-gpu-targets "$@" \
        -c $f.cu -o "$out/$f.o" &
