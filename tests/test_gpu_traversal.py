@@ -111,3 +111,35 @@ def test_edge_cases(oracle_mod):
             r.update_scene_data(s)
             o = oracle_mod.OracleScene(s)
             compare_hits(r.first_hit_aov(s.default_params(), 64, 64), o.first_hit_aov(s.default_params(), 64, 64))
+
+
+@pytest.mark.parametrize("builder", [0, 1])
+def test_pathological_geometry_builds_and_renders(builder):
+    """Many identical triangles, zero-area triangles, a NaN vertex and one huge triangle among tiny ones:
+    both BVH builders terminate (PLOC's pair order guarantees progress on equal and on non-finite boxes) and
+    the finite part of the scene is still hit."""
+    rs = np.random.default_rng(4)
+    n = 3000
+    v = np.zeros(3 * n, sc.VERTEX)
+    tri = np.array([[-0.2, -0.2, 0.0], [0.2, -0.2, 0.0], [0.0, 0.2, 0.0]], np.float32)
+    v["position"] = np.tile(tri, (n, 1))                       # n copies of one triangle
+    v["position"][300:600] = 0.5                                # 100 point triangles
+    v["position"][600:900] += rs.uniform(-1, 1, (100, 1, 3)).repeat(3, 1).reshape(300, 3)  # scattered small ones
+    v["position"][900:903] = [[-50, -50, 5], [50, -50, 5], [0, 80, 5]]                    # a huge backdrop
+    v["position"][903, 0] = np.nan                              # a NaN vertex
+    v["normal"] = (0, 0, -1)
+    v["tangent"], v["bitangent"] = (1, 0, 0), (0, 1, 0)
+    b = scenes.SceneBuilder()
+    g = b.add_geometry(v, np.arange(3 * n, dtype=np.uint32))
+    b.add_instance(b.add_model([(g, b.add_material_mr(), None)]))
+    s = b.build(scenes.camera_matrices((0, 0, -3), (0, 0, 1), 64, 64), (64, 64))
+    with conftest.core.Renderer(0) as r:
+        r.set_tuning("bvh_builder", builder)
+        r.update_scene_data(s)
+        aov = r.first_hit_aov(s.default_params(), 64, 64)
+        assert (aov["instance"] != sc.NO_HIT).mean() > 0.9     # the backdrop fills the frame
+        assert aov["primitive"][32, 32] < n and aov["t"][32, 32] == pytest.approx(3.0, abs=1e-3)  # a copy at z = 0: the lowest id wins
+        assert aov["primitive"][32, 32] == 0
+        r.on_resize(64, 64)
+        r.render(2, params=s.default_params(bounce_count=3))
+        assert np.isfinite(r.read_accumulation()).all()
