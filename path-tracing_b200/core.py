@@ -145,6 +145,32 @@ def write_png(path: str, rgba8: np.ndarray):
                 chunk(b"IDAT", zlib.compress(raw, 6)) + chunk(b"IEND", b""))
 
 
+def write_hdr(path: str, rgba: np.ndarray):
+    """Radiance .hdr (RGBE, flat scanlines) of a float image — the reference writes OutputFormat::Hdr with
+    stbi_write_hdr (Path-Tracing/Renderer/OutputSaver.cpp:240-245); same encoding rule: shared exponent of the
+    largest component, mantissas truncated."""
+    rgb = np.ascontiguousarray(rgba[..., :3], np.float32)
+    h, w = rgb.shape[:2]
+    m = rgb.max(-1)
+    mant, exp = np.frexp(m)  # m = mant * 2^exp, mant in [0.5, 1)
+    scale = np.where(m < 1e-32, 0.0, mant * 256.0 / np.where(m < 1e-32, 1.0, m))
+    out = np.zeros((h, w, 4), np.uint8)
+    out[..., :3] = (rgb * scale[..., None]).astype(np.uint8)
+    out[..., 3] = np.where(m < 1e-32, 0, exp + 128).astype(np.uint8)
+    with open(path, "wb") as f:
+        f.write(b"#?RADIANCE\nFORMAT=32-bit_rle_rgbe\n\n" + f"-Y {h} +X {w}\n".encode() + out.tobytes())
+
+
+def write_tga(path: str, rgba8: np.ndarray):
+    """Uncompressed 32-bit TGA, top-left origin (OutputFormat::Tga, stbi_write_tga without RLE)."""
+    import struct
+
+    h, w = rgba8.shape[:2]
+    bgra = np.ascontiguousarray(rgba8[..., [2, 1, 0, 3]], np.uint8)
+    with open(path, "wb") as f:
+        f.write(struct.pack("<BBBHHBHHHHBB", 0, 0, 2, 0, 0, 0, 0, 0, w, h, 32, 0x28) + bgra.tobytes())
+
+
 _lib = None
 
 
@@ -310,6 +336,14 @@ class Renderer:
         """OutputSaver::WriteImage for OutputFormat::Png (Path-Tracing/Renderer/OutputSaver.cpp:227-253):
         8-bit RGBA, rows top to bottom."""
         write_png(path, self.postprocess(hdr=False, **postprocess_args))
+
+    def save_hdr(self, path: str, **postprocess_args):
+        """OutputFormat::Hdr: the chain without the tone curve, written as Radiance RGBE."""
+        write_hdr(path, self.postprocess(hdr=True, **postprocess_args))
+
+    def save_tga(self, path: str, **postprocess_args):
+        """OutputFormat::Tga: the same 8-bit sRGB image as the PNG."""
+        write_tga(path, self.postprocess(hdr=False, **postprocess_args))
 
     def readback_into(self, host_ptr: int, nbytes: int):
         """pt_readback into caller-owned (e.g. pinned) host memory."""

@@ -103,3 +103,32 @@ def test_small_frames_skip_bloom(oracle_mod):
     acc = np.full((4, 6, 4), 8.0, np.float32)
     hdr = oracle_mod.postprocess(acc, 2, bloom_intensity=1.0, hdr=True)
     assert (hdr[..., :3] == half(np.float32(1.0) * np.float32(0.1) * np.float32(3.0) + np.float32(4.0))).all()
+
+
+def test_output_file_writers(tmp_path):
+    """The Python mirror's .hdr (RGBE) and .tga writers round-trip what they are given."""
+    import importlib
+    import os
+
+    core = importlib.import_module("path-tracing_b200.core")
+    rs = np.random.default_rng(2)
+    img = (rs.random((7, 9, 4)) ** 3 * 40).astype(np.float32)
+    img[0, 0, :3] = 0
+    path = os.path.join(tmp_path, "a.hdr")
+    core.write_hdr(path, img)
+    data = open(path, "rb").read()
+    head, body = data.split(b"\n\n", 1)
+    assert head.startswith(b"#?RADIANCE") and b"32-bit_rle_rgbe" in head
+    dims, raw = body.split(b"\n", 1)
+    assert dims == b"-Y 7 +X 9"
+    rgbe = np.frombuffer(raw, np.uint8).reshape(7, 9, 4).astype(np.float64)
+    dec = rgbe[..., :3] * np.exp2(rgbe[..., 3:4] - 136.0)
+    dec[rgbe[..., 3] == 0] = 0
+    quantum = img[..., :3].max(-1, keepdims=True) / 128.0  # 8-bit mantissas under the exponent of the largest component
+    assert (np.abs(dec - img[..., :3]) <= quantum + 1e-6).all() and (dec <= img[..., :3] + 1e-6).all()  # truncation
+    rgba8 = rs.integers(0, 256, (5, 6, 4), dtype=np.uint8)
+    path = os.path.join(tmp_path, "a.tga")
+    core.write_tga(path, rgba8)
+    data = open(path, "rb").read()
+    assert data[2] == 2 and int.from_bytes(data[12:14], "little") == 6 and int.from_bytes(data[14:16], "little") == 5 and data[16] == 32
+    assert np.array_equal(np.frombuffer(data[18:], np.uint8).reshape(5, 6, 4)[..., [2, 1, 0, 3]], rgba8)
