@@ -249,7 +249,9 @@ def run_reference(args):
         "config": {"workload": f"{scene_name}, {args.width}x{args.height}, depth {args.bounces}; "
                                f"each step = {step_spp} spp of the whole frame on the host CPU (bounded sample of the {args.spp}-spp step)",
                    "triangles": scene.instanced_triangle_count()},
-        "cpu_baseline": {"value": value, "unit": "Mrays/s", "cores": threads, "kind": "port", "sample": base["sample"]},
+        "cpu_baseline": {"value": value, "unit": "Mrays/s", "cores": threads, "kind": "port",
+                         "sample": f"CPU restatement of the reference shaders (lavapipe unavailable): {args.steps} steps x {step_spp} spp of the "
+                                   f"whole {args.width}x{args.height} frame, depth {args.bounces}; {rays} rays in {dt:.2f} s on {threads} threads"},
         "e2e": {"value": value, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
