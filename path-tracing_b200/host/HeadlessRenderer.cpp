@@ -99,10 +99,10 @@ void HeadlessRenderer::SetSettings(const PostProcessSettings &settings)
     m_PostProcess = settings;
 }
 
-void HeadlessRenderer::Render(uint32_t samples)
+pt_render_params HeadlessRenderer::MakeRenderParams()
 {
     if (m_Scene == nullptr)
-        throw error("HeadlessRenderer::Render called without a scene");
+        throw error("HeadlessRenderer: no scene");
 
     /* Renderer.cpp:1686-1694 */
     Camera &camera = m_Scene->GetActiveCamera();
@@ -122,6 +122,27 @@ void HeadlessRenderer::Render(uint32_t samples)
                                                                                    : PT_MISS_FLAGS_NONE;
     params.hit_flags = m_Scene->HasDxNormalTextures() ? PT_HIT_FLAGS_DX_NORMAL_TEXTURES : PT_HIT_FLAGS_NONE;
 
+    return params;
+}
+
+void HeadlessRenderer::SetDebugRaytracingPipeline(const DebugRaytracingPipelineConfig &config)
+{
+    m_Debug = config;
+}
+
+std::vector<float> HeadlessRenderer::RenderDebug()
+{
+    pt_render_params params = MakeRenderParams();
+    params.miss_flags = m_Debug.MissFlags;
+    const pt_debug_params debug = { m_Debug.RenderMode, m_Debug.RaygenFlags, m_Debug.HitGroupFlags };
+    std::vector<float> pixels(static_cast<size_t>(m_Width) * m_Height * 4);
+    Check(pt_debug_render(m_Context, &params, &debug, m_Width, m_Height, pixels.data()), "pt_debug_render");
+    return pixels;
+}
+
+void HeadlessRenderer::Render(uint32_t samples)
+{
+    const pt_render_params params = MakeRenderParams();
     Check(pt_render_samples(m_Context, &params, m_TotalSamples, samples, nullptr, 0), "pt_render_samples");
     m_TotalSamples += samples;
 }

@@ -68,6 +68,16 @@ public:
         float BloomIntensity = 0.1f;
     };
 
+    /* Renderer::SetDebugRaytracingPipeline's PipelineConfig<4> (Renderer.h:30, 58): the four specialisation
+     * constants of the debug pipeline in constant-id order (Debug/DebugShaderTypes.incl:13-16) */
+    struct DebugRaytracingPipelineConfig
+    {
+        uint32_t RenderMode = 0;
+        uint32_t RaygenFlags = 0;
+        uint32_t MissFlags = 0;
+        uint32_t HitGroupFlags = 0;
+    };
+
     explicit HeadlessRenderer(int cudaDevice = 0); /* Renderer::Init     */
     ~HeadlessRenderer();                           /* Renderer::Shutdown */
 
@@ -83,6 +93,9 @@ public:
 
     /* Renderer::Render (Renderer.cpp:1659-1808) with SamplesPerFrame = samples */
     void Render(uint32_t samples = 1);
+    /* Renderer::SetDebugRaytracingPipeline + one frame of that pipeline: width*height RGBA floats */
+    void SetDebugRaytracingPipeline(const DebugRaytracingPipelineConfig &config);
+    [[nodiscard]] std::vector<float> RenderDebug();
 
     [[nodiscard]] uint32_t GetTotalSamples() const { return m_TotalSamples; }
     /* raw sum image, RGBA float, width*height*4 */
@@ -96,6 +109,7 @@ public:
 
 private:
     void Check(pt_status status, const char *what);
+    pt_render_params MakeRenderParams();
     void ResetAccumulation();
 
     pt_context *m_Context = nullptr;
@@ -104,6 +118,7 @@ private:
     uint32_t m_TotalSamples = 0;
     PathTracingSettings m_PathTracing;
     PostProcessSettings m_PostProcess;
+    DebugRaytracingPipelineConfig m_Debug;
 };
 
 }
