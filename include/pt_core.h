@@ -524,8 +524,31 @@ enum {
     PT_TEST_OFFSET_SELF_INTERSECTION = 13, /* in: origin.xyz, normal.xyz   out: p.xyz              */
     PT_TEST_CONCENTRIC_DISK = 14,    /* in: u.xy                     out: d.xy                     */
     PT_TEST_TANGENT_SPACE = 15,      /* in: n.xyz                    out: t.xyz, b.xyz, n.xyz      */
-    PT_TEST_MODE_COUNT = 16
+    /* tracing.glsl:2-148, ray.glsl:109-131, sampling.glsl:5-56, material.glsl:55-60, common.glsl:17-20 */
+    PT_TEST_DPN_DUV = 16,            /* in: v0, v1, v2 as (position.xyz, uv.xy, normal.xyz), vertex tangent.xyz,
+                                        bitangent.xyz (30)            out: dpdu, dpdv, dndu, dndv (12) */
+    PT_TEST_DP_DXY = 17,             /* in: p, rxOrigin, rxDirection, ryOrigin, ryDirection, n (18)  out: dpdx, dpdy */
+    PT_TEST_DERIVATIVES = 18,        /* in: dpdx, dpdy, dpdu, dpdv (12)   out: dudx, dvdx, dudy, dvdy */
+    PT_TEST_REFLECTED_DIFFERENTIALS = 19, /* in: derivatives[4], n, p, viewDir, reflectedDir, dndu, dndv, rxO, rxD,
+                                        ryO, ryD (34)                 out: rxO, rxD, ryO, ryD (12)  */
+    PT_TEST_REFRACTED_DIFFERENTIALS = 20, /* in: derivatives[4], n, p, viewDir, refractedDir, dndu, dndv, eta, rxO,
+                                        rxD, ryO, ryD (35)            out: rxO, rxD, ryO, ryD (12)  */
+    PT_TEST_SHADOW_TERMINATOR = 21,  /* in: vertex position, (position, normal) of v0, v1, v2, barycentrics.xyz,
+                                        isRefracted (25)              out: origin.xyz               */
+    PT_TEST_SAMPLE_LIGHT = 22,       /* in: u.xyz, position.xyz, directional colour.xyz + direction.xyz, one point
+                                        light colour.xyz + position.xyz + attenuation c/l/q, light count (bits,
+                                        0 or 1) (22)   out: direction.xyz, distance, colour.xyz, attenuation, pdf */
+    PT_TEST_TRANSFORM_VERTEX = 23,   /* in: position, normal, tangent, bitangent (12), mesh transform (12: GLSL
+                                        mat3x4 = the rows), instance object-to-world (12: rows)
+                                        out: position, normal, tangent, bitangent (12)               */
+    PT_TEST_RECONSTRUCT_NORMAL = 24, /* in: texel.xyz                out: normal.xyz                */
+    PT_TEST_HDR_TO_LDR = 25,         /* in: rgb                      out: rgb                       */
+    PT_TEST_MODE_COUNT = 26
 };
+
+/* floats per input / output record of each mode (initialiser lists for a uint32_t[PT_TEST_MODE_COUNT]) */
+#define PT_TEST_INPUT_STRIDES { 4, 4, 4, 2, 1, 10, 11, 6, 3, 23, 21, 4, 42, 6, 2, 3, 30, 18, 12, 34, 35, 25, 22, 36, 3, 3 }
+#define PT_TEST_OUTPUT_STRIDES { 1, 1, 1, 1, 1, 4, 4, 3, 4, 4, 8, 9, 18, 3, 2, 9, 12, 6, 4, 12, 12, 3, 9, 12, 3, 3 }
 
 /* Number of floats per input / output record of a mode (0 for an unknown mode). */
 PT_API uint32_t pt_test_input_stride(uint32_t mode);

@@ -79,6 +79,7 @@ inline vec3 &operator/=(vec3 &a, float s)
 }
 
 inline vec4 operator+(vec4 a, vec4 b) { return { a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w }; }
+inline vec4 operator-(vec4 a, vec4 b) { return { a.x - b.x, a.y - b.y, a.z - b.z, a.w - b.w }; }
 inline vec4 operator*(vec4 a, float s) { return { a.x * s, a.y * s, a.z * s, a.w * s }; }
 inline vec4 operator*(vec4 a, vec4 b) { return { a.x * b.x, a.y * b.y, a.z * b.z, a.w * b.w }; }
 
@@ -160,15 +161,22 @@ struct mat3x4
 
 inline mat3 M3(vec3 a, vec3 b, vec3 c) { return mat3 { { a, b, c } }; }
 inline vec3 operator*(const mat3 &m, vec3 v) { return m.c[0] * v.x + m.c[1] * v.y + m.c[2] * v.z; }
-inline vec4 operator*(const mat4 &m, vec4 v) { return m.c[0] * v.x + m.c[1] * v.y + m.c[2] * v.z + m.c[3] * v.w; }
+/* glm sums the four products pairwise: (c0 x + c1 y) + (c2 z + c3 w) (vendor/glm/glm/detail/type_mat4x4.inl) */
+inline vec4 operator*(const mat4 &m, vec4 v) { return (m.c[0] * v.x + m.c[1] * v.y) + (m.c[2] * v.z + m.c[3] * v.w); }
 /* row vector times matrix */
 inline vec3 operator*(vec4 v, const mat3x4 &m) { return { dot(v, m.c[0]), dot(v, m.c[1]), dot(v, m.c[2]) }; }
 inline vec4 operator*(vec4 v, const mat4 &m)
 {
     return { dot(v, m.c[0]), dot(v, m.c[1]), dot(v, m.c[2]), dot(v, m.c[3]) };
 }
-/* mat4 * mat3x4 -> mat3x4 (column j = M * B.c[j]) */
-inline mat3x4 operator*(const mat4 &m, const mat3x4 &b) { return mat3x4 { { m * b.c[0], m * b.c[1], m * b.c[2] } }; }
+/* mat4 * mat3x4 -> mat3x4 (column j = M * B.c[j]); glm sums these left to right (type_mat4x4.inl:469-484) */
+inline mat3x4 operator*(const mat4 &m, const mat3x4 &b)
+{
+    mat3x4 r;
+    for (int j = 0; j < 3; j++)
+        r.c[j] = m.c[0] * b.c[j].x + m.c[1] * b.c[j].y + m.c[2] * b.c[j].z + m.c[3] * b.c[j].w;
+    return r;
+}
 /* mat4(mat3x4): missing column comes from the identity */
 inline mat4 M4(const mat3x4 &m) { return mat4 { { m.c[0], m.c[1], m.c[2], V4(0.0f, 0.0f, 0.0f, 1.0f) } }; }
 
@@ -197,49 +205,52 @@ inline mat3 inverse(const mat3 &m)
     return r;
 }
 
-/* inverse(mat4) by 2x2 sub-determinants and cofactors (Laplace expansion).  The formula is
- * written for A(r,c) = a[r*4+c]; applied to column-major storage it inverts the transpose and
- * stores the transpose of that, i.e. the column-major inverse. */
-inline mat4 inverse(const mat4 &m)
+/* inverse(mat4) exactly as the reference's vendored glm evaluates it (vendor/glm/glm/detail/func_matrix.inl,
+ * compute_inverse<4, 4>): 18 2x2 sub-determinants, four cofactor columns `a*b - c*d + e*f`, the determinant
+ * as the pairwise sum (d.x + d.y) + (d.z + d.w) of column 0 times the first cofactor row, then one multiply
+ * by 1/det.  GLSL leaves the algorithm to the implementation; the oracle follows glm so that it can be
+ * compared bit for bit with the reference's shaders compiled against glm (oracle/_ref/libglsl_ref.so). */
+inline mat4 inverse(const mat4 &mm)
 {
-    const float *a = &m.c[0].x;
-#define A(r, c) a[(r) * 4 + (c)]
-    const float s0 = A(0, 0) * A(1, 1) - A(1, 0) * A(0, 1);
-    const float s1 = A(0, 0) * A(1, 2) - A(1, 0) * A(0, 2);
-    const float s2 = A(0, 0) * A(1, 3) - A(1, 0) * A(0, 3);
-    const float s3 = A(0, 1) * A(1, 2) - A(1, 1) * A(0, 2);
-    const float s4 = A(0, 1) * A(1, 3) - A(1, 1) * A(0, 3);
-    const float s5 = A(0, 2) * A(1, 3) - A(1, 2) * A(0, 3);
-    const float c5 = A(2, 2) * A(3, 3) - A(3, 2) * A(2, 3);
-    const float c4 = A(2, 1) * A(3, 3) - A(3, 1) * A(2, 3);
-    const float c3 = A(2, 1) * A(3, 2) - A(3, 1) * A(2, 2);
-    const float c2 = A(2, 0) * A(3, 3) - A(3, 0) * A(2, 3);
-    const float c1 = A(2, 0) * A(3, 2) - A(3, 0) * A(2, 2);
-    const float c0 = A(2, 0) * A(3, 1) - A(3, 0) * A(2, 1);
-    const float det = s0 * c5 - s1 * c4 + s2 * c3 + s3 * c2 - s4 * c1 + s5 * c0;
-    const float inv = 1.0f / det;
-    mat4 r;
-    float *b = &r.c[0].x;
-#define B(r, c) b[(r) * 4 + (c)]
-    B(0, 0) = (A(1, 1) * c5 - A(1, 2) * c4 + A(1, 3) * c3) * inv;
-    B(0, 1) = (-A(0, 1) * c5 + A(0, 2) * c4 - A(0, 3) * c3) * inv;
-    B(0, 2) = (A(3, 1) * s5 - A(3, 2) * s4 + A(3, 3) * s3) * inv;
-    B(0, 3) = (-A(2, 1) * s5 + A(2, 2) * s4 - A(2, 3) * s3) * inv;
-    B(1, 0) = (-A(1, 0) * c5 + A(1, 2) * c2 - A(1, 3) * c1) * inv;
-    B(1, 1) = (A(0, 0) * c5 - A(0, 2) * c2 + A(0, 3) * c1) * inv;
-    B(1, 2) = (-A(3, 0) * s5 + A(3, 2) * s2 - A(3, 3) * s1) * inv;
-    B(1, 3) = (A(2, 0) * s5 - A(2, 2) * s2 + A(2, 3) * s1) * inv;
-    B(2, 0) = (A(1, 0) * c4 - A(1, 1) * c2 + A(1, 3) * c0) * inv;
-    B(2, 1) = (-A(0, 0) * c4 + A(0, 1) * c2 - A(0, 3) * c0) * inv;
-    B(2, 2) = (A(3, 0) * s4 - A(3, 1) * s2 + A(3, 3) * s0) * inv;
-    B(2, 3) = (-A(2, 0) * s4 + A(2, 1) * s2 - A(2, 3) * s0) * inv;
-    B(3, 0) = (-A(1, 0) * c3 + A(1, 1) * c1 - A(1, 2) * c0) * inv;
-    B(3, 1) = (A(0, 0) * c3 - A(0, 1) * c1 + A(0, 2) * c0) * inv;
-    B(3, 2) = (-A(3, 0) * s3 + A(3, 1) * s1 - A(3, 2) * s0) * inv;
-    B(3, 3) = (A(2, 0) * s3 - A(2, 1) * s1 + A(2, 2) * s0) * inv;
-#undef A
-#undef B
-    return r;
+    const float *a = &mm.c[0].x;
+#define M(c, r) a[(c) * 4 + (r)]
+    const float Coef00 = M(2, 2) * M(3, 3) - M(3, 2) * M(2, 3);
+    const float Coef02 = M(1, 2) * M(3, 3) - M(3, 2) * M(1, 3);
+    const float Coef03 = M(1, 2) * M(2, 3) - M(2, 2) * M(1, 3);
+    const float Coef04 = M(2, 1) * M(3, 3) - M(3, 1) * M(2, 3);
+    const float Coef06 = M(1, 1) * M(3, 3) - M(3, 1) * M(1, 3);
+    const float Coef07 = M(1, 1) * M(2, 3) - M(2, 1) * M(1, 3);
+    const float Coef08 = M(2, 1) * M(3, 2) - M(3, 1) * M(2, 2);
+    const float Coef10 = M(1, 1) * M(3, 2) - M(3, 1) * M(1, 2);
+    const float Coef11 = M(1, 1) * M(2, 2) - M(2, 1) * M(1, 2);
+    const float Coef12 = M(2, 0) * M(3, 3) - M(3, 0) * M(2, 3);
+    const float Coef14 = M(1, 0) * M(3, 3) - M(3, 0) * M(1, 3);
+    const float Coef15 = M(1, 0) * M(2, 3) - M(2, 0) * M(1, 3);
+    const float Coef16 = M(2, 0) * M(3, 2) - M(3, 0) * M(2, 2);
+    const float Coef18 = M(1, 0) * M(3, 2) - M(3, 0) * M(1, 2);
+    const float Coef19 = M(1, 0) * M(2, 2) - M(2, 0) * M(1, 2);
+    const float Coef20 = M(2, 0) * M(3, 1) - M(3, 0) * M(2, 1);
+    const float Coef22 = M(1, 0) * M(3, 1) - M(3, 0) * M(1, 1);
+    const float Coef23 = M(1, 0) * M(2, 1) - M(2, 0) * M(1, 1);
+    const vec4 Fac0 = V4(Coef00, Coef00, Coef02, Coef03), Fac1 = V4(Coef04, Coef04, Coef06, Coef07);
+    const vec4 Fac2 = V4(Coef08, Coef08, Coef10, Coef11), Fac3 = V4(Coef12, Coef12, Coef14, Coef15);
+    const vec4 Fac4 = V4(Coef16, Coef16, Coef18, Coef19), Fac5 = V4(Coef20, Coef20, Coef22, Coef23);
+    const vec4 Vec0 = V4(M(1, 0), M(0, 0), M(0, 0), M(0, 0)), Vec1 = V4(M(1, 1), M(0, 1), M(0, 1), M(0, 1));
+    const vec4 Vec2 = V4(M(1, 2), M(0, 2), M(0, 2), M(0, 2)), Vec3 = V4(M(1, 3), M(0, 3), M(0, 3), M(0, 3));
+#undef M
+    const vec4 Inv0 = Vec1 * Fac0 - Vec2 * Fac1 + Vec3 * Fac2;
+    const vec4 Inv1 = Vec0 * Fac0 - Vec2 * Fac3 + Vec3 * Fac4;
+    const vec4 Inv2 = Vec0 * Fac1 - Vec1 * Fac3 + Vec3 * Fac5;
+    const vec4 Inv3 = Vec0 * Fac2 - Vec1 * Fac4 + Vec2 * Fac5;
+    const vec4 SignA = V4(+1.0f, -1.0f, +1.0f, -1.0f), SignB = V4(-1.0f, +1.0f, -1.0f, +1.0f);
+    mat4 Inverse = { { Inv0 * SignA, Inv1 * SignB, Inv2 * SignA, Inv3 * SignB } };
+    const vec4 Row0 = V4(Inverse.c[0].x, Inverse.c[1].x, Inverse.c[2].x, Inverse.c[3].x);
+    const vec4 Dot0 = mm.c[0] * Row0;
+    const float Dot1 = (Dot0.x + Dot0.y) + (Dot0.z + Dot0.w);
+    const float OneOverDeterminant = 1.0f / Dot1;
+    for (int c = 0; c < 4; c++)
+        Inverse.c[c] = Inverse.c[c] * OneOverDeterminant;
+    return Inverse;
 }
 
 } // namespace glsl

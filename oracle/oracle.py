@@ -73,6 +73,9 @@ def lib():
             C.c_int32,
             C.c_void_p,
         ]
+        L.pto_render_frames.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32,
+                                        C.c_void_p, C.c_uint32, C.c_void_p, C.c_int32, C.c_void_p]
+        L.pto_closest_hit.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.pto_first_hit_aov.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p]
         L.pto_trace_closest.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]
         L.pto_trace_occlusion.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]
@@ -113,8 +116,8 @@ def round_half(values: np.ndarray) -> np.ndarray:
 
 
 # record strides of pt(o)_test_shading, include/pt_core.h
-TEST_IN = [4, 4, 4, 2, 1, 10, 11, 6, 3, 23, 21, 4, 42, 6, 2, 3]
-TEST_OUT = [1, 1, 1, 1, 1, 4, 4, 3, 4, 4, 8, 9, 18, 3, 2, 9]
+TEST_IN = [4, 4, 4, 2, 1, 10, 11, 6, 3, 23, 21, 4, 42, 6, 2, 3, 30, 18, 12, 34, 35, 25, 22, 36, 3, 3]
+TEST_OUT = [1, 1, 1, 1, 1, 4, 4, 3, 4, 4, 8, 9, 18, 3, 2, 9, 12, 6, 4, 12, 12, 3, 9, 12, 3, 3]
 
 
 def test_shading(mode: int, inputs: np.ndarray) -> np.ndarray:
@@ -172,6 +175,32 @@ class OracleScene:
         )
         assert rc == 0, rc
         return accum, cnt.as_dict()
+
+    def render_frames(self, params, width, height, first_sample, frame_count, samples_per_frame, accum=None, tiles=None,
+                      threads=0):
+        """frame_count frames of samples_per_frame samples each (SampleCount > 1, Renderer.cpp:1688-1700)."""
+        if accum is None:
+            accum = np.zeros((height, width, 4), np.float32)
+        p = params.to_c()
+        cnt = Counters()
+        tl = None if tiles is None else np.ascontiguousarray(tiles, self._sc.TILE)
+        rc = lib().pto_render_frames(self._h, C.addressof(p), width, height, first_sample, frame_count, samples_per_frame,
+                                     None if tl is None else tl.ctypes.data, 0 if tl is None else len(tl),
+                                     accum.ctypes.data, threads, C.addressof(cnt))
+        assert rc == 0, rc
+        return accum, cnt.as_dict()
+
+    def closest_hit(self, params, hits, rays6, payload_in):
+        """closestHit.rchit on given hits; payloads as 36-word Shaders::Payload records."""
+        hits = np.ascontiguousarray(hits, self._sc.HIT)
+        rays6 = np.ascontiguousarray(rays6, np.float32).reshape(-1, 6)
+        payload_in = np.ascontiguousarray(payload_in, np.float32).reshape(-1, 36)
+        out = np.zeros_like(payload_in)
+        p = params.to_c()
+        rc = lib().pto_closest_hit(self._h, C.addressof(p), len(hits), hits.ctypes.data, rays6.ctypes.data,
+                                   payload_in.ctypes.data, out.ctypes.data)
+        assert rc == 0, rc
+        return out
 
     def first_hit_aov(self, params, width, height):
         out = np.zeros(width * height, self._sc.HIT)

@@ -1464,7 +1464,16 @@ bool rayCanHit(vec3 org, vec3 dir)
 /* closest hit with the primary any-hit shader.  Ties in t are broken towards the smaller flattened
  * triangle index so that the result does not depend on the BVH (the hardware's choice is
  * implementation-defined). */
-HitInfo traceClosest(const pto_scene &s, vec3 org, vec3 dir, float tmin, float tmax, Counters &c, bool forceOpaque = false)
+/* External any-hit stage (pto_trace_anyhit): the candidate goes to the hook instead of the inline
+ * restatement of anyhit.rahit / occlusionAnyhit.rahit; returns 1 = accept, 0 = ignoreIntersectionEXT. */
+struct AnyHitHook
+{
+    pto_anyhit_fn fn = nullptr;
+    void *ctx = nullptr;
+};
+
+HitInfo traceClosest(const pto_scene &s, vec3 org, vec3 dir, float tmin, float tmax, Counters &c, bool forceOpaque = false,
+                     const AnyHitHook *hook = nullptr)
 {
     HitInfo hit;
     c.rays_closest++;
@@ -1523,6 +1532,17 @@ HitInfo traceClosest(const pto_scene &s, vec3 org, vec3 dir, float tmin, float t
             {
                 /* anyhit.rahit:36-65 */
                 c.alpha_c++;
+                if (hook)
+                {
+                    if (!hook->fn(hook->ctx, tri.instance, tri.geometry, tri.primitive, t, b1, b2))
+                        continue;
+                    best = t;
+                    hit.tri = ti;
+                    hit.t = t;
+                    hit.b1 = b1;
+                    hit.b2 = b2;
+                    continue;
+                }
                 const vec4 color = anyHitColor(s, tri, b1, b2);
                 if (color.w < 0.5f)
                 {
@@ -1548,7 +1568,8 @@ HitInfo traceClosest(const pto_scene &s, vec3 org, vec3 dir, float tmin, float t
 }
 
 /* raygen.rgen:22-34 checkOccluded's traceRayEXT: TerminateOnFirstHit, occlusionAnyhit.rahit, occlusion.rmiss */
-bool traceOccluded(const pto_scene &s, vec3 org, vec3 dir, float tmin, float tmax, Counters &c)
+bool traceOccluded(const pto_scene &s, vec3 org, vec3 dir, float tmin, float tmax, Counters &c,
+                   const AnyHitHook *hook = nullptr, HitInfo *outHit = nullptr)
 {
     c.rays_shadow++;
     if (s.tris.empty() || !rayCanHit(org, dir))
@@ -1586,9 +1607,24 @@ bool traceOccluded(const pto_scene &s, vec3 org, vec3 dir, float tmin, float tma
             {
                 /* occlusionAnyhit.rahit:35-54 */
                 c.alpha_s++;
-                const float alpha = anyHitColor(s, tri, b1, b2).w;
-                if (alpha < 1.0f)
-                    continue;
+                if (hook)
+                {
+                    if (!hook->fn(hook->ctx, tri.instance, tri.geometry, tri.primitive, t, b1, b2))
+                        continue;
+                }
+                else
+                {
+                    const float alpha = anyHitColor(s, tri, b1, b2).w;
+                    if (alpha < 1.0f)
+                        continue;
+                }
+            }
+            if (outHit)
+            {
+                outHit->tri = s.triOrder[i];
+                outHit->t = t;
+                outHit->b1 = b1;
+                outHit->b2 = b2;
             }
             return true;
         }
@@ -2102,8 +2138,20 @@ MaterialSample materialFromFloats(const float *f)
     return m;
 }
 
-const uint32_t kTestIn[PT_TEST_MODE_COUNT] = { 4, 4, 4, 2, 1, 10, 11, 6, 3, 23, 21, 4, 42, 6, 2, 3 };
-const uint32_t kTestOut[PT_TEST_MODE_COUNT] = { 1, 1, 1, 1, 1, 4, 4, 3, 4, 4, 8, 9, 18, 3, 2, 9 };
+const uint32_t kTestIn[PT_TEST_MODE_COUNT] = PT_TEST_INPUT_STRIDES;
+const uint32_t kTestOut[PT_TEST_MODE_COUNT] = PT_TEST_OUTPUT_STRIDES;
+
+/* (position.xyz, uv.xy, normal.xyz) record of PT_TEST_DPN_DUV */
+Vertex vertexPUN(const float *a)
+{
+    Vertex v;
+    v.Position = V3(a[0], a[1], a[2]);
+    v.TexCoords = V2(a[3], a[4]);
+    v.Normal = V3(a[5], a[6], a[7]);
+    v.Tangent = V3(0.0f);
+    v.Bitangent = V3(0.0f);
+    return v;
+}
 
 } // namespace
 
@@ -2362,11 +2410,11 @@ void pto_scene_destroy(pto_scene *s) { delete s; }
 
 uint64_t pto_scene_triangle_count(const pto_scene *s) { return s ? s->tris.size() : 0; }
 
-int32_t pto_render(const pto_scene *s, const pt_render_params *p, uint32_t width, uint32_t height, uint32_t first_sample,
-                   uint32_t sample_count, const pt_tile *tiles, uint32_t tile_count, float *accum, int32_t threads,
-                   pto_counters *out)
+int32_t pto_render_frames(const pto_scene *s, const pt_render_params *p, uint32_t width, uint32_t height,
+                          uint32_t first_sample, uint32_t frame_count, uint32_t samples_per_frame, const pt_tile *tiles,
+                          uint32_t tile_count, float *accum, int32_t threads, pto_counters *out)
 {
-    if (!s || !p || !accum)
+    if (!s || !p || !accum || samples_per_frame == 0)
         return PT_ERR_INVALID_ARGUMENT;
     int nthreads = threads > 0 ? threads : (int)std::thread::hardware_concurrency();
     if (nthreads < 1)
@@ -2385,10 +2433,12 @@ int32_t pto_render(const pto_scene *s, const pt_render_params *p, uint32_t width
                 if (!inTiles(x, y, tiles, tile_count))
                     continue;
                 float *px = accum + ((size_t)y * width + x) * 4;
-                for (uint32_t f = 0; f < sample_count; f++)
+                for (uint32_t f = 0; f < frame_count; f++)
                 {
-                    /* one frame: SampleCount = 1, TotalSamples = first_sample + f; raygen.rgen:115-117 */
-                    const vec3 radiance = raygenPixel(*s, *p, x, y, width, height, 1, first_sample + f, c);
+                    /* one frame = one vkCmdTraceRaysKHR: SampleCount = samples_per_frame, TotalSamples = samples
+                     * accumulated so far (Renderer.cpp:1688-1700); raygen.rgen:115-117 */
+                    const vec3 radiance = raygenPixel(*s, *p, x, y, width, height, samples_per_frame,
+                                                      first_sample + f * samples_per_frame, c);
                     px[0] = radiance.x + px[0];
                     px[1] = radiance.y + px[1];
                     px[2] = radiance.z + px[2];
@@ -2424,6 +2474,104 @@ int32_t pto_render(const pto_scene *s, const pt_render_params *p, uint32_t width
         out->alpha_tests_shadow = total.alpha_s;
         out->texel_fetches = total.texels;
         out->restarts = total.restarts;
+    }
+    return PT_OK;
+}
+
+int32_t pto_render(const pto_scene *s, const pt_render_params *p, uint32_t width, uint32_t height, uint32_t first_sample,
+                   uint32_t sample_count, const pt_tile *tiles, uint32_t tile_count, float *accum, int32_t threads,
+                   pto_counters *out)
+{
+    return pto_render_frames(s, p, width, height, first_sample, sample_count, 1, tiles, tile_count, accum, threads, out);
+}
+
+int32_t pto_trace_anyhit(const pto_scene *s, const float *org, const float *dir, float tmin, float tmax,
+                         uint32_t terminate_on_first_hit, pto_anyhit_fn anyhit, void *ctx, pt_hit *out)
+{
+    if (!s || !org || !dir || !out)
+        return 0;
+    Counters c;
+    AnyHitHook hook;
+    hook.fn = anyhit;
+    hook.ctx = ctx;
+    const AnyHitHook *hp = anyhit ? &hook : nullptr;
+    HitInfo h;
+    if (terminate_on_first_hit)
+        traceOccluded(*s, V3(org[0], org[1], org[2]), V3(dir[0], dir[1], dir[2]), tmin, tmax, c, hp, &h);
+    else
+        h = traceClosest(*s, V3(org[0], org[1], org[2]), V3(dir[0], dir[1], dir[2]), tmin, tmax, c, false, hp);
+    *out = toPtHit(*s, h);
+    return h.tri != PT_NO_HIT ? 1 : 0;
+}
+
+int32_t pto_sky_sample(const pto_scene *s, uint32_t kind, const float *in3, float *out4)
+{
+    if (!s || !in3 || !out4)
+        return PT_ERR_INVALID_ARGUMENT;
+    vec4 r = V4(0.0f, 0.0f, 0.0f, 0.0f);
+    if (kind == 0 && s->hasSky2D)
+        r = textureLod0(s->sky2D, V2(in3[0], in3[1]));
+    else if (kind == 1 && s->hasSkyCube)
+        r = sampleCube(s->skyCube, V3(in3[0], in3[1], in3[2]));
+    else
+        return PT_ERR_INVALID_ARGUMENT;
+    out4[0] = r.x, out4[1] = r.y, out4[2] = r.z, out4[3] = r.w;
+    return PT_OK;
+}
+
+int32_t pto_closest_hit(const pto_scene *s, const pt_render_params *p, uint32_t count, const pt_hit *hits, const float *rays6,
+                        const float *payload_in, float *payload_out)
+{
+    if (!s || !p || !hits || !rays6 || !payload_in || !payload_out)
+        return PT_ERR_INVALID_ARGUMENT;
+    Counters c;
+    for (uint32_t i = 0; i < count; i++)
+    {
+        /* find the flattened triangle of (instance, geometry, primitive) */
+        HitInfo h;
+        for (size_t ti = 0; ti < s->tris.size(); ti++)
+        {
+            const FlatTri &t = s->tris[ti];
+            if (t.instance == hits[i].instance && t.geometry == hits[i].geometry && t.primitive == hits[i].primitive)
+            {
+                h.tri = (uint32_t)ti;
+                break;
+            }
+        }
+        if (h.tri == PT_NO_HIT)
+            return PT_ERR_INVALID_ARGUMENT;
+        h.t = hits[i].t;
+        h.b1 = hits[i].u;
+        h.b2 = hits[i].v;
+        const float *f = payload_in + 36 * (size_t)i;
+        /* Shaders::Payload, ShaderRendererTypes.incl:101-118, as 36 words */
+        Payload pl;
+        pl.Position = V3(f[0], f[1], f[2]);
+        pl.Direction = V3(f[4], f[5], f[6]);
+        pl.MaxRoughness = f[7];
+        pl.Bsdf = V3(f[8], f[9], f[10]);
+        pl.Pdf = f[11];
+        pl.Emissive = V3(f[12], f[13], f[14]);
+        pl.RngState = floatBitsToUint(f[15]);
+        pl.DirectLight = V3(f[16], f[17], f[18]);
+        pl.DirectLightPdf = f[19];
+        pl.LightDirection = V3(f[20], f[21], f[22]);
+        pl.LightDistance = f[23];
+        pl.RayDifferentials0 = V4(f[24], f[25], f[26], f[27]);
+        pl.RayDifferentials1 = V4(f[28], f[29], f[30], f[31]);
+        pl.RayDifferentials2 = V4(f[32], f[33], f[34], f[35]);
+        const float *r = rays6 + 6 * (size_t)i;
+        closestHitShader(*s, *p, h, V3(r[0], r[1], r[2]), V3(r[3], r[4], r[5]), pl, c);
+        float *o = payload_out + 36 * (size_t)i;
+        o[0] = pl.Position.x, o[1] = pl.Position.y, o[2] = pl.Position.z, o[3] = f[3];
+        o[4] = pl.Direction.x, o[5] = pl.Direction.y, o[6] = pl.Direction.z, o[7] = pl.MaxRoughness;
+        o[8] = pl.Bsdf.x, o[9] = pl.Bsdf.y, o[10] = pl.Bsdf.z, o[11] = pl.Pdf;
+        o[12] = pl.Emissive.x, o[13] = pl.Emissive.y, o[14] = pl.Emissive.z, o[15] = uintBitsToFloat(pl.RngState);
+        o[16] = pl.DirectLight.x, o[17] = pl.DirectLight.y, o[18] = pl.DirectLight.z, o[19] = pl.DirectLightPdf;
+        o[20] = pl.LightDirection.x, o[21] = pl.LightDirection.y, o[22] = pl.LightDirection.z, o[23] = pl.LightDistance;
+        o[24] = pl.RayDifferentials0.x, o[25] = pl.RayDifferentials0.y, o[26] = pl.RayDifferentials0.z, o[27] = pl.RayDifferentials0.w;
+        o[28] = pl.RayDifferentials1.x, o[29] = pl.RayDifferentials1.y, o[30] = pl.RayDifferentials1.z, o[31] = pl.RayDifferentials1.w;
+        o[32] = pl.RayDifferentials2.x, o[33] = pl.RayDifferentials2.y, o[34] = pl.RayDifferentials2.z, o[35] = pl.RayDifferentials2.w;
     }
     return PT_OK;
 }
@@ -2647,6 +2795,100 @@ int32_t pto_test_shading(uint32_t mode, const float *in, float *out, uint32_t co
             const mat3 m = computeTangentSpace(V3(a[0], a[1], a[2]));
             for (int k = 0; k < 3; k++)
                 o[k * 3] = m.c[k].x, o[k * 3 + 1] = m.c[k].y, o[k * 3 + 2] = m.c[k].z;
+            break;
+        }
+        case PT_TEST_DPN_DUV: {
+            const Vertex v0 = vertexPUN(a), v1 = vertexPUN(a + 8), v2 = vertexPUN(a + 16);
+            Vertex vertex = vertexPUN(a);
+            vertex.Tangent = V3(a[24], a[25], a[26]);
+            vertex.Bitangent = V3(a[27], a[28], a[29]);
+            vec3 r[4];
+            computeDpnDuv(v0, v1, v2, vertex, r[0], r[1], r[2], r[3]);
+            for (int k = 0; k < 4; k++)
+                o[k * 3] = r[k].x, o[k * 3 + 1] = r[k].y, o[k * 3 + 2] = r[k].z;
+            break;
+        }
+        case PT_TEST_DP_DXY: {
+            vec3 dpdx, dpdy;
+            computeDpDxy(V3(a[0], a[1], a[2]), V3(a[3], a[4], a[5]), V3(a[6], a[7], a[8]), V3(a[9], a[10], a[11]),
+                         V3(a[12], a[13], a[14]), V3(a[15], a[16], a[17]), dpdx, dpdy);
+            o[0] = dpdx.x, o[1] = dpdx.y, o[2] = dpdx.z, o[3] = dpdy.x, o[4] = dpdy.y, o[5] = dpdy.z;
+            break;
+        }
+        case PT_TEST_DERIVATIVES: {
+            const vec4 r = computeDerivatives(V3(a[0], a[1], a[2]), V3(a[3], a[4], a[5]), V3(a[6], a[7], a[8]),
+                                              V3(a[9], a[10], a[11]));
+            o[0] = r.x, o[1] = r.y, o[2] = r.z, o[3] = r.w;
+            break;
+        }
+        case PT_TEST_REFLECTED_DIFFERENTIALS:
+        case PT_TEST_REFRACTED_DIFFERENTIALS: {
+            const bool refr = mode == PT_TEST_REFRACTED_DIFFERENTIALS;
+            const float *b = a + 22 + (refr ? 1 : 0);
+            vec3 r[4] = { V3(b[0], b[1], b[2]), V3(b[3], b[4], b[5]), V3(b[6], b[7], b[8]), V3(b[9], b[10], b[11]) };
+            const vec4 der = V4(a[0], a[1], a[2], a[3]);
+            const vec3 n = V3(a[4], a[5], a[6]), pp = V3(a[7], a[8], a[9]), viewDir = V3(a[10], a[11], a[12]);
+            const vec3 outDir = V3(a[13], a[14], a[15]), dndu = V3(a[16], a[17], a[18]), dndv = V3(a[19], a[20], a[21]);
+            if (refr)
+                computeRefractedDifferentialRays(der, n, pp, viewDir, outDir, dndu, dndv, a[22], r[0], r[1], r[2], r[3]);
+            else
+                computeReflectedDifferentialRays(der, n, pp, viewDir, outDir, dndu, dndv, r[0], r[1], r[2], r[3]);
+            for (int k = 0; k < 4; k++)
+                o[k * 3] = r[k].x, o[k * 3 + 1] = r[k].y, o[k * 3 + 2] = r[k].z;
+            break;
+        }
+        case PT_TEST_SHADOW_TERMINATOR: {
+            Vertex vertex = vertexPUN(a), v0 = vertex, v1 = vertex, v2 = vertex;
+            vertex.Position = V3(a[0], a[1], a[2]);
+            v0.Position = V3(a[3], a[4], a[5]), v0.Normal = V3(a[6], a[7], a[8]);
+            v1.Position = V3(a[9], a[10], a[11]), v1.Normal = V3(a[12], a[13], a[14]);
+            v2.Position = V3(a[15], a[16], a[17]), v2.Normal = V3(a[18], a[19], a[20]);
+            const vec3 r = offsetRayOriginShadowTerminator(vertex, v0, v1, v2, V3(a[21], a[22], a[23]), a[24] != 0.0f);
+            o[0] = r.x, o[1] = r.y, o[2] = r.z;
+            break;
+        }
+        case PT_TEST_SAMPLE_LIGHT: {
+            pto_scene sc;
+            std::memset(&sc.directional, 0, sizeof(sc.directional));
+            for (int k = 0; k < 3; k++)
+                sc.directional.color[k] = a[6 + k], sc.directional.direction[k] = a[9 + k];
+            if (floatBitsToUint(a[21]))
+            {
+                pt_point_light pl;
+                std::memset(&pl, 0, sizeof(pl));
+                for (int k = 0; k < 3; k++)
+                    pl.color[k] = a[12 + k], pl.position[k] = a[15 + k];
+                pl.attenuation_constant = a[18], pl.attenuation_linear = a[19], pl.attenuation_quadratic = a[20];
+                sc.pointLights.push_back(pl);
+            }
+            float pdf;
+            const LightSample l = sampleLight(sc, V3(a[0], a[1], a[2]), V3(a[3], a[4], a[5]), pdf);
+            o[0] = l.Direction.x, o[1] = l.Direction.y, o[2] = l.Direction.z, o[3] = l.Distance;
+            o[4] = l.Color.x, o[5] = l.Color.y, o[6] = l.Color.z, o[7] = l.Attenuation, o[8] = pdf;
+            break;
+        }
+        case PT_TEST_TRANSFORM_VERTEX: {
+            pto_scene sc;
+            Vertex v = vertexPUN(a);
+            v.Position = V3(a[0], a[1], a[2]), v.Normal = V3(a[3], a[4], a[5]);
+            v.Tangent = V3(a[6], a[7], a[8]), v.Bitangent = V3(a[9], a[10], a[11]);
+            const float *m = a + 12, *w = a + 24;
+            sc.transforms.push_back(mat3x4 { { V4(m[0], m[1], m[2], m[3]), V4(m[4], m[5], m[6], m[7]), V4(m[8], m[9], m[10], m[11]) } });
+            const mat3x4 o2w = { { V4(w[0], w[1], w[2], w[3]), V4(w[4], w[5], w[6], w[7]), V4(w[8], w[9], w[10], w[11]) } };
+            const Vertex r = transformVertex(sc, v, 0, o2w);
+            o[0] = r.Position.x, o[1] = r.Position.y, o[2] = r.Position.z, o[3] = r.Normal.x, o[4] = r.Normal.y, o[5] = r.Normal.z;
+            o[6] = r.Tangent.x, o[7] = r.Tangent.y, o[8] = r.Tangent.z, o[9] = r.Bitangent.x, o[10] = r.Bitangent.y,
+            o[11] = r.Bitangent.z;
+            break;
+        }
+        case PT_TEST_RECONSTRUCT_NORMAL: {
+            const vec3 r = ReconstructNormalFromXY(V3(a[0], a[1], a[2]));
+            o[0] = r.x, o[1] = r.y, o[2] = r.z;
+            break;
+        }
+        case PT_TEST_HDR_TO_LDR: {
+            const vec3 r = hdrToLdr(V3(a[0], a[1], a[2]));
+            o[0] = r.x, o[1] = r.y, o[2] = r.z;
             break;
         }
         }

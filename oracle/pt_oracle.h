@@ -53,6 +53,29 @@ PT_API int32_t pto_render(const pto_scene *scene, const pt_render_params *params
                           uint32_t height, uint32_t first_sample, uint32_t sample_count, const pt_tile *tiles,
                           uint32_t tile_count, float *accum, int32_t threads, pto_counters *out_counters);
 
+/* The same with the reference's Release-profile frame structure (SamplesPerFrame > 1, Renderer.cpp:1688-1700):
+ * frame f runs raygen.rgen:36-118 once per pixel with SampleCount = samples_per_frame and
+ * TotalSamples = first_sample + f * samples_per_frame — ONE RNG stream and ONE radiance sum per frame. */
+PT_API int32_t pto_render_frames(const pto_scene *scene, const pt_render_params *params, uint32_t width, uint32_t height,
+                                 uint32_t first_sample, uint32_t frame_count, uint32_t samples_per_frame,
+                                 const pt_tile *tiles, uint32_t tile_count, float *accum, int32_t threads,
+                                 pto_counters *out_counters);
+
+/* Hooks for oracle/_ref/libglsl_ref.so (the reference's shaders compiled as C++, oracle/ref_overlay/build_glsl.sh):
+ * the two services the reference leaves to the Vulkan implementation.  pto_trace_anyhit is the oracle's own
+ * traversal with the any-hit stage handed to the caller (1 = accept, 0 = ignoreIntersectionEXT; NULL = the
+ * oracle's inline any-hit); returns 1 and fills *out on a hit.  pto_sky_sample: kind 0 = texture(skybox2D, uv),
+ * kind 1 = texture(skyboxCube, dir). */
+typedef int32_t (*pto_anyhit_fn)(void *ctx, uint32_t instance, uint32_t geometry, uint32_t primitive, float t, float b1,
+                                 float b2);
+PT_API int32_t pto_trace_anyhit(const pto_scene *scene, const float *org, const float *dir, float tmin, float tmax,
+                                uint32_t terminate_on_first_hit, pto_anyhit_fn anyhit, void *ctx, pt_hit *out);
+PT_API int32_t pto_sky_sample(const pto_scene *scene, uint32_t kind, const float *in3, float *out4);
+/* closestHit.rchit:52-161 on `count` given hits: rays6 = world ray origin.xyz, direction.xyz; payloads are the 36
+ * words of Shaders::Payload (ShaderRendererTypes.incl:101-118; RngState as bits). */
+PT_API int32_t pto_closest_hit(const pto_scene *scene, const pt_render_params *params, uint32_t count, const pt_hit *hits,
+                               const float *rays6, const float *payload_in, float *payload_out);
+
 PT_API int32_t pto_first_hit_aov(const pto_scene *scene, const pt_render_params *params, uint32_t width,
                                  uint32_t height, pt_hit *out_hits);
 PT_API int32_t pto_trace_closest(const pto_scene *scene, const pt_ray *rays, uint64_t ray_count,

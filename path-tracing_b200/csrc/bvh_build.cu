@@ -623,41 +623,61 @@ template <typename T> pt_status devAlloc(Context *ctx, T **ptr, size_t count, st
 }
 
 // The normal matrix of sampling.glsl:12 / skinning.comp:44, `transpose(inverse(mat4(transform)))`, for
-// a 3x4 row-major affine matrix P — evaluated the way the GLSL evaluates it: fp32 throughout, the
-// 4x4 inverse by cofactors over 2x2 sub-determinants.  (A double-precision 3x3 inverse is more
-// accurate but rounds differently from the shader in the last bit; on scenes modelled in millimetres
+// a 3x4 row-major affine matrix P — evaluated in fp32 with the very operation order of the glm the
+// reference vendors (glm/detail/func_matrix.inl, compute_inverse<4, 4>: 2x2 sub-determinants, cofactor
+// columns a*b - c*d + e*f, pairwise determinant sum, one multiply by 1 / det), which is also what the
+// oracle and the compiled-GLSL reference (oracle/_ref/libglsl_ref.so) do.  (A double-precision 3x3
+// inverse is more accurate but rounds differently in the last bit; on scenes modelled in millimetres
 // that last bit decides whether a shadow ray leaves its own triangle, i.e. whole pixels.)
-// N[j*3 + i] = inverse(A)(i, j): world normal_j = sum_i N[j*3 + i] * n_i.
+// mat4(transform) has the ROWS of P as its columns.  N[j*3 + i] = inverse(m)[i][j]:
+// world normal_j = sum_i N[j*3 + i] * n_i  (= (vec4(n, 0) * transpose(inverse(m))).xyz).
 void normalMatrix(const float P[12], float N[9])
 {
-    const float A[4][4] = { { P[0], P[1], P[2], P[3] }, { P[4], P[5], P[6], P[7] }, { P[8], P[9], P[10], P[11] }, { 0.0f, 0.0f, 0.0f, 1.0f } };
-    const volatile float s0 = A[0][0] * A[1][1] - A[1][0] * A[0][1];
-    const volatile float s1 = A[0][0] * A[1][2] - A[1][0] * A[0][2];
-    const volatile float s2 = A[0][0] * A[1][3] - A[1][0] * A[0][3];
-    const volatile float s3 = A[0][1] * A[1][2] - A[1][1] * A[0][2];
-    const volatile float s4 = A[0][1] * A[1][3] - A[1][1] * A[0][3];
-    const volatile float s5 = A[0][2] * A[1][3] - A[1][2] * A[0][3];
-    const volatile float c5 = A[2][2] * A[3][3] - A[3][2] * A[2][3];
-    const volatile float c4 = A[2][1] * A[3][3] - A[3][1] * A[2][3];
-    const volatile float c3 = A[2][1] * A[3][2] - A[3][1] * A[2][2];
-    const volatile float c2 = A[2][0] * A[3][3] - A[3][0] * A[2][3];
-    const volatile float c1 = A[2][0] * A[3][2] - A[3][0] * A[2][2];
-    const volatile float c0 = A[2][0] * A[3][1] - A[3][0] * A[2][1];
-    const volatile float det = s0 * c5 - s1 * c4 + s2 * c3 + s3 * c2 - s4 * c1 + s5 * c0;
+    const float m[4][4] = { { P[0], P[1], P[2], P[3] }, { P[4], P[5], P[6], P[7] }, { P[8], P[9], P[10], P[11] }, { 0.0f, 0.0f, 0.0f, 1.0f } };
+    // volatile: one rounding per operation whatever the host compiler would like to contract
+    auto dop = [](float a, float b, float c, float d) {
+        const volatile float ab = a * b, cd = c * d;
+        const volatile float r = ab - cd;
+        return (float)r;
+    };
+    const float Coef00 = dop(m[2][2], m[3][3], m[3][2], m[2][3]), Coef02 = dop(m[1][2], m[3][3], m[3][2], m[1][3]);
+    const float Coef03 = dop(m[1][2], m[2][3], m[2][2], m[1][3]), Coef04 = dop(m[2][1], m[3][3], m[3][1], m[2][3]);
+    const float Coef06 = dop(m[1][1], m[3][3], m[3][1], m[1][3]), Coef07 = dop(m[1][1], m[2][3], m[2][1], m[1][3]);
+    const float Coef08 = dop(m[2][1], m[3][2], m[3][1], m[2][2]), Coef10 = dop(m[1][1], m[3][2], m[3][1], m[1][2]);
+    const float Coef11 = dop(m[1][1], m[2][2], m[2][1], m[1][2]), Coef12 = dop(m[2][0], m[3][3], m[3][0], m[2][3]);
+    const float Coef14 = dop(m[1][0], m[3][3], m[3][0], m[1][3]), Coef15 = dop(m[1][0], m[2][3], m[2][0], m[1][3]);
+    const float Coef16 = dop(m[2][0], m[3][2], m[3][0], m[2][2]), Coef18 = dop(m[1][0], m[3][2], m[3][0], m[1][2]);
+    const float Coef19 = dop(m[1][0], m[2][2], m[2][0], m[1][2]), Coef20 = dop(m[2][0], m[3][1], m[3][0], m[2][1]);
+    const float Coef22 = dop(m[1][0], m[3][1], m[3][0], m[1][1]), Coef23 = dop(m[1][0], m[2][1], m[2][0], m[1][1]);
+    const float Fac0[4] = { Coef00, Coef00, Coef02, Coef03 }, Fac1[4] = { Coef04, Coef04, Coef06, Coef07 };
+    const float Fac2[4] = { Coef08, Coef08, Coef10, Coef11 }, Fac3[4] = { Coef12, Coef12, Coef14, Coef15 };
+    const float Fac4[4] = { Coef16, Coef16, Coef18, Coef19 }, Fac5[4] = { Coef20, Coef20, Coef22, Coef23 };
+    const float Vec0[4] = { m[1][0], m[0][0], m[0][0], m[0][0] }, Vec1[4] = { m[1][1], m[0][1], m[0][1], m[0][1] };
+    const float Vec2[4] = { m[1][2], m[0][2], m[0][2], m[0][2] }, Vec3[4] = { m[1][3], m[0][3], m[0][3], m[0][3] };
+    // a*b - c*d + e*f
+    auto col = [](const float *a, const float *b, const float *c, const float *d, const float *e, const float *f, const float *sign,
+                  float *out) {
+        for (int k = 0; k < 4; k++)
+        {
+            const volatile float ab = a[k] * b[k], cd = c[k] * d[k], ef = e[k] * f[k];
+            const volatile float t = ab - cd;
+            const volatile float r = t + ef;
+            out[k] = r * sign[k];
+        }
+    };
+    const float SignA[4] = { +1.0f, -1.0f, +1.0f, -1.0f }, SignB[4] = { -1.0f, +1.0f, -1.0f, +1.0f };
+    float Inv[4][4];
+    col(Vec1, Fac0, Vec2, Fac1, Vec3, Fac2, SignA, Inv[0]);
+    col(Vec0, Fac0, Vec2, Fac3, Vec3, Fac4, SignB, Inv[1]);
+    col(Vec0, Fac1, Vec1, Fac3, Vec3, Fac5, SignA, Inv[2]);
+    col(Vec0, Fac2, Vec1, Fac4, Vec2, Fac5, SignB, Inv[3]);
+    const volatile float d0 = m[0][0] * Inv[0][0], d1 = m[0][1] * Inv[1][0], d2 = m[0][2] * Inv[2][0], d3 = m[0][3] * Inv[3][0];
+    const volatile float s01 = d0 + d1, s23 = d2 + d3;
+    const volatile float det = s01 + s23;
     const float inv = 1.0f / det;
-    float B[3][3]; // rows 0-2, columns 0-2 of the inverse
-    B[0][0] = (A[1][1] * c5 - A[1][2] * c4 + A[1][3] * c3) * inv;
-    B[0][1] = (-A[0][1] * c5 + A[0][2] * c4 - A[0][3] * c3) * inv;
-    B[0][2] = (A[3][1] * s5 - A[3][2] * s4 + A[3][3] * s3) * inv;
-    B[1][0] = (-A[1][0] * c5 + A[1][2] * c2 - A[1][3] * c1) * inv;
-    B[1][1] = (A[0][0] * c5 - A[0][2] * c2 + A[0][3] * c1) * inv;
-    B[1][2] = (-A[3][0] * s5 + A[3][2] * s2 - A[3][3] * s1) * inv;
-    B[2][0] = (A[1][0] * c4 - A[1][1] * c2 + A[1][3] * c0) * inv;
-    B[2][1] = (-A[0][0] * c4 + A[0][1] * c2 - A[0][3] * c0) * inv;
-    B[2][2] = (A[3][0] * s4 - A[3][1] * s2 + A[3][3] * s0) * inv;
     for (int j = 0; j < 3; j++)
         for (int i = 0; i < 3; i++)
-            N[j * 3 + i] = B[i][j];
+            N[j * 3 + i] = Inv[i][j] * inv;
 }
 
 
@@ -876,6 +896,21 @@ pt_status skinAnimatedVertices(Context *ctx, const float *boneTransforms)
     return PT_OK;
 }
 
+// P = Instance * Mesh with the evaluation order of `mat4(transforms[i]) * gl_ObjectToWorld3x4EXT`
+// (PT/Shaders/sampling.glsl:7); A = the mesh transform, B = the instance transform, both as 3x4 rows
+void composeTransform(const float *A, const float *B, float P[12])
+{
+    for (int j = 0; j < 3; j++)
+        for (int c = 0; c < 4; c++)
+        {
+            float v = A[0 * 4 + c] * B[j * 4 + 0] + A[1 * 4 + c] * B[j * 4 + 1];
+            v = v + A[2 * 4 + c] * B[j * 4 + 2];
+            if (c == 3)
+                v = v + 1.0f * B[j * 4 + 3];
+            P[j * 4 + c] = v;
+        }
+}
+
 // Flattens instances x meshes into one MeshInstance per (instance, mesh) pair with its baked
 // object-to-world and normal matrices (host, tiny).
 pt_status flattenInstances(Context *ctx, const SceneTopology &t, std::vector<MeshInstance> &mis, bool &hasAlpha)
@@ -908,19 +943,7 @@ pt_status flattenInstances(Context *ctx, const SceneTopology &t, std::vector<Mes
             if (index >= limit)
                 return fail(ctx, PT_ERR_INVALID_ARGUMENT, "pt_scene_upload", "material index out of range");
             MeshInstance m = {};
-            // P = Instance * Mesh with the evaluation order of
-            // `mat4(transforms[i]) * gl_ObjectToWorld3x4EXT` (PT/Shaders/sampling.glsl:7)
-            const float *A = t.transforms.data() + 12 * (size_t)rec.transform_index; // mesh, rows
-            const float *B = inst.transform;                                   // instance, rows
-            for (int j = 0; j < 3; j++)
-                for (int c = 0; c < 4; c++)
-                {
-                    float v = A[0 * 4 + c] * B[j * 4 + 0] + A[1 * 4 + c] * B[j * 4 + 1];
-                    v = v + A[2 * 4 + c] * B[j * 4 + 2];
-                    if (c == 3)
-                        v = v + 1.0f * B[j * 4 + 3];
-                    m.P[j * 4 + c] = v;
-                }
+            composeTransform(t.transforms.data() + 12 * (size_t)rec.transform_index, inst.transform, m.P);
             normalMatrix(m.P, m.N);
             m.triOffset = (uint32_t)triTotal;
             m.triCount = g.index_length / 3;
@@ -945,6 +968,13 @@ pt_status flattenInstances(Context *ctx, const SceneTopology &t, std::vector<Mes
 }
 
 } // namespace
+
+// PT_TEST_TRANSFORM_VERTEX: the host half of the vertex transform (flattenInstances' matrices)
+void testComposeTransform(const float *meshRows, const float *instanceRows, float P[12], float N[9])
+{
+    composeTransform(meshRows, instanceRows, P);
+    normalMatrix(P, N);
+}
 
 void freeScene(Context *ctx)
 {

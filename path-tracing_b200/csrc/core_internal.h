@@ -192,6 +192,7 @@ pt_status postProcess(Context *ctx, const pt_postprocess_params *params, uint32_
                       void *out, size_t outBytes);
 
 // unit_kernels.cu
+void testComposeTransform(const float *meshRows, const float *instanceRows, float P[12], float N[9]);
 pt_status testShading(Context *ctx, uint32_t mode, const float *input, float *output, uint32_t count);
 pt_status testTexture(Context *ctx, uint32_t slot, const float *in6, float *out4, uint32_t count, int32_t useGrad);
 uint32_t testInputStride(uint32_t mode);

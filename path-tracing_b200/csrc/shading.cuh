@@ -6,6 +6,7 @@
 // per-hit matrix work is replaced by data baked at scene upload.  RNG consumption order is kept
 // exactly because the stream is threaded through every stage.
 #pragma once
+#include "scene.cuh"
 #include "vecmath.cuh"
 
 namespace pt
@@ -334,9 +335,10 @@ struct CameraMatrices
 };
 PT_DEV vec3 mulPoint(const float *m, float x, float y, float z, float w)
 {
-    // (M * vec4).xyz with GLSL's column order: c0*x + c1*y + c2*z + c3*w
-    return V3(m[0] * x + m[4] * y + m[8] * z + m[12] * w, m[1] * x + m[5] * y + m[9] * z + m[13] * w,
-              m[2] * x + m[6] * y + m[10] * z + m[14] * w);
+    // (M * vec4).xyz summed pairwise, (c0*x + c1*y) + (c2*z + c3*w), as the reference's vendored glm (and with
+    // it the oracle and the compiled-GLSL reference) evaluates mat4 * vec4 (glm/detail/type_mat4x4.inl)
+    return V3((m[0] * x + m[4] * y) + (m[8] * z + m[12] * w), (m[1] * x + m[5] * y) + (m[9] * z + m[13] * w),
+              (m[2] * x + m[6] * y) + (m[10] * z + m[14] * w));
 }
 struct PrimaryRays
 {
@@ -402,6 +404,37 @@ PT_DEV float4 computeDerivatives(vec3 dpdx, vec3 dpdy, vec3 dpdu, vec3 dpdv)
     return make_float4(clampDerivative(dudx), clampDerivative(dvdx), clampDerivative(dudy), clampDerivative(dvdy));
 }
 
+// :2-28 with e1 = p1 - p0, e2 = p2 - p0 (world space), en = normal differences, duv = uv differences
+PT_DEV void computeDpnDuv(vec3 e1, vec3 e2, vec3 en1, vec3 en2, vec2 duv1, vec2 duv2, vec3 tangent, vec3 bitangent, vec3 &dpdu,
+                          vec3 &dpdv, vec3 &dndu, vec3 &dndv)
+{
+    const float det = duv1.x * duv2.y - duv2.x * duv1.y;
+    if (fabsf(det) < 1e-8f)
+    {
+        dpdu = tangent;
+        dpdv = bitangent;
+        dndu = V3(0.0f);
+        dndv = V3(0.0f);
+    }
+    else
+    {
+        const float invDet = 1.0f / det;
+        dpdu = (duv2.y * e1 - duv1.y * e2) * invDet;
+        dpdv = (-duv2.x * e1 + duv1.x * e2) * invDet;
+        dndu = (duv2.y * en1 - duv1.y * en2) * invDet;
+        dndv = (-duv2.x * en1 + duv1.x * en2) * invDet;
+    }
+}
+// :31-41
+PT_DEV void computeDpDxy(vec3 p, vec3 rxOrigin, vec3 rxDirection, vec3 ryOrigin, vec3 ryDirection, vec3 n, vec3 &dpdx, vec3 &dpdy)
+{
+    const float d = -dot(n, p);
+    const float tx = (-dot(n, rxOrigin) - d) / dot(n, rxDirection);
+    const float ty = (-dot(n, ryOrigin) - d) / dot(n, ryDirection);
+    dpdx = (rxOrigin + tx * rxDirection) - p;
+    dpdy = (ryOrigin + ty * ryDirection) - p;
+}
+
 struct RayDifferentials
 {
     vec3 rxOrigin, rxDirection, ryOrigin, ryDirection;
@@ -447,5 +480,58 @@ PT_DEV void propagateDifferentials(float4 derivatives, vec3 n, vec3 p, vec3 view
     rd.rxDirection = normalize(newDir - eta * dwodx + (mu * dndx + dmudx * n));
     rd.ryDirection = normalize(newDir - eta * dwody + (mu * dndy + dmudy * n));
 }
+
+
+// common.glsl:17-20
+PT_DEV vec3 hdrToLdr(vec3 rgb) { return rgb / (1.0f + maxComponent(rgb)); }
+
+// material.glsl:55-60
+PT_DEV vec3 reconstructNormalFromXY(float4 t)
+{
+    const float x = 2.0f * t.x - 1.0f, y = 2.0f * t.y - 1.0f;
+    return V3(x, y, sqrtf(fmaxf(1 - x * x - y * y, 0.0f)));
+}
+
+// ---------------------------------------------------------------------------------------------
+// sampling.glsl:25-56
+// ---------------------------------------------------------------------------------------------
+struct LightSample
+{
+    vec3 Direction;
+    float Distance;
+    vec3 Color;
+    float Attenuation;
+};
+
+PT_DEV LightSample sampleLight(const LightBlock *lb, vec3 u, vec3 position, float &pdf)
+{
+    const uint32_t count = __ldg(&lb->count);
+    const uint32_t lightIndex = (uint32_t)(u.x * (float)(count + 1));
+    pdf = 1.0f / (float)(count + 1);
+    const vec2 dp = sampleUniformDiskConcentric(V2(u.y, u.z));
+    LightSample r;
+    if (lightIndex >= count)
+    {
+        const vec3 diskPoint = V3(dp.x, dp.y, 0.0f) * 0.001f;
+        const vec3 direction = normalize(V3(__ldg(&lb->dirDirection)));
+        r.Direction = normalize(direction + mul(computeTangentSpace(direction), diskPoint));
+        r.Color = V3(__ldg(&lb->dirColor));
+        r.Distance = 100000.0f;
+        r.Attenuation = 1.0f;
+        return r;
+    }
+    const float4 lc = __ldg(&lb->point[lightIndex * 3]), lp = __ldg(&lb->point[lightIndex * 3 + 1]);
+    const float4 la = __ldg(&lb->point[lightIndex * 3 + 2]);
+    const vec3 diskPoint = V3(dp.x, dp.y, 0.0f) * 0.1f;
+    const vec3 direction = normalize(position - V3(lp));
+    const vec3 newPosition = V3(lp) + mul(computeTangentSpace(direction), diskPoint);
+    r.Distance = length(position - newPosition);
+    r.Direction = normalize(position - newPosition);
+    r.Color = V3(lc);
+    const float attenuation = 1.0f / (la.x + r.Distance * la.y + r.Distance * r.Distance * la.z);
+    r.Attenuation = clampf(attenuation, 0.0f, 1.0f);
+    return r;
+}
+
 
 } // namespace pt

@@ -4,16 +4,19 @@
 #include "core_internal.h"
 #include "shading.cuh"
 
+#include <cstring>
+#include <vector>
+
 namespace pt
 {
 
 namespace
 {
 
-__constant__ uint32_t c_in[PT_TEST_MODE_COUNT] = { 4, 4, 4, 2, 1, 10, 11, 6, 3, 23, 21, 4, 42, 6, 2, 3 };
-__constant__ uint32_t c_out[PT_TEST_MODE_COUNT] = { 1, 1, 1, 1, 1, 4, 4, 3, 4, 4, 8, 9, 18, 3, 2, 9 };
-const uint32_t h_in[PT_TEST_MODE_COUNT] = { 4, 4, 4, 2, 1, 10, 11, 6, 3, 23, 21, 4, 42, 6, 2, 3 };
-const uint32_t h_out[PT_TEST_MODE_COUNT] = { 1, 1, 1, 1, 1, 4, 4, 3, 4, 4, 8, 9, 18, 3, 2, 9 };
+__constant__ uint32_t c_in[PT_TEST_MODE_COUNT] = PT_TEST_INPUT_STRIDES;
+__constant__ uint32_t c_out[PT_TEST_MODE_COUNT] = PT_TEST_OUTPUT_STRIDES;
+const uint32_t h_in[PT_TEST_MODE_COUNT] = PT_TEST_INPUT_STRIDES;
+const uint32_t h_out[PT_TEST_MODE_COUNT] = PT_TEST_OUTPUT_STRIDES;
 
 __device__ MaterialSample materialFromFloats(const float *f)
 {
@@ -30,7 +33,7 @@ __device__ MaterialSample materialFromFloats(const float *f)
     return m;
 }
 
-__global__ void k_test(uint32_t mode, const float *__restrict__ in, float *__restrict__ out, uint32_t count)
+__global__ void k_test(uint32_t mode, const float *__restrict__ in, float *__restrict__ out, uint32_t count, LightBlock *scratch)
 {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= count)
@@ -138,6 +141,90 @@ __global__ void k_test(uint32_t mode, const float *__restrict__ in, float *__res
         o[6] = m.c2.x, o[7] = m.c2.y, o[8] = m.c2.z;
         break;
     }
+    case PT_TEST_DPN_DUV: {
+        // records are (position, uv, normal) per corner; the production function takes the differences
+        const vec3 p0 = V3(a[0], a[1], a[2]), p1 = V3(a[8], a[9], a[10]), p2 = V3(a[16], a[17], a[18]);
+        const vec2 uv0 = V2(a[3], a[4]), uv1 = V2(a[11], a[12]), uv2 = V2(a[19], a[20]);
+        const vec3 n0 = V3(a[5], a[6], a[7]), n1 = V3(a[13], a[14], a[15]), n2 = V3(a[21], a[22], a[23]);
+        vec3 r[4];
+        computeDpnDuv(p1 - p0, p2 - p0, n1 - n0, n2 - n0, uv1 - uv0, uv2 - uv0, V3(a[24], a[25], a[26]), V3(a[27], a[28], a[29]),
+                      r[0], r[1], r[2], r[3]);
+        for (int k = 0; k < 4; k++)
+            o[k * 3] = r[k].x, o[k * 3 + 1] = r[k].y, o[k * 3 + 2] = r[k].z;
+        break;
+    }
+    case PT_TEST_DP_DXY: {
+        vec3 dpdx, dpdy;
+        computeDpDxy(V3(a[0], a[1], a[2]), V3(a[3], a[4], a[5]), V3(a[6], a[7], a[8]), V3(a[9], a[10], a[11]),
+                     V3(a[12], a[13], a[14]), V3(a[15], a[16], a[17]), dpdx, dpdy);
+        o[0] = dpdx.x, o[1] = dpdx.y, o[2] = dpdx.z, o[3] = dpdy.x, o[4] = dpdy.y, o[5] = dpdy.z;
+        break;
+    }
+    case PT_TEST_DERIVATIVES: {
+        const float4 r = computeDerivatives(V3(a[0], a[1], a[2]), V3(a[3], a[4], a[5]), V3(a[6], a[7], a[8]), V3(a[9], a[10], a[11]));
+        o[0] = r.x, o[1] = r.y, o[2] = r.z, o[3] = r.w;
+        break;
+    }
+    case PT_TEST_REFLECTED_DIFFERENTIALS:
+    case PT_TEST_REFRACTED_DIFFERENTIALS: {
+        const bool refr = mode == PT_TEST_REFRACTED_DIFFERENTIALS;
+        const float *b = a + 22 + (refr ? 1 : 0);
+        RayDifferentials rd;
+        rd.rxOrigin = V3(b[0], b[1], b[2]), rd.rxDirection = V3(b[3], b[4], b[5]);
+        rd.ryOrigin = V3(b[6], b[7], b[8]), rd.ryDirection = V3(b[9], b[10], b[11]);
+        propagateDifferentials(make_float4(a[0], a[1], a[2], a[3]), V3(a[4], a[5], a[6]), V3(a[7], a[8], a[9]),
+                               V3(a[10], a[11], a[12]), V3(a[13], a[14], a[15]), V3(a[16], a[17], a[18]), V3(a[19], a[20], a[21]),
+                               refr ? a[22] : 1.0f, refr, rd);
+        const vec3 r[4] = { rd.rxOrigin, rd.rxDirection, rd.ryOrigin, rd.ryDirection };
+        for (int k = 0; k < 4; k++)
+            o[k * 3] = r[k].x, o[k * 3 + 1] = r[k].y, o[k * 3 + 2] = r[k].z;
+        break;
+    }
+    case PT_TEST_SHADOW_TERMINATOR: {
+        const vec3 r = offsetRayOriginShadowTerminator(V3(a[0], a[1], a[2]), V3(a[3], a[4], a[5]), V3(a[9], a[10], a[11]),
+                                                       V3(a[15], a[16], a[17]), V3(a[6], a[7], a[8]), V3(a[12], a[13], a[14]),
+                                                       V3(a[18], a[19], a[20]), V3(a[21], a[22], a[23]), a[24] != 0.0f);
+        o[0] = r.x, o[1] = r.y, o[2] = r.z;
+        break;
+    }
+    case PT_TEST_SAMPLE_LIGHT: {
+        // the production function reads the light block through __ldg: testShading built one per record
+        const LightBlock *lb = scratch + i;
+        float pdf;
+        const LightSample l = sampleLight(lb, V3(a[0], a[1], a[2]), V3(a[3], a[4], a[5]), pdf);
+        o[0] = l.Direction.x, o[1] = l.Direction.y, o[2] = l.Direction.z, o[3] = l.Distance;
+        o[4] = l.Color.x, o[5] = l.Color.y, o[6] = l.Color.z, o[7] = l.Attenuation, o[8] = pdf;
+        break;
+    }
+    case PT_TEST_TRANSFORM_VERTEX: {
+        // a[12..23]: the (instance x mesh) matrix P and a[24..32]: its normal matrix N, both composed on the host by
+        // the production flattenInstances arithmetic (testShading rewrites the record); then k_bake's arithmetic
+        const float *P = a + 12, *N = a + 24;
+        vec3 pos, nrm, tan, bit;
+        float *pp = &pos.x, *pn = &nrm.x, *pt = &tan.x, *pb = &bit.x;
+        for (int j = 0; j < 3; j++)
+        {
+            const float *Pj = P + j * 4;
+            pp[j] = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(a[0], Pj[0]), __fmul_rn(a[1], Pj[1])), __fmul_rn(a[2], Pj[2])), Pj[3]);
+            pn[j] = N[j * 3 + 0] * a[3] + N[j * 3 + 1] * a[4] + N[j * 3 + 2] * a[5];
+            pt[j] = Pj[0] * a[6] + Pj[1] * a[7] + Pj[2] * a[8];
+            pb[j] = Pj[0] * a[9] + Pj[1] * a[10] + Pj[2] * a[11];
+        }
+        nrm = normalize(nrm), tan = normalize(tan), bit = normalize(bit);
+        o[0] = pos.x, o[1] = pos.y, o[2] = pos.z, o[3] = nrm.x, o[4] = nrm.y, o[5] = nrm.z;
+        o[6] = tan.x, o[7] = tan.y, o[8] = tan.z, o[9] = bit.x, o[10] = bit.y, o[11] = bit.z;
+        break;
+    }
+    case PT_TEST_RECONSTRUCT_NORMAL: {
+        const vec3 r = reconstructNormalFromXY(make_float4(a[0], a[1], a[2], 0.0f));
+        o[0] = r.x, o[1] = r.y, o[2] = r.z;
+        break;
+    }
+    case PT_TEST_HDR_TO_LDR: {
+        const vec3 r = hdrToLdr(V3(a[0], a[1], a[2]));
+        o[0] = r.x, o[1] = r.y, o[2] = r.z;
+        break;
+    }
     }
 }
 
@@ -193,20 +280,58 @@ pt_status testShading(Context *ctx, uint32_t mode, const float *input, float *ou
     if (count == 0)
         return PT_OK;
     const size_t inBytes = (size_t)count * h_in[mode] * 4, outBytes = (size_t)count * h_out[mode] * 4;
+    std::vector<float> composed;
+    if (mode == PT_TEST_TRANSFORM_VERTEX)
+    {
+        // the matrices are composed and inverted on the host in production (flattenInstances)
+        composed.assign(input, input + (size_t)count * h_in[mode]);
+        for (uint32_t i = 0; i < count; i++)
+        {
+            float *a = composed.data() + (size_t)i * h_in[mode];
+            float P[12], N[9];
+            testComposeTransform(a + 12, a + 24, P, N);
+            std::memcpy(a + 12, P, sizeof(P));
+            std::memcpy(a + 24, N, sizeof(N));
+        }
+        input = composed.data();
+    }
     float *dIn = nullptr, *dOut = nullptr;
+    LightBlock *dScratch = nullptr;
     PT_CUDA_CHECK(ctx, cudaMalloc((void **)&dIn, inBytes));
     cudaError_t err = cudaMalloc((void **)&dOut, outBytes);
+    if (err == cudaSuccess && mode == PT_TEST_SAMPLE_LIGHT)
+    {
+        std::vector<LightBlock> blocks(count);
+        for (uint32_t i = 0; i < count; i++)
+        {
+            const float *a = input + (size_t)i * h_in[mode];
+            LightBlock &lb = blocks[i];
+            std::memset(&lb, 0, sizeof(lb));
+            uint32_t bits;
+            std::memcpy(&bits, a + 21, 4);
+            lb.count = bits ? 1u : 0u;
+            lb.dirColor = make_float4(a[6], a[7], a[8], 0.0f);
+            lb.dirDirection = make_float4(a[9], a[10], a[11], 0.0f);
+            lb.point[0] = make_float4(a[12], a[13], a[14], 0.0f);
+            lb.point[1] = make_float4(a[15], a[16], a[17], 0.0f);
+            lb.point[2] = make_float4(a[18], a[19], a[20], 0.0f);
+        }
+        err = cudaMalloc((void **)&dScratch, (size_t)count * sizeof(LightBlock));
+        if (err == cudaSuccess)
+            err = cudaMemcpy(dScratch, blocks.data(), (size_t)count * sizeof(LightBlock), cudaMemcpyHostToDevice);
+    }
     if (err == cudaSuccess)
         err = cudaMemcpyAsync(dIn, input, inBytes, cudaMemcpyHostToDevice, ctx->stream);
     if (err == cudaSuccess)
     {
-        k_test<<<(count + 63) / 64, 64, 0, ctx->stream>>>(mode, dIn, dOut, count);
+        k_test<<<(count + 63) / 64, 64, 0, ctx->stream>>>(mode, dIn, dOut, count, dScratch);
         err = cudaMemcpyAsync(output, dOut, outBytes, cudaMemcpyDeviceToHost, ctx->stream);
     }
     if (err == cudaSuccess)
         err = cudaStreamSynchronize(ctx->stream);
     cudaFree(dIn);
     cudaFree(dOut);
+    cudaFree(dScratch);
     PT_CUDA_CHECK(ctx, err);
     return PT_OK;
 }

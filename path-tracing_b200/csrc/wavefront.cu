@@ -182,7 +182,7 @@ __device__ __forceinline__ vec3 skyRadiance(const RenderConst &rc, vec3 dir)
         const float latitude = asinf(-dir.y);
         const float4 c = textureLod0(rc.scene, rc.scene.sky2D, longitude / 2.0f / PT_PI + 0.5f, latitude / PT_PI + 0.5f);
         const vec3 rgb = V3(c);
-        return rgb / (1.0f + maxComponent(rgb)); // hdrToLdr
+        return hdrToLdr(rgb);
     }
     if ((rc.missFlags & PT_MISS_FLAGS_SKYBOX_CUBE) && rc.scene.skyCubeSlot)
         return V3(sampleCube(rc.scene, rc.scene.skyCubeSlot, dir));
@@ -302,12 +302,6 @@ template <bool ALPHA, bool STATS> __global__ void __launch_bounds__(128, PT_TRAC
 // ---------------------------------------------------------------------------------------------
 // material.glsl
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ vec3 reconstructNormalFromXY(float4 t)
-{
-    const float x = 2.0f * t.x - 1.0f, y = 2.0f * t.y - 1.0f;
-    return V3(x, y, sqrtf(fmaxf(1 - x * x - y * y, 0.0f)));
-}
-
 __device__ __forceinline__ MaterialSample sampleMaterial(const DeviceScene &s, uint32_t materialId, float u, float v,
                                                          float4 deriv, bool inside, bool flipNormalY, uint32_t *texels,
                                                          uint32_t debugFlags = 0)
@@ -367,47 +361,6 @@ __device__ __forceinline__ MaterialSample sampleMaterial(const DeviceScene &s, u
     }
     if (flipNormalY)
         r.Normal.y *= -1.0f;
-    return r;
-}
-
-// ---------------------------------------------------------------------------------------------
-// sampling.glsl:25-56
-// ---------------------------------------------------------------------------------------------
-struct LightSample
-{
-    vec3 Direction;
-    float Distance;
-    vec3 Color;
-    float Attenuation;
-};
-
-__device__ __forceinline__ LightSample sampleLight(const LightBlock *lb, vec3 u, vec3 position, float &pdf)
-{
-    const uint32_t count = __ldg(&lb->count);
-    const uint32_t lightIndex = (uint32_t)(u.x * (float)(count + 1));
-    pdf = 1.0f / (float)(count + 1);
-    const vec2 dp = sampleUniformDiskConcentric(V2(u.y, u.z));
-    LightSample r;
-    if (lightIndex >= count)
-    {
-        const vec3 diskPoint = V3(dp.x, dp.y, 0.0f) * 0.001f;
-        const vec3 direction = normalize(V3(__ldg(&lb->dirDirection)));
-        r.Direction = normalize(direction + mul(computeTangentSpace(direction), diskPoint));
-        r.Color = V3(__ldg(&lb->dirColor));
-        r.Distance = 100000.0f;
-        r.Attenuation = 1.0f;
-        return r;
-    }
-    const float4 lc = __ldg(&lb->point[lightIndex * 3]), lp = __ldg(&lb->point[lightIndex * 3 + 1]);
-    const float4 la = __ldg(&lb->point[lightIndex * 3 + 2]);
-    const vec3 diskPoint = V3(dp.x, dp.y, 0.0f) * 0.1f;
-    const vec3 direction = normalize(position - V3(lp));
-    const vec3 newPosition = V3(lp) + mul(computeTangentSpace(direction), diskPoint);
-    r.Distance = length(position - newPosition);
-    r.Direction = normalize(position - newPosition);
-    r.Color = V3(lc);
-    const float attenuation = 1.0f / (la.x + r.Distance * la.y + r.Distance * r.Distance * la.z);
-    r.Attenuation = clampf(attenuation, 0.0f, 1.0f);
     return r;
 }
 
@@ -477,41 +430,15 @@ template <bool ALPHA, bool STATS> __global__ void __launch_bounds__(128, PT_SHAD
 
         // ---- tracing.glsl:2-28 -------------------------------------------------------------
         vec3 dpdu, dpdv, dndu, dndv;
-        {
-            const vec3 en1 = n1 - n0, en2 = n2 - n0;
-            const vec2 duv1 = uv1 - uv0, duv2 = uv2 - uv0;
-            const float det = duv1.x * duv2.y - duv2.x * duv1.y;
-            if (fabsf(det) < 1e-8f)
-            {
-                dpdu = tangent;
-                dpdv = bitangent;
-                dndu = V3(0.0f);
-                dndv = V3(0.0f);
-            }
-            else
-            {
-                const float invDet = 1.0f / det;
-                dpdu = (duv2.y * edge1 - duv1.y * edge2) * invDet;
-                dpdv = (-duv2.x * edge1 + duv1.x * edge2) * invDet;
-                dndu = (duv2.y * en1 - duv1.y * en2) * invDet;
-                dndv = (-duv2.x * en1 + duv1.x * en2) * invDet;
-            }
-        }
+        computeDpnDuv(edge1, edge2, n1 - n0, n2 - n0, uv1 - uv0, uv2 - uv0, tangent, bitangent, dpdu, dpdv, dndu, dndv);
         const float4 d0 = rc.ps.rec[slot].diff0, d1 = rc.ps.rec[slot].diff1, d2 = rc.ps.rec[slot].diff2;
         RayDifferentials rd;
         rd.rxOrigin = V3(d0.x, d0.y, d0.z);
         rd.rxDirection = V3(d0.w, d1.x, d1.y);
         rd.ryOrigin = V3(d1.z, d1.w, d2.x);
         rd.ryDirection = V3(d2.y, d2.z, d2.w);
-        // tracing.glsl:31-41
         vec3 dpdx, dpdy;
-        {
-            const float d = -dot(normal, position);
-            const float tx = (-dot(normal, rd.rxOrigin) - d) / dot(normal, rd.rxDirection);
-            const float ty = (-dot(normal, rd.ryOrigin) - d) / dot(normal, rd.ryDirection);
-            dpdx = (rd.rxOrigin + tx * rd.rxDirection) - position;
-            dpdy = (rd.ryOrigin + ty * rd.ryDirection) - position;
-        }
+        computeDpDxy(position, rd.rxOrigin, rd.rxDirection, rd.ryOrigin, rd.ryDirection, normal, dpdx, dpdy);
         const float4 derivatives = computeDerivatives(dpdx, dpdy, dpdu, dpdv);
 
         // ---- material, closestHit.rchit:101-117 -------------------------------------------------

@@ -158,3 +158,31 @@ def test_camera_and_offsets(renderer, oracle_mod, default_scene):
     d = rs.uniform(0, 1, (n, 2)).astype(np.float32)
     assert_close(renderer.test_shading(14, d), oracle_mod.test_shading(14, d), atol=1e-7)
     assert_close(renderer.test_shading(15, nn), oracle_mod.test_shading(15, nn), atol=1e-7)
+
+
+# ---- the units the reference's tests do not cover: tracing.glsl, ray.glsl:109-131, sampling.glsl, material.glsl ----
+# (the ORACLE's functions are bit-identical to the reference's compiled GLSL on the same generators:
+# tests/test_oracle_vs_glsl.py)
+
+import unit_inputs as ui
+
+
+@pytest.mark.parametrize("mode", [16, 17, 18, 19, 20, 21, 22, 23, 24, 25], ids=[ui.MODE_NAMES[m] for m in range(16, 26)])
+def test_geometry_and_differential_units(renderer, oracle_mod, mode):
+    n = 2000 if mode == 22 else 20000  # one 3 KB light block per sampleLight record
+    x = ui.inputs(mode, n, seed=21)
+    got, want = renderer.test_shading(mode, x), oracle_mod.test_shading(mode, x)
+    assert (np.isnan(got) == np.isnan(want)).all()
+    if mode in (16, 17, 21, 24, 25):
+        # same operations in the same order: bit for bit
+        assert ui.bit_equal(got, want).all(), f"{(~ui.bit_equal(got, want)).sum()} records differ"
+        return
+    floor = noise_floor(oracle_mod, mode, x)
+    if mode == 23:
+        # the core transforms with the precomposed (instance x mesh) matrix and normal matrix (k_bake); the GLSL
+        # inverts per vertex: positions bit for bit, unit vectors to 1e-5 of their length
+        assert ui.bit_equal(got[:, :3], want[:, :3]).all()
+        assert_close(got[:, 3:], want[:, 3:], atol=1e-5, floor=floor[:, 3:])
+        return
+    # unit directions / clamped derivatives: relative 1e-5 on the scale of the value, plus the conditioning floor
+    assert_close(got, want, atol=1e-6, floor=floor)
