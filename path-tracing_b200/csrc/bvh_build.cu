@@ -452,6 +452,68 @@ __global__ void k_ploc_merge(const int *__restrict__ clusters, uint32_t m, const
     clustersOut[pos] = node;
 }
 
+// Writes one wide node from the exact child boxes (empty slots: lo = +inf, hi = -inf, ref = PT_CHILD_EMPTY).
+__device__ __forceinline__ void writeWideNode(BvhNode *dst, const float lo[3][4], const float hi[3][4], const int ref[4], int cc)
+{
+    BvhNode out;
+#if PT_QNODES
+    float o[3], step[3];
+    uint32_t qlo[3] = { 0, 0, 0 }, qhi[3] = { 0, 0, 0 };
+    for (int j = 0; j < 3; j++)
+    {
+        float mn = INFINITY, mx = -INFINITY;
+        for (int i = 0; i < 4; i++)
+            if (ref[i] != PT_CHILD_EMPTY)
+            {
+                mn = fminf(mn, lo[j][i]);
+                mx = fmaxf(mx, hi[j][i]);
+            }
+        if (!(mn <= mx) || !isfinite(mn) || !isfinite(mx)) // no children, or non-finite geometry: a box nothing hits
+            mn = mx = 0.0f;
+        // grid: 254 steps must span the node (one step of head room for the outward rounding below)
+        int ex = 0;
+        const float ext = mx - mn;
+        (void)frexpf(fmaxf(ext / 254.0f, 1e-30f), &ex); // ext / 254 = m * 2^ex, m in [0.5, 1)  =>  2^ex >= ext / 254
+        o[j] = mn;
+        step[j] = ldexpf(1.0f, ex);
+        for (int i = 0; i < 4; i++)
+        {
+            uint32_t a = 255u, b = 0u; // empty: entry plane beyond exit plane
+            if (ref[i] != PT_CHILD_EMPTY && isfinite(lo[j][i]) && isfinite(hi[j][i]))
+            {
+                // outward rounding, verified with directed rounding: origin + a * step <= lo, origin + b * step >= hi
+                int qa = (int)floorf((lo[j][i] - mn) / step[j]), qb = (int)ceilf((hi[j][i] - mn) / step[j]);
+                qa = max(0, min(255, qa));
+                qb = max(0, min(255, qb));
+                while (qa > 0 && __fmaf_ru((float)qa, step[j], mn) > lo[j][i])
+                    qa--;
+                while (qb < 255 && __fmaf_rd((float)qb, step[j], mn) < hi[j][i])
+                    qb++;
+                a = (uint32_t)qa, b = (uint32_t)qb;
+            }
+            qlo[j] |= a << (8 * i);
+            qhi[j] |= b << (8 * i);
+        }
+    }
+    out.ox = o[0], out.oy = o[1], out.oz = o[2];
+    out.sx = step[0], out.sy = step[1], out.sz = step[2];
+    out.qlox = qlo[0], out.qloy = qlo[1], out.qloz = qlo[2];
+    out.qhix = qhi[0], out.qhiy = qhi[1], out.qhiz = qhi[2];
+    out.child = make_int4(ref[0], ref[1], ref[2], ref[3]);
+    (void)cc;
+#else
+    out.lox = make_float4(lo[0][0], lo[0][1], lo[0][2], lo[0][3]);
+    out.loy = make_float4(lo[1][0], lo[1][1], lo[1][2], lo[1][3]);
+    out.loz = make_float4(lo[2][0], lo[2][1], lo[2][2], lo[2][3]);
+    out.hix = make_float4(hi[0][0], hi[0][1], hi[0][2], hi[0][3]);
+    out.hiy = make_float4(hi[1][0], hi[1][1], hi[1][2], hi[1][3]);
+    out.hiz = make_float4(hi[2][0], hi[2][1], hi[2][2], hi[2][3]);
+    out.child = make_int4(ref[0], ref[1], ref[2], ref[3]);
+    out.pad = make_int4(cc, 0, 0, 0);
+#endif
+    *dst = out;
+}
+
 // One work item = (BVH2 internal node, wide node index, first triangle of the node's range in the
 // final order).  Children are opened largest-area first until the node is 4 wide; sub-trees of
 // <= PT_MAX_LEAF_TRIS primitives become leaves.  The triangles are laid out depth first: child k
@@ -544,16 +606,7 @@ __global__ void k_collapse(Bvh2 t, int n, const uint4 *__restrict__ work, uint32
         }
         first += count;
     }
-    BvhNode out;
-    out.lox = make_float4(lo[0][0], lo[0][1], lo[0][2], lo[0][3]);
-    out.loy = make_float4(lo[1][0], lo[1][1], lo[1][2], lo[1][3]);
-    out.loz = make_float4(lo[2][0], lo[2][1], lo[2][2], lo[2][3]);
-    out.hix = make_float4(hi[0][0], hi[0][1], hi[0][2], hi[0][3]);
-    out.hiy = make_float4(hi[1][0], hi[1][1], hi[1][2], hi[1][3]);
-    out.hiz = make_float4(hi[2][0], hi[2][1], hi[2][2], hi[2][3]);
-    out.child = make_int4(ref[0], ref[1], ref[2], ref[3]);
-    out.pad = make_int4(cc, 0, 0, 0);
-    nodes[dst] = out;
+    writeWideNode(nodes + dst, lo, hi, ref, cc);
 }
 
 // root of a scene whose whole BVH2 is one leaf (1..PT_MAX_LEAF_TRIS primitives)
@@ -572,16 +625,15 @@ __global__ void k_single_leaf_root(const Aabb *__restrict__ primBoxes, const uin
             m.lo[j] = fminf(m.lo[j], primBoxes[sortedIdx[k]].lo[j]);
             m.hi[j] = fmaxf(m.hi[j], primBoxes[sortedIdx[k]].hi[j]);
         }
-    BvhNode out;
-    out.lox = make_float4(m.lo[0], INFINITY, INFINITY, INFINITY);
-    out.loy = make_float4(m.lo[1], INFINITY, INFINITY, INFINITY);
-    out.loz = make_float4(m.lo[2], INFINITY, INFINITY, INFINITY);
-    out.hix = make_float4(m.hi[0], -INFINITY, -INFINITY, -INFINITY);
-    out.hiy = make_float4(m.hi[1], -INFINITY, -INFINITY, -INFINITY);
-    out.hiz = make_float4(m.hi[2], -INFINITY, -INFINITY, -INFINITY);
-    out.child = make_int4(encodeLeaf(0, n), PT_CHILD_EMPTY, PT_CHILD_EMPTY, PT_CHILD_EMPTY);
-    out.pad = make_int4(1, 0, 0, 0);
-    nodes[0] = out;
+    float lo[3][4], hi[3][4];
+    int ref[4] = { encodeLeaf(0, n), PT_CHILD_EMPTY, PT_CHILD_EMPTY, PT_CHILD_EMPTY };
+    for (int j = 0; j < 3; j++)
+        for (int i = 0; i < 4; i++)
+        {
+            lo[j][i] = i == 0 ? m.lo[j] : INFINITY;
+            hi[j][i] = i == 0 ? m.hi[j] : -INFINITY;
+        }
+    writeWideNode(nodes, lo, hi, ref, 1);
 }
 
 __global__ void k_gather(const uint32_t *__restrict__ sortedIdx, uint32_t n, const float4 *__restrict__ posIn,

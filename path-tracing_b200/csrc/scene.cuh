@@ -21,8 +21,27 @@ namespace pt
 {
 
 // ---------------------------------------------------------------------------------------------
-// BVH4 node, 128 bytes
+// BVH4 node.  PT_QNODES = 0: 128 bytes, fp32 child boxes (SoA).  PT_QNODES = 1: 64 bytes — the child
+// boxes quantised to 8 bits per plane on a per-node grid (origin = min corner of the node, one power-of-two
+// step per axis; Ylitie, Karras, Laine 2017 in 4-wide form), rounded OUTWARDS so that a quantised box
+// always contains the exact one: traversal stays conservative, hits are unchanged, and a node costs
+// half the cache footprint (the trace kernels live on L1 / L2 capacity for nodes).
 // ---------------------------------------------------------------------------------------------
+#ifndef PT_QNODES
+#define PT_QNODES 1
+#endif
+#if PT_QNODES
+struct __align__(16) BvhNode
+{
+    float ox, oy, oz; // grid origin
+    float sx;         // grid steps (powers of two)
+    float sy, sz;
+    uint32_t qlox, qloy; // byte i of q* = plane of child i in grid steps from the origin
+    uint32_t qloz, qhix, qhiy, qhiz;
+    int4 child; // >= 0: internal node index; < 0: leaf, ~child = (firstTri << 2) | (count - 1)
+};
+static_assert(sizeof(BvhNode) == 64, "quantised BvhNode must be 64 bytes");
+#else
 struct __align__(16) BvhNode
 {
     float4 lox, loy, loz; // child i: lo = (lox[i], loy[i], loz[i])
@@ -31,6 +50,7 @@ struct __align__(16) BvhNode
     int4 pad;
 };
 static_assert(sizeof(BvhNode) == 128, "BvhNode must be one 128-byte line");
+#endif
 
 #define PT_CHILD_EMPTY 0x7fffffff
 #ifndef PT_MAX_LEAF_TRIS

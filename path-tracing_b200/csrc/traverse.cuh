@@ -201,6 +201,37 @@ PT_DEV float4 anyHitColor(const DeviceScene &s, uint32_t tri, uint32_t materialI
 // The entry / exit planes of every slab are picked by the ray's direction signs when the node is
 // LOADED (per-ray float4 offsets), so a box costs 6 subtractions, 6 multiplications and two
 // four-input max / min (FMNMX + FMNMX3) instead of twelve more two-input min / max.
+#if PT_QNODES
+PT_DEV void intersectNode(const BvhNode *__restrict__ node, const RaySetup &r, float tmin, float tmax, float d[4],
+                          int c[4])
+{
+    const uint4 *q = reinterpret_cast<const uint4 *>(node);
+    const uint4 w0 = __ldg(q), w1 = __ldg(q + 1), w2 = __ldg(q + 2);
+    const int4 ch = __ldg(&node->child);
+    c[0] = ch.x, c[1] = ch.y, c[2] = ch.z, c[3] = ch.w;
+    // plane distance = (origin + k * step - org) * idir = k * (step * idir) + (origin - org) * idir: one FMA per
+    // plane.  A non-finite product (axis-parallel ray) yields NaN, which fminf / fmaxf drop: the axis then
+    // does not constrain the box — conservative.
+    const float ax = __uint_as_float(w0.w) * r.idx, ay = __uint_as_float(w1.x) * r.idy, az = __uint_as_float(w1.y) * r.idz;
+    const float bx = (__uint_as_float(w0.x) - r.org.x) * r.idx, by = (__uint_as_float(w0.y) - r.org.y) * r.idy;
+    const float bz = (__uint_as_float(w0.z) - r.org.z) * r.idz;
+    // entry / exit planes by the sign of the direction
+    const uint32_t nxw = r.nearX ? w2.y : w1.z, fxw = r.nearX ? w1.z : w2.y;
+    const uint32_t nyw = r.nearY ? w2.z : w1.w, fyw = r.nearY ? w1.w : w2.z;
+    const uint32_t nzw = r.nearZ ? w2.w : w2.x, fzw = r.nearZ ? w2.x : w2.w;
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+    {
+        const float tnx = fmaf((float)((nxw >> (8 * i)) & 0xffu), ax, bx), tfx = fmaf((float)((fxw >> (8 * i)) & 0xffu), ax, bx);
+        const float tny = fmaf((float)((nyw >> (8 * i)) & 0xffu), ay, by), tfy = fmaf((float)((fyw >> (8 * i)) & 0xffu), ay, by);
+        const float tnz = fmaf((float)((nzw >> (8 * i)) & 0xffu), az, bz), tfz = fmaf((float)((fzw >> (8 * i)) & 0xffu), az, bz);
+        const float t0 = fmaxf(fmaxf(tnx, tny), fmaxf(tnz, tmin));
+        const float t1 = fminf(fminf(tfx, tfy), fminf(tfz, tmax));
+        // conservative: the slack absorbs the rounding of the three-operation plane distance
+        d[i] = (c[i] != PT_CHILD_EMPTY && t0 <= t1 * 1.0000008f) ? t0 : INFINITY;
+    }
+}
+#else
 PT_DEV void intersectNode(const BvhNode *__restrict__ node, const RaySetup &r, float tmin, float tmax, float d[4],
                           int c[4])
 {
@@ -231,6 +262,8 @@ PT_DEV void intersectNode(const BvhNode *__restrict__ node, const RaySetup &r, f
         d[i] = (c[i] != PT_CHILD_EMPTY && t0 <= t1 * 1.0000004f) ? t0 : INFINITY;
     }
 }
+
+#endif
 
 #define PT_CSWAP(i, j)                                                                                                \
     if (d[j] < d[i])                                                                                                  \
@@ -572,6 +605,15 @@ PT_DEV void traverse(const DeviceScene &s, vec3 org, vec3 dir, float tmin, float
 //     that sub-tree, and its result is merged into the owner's with the same (t, triangle id)
 //     order the serial traversal uses — the answer is identical, the tail up to 32x shorter.
 // ---------------------------------------------------------------------------------------------
+// the prefetch stages of tracePersistent as calls (0) or inlined at their call sites (1)
+#ifndef PT_INLINE_PREFETCH
+#define PT_INLINE_PREFETCH 1
+#endif
+#if PT_INLINE_PREFETCH
+#define PT_PREFETCH_INLINE __attribute__((always_inline))
+#else
+#define PT_PREFETCH_INLINE
+#endif
 #ifndef PT_FETCH_CHUNK
 #define PT_FETCH_CHUNK 32u
 #endif
@@ -612,7 +654,7 @@ PT_DEV void tracePersistent(const DeviceScene &s, uint32_t n, uint32_t *workCoun
     uint32_t nxCount = 0; // warp-uniform: lanes [0, nxCount) hold the slot indices of the batch after the buffer
     uint32_t nxSlot = 0;
     // stage 1: request the slot indices of the next batch of the warp's chunk
-    auto prefetchSlots = [&]() {
+    auto prefetchSlots = [&]() PT_PREFETCH_INLINE {
         nxCount = 0;
         if (exhausted)
             return;
@@ -636,7 +678,7 @@ PT_DEV void tracePersistent(const DeviceScene &s, uint32_t n, uint32_t *workCoun
         wBase += nxCount;
     };
     // stage 2: request the rays of the batch whose slot indices arrived meanwhile, then stage 1 again
-    auto prefetch = [&]() {
+    auto prefetch = [&]() PT_PREFETCH_INLINE {
         pfPos = 0;
         pfCount = nxCount;
         if (lane < nxCount)

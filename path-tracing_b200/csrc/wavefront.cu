@@ -51,6 +51,16 @@ namespace
 #define PT_SHADE_MIN_BLOCKS 4
 #endif
 
+// the ray-load lambda of k_extend (which also regenerates ended paths) as a call (0) or inlined at its two call sites (1)
+#ifndef PT_INLINE_LOADRAY
+#define PT_INLINE_LOADRAY 1
+#endif
+#if PT_INLINE_LOADRAY
+#define PT_LOADRAY_INLINE __attribute__((always_inline))
+#else
+#define PT_LOADRAY_INLINE
+#endif
+
 constexpr uint32_t kMaxRestarts = 1024; // the reference's restart loop is unbounded; see oracle
 
 struct RenderConst
@@ -255,7 +265,7 @@ template <bool ALPHA, bool STATS> __global__ void __launch_bounds__(128, PT_TRAC
     tracePersistent(
         rc.scene, n, &rc.qc->extendWork, tr, 0.00001f,
         [&](uint32_t i) { return activeSlot(rc, cur, i, nCont); },
-        [&](uint32_t entry) {
+        [&](uint32_t entry) PT_LOADRAY_INLINE {
             if (entry & kRegen)
                 return regeneratePath(rc, entry, samples, restarts);
             RayPacket p;

@@ -17,6 +17,8 @@ from __future__ import annotations
 
 import math
 
+import os
+
 import numpy as np
 
 from . import scene as sc
@@ -757,16 +759,19 @@ def atrium_scene(width: int = 3840, height: int = 2160, bays: int = 12, column_s
     # branch: cards scattered in a flat slab (a hanging curtain of leaves), random orientation
     cards_v, cards_i = [], []
     qv, qi = quad(0.22, 0.22)
+    _tess = int(os.environ.get("PT_ATRIUM_CARD_TESS", "1"))  # experiment: tessellated cards (what reference splitting buys)
+    if _tess > 1:
+        qv, qi = grid(_tess, _tess, 0.22, 0.22)
     for k in range(cards_per_branch):
         m = (translate(*(rs.uniform(-0.5, 0.5, 3) * np.array([1.0, 1.0, 0.25]))) @ rotate_y(rs.uniform(0, 360)) @
              rotate_x(rs.uniform(40, 140)))
         v = qv.copy()
-        p = np.concatenate([qv["position"], np.ones((4, 1), F)], 1) @ m.T
+        p = np.concatenate([qv["position"], np.ones((len(qv), 1), F)], 1) @ m.T
         v["position"] = p[:, :3]
         for f in ("normal", "tangent", "bitangent"):
             v[f] = qv[f] @ m[:3, :3].T
         cards_v.append(v)
-        cards_i.append(qi + 4 * k)
+        cards_i.append(qi + len(qv) * k)
     g_branch = b.add_geometry(np.concatenate(cards_v), np.concatenate(cards_i), is_opaque=False)
 
     column = b.add_model([(g_column, m_stone, None)])
