@@ -2583,17 +2583,39 @@ int32_t pto_first_hit_aov(const pto_scene *s, const pt_render_params *p, uint32_
         return PT_ERR_INVALID_ARGUMENT;
     const mat4 ViewInverse = toMat4(p->view_inverse);
     const mat4 ProjInverse = toMat4(p->proj_inverse);
-    Counters c;
-    for (uint32_t y = 0; y < height; y++)
-        for (uint32_t x = 0; x < width; x++)
+    /* rows are independent: all host threads */
+    int nthreads = (int)std::thread::hardware_concurrency();
+    if (nthreads < 1 || (uint64_t)width * height < 65536)
+        nthreads = 1;
+    std::atomic<uint32_t> nextRow { 0 };
+    auto worker = [&]() {
+        Counters c;
+        for (;;)
         {
-            Ray rx, ry;
-            /* PT/Shaders/ray.glsl:87-90: pixel centre */
-            const Ray ray = constructPrimaryRay(V2((float)x, (float)y), V2((float)width, (float)height), ViewInverse,
-                                                ProjInverse, V2(0.5f, 0.5f), rx, ry);
-            const HitInfo h = traceClosest(*s, ray.Origin, ray.Direction, ray.tmin, ray.tmax, c);
-            out_hits[(size_t)y * width + x] = toPtHit(*s, h);
+            const uint32_t y = nextRow.fetch_add(1);
+            if (y >= height)
+                break;
+            for (uint32_t x = 0; x < width; x++)
+            {
+                Ray rx, ry;
+                /* PT/Shaders/ray.glsl:87-90: pixel centre */
+                const Ray ray = constructPrimaryRay(V2((float)x, (float)y), V2((float)width, (float)height), ViewInverse,
+                                                    ProjInverse, V2(0.5f, 0.5f), rx, ry);
+                const HitInfo h = traceClosest(*s, ray.Origin, ray.Direction, ray.tmin, ray.tmax, c);
+                out_hits[(size_t)y * width + x] = toPtHit(*s, h);
+            }
         }
+    };
+    if (nthreads == 1)
+        worker();
+    else
+    {
+        std::vector<std::thread> pool;
+        for (int i = 0; i < nthreads; i++)
+            pool.emplace_back(worker);
+        for (auto &t : pool)
+            t.join();
+    }
     return PT_OK;
 }
 

@@ -45,7 +45,7 @@ def test_image_parity(config):
     # chaotic paths: a 1-ulp difference re-routes a path; transmissive / alpha-tested scenes have more of them
     assert metrics.close_fraction(img, ref, 1e-3) > (0.93 if name == "dragon" else 0.96), name
     assert metrics.rel_mse(img / spp, ref / spp) <= 1e-3, name
-    assert metrics.flip_lite(img / spp, ref / spp) <= 5e-3, name
+    assert metrics.flip(img / spp, ref / spp) <= 5e-3, name
     assert abs(st["rays_closest"] - cnt["rays_closest"]) <= 3e-3 * cnt["rays_closest"]
     assert abs(st["hits"] - cnt["hits"]) <= 3e-3 * cnt["hits"]
     assert st["rays_shadow"] <= cnt["rays_shadow"]  # exactly-zero contributions are not traced

@@ -27,7 +27,7 @@ def test_default_scene_config0(default_renderer, default_oracle, default_scene):
     assert metrics.close_fraction(img, ref, 1e-4) > 0.995
     # image-level bars of BASELINE.md §5 at matched spp
     assert metrics.rel_mse(img / 16, ref / 16) <= 1e-3
-    assert metrics.flip_lite(img / 16, ref / 16) <= 5e-3
+    assert metrics.flip(img / 16, ref / 16) <= 5e-3
     assert abs(img[..., :3].mean() - ref[..., :3].mean()) <= 1e-3 * ref[..., :3].mean()
     # same work: ray and sample counts agree to a handful of diverged paths
     assert st["samples"] == cnt["samples"] == 512 * 512 * 16
@@ -135,7 +135,7 @@ def test_feature_scene(feature, lens):
     assert st["rays_shadow"] > 0 and cnt["alpha_tests_closest"] > 0
     assert metrics.close_fraction(img, ref, 1e-3) > 0.97
     assert metrics.rel_mse(img / spp, ref / spp) <= 1e-3
-    assert metrics.flip_lite(img / spp, ref / spp) <= 5e-3
+    assert metrics.flip(img / spp, ref / spp) <= 5e-3
     assert abs(st["rays_closest"] - cnt["rays_closest"]) <= 2e-3 * cnt["rays_closest"]
     # the core skips occlusion queries whose contribution is exactly zero, the oracle traces them
     assert st["rays_shadow"] <= cnt["rays_shadow"]
