@@ -418,6 +418,16 @@ PT_API pt_status pt_render_begin(pt_context *ctx, uint32_t width, uint32_t heigh
 PT_API pt_status pt_render_samples(pt_context *ctx, const pt_render_params *params, uint32_t first_sample,
                                    uint32_t sample_count, const pt_tile *tiles, uint32_t tile_count);
 
+/* The same with the reference's Release-profile frame structure (Config::SamplesPerFrame > 1 and the adaptive
+ * Renderer::s_SamplesPerFrame, PT/Renderer/Renderer.cpp:1631-1657, 1688-1700): frame f is one vkCmdTraceRaysKHR with
+ * SampleCount = samples_per_frame and TotalSamples = first_sample + f * samples_per_frame, i.e. raygen.rgen:36-118 runs
+ * the samples of a pixel on ONE rng stream (seeded from TotalSamples), sums their radiance before touching the image
+ * and restarts ALL of them when the running sum turns NaN / Inf (raygen.rgen:99-112).  samples_per_frame = 1 is
+ * pt_render_samples.  1 <= samples_per_frame <= 8192. */
+PT_API pt_status pt_render_frames(pt_context *ctx, const pt_render_params *params, uint32_t first_sample,
+                                  uint32_t frame_count, uint32_t samples_per_frame, const pt_tile *tiles,
+                                  uint32_t tile_count);
+
 /* Device address of the float4 accumulation (sum) buffer, row pitch in bytes, and the CUDA
  * stream (cudaStream_t as void*) work is queued on — for an NCCL reduce/gather in the caller. */
 PT_API pt_status pt_accum_device_ptr(pt_context *ctx, void **out_float4_device_ptr, size_t *out_pitch_bytes,

@@ -30,6 +30,7 @@ ABI_SYMBOLS = [
     "pt_texture_upload",
     "pt_render_begin",
     "pt_render_samples",
+    "pt_render_frames",
     "pt_accum_device_ptr",
     "pt_readback",
     "pt_postprocess",
@@ -193,6 +194,7 @@ def lib():
     L.pt_texture_upload.argtypes = [vp, u32, vp]
     L.pt_render_begin.argtypes = [vp, u32, u32]
     L.pt_render_samples.argtypes = [vp, vp, u32, u32, vp, u32]
+    L.pt_render_frames.argtypes = [vp, vp, u32, u32, u32, vp, u32]
     L.pt_accum_device_ptr.argtypes = [vp, C.POINTER(vp), C.POINTER(C.c_size_t), C.POINTER(vp)]
     L.pt_readback.argtypes = [vp, vp, C.c_size_t]
     L.pt_postprocess.argtypes = [vp, vp, u32, u32, vp, C.c_size_t]
@@ -311,6 +313,18 @@ class Renderer:
         )
         if first_sample is None:
             self.total_samples += samples
+
+    def render_frames(self, frames: int, samples_per_frame: int, tiles=None, params: sc.RenderParams | None = None,
+                      first_sample: int | None = None):
+        """Renderer::Render `frames` times with SamplesPerFrame = samples_per_frame (one rng stream and one radiance
+        sum per pixel and frame, Renderer.cpp:1688-1700)."""
+        p = (params or self.params).to_c()
+        first = self.total_samples if first_sample is None else first_sample
+        tl = None if tiles is None else np.ascontiguousarray(tiles, sc.TILE)
+        self._check(self._L.pt_render_frames(self._h, C.addressof(p), first, frames, samples_per_frame,
+                                             None if tl is None else tl.ctypes.data, 0 if tl is None else len(tl)))
+        if first_sample is None:
+            self.total_samples += frames * samples_per_frame
 
     def read_accumulation(self, out: np.ndarray | None = None) -> np.ndarray:
         if out is None:

@@ -179,7 +179,7 @@ pt_texture_desc defaultTexture(const uint32_t *rgba, bool srgb);
 
 // wavefront.cu
 pt_status allocSortTemp(Context *ctx, size_t slots);
-pt_status renderSamples(Context *ctx, const pt_render_params *params, uint32_t firstSample, uint32_t sampleCount,
+pt_status renderFrames(Context *ctx, const pt_render_params *params, uint32_t firstSample, uint32_t frameCount, uint32_t samplesPerFrame,
                         const pt_tile *tiles, uint32_t tileCount);
 pt_status firstHitAov(Context *ctx, const pt_render_params *params, uint32_t width, uint32_t height, pt_hit *out);
 pt_status debugRender(Context *ctx, const pt_render_params *params, const pt_debug_params *debug, uint32_t width, uint32_t height,

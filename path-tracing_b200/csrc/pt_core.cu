@@ -257,7 +257,16 @@ pt_status pt_render_samples(pt_context *ctx, const pt_render_params *params, uin
     if (!ctx)
         return PT_ERR_INVALID_ARGUMENT;
     cudaSetDevice(ctx->device);
-    return renderSamples(ctx, params, first_sample, sample_count, tiles, tile_count);
+    return renderFrames(ctx, params, first_sample, sample_count, 1, tiles, tile_count);
+}
+
+pt_status pt_render_frames(pt_context *ctx, const pt_render_params *params, uint32_t first_sample, uint32_t frame_count,
+                           uint32_t samples_per_frame, const pt_tile *tiles, uint32_t tile_count)
+{
+    if (!ctx)
+        return PT_ERR_INVALID_ARGUMENT;
+    cudaSetDevice(ctx->device);
+    return renderFrames(ctx, params, first_sample, frame_count, samples_per_frame, tiles, tile_count);
 }
 
 pt_status pt_accum_device_ptr(pt_context *ctx, void **out_ptr, size_t *out_pitch, void **out_stream)

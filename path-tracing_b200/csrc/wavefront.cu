@@ -62,6 +62,9 @@ namespace
 #endif
 
 constexpr uint32_t kMaxRestarts = 1024; // the reference's restart loop is unbounded; see oracle
+// path state word (PathRecord::thr.w): bounce [0, 8), NaN/Inf restarts of the frame [8, 19), sample of the frame [19, 32)
+constexpr uint32_t kRestartShift = 8, kRestartMask = 0x7ffu, kSampleShift = 19;
+constexpr uint32_t kMaxSamplesPerFrame = 1u << (32 - kSampleShift);
 
 struct RenderConst
 {
@@ -73,6 +76,7 @@ struct RenderConst
     QueueCounts *qc;
     uint32_t width, height;
     uint32_t firstSample, sampleCount;
+    uint32_t samplesPerFrame;    // raygen.rgen's SampleCount: samples one work item (pixel, frame) runs on ONE rng stream
     uint32_t bounceCount;
     float lensRadius, focalDistance;
     uint32_t missFlags, hitFlags;
@@ -121,7 +125,7 @@ constexpr uint32_t kDeadSlot = 0xffffffffu;  // RayPacket::slot of a regen entry
 // raygen.rgen:44-60 — start one sample of a slot's pixel; returns the primary ray
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ PrimaryRays generatePath(const RenderConst &rc, uint32_t slot, uint32_t pixel, uint32_t item,
-                                                    uint32_t rng, uint32_t restarts)
+                                                    uint32_t rng, uint32_t restarts, uint32_t smpl = 0, vec3 radiance = { 0.0f, 0.0f, 0.0f })
 {
     const uint32_t py = pixel / rc.width, px = pixel - py * rc.width;
     const float ux = rnd(rng);
@@ -137,8 +141,8 @@ __device__ __forceinline__ PrimaryRays generatePath(const RenderConst &rc, uint3
     PathRecord &rec = rc.ps.rec[slot];
     rec.rayO = make_float4(pr.origin.x, pr.origin.y, pr.origin.z, 0.0f); // MaxRoughness = 0
     rec.rayD = make_float4(pr.direction.x, pr.direction.y, pr.direction.z, __uint_as_float(rng));
-    rec.thr = make_float4(1.0f, 1.0f, 1.0f, __uint_as_float(restarts << 8)); // bounce 0
-    rec.rad = make_float4(0.0f, 0.0f, 0.0f, __uint_as_float(item));
+    rec.thr = make_float4(1.0f, 1.0f, 1.0f, __uint_as_float((smpl << kSampleShift) | (restarts << kRestartShift))); // bounce 0
+    rec.rad = make_float4(radiance.x, radiance.y, radiance.z, __uint_as_float(item));
     rec.diff0 = make_float4(pr.origin.x, pr.origin.y, pr.origin.z, pr.rxDirection.x);
     rec.diff1 = make_float4(pr.rxDirection.y, pr.rxDirection.z, pr.origin.x, pr.origin.y);
     rec.diff2 = make_float4(pr.origin.z, pr.ryDirection.x, pr.ryDirection.y, pr.ryDirection.z);
@@ -151,7 +155,8 @@ __device__ __forceinline__ PrimaryRays startItem(const RenderConst &rc, uint32_t
     const uint32_t s = item / rc.pixelCount, pi = item - s * rc.pixelCount;
     const uint32_t pixel = __ldg(rc.pixelList + pi);
     const uint32_t py = pixel / rc.width, px = pixel - py * rc.width;
-    return generatePath(rc, slot, pixel, item, initRng(px, py, rc.width, rc.firstSample + rc.roundBase + s), 0);
+    // frame s of the round: TotalSamples = samples accumulated before it (Renderer.cpp:1694-1700)
+    return generatePath(rc, slot, pixel, item, initRng(px, py, rc.width, rc.firstSample + (rc.roundBase + s) * rc.samplesPerFrame), 0);
 }
 
 // slot i (of all pools together) starts with work item i of the round
@@ -214,25 +219,32 @@ __device__ __forceinline__ RayPacket regeneratePath(const RenderConst &rc, uint3
     if (entry & kRegenMiss) // miss.rmiss + raygen.rgen:71-75: the path ended with the sky radiance
         radiance = radiance + V3(thr4) * skyRadiance(rc, V3(d4));
     uint32_t item = __float_as_uint(rad4.w);
-    uint32_t restartCount = __float_as_uint(thr4.w) >> 8;
+    const uint32_t state = __float_as_uint(thr4.w);
+    const uint32_t restartCount = (state >> kRestartShift) & kRestartMask, smpl = state >> kSampleShift;
     const bool isBad = bad(radiance.x) || bad(radiance.y) || bad(radiance.z);
-    // raygen.rgen:99-112: radiance = 0; smpl = -1 — the sample is redone with the ADVANCED rng state
+    // raygen.rgen:99-112: radiance = 0; smpl = -1 — ALL samples of the frame are redone with the ADVANCED rng state
     const bool restart = isBad && restartCount < kMaxRestarts;
     RayPacket p;
     p.slot = kDeadSlot;
     p.ox = p.oy = p.oz = p.dx = p.dy = p.dz = p.tmax = 0.0f;
     PrimaryRays pr;
-    if (restart)
+    if (!restart)
+        samples++; // one kept iteration of the sample loop (raygen.rgen:42) has ended
+    if (restart || smpl + 1 < rc.samplesPerFrame)
     {
-        restarts++;
         const uint32_t s = item / rc.pixelCount, pi = item - s * rc.pixelCount;
-        pr = generatePath(rc, slot, __ldg(rc.pixelList + pi), item, __float_as_uint(d4.w), restartCount + 1);
+        if (restart)
+        {
+            restarts++;
+            pr = generatePath(rc, slot, __ldg(rc.pixelList + pi), item, __float_as_uint(d4.w), restartCount + 1);
+        }
+        else // the frame's next sample: same rng stream, radiance keeps summing (raygen.rgen:40-42)
+            pr = generatePath(rc, slot, __ldg(rc.pixelList + pi), item, __float_as_uint(d4.w), restartCount, smpl + 1, radiance);
     }
     else
     {
-        // park the sample; k_resolve adds the round's samples to the image in sample order
+        // park the frame's radiance; k_resolve adds the round's frames to the image in frame order
         rc.sbuf[item] = isBad ? make_float4(0.0f, 0.0f, 0.0f, 0.0f) : make_float4(radiance.x, radiance.y, radiance.z, 1.0f);
-        samples++;
         item = atomicAggInc(rc.nextItem);
         if (item >= rc.itemCount)
             return p; // the round has no work left for this slot
@@ -915,7 +927,7 @@ pt_status allocSortTemp(Context *ctx, size_t slots)
     return PT_OK;
 }
 
-pt_status renderSamples(Context *ctx, const pt_render_params *params, uint32_t firstSample, uint32_t sampleCount,
+pt_status renderFrames(Context *ctx, const pt_render_params *params, uint32_t firstSample, uint32_t sampleCount, uint32_t samplesPerFrame,
                         const pt_tile *tiles, uint32_t tileCount)
 {
     if (!params)
@@ -926,6 +938,8 @@ pt_status renderSamples(Context *ctx, const pt_render_params *params, uint32_t f
         return fail(ctx, PT_ERR_NO_TARGET, "pt_render_samples", "pt_render_begin has not been called");
     if (params->bounce_count == 0 || params->bounce_count > 255)
         return fail(ctx, PT_ERR_INVALID_ARGUMENT, "pt_render_samples", "bounce_count must be in 1..255");
+    if (samplesPerFrame == 0 || samplesPerFrame > kMaxSamplesPerFrame)
+        return fail(ctx, PT_ERR_INVALID_ARGUMENT, "pt_render_frames", "samples_per_frame must be in 1..8192");
     if (tiles == nullptr)
         tileCount = 0;
 
@@ -1040,6 +1054,7 @@ pt_status renderSamples(Context *ctx, const pt_render_params *params, uint32_t f
         base.height = H;
         base.firstSample = firstSample;
         base.sampleCount = sampleCount;
+        base.samplesPerFrame = samplesPerFrame;
         base.bounceCount = params->bounce_count;
         base.lensRadius = params->lens_radius;
         base.focalDistance = params->focal_distance;

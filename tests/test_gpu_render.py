@@ -270,3 +270,58 @@ def test_errors(default_scene):
             r.render(1, params=bad)
     with pytest.raises(core.PtError):
         core.Renderer(99)
+
+
+@pytest.mark.parametrize("samples_per_frame", [2, 4])
+def test_samples_per_frame(feature, default_renderer, default_oracle, default_scene, samples_per_frame):
+    """pt_render_frames: the reference's Release profile renders SamplesPerFrame > 1 samples per vkCmdTraceRaysKHR —
+    one rng stream seeded from TotalSamples and one radiance sum per pixel and frame (raygen.rgen:36-118,
+    Renderer.cpp:1688-1700).  The oracle's frame loop is bit-identical to the reference's compiled raygen
+    (tests/test_oracle_vs_glsl.py)."""
+    for (s, r, o, W, H, bounces) in ((default_scene, default_renderer, default_oracle, 256, 256, 8),) + ((feature[0], feature[1], feature[2], 160, 120, 6),):
+        p = s.default_params(bounce_count=bounces)
+        frames = 6
+        r.on_resize(W, H)
+        r.render_frames(frames, samples_per_frame, params=p)
+        img = r.read_accumulation()
+        st = r.stats()
+        ref, cnt = o.render_frames(p, W, H, 0, frames, samples_per_frame)
+        n = frames * samples_per_frame
+        assert np.isfinite(img).all() and (img[..., 3] == 1).all()
+        assert st["samples"] == W * H * n
+        assert metrics.close_fraction(img, ref, 1e-3) > 0.97
+        assert metrics.rel_mse(img / n, ref / n) <= 1e-3
+        assert abs(st["rays_closest"] - cnt["rays_closest"]) <= 2e-3 * cnt["rays_closest"]
+        # a frame of S samples is NOT S frames of one sample: different seeds (TotalSamples advances by S per frame)
+        r.on_resize(W, H)
+        r.render(n, params=p)
+        assert not np.array_equal(r.read_accumulation(), img)
+        # but with S = 1 the two entry points are the same thing, bit for bit
+        single = r.read_accumulation()
+        r.on_resize(W, H)
+        r.render_frames(n, 1, params=p)
+        assert np.array_equal(r.read_accumulation(), single)
+
+
+def test_samples_per_frame_continues_and_partitions(default_renderer, default_scene):
+    """Frames are independent given TotalSamples: two calls == one call; tiles == full frame (bit for bit)."""
+    p = default_scene.default_params()
+    r = default_renderer
+    W = H = 128
+    r.on_resize(W, H)
+    r.render_frames(4, 3, params=p)
+    whole = r.read_accumulation()
+    r.on_resize(W, H)
+    r.render_frames(2, 3, params=p)
+    r.render_frames(2, 3, params=p)  # first_sample continues at 6
+    assert np.array_equal(r.read_accumulation(), whole)
+    r.on_resize(W, H)
+    tiles = np.array([(0, 0, W, 40), (0, 40, 64, H)], sc.TILE)
+    r.render_frames(4, 3, params=p, tiles=tiles, first_sample=0)
+    part = r.read_accumulation()
+    mask = np.zeros((H, W), bool)
+    mask[:40] = True
+    mask[40:, :64] = True
+    assert np.array_equal(part[mask], whole[mask]) and (part[~mask] == 0).all()
+    with pytest.raises(conftest.core.PtError):
+        r.render_frames(1, 0, params=p)
