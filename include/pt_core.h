@@ -342,6 +342,9 @@ typedef struct pt_stats {
     uint64_t warp_iterations;
     uint64_t warp_drain_iterations;
     uint64_t max_warp_drain_iterations;
+    uint32_t bvh_max_depth;   /* levels of the wide BVH of the uploaded scene                                     */
+    uint32_t stack_overflows; /* entries the traversal stack could not hold in the last call: non-zero FAILS the
+                                 call (PT_ERR_UNSUPPORTED) — a dropped entry is a skipped sub-tree              */
 } pt_stats;
 
 /* ------------------------------------------------------------------------- */
@@ -508,6 +511,8 @@ PT_API pt_status pt_set_kernel_timing(pt_context *ctx, int32_t enable);
  * order), "sbuf_mb" (sample-buffer budget per round).  The same knobs are read from the
  * environment at pt_context_create: PT_POOLS, PT_SLOTS, PT_SORT_HITS, PT_SBUF_MB. */
 PT_API pt_status pt_set_tuning(pt_context *ctx, const char *key, uint64_t value);
+/* NOTE: keys that resize the path state ("slots", "pools") reallocate the render target like pt_render_begin does:
+ * the accumulated image is reset.  Set them before rendering. */
 
 /* ------------------------------------------------------------------------- */
 /* shader unit-test entry point                                              */

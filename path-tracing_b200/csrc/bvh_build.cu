@@ -34,6 +34,7 @@ struct MeshInstance
     float N[9];   // normal matrix (inverse transpose of the linear part), row-major
     uint32_t triOffset, triCount;
     uint32_t vertexOffset, indexOffset;
+    uint32_t vertexLength;       // vertices of the geometry: every index must be below it
     uint32_t instance, geometry; // gl_InstanceID, geometry index inside the model
     uint32_t materialId, flags;
 };
@@ -58,7 +59,8 @@ __device__ __forceinline__ float floatUnflip(uint32_t u)
 // ---------------------------------------------------------------------------------------------
 __global__ void k_bake(const MeshInstance *__restrict__ mis, uint32_t miCount, const float *__restrict__ vertices,
                        const uint32_t *__restrict__ indices, uint32_t triCount, float4 *__restrict__ triPos,
-                       TriShade *__restrict__ triShade, Aabb *__restrict__ boxes, uint32_t *__restrict__ sceneBounds)
+                       TriShade *__restrict__ triShade, Aabb *__restrict__ boxes, uint32_t *__restrict__ sceneBounds,
+                       uint32_t *__restrict__ badIndexCount)
 {
     const uint32_t tri = blockIdx.x * blockDim.x + threadIdx.x;
     if (tri >= triCount)
@@ -81,7 +83,13 @@ __global__ void k_bake(const MeshInstance *__restrict__ mis, uint32_t miCount, c
     for (int k = 0; k < 3; k++)
     {
         // indices are relative to the geometry's first vertex (PT/Shaders/common.glsl:27-34)
-        const uint32_t index = indices[mi.indexOffset + prim * 3 + k];
+        uint32_t index = indices[mi.indexOffset + prim * 3 + k];
+        if (index >= mi.vertexLength)
+        {
+            // a malformed file: never read outside the geometry's vertices; the upload fails (PT_ERR_INVALID_ARGUMENT)
+            atomicAdd(badIndexCount, 1u);
+            index = 0;
+        }
         const float *v = vertices + (size_t)(mi.vertexOffset + index) * 14;
         const float px = v[0], py = v[1], pz = v[2];
 #pragma unroll
@@ -659,7 +667,7 @@ template <typename T> pt_status devAllocPool(Context *ctx, T **ptr, size_t count
     *ptr = nullptr;
     if (count == 0)
         count = 1;
-    PT_CUDA_CHECK(ctx, cudaMallocAsync((void **)ptr, count * sizeof(T), ctx->stream));
+    PT_CUDA_CHECK(ctx, poolAlloc(ctx, (void **)ptr, count * sizeof(T), ctx->stream));
     owner.push_back(*ptr);
     return PT_OK;
 }
@@ -783,14 +791,24 @@ pt_status buildAccel(Context *ctx, const std::vector<MeshInstance> &mis, uint32_
         PT_TRY(devAllocPool(ctx, &posUnsorted, (size_t)n * 3, temp));
         PT_TRY(devAllocPool(ctx, &shadeUnsorted, (size_t)n, temp));
         PT_TRY(devAllocPool(ctx, &primBoxes, (size_t)n, temp));
-        PT_TRY(devAllocPool(ctx, &sceneBounds, 6, temp));
+        PT_TRY(devAllocPool(ctx, &sceneBounds, 7, temp)); // 6 bounds + the bad-index counter of k_bake
         PT_CUDA_CHECK(ctx, cudaMemcpyAsync(dMis, mis.data(), mis.size() * sizeof(MeshInstance), cudaMemcpyHostToDevice, ctx->stream));
-        const uint32_t boundsInit[6] = { 0xffffffffu, 0xffffffffu, 0xffffffffu, 0u, 0u, 0u };
+        const uint32_t boundsInit[7] = { 0xffffffffu, 0xffffffffu, 0xffffffffu, 0u, 0u, 0u, 0u };
         PT_CUDA_CHECK(ctx, cudaMemcpyAsync(sceneBounds, boundsInit, sizeof(boundsInit), cudaMemcpyHostToDevice, ctx->stream));
         PT_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
         const uint32_t T = 256, G = (n + T - 1) / T;
         k_bake<<<G, T, 0, ctx->stream>>>(dMis, (uint32_t)mis.size(), dVertices, dIndices, n, posUnsorted, shadeUnsorted,
-                                         primBoxes, sceneBounds);
+                                         primBoxes, sceneBounds, sceneBounds + 6);
+        {
+            uint32_t badIndices = 0;
+            PT_CUDA_CHECK(ctx, cudaMemcpyAsync(&badIndices, sceneBounds + 6, 4, cudaMemcpyDeviceToHost, ctx->stream));
+            PT_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+            if (badIndices != 0)
+            {
+                freeTemp();
+                return fail(ctx, PT_ERR_INVALID_ARGUMENT, "pt_scene_upload", "an index is not below its geometry's vertex_length");
+            }
+        }
 
         // ---- Morton codes + sort ------------------------------------------------------------
         uint64_t *keysIn, *keysOut;
@@ -814,7 +832,10 @@ pt_status buildAccel(Context *ctx, const std::vector<MeshInstance> &mis, uint32_
         uint32_t wideCount = 1;
         uint32_t *order = valsOut; // source index of the triangle at every position of the final order
         if (n <= PT_MAX_LEAF_TRIS)
+        {
             k_single_leaf_root<<<1, 1, 0, ctx->stream>>>(primBoxes, valsOut, n, wide);
+            ctx->bvhMaxDepth = 1;
+        }
         else
         {
             Bvh2 t;
@@ -890,8 +911,10 @@ pt_status buildAccel(Context *ctx, const std::vector<MeshInstance> &mis, uint32_
             PT_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
             uint32_t workCount = 1;
             int cur = 0;
+            ctx->bvhMaxDepth = 0;
             while (workCount > 0)
             {
+                ctx->bvhMaxDepth++; // one pass of the collapse = one level of the wide tree
                 PT_CUDA_CHECK(ctx, cudaMemsetAsync(counters + 1 + (cur ^ 1), 0, 4, ctx->stream));
                 k_collapse<<<(workCount + 127) / 128, 128, 0, ctx->stream>>>(t, (int)n, work[cur], workCount, work[cur ^ 1],
                                                                              counters + 1 + (cur ^ 1), wide, counters, valsOut,
@@ -1002,6 +1025,7 @@ pt_status flattenInstances(Context *ctx, const SceneTopology &t, std::vector<Mes
             // skinned vertices / animated indices sit behind the static ones in the device buffers
             m.vertexOffset = g.vertex_offset + (animated ? (uint32_t)t.vertexCount : 0u);
             m.indexOffset = g.index_offset + (animated ? (uint32_t)t.indexCount : 0u);
+            m.vertexLength = g.vertex_length;
             m.instance = ii;
             m.geometry = mi;
             m.materialId = rec.material_id;
@@ -1035,9 +1059,8 @@ void freeScene(Context *ctx)
     {
         // hand the pool's cached blocks back to the driver: the next scene may be of another size
         cudaStreamSynchronize(ctx->stream);
-        cudaMemPool_t pool;
-        if (cudaDeviceGetDefaultMemPool(&pool, ctx->device) == cudaSuccess)
-            cudaMemPoolTrimTo(pool, 0);
+        if (ctx->memPool)
+            cudaMemPoolTrimTo(ctx->memPool, 0);
     }
     for (void *p : ctx->sceneAllocs)
         cudaFree(p);
@@ -1077,7 +1100,9 @@ pt_status uploadScene(Context *ctx, const pt_scene_desc *d)
         return fail(ctx, PT_ERR_INVALID_ARGUMENT, "pt_scene_upload", "transforms[0] (identity) is required");
     if ((d->vertex_count && !d->vertices) || (d->index_count && !d->indices) || (d->geometry_count && !d->geometries) ||
         (d->mesh_record_count && !d->mesh_records) || (d->model_count && !d->models) ||
-        (d->instance_count && !d->instances) || (d->texture_count && !d->textures))
+        (d->instance_count && !d->instances) || (d->texture_count && !d->textures) ||
+        (d->mr_material_count && !d->mr_materials) || (d->sg_material_count && !d->sg_materials) ||
+        (d->phong_material_count && !d->phong_materials) || (d->point_light_count && !d->point_lights))
         return fail(ctx, PT_ERR_INVALID_ARGUMENT, "pt_scene_upload", "array pointer is NULL with a non-zero count");
 
     if (d->geometry_is_animated &&

@@ -104,6 +104,7 @@ struct Context
     int smCount = 0;
     uint32_t traceBlocksPerSM = 0; // 0 = occupancy query; PT_TRACE_BLOCKS overrides (tuning)
     cudaStream_t stream = nullptr;
+    cudaMemPool_t memPool = nullptr; // private stream-ordered pool: nothing of the host application's default pool is touched
     std::string lastError;
 
     // scene
@@ -125,6 +126,7 @@ struct Context
     uint32_t bvhBuilder = 1;  // 1 = PLOC (default), 0 = LBVH; PT_BVH / tuning key "bvh_builder"
     uint32_t plocRadius = 8;  // PLOC search window on either side; PT_PLOC_RADIUS / "ploc_radius"
     uint32_t bvhBuildPasses = 0;
+    uint32_t bvhMaxDepth = 0; // levels of the wide BVH (the traversal stack holds at most 3 entries per level)
 
     // target
     uint32_t width = 0, height = 0;
@@ -166,6 +168,37 @@ struct Context
 };
 
 pt_status fail(Context *ctx, pt_status code, const char *what, const char *detail);
+
+// Every entry point of the C ABI works on the context's device and leaves the caller's current device as it was.
+struct DeviceGuard
+{
+    int previous = -1;
+    explicit DeviceGuard(int device)
+    {
+        if (cudaGetDevice(&previous) != cudaSuccess)
+            previous = -1;
+        if (previous != device)
+            cudaSetDevice(device);
+        else
+            previous = -1;
+    }
+    ~DeviceGuard()
+    {
+        if (previous >= 0)
+            cudaSetDevice(previous);
+    }
+    DeviceGuard(const DeviceGuard &) = delete;
+    DeviceGuard &operator=(const DeviceGuard &) = delete;
+};
+
+// stream-ordered allocation from the context's private pool
+inline cudaError_t poolAlloc(Context *ctx, void **ptr, size_t bytes, cudaStream_t stream)
+{
+    return cudaMallocFromPoolAsync(ptr, bytes, ctx->memPool, stream);
+}
+
+// traversal-stack overflows since the last call (wavefront.cu); non-zero fails the call that caused them
+pt_status checkStackOverflow(Context *ctx, const char *what);
 
 // bvh_build.cu
 pt_status uploadScene(Context *ctx, const pt_scene_desc *desc);

@@ -199,8 +199,8 @@ pt_status postProcess(Context *ctx, const pt_postprocess_params *p, uint32_t tot
     void *dOut = nullptr;
     // stream-ordered pool (see bvh_build.cu): repeated calls at one extent make no driver allocation
     cudaStream_t st = ctx->stream;
-    PT_CUDA_CHECK(ctx, cudaMallocAsync((void **)&mem, (n + texels) * sizeof(uint2), st));
-    cudaError_t err = cudaMallocAsync(&dOut, need, st);
+    PT_CUDA_CHECK(ctx, poolAlloc(ctx, (void **)&mem, (n + texels) * sizeof(uint2), st));
+    cudaError_t err = poolAlloc(ctx, &dOut, need, st);
     if (err != cudaSuccess)
     {
         cudaFreeAsync(mem, st);

@@ -78,9 +78,7 @@ pt_status pt_context_create(int32_t cuda_device, pt_context **out_ctx)
                       prop.major, prop.minor);
         return fail(nullptr, PT_ERR_NO_DEVICE, "pt_context_create", buf);
     }
-    err = cudaSetDevice(cuda_device);
-    if (err != cudaSuccess)
-        return fail(nullptr, PT_ERR_CUDA, "cudaSetDevice", cudaGetErrorString(err));
+    DeviceGuard guard(cuda_device);
 
     pt_context *ctx = new pt_context();
     ctx->device = cuda_device;
@@ -113,11 +111,16 @@ pt_status pt_context_create(int32_t cuda_device, pt_context **out_ctx)
     } while (0)
     PT_CREATE_CHECK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
     {
-        // keep freed blocks of the stream-ordered allocator cached (bvh_build.cu: buildAccel)
-        cudaMemPool_t pool;
-        PT_CREATE_CHECK(cudaDeviceGetDefaultMemPool(&pool, cuda_device));
+        // a PRIVATE stream-ordered pool that keeps its freed blocks cached (bvh_build.cu: buildAccel makes no driver
+        // allocation on a rebuild); the device's default pool — possibly shared with the host application — is untouched
+        cudaMemPoolProps props = {};
+        props.allocType = cudaMemAllocationTypePinned;
+        props.handleTypes = cudaMemHandleTypeNone;
+        props.location.type = cudaMemLocationTypeDevice;
+        props.location.id = cuda_device;
+        PT_CREATE_CHECK(cudaMemPoolCreate(&ctx->memPool, &props));
         uint64_t threshold = UINT64_MAX;
-        PT_CREATE_CHECK(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &threshold));
+        PT_CREATE_CHECK(cudaMemPoolSetAttribute(ctx->memPool, cudaMemPoolAttrReleaseThreshold, &threshold));
     }
     PT_CREATE_CHECK(cudaEventCreate(&ctx->evStart));
     PT_CREATE_CHECK(cudaEventCreate(&ctx->evStop));
@@ -149,7 +152,7 @@ void pt_context_destroy(pt_context *ctx)
 {
     if (!ctx)
         return;
-    cudaSetDevice(ctx->device);
+    DeviceGuard guard(ctx->device);
     if (ctx->stream)
         cudaStreamSynchronize(ctx->stream);
     freeScene(ctx);
@@ -173,6 +176,8 @@ void pt_context_destroy(pt_context *ctx)
         cudaEventDestroy(ctx->evStop);
     if (ctx->stream)
         cudaStreamDestroy(ctx->stream);
+    if (ctx->memPool)
+        cudaMemPoolDestroy(ctx->memPool);
     delete ctx;
 }
 
@@ -182,7 +187,7 @@ pt_status pt_scene_upload(pt_context *ctx, const pt_scene_desc *scene)
 {
     if (!ctx)
         return PT_ERR_INVALID_ARGUMENT;
-    cudaSetDevice(ctx->device);
+    DeviceGuard guard(ctx->device);
     return uploadScene(ctx, scene);
 }
 
@@ -190,7 +195,7 @@ pt_status pt_texture_upload(pt_context *ctx, uint32_t slot, const pt_texture_des
 {
     if (!ctx)
         return PT_ERR_INVALID_ARGUMENT;
-    cudaSetDevice(ctx->device);
+    DeviceGuard guard(ctx->device);
     return uploadTextureSlot(ctx, slot, texture);
 }
 
@@ -200,7 +205,7 @@ pt_status pt_render_begin(pt_context *ctx, uint32_t width, uint32_t height)
         return PT_ERR_INVALID_ARGUMENT;
     if (width == 0 || height == 0 || (uint64_t)width * height > 0x7fffffffull)
         return fail(ctx, PT_ERR_INVALID_ARGUMENT, "pt_render_begin", "bad extent");
-    cudaSetDevice(ctx->device);
+    DeviceGuard guard(ctx->device);
     const size_t n = (size_t)width * height;
     const bool reuse = ctx->accum && ctx->width == width && ctx->height == height;
     if (!reuse)
@@ -256,7 +261,7 @@ pt_status pt_render_samples(pt_context *ctx, const pt_render_params *params, uin
 {
     if (!ctx)
         return PT_ERR_INVALID_ARGUMENT;
-    cudaSetDevice(ctx->device);
+    DeviceGuard guard(ctx->device);
     return renderFrames(ctx, params, first_sample, sample_count, 1, tiles, tile_count);
 }
 
@@ -265,7 +270,7 @@ pt_status pt_render_frames(pt_context *ctx, const pt_render_params *params, uint
 {
     if (!ctx)
         return PT_ERR_INVALID_ARGUMENT;
-    cudaSetDevice(ctx->device);
+    DeviceGuard guard(ctx->device);
     return renderFrames(ctx, params, first_sample, frame_count, samples_per_frame, tiles, tile_count);
 }
 
@@ -293,7 +298,7 @@ pt_status pt_readback(pt_context *ctx, float *out_rgba, size_t out_bytes)
     const size_t need = (size_t)ctx->width * ctx->height * sizeof(float4);
     if (!out_rgba || out_bytes < need)
         return fail(ctx, PT_ERR_INVALID_ARGUMENT, "pt_readback", "output buffer too small");
-    cudaSetDevice(ctx->device);
+    DeviceGuard guard(ctx->device);
     PT_CUDA_CHECK(ctx, cudaMemcpyAsync(out_rgba, ctx->accum, need, cudaMemcpyDeviceToHost, ctx->stream));
     PT_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
     return PT_OK;
@@ -303,7 +308,7 @@ pt_status pt_scene_update(pt_context *ctx, const pt_scene_update_desc *desc)
 {
     if (!ctx)
         return PT_ERR_INVALID_ARGUMENT;
-    cudaSetDevice(ctx->device);
+    DeviceGuard guard(ctx->device);
     return updateScene(ctx, desc);
 }
 
@@ -312,7 +317,7 @@ pt_status pt_postprocess(pt_context *ctx, const pt_postprocess_params *params, u
 {
     if (!ctx)
         return PT_ERR_INVALID_ARGUMENT;
-    cudaSetDevice(ctx->device);
+    DeviceGuard guard(ctx->device);
     return postProcess(ctx, params, total_samples, output_format, out_pixels, out_bytes);
 }
 
@@ -320,7 +325,7 @@ pt_status pt_synchronize(pt_context *ctx)
 {
     if (!ctx)
         return PT_ERR_INVALID_ARGUMENT;
-    cudaSetDevice(ctx->device);
+    DeviceGuard guard(ctx->device);
     PT_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
     return PT_OK;
 }
@@ -330,7 +335,7 @@ pt_status pt_first_hit_aov(pt_context *ctx, const pt_render_params *params, uint
 {
     if (!ctx)
         return PT_ERR_INVALID_ARGUMENT;
-    cudaSetDevice(ctx->device);
+    DeviceGuard guard(ctx->device);
     return firstHitAov(ctx, params, width, height, out_hits);
 }
 
@@ -338,7 +343,7 @@ pt_status pt_trace_closest(pt_context *ctx, const pt_ray *rays, uint64_t ray_cou
 {
     if (!ctx)
         return PT_ERR_INVALID_ARGUMENT;
-    cudaSetDevice(ctx->device);
+    DeviceGuard guard(ctx->device);
     return traceClosest(ctx, rays, ray_count, out_hits);
 }
 
@@ -346,7 +351,7 @@ pt_status pt_trace_occlusion(pt_context *ctx, const pt_ray *rays, uint64_t ray_c
 {
     if (!ctx)
         return PT_ERR_INVALID_ARGUMENT;
-    cudaSetDevice(ctx->device);
+    DeviceGuard guard(ctx->device);
     return traceOcclusion(ctx, rays, ray_count, out_occluded);
 }
 
@@ -354,7 +359,7 @@ pt_status pt_get_stats(pt_context *ctx, pt_stats *out)
 {
     if (!ctx || !out)
         return PT_ERR_INVALID_ARGUMENT;
-    cudaSetDevice(ctx->device);
+    DeviceGuard guard(ctx->device);
     DeviceCounters c;
     PT_CUDA_CHECK(ctx, cudaMemcpyAsync(&c, ctx->dCounters, sizeof(c), cudaMemcpyDeviceToHost, ctx->stream));
     PT_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
@@ -379,6 +384,7 @@ pt_status pt_get_stats(pt_context *ctx, pt_stats *out)
     s.triangle_count = ctx->scene.triCount;
     s.bvh_node_count = ctx->nodeCount;
     s.bvh_bytes = ctx->bvhBytes;
+    s.bvh_max_depth = ctx->bvhMaxDepth;
     s.bvh_build_ms = ctx->bvhBuildMs;
     s.scene_upload_ms = ctx->sceneUploadMs;
     *out = s;
@@ -415,7 +421,7 @@ pt_status pt_set_tuning(pt_context *ctx, const char *key, uint64_t value)
         {
             // re-create the path state with the new pool size
             const uint32_t w = ctx->width, h = ctx->height;
-            cudaSetDevice(ctx->device);
+            DeviceGuard guard(ctx->device);
             PT_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
             freeTarget(ctx);
             return pt_render_begin(ctx, w, h);
@@ -439,7 +445,7 @@ pt_status pt_debug_render(pt_context *ctx, const pt_render_params *params, const
 {
     if (!ctx)
         return PT_ERR_INVALID_ARGUMENT;
-    cudaSetDevice(ctx->device);
+    DeviceGuard guard(ctx->device);
     return debugRender(ctx, params, debug, width, height, out_rgba);
 }
 
@@ -447,7 +453,7 @@ pt_status pt_test_texture(pt_context *ctx, uint32_t slot, const float *in6, floa
 {
     if (!ctx)
         return PT_ERR_INVALID_ARGUMENT;
-    cudaSetDevice(ctx->device);
+    DeviceGuard guard(ctx->device);
     return testTexture(ctx, slot, in6, out4, count, use_grad);
 }
 
@@ -458,7 +464,7 @@ pt_status pt_test_shading(pt_context *ctx, uint32_t mode, const float *input, fl
 {
     if (!ctx)
         return PT_ERR_INVALID_ARGUMENT;
-    cudaSetDevice(ctx->device);
+    DeviceGuard guard(ctx->device);
     return testShading(ctx, mode, input, output, count);
 }
 

@@ -61,6 +61,11 @@ namespace pt
 #define PT_BOX_FMA 0 // slab distances as one FMA per plane (precomputed org / dir, error folded into the planes)
 #endif
 
+// Entries a traversal could not push because its stack (PT_STACK_SIZE entries) was full.  A dropped entry is a lost
+// sub-tree, i.e. possibly a missed hit: the host reads this counter after every call and FAILS the call when it is
+// non-zero (checkStackOverflow).  The build also reports the depth of the wide BVH (pt_stats::bvh_max_depth).
+static __device__ unsigned int g_stackOverflows;
+
 PT_DEV void prefetchL1(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 
 struct Hit
@@ -369,6 +374,8 @@ template <bool CLOSEST, bool ALPHA, bool STATS, int SMEM = 0> struct Traverser
             stack[sp - SMEM] = e;
             sp++;
         }
+        else
+            atomicAdd(&g_stackOverflows, 1u);
     }
 
     // cur is an internal node: test its children, descend into the nearest, push the others

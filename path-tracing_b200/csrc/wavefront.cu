@@ -953,18 +953,37 @@ pt_status renderFrames(Context *ctx, const pt_render_params *params, uint32_t fi
                           (want.empty() || std::memcmp(want.data(), ctx->pixelTiles.data(), want.size() * sizeof(pt_tile)) == 0);
         if (!same)
         {
-            std::vector<uint32_t> list;
+            // the tiles must be disjoint: a pixel listed twice would be sampled twice and k_resolve would race on it.
+            // The total area is checked BEFORE any pixel is listed (many large tiles cannot exhaust host memory),
+            // overlap with one bit per pixel while listing.
+            uint64_t area = 0;
             for (const pt_tile &in : want)
             {
                 const pt_tile t = { std::min(in.x0, W), std::min(in.y0, H), std::min(in.x1, W), std::min(in.y1, H) };
+                if (t.x1 > t.x0 && t.y1 > t.y0)
+                    area += (uint64_t)(t.x1 - t.x0) * (t.y1 - t.y0);
+                if (area > (uint64_t)W * H)
+                    return fail(ctx, PT_ERR_INVALID_ARGUMENT, "pt_render_samples", "tiles overlap (their area exceeds the frame)");
+            }
+            std::vector<uint32_t> list;
+            list.reserve((size_t)area);
+            std::vector<bool> covered((size_t)W * H, false);
+            for (const pt_tile &in : want)
+            {
+                const pt_tile t = { std::min(in.x0, W), std::min(in.y0, H), std::min(in.x1, W), std::min(in.y1, H) };
+                for (uint32_t y = t.y0; y < t.y1; y++)
+                    for (uint32_t x = t.x0; x < t.x1; x++)
+                    {
+                        if (covered[(size_t)y * W + x])
+                            return fail(ctx, PT_ERR_INVALID_ARGUMENT, "pt_render_samples", "tiles overlap");
+                        covered[(size_t)y * W + x] = true;
+                    }
                 for (uint32_t by = t.y0; by < t.y1; by += 4)
                     for (uint32_t bx = t.x0; bx < t.x1; bx += 8)
                         for (uint32_t y = by; y < std::min(by + 4, t.y1); y++)
                             for (uint32_t x = bx; x < std::min(bx + 8, t.x1); x++)
                                 list.push_back(y * W + x);
             }
-            if (list.size() > (size_t)W * H)
-                return fail(ctx, PT_ERR_INVALID_ARGUMENT, "pt_render_samples", "tiles overlap or exceed the frame");
             if (!list.empty())
                 PT_CUDA_CHECK(ctx, cudaMemcpyAsync(ctx->pixelList, list.data(), list.size() * 4, cudaMemcpyHostToDevice,
                                                    ctx->stream));
@@ -1237,7 +1256,22 @@ pt_status renderFrames(Context *ctx, const pt_render_params *params, uint32_t fi
     PT_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
     PT_CUDA_CHECK(ctx, cudaGetLastError());
     PT_CUDA_CHECK(ctx, cudaEventElapsedTime(&ctx->stats.last_render_ms, ctx->evStart, ctx->evStop));
-    return PT_OK;
+    return checkStackOverflow(ctx, "pt_render_samples");
+}
+
+pt_status checkStackOverflow(Context *ctx, const char *what)
+{
+    unsigned int n = 0;
+    PT_CUDA_CHECK(ctx, cudaMemcpyFromSymbol(&n, g_stackOverflows, sizeof(n)));
+    if (n == 0)
+        return PT_OK;
+    const unsigned int zero = 0;
+    cudaMemcpyToSymbol(g_stackOverflows, &zero, sizeof(zero));
+    ctx->stats.stack_overflows = n;
+    char buf[192];
+    std::snprintf(buf, sizeof(buf), "the traversal stack (%d entries) overflowed %u times on a BVH of depth %u: sub-trees were "
+                                    "skipped, the result is not valid", PT_STACK_SIZE, n, ctx->bvhMaxDepth);
+    return fail(ctx, PT_ERR_UNSUPPORTED, what, buf);
 }
 
 pt_status firstHitAov(Context *ctx, const pt_render_params *params, uint32_t width, uint32_t height, pt_hit *out)
@@ -1259,7 +1293,7 @@ pt_status firstHitAov(Context *ctx, const pt_render_params *params, uint32_t wid
         err = cudaStreamSynchronize(ctx->stream);
     cudaFree(dOut);
     PT_CUDA_CHECK(ctx, err);
-    return PT_OK;
+    return checkStackOverflow(ctx, "pt_first_hit_aov");
 }
 
 pt_status debugRender(Context *ctx, const pt_render_params *params, const pt_debug_params *dbg, uint32_t width, uint32_t height,
@@ -1273,7 +1307,7 @@ pt_status debugRender(Context *ctx, const pt_render_params *params, const pt_deb
         return fail(ctx, PT_ERR_NO_SCENE, "pt_debug_render", "no scene uploaded");
     const size_t n = (size_t)width * height;
     float4 *dOut = nullptr;
-    PT_CUDA_CHECK(ctx, cudaMallocAsync((void **)&dOut, n * sizeof(float4), ctx->stream));
+    PT_CUDA_CHECK(ctx, poolAlloc(ctx, (void **)&dOut, n * sizeof(float4), ctx->stream));
     const uint32_t grid = (uint32_t)((n + 127) / 128);
     const bool alphaScene = ctx->scene.hasAlpha != 0;
     const bool alphaPrimary = alphaScene && !(dbg->raygen_flags & PT_DEBUG_RAYGEN_FORCE_OPAQUE);
@@ -1291,7 +1325,7 @@ pt_status debugRender(Context *ctx, const pt_render_params *params, const pt_deb
         err = cudaStreamSynchronize(ctx->stream);
     cudaFreeAsync(dOut, ctx->stream);
     PT_CUDA_CHECK(ctx, err);
-    return PT_OK;
+    return checkStackOverflow(ctx, "pt_debug_render");
 }
 
 pt_status traceClosest(Context *ctx, const pt_ray *rays, uint64_t n, pt_hit *out)
@@ -1322,7 +1356,7 @@ pt_status traceClosest(Context *ctx, const pt_ray *rays, uint64_t n, pt_hit *out
     cudaFree(dRays);
     cudaFree(dOut);
     PT_CUDA_CHECK(ctx, err);
-    return PT_OK;
+    return checkStackOverflow(ctx, "pt_trace_closest");
 }
 
 pt_status traceOcclusion(Context *ctx, const pt_ray *rays, uint64_t n, uint8_t *out)
@@ -1353,7 +1387,7 @@ pt_status traceOcclusion(Context *ctx, const pt_ray *rays, uint64_t n, uint8_t *
     cudaFree(dRays);
     cudaFree(dOut);
     PT_CUDA_CHECK(ctx, err);
-    return PT_OK;
+    return checkStackOverflow(ctx, "pt_trace_occlusion");
 }
 
 } // namespace pt

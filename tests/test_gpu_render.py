@@ -325,3 +325,30 @@ def test_samples_per_frame_continues_and_partitions(default_renderer, default_sc
     assert np.array_equal(part[mask], whole[mask]) and (part[~mask] == 0).all()
     with pytest.raises(conftest.core.PtError):
         r.render_frames(1, 0, params=p)
+
+
+def test_robustness_of_the_boundary(default_scene):
+    """Malformed input fails loudly instead of faulting the device: an index beyond its geometry's vertices,
+    overlapping tiles, NULL arrays with non-zero counts; the BVH depth is reported and no traversal overflowed."""
+    import copy
+
+    core = conftest.core
+    with core.Renderer(0) as r:
+        bad = copy.copy(default_scene)
+        bad.indices = default_scene.indices.copy()
+        bad.indices[5] = 1_000_000
+        with pytest.raises(core.PtError) as e:
+            r.update_scene_data(bad)
+        assert e.value.status == -1 and "vertex_length" in str(e.value)
+        r.update_scene_data(default_scene)  # the context is still usable
+        p = default_scene.default_params()
+        r.on_resize(64, 64)
+        with pytest.raises(core.PtError) as e:
+            r.render(1, params=p, tiles=np.array([(0, 0, 40, 40), (30, 30, 64, 64)], sc.TILE))
+        assert "overlap" in str(e.value)
+        with pytest.raises(core.PtError):
+            r.render(1, params=p, tiles=np.array([(0, 0, 64, 64)] * 3, sc.TILE))
+        r.render(2, params=p, tiles=np.array([(0, 0, 32, 64), (32, 0, 64, 64)], sc.TILE))
+        st = r.stats()
+        assert 1 <= st["bvh_max_depth"] <= 8 and st["stack_overflows"] == 0
+        assert np.isfinite(r.read_accumulation()).all()

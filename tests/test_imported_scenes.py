@@ -57,4 +57,4 @@ def test_gpu_matches_oracle(imported, oracle_mod):
     ref, _ = ora.render(p, w, h, 0, 4)
     assert metrics.close_fraction(img, ref, 1e-4) > 0.99, name
     assert metrics.rel_mse(img / 4, ref / 4) <= 1e-3
-    assert metrics.flip_lite(img / 4, ref / 4) <= 5e-3
+    assert metrics.flip(img / 4, ref / 4) <= 5e-3
