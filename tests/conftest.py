@@ -65,3 +65,20 @@ def renderer():
 def default_renderer(renderer, default_scene):
     renderer.update_scene_data(default_scene)
     return renderer
+
+
+def diverged_path_fraction(renderer, oracle_scene, params, width, height, first_sample, count, tol=1e-4):
+    """Fraction of (pixel, sample) pairs whose single-sample radiance differs between the CUDA core and the oracle by
+    more than tol * max(1, |radiance|): paths that took a different route (another lobe, another side of an alpha
+    or visibility test) because an intermediate value differed in its last bits."""
+    bad = total = 0
+    for s in range(first_sample, first_sample + count):
+        renderer.on_resize(width, height)
+        renderer.render(1, params=params, first_sample=s)
+        a = renderer.read_accumulation()[..., :3]
+        b, _ = oracle_scene.render(params, width, height, s, 1)
+        b = b[..., :3]
+        d = np.abs(a - b).max(-1)
+        bad += int((d > tol * np.maximum(1.0, np.abs(b).max(-1))).sum())
+        total += d.size
+    return bad / total

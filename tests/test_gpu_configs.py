@@ -49,6 +49,10 @@ def test_image_parity(config):
     assert abs(st["rays_closest"] - cnt["rays_closest"]) <= 3e-3 * cnt["rays_closest"]
     assert abs(st["hits"] - cnt["hits"]) <= 3e-3 * cnt["hits"]
     assert st["rays_shadow"] <= cnt["rays_shadow"]  # exactly-zero contributions are not traced
+    # how many PATHS took another route (a lobe choice or an alpha / visibility test decided by the last bit): the
+    # per-sample radiance of every (pixel, sample) — a regression cannot hide behind the image-level tolerance
+    diverged = conftest.diverged_path_fraction(r, o, p, W, H, 0, 8)
+    assert diverged <= (0.02 if name == "dragon" else 0.008), (name, diverged)
     if name == "atrium":
         r.set_traversal_stats(True)
         r.on_resize(W, H)
