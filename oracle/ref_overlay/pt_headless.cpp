@@ -4,10 +4,16 @@
  * the C ABI, renders `spp` samples and writes a PNG, i.e. the reference's "Render" button flow
  * (Path-Tracing/UserInterface.cpp:1074-1092) without a window.
  *
- *   pt_headless <group> <scene> <width> <height> <spp> <bounces> <out.png>
- *   pt_headless --file <model.gltf|.glb|.obj> <width> <height> <spp> <bounces> <out.png>   (assimp overlay)
+ *   pt_headless <group> <scene> <width> <height> <spp> <bounces> <out>
+ *   pt_headless --file <model.gltf|.glb|.obj> <width> <height> <spp> <bounces> <out>   (assimp overlay)
+ * <out>: .png / .jpg / .tga / .hdr like OutputSaver's formats (Renderer/OutputSaver.h:16-19), or .f32 = the raw float4
+ * accumulation (sum) image, width*height*16 bytes — what tests/test_gpu_shim.py compares bit for bit.
+ * PT_SAMPLES_PER_FRAME=n renders frames of n samples (RenderSettings::SamplesPerFrame); <spp> must be a multiple.
  */
 #include <cstdio>
+#include <cstdlib>
+#include <string>
+#include <vector>
 
 #include "Core/Core.h"
 
@@ -53,8 +59,29 @@ int main(int argc, char **argv)
         const uint32_t spp = std::atoi(argv[5]);
         const bool updated = scene->Update(0.0f);
         renderer.UpdateSceneData(scene, updated);
-        renderer.Render(spp);
-        renderer.SavePng(argv[7]);
+        uint32_t perFrame = 1;
+        if (const char *e = std::getenv("PT_SAMPLES_PER_FRAME"))
+            perFrame = std::max(1, std::atoi(e));
+        renderer.SetSamplesPerFrame(perFrame);
+        renderer.Render(spp / perFrame);
+        const std::string out = argv[7];
+        const std::string ext = out.size() >= 4 ? out.substr(out.size() - 4) : "";
+        if (ext == ".jpg")
+            renderer.SaveJpg(out);
+        else if (ext == ".tga")
+            renderer.SaveTga(out);
+        else if (ext == ".hdr")
+            renderer.SaveHdr(out);
+        else if (ext == ".f32")
+        {
+            const std::vector<float> acc = renderer.ReadAccumulation();
+            FILE *f = std::fopen(out.c_str(), "wb");
+            if (!f || std::fwrite(acc.data(), sizeof(float), acc.size(), f) != acc.size())
+                throw error("Could not write " + out);
+            std::fclose(f);
+        }
+        else
+            renderer.SavePng(out);
 
         const pt_stats stats = renderer.GetStats();
         std::printf(

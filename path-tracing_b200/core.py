@@ -361,6 +361,14 @@ class Renderer:
         """OutputFormat::Tga: the same 8-bit sRGB image as the PNG."""
         write_tga(path, self.postprocess(hdr=False, **postprocess_args))
 
+    def save_jpg(self, path: str, **postprocess_args):
+        """OutputFormat::Jpg (OutputSaver.cpp:237-238: stbi_write_jpg, quality argument 0 = stb's default of 90): the same
+        8-bit sRGB image, baseline JPEG of its RGB channels.  Written with Pillow here (the C++ shim uses the reference's
+        own stb writer): the files decode to the same picture, the byte streams are not compared."""
+        from PIL import Image
+
+        Image.fromarray(self.postprocess(hdr=False, **postprocess_args)[..., :3], "RGB").save(path, "JPEG", quality=90)
+
     def readback_into(self, host_ptr: int, nbytes: int):
         """pt_readback into caller-owned (e.g. pinned) host memory."""
         self._check(self._L.pt_readback(self._h, host_ptr, nbytes))

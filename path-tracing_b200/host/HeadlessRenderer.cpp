@@ -140,11 +140,19 @@ std::vector<float> HeadlessRenderer::RenderDebug()
     return pixels;
 }
 
-void HeadlessRenderer::Render(uint32_t samples)
+void HeadlessRenderer::SetSamplesPerFrame(uint32_t samplesPerFrame)
 {
+    if (samplesPerFrame == 0)
+        throw error("HeadlessRenderer: SamplesPerFrame must be at least 1");
+    m_SamplesPerFrame = samplesPerFrame;
+}
+
+void HeadlessRenderer::Render(uint32_t frames)
+{
+    /* Renderer.cpp:1688-1700: TotalSamples = samples accumulated so far, SampleCount = SamplesPerFrame */
     const pt_render_params params = MakeRenderParams();
-    Check(pt_render_samples(m_Context, &params, m_TotalSamples, samples, nullptr, 0), "pt_render_samples");
-    m_TotalSamples += samples;
+    Check(pt_render_frames(m_Context, &params, m_TotalSamples, frames, m_SamplesPerFrame, nullptr, 0), "pt_render_frames");
+    m_TotalSamples += frames * m_SamplesPerFrame;
 }
 
 std::vector<float> HeadlessRenderer::ReadAccumulation()
@@ -156,14 +164,35 @@ std::vector<float> HeadlessRenderer::ReadAccumulation()
 
 /* Renderer::RecordPostProcessCommands + RecordSaveOutputCommands + OutputSaver::WriteImage
  * (Renderer.cpp:928-1060, 1205-1250; OutputSaver.cpp:227-253): the whole chain runs in the core. */
-void HeadlessRenderer::SavePng(const std::string &path)
+std::vector<uint8_t> HeadlessRenderer::PostProcessSrgb8()
 {
     const pt_postprocess_params params = { m_PostProcess.Exposure, m_PostProcess.BloomThreshold,
                                            m_PostProcess.BloomIntensity, PT_TONE_MAPPING_SDR };
     std::vector<uint8_t> out(static_cast<size_t>(m_Width) * m_Height * 4);
     Check(pt_postprocess(m_Context, &params, std::max(1u, m_TotalSamples), PT_OUTPUT_RGBA8_SRGB, out.data(), out.size()),
           "pt_postprocess");
+    return out;
+}
+
+void HeadlessRenderer::SavePng(const std::string &path)
+{
+    const std::vector<uint8_t> out = PostProcessSrgb8();
     if (stbi_write_png(path.c_str(), m_Width, m_Height, 4, out.data(), 0) == 0)
+        throw error(std::format("Could not write {}", path));
+}
+
+/* OutputSaver.cpp:237-242: quality argument 0 (stb's default), four components */
+void HeadlessRenderer::SaveJpg(const std::string &path)
+{
+    const std::vector<uint8_t> out = PostProcessSrgb8();
+    if (stbi_write_jpg(path.c_str(), m_Width, m_Height, 4, out.data(), 0) == 0)
+        throw error(std::format("Could not write {}", path));
+}
+
+void HeadlessRenderer::SaveTga(const std::string &path)
+{
+    const std::vector<uint8_t> out = PostProcessSrgb8();
+    if (stbi_write_tga(path.c_str(), m_Width, m_Height, 4, out.data()) == 0)
         throw error(std::format("Could not write {}", path));
 }
 

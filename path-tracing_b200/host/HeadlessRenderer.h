@@ -91,8 +91,12 @@ public:
     void SetSettings(const PathTracingSettings &settings);
     void SetSettings(const PostProcessSettings &settings);
 
-    /* Renderer::Render (Renderer.cpp:1659-1808) with SamplesPerFrame = samples */
-    void Render(uint32_t samples = 1);
+    /* Renderer::RenderSettings::SamplesPerFrame / the adaptive s_SamplesPerFrame (Renderer.cpp:1631-1657): samples one
+     * frame = one vkCmdTraceRaysKHR renders per pixel, on one rng stream (raygen.rgen:36-118).  Default 1, the value of
+     * the reference's Profile / Debug builds (Core/Config.h:34-36). */
+    void SetSamplesPerFrame(uint32_t samplesPerFrame);
+    /* Renderer::Render (Renderer.cpp:1659-1808), `frames` times: every frame adds SamplesPerFrame samples */
+    void Render(uint32_t frames = 1);
     /* Renderer::SetDebugRaytracingPipeline + one frame of that pipeline: width*height RGBA floats */
     void SetDebugRaytracingPipeline(const DebugRaytracingPipelineConfig &config);
     [[nodiscard]] std::vector<float> RenderDebug();
@@ -102,6 +106,9 @@ public:
     [[nodiscard]] std::vector<float> ReadAccumulation();
     /* exposure + bloom + composition + SDR tone mapping + sRGB8 (pt_postprocess), written with stb like OutputSaver */
     void SavePng(const std::string &path);
+    /* OutputFormat::Jpg / Tga (OutputSaver.cpp:237-242): the same 8-bit sRGB pixels through stb's writers */
+    void SaveJpg(const std::string &path);
+    void SaveTga(const std::string &path);
     /* OutputFormat::Hdr: same chain without the tone curve, as Radiance .hdr */
     void SaveHdr(const std::string &path);
 
@@ -111,11 +118,13 @@ private:
     void Check(pt_status status, const char *what);
     pt_render_params MakeRenderParams();
     void ResetAccumulation();
+    std::vector<uint8_t> PostProcessSrgb8();
 
     pt_context *m_Context = nullptr;
     std::shared_ptr<Scene> m_Scene;
     uint32_t m_Width = 0, m_Height = 0;
     uint32_t m_TotalSamples = 0;
+    uint32_t m_SamplesPerFrame = 1;
     PathTracingSettings m_PathTracing;
     PostProcessSettings m_PostProcess;
     DebugRaytracingPipelineConfig m_Debug;
