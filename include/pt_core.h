@@ -591,7 +591,8 @@ enum {
     PT_DEBUG_MODE_PRIMITIVE = 6,
     PT_DEBUG_MODE_INSTANCE = 7
 };
-enum { PT_DEBUG_RAYGEN_FORCE_OPAQUE = 0x1, PT_DEBUG_RAYGEN_CULL_BACK_FACES = 0x2 /* PT_ERR_UNSUPPORTED */ };
+enum { PT_DEBUG_RAYGEN_FORCE_OPAQUE = 0x1, PT_DEBUG_RAYGEN_CULL_BACK_FACES = 0x2 /* gl_RayFlagsCullBackFacingTrianglesEXT:
+    facing in object space, front = clockwise from the ray origin (Vulkan's default, no instance flags) */ };
 enum {
     PT_DEBUG_HIT_DISABLE_COLOR_TEXTURE = 0x01,
     PT_DEBUG_HIT_DISABLE_NORMAL_TEXTURE = 0x02,

@@ -1472,8 +1472,24 @@ struct AnyHitHook
     void *ctx = nullptr;
 };
 
+/* gl_RayFlagsCullBackFacingTrianglesEXT (Debug/debugRaygen.rgen:32-35).  Vulkan decides the facing in OBJECT space (the
+ * BLAS's space: after the mesh transform, before the instance transform), front = the vertices appear clockwise from
+ * the ray origin = dot((v1 - v0) x (v2 - v0), d) < 0; the instance flags are empty (AccelerationStructure.cpp:273), so
+ * nothing flips it.  With world-space data: an instance transform of negative determinant reverses the sign. */
+bool isBackFacing(const pto_scene &s, const FlatTri &tri, vec3 dir)
+{
+    const vec3 n = cross(tri.p1 - tri.p0, tri.p2 - tri.p0);
+    float facing = dot(n, dir);
+    const float *I = s.instances[tri.instance].transform;
+    const double det = (double)I[0] * ((double)I[5] * I[10] - (double)I[6] * I[9]) - (double)I[1] * ((double)I[4] * I[10] - (double)I[6] * I[8]) +
+                       (double)I[2] * ((double)I[4] * I[9] - (double)I[5] * I[8]);
+    if (det < 0.0)
+        facing = -facing;
+    return !(facing < 0.0f);
+}
+
 HitInfo traceClosest(const pto_scene &s, vec3 org, vec3 dir, float tmin, float tmax, Counters &c, bool forceOpaque = false,
-                     const AnyHitHook *hook = nullptr)
+                     const AnyHitHook *hook = nullptr, bool cullBackFaces = false)
 {
     HitInfo hit;
     c.rays_closest++;
@@ -1527,6 +1543,8 @@ HitInfo traceClosest(const pto_scene &s, vec3 org, vec3 dir, float tmin, float t
             if (!(t > tmin))
                 continue;
             if (!(t < best || (t == best && hit.tri != PT_NO_HIT && ti < hit.tri)))
+                continue;
+            if (cullBackFaces && isBackFacing(s, tri, dir))
                 continue;
             if (!tri.opaque && !forceOpaque) /* gl_RayFlagsOpaqueEXT skips the any-hit stage */
             {
@@ -2221,7 +2239,8 @@ vec4 debugPixel(const pto_scene &s, const pt_render_params &p, const pt_debug_pa
     const Ray ray = constructPrimaryRay(V2((float)x, (float)y), V2((float)width, (float)height), toMat4(p.view_inverse),
                                         toMat4(p.proj_inverse), V2(0.5f, 0.5f), rx, ry);
     const bool forceOpaque = (dbg.raygen_flags & PT_DEBUG_RAYGEN_FORCE_OPAQUE) != 0;
-    const HitInfo hit = traceClosest(s, ray.Origin, ray.Direction, ray.tmin, ray.tmax, c, forceOpaque);
+    const bool cull = (dbg.raygen_flags & PT_DEBUG_RAYGEN_CULL_BACK_FACES) != 0;
+    const HitInfo hit = traceClosest(s, ray.Origin, ray.Direction, ray.tmin, ray.tmax, c, forceOpaque, nullptr, cull);
     if (hit.tri == PT_NO_HIT)
     {
         /* debugMiss.rmiss:17-36 (no hdrToLdr here) */
@@ -2964,8 +2983,6 @@ int32_t pto_debug_render(const pto_scene *s, const pt_render_params *p, const pt
 {
     if (!s || !p || !dbg || !out_rgba || dbg->render_mode > PT_DEBUG_MODE_INSTANCE)
         return PT_ERR_INVALID_ARGUMENT;
-    if (dbg->raygen_flags & PT_DEBUG_RAYGEN_CULL_BACK_FACES)
-        return PT_ERR_UNSUPPORTED;
     Counters c;
     for (uint32_t y = 0; y < height; y++)
         for (uint32_t x = 0; x < width; x++)

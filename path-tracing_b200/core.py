@@ -174,6 +174,61 @@ def write_tga(path: str, rgba8: np.ndarray):
         f.write(struct.pack("<BBBHHBHHHHBB", 0, 0, 2, 0, 0, 0, 0, 0, w, h, 32, 0x28) + bgra.tobytes())
 
 
+def write_exr(path: str, rgba: np.ndarray):
+    """OpenEXR 2.0 scanline file, uncompressed, 32-bit float channels A, B, G, R — the headless float output the task names
+    beside PNG (the reference's own float format is .hdr; EXR keeps all 32 bits and the alpha).  One chunk per scanline:
+    y, byte count, then the channels in alphabetical order, each a row of little-endian floats."""
+    import struct
+
+    img = np.ascontiguousarray(rgba, np.float32)
+    h, w = img.shape[:2]
+
+    def attr(name: str, typ: str, data: bytes) -> bytes:
+        return name.encode() + b"\0" + typ.encode() + b"\0" + struct.pack("<i", len(data)) + data
+
+    chlist = b"".join(c.encode() + b"\0" + struct.pack("<iBBBBii", 2, 0, 0, 0, 0, 1, 1) for c in "ABGR") + b"\0"
+    box = struct.pack("<iiii", 0, 0, w - 1, h - 1)
+    header = (attr("channels", "chlist", chlist) + attr("compression", "compression", b"\0") + attr("dataWindow", "box2i", box) +
+              attr("displayWindow", "box2i", box) + attr("lineOrder", "lineOrder", b"\0") + attr("pixelAspectRatio", "float", struct.pack("<f", 1.0)) +
+              attr("screenWindowCenter", "v2f", struct.pack("<ff", 0.0, 0.0)) + attr("screenWindowWidth", "float", struct.pack("<f", 1.0)) + b"\0")
+    magic = struct.pack("<ii", 20000630, 2)
+    row_bytes = 4 * 4 * w
+    first = len(magic) + len(header) + 8 * h
+    offsets = b"".join(struct.pack("<Q", first + y * (8 + row_bytes)) for y in range(h))
+    planes = img[..., [3, 2, 1, 0]].transpose(0, 2, 1)  # (h, channel A B G R, w)
+    with open(path, "wb") as f:
+        f.write(magic + header + offsets)
+        for y in range(h):
+            f.write(struct.pack("<ii", y, row_bytes) + planes[y].tobytes())
+
+
+def read_exr(path: str) -> np.ndarray:
+    """Reads back what write_exr wrote (uncompressed float scanlines, channels A B G R): (h, w, 4) float32 RGBA."""
+    import struct
+
+    data = open(path, "rb").read()
+    assert struct.unpack_from("<ii", data, 0) == (20000630, 2)
+    pos, attrs = 8, {}
+    while data[pos] != 0:
+        end = data.index(b"\0", pos)
+        name = data[pos:end].decode()
+        tend = data.index(b"\0", end + 1)
+        size = struct.unpack_from("<i", data, tend + 1)[0]
+        attrs[name] = data[tend + 5 : tend + 5 + size]
+        pos = tend + 5 + size
+    pos += 1
+    x0, y0, x1, y1 = struct.unpack("<iiii", attrs["dataWindow"])
+    w, h = x1 - x0 + 1, y1 - y0 + 1
+    assert attrs["compression"] == b"\0"
+    out = np.zeros((h, w, 4), np.float32)
+    for k in range(h):
+        off = struct.unpack_from("<Q", data, pos + 8 * k)[0]
+        y, n = struct.unpack_from("<ii", data, off)
+        planes = np.frombuffer(data, np.float32, 4 * w, off + 8).reshape(4, w)
+        out[y - y0] = planes[[3, 2, 1, 0]].T
+    return out
+
+
 _lib = None
 
 
@@ -360,6 +415,10 @@ class Renderer:
     def save_tga(self, path: str, **postprocess_args):
         """OutputFormat::Tga: the same 8-bit sRGB image as the PNG."""
         write_tga(path, self.postprocess(hdr=False, **postprocess_args))
+
+    def save_exr(self, path: str, **postprocess_args):
+        """The float output (the chain without the tone curve, like .hdr) as an OpenEXR file with all 32 bits per channel."""
+        write_exr(path, self.postprocess(hdr=True, **postprocess_args))
 
     def save_jpg(self, path: str, **postprocess_args):
         """OutputFormat::Jpg (OutputSaver.cpp:237-238: stbi_write_jpg, quality argument 0 = stb's default of 90): the same

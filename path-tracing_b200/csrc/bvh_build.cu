@@ -1030,6 +1030,16 @@ pt_status flattenInstances(Context *ctx, const SceneTopology &t, std::vector<Mes
             m.geometry = mi;
             m.materialId = rec.material_id;
             m.flags = g.is_opaque ? PT_TRI_FLAG_OPAQUE : 0u;
+            {
+                // facing is decided in OBJECT space = the BLAS's space, after the mesh transform and before the
+                // instance transform (gl_RayFlagsCullBackFacingTrianglesEXT, Debug/debugRaygen.rgen:32-35)
+                const float *I = inst.transform;
+                const double det = (double)I[0] * ((double)I[5] * I[10] - (double)I[6] * I[9]) -
+                                   (double)I[1] * ((double)I[4] * I[10] - (double)I[6] * I[8]) +
+                                   (double)I[2] * ((double)I[4] * I[9] - (double)I[5] * I[8]);
+                if (det < 0.0)
+                    m.flags |= PT_TRI_FLAG_MIRRORED;
+            }
             hasAlpha |= !g.is_opaque;
             if (m.triCount == 0)
                 continue;

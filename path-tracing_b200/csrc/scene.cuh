@@ -60,6 +60,7 @@ static_assert(sizeof(BvhNode) == 128, "BvhNode must be one 128-byte line");
 PT_HD int encodeLeaf(uint32_t first, uint32_t count) { return ~(int)((first << 2) | (count - 1)); }
 
 #define PT_TRI_FLAG_OPAQUE 1u
+#define PT_TRI_FLAG_MIRRORED 2u // the instance transform has a negative determinant: object-space winding = world-space winding reversed
 
 struct __align__(16) TriShade
 {

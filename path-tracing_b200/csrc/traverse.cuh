@@ -291,8 +291,13 @@ PT_DEV void intersectNode(const BvhNode *__restrict__ node, const RaySetup &r, f
 // loop (traverse(), standalone queries) or warp-synchronously with dynamic ray fetch (wavefront).
 //   CLOSEST = true : nearest hit (+ decal record if ALPHA)
 //   CLOSEST = false: any hit in (tmin, tmax) with alpha >= 1 -> hit.tri != miss
-template <bool CLOSEST, bool ALPHA, bool STATS, int SMEM = 0> struct Traverser
+//   CULL = true    : gl_RayFlagsCullBackFacingTrianglesEXT (debug pipeline only): back-facing triangles are no
+//                    candidates at all.  Vulkan decides the facing in OBJECT space: front = the vertices appear
+//                    clockwise from the ray origin, i.e. dot((v1 - v0) x (v2 - v0), d) < 0 there; a mirroring
+//                    instance transform reverses the world-space winding (PT_TRI_FLAG_MIRRORED).
+template <bool CLOSEST, bool ALPHA, bool STATS, int SMEM = 0, bool CULL = false> struct Traverser
 {
+    vec3 cullDir; // world ray direction (CULL only)
     static constexpr bool kClosest = CLOSEST, kAlpha = ALPHA, kStats = STATS;
     unsigned long long *sstack; // this thread's column of the block's shared stack (SMEM > 0)
     RaySetup r;
@@ -499,6 +504,15 @@ template <bool CLOSEST, bool ALPHA, bool STATS, int SMEM = 0> struct Traverser
                 if (!(t > tmin))
                     continue;
                 const uint32_t flat = __float_as_uint(q0.w);
+                if (CULL)
+                {
+                    const vec3 n = cross(V3(q1) - V3(q0), V3(q2) - V3(q0));
+                    float facing = dot(n, cullDir);
+                    if (__float_as_uint(q1.w) & PT_TRI_FLAG_MIRRORED)
+                        facing = -facing;
+                    if (!(facing < 0.0f))
+                        continue; // back-facing (or edge-on)
+                }
                 if (CLOSEST)
                 {
                     if (!(t < best || (t == best && flat < bestFlat)))
@@ -555,13 +569,14 @@ template <bool CLOSEST, bool ALPHA, bool STATS, int SMEM = 0> struct Traverser
 };
 
 // plain per-thread traversal (standalone queries)
-template <bool CLOSEST, bool ALPHA, bool STATS>
+template <bool CLOSEST, bool ALPHA, bool STATS, bool CULL = false>
 PT_DEV void traverse(const DeviceScene &s, vec3 org, vec3 dir, float tmin, float tmax, Hit &hit, Decal &decal,
                      TraversalStats &st)
 {
     unsigned long long stack[PT_STACK_SIZE];
-    Traverser<CLOSEST, ALPHA, STATS> tr;
+    Traverser<CLOSEST, ALPHA, STATS, 0, CULL> tr;
     tr.stack = stack;
+    tr.cullDir = dir;
     tr.st = st;
     tr.begin(s, org, dir, tmin, tmax);
     while (!tr.finished())

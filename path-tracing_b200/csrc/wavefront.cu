@@ -725,7 +725,7 @@ __device__ __forceinline__ vec3 debugLightContribution(vec3 lightDir, vec3 light
     return (kD * color / PT_PI + specular) * radiance * NdotL;
 }
 
-template <bool ALPHA_PRIMARY, bool ALPHA_SHADOW>
+template <bool ALPHA_PRIMARY, bool ALPHA_SHADOW, bool CULL>
 __global__ void k_debug(DeviceScene s, CameraMatrices cam, uint32_t width, uint32_t height, uint32_t missFlags, pt_debug_params dbg,
                         float4 *out)
 {
@@ -738,7 +738,7 @@ __global__ void k_debug(DeviceScene s, CameraMatrices cam, uint32_t width, uint3
     Hit hit;
     Decal decal;
     TraversalStats st;
-    traverse<true, ALPHA_PRIMARY, false>(s, pr.origin, pr.direction, 0.00001f, 10000.0f, hit, decal, st);
+    traverse<true, ALPHA_PRIMARY, false, CULL>(s, pr.origin, pr.direction, 0.00001f, 10000.0f, hit, decal, st);
     if (hit.tri == 0xffffffffu)
     {
         // debugMiss.rmiss:17-36 (no hdrToLdr here)
@@ -1301,8 +1301,6 @@ pt_status debugRender(Context *ctx, const pt_render_params *params, const pt_deb
 {
     if (!params || !dbg || !out || width == 0 || height == 0 || dbg->render_mode > PT_DEBUG_MODE_INSTANCE)
         return fail(ctx, PT_ERR_INVALID_ARGUMENT, "pt_debug_render", "bad argument");
-    if (dbg->raygen_flags & PT_DEBUG_RAYGEN_CULL_BACK_FACES)
-        return fail(ctx, PT_ERR_UNSUPPORTED, "pt_debug_render", "back-face culling (gl_RayFlagsCullBackFacingTrianglesEXT) is not supported");
     if (!ctx->hasScene)
         return fail(ctx, PT_ERR_NO_SCENE, "pt_debug_render", "no scene uploaded");
     const size_t n = (size_t)width * height;
@@ -1312,12 +1310,22 @@ pt_status debugRender(Context *ctx, const pt_render_params *params, const pt_deb
     const bool alphaScene = ctx->scene.hasAlpha != 0;
     const bool alphaPrimary = alphaScene && !(dbg->raygen_flags & PT_DEBUG_RAYGEN_FORCE_OPAQUE);
     const CameraMatrices cam = toCamera(params);
+    const bool cull = (dbg->raygen_flags & PT_DEBUG_RAYGEN_CULL_BACK_FACES) != 0;
+#define PT_DEBUG_LAUNCH(AP, AS)                                                                                       \
+    do                                                                                                                \
+    {                                                                                                                 \
+        if (cull)                                                                                                     \
+            k_debug<AP, AS, true><<<grid, 128, 0, ctx->stream>>>(ctx->scene, cam, width, height, params->miss_flags, *dbg, dOut); \
+        else                                                                                                          \
+            k_debug<AP, AS, false><<<grid, 128, 0, ctx->stream>>>(ctx->scene, cam, width, height, params->miss_flags, *dbg, dOut); \
+    } while (0)
     if (alphaPrimary)
-        k_debug<true, true><<<grid, 128, 0, ctx->stream>>>(ctx->scene, cam, width, height, params->miss_flags, *dbg, dOut);
+        PT_DEBUG_LAUNCH(true, true);
     else if (alphaScene)
-        k_debug<false, true><<<grid, 128, 0, ctx->stream>>>(ctx->scene, cam, width, height, params->miss_flags, *dbg, dOut);
+        PT_DEBUG_LAUNCH(false, true);
     else
-        k_debug<false, false><<<grid, 128, 0, ctx->stream>>>(ctx->scene, cam, width, height, params->miss_flags, *dbg, dOut);
+        PT_DEBUG_LAUNCH(false, false);
+#undef PT_DEBUG_LAUNCH
     cudaError_t err = cudaGetLastError();
     if (err == cudaSuccess)
         err = cudaMemcpyAsync(out, dOut, n * sizeof(float4), cudaMemcpyDeviceToHost, ctx->stream);

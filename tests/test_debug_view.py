@@ -88,8 +88,8 @@ def test_gpu_matches_oracle(feature_oracle, mode):
     p = s.default_params()
     with core.Renderer(0) as r:
         r.update_scene_data(s)
-        for raygen, hitflags in ((0, 0), (0x1, 0), (0, FLAG["no_color"] | FLAG["no_normal"]), (0, FLAG["no_mips"] | FLAG["no_shadows"]),
-                                 (0, FLAG["dx"])):
+        for raygen, hitflags in ((0, 0), (0x1, 0), (0x2, 0), (0x3, 0), (0, FLAG["no_color"] | FLAG["no_normal"]),
+                                 (0, FLAG["no_mips"] | FLAG["no_shadows"]), (0, FLAG["dx"])):
             got = r.debug_render(p, W, H, mode, raygen, hitflags)
             want = o.debug_render(p, W, H, mode, raygen, hitflags)
             if mode in ("geometry", "primitive", "instance"):
@@ -106,5 +106,39 @@ def test_gpu_default_scene_and_sky(default_renderer, default_oracle, default_sce
         got = default_renderer.debug_render(p, 160, 160, mode)
         want = default_oracle.debug_render(p, 160, 160, mode)
         assert np.isclose(got, want, rtol=2e-4, atol=2e-5).all(-1).mean() > 0.995, mode
-    with pytest.raises(core.PtError):
-        default_renderer.debug_render(p, 16, 16, "color", raygen_flags=0x2)  # back-face culling is not supported
+    # back-face culling (gl_RayFlagsCullBackFacingTrianglesEXT): ids bit for bit with the oracle
+    got = default_renderer.debug_render(p, 160, 160, "primitive", raygen_flags=0x2)
+    assert np.array_equal(got, default_oracle.debug_render(p, 160, 160, "primitive", raygen_flags=0x2))
+
+
+def test_oracle_back_face_culling(oracle_mod):
+    """gl_RayFlagsCullBackFacingTrianglesEXT against a closed form: a single quad seen from its front, from its back,
+    and through a MIRRORING instance transform (negative determinant), which reverses the world-space winding but not
+    the object-space facing Vulkan culls by.  Front = the vertices appear clockwise from the ray origin."""
+    def scene_with(instance_matrix, eye):
+        b = scenes.SceneBuilder()
+        m = b.add_material_mr(color=(0.8, 0.8, 0.8, 1))
+        g = b.add_geometry(*scenes.quad(2.0, 2.0))  # in the xz-plane; triangles (0, 1, 2), (2, 3, 0)
+        b.add_instance(b.add_model([(g, m, None)]), instance_matrix)
+        eye = np.asarray(eye, np.float64)
+        return b.build(scenes.camera_matrices(eye, -eye, 32, 32, fov_deg=40, up=(0.0, 0.0, 1.0)), (32, 32))
+
+    quad_v, quad_i = scenes.quad(2.0, 2.0)
+    p0, p1, p2 = (quad_v["position"][quad_i[k]].astype(np.float64) for k in range(3))
+    n_obj = np.cross(p1 - p0, p2 - p0)  # numeric normal of the object-space winding
+    ident = np.eye(4)
+    mirror = np.diag([1.0, -1.0, 1.0, 1.0])  # flips y: the quad stays in place, the determinant is negative
+    for matrix, mirrored in ((ident, False), (mirror, True)):
+        for eye in ((0.0, 3.0, 0.0), (0.0, -3.0, 0.0)):
+            s = scene_with(matrix, eye)
+            o = oracle_mod.OracleScene(s)
+            p = s.default_params()
+            plain = o.debug_render(p, 32, 32, "instance")
+            culled = o.debug_render(p, 32, 32, "instance", raygen_flags=0x2)
+            centre_hit = not np.allclose(plain[16, 16, :3], 0.2)
+            assert centre_hit
+            # object-space ray direction at the centre: world direction is -eye; the mirror maps it back
+            d_obj = -np.asarray(eye) * (np.array([1.0, -1.0, 1.0]) if mirrored else 1.0)
+            front = np.dot(n_obj, d_obj) < 0
+            still_hit = not np.allclose(culled[16, 16, :3], 0.2)
+            assert still_hit == front, (mirrored, eye)

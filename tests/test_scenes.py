@@ -38,3 +38,23 @@ def test_default_sizes_are_the_declared_ones():
     assert 2 * 4096 * 64 == 524_288
     assert 4 * 12 * 2 * 256 * 511 + 2 * 2 * 1024 ** 2 + 4 * 12 + 12288 * 512 * 2 == 29_335_600
     assert 48 * 2 * 192 ** 2 + 2 * 768 ** 2 + 4096 * (2 + 2 * 32 * 15) == 8_658_944
+
+
+def test_exr_writer_round_trip(tmp_path):
+    """write_exr: a valid uncompressed scanline OpenEXR 2.0 file (magic, version, header attributes, offset table) that
+    keeps every bit of the float image."""
+    import importlib
+    import struct
+
+    import numpy as np
+
+    core = importlib.import_module("path-tracing_b200.core")
+    rs = np.random.default_rng(3)
+    img = rs.normal(0, 10, (7, 13, 4)).astype(np.float32)
+    img[0, 0] = [np.inf, 1e-38, -0.0, 1.0]
+    path = tmp_path / "a.exr"
+    core.write_exr(str(path), img)
+    raw = path.read_bytes()
+    assert struct.unpack_from("<ii", raw, 0) == (20000630, 2) and b"channels\0chlist\0" in raw and b"dataWindow\0box2i\0" in raw
+    back = core.read_exr(str(path))
+    assert back.dtype == np.float32 and np.array_equal(back.view(np.uint32), img.view(np.uint32))
