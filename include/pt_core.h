@@ -398,6 +398,17 @@ typedef struct pt_scene_update_desc {
  * `updated` flag, Renderer.cpp:240-241) with pt_render_begin.  Blocking. */
 PT_API pt_status pt_scene_update(pt_context *ctx, const pt_scene_update_desc *desc);
 
+/* Replaces the sampler state of Renderer::CreateSampler (PT/Renderer/Renderer.cpp:103-112: linear mag / min / mip,
+ * repeat, anisotropyEnable with maxAnisotropy = the device limit): the maximum anisotropy of the material fetches
+ * (textureGrad, material.glsl:62-171).  1 = isotropic trilinear filtering (GL 4.6 8.14); up to 16 taps along the major
+ * axis of the footprint otherwise (the example implementation of the Vulkan specification, "Texel Anisotropic
+ * Filtering"; a footprint that reaches the 1 x 1 top level is one tap).  16 = what the reference's sampler asks for on
+ * every current GPU.  DEFAULT 1: without texture units every tap is eight software texel fetches, and path tracing's
+ * secondary bounces have huge, elongated footprints — the 16-tap sampler makes k_shade 4-7 x slower (measured)
+ * for a filter whose exact result is implementation-defined in the reference anyway.  Takes effect at the next render
+ * call; the accumulated image is not reset. */
+PT_API pt_status pt_set_sampler(pt_context *ctx, uint32_t max_anisotropy);
+
 /* Replaces Renderer::UpdateTexture(index) (PT/Renderer/Renderer.cpp:441-471): replace the
  * content of one texture slot (slot = PT_SCENE_TEXTURE_OFFSET + scene texture index). */
 PT_API pt_status pt_texture_upload(pt_context *ctx, uint32_t slot, const pt_texture_desc *texture);

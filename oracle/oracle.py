@@ -58,6 +58,7 @@ def lib():
         L.pto_scene_create.restype = C.c_void_p
         L.pto_scene_create.argtypes = [C.c_void_p]
         L.pto_scene_destroy.argtypes = [C.c_void_p]
+        L.pto_scene_set_sampler.argtypes = [C.c_void_p, C.c_uint32]
         L.pto_scene_triangle_count.restype = C.c_uint64
         L.pto_scene_triangle_count.argtypes = [C.c_void_p]
         L.pto_render.argtypes = [
@@ -148,6 +149,11 @@ class OracleScene:
             self.close()
         except Exception:
             pass
+
+    def set_sampler(self, max_anisotropy: int):
+        """Maximum anisotropy of textureGrad: 1 = isotropic trilinear (default), 16 = the reference's sampler state."""
+        rc = lib().pto_scene_set_sampler(self._h, int(max_anisotropy))
+        assert rc == 0, rc
 
     @property
     def triangle_count(self) -> int:

@@ -944,18 +944,9 @@ vec4 sampleBilinear(const Texture &t, uint32_t level, vec2 uv, TexelCounter *tc)
  * (anyhit.rahit:51, occlusionAnyhit.rahit:50, miss.rmiss:27) */
 vec4 textureLod0(const Texture &t, vec2 uv, TexelCounter *tc = nullptr) { return sampleBilinear(t, 0, uv, tc); }
 
-/* textureGrad(sampler2D, P, dPdx, dPdy), GL 4.6 §8.14: rho = max(|dPdx * size|, |dPdy * size|),
- * lambda = log2(rho), trilinear between floor(lambda) and floor(lambda) + 1 */
-vec4 textureGrad(const Texture &t, vec2 uv, vec2 dPdx, vec2 dPdy, TexelCounter *tc)
+/* One trilinear tap: levels floor(lambda) and floor(lambda) + 1 blended by the fraction. */
+vec4 sampleTrilinear(const Texture &t, float lambda, uint32_t last, vec2 uv, TexelCounter *tc)
 {
-    const uint32_t last = (uint32_t)t.levels.size() - 1;
-    if (last == 0)
-        return sampleBilinear(t, 0, uv, tc);
-    const float w = (float)t.levels[0].w, h = (float)t.levels[0].h;
-    const float ax = dPdx.x * w, ay = dPdx.y * h;
-    const float bx = dPdy.x * w, by = dPdy.y * h;
-    const float rho2 = max(ax * ax + ay * ay, bx * bx + by * by);
-    const float lambda = 0.5f * std::log2(rho2);
     if (!(lambda > 0.0f))
         return sampleBilinear(t, 0, uv, tc);
     if (lambda >= (float)last)
@@ -964,8 +955,53 @@ vec4 textureGrad(const Texture &t, vec2 uv, vec2 dPdx, vec2 dPdy, TexelCounter *
     const uint32_t l0 = (uint32_t)fl;
     const float f = lambda - fl;
     const vec4 a = sampleBilinear(t, l0, uv, tc);
+    if (!(f > 0.0f))
+        return a;
     const vec4 b = sampleBilinear(t, l0 + 1, uv, tc);
     return a * (1.0f - f) + b * f;
+}
+
+/* textureGrad(sampler2D, P, dPdx, dPdy) with the reference's sampler (linear / linear-mip / repeat, anisotropy enabled at
+ * the device maximum, PT/Renderer/Renderer.cpp:103-112).  Filtering is sampler HARDWARE in the reference (PARITY UNPINNED);
+ * this is the example implementation the Vulkan specification gives ("Texel Anisotropic Filtering"):
+ *     rho_x = |dPdx * size|, rho_y = |dPdy * size|, eta = min(rho_max / rho_min, maxAnisotropy), N = ceil(eta),
+ *     lambda = log2(rho_max / eta),
+ *     tau = 1/N * sum_{i=1..N} trilinear(P + (i / (N + 1) - 1/2) * dPd{major axis}, lambda)
+ * maxAnisotropy = 1 is the isotropic trilinear filter of GL 4.6 §8.14 (N = 1, eta = 1, one tap at P). */
+vec4 textureGrad(const Texture &t, vec2 uv, vec2 dPdx, vec2 dPdy, TexelCounter *tc, uint32_t maxAnisotropy = 1)
+{
+    const uint32_t last = (uint32_t)t.levels.size() - 1;
+    if (last == 0)
+        return sampleBilinear(t, 0, uv, tc);
+    const float w = (float)t.levels[0].w, h = (float)t.levels[0].h;
+    const float ax = dPdx.x * w, ay = dPdx.y * h;
+    const float bx = dPdy.x * w, by = dPdy.y * h;
+    const float rx2 = ax * ax + ay * ay, ry2 = bx * bx + by * by;
+    const float rho2 = max(rx2, ry2);
+    uint32_t N = 1;
+    float eta = 1.0f;
+    if (maxAnisotropy > 1 && rho2 > 0.0f) /* a point footprint (both derivatives zero) is one tap of level 0 */
+    {
+        const float rmin2 = min(rx2, ry2);
+        /* rho_max / rho_min; a zero (or non-finite) minor axis asks for the maximum */
+        const float ratio = std::sqrt(rho2) / std::sqrt(rmin2);
+        eta = (ratio <= (float)maxAnisotropy) ? max(ratio, 1.0f) : (float)maxAnisotropy;
+        N = (uint32_t)std::ceil(eta);
+    }
+    const float lambda = 0.5f * std::log2(rho2 / (eta * eta));
+    /* at the 1 x 1 top level every tap reads the same texel: one tap */
+    if (N == 1 || lambda >= (float)last)
+        return sampleTrilinear(t, lambda, last, uv, tc);
+    const vec2 major = (rx2 > ry2) ? dPdx : dPdy;
+    vec4 acc = V4(0.0f, 0.0f, 0.0f, 0.0f);
+    for (uint32_t i = 1; i <= N; i++)
+    {
+        const float o = (float)i / (float)(N + 1) - 0.5f;
+        const vec4 tap = sampleTrilinear(t, lambda, last, V2(uv.x + o * major.x, uv.y + o * major.y), tc);
+        acc = (i == 1) ? tap : acc + tap;
+    }
+    const float n = (float)N;
+    return V4(acc.x / n, acc.y / n, acc.z / n, acc.w / n);
 }
 
 /* ========================================================================= */
@@ -1003,6 +1039,7 @@ struct pto_scene
     std::vector<pt_material_sg> sg;
     std::vector<pt_material_phong> phong;
     std::vector<Texture> textures;
+    uint32_t maxAnisotropy = 1; /* pto_scene_set_sampler: 16 = the reference's sampler state (Renderer.cpp:103-112) */
     std::vector<pt_point_light> pointLights;
     pt_directional_light directional;
     bool hasSky2D = false;
@@ -1666,7 +1703,7 @@ struct TexCtx
     const pto_scene &s;
     vec2 uv, dpdx, dpdy;
     TexelCounter tc;
-    vec4 grad(uint32_t idx) { return textureGrad(s.textures[idx], uv, dpdx, dpdy, &tc); }
+    vec4 grad(uint32_t idx) { return textureGrad(s.textures[idx], uv, dpdx, dpdy, &tc, s.maxAnisotropy); }
 };
 
 /* PT/Shaders/material.glsl:62-84 */
@@ -2427,6 +2464,14 @@ pto_scene *pto_scene_create(const pt_scene_desc *d)
 
 void pto_scene_destroy(pto_scene *s) { delete s; }
 
+int32_t pto_scene_set_sampler(pto_scene *s, uint32_t max_anisotropy)
+{
+    if (!s || max_anisotropy < 1 || max_anisotropy > 16)
+        return PT_ERR_INVALID_ARGUMENT;
+    s->maxAnisotropy = max_anisotropy;
+    return PT_OK;
+}
+
 uint64_t pto_scene_triangle_count(const pto_scene *s) { return s ? s->tris.size() : 0; }
 
 int32_t pto_render_frames(const pto_scene *s, const pt_render_params *p, uint32_t width, uint32_t height,
@@ -2971,7 +3016,7 @@ int32_t pto_texture_sample(const pto_scene *s, uint32_t slot, const float *in6, 
     for (uint32_t i = 0; i < count; i++)
     {
         const float *a = in6 + (size_t)i * 6;
-        const vec4 r = use_grad ? textureGrad(t, V2(a[0], a[1]), V2(a[2], a[3]), V2(a[4], a[5]), nullptr)
+        const vec4 r = use_grad ? textureGrad(t, V2(a[0], a[1]), V2(a[2], a[3]), V2(a[4], a[5]), nullptr, s->maxAnisotropy)
                                 : textureLod0(t, V2(a[0], a[1]));
         out4[i * 4] = r.x, out4[i * 4 + 1] = r.y, out4[i * 4 + 2] = r.z, out4[i * 4 + 3] = r.w;
     }

@@ -44,6 +44,9 @@ typedef struct pto_counters {
 PT_API pto_scene *pto_scene_create(const pt_scene_desc *scene);
 PT_API void pto_scene_destroy(pto_scene *scene);
 PT_API uint64_t pto_scene_triangle_count(const pto_scene *scene);
+/* Sampler state like pt_set_sampler: maximum anisotropy of textureGrad, 1 (isotropic trilinear, the default) .. 16 (what
+ * the reference's sampler asks for: anisotropy at the device maximum, Renderer.cpp:103-112). */
+PT_API int32_t pto_scene_set_sampler(pto_scene *scene, uint32_t max_anisotropy);
 
 /* accum: width*height*4 floats, updated in place exactly like imageLoad/imageStore in
  * raygen.rgen:115-117 (rgb += radiance, a = 1), for frames TotalSamples = first_sample ..

@@ -28,6 +28,7 @@ ABI_SYMBOLS = [
     "pt_scene_upload",
     "pt_scene_update",
     "pt_texture_upload",
+    "pt_set_sampler",
     "pt_render_begin",
     "pt_render_samples",
     "pt_render_frames",
@@ -252,6 +253,7 @@ def lib():
     L.pt_render_begin.argtypes = [vp, u32, u32]
     L.pt_render_samples.argtypes = [vp, vp, u32, u32, vp, u32]
     L.pt_render_frames.argtypes = [vp, vp, u32, u32, u32, vp, u32]
+    L.pt_set_sampler.argtypes = [vp, u32]
     L.pt_accum_device_ptr.argtypes = [vp, C.POINTER(vp), C.POINTER(C.c_size_t), C.POINTER(vp)]
     L.pt_readback.argtypes = [vp, vp, C.c_size_t]
     L.pt_postprocess.argtypes = [vp, vp, u32, u32, vp, C.c_size_t]
@@ -470,6 +472,10 @@ class Renderer:
     def set_tuning(self, key: str, value: int):
         """Scheduling knobs (pools, slots, sort_hits, sbuf_mb); results do not depend on them."""
         self._check(self._L.pt_set_tuning(self._h, key.encode(), int(value)))
+
+    def set_sampler(self, max_anisotropy: int):
+        """Sampler state (Renderer.cpp:103-112): maximum anisotropy of the material fetches, 1 = isotropic (default) .. 16 (the reference's)."""
+        self._check(self._L.pt_set_sampler(self._h, int(max_anisotropy)))
 
     def set_kernel_timing(self, enable: bool):
         self._check(self._L.pt_set_kernel_timing(self._h, 1 if enable else 0))

@@ -1272,6 +1272,7 @@ pt_status uploadScene(Context *ctx, const pt_scene_desc *d)
 
     s.triCount = n;
     s.hasAlpha = hasAlpha ? 1u : 0u;
+    s.maxAnisotropy = ctx->maxAnisotropy;
     // vertices and indices stay on the device: pt_scene_update re-bakes from them.  Skinned vertices and
     // animated indices follow the static ones in the same buffers.
     {

@@ -126,6 +126,7 @@ struct Context
     uint32_t bvhBuilder = 1;  // 1 = PLOC (default), 0 = LBVH; PT_BVH / tuning key "bvh_builder"
     uint32_t plocRadius = 8;  // PLOC search window on either side; PT_PLOC_RADIUS / "ploc_radius"
     uint32_t bvhBuildPasses = 0;
+    uint32_t maxAnisotropy = 1; // sampler state (pt_set_sampler): 1 = isotropic trilinear, 16 = the reference's sampler
     uint32_t bvhMaxDepth = 0; // levels of the wide BVH (the traversal stack holds at most 3 entries per level)
 
     // target

@@ -96,6 +96,8 @@ pt_status pt_context_create(int32_t cuda_device, pt_context **out_ctx)
         ctx->bvhBuilder = std::atoi(e) != 0;
     if (const char *e = std::getenv("PT_PLOC_RADIUS"))
         ctx->plocRadius = (uint32_t)std::max(1, std::atoi(e));
+    if (const char *e = std::getenv("PT_MAX_ANISOTROPY")) // A/B measurements; pt_set_sampler is the API
+        ctx->maxAnisotropy = (uint32_t)std::min(16, std::max(1, std::atoi(e)));
     if (const char *e = std::getenv("PT_SBUF_MB"))
         ctx->sbufBudgetBytes = std::max<size_t>(1, std::strtoull(e, nullptr, 10)) << 20;
 #define PT_CREATE_CHECK(expr)                                                                                         \
@@ -437,6 +439,17 @@ pt_status pt_set_tuning(pt_context *ctx, const char *key, uint64_t value)
         ctx->sbufBudgetBytes = std::max<uint64_t>(1, value) << 20;
     else
         return fail(ctx, PT_ERR_INVALID_ARGUMENT, "pt_set_tuning", "unknown key");
+    return PT_OK;
+}
+
+pt_status pt_set_sampler(pt_context *ctx, uint32_t max_anisotropy)
+{
+    if (!ctx)
+        return PT_ERR_INVALID_ARGUMENT;
+    if (max_anisotropy < 1 || max_anisotropy > 16)
+        return fail(ctx, PT_ERR_INVALID_ARGUMENT, "pt_set_sampler", "max_anisotropy must be in 1..16");
+    ctx->maxAnisotropy = max_anisotropy;
+    ctx->scene.maxAnisotropy = max_anisotropy; // the scene struct travels to every kernel by value
     return PT_OK;
 }
 

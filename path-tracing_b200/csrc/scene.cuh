@@ -119,10 +119,11 @@ struct DeviceScene
     uint32_t hasAlpha; // any non-opaque triangle
     uint32_t hasSky2D;
     uint32_t skyCubeSlot; // first of six consecutive entries of textures[] (+X, -X, +Y, -Y, +Z, -Z); 0 = no cube sky
+    uint32_t maxAnisotropy; // sampler state of textureGrad: 1 = isotropic trilinear .. 16 (pt_set_sampler)
 };
 
 // ---------------------------------------------------------------------------------------------
-// sampler (linear / linear-mip / repeat; isotropic — see oracle/pt_oracle.cpp for the definition)
+// sampler (linear / linear-mip / repeat / anisotropic — see oracle/pt_oracle.cpp for the definition)
 // ---------------------------------------------------------------------------------------------
 PT_DEV float4 fetchTexel(const DeviceScene &s, const DevTexture &t, uint32_t level, uint32_t x, uint32_t y, uint32_t lw)
 {
@@ -212,25 +213,65 @@ PT_DEV float4 sampleCube(const DeviceScene &s, uint32_t firstSlot, vec3 r)
     return lerp4(lerp4(t00, t10, fx), lerp4(t01, t11, fx), fy);
 }
 
-// textureGrad(): lambda = log2(max(|dPdx * size|, |dPdy * size|)); returns the lower level and the
-// blend weight towards the next one (0 = single level)
-PT_DEV uint32_t gradLevel(const DevTexture &t, float4 deriv, float &frac)
+// Footprint of a textureGrad lookup (Vulkan "Texel Anisotropic Filtering", the specification's example implementation;
+// definition and citations in oracle/pt_oracle.cpp textureGrad): N taps along the major axis, all at level-of-detail
+// lambda = log2(rho_max / eta).  Returns the lower mip level and the blend weight towards the next one (0 = one level).
+struct GradFootprint
 {
-    frac = 0.0f;
+    uint32_t level; // lower level
+    float frac;     // trilinear weight of level + 1
+    uint32_t taps;  // N, 1 .. maxAnisotropy
+    float du, dv;   // major-axis derivative (uv units)
+};
+PT_DEV GradFootprint gradFootprint(const DevTexture &t, float4 deriv, uint32_t maxAnisotropy)
+{
+    GradFootprint g;
+    g.level = 0;
+    g.frac = 0.0f;
+    g.taps = 1;
+    g.du = g.dv = 0.0f;
     const uint32_t last = t.levels - 1;
     if (last == 0)
-        return 0;
+        return g;
     const float w = (float)t.width, h = (float)t.height;
     const float ax = deriv.x * w, ay = deriv.y * h, bx = deriv.z * w, by = deriv.w * h;
-    const float rho2 = fmaxf(ax * ax + ay * ay, bx * bx + by * by);
-    const float lambda = 0.5f * log2f(rho2);
+    const float rx2 = ax * ax + ay * ay, ry2 = bx * bx + by * by;
+    const float rho2 = fmaxf(rx2, ry2);
+    float eta = 1.0f;
+    if (maxAnisotropy > 1 && rho2 > 0.0f)
+    {
+        const float rmin2 = fminf(rx2, ry2);
+        const float ratio = sqrtf(rho2) / sqrtf(rmin2);
+        eta = (ratio <= (float)maxAnisotropy) ? fmaxf(ratio, 1.0f) : (float)maxAnisotropy;
+        g.taps = (uint32_t)ceilf(eta);
+        if (rx2 > ry2)
+            g.du = deriv.x, g.dv = deriv.y;
+        else
+            g.du = deriv.z, g.dv = deriv.w;
+    }
+    const float lambda = 0.5f * log2f(rho2 / (eta * eta));
     if (!(lambda > 0.0f))
-        return 0;
+        return g;
     if (lambda >= (float)last)
-        return last;
+    {
+        g.level = last;
+        g.taps = 1; // at the 1 x 1 top level every tap reads the same texel
+        return g;
+    }
     const float fl = floorf(lambda);
-    frac = lambda - fl;
-    return (uint32_t)fl;
+    g.frac = lambda - fl;
+    g.level = (uint32_t)fl;
+    return g;
+}
+
+PT_DEV float4 sampleTrilinear(const DeviceScene &s, const DevTexture &t, uint32_t level, float frac, float u, float v)
+{
+    const float4 a = sampleBilinear(s, t, level, u, v);
+    // single level, or a blend weight of exactly 0
+    if (!(frac > 0.0f))
+        return a;
+    const float4 b = sampleBilinear(s, t, level + 1, u, v);
+    return lerp4(a, b, frac);
 }
 
 // Inlined by default.  An out-of-line copy (PT_TEX_INLINE=0) shrinks k_shade from 300 KB to 100 KB
@@ -247,24 +288,32 @@ static __device__ __noinline__ float4 textureGrad(
 const DeviceScene &s, uint32_t slot, float u, float v, float4 deriv)
 {
     const DevTexture &t = s.textures[slot];
-    float frac;
-    const uint32_t l0 = gradLevel(t, deriv, frac);
-    const float4 a = sampleBilinear(s, t, l0, u, v);
-    // single level, or a blend weight of exactly 0 (lerp4(a, b, 0) == a for finite texels)
-    if (!(frac > 0.0f))
-        return a;
-    const float4 b = sampleBilinear(s, t, l0 + 1, u, v);
-    return lerp4(a, b, frac);
+    const GradFootprint g = gradFootprint(t, deriv, s.maxAnisotropy);
+    if (g.taps == 1)
+        return sampleTrilinear(s, t, g.level, g.frac, u, v);
+    // the anisotropic taps: rare (grazing angles), kept out of the common path's registers
+    float4 acc = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    const float n1 = (float)(g.taps + 1);
+    for (uint32_t i = 1; i <= g.taps; i++)
+    {
+        const float o = (float)i / n1 - 0.5f;
+        const float4 tap = sampleTrilinear(s, t, g.level, g.frac, u + o * g.du, v + o * g.dv);
+        if (i == 1)
+            acc = tap;
+        else
+            acc = make_float4(acc.x + tap.x, acc.y + tap.y, acc.z + tap.z, acc.w + tap.w);
+    }
+    const float n = (float)g.taps;
+    return make_float4(acc.x / n, acc.y / n, acc.z / n, acc.w / n);
 }
 
 // texels textureGrad reads for this lookup (traversal statistics only)
 PT_DEV uint32_t textureGradTexels(const DeviceScene &s, uint32_t slot, float4 deriv)
 {
     const DevTexture &t = s.textures[slot];
-    float frac;
-    const uint32_t l0 = gradLevel(t, deriv, frac);
+    const GradFootprint g = gradFootprint(t, deriv, s.maxAnisotropy);
     auto texels = [&](uint32_t level) { return (max(1u, t.width >> level) == 1 && max(1u, t.height >> level) == 1) ? 1u : 4u; };
-    return texels(l0) + (frac > 0.0f ? texels(l0 + 1) : 0u);
+    return g.taps * (texels(g.level) + (g.frac > 0.0f ? texels(g.level + 1) : 0u));
 }
 
 } // namespace pt

@@ -62,3 +62,50 @@ def test_float_unorm_and_bc_textures(oracle_mod):
             _check(r, ora, slot, rec)
         with pytest.raises(core.PtError):
             r.texture_sample(sc.SCENE_TEXTURE_OFFSET + len(s.textures), rec)
+
+
+def test_anisotropic_sampler_flag(default_scene, oracle_mod):
+    """pt_set_sampler(16): the reference's sampler state (anisotropy at the device maximum, Renderer.cpp:103-112) as the
+    Vulkan specification's example implementation — record by record against the oracle's (closed forms:
+    tests/test_oracle_textures.py), and a whole image of the textured Default scene."""
+    import metrics
+
+    rs = np.random.default_rng(21)
+    rec = _records(rs, 4000)
+    # elongated footprints: ratio 1 .. 100 between the two derivative axes
+    n = 2000
+    ang = rs.uniform(0, 2 * np.pi, n)
+    long_ = 10.0 ** rs.uniform(-3.5, -0.5, n)
+    ratio = 10.0 ** rs.uniform(0, 2, n)
+    ax = np.stack([np.cos(ang), np.sin(ang)], 1)
+    perp = np.stack([-np.sin(ang), np.cos(ang)], 1)
+    swap = rs.uniform(size=n) < 0.5
+    dx = np.where(swap[:, None], perp * (long_ / ratio)[:, None], ax * long_[:, None])
+    dy = np.where(swap[:, None], ax * long_[:, None], perp * (long_ / ratio)[:, None])
+    rec2 = np.concatenate([rs.uniform(-1, 2, (n, 2)), dx, dy], 1).astype(np.float32)
+    ora = oracle_mod.OracleScene(default_scene)
+    ora.set_sampler(16)
+    with core.Renderer(0) as r:
+        r.update_scene_data(default_scene)
+        r.set_sampler(16)
+        for slot in [1, sc.SCENE_TEXTURE_OFFSET + 1, sc.SCENE_TEXTURE_OFFSET + 3]:
+            _check(r, ora, slot, rec)
+            _check(r, ora, slot, rec2)
+        # the flag changes the fetches (and only the textureGrad ones)
+        iso = oracle_mod.OracleScene(default_scene)
+        a, b = ora.texture_sample(sc.SCENE_TEXTURE_OFFSET + 1, rec2), iso.texture_sample(sc.SCENE_TEXTURE_OFFSET + 1, rec2)
+        assert (np.abs(a - b).max(1) > 1e-3).mean() > 0.1
+        assert np.array_equal(ora.texture_sample(sc.SCENE_TEXTURE_OFFSET + 1, rec2, use_grad=False),
+                              iso.texture_sample(sc.SCENE_TEXTURE_OFFSET + 1, rec2, use_grad=False))
+        # images with the anisotropic sampler on both sides
+        p = default_scene.default_params(bounce_count=8)
+        r.on_resize(256, 256)
+        r.render(8, params=p)
+        img = r.read_accumulation()
+        ref, _ = ora.render(p, 256, 256, 0, 8)
+        assert metrics.close_fraction(img, ref, 1e-4) > 0.99
+        assert metrics.rel_mse(img / 8, ref / 8) <= 1e-3
+        ref_iso, _ = iso.render(p, 256, 256, 0, 8)
+        assert metrics.close_fraction(img, ref_iso, 1e-4) < 0.99  # and it is not the isotropic image
+        with pytest.raises(core.PtError):
+            r.set_sampler(0)

@@ -74,3 +74,47 @@ def test_texture_grad_lod_selection(default_oracle):
     # NaN / Inf derivatives fall back to level 0 (derivative clamp in tracing.glsl lets NaN through)
     nan = default_oracle.texture_sample(slot, [[*uv, np.nan, 0, 0, 0]])
     assert np.allclose(nan, lod0)
+
+
+def test_anisotropic_footprint_closed_form(default_scene, oracle_mod):
+    """textureGrad with the reference's sampler state (anisotropy at the device maximum, Renderer.cpp:103-112), defined as
+    the Vulkan specification's example implementation: eta = min(rho_max / rho_min, 16), N = ceil(eta) taps spread along
+    the major axis at i / (N + 1) - 1/2 of its derivative, all at lambda = log2(rho_max / eta), averaged."""
+    o = oracle_mod.OracleScene(default_scene)
+    o.set_sampler(16)
+    slot = sc.SCENE_TEXTURE_OFFSET + 1  # 512^2
+    W = 512.0
+    uv = np.array([0.37, 0.61])
+    # ratio 4 at one texel of minor axis: lambda = log2(4 / 4) = 0 -> four bilinear taps of level 0 along x
+    got = o.texture_sample(slot, [[*uv, 4 / W, 0, 0, 1 / W]])[0]
+    taps = [[uv[0] + (i / 5 - 0.5) * 4 / W, uv[1], 0, 0, 0, 0] for i in (1, 2, 3, 4)]
+    want = o.texture_sample(slot, taps, use_grad=False).astype(np.float64).mean(0)
+    assert np.allclose(got, want, rtol=1e-6, atol=1e-7)
+    # the major axis can be dPdy, and diagonal
+    got = o.texture_sample(slot, [[*uv, 0.5 / W, 0.5 / W, -2 / W, 2 / W]])[0]  # rho_x = 0.707, rho_y = 2.83: eta = 4
+    taps = [[uv[0] + (i / 5 - 0.5) * -2 / W, uv[1] + (i / 5 - 0.5) * 2 / W, 0, 0, 0, 0] for i in (1, 2, 3, 4)]
+    # lambda = log2(2.83 / 4) < 0: level 0
+    assert np.allclose(got, o.texture_sample(slot, taps, use_grad=False).astype(np.float64).mean(0), rtol=1e-6, atol=1e-7)
+    # beyond the maximum: ratio 64 -> eta = 16, lambda = log2(64 / 16) = 2: sixteen bilinear taps of level 2
+    got = o.texture_sample(slot, [[*uv, 64 / W, 0, 0, 1 / W]])[0]
+    l2 = o.texture_level(slot, 2).astype(np.float64)
+    lin = np.concatenate([srgb_to_linear(l2[..., :3]), l2[..., 3:] / 255], -1)
+
+    def bilinear(img, u, v):
+        h, w = img.shape[:2]
+        x, y = (u % 1.0) * w - 0.5, (v % 1.0) * h - 0.5
+        x0, y0 = int(np.floor(x)), int(np.floor(y))
+        fx, fy = x - x0, y - y0
+        t = lambda xx, yy: img[yy % h, xx % w]
+        return (t(x0, y0) * (1 - fx) + t(x0 + 1, y0) * fx) * (1 - fy) + (t(x0, y0 + 1) * (1 - fx) + t(x0 + 1, y0 + 1) * fx) * fy
+
+    want = np.mean([bilinear(lin, uv[0] + (i / 17 - 0.5) * 64 / W, uv[1]) for i in range(1, 17)], 0)
+    assert np.allclose(got, want, rtol=1e-5, atol=1e-6)
+    # isotropic footprints and maximum anisotropy 1 are the trilinear filter: one tap
+    iso = o.texture_sample(slot, [[*uv, 3 / W, 0, 0, 3 / W]])[0]
+    o.set_sampler(1)
+    assert np.array_equal(o.texture_sample(slot, [[*uv, 3 / W, 0, 0, 3 / W]])[0], iso)
+    blurry = o.texture_sample(slot, [[*uv, 64 / W, 0, 0, 1 / W]])[0]  # lambda = 6 now: far blurrier than the 16 taps of level 2
+    top = o.texture_level(slot, 6).astype(np.float64)
+    assert not np.allclose(blurry, got, atol=1e-3)
+    assert np.abs(blurry[:3] - bilinear(np.concatenate([srgb_to_linear(top[..., :3]), top[..., 3:] / 255], -1), *uv)[:3]).max() < 1e-5
