@@ -57,6 +57,8 @@ def lib():
         L = C.CDLL(_LIB_PATH)
         L.pto_scene_create.restype = C.c_void_p
         L.pto_scene_create.argtypes = [C.c_void_p]
+        L.pto_scene_create_limits.restype = C.c_void_p
+        L.pto_scene_create_limits.argtypes = [C.c_void_p, C.c_uint32, C.c_uint64]
         L.pto_scene_destroy.argtypes = [C.c_void_p]
         L.pto_scene_set_sampler.argtypes = [C.c_void_p, C.c_uint32]
         L.pto_scene_triangle_count.restype = C.c_uint64
@@ -130,12 +132,12 @@ def test_shading(mode: int, inputs: np.ndarray) -> np.ndarray:
 
 
 class OracleScene:
-    def __init__(self, scene):
+    def __init__(self, scene, max_texture_size: int = 4096, texture_budget_mb: int = 0):
         from importlib import import_module
 
         self._sc = import_module("path-tracing_b200.scene")
         desc, keep = scene.to_c()
-        self._h = lib().pto_scene_create(C.addressof(desc))
+        self._h = lib().pto_scene_create_limits(C.addressof(desc), int(max_texture_size), int(texture_budget_mb) << 20)
         del keep
         assert self._h, "pto_scene_create failed"
 

@@ -711,6 +711,52 @@ struct Texture
 /* Mip chain: levels = floor(log2(max(w,h))) + 1 (PT/Renderer/Image.cpp:14-17), each level a linear
  * vkCmdBlitImage of the previous one (Image.cpp:264-305): destination texel centre mapped to the
  * source, bilinear with clamp-to-edge; filtering in linear space, stored back as 8-bit. */
+/* one linear vkCmdBlitImage of level `k` of t into a dw x dh level */
+TexLevel blitLinear(const Texture &t, uint32_t k, uint32_t dw, uint32_t dh)
+{
+    const TexLevel &src = t.levels[k];
+    TexLevel dst;
+    dst.w = dw;
+    dst.h = dh;
+    if (t.isFloat)
+        dst.rgbaf.resize((size_t)dst.w * dst.h * 4);
+    else
+        dst.rgba8.resize((size_t)dst.w * dst.h * 4);
+    const float sxScale = (float)src.w / (float)dst.w;
+    const float syScale = (float)src.h / (float)dst.h;
+    for (uint32_t y = 0; y < dst.h; y++)
+        for (uint32_t x = 0; x < dst.w; x++)
+        {
+            const float sx = ((float)x + 0.5f) * sxScale - 0.5f;
+            const float sy = ((float)y + 0.5f) * syScale - 0.5f;
+            const float fx0 = std::floor(sx), fy0 = std::floor(sy);
+            const float fx = sx - fx0, fy = sy - fy0;
+            const int x0 = std::clamp((int)fx0, 0, (int)src.w - 1), x1 = std::clamp((int)fx0 + 1, 0, (int)src.w - 1);
+            const int y0 = std::clamp((int)fy0, 0, (int)src.h - 1), y1 = std::clamp((int)fy0 + 1, 0, (int)src.h - 1);
+            const vec4 t00 = t.texel(k, x0, y0), t10 = t.texel(k, x1, y0);
+            const vec4 t01 = t.texel(k, x0, y1), t11 = t.texel(k, x1, y1);
+            const vec4 top = t00 * (1.0f - fx) + t10 * fx;
+            const vec4 bot = t01 * (1.0f - fx) + t11 * fx;
+            const vec4 v = top * (1.0f - fy) + bot * fy;
+            const size_t o = ((size_t)y * dst.w + x) * 4;
+            if (t.isFloat)
+            {
+                dst.rgbaf[o] = v.x;
+                dst.rgbaf[o + 1] = v.y;
+                dst.rgbaf[o + 2] = v.z;
+                dst.rgbaf[o + 3] = v.w;
+            }
+            else
+            {
+                dst.rgba8[o] = t.srgb ? encodeSrgb8(v.x) : encodeUnorm8(v.x);
+                dst.rgba8[o + 1] = t.srgb ? encodeSrgb8(v.y) : encodeUnorm8(v.y);
+                dst.rgba8[o + 2] = t.srgb ? encodeSrgb8(v.z) : encodeUnorm8(v.z);
+                dst.rgba8[o + 3] = encodeUnorm8(v.w);
+            }
+        }
+    return dst;
+}
+
 void buildMips(Texture &t)
 {
     uint32_t w = t.levels[0].w, h = t.levels[0].h;
@@ -718,50 +764,38 @@ void buildMips(Texture &t)
     for (uint32_t m = std::max(w, h); m > 1; m >>= 1)
         count++;
     for (uint32_t k = 1; k < count; k++)
-    {
-        const TexLevel &src = t.levels[k - 1];
-        TexLevel dst;
-        dst.w = std::max(1u, w >> k);
-        dst.h = std::max(1u, h >> k);
-        if (t.isFloat)
-            dst.rgbaf.resize((size_t)dst.w * dst.h * 4);
-        else
-            dst.rgba8.resize((size_t)dst.w * dst.h * 4);
-        const float sxScale = (float)src.w / (float)dst.w;
-        const float syScale = (float)src.h / (float)dst.h;
-        for (uint32_t y = 0; y < dst.h; y++)
-            for (uint32_t x = 0; x < dst.w; x++)
-            {
-                const float sx = ((float)x + 0.5f) * sxScale - 0.5f;
-                const float sy = ((float)y + 0.5f) * syScale - 0.5f;
-                const float fx0 = std::floor(sx), fy0 = std::floor(sy);
-                const float fx = sx - fx0, fy = sy - fy0;
-                const int x0 = std::clamp((int)fx0, 0, (int)src.w - 1), x1 = std::clamp((int)fx0 + 1, 0, (int)src.w - 1);
-                const int y0 = std::clamp((int)fy0, 0, (int)src.h - 1), y1 = std::clamp((int)fy0 + 1, 0, (int)src.h - 1);
-                const vec4 t00 = t.texel(k - 1, x0, y0), t10 = t.texel(k - 1, x1, y0);
-                const vec4 t01 = t.texel(k - 1, x0, y1), t11 = t.texel(k - 1, x1, y1);
-                const vec4 top = t00 * (1.0f - fx) + t10 * fx;
-                const vec4 bot = t01 * (1.0f - fx) + t11 * fx;
-                const vec4 v = top * (1.0f - fy) + bot * fy;
-                const size_t o = ((size_t)y * dst.w + x) * 4;
-                if (t.isFloat)
-                {
-                    dst.rgbaf[o] = v.x;
-                    dst.rgbaf[o + 1] = v.y;
-                    dst.rgbaf[o + 2] = v.z;
-                    dst.rgbaf[o + 3] = v.w;
-                }
-                else
-                {
-                    dst.rgba8[o] = t.srgb ? encodeSrgb8(v.x) : encodeUnorm8(v.x);
-                    dst.rgba8[o + 1] = t.srgb ? encodeSrgb8(v.y) : encodeUnorm8(v.y);
-                    dst.rgba8[o + 2] = t.srgb ? encodeSrgb8(v.z) : encodeUnorm8(v.z);
-                    dst.rgba8[o + 3] = encodeUnorm8(v.w);
-                }
-            }
-        t.levels.push_back(std::move(dst));
-    }
+        t.levels.push_back(blitLinear(t, k - 1, std::max(1u, w >> k), std::max(1u, h >> k)));
 }
+
+/* TextureUploader::DetermineMaxTextureSizes + UploadTexture (TextureUploader.cpp:408-415, 551-569): the largest extent a
+ * texture may have — MaxTextureDataSize = 4096, halved while a full mip chain of that extent exceeds the per-texture
+ * share of the budget (0 = ForceFullTextureSize) — and the integer factor a larger texture is scaled down by. */
+struct TextureLimits
+{
+    uint32_t maxTextureSize = 4096;
+    uint64_t budgetBytes = 0;
+    uint32_t textureCount = 1;
+    uint32_t maxExtent(uint32_t bytesPerTexel) const
+    {
+        uint32_t extent = maxTextureSize;
+        if (budgetBytes == 0)
+            return extent;
+        const uint64_t perTexture = budgetBytes / std::max<uint64_t>(1, textureCount);
+        auto chainBytes = [&](uint32_t e) {
+            uint64_t n = 0;
+            for (uint32_t m = e;; m >>= 1)
+            {
+                n += (uint64_t)std::max(1u, m) * std::max(1u, m) * bytesPerTexel;
+                if (m <= 1)
+                    break;
+            }
+            return n;
+        };
+        while (extent > 1 && chainBytes(extent) > perTexture)
+            extent /= 2;
+        return extent;
+    }
+};
 
 /* Block-compressed formats (TextureFormat::BC1 / BC3 / BC5, PT/Scene.h:35-42; VK_FORMAT_BC1_RGBA /
  * BC3 / BC5 in PT/Renderer/TextureUploader.cpp:586-591), decoded per the format definition: 565
@@ -874,7 +908,7 @@ Texture makeBlockCompressedTexture(const pt_texture_desc &d)
     return t;
 }
 
-Texture makeTexture(const pt_texture_desc &d)
+Texture makeTexture(const pt_texture_desc &d, const TextureLimits *limits = nullptr)
 {
     if (d.format >= PT_TEXTURE_BC1)
         return makeBlockCompressedTexture(d);
@@ -890,6 +924,16 @@ Texture makeTexture(const pt_texture_desc &d)
     else
         l.rgba8.assign((const uint8_t *)d.pixels, (const uint8_t *)d.pixels + n);
     t.levels.push_back(std::move(l));
+    if (limits && !t.isFloat)
+    {
+        const uint32_t e = limits->maxExtent(4);
+        const uint32_t scale = std::max((d.width + e - 1) / e, (d.height + e - 1) / e);
+        if (scale > 1) /* linear blit of the full-size staging image into the smaller level 0 */
+        {
+            TexLevel small = blitLinear(t, 0, std::max(d.width / scale, 1u), std::max(d.height / scale, 1u));
+            t.levels[0] = std::move(small);
+        }
+    }
     buildMips(t);
     return t;
 }
@@ -2365,10 +2409,16 @@ vec4 debugPixel(const pto_scene &s, const pt_render_params &p, const pt_debug_pa
 
 extern "C" {
 
-pto_scene *pto_scene_create(const pt_scene_desc *d)
+pto_scene *pto_scene_create(const pt_scene_desc *d) { return pto_scene_create_limits(d, 4096, 0); }
+
+pto_scene *pto_scene_create_limits(const pt_scene_desc *d, uint32_t max_texture_size, uint64_t texture_budget_bytes)
 {
     if (!d)
         return nullptr;
+    TextureLimits limits;
+    limits.maxTextureSize = std::max(1u, max_texture_size);
+    limits.budgetBytes = texture_budget_bytes;
+    limits.textureCount = std::max(1u, d->texture_count);
     pto_scene *s = new pto_scene();
     s->vertices.assign(d->vertices, d->vertices + d->vertex_count);
     s->indices.assign(d->indices, d->indices + d->index_count);
@@ -2419,7 +2469,7 @@ pto_scene *pto_scene_create(const pt_scene_desc *d)
     s->textures.push_back(makeDefaultTexture(0x00000000u, false)); /* 7 shininess   */
     s->textures.push_back(makeDefaultTexture(0xffffffffu, true));  /* 8 placeholder */
     for (uint32_t i = 0; i < d->texture_count; i++)
-        s->textures.push_back(makeTexture(d->textures[i]));
+        s->textures.push_back(makeTexture(d->textures[i], &limits));
     if (d->skybox_2d)
     {
         s->hasSky2D = true;

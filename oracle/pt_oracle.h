@@ -42,6 +42,10 @@ typedef struct pto_counters {
 } pto_counters;
 
 PT_API pto_scene *pto_scene_create(const pt_scene_desc *scene);
+/* The same with TextureUploader's limits (TextureUploader.cpp:408-415, 551-569; like the core's tuning keys
+ * "max_texture_size" and "texture_budget_mb"): RGBA8 scene textures beyond the maximum extent are scaled down by an integer
+ * factor with a linear blit before their mips are generated.  pto_scene_create = (4096, 0 = ForceFullTextureSize). */
+PT_API pto_scene *pto_scene_create_limits(const pt_scene_desc *scene, uint32_t max_texture_size, uint64_t texture_budget_bytes);
 PT_API void pto_scene_destroy(pto_scene *scene);
 PT_API uint64_t pto_scene_triangle_count(const pto_scene *scene);
 /* Sampler state like pt_set_sampler: maximum anisotropy of textureGrad, 1 (isotropic trilinear, the default) .. 16 (what

@@ -1088,7 +1088,7 @@ pt_status uploadTextureSlot(Context *ctx, uint32_t slot, const pt_texture_desc *
         return fail(ctx, PT_ERR_INVALID_ARGUMENT, "pt_texture_upload", "slot out of range");
     DevTexture t;
     void *mem = nullptr;
-    const pt_status st = createTexture(ctx, *tex, t, &mem);
+    const pt_status st = createTexture(ctx, *tex, t, &mem, slot >= PT_SCENE_TEXTURE_OFFSET);
     if (st != PT_OK)
         return st;
     // the old allocation stays owned by the scene until the next scene upload
@@ -1219,6 +1219,7 @@ pt_status uploadScene(Context *ctx, const pt_scene_desc *d)
                     d->skybox_cube[f].format != d->skybox_cube[0].format)
                     return fail(ctx, PT_ERR_INVALID_ARGUMENT, "pt_scene_upload", "cube sky faces differ in size or format");
         ctx->hostTextures.resize(sceneSlots + (d->skybox_cube ? 6 : 0));
+        ctx->textureBudgetCount = std::max(1u, d->texture_count); // TextureUploader.cpp:554: the budget is shared by the scene's textures
         s.skyCubeSlot = d->skybox_cube ? sceneSlots : 0;
         for (uint32_t i = 0; i < ctx->hostTextures.size(); i++)
         {
@@ -1226,7 +1227,7 @@ pt_status uploadScene(Context *ctx, const pt_scene_desc *d)
                                          : i < sceneSlots            ? d->textures[i - PT_SCENE_TEXTURE_OFFSET]
                                                                      : d->skybox_cube[i - sceneSlots];
             void *mem = nullptr;
-            PT_TRY(createTexture(ctx, desc, ctx->hostTextures[i], &mem));
+            PT_TRY(createTexture(ctx, desc, ctx->hostTextures[i], &mem, i >= PT_SCENE_TEXTURE_OFFSET && i < sceneSlots));
             own.push_back(mem);
         }
         DevTexture *dt;

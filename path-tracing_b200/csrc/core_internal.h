@@ -126,6 +126,11 @@ struct Context
     uint32_t bvhBuilder = 1;  // 1 = PLOC (default), 0 = LBVH; PT_BVH / tuning key "bvh_builder"
     uint32_t plocRadius = 8;  // PLOC search window on either side; PT_PLOC_RADIUS / "ploc_radius"
     uint32_t bvhBuildPasses = 0;
+    // TextureUploader's limits: textures beyond maxTextureSize (MaxTextureDataSize = 4096, always) or beyond the per-texture share
+    // of textureBudgetBytes (0 = ForceFullTextureSize, the default on a 180 GB device) are scaled down at upload
+    uint32_t maxTextureSize = 4096;
+    uint64_t textureBudgetBytes = 0;
+    uint32_t textureBudgetCount = 1; // scene textures sharing the budget
     uint32_t maxAnisotropy = 1; // sampler state (pt_set_sampler): 1 = isotropic trilinear, 16 = the reference's sampler
     uint32_t bvhMaxDepth = 0; // levels of the wide BVH (the traversal stack holds at most 3 entries per level)
 
@@ -208,7 +213,7 @@ pt_status uploadTextureSlot(Context *ctx, uint32_t slot, const pt_texture_desc *
 pt_status updateScene(Context *ctx, const pt_scene_update_desc *desc);
 
 // textures.cu
-pt_status createTexture(Context *ctx, const pt_texture_desc &desc, DevTexture &out, void **outAlloc);
+pt_status createTexture(Context *ctx, const pt_texture_desc &desc, DevTexture &out, void **outAlloc, bool scalable = false);
 pt_texture_desc defaultTexture(const uint32_t *rgba, bool srgb);
 
 // wavefront.cu

@@ -435,6 +435,10 @@ pt_status pt_set_tuning(pt_context *ctx, const char *key, uint64_t value)
         ctx->bvhBuilder = value != 0;
     else if (k == "ploc_radius")
         ctx->plocRadius = (uint32_t)std::max<uint64_t>(1, value);
+    else if (k == "max_texture_size") // TextureUploader::MaxTextureDataSize (4096); takes effect at the next upload
+        ctx->maxTextureSize = (uint32_t)std::min<uint64_t>(32768, std::max<uint64_t>(1, value));
+    else if (k == "texture_budget_mb") // Config::MaxTextureMemoryBudget*; 0 = ForceFullTextureSize (default)
+        ctx->textureBudgetBytes = value << 20;
     else if (k == "sbuf_mb")
         ctx->sbufBudgetBytes = std::max<uint64_t>(1, value) << 20;
     else

@@ -56,11 +56,13 @@ __device__ __forceinline__ uint8_t encodeSrgb8(const float *lut, float v)
     return (uint8_t)lo;
 }
 
-// level k from level k-1: linear vkCmdBlitImage (PT/Renderer/Image.cpp:264-305)
-__global__ void k_mip(DevTexture t, const float *__restrict__ lut, uint32_t level)
+// Linear vkCmdBlitImage of one whole level into another (PT/Renderer/Image.cpp:264-305): level k from level k - 1 of
+// the same texture (mip generation), or a full-size staging image into the down-scaled level 0
+// (TextureUploader.cpp:408-415, 470-520: textures beyond the maximum texture size).
+__global__ void k_blit(DevTexture src, uint32_t srcLevel, DevTexture dst, uint32_t dstLevel, const float *__restrict__ lut)
 {
-    const uint32_t sw = max(1u, t.width >> (level - 1)), sh = max(1u, t.height >> (level - 1));
-    const uint32_t dw = max(1u, t.width >> level), dh = max(1u, t.height >> level);
+    const uint32_t sw = max(1u, src.width >> srcLevel), sh = max(1u, src.height >> srcLevel);
+    const uint32_t dw = max(1u, dst.width >> dstLevel), dh = max(1u, dst.height >> dstLevel);
     const uint32_t x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
     if (x >= dw || y >= dh)
         return;
@@ -71,25 +73,25 @@ __global__ void k_mip(DevTexture t, const float *__restrict__ lut, uint32_t leve
     const float fx = __fsub_rn(sx, fx0), fy = __fsub_rn(sy, fy0);
     const int x0 = min(max((int)fx0, 0), (int)sw - 1), x1 = min(max((int)fx0 + 1, 0), (int)sw - 1);
     const int y0 = min(max((int)fy0, 0), (int)sh - 1), y1 = min(max((int)fy0 + 1, 0), (int)sh - 1);
-    const float4 t00 = mipTexel(t, lut, level - 1, x0, y0, sw), t10 = mipTexel(t, lut, level - 1, x1, y0, sw);
-    const float4 t01 = mipTexel(t, lut, level - 1, x0, y1, sw), t11 = mipTexel(t, lut, level - 1, x1, y1, sw);
+    const float4 t00 = mipTexel(src, lut, srcLevel, x0, y0, sw), t10 = mipTexel(src, lut, srcLevel, x1, y0, sw);
+    const float4 t01 = mipTexel(src, lut, srcLevel, x0, y1, sw), t11 = mipTexel(src, lut, srcLevel, x1, y1, sw);
     float4 v;
     v.x = lerpExact(lerpExact(t00.x, t10.x, fx), lerpExact(t01.x, t11.x, fx), fy);
     v.y = lerpExact(lerpExact(t00.y, t10.y, fx), lerpExact(t01.y, t11.y, fx), fy);
     v.z = lerpExact(lerpExact(t00.z, t10.z, fx), lerpExact(t01.z, t11.z, fx), fy);
     v.w = lerpExact(lerpExact(t00.w, t10.w, fx), lerpExact(t01.w, t11.w, fx), fy);
-    const size_t idx = (size_t)t.levelOffset[level] + (size_t)y * dw + x;
-    if (t.flags & PT_TEX_FLAG_FLOAT)
+    const size_t idx = (size_t)dst.levelOffset[dstLevel] + (size_t)y * dw + x;
+    if (dst.flags & PT_TEX_FLAG_FLOAT)
     {
-        reinterpret_cast<float4 *>(t.base)[idx] = v;
+        reinterpret_cast<float4 *>(dst.base)[idx] = v;
         return;
     }
     uchar4 o;
-    if (t.flags & PT_TEX_FLAG_SRGB)
+    if (dst.flags & PT_TEX_FLAG_SRGB)
         o = make_uchar4(encodeSrgb8(lut, v.x), encodeSrgb8(lut, v.y), encodeSrgb8(lut, v.z), encodeUnorm8(v.w));
     else
         o = make_uchar4(encodeUnorm8(v.x), encodeUnorm8(v.y), encodeUnorm8(v.z), encodeUnorm8(v.w));
-    reinterpret_cast<uchar4 *>(t.base)[idx] = o;
+    reinterpret_cast<uchar4 *>(dst.base)[idx] = o;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -193,7 +195,30 @@ __global__ void k_bc_decode(const uint8_t *__restrict__ blocks, uint32_t format,
 
 } // namespace
 
-pt_status createTexture(Context *ctx, const pt_texture_desc &d, DevTexture &out, void **outAlloc)
+// TextureUploader::DetermineMaxTextureSizes (TextureUploader.cpp:551-569): 4096 (MaxTextureDataSize), halved while the full
+// mip chain of a texture of that extent exceeds the per-texture share of the budget (0 = ForceFullTextureSize)
+uint32_t maxTextureExtent(Context *ctx, uint32_t bytesPerTexel, bool scalable)
+{
+    uint32_t extent = ctx->maxTextureSize;
+    if (!scalable || ctx->textureBudgetBytes == 0)
+        return extent;
+    const uint64_t perTexture = ctx->textureBudgetBytes / std::max<uint64_t>(1, ctx->textureBudgetCount);
+    auto chainBytes = [&](uint32_t e) {
+        uint64_t n = 0;
+        for (uint32_t m = e;; m >>= 1)
+        {
+            n += (uint64_t)std::max(1u, m) * std::max(1u, m) * bytesPerTexel;
+            if (m <= 1)
+                break;
+        }
+        return n;
+    };
+    while (extent > 1 && chainBytes(extent) > perTexture)
+        extent /= 2;
+    return extent;
+}
+
+pt_status createTexture(Context *ctx, const pt_texture_desc &d, DevTexture &out, void **outAlloc, bool scalable)
 {
     if (d.width == 0 || d.height == 0 || !d.pixels)
         return fail(ctx, PT_ERR_INVALID_ARGUMENT, "texture", "empty texture");
@@ -252,12 +277,19 @@ pt_status createTexture(Context *ctx, const pt_texture_desc &d, DevTexture &out,
         return PT_OK;
     }
     DevTexture t = {};
-    t.width = d.width;
-    t.height = d.height;
     t.flags = d.format == PT_TEXTURE_RGBAF32 ? PT_TEX_FLAG_FLOAT : (d.srgb ? PT_TEX_FLAG_SRGB : 0u);
+    // TextureUploader::UploadTexture (TextureUploader.cpp:408-415): textures beyond the maximum extent are scaled down by
+    // an integer factor with a linear blit before their mips are generated
+    const uint32_t maxExtent = maxTextureExtent(ctx, (t.flags & PT_TEX_FLAG_FLOAT) ? 16 : 4, scalable);
+    const uint32_t scale = std::max((d.width + maxExtent - 1) / maxExtent, (d.height + maxExtent - 1) / maxExtent);
+    if (scale > 1 && (t.flags & PT_TEX_FLAG_FLOAT))
+        return fail(ctx, PT_ERR_UNSUPPORTED, "texture", "a float texture exceeds the maximum texture size and its format cannot be "
+                                                        "scaled (TextureUploader.cpp:466-480: the reference rejects it too)");
+    t.width = std::max(d.width / scale, 1u);
+    t.height = std::max(d.height / scale, 1u);
     // floor(log2(max(w, h))) + 1 levels (PT/Renderer/Image.cpp:14-17)
     uint32_t levels = 1;
-    for (uint32_t m = std::max(d.width, d.height); m > 1; m >>= 1)
+    for (uint32_t m = std::max(t.width, t.height); m > 1; m >>= 1)
         levels++;
     if (levels > PT_MAX_TEX_LEVELS)
         return fail(ctx, PT_ERR_UNSUPPORTED, "texture", "texture larger than 32768 texels per side");
@@ -266,20 +298,45 @@ pt_status createTexture(Context *ctx, const pt_texture_desc &d, DevTexture &out,
     for (uint32_t l = 0; l < levels; l++)
     {
         t.levelOffset[l] = (uint32_t)texels;
-        texels += (uint64_t)std::max(1u, d.width >> l) * std::max(1u, d.height >> l);
+        texels += (uint64_t)std::max(1u, t.width >> l) * std::max(1u, t.height >> l);
     }
     const uint64_t bpp = (t.flags & PT_TEX_FLAG_FLOAT) ? 16 : 4;
     void *mem = nullptr;
     PT_CUDA_CHECK(ctx, cudaMalloc(&mem, texels * bpp));
     t.base = (uint64_t)mem;
-    PT_CUDA_CHECK(ctx, cudaMemcpyAsync(mem, d.pixels, (uint64_t)d.width * d.height * bpp, cudaMemcpyHostToDevice, ctx->stream));
+    void *staging = nullptr;
+    if (scale > 1)
+    {
+        DevTexture full = {};
+        full.width = d.width, full.height = d.height, full.levels = 1, full.flags = t.flags;
+        cudaError_t err = cudaMalloc(&staging, (uint64_t)d.width * d.height * bpp);
+        if (err == cudaSuccess)
+            err = cudaMemcpyAsync(staging, d.pixels, (uint64_t)d.width * d.height * bpp, cudaMemcpyHostToDevice, ctx->stream);
+        if (err != cudaSuccess)
+        {
+            cudaFree(staging);
+            cudaFree(mem);
+            PT_CUDA_CHECK(ctx, err);
+        }
+        full.base = (uint64_t)staging;
+        const dim3 block(16, 16), grid((t.width + 15) / 16, (t.height + 15) / 16);
+        k_blit<<<grid, block, 0, ctx->stream>>>(full, 0, t, 0, ctx->dLut);
+    }
+    else
+        PT_CUDA_CHECK(ctx, cudaMemcpyAsync(mem, d.pixels, (uint64_t)d.width * d.height * bpp, cudaMemcpyHostToDevice, ctx->stream));
     for (uint32_t l = 1; l < levels; l++)
     {
-        const uint32_t dw = std::max(1u, d.width >> l), dh = std::max(1u, d.height >> l);
+        const uint32_t dw = std::max(1u, t.width >> l), dh = std::max(1u, t.height >> l);
         const dim3 block(16, 16), grid((dw + 15) / 16, (dh + 15) / 16);
-        k_mip<<<grid, block, 0, ctx->stream>>>(t, ctx->dLut, l);
+        k_blit<<<grid, block, 0, ctx->stream>>>(t, l - 1, t, l, ctx->dLut);
     }
-    PT_CUDA_CHECK(ctx, cudaGetLastError());
+    if (cudaGetLastError() != cudaSuccess || cudaStreamSynchronize(ctx->stream) != cudaSuccess)
+    {
+        cudaFree(staging);
+        cudaFree(mem);
+        return fail(ctx, PT_ERR_CUDA, "texture", "mip generation failed");
+    }
+    cudaFree(staging);
     // the host pixels may be released as soon as we return
     PT_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
     out = t;

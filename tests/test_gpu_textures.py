@@ -109,3 +109,18 @@ def test_anisotropic_sampler_flag(default_scene, oracle_mod):
         assert metrics.close_fraction(img, ref_iso, 1e-4) < 0.99  # and it is not the isotropic image
         with pytest.raises(core.PtError):
             r.set_sampler(0)
+
+
+def test_texture_size_limits(default_scene, oracle_mod):
+    """Tuning keys max_texture_size / texture_budget_mb = TextureUploader's limits: the down-scaled textures and their mip
+    chains equal the oracle's (blit arithmetic bit for bit), through the sampler probe."""
+    rec = _records(np.random.default_rng(5), 2000)
+    for kwargs, extent0 in (({"max_texture_size": 512}, (512, 512)), ({"texture_budget_mb": 4}, (256, 256))):
+        ora = oracle_mod.OracleScene(default_scene, **kwargs)
+        with core.Renderer(0) as r:
+            for k, v in kwargs.items():
+                r.set_tuning(k, v)
+            r.update_scene_data(default_scene)
+            assert ora.texture_info(sc.SCENE_TEXTURE_OFFSET)[:2] == extent0
+            for slot in range(sc.SCENE_TEXTURE_OFFSET, sc.SCENE_TEXTURE_OFFSET + len(default_scene.textures)):
+                _check(r, ora, slot, rec)

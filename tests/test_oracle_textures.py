@@ -118,3 +118,22 @@ def test_anisotropic_footprint_closed_form(default_scene, oracle_mod):
     top = o.texture_level(slot, 6).astype(np.float64)
     assert not np.allclose(blurry, got, atol=1e-3)
     assert np.abs(blurry[:3] - bilinear(np.concatenate([srgb_to_linear(top[..., :3]), top[..., 3:] / 255], -1), *uv)[:3]).max() < 1e-5
+
+
+def test_textures_beyond_the_maximum_size_are_scaled_down(default_scene, oracle_mod):
+    """TextureUploader::UploadTexture (TextureUploader.cpp:408-415): scale = max(ceil(w / max), ceil(h / max)), extent =
+    (w / scale, h / scale), a linear blit of the full image; then the usual mip chain.  MaxTextureDataSize is 4096 in the
+    reference; the limit is lowered here so that the 1024 / 512 / 2024-pixel Default-scene textures exercise it."""
+    full = oracle_mod.OracleScene(default_scene)
+    small = oracle_mod.OracleScene(default_scene, max_texture_size=512)
+    base = sc.SCENE_TEXTURE_OFFSET
+    assert full.texture_info(base + 0)[:2] == (1024, 1024) and small.texture_info(base + 0) == (512, 512, 10)  # scale 2
+    assert small.texture_info(base + 1) == full.texture_info(base + 1)                                         # fits
+    assert full.texture_info(base + 3)[:2] == (2024, 2024) and small.texture_info(base + 3) == (506, 506, 9)   # scale 4
+    # scale 2 of an even extent = the 2 x 2 box filter = level 1 of the full-size chain, and so on down the chain
+    for level in range(3):
+        assert np.array_equal(small.texture_level(base + 0, level), full.texture_level(base + 0, level + 1))
+    # the budget: 4 scene textures sharing 4 MB -> 1 MB each -> largest extent whose full RGBA8 chain fits: 256
+    tight = oracle_mod.OracleScene(default_scene, texture_budget_mb=4)
+    assert tight.texture_info(base + 0)[:2] == (256, 256) and tight.texture_info(base + 1)[:2] == (256, 256)
+    assert tight.texture_info(base + 3)[:2] == (253, 253)  # 2024 / ceil(2024 / 256 = 7.9) = 2024 / 8
