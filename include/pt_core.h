@@ -342,6 +342,8 @@ typedef struct pt_stats {
     uint64_t warp_iterations;
     uint64_t warp_drain_iterations;
     uint64_t max_warp_drain_iterations;
+    uint64_t bvh_reference_count; /* leaf entries of the BVH: >= triangle_count (a large diagonal triangle enters the BVH
+                                     as several references to the same triangle, bvh_build.cu k_split_*)            */
     uint32_t bvh_max_depth;   /* levels of the wide BVH of the uploaded scene                                     */
     uint32_t stack_overflows; /* entries the traversal stack could not hold in the last call: non-zero FAILS the
                                  call (PT_ERR_UNSUPPORTED) — a dropped entry is a skipped sub-tree              */

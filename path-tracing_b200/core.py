@@ -115,6 +115,7 @@ class Stats(C.Structure):
         ("warp_iterations", C.c_uint64),
         ("warp_drain_iterations", C.c_uint64),
         ("max_warp_drain_iterations", C.c_uint64),
+        ("bvh_reference_count", C.c_uint64),
         ("bvh_max_depth", C.c_uint32),
         ("stack_overflows", C.c_uint32),
     ]

@@ -224,6 +224,97 @@ __global__ void k_morton(const Aabb *__restrict__ boxes, uint32_t n, const uint3
 }
 
 // ---------------------------------------------------------------------------------------------
+// Reference splitting (early split clipping, Ernst & Greiner 2007, in the midpoint-subdivision form).
+// A triangle whose bounding box is large compared with the space a primitive has in this scene — a big
+// triangle lying diagonally, e.g. the randomly oriented alpha-tested cards of foliage — makes every
+// box around it mostly empty, and in a dense soup of such triangles every ray walks through hundreds of
+// overlapping boxes.  Such a triangle enters the BVH as 4^L REFERENCES, one per piece of its L-fold
+// midpoint subdivision, each with the (slightly padded) box of its piece; all of them carry the PARENT's
+// three corners, so the ray / triangle arithmetic, hit distances, barycentrics and ids are exactly what
+// they are without splitting (a parent reached through two references is the same candidate twice: the
+// closest-hit rule "t < best, or the same t and a smaller id" drops the repeat).
+// ---------------------------------------------------------------------------------------------
+#define PT_SPLIT_MAX_LEVEL 3
+
+__global__ void k_split_count(const Aabb *__restrict__ boxes, uint32_t n, const uint32_t *__restrict__ sceneBounds, float threshold,
+                              uint32_t *__restrict__ refCount)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n)
+        return;
+    // the space one primitive has: the volume of the scene (centroid bounds, padded) over the primitive count
+    float ext[3];
+    for (int j = 0; j < 3; j++)
+        ext[j] = fmaxf(floatUnflip(sceneBounds[3 + j]) - floatUnflip(sceneBounds[j]), 1e-20f);
+    const float share = ext[0] * ext[1] * ext[2] / (float)n;
+    const Aabb b = boxes[i];
+    const float v = (b.hi[0] - b.lo[0]) * (b.hi[1] - b.lo[1]) * (b.hi[2] - b.lo[2]);
+    // every level of subdivision divides the box volume of a piece by 8 (and the summed volume by 2)
+    uint32_t level = 0;
+    float r = v / share;
+    while (level < PT_SPLIT_MAX_LEVEL && r > threshold && isfinite(r))
+    {
+        level++;
+        r *= 0.125f;
+    }
+    refCount[i] = 1u << (2 * level);
+}
+
+__global__ void k_split_emit(const float4 *__restrict__ triPos, const Aabb *__restrict__ boxes, uint32_t n,
+                             const uint32_t *__restrict__ refCount, const uint32_t *__restrict__ refOffset, Aabb *__restrict__ refBoxes,
+                             uint32_t *__restrict__ refTri)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n)
+        return;
+    const uint32_t count = refCount[i], first = refOffset[i];
+    if (count == 1)
+    {
+        refBoxes[first] = boxes[i];
+        refTri[first] = i;
+        return;
+    }
+    const float4 q0 = triPos[3 * (size_t)i], q1 = triPos[3 * (size_t)i + 1], q2 = triPos[3 * (size_t)i + 2];
+    const Aabb parent = boxes[i];
+    for (uint32_t k = 0; k < count; k++)
+    {
+        float a[3] = { q0.x, q0.y, q0.z }, b[3] = { q1.x, q1.y, q1.z }, c[3] = { q2.x, q2.y, q2.z };
+        // base-4 digits of k, most significant first: 0, 1, 2 = the corner piece at a, b, c; 3 = the middle piece
+        for (uint32_t div = count >> 2; div >= 1; div >>= 2)
+        {
+            const uint32_t digit = (k / div) & 3u;
+            float ab[3], bc[3], ca[3];
+            for (int j = 0; j < 3; j++)
+            {
+                ab[j] = 0.5f * (a[j] + b[j]);
+                bc[j] = 0.5f * (b[j] + c[j]);
+                ca[j] = 0.5f * (c[j] + a[j]);
+            }
+            for (int j = 0; j < 3; j++)
+            {
+                const float na = digit == 0 ? a[j] : digit == 1 ? ab[j] : digit == 2 ? ca[j] : ab[j];
+                const float nb = digit == 0 ? ab[j] : digit == 1 ? b[j] : digit == 2 ? bc[j] : bc[j];
+                const float nc = digit == 0 ? ca[j] : digit == 1 ? bc[j] : digit == 2 ? c[j] : ca[j];
+                a[j] = na, b[j] = nb, c[j] = nc;
+            }
+            if (div == 1)
+                break;
+        }
+        Aabb r;
+        for (int j = 0; j < 3; j++)
+        {
+            const float lo = fminf(a[j], fminf(b[j], c[j])), hi = fmaxf(a[j], fmaxf(b[j], c[j]));
+            // the computed midpoints are within an ulp of the true edges: pad, and never beyond the parent's box
+            const float pad = 4.0f * 1.1920929e-7f * fmaxf(fabsf(lo), fabsf(hi)) + 1e-30f;
+            r.lo[j] = fmaxf(lo - pad, parent.lo[j]);
+            r.hi[j] = fminf(hi + pad, parent.hi[j]);
+        }
+        refBoxes[first + k] = r;
+        refTri[first + k] = i;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // LBVH (Karras 2012).  Nodes 0..n-2 internal, n-1..2n-2 leaves (leaf k <-> sorted primitive k).
 // ---------------------------------------------------------------------------------------------
 struct Bvh2
@@ -644,17 +735,20 @@ __global__ void k_single_leaf_root(const Aabb *__restrict__ primBoxes, const uin
     writeWideNode(nodes, lo, hi, ref, 1);
 }
 
-__global__ void k_gather(const uint32_t *__restrict__ sortedIdx, uint32_t n, const float4 *__restrict__ posIn,
-                         const TriShade *__restrict__ shadeIn, float4 *__restrict__ posOut, TriShade *__restrict__ shadeOut)
+__global__ void k_gather(const uint32_t *__restrict__ sortedIdx, const uint32_t *__restrict__ refTri, uint32_t n,
+                         const float4 *__restrict__ posIn, const TriShade *__restrict__ shadeIn, float4 *__restrict__ posOut,
+                         TriShade *__restrict__ shadeOut)
 {
     const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= n)
         return;
-    const uint32_t src = sortedIdx[k];
+    // leaf-order position k holds reference sortedIdx[k], i.e. (a copy of) its parent triangle
+    const uint32_t src = refTri ? refTri[sortedIdx[k]] : sortedIdx[k];
     posOut[3 * (size_t)k + 0] = posIn[3 * (size_t)src + 0];
     posOut[3 * (size_t)k + 1] = posIn[3 * (size_t)src + 1];
     posOut[3 * (size_t)k + 2] = posIn[3 * (size_t)src + 2];
-    shadeOut[k] = shadeIn[src];
+    if (shadeOut)
+        shadeOut[k] = shadeIn[src];
 }
 
 
@@ -789,14 +883,19 @@ pt_status buildAccel(Context *ctx, const std::vector<MeshInstance> &mis, uint32_
         uint32_t *sceneBounds;
         PT_TRY(devAllocPool(ctx, &dMis, mis.size(), temp));
         PT_TRY(devAllocPool(ctx, &posUnsorted, (size_t)n * 3, temp));
+#if PT_SHADE_BY_FLAT
+        PT_TRY(devAllocPool(ctx, &shadeUnsorted, (size_t)n, ctx->accelAllocs)); // stays: the scene's shading records
+#else
         PT_TRY(devAllocPool(ctx, &shadeUnsorted, (size_t)n, temp));
+#endif
         PT_TRY(devAllocPool(ctx, &primBoxes, (size_t)n, temp));
         PT_TRY(devAllocPool(ctx, &sceneBounds, 7, temp)); // 6 bounds + the bad-index counter of k_bake
         PT_CUDA_CHECK(ctx, cudaMemcpyAsync(dMis, mis.data(), mis.size() * sizeof(MeshInstance), cudaMemcpyHostToDevice, ctx->stream));
         const uint32_t boundsInit[7] = { 0xffffffffu, 0xffffffffu, 0xffffffffu, 0u, 0u, 0u, 0u };
         PT_CUDA_CHECK(ctx, cudaMemcpyAsync(sceneBounds, boundsInit, sizeof(boundsInit), cudaMemcpyHostToDevice, ctx->stream));
         PT_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
-        const uint32_t T = 256, G = (n + T - 1) / T;
+        const uint32_t T = 256;
+        uint32_t G = (n + T - 1) / T;
         k_bake<<<G, T, 0, ctx->stream>>>(dMis, (uint32_t)mis.size(), dVertices, dIndices, n, posUnsorted, shadeUnsorted,
                                          primBoxes, sceneBounds, sceneBounds + 6);
         {
@@ -809,6 +908,37 @@ pt_status buildAccel(Context *ctx, const std::vector<MeshInstance> &mis, uint32_
                 return fail(ctx, PT_ERR_INVALID_ARGUMENT, "pt_scene_upload", "an index is not below its geometry's vertex_length");
             }
         }
+
+        // ---- reference splitting (k_split_*): from here on `n` counts references ---------------------
+        uint32_t *refTri = nullptr;
+        ctx->triangleCount = n;
+        if (ctx->splitThreshold > 0.0f && n > PT_MAX_LEAF_TRIS)
+        {
+            uint32_t *refCount, *refOffset;
+            PT_TRY(devAllocPool(ctx, &refCount, (size_t)n + 1, temp));
+            PT_TRY(devAllocPool(ctx, &refOffset, (size_t)n + 1, temp));
+            PT_CUDA_CHECK(ctx, cudaMemsetAsync(refCount + n, 0, 4, ctx->stream));
+            k_split_count<<<G, T, 0, ctx->stream>>>(primBoxes, n, sceneBounds, ctx->splitThreshold, refCount);
+            size_t scanBytes = 0;
+            cub::DeviceScan::ExclusiveSum(nullptr, scanBytes, refCount, refOffset, (int)n + 1, ctx->stream);
+            uint8_t *scanTemp;
+            PT_TRY(devAllocPool(ctx, &scanTemp, scanBytes, temp));
+            PT_CUDA_CHECK(ctx, cub::DeviceScan::ExclusiveSum(scanTemp, scanBytes, refCount, refOffset, (int)n + 1, ctx->stream));
+            uint32_t total = 0;
+            PT_CUDA_CHECK(ctx, cudaMemcpyAsync(&total, refOffset + n, 4, cudaMemcpyDeviceToHost, ctx->stream));
+            PT_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+            if (total > n && (uint64_t)total < (1ull << 29))
+            {
+                Aabb *refBoxes;
+                PT_TRY(devAllocPool(ctx, &refBoxes, (size_t)total, temp));
+                PT_TRY(devAllocPool(ctx, &refTri, (size_t)total, temp));
+                k_split_emit<<<G, T, 0, ctx->stream>>>(posUnsorted, primBoxes, n, refCount, refOffset, refBoxes, refTri);
+                primBoxes = refBoxes;
+                n = total;
+                G = (n + T - 1) / T;
+            }
+        }
+        s.triCount = n;
 
         // ---- Morton codes + sort ------------------------------------------------------------
         uint64_t *keysIn, *keysOut;
@@ -931,8 +1061,13 @@ pt_status buildAccel(Context *ctx, const std::vector<MeshInstance> &mis, uint32_
         float4 *triPos;
         TriShade *triShade;
         PT_TRY(devAllocPool(ctx, &triPos, (size_t)n * 3, ctx->accelAllocs));
+#if PT_SHADE_BY_FLAT
+        triShade = shadeUnsorted;
+        k_gather<<<G, T, 0, ctx->stream>>>(order, refTri, n, posUnsorted, shadeUnsorted, triPos, nullptr);
+#else
         PT_TRY(devAllocPool(ctx, &triShade, (size_t)n, ctx->accelAllocs));
-        k_gather<<<G, T, 0, ctx->stream>>>(order, n, posUnsorted, shadeUnsorted, triPos, triShade);
+        k_gather<<<G, T, 0, ctx->stream>>>(order, refTri, n, posUnsorted, shadeUnsorted, triPos, triShade);
+#endif
         s.triPos = triPos;
         s.triShade = triShade;
         BvhNode *nodes;
@@ -940,7 +1075,12 @@ pt_status buildAccel(Context *ctx, const std::vector<MeshInstance> &mis, uint32_
         PT_CUDA_CHECK(ctx, cudaMemcpyAsync(nodes, wide, (size_t)wideCount * sizeof(BvhNode), cudaMemcpyDeviceToDevice, ctx->stream));
         s.nodes = nodes;
         ctx->nodeCount = wideCount;
+#if PT_SHADE_BY_FLAT
+        ctx->bvhBytes = (uint64_t)wideCount * sizeof(BvhNode) + (uint64_t)n * 48 + ctx->triangleCount * 144;
+#else
         ctx->bvhBytes = (uint64_t)wideCount * sizeof(BvhNode) + (uint64_t)n * (48 + 144);
+#endif
+        ctx->referenceCount = n;
     }
     PT_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
     PT_CUDA_CHECK(ctx, cudaGetLastError());
@@ -1271,7 +1411,7 @@ pt_status uploadScene(Context *ctx, const pt_scene_desc *d)
         }
     }
 
-    s.triCount = n;
+    // (s.triCount was set by buildAccel: the number of leaf entries = references)
     s.hasAlpha = hasAlpha ? 1u : 0u;
     s.maxAnisotropy = ctx->maxAnisotropy;
     // vertices and indices stay on the device: pt_scene_update re-bakes from them.  Skinned vertices and

@@ -132,6 +132,10 @@ struct Context
     uint64_t textureBudgetBytes = 0;
     uint32_t textureBudgetCount = 1; // scene textures sharing the budget
     uint32_t maxAnisotropy = 1; // sampler state (pt_set_sampler): 1 = isotropic trilinear, 16 = the reference's sampler
+    // reference splitting (bvh_build.cu k_split_*): a triangle whose box volume exceeds splitThreshold x the scene volume per
+    // primitive enters the BVH as 4^L references; 0 = off.  Tuning key "split_threshold_x100" / PT_SPLIT.
+    float splitThreshold = 4.0f;
+    uint64_t triangleCount = 0, referenceCount = 0;
     uint32_t bvhMaxDepth = 0; // levels of the wide BVH (the traversal stack holds at most 3 entries per level)
 
     // target

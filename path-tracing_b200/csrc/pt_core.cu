@@ -96,6 +96,8 @@ pt_status pt_context_create(int32_t cuda_device, pt_context **out_ctx)
         ctx->bvhBuilder = std::atoi(e) != 0;
     if (const char *e = std::getenv("PT_PLOC_RADIUS"))
         ctx->plocRadius = (uint32_t)std::max(1, std::atoi(e));
+    if (const char *e = std::getenv("PT_SPLIT")) // reference-splitting threshold (0 = off)
+        ctx->splitThreshold = (float)std::atof(e);
     if (const char *e = std::getenv("PT_MAX_ANISOTROPY")) // A/B measurements; pt_set_sampler is the API
         ctx->maxAnisotropy = (uint32_t)std::min(16, std::max(1, std::atoi(e)));
     if (const char *e = std::getenv("PT_SBUF_MB"))
@@ -383,7 +385,8 @@ pt_status pt_get_stats(pt_context *ctx, pt_stats *out)
     s.warp_iterations = c.warpIters;
     s.warp_drain_iterations = c.warpDrainIters;
     s.max_warp_drain_iterations = c.maxWarpDrainIters;
-    s.triangle_count = ctx->scene.triCount;
+    s.triangle_count = ctx->scene.triCount ? ctx->triangleCount : 0;
+    s.bvh_reference_count = ctx->scene.triCount;
     s.bvh_node_count = ctx->nodeCount;
     s.bvh_bytes = ctx->bvhBytes;
     s.bvh_max_depth = ctx->bvhMaxDepth;
@@ -435,6 +438,8 @@ pt_status pt_set_tuning(pt_context *ctx, const char *key, uint64_t value)
         ctx->bvhBuilder = value != 0;
     else if (k == "ploc_radius")
         ctx->plocRadius = (uint32_t)std::max<uint64_t>(1, value);
+    else if (k == "split_threshold_x100") // reference splitting; takes effect at the next upload / update
+        ctx->splitThreshold = (float)value / 100.0f;
     else if (k == "max_texture_size") // TextureUploader::MaxTextureDataSize (4096); takes effect at the next upload
         ctx->maxTextureSize = (uint32_t)std::min<uint64_t>(32768, std::max<uint64_t>(1, value));
     else if (k == "texture_budget_mb") // Config::MaxTextureMemoryBudget*; 0 = ForceFullTextureSize (default)

@@ -59,6 +59,19 @@ static_assert(sizeof(BvhNode) == 128, "BvhNode must be one 128-byte line");
 
 PT_HD int encodeLeaf(uint32_t first, uint32_t count) { return ~(int)((first << 2) | (count - 1)); }
 
+// The shading records (TriShade, 144 B) stay in FLATTENED triangle order and are reached through the flat id a leaf entry
+// carries (triPos[3 * k].w) — one record per triangle however many references the BVH holds to it (1) — or are copied into
+// leaf order next to the positions (0: 192 B per leaf entry, the round-1 layout).
+#ifndef PT_SHADE_BY_FLAT
+#define PT_SHADE_BY_FLAT 1
+#endif
+// index of the shading record of leaf entry `tri` whose first position word is q0
+#if PT_SHADE_BY_FLAT
+#define PT_SHADE_INDEX(tri, q0w) (__float_as_uint(q0w))
+#else
+#define PT_SHADE_INDEX(tri, q0w) (tri)
+#endif
+
 #define PT_TRI_FLAG_OPAQUE 1u
 #define PT_TRI_FLAG_MIRRORED 2u // the instance transform has a negative determinant: object-space winding = world-space winding reversed
 

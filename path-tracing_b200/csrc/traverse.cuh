@@ -183,9 +183,9 @@ PT_DEV bool intersectTriangle(const RaySetup &r, vec3 p0, vec3 p1, vec3 p2, floa
 }
 
 // colour texture x colour factor at a candidate hit (anyhit.rahit:36-51, occlusionAnyhit.rahit:35-50)
-PT_DEV float4 anyHitColor(const DeviceScene &s, uint32_t tri, uint32_t materialId, float b1, float b2)
+PT_DEV float4 anyHitColor(const DeviceScene &s, uint32_t shadeIndex, uint32_t materialId, float b1, float b2)
 {
-    const TriShade &ts = s.triShade[tri];
+    const TriShade &ts = s.triShade[shadeIndex];
     const float4 a6 = __ldg(&ts.a[6]), a7 = __ldg(&ts.a[7]), a8 = __ldg(&ts.a[8]);
     const float b0 = 1.0f - b1 - b2;
     const float u = a6.w * b0 + a7.y * b1 + a7.w * b2;
@@ -524,7 +524,7 @@ template <bool CLOSEST, bool ALPHA, bool STATS, int SMEM = 0, bool CULL = false>
                 {
                     if (STATS)
                         st.alphaTests++;
-                    const float4 color = anyHitColor(s, tri, __float_as_uint(q2.w), b1, b2);
+                    const float4 color = anyHitColor(s, PT_SHADE_INDEX(tri, q0.w), __float_as_uint(q2.w), b1, b2);
                     if (CLOSEST)
                     {
                         if (color.w < 0.5f)

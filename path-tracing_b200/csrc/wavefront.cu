@@ -421,7 +421,7 @@ template <bool ALPHA, bool STATS> __global__ void __launch_bounds__(128, PT_SHAD
         // ---- closestHit.rchit:54-83 with baked world-space data ---------------------------------
         const float4 q0 = __ldg(s.triPos + 3 * (size_t)tri), q1 = __ldg(s.triPos + 3 * (size_t)tri + 1);
         const float4 q2 = __ldg(s.triPos + 3 * (size_t)tri + 2);
-        const TriShade &ts = s.triShade[tri];
+        const TriShade &ts = s.triShade[PT_SHADE_INDEX(tri, q0.w)];
         const float4 a0 = __ldg(&ts.a[0]), a1 = __ldg(&ts.a[1]), a2 = __ldg(&ts.a[2]), a3 = __ldg(&ts.a[3]);
         const float4 a4 = __ldg(&ts.a[4]), a5 = __ldg(&ts.a[5]), a6 = __ldg(&ts.a[6]), a7 = __ldg(&ts.a[7]);
         const float4 a8 = __ldg(&ts.a[8]);
@@ -655,7 +655,7 @@ __device__ __forceinline__ pt_hit toPtHit(const DeviceScene &s, const Hit &h)
         r.t = r.u = r.v = 0.0f;
         return r;
     }
-    const float4 a8 = __ldg(&s.triShade[h.tri].a[8]);
+    const float4 a8 = __ldg(&s.triShade[PT_SHADE_INDEX(h.tri, __ldg(s.triPos + 3 * (size_t)h.tri).w)].a[8]);
     r.instance = __float_as_uint(a8.y);
     r.geometry = __float_as_uint(a8.z);
     r.primitive = __float_as_uint(a8.w);
@@ -759,7 +759,7 @@ __global__ void k_debug(DeviceScene s, CameraMatrices cam, uint32_t width, uint3
     const vec3 bary = V3(1.0f - hit.b1 - hit.b2, hit.b1, hit.b2);
     const float4 q0 = __ldg(s.triPos + 3 * (size_t)tri), q1 = __ldg(s.triPos + 3 * (size_t)tri + 1);
     const float4 q2 = __ldg(s.triPos + 3 * (size_t)tri + 2);
-    const TriShade &ts = s.triShade[tri];
+    const TriShade &ts = s.triShade[PT_SHADE_INDEX(tri, q0.w)];
     const float4 a0 = __ldg(&ts.a[0]), a1 = __ldg(&ts.a[1]), a2 = __ldg(&ts.a[2]), a3 = __ldg(&ts.a[3]);
     const float4 a4 = __ldg(&ts.a[4]), a5 = __ldg(&ts.a[5]), a6 = __ldg(&ts.a[6]), a7 = __ldg(&ts.a[7]);
     const float4 a8 = __ldg(&ts.a[8]);
