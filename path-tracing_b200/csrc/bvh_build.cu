@@ -1271,10 +1271,7 @@ pt_status uploadScene(Context *ctx, const pt_scene_desc *d)
             cudaFree(p);
         temp.clear();
     };
-    cudaEvent_t ev0, ev1, ev2;
-    cudaEventCreate(&ev0);
-    cudaEventCreate(&ev1);
-    cudaEventCreate(&ev2);
+    ScopedEvent ev0, ev1, ev2; // destroyed on every (error) path out of this function
     cudaEventRecord(ev0, ctx->stream);
 
 #define PT_TRY(expr)                                                                                                  \
@@ -1452,9 +1449,6 @@ pt_status uploadScene(Context *ctx, const pt_scene_desc *d)
     freeTemp();
     cudaEventElapsedTime(&ctx->sceneUploadMs, ev0, ev2);
     cudaEventElapsedTime(&ctx->bvhBuildMs, ev1, ev2);
-    cudaEventDestroy(ev0);
-    cudaEventDestroy(ev1);
-    cudaEventDestroy(ev2);
     ctx->hasScene = true;
     ctx->sceneUpdates = 0;
     return PT_OK;

@@ -201,6 +201,21 @@ struct DeviceGuard
     DeviceGuard &operator=(const DeviceGuard &) = delete;
 };
 
+// a CUDA event that is destroyed on every path out of a function
+struct ScopedEvent
+{
+    cudaEvent_t ev = nullptr;
+    ScopedEvent() { cudaEventCreate(&ev); }
+    ~ScopedEvent()
+    {
+        if (ev)
+            cudaEventDestroy(ev);
+    }
+    ScopedEvent(const ScopedEvent &) = delete;
+    ScopedEvent &operator=(const ScopedEvent &) = delete;
+    operator cudaEvent_t() const { return ev; }
+};
+
 // stream-ordered allocation from the context's private pool
 inline cudaError_t poolAlloc(Context *ctx, void **ptr, size_t bytes, cudaStream_t stream)
 {

@@ -1035,6 +1035,34 @@ pt_status renderFrames(Context *ctx, const pt_render_params *params, uint32_t fi
         cudaEvent_t a, b;
     };
     std::vector<Timed> timed;
+    // every path out of this function — PT_CUDA_CHECK returns early on an error — destroys the timing events still
+    // alive and, if the render did not finish, waits for what the pools' streams were already given
+    bool finished = false;
+    struct Cleanup
+    {
+        Context *ctx;
+        std::vector<Timed> &timed;
+        bool &finished;
+        ~Cleanup()
+        {
+            for (Timed &t : timed)
+            {
+                if (t.a)
+                    cudaEventDestroy(t.a);
+                if (t.b)
+                    cudaEventDestroy(t.b);
+            }
+            timed.clear();
+            if (!finished)
+            {
+                for (int i = 0; i < PT_MAX_POOLS; i++)
+                    if (ctx->poolStreams[i])
+                        cudaStreamSynchronize(ctx->poolStreams[i]);
+                cudaStreamSynchronize(ctx->stream);
+                cudaGetLastError();
+            }
+        }
+    } cleanup { ctx, timed, finished };
     const bool timing = ctx->kernelTiming;
     auto begin = [&](int cls, cudaStream_t st) {
         if (!timing)
@@ -1248,14 +1276,13 @@ pt_status renderFrames(Context *ctx, const pt_render_params *params, uint32_t fi
             float ms = 0.0f;
             cudaEventElapsedTime(&ms, t.a, t.b);
             ctx->stats.kernel_ms[t.cls] += ms;
-            cudaEventDestroy(t.a);
-            cudaEventDestroy(t.b);
         }
     }
     PT_CUDA_CHECK(ctx, cudaEventRecord(ctx->evStop, ctx->stream));
     PT_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
     PT_CUDA_CHECK(ctx, cudaGetLastError());
     PT_CUDA_CHECK(ctx, cudaEventElapsedTime(&ctx->stats.last_render_ms, ctx->evStart, ctx->evStop));
+    finished = true;
     return checkStackOverflow(ctx, "pt_render_samples");
 }
 
