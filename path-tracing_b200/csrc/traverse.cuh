@@ -11,7 +11,7 @@
 namespace pt
 {
 
-#define PT_STACK_SIZE 64
+#define PT_STACK_SIZE 96 // >= 3 entries per level of the wide BVH + 1 (depths seen: 14-21); an overflow fails the call
 // PT_SMEM_STACK > 0 puts the first PT_SMEM_STACK entries of a wavefront lane's traversal stack in SHARED
 // memory, laid out [entry][thread] (64-bit words: conflict-free whatever the lanes' depths), deeper
 // entries in the local-memory array.  Measured on the B200 (chess / street / atrium, 8 blocks per SM):
