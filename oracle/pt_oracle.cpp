@@ -11,19 +11,22 @@
  * PT/ = Path-Tracing/).
  *
  * Parity pinning:
- *   - RNG: pinned bit-exactly by the known answers derived from the integer spec
- *     (tests/test_oracle_rng.py).
- *   - shading.glsl / bsdf.glsl: the reference's own tests (PTT/ShadingTest.cpp, BsdfTest.cpp)
- *     pin INPUT GRIDS and invariants only (finite; lobe weights sum to 1) — the oracle is
- *     checked against those and against fp64 closed forms of the same formulas.
+ *   - EVERYTHING the reference's shaders compute — common / ray / tracing / shading / bsdf / sampling / material .glsl and
+ *     the main()s of raygen.rgen, closestHit.rchit, anyhit.rahit, occlusionAnyhit.rahit, miss.rmiss, occlusion.rmiss — is
+ *     pinned BIT FOR BIT to the reference's own source: oracle/ref_overlay/build_glsl.sh compiles those files as C++
+ *     (mechanical transform glsl2cpp.py, the reference's vendored glm) into oracle/_ref/libglsl_ref.so, and
+ *     tests/test_oracle_vs_glsl.py compares every function (26 probe modes; the reference's PTT/TestData.h grids and 10^5
+ *     random records each), closest-hit payloads and whole accumulation images with this file: zero differing records.
+ *     Golden vectors of the compiled GLSL travel in tests/golden/glsl_vectors.npz.  Where GLSL leaves an algorithm open
+ *     (inverse(mat4), the summation order of mat4 * vec4) this file follows glm, the reference's own host-side choice.
+ *   - RNG: additionally pinned by the known answers derived from the integer spec (tests/test_oracle_rng.py).
  *   - struct layouts: pinned by PTT/PaddingTest.cpp literals (tests/test_layout.py).
- *   - ray/box, ray/triangle, BVH: PARITY UNPINNED — in the reference they run inside the
- *     Vulkan driver / RT hardware and there is no source or test.  The oracle's fp32
+ *   - ray/box, ray/triangle, BVH: PARITY UNPINNED — in the reference they run inside the Vulkan driver / RT hardware and
+ *     there is no source or test (the compiled GLSL reaches them through a callback into this file).  The oracle's fp32
  *     watertight test (Woop, Benthin, Wald 2013) is validated against an fp64 brute force.
- *   - texture filtering (textureGrad, anisotropic): PARITY UNPINNED — sampler hardware.
- *     The oracle defines isotropic trilinear filtering per the GL 4.6 spec §8.14.
- *   - the full pipeline (images): PARITY UNPINNED by any reference artefact — the reference
- *     cannot run here (no Vulkan); the oracle itself is the arbiter.
+ *   - texture filtering (textureGrad, anisotropic), block decompression: PARITY UNPINNED — sampler hardware.  The oracle
+ *     defines trilinear filtering per the GL 4.6 spec §8.14 and, behind pto_scene_set_sampler, the anisotropic example
+ *     implementation of the Vulkan specification; closed forms in tests/test_oracle_textures.py.
  */
 #include "pt_oracle.h"
 #include "glsl_math.h"
