@@ -131,6 +131,7 @@ pt_status pt_context_create(int32_t cuda_device, pt_context **out_ctx)
     PT_CREATE_CHECK(cudaMalloc((void **)&ctx->dCounters, sizeof(DeviceCounters)));
     PT_CREATE_CHECK(cudaMemset(ctx->dCounters, 0, sizeof(DeviceCounters)));
     PT_CREATE_CHECK(cudaMalloc((void **)&ctx->dQueueCounts, sizeof(QueueCounts) * PT_MAX_POOLS));
+    PT_CREATE_CHECK(cudaMemset(ctx->dQueueCounts, 0, sizeof(QueueCounts) * PT_MAX_POOLS));
     PT_CREATE_CHECK(cudaMallocHost((void **)&ctx->hQueueCounts, sizeof(QueueCounts) * PT_MAX_POOLS));
     PT_CREATE_CHECK(cudaMalloc((void **)&ctx->dNextItem, 4));
     PT_CREATE_CHECK(cudaMallocHost((void **)&ctx->hNextItem, 4));
@@ -252,6 +253,10 @@ pt_status pt_render_begin(pt_context *ctx, uint32_t width, uint32_t height)
         }
         PT_T(targetAlloc(ctx, &ps.shadowQueue, slots));
 #undef PT_T
+        // the hit sort moves all `slots` (key, value) pairs; the values behind the live entries are never consumed,
+        // but they are defined once here so that the sort reads no uninitialised memory (compute-sanitizer initcheck)
+        PT_CUDA_CHECK(ctx, cudaMemsetAsync(ps.hitQ, 0, slots * sizeof(*ps.hitQ), ctx->stream));
+        PT_CUDA_CHECK(ctx, cudaMemsetAsync(ps.hitQSorted, 0, slots * sizeof(*ps.hitQSorted), ctx->stream));
         ctx->width = width;
         ctx->height = height;
         ctx->slotCapacity = (uint32_t)slots;
