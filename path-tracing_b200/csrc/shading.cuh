@@ -441,11 +441,11 @@ struct RayDifferentials
 };
 
 // :81-108 and :111-148; `refracted` selects the transmission formulas
-PT_DEV void propagateDifferentials(float4 derivatives, vec3 n, vec3 p, vec3 viewDir, vec3 newDir, vec3 dndu, vec3 dndv,
-                                   float eta, bool refracted, RayDifferentials &rd)
+// (dndx, dndy) = dndu * derivatives.xz + dndv * derivatives.yw, the first two statements of the GLSL function, are
+// the caller's: the wavefront computes them before the material fetch, where dndu / dndv / derivatives die
+PT_DEV void propagateDifferentials(vec3 n, vec3 p, vec3 viewDir, vec3 newDir, vec3 dndx, vec3 dndy, float eta, bool refracted,
+                                   RayDifferentials &rd)
 {
-    vec3 dndx = dndu * derivatives.x + dndv * derivatives.y;
-    vec3 dndy = dndu * derivatives.z + dndv * derivatives.w;
     const float d = -dot(n, p);
     const float tx = (-dot(n, rd.rxOrigin) - d) / dot(n, rd.rxDirection);
     const vec3 px = rd.rxOrigin + tx * rd.rxDirection;
@@ -481,6 +481,13 @@ PT_DEV void propagateDifferentials(float4 derivatives, vec3 n, vec3 p, vec3 view
     rd.ryDirection = normalize(newDir - eta * dwody + (mu * dndy + dmudy * n));
 }
 
+PT_DEV void propagateDifferentials(float4 derivatives, vec3 n, vec3 p, vec3 viewDir, vec3 newDir, vec3 dndu, vec3 dndv,
+                                   float eta, bool refracted, RayDifferentials &rd)
+{
+    const vec3 dndx = dndu * derivatives.x + dndv * derivatives.y;
+    const vec3 dndy = dndu * derivatives.z + dndv * derivatives.w;
+    propagateDifferentials(n, p, viewDir, newDir, dndx, dndy, eta, refracted, rd);
+}
 
 // common.glsl:17-20
 PT_DEV vec3 hdrToLdr(vec3 rgb) { return rgb / (1.0f + maxComponent(rgb)); }

@@ -52,6 +52,9 @@ namespace
 #endif
 
 // the ray-load lambda of k_extend (which also regenerates ended paths) as a call (0) or inlined at its two call sites (1)
+#ifndef PT_SHADE_DIET
+#define PT_SHADE_DIET 1
+#endif
 #ifndef PT_INLINE_LOADRAY
 #define PT_INLINE_LOADRAY 1
 #endif
@@ -406,10 +409,12 @@ template <bool ALPHA, bool STATS> __global__ void __launch_bounds__(128, PT_SHAD
         const uint32_t slot = hitQueue[i];
         const float4 hitv = rc.ps.rec[slot].hit;
         const float4 rayO = rc.ps.rec[slot].rayO, rayD = rc.ps.rec[slot].rayD;
+#if !PT_SHADE_DIET
         float4 thr4 = rc.ps.rec[slot].thr;
         float4 rad4 = rc.ps.rec[slot].rad;
         vec3 throughput = V3(thr4), radiance = V3(rad4);
         uint32_t state = __float_as_uint(thr4.w);
+#endif
         const vec3 rayDir = V3(rayD);
         const uint32_t tri = __float_as_uint(hitv.x);
 
@@ -462,6 +467,18 @@ template <bool ALPHA, bool STATS> __global__ void __launch_bounds__(128, PT_SHAD
         vec3 dpdx, dpdy;
         computeDpDxy(position, rd.rxOrigin, rd.rxDirection, rd.ryOrigin, rd.ryDirection, normal, dpdx, dpdy);
         const float4 derivatives = computeDerivatives(dpdx, dpdy, dpdu, dpdv);
+#if PT_SHADE_DIET
+        // Register diet: what the code AFTER the BSDF sample needs of the geometry is reduced to its results now — the
+        // ray origin of either outcome (reflected / refracted: same operations as the one call the shader makes, for
+        // both values of its flag) and the normal's screen-space derivatives — so that the triangle's corners, vertex
+        // normals, barycentrics and uv derivatives are dead while the material and the BSDF are evaluated; the ray
+        // differentials are re-read from the path record where they are propagated.
+        const vec3 originReflected = offsetRayOriginShadowTerminator(position, p0, p1, p2, n0, n1, n2, bary, false);
+        const vec3 originRefracted = offsetRayOriginShadowTerminator(position, p0, p1, p2, n0, n1, n2, bary, true);
+        const vec3 originThrough = offsetRayOriginSelfIntersection(position, -geometricNormal);
+        const vec3 dndx = dndu * derivatives.x + dndv * derivatives.y;
+        const vec3 dndy = dndu * derivatives.z + dndv * derivatives.w;
+#endif
 
         // ---- material, closestHit.rchit:101-117 -------------------------------------------------
         MaterialSample material = sampleMaterial(s, materialId, texCoords.x, texCoords.y, derivatives, inside,
@@ -492,7 +509,11 @@ template <bool ALPHA, bool STATS> __global__ void __launch_bounds__(128, PT_SHAD
             bsdf.Color.z *= powf(material.AttenuationColor.z, e);
         }
         const bool isRefracted = bsdf.Direction.z < 0.0f;
+#if PT_SHADE_DIET
+        const vec3 rayOrigin = isRefracted ? originRefracted : originReflected;
+#else
         const vec3 rayOrigin = offsetRayOriginShadowTerminator(position, p0, p1, p2, n0, n1, n2, bary, isRefracted);
+#endif
 
         float lightPdf, lightSmplPdf;
         const float l0 = rnd(rng);
@@ -503,12 +524,36 @@ template <bool ALPHA, bool STATS> __global__ void __launch_bounds__(128, PT_SHAD
         const vec3 lightBsdf = evaluateBSDF(material, V, L, lightSmplPdf);
 
         const vec3 newDir = normalize(mul(TBN, bsdf.Direction));
+#if PT_SHADE_DIET
+        const vec3 newPos = isRefracted ? originThrough : rayOrigin;
+#else
         const vec3 newPos = isRefracted ? offsetRayOriginSelfIntersection(position, -geometricNormal) : rayOrigin;
+#endif
         const vec3 directLight = light.Color * light.Attenuation * lightBsdf;
 
+#if PT_SHADE_DIET
+        {
+            // __ldcg is an asm volatile load: a second read of the record (an L2 hit), not the registers of the first
+            // one kept alive across the BSDF
+            const float4 *dv = &rc.ps.rec[slot].diff0;
+            const float4 e0 = __ldcg(dv), e1 = __ldcg(dv + 1), e2 = __ldcg(dv + 2);
+            rd.rxOrigin = V3(e0.x, e0.y, e0.z);
+            rd.rxDirection = V3(e0.w, e1.x, e1.y);
+            rd.ryOrigin = V3(e1.z, e1.w, e2.x);
+            rd.ryDirection = V3(e2.y, e2.z, e2.w);
+        }
+        propagateDifferentials(normal, rayOrigin, -rayDir, newDir, dndx, dndy, material.Eta, isRefracted, rd);
+#else
         propagateDifferentials(derivatives, normal, rayOrigin, -rayDir, newDir, dndu, dndv, material.Eta, isRefracted, rd);
+#endif
 
         // ---- raygen.rgen:71-96 ----------------------------------------------------------------
+#if PT_SHADE_DIET
+        // throughput, radiance and the bounce state are first needed here: read now (same line as rayO / rayD)
+        const float4 thr4 = __ldcg(&rc.ps.rec[slot].thr), rad4 = __ldcg(&rc.ps.rec[slot].rad);
+        vec3 throughput = V3(thr4), radiance = V3(rad4);
+        uint32_t state = __float_as_uint(thr4.w);
+#endif
         radiance += throughput * material.EmissiveColor;
         bool done = false;
         if (bsdf.Pdf == -1.0f)
