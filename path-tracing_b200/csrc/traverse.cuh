@@ -182,24 +182,90 @@ PT_DEV bool intersectTriangle(const RaySetup &r, vec3 p0, vec3 p1, vec3 p2, floa
     return true;
 }
 
-// colour texture x colour factor at a candidate hit (anyhit.rahit:36-51, occlusionAnyhit.rahit:35-50)
-PT_DEV float4 anyHitColor(const DeviceScene &s, uint32_t shadeIndex, uint32_t materialId, float b1, float b2)
+// colour texture x colour factor at a candidate hit (anyhit.rahit:36-51, occlusionAnyhit.rahit:35-50), in two
+// steps: the alpha channel decides (>= 0.5 accepts a closest-hit candidate, >= 1 an occluder), and only an IGNORED
+// closest-hit candidate that is the nearest one so far needs the colour (the decal record).  Same texels, same
+// weights, same per-channel arithmetic as sampleBilinear(level 0) — the three colour channels are simply evaluated
+// later, or never: 12 of the 16 dependent table look-ups and 27 of the 36 interpolation operations of a test.
+struct AnyHitSample
+{
+    float4 factor;
+    float4 full;                // the whole colour where the two-step path does not apply (float / 1x1 textures)
+    uint32_t t00, t10, t01, t11; // RGBA8 texels of the footprint
+    float fx, fy;
+    uint32_t lutOffset; // 256 = sRGB decode of the colour channels
+    bool whole;
+};
+
+PT_DEV float anyHitAlpha(const DeviceScene &s, uint32_t shadeIndex, uint32_t materialId, float b1, float b2, AnyHitSample &a)
 {
     const TriShade &ts = s.triShade[shadeIndex];
     const float4 a6 = __ldg(&ts.a[6]), a7 = __ldg(&ts.a[7]), a8 = __ldg(&ts.a[8]);
     const float b0 = 1.0f - b1 - b2;
-    const float u = a6.w * b0 + a7.y * b1 + a7.w * b2;
-    const float v = a7.x * b0 + a7.z * b1 + a8.x * b2;
+    float u = a6.w * b0 + a7.y * b1 + a7.w * b2;
+    float v = a7.x * b0 + a7.z * b1 + a8.x * b2;
     const uint32_t type = materialId & 0xffu, index = materialId >> 8;
+    a.whole = true;
     if (type > 2)
-        return make_float4(1.0f, 0.0f, 0.0f, 1.0f); // getColorFactor default, texture 0 is white
+    {
+        a.full = make_float4(1.0f, 0.0f, 0.0f, 1.0f); // getColorFactor default, texture 0 is white
+        return 1.0f;
+    }
     const MaterialRaw *m = (type == 0 ? s.materials[0] : type == 1 ? s.materials[1] : s.materials[2]) + index;
-    const float4 factor = __ldg(&m->q[1]); // vec4 Color sits at byte 16 in all three structs
+    a.factor = __ldg(&m->q[1]); // vec4 Color sits at byte 16 in all three structs
     // ColorIdx: MR byte 80 (q[5].x); SG / Phong byte 76 (q[4].w)
     const uint32_t colorIdx =
         type == 0 ? __float_as_uint(__ldg(&m->q[5]).x) : __float_as_uint(__ldg(&m->q[4]).w);
-    const float4 c = textureLod0(s, s.textures[colorIdx], u, v);
-    return make_float4(c.x * factor.x, c.y * factor.y, c.z * factor.z, c.w * factor.w);
+    const DevTexture &t = s.textures[colorIdx];
+    const uint32_t lw = t.width, lh = t.height, flags = t.flags;
+    if ((flags & PT_TEX_FLAG_FLOAT) || (lw == 1 && lh == 1))
+    {
+        const float4 c = textureLod0(s, t, u, v);
+        a.full = make_float4(c.x * a.factor.x, c.y * a.factor.y, c.z * a.factor.z, c.w * a.factor.w);
+        return a.full.w;
+    }
+    a.whole = false;
+    a.lutOffset = (flags & PT_TEX_FLAG_SRGB) ? 256u : 0u;
+    // sampleBilinear(level 0): repeat wrap, texel centres at half integers
+    u = isfinite(u) ? u : 0.0f;
+    v = isfinite(v) ? v : 0.0f;
+    u = u - floorf(u);
+    v = v - floorf(v);
+    const float x = u * (float)lw - 0.5f, y = v * (float)lh - 0.5f;
+    const float fx0 = floorf(x), fy0 = floorf(y);
+    a.fx = x - fx0, a.fy = y - fy0;
+    const int W = (int)lw, H = (int)lh;
+    const int ix = (int)fx0, iy = (int)fy0;
+    const int x0 = ix < 0 ? W - 1 : ix, x1 = x0 + 1 == W ? 0 : x0 + 1;
+    const int y0 = iy < 0 ? H - 1 : iy, y1 = y0 + 1 == H ? 0 : y0 + 1;
+    const uint32_t *texels = reinterpret_cast<const uint32_t *>(t.base) + t.levelOffset[0];
+    a.t00 = __ldg(texels + (size_t)y0 * lw + x0), a.t10 = __ldg(texels + (size_t)y0 * lw + x1);
+    a.t01 = __ldg(texels + (size_t)y1 * lw + x0), a.t11 = __ldg(texels + (size_t)y1 * lw + x1);
+    // alpha is never sRGB-encoded: table entries [0, 255]
+    const float a00 = __ldg(s.lut + (a.t00 >> 24)), a10 = __ldg(s.lut + (a.t10 >> 24));
+    const float a01 = __ldg(s.lut + (a.t01 >> 24)), a11 = __ldg(s.lut + (a.t11 >> 24));
+    const float gx = 1.0f - a.fx, gy = 1.0f - a.fy;
+    const float top = a00 * gx + a10 * a.fx, bottom = a01 * gx + a11 * a.fx;
+    return (top * gy + bottom * a.fy) * a.factor.w;
+}
+
+// the colour channels of the sample anyHitAlpha looked at (x factor)
+PT_DEV vec3 anyHitRgb(const DeviceScene &s, const AnyHitSample &a)
+{
+    if (a.whole)
+        return V3(a.full);
+    const float *lut = s.lut + a.lutOffset;
+    const float gx = 1.0f - a.fx, gy = 1.0f - a.fy;
+    float c[3];
+#pragma unroll
+    for (int k = 0; k < 3; k++)
+    {
+        const float c00 = __ldg(lut + ((a.t00 >> (8 * k)) & 0xffu)), c10 = __ldg(lut + ((a.t10 >> (8 * k)) & 0xffu));
+        const float c01 = __ldg(lut + ((a.t01 >> (8 * k)) & 0xffu)), c11 = __ldg(lut + ((a.t11 >> (8 * k)) & 0xffu));
+        const float top = c00 * gx + c10 * a.fx, bottom = c01 * gx + c11 * a.fx;
+        c[k] = top * gy + bottom * a.fy;
+    }
+    return V3(c[0] * a.factor.x, c[1] * a.factor.y, c[2] * a.factor.z);
 }
 
 // One BVH4 node: tests the four child boxes, returns entry distances (INF if missed / empty).
@@ -524,20 +590,22 @@ template <bool CLOSEST, bool ALPHA, bool STATS, int SMEM = 0, bool CULL = false>
                 {
                     if (STATS)
                         st.alphaTests++;
-                    const float4 color = anyHitColor(s, PT_SHADE_INDEX(tri, q0.w), __float_as_uint(q2.w), b1, b2);
+                    AnyHitSample ah;
+                    const float alpha = anyHitAlpha(s, PT_SHADE_INDEX(tri, q0.w), __float_as_uint(q2.w), b1, b2, ah);
                     if (CLOSEST)
                     {
-                        if (color.w < 0.5f)
+                        if (alpha < 0.5f)
                         {
                             if (decal.dist == -1.0f || t < decal.dist)
                             {
-                                decal.r = color.x, decal.g = color.y, decal.b = color.z, decal.a = color.w;
+                                const vec3 rgb = anyHitRgb(s, ah);
+                                decal.r = rgb.x, decal.g = rgb.y, decal.b = rgb.z, decal.a = alpha;
                                 decal.dist = t;
                             }
                             continue; // ignoreIntersectionEXT
                         }
                     }
-                    else if (color.w < 1.0f)
+                    else if (alpha < 1.0f)
                         continue;
                 }
                 hit.tri = tri;
