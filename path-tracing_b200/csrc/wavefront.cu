@@ -55,6 +55,9 @@ namespace
 #ifndef PT_SHADE_DIET
 #define PT_SHADE_DIET 1
 #endif
+#ifndef PT_SHADE_LATE_READS
+#define PT_SHADE_LATE_READS 0 // measured: re-reading differentials / throughput / radiance where they are used exposes their latency, k_shade +12 % (chess)
+#endif
 #ifndef PT_INLINE_LOADRAY
 #define PT_INLINE_LOADRAY 1
 #endif
@@ -409,7 +412,7 @@ template <bool ALPHA, bool STATS> __global__ void __launch_bounds__(128, PT_SHAD
         const uint32_t slot = hitQueue[i];
         const float4 hitv = rc.ps.rec[slot].hit;
         const float4 rayO = rc.ps.rec[slot].rayO, rayD = rc.ps.rec[slot].rayD;
-#if !PT_SHADE_DIET
+#if !PT_SHADE_LATE_READS
         float4 thr4 = rc.ps.rec[slot].thr;
         float4 rad4 = rc.ps.rec[slot].rad;
         vec3 throughput = V3(thr4), radiance = V3(rad4);
@@ -531,7 +534,7 @@ template <bool ALPHA, bool STATS> __global__ void __launch_bounds__(128, PT_SHAD
 #endif
         const vec3 directLight = light.Color * light.Attenuation * lightBsdf;
 
-#if PT_SHADE_DIET
+#if PT_SHADE_LATE_READS
         {
             // __ldcg is an asm volatile load: a second read of the record (an L2 hit), not the registers of the first
             // one kept alive across the BSDF
@@ -542,13 +545,15 @@ template <bool ALPHA, bool STATS> __global__ void __launch_bounds__(128, PT_SHAD
             rd.ryOrigin = V3(e1.z, e1.w, e2.x);
             rd.ryDirection = V3(e2.y, e2.z, e2.w);
         }
+#endif
+#if PT_SHADE_DIET
         propagateDifferentials(normal, rayOrigin, -rayDir, newDir, dndx, dndy, material.Eta, isRefracted, rd);
 #else
         propagateDifferentials(derivatives, normal, rayOrigin, -rayDir, newDir, dndu, dndv, material.Eta, isRefracted, rd);
 #endif
 
         // ---- raygen.rgen:71-96 ----------------------------------------------------------------
-#if PT_SHADE_DIET
+#if PT_SHADE_LATE_READS
         // throughput, radiance and the bounce state are first needed here: read now (same line as rayO / rayD)
         const float4 thr4 = __ldcg(&rc.ps.rec[slot].thr), rad4 = __ldcg(&rc.ps.rec[slot].rad);
         vec3 throughput = V3(thr4), radiance = V3(rad4);

@@ -21,6 +21,7 @@ def main():
     ap.add_argument("--spp", type=int, default=32)
     ap.add_argument("--reps", type=int, default=3)
     ap.add_argument("--stats", action="store_true")
+    ap.add_argument("--kernels", action="store_true", help="per-kernel-class CUDA-event times of a separate ONE-pool render")
     ap.add_argument("--hash", action="store_true", help="sha1 of a 2-spp accumulation image (bit-identity of variants)")
     ap.add_argument("--tuning", default="")
     ap.add_argument("--tag", default=os.environ.get("PT_CORE_LIB", "in-tree"))
@@ -56,6 +57,16 @@ def main():
                        n_tri_closest=round(st["tri_tests_closest"] / max(1, st["rays_closest"]), 2),
                        n_box_shadow=round(st["box_tests_shadow"] / max(1, st["rays_shadow"]), 2),
                        n_tri_shadow=round(st["tri_tests_shadow"] / max(1, st["rays_shadow"]), 2))
+        if a.kernels:
+            r.set_traversal_stats(False)
+            r.set_tuning("pools", 1)
+            r.set_kernel_timing(True)
+            r.on_resize(w, h)
+            r.render(a.spp, params=params)
+            st = r.stats()
+            out["one_pool_ms"] = {k: round(v, 2) for k, v in st["kernel_ms"].items()}
+            r.set_kernel_timing(False)
+            r.set_tuning("pools", 2)
         if a.hash:
             import hashlib
             r.set_traversal_stats(False)
