@@ -30,8 +30,10 @@ a `weak` block alongside times the round-1 arrangement (every rank adds its own 
 from __future__ import annotations
 
 import argparse
+import contextlib
 import ctypes
 import importlib
+import io
 import json
 import os
 import statistics
@@ -610,10 +612,24 @@ def run_ours(args):
 
 def main():
     args = parse_args()
-    if args.impl == "reference":
-        run_reference(args)
-    else:
-        run_ours(args)
+    # The contract is ONE JSON line on stdout.  Libraries write there too (NCCL prints its version banner to fd 1 when
+    # the box sets NCCL_DEBUG): while the bench runs, fd 1 is stderr; the line goes to the saved descriptor.
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    try:
+        buf = io.StringIO()
+        with contextlib.redirect_stdout(buf):
+            if args.impl == "reference":
+                run_reference(args)
+            else:
+                run_ours(args)
+        sys.stdout.flush()
+    finally:
+        os.dup2(real_stdout, 1)
+        os.close(real_stdout)
+    sys.stdout.write(buf.getvalue())
+    sys.stdout.flush()
 
 
 if __name__ == "__main__":

@@ -11,6 +11,7 @@ def test_reference_arm_line():
     out = subprocess.run([sys.executable, os.path.join(conftest.ROOT, "bench.py"), "--impl", "reference", "--small", "--width", "96",
                           "--height", "54", "--steps", "2", "--warmup", "1"], capture_output=True, text=True, timeout=300, cwd=conftest.ROOT)
     assert out.returncode == 0, out.stderr[-2000:]
+    assert len(out.stdout.strip().splitlines()) == 1, "stdout carries the JSON line and nothing else"
     line = json.loads(out.stdout.strip().splitlines()[-1])
     assert line["impl"] == "reference" and line["unit"] == "Mrays/s" and line["higher_is_better"] is True
     assert line["metric"].startswith("Mrays/s") and line["value"] > 0 and line["steps"] == 2 and line["warmup"] == 1
