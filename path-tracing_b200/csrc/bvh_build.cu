@@ -120,6 +120,18 @@ __global__ void k_bake(const MeshInstance *__restrict__ mis, uint32_t miCount, c
     ts.a[6] = make_float4(bit[2][0], bit[2][1], bit[2][2], uv[0][0]);
     ts.a[7] = make_float4(uv[0][1], uv[1][0], uv[1][1], uv[2][0]);
     ts.a[8] = make_float4(uv[2][1], __uint_as_float(mi.instance), __uint_as_float(mi.geometry), __uint_as_float(prim));
+#if PT_SHADE_UNIT_NORMALS
+    {
+        const vec3 u0 = normalize(V3(nrm[0][0], nrm[0][1], nrm[0][2])), u1 = normalize(V3(nrm[1][0], nrm[1][1], nrm[1][2]));
+        const vec3 u2 = normalize(V3(nrm[2][0], nrm[2][1], nrm[2][2]));
+        const vec3 w0 = V3(pos[0][0], pos[0][1], pos[0][2]), w1 = V3(pos[1][0], pos[1][1], pos[1][2]);
+        const vec3 w2 = V3(pos[2][0], pos[2][1], pos[2][2]);
+        const vec3 g = normalize(cross(w1 - w0, w2 - w0));
+        ts.a[9] = make_float4(u0.x, u0.y, u0.z, u1.x);
+        ts.a[10] = make_float4(u1.y, u1.z, u2.x, u2.y);
+        ts.a[11] = make_float4(u2.z, g.x, g.y, g.z);
+    }
+#endif
     triShade[tri] = ts;
 
     Aabb b;
@@ -1076,9 +1088,9 @@ pt_status buildAccel(Context *ctx, const std::vector<MeshInstance> &mis, uint32_
         s.nodes = nodes;
         ctx->nodeCount = wideCount;
 #if PT_SHADE_BY_FLAT
-        ctx->bvhBytes = (uint64_t)wideCount * sizeof(BvhNode) + (uint64_t)n * 48 + ctx->triangleCount * 144;
+        ctx->bvhBytes = (uint64_t)wideCount * sizeof(BvhNode) + (uint64_t)n * 48 + ctx->triangleCount * sizeof(TriShade);
 #else
-        ctx->bvhBytes = (uint64_t)wideCount * sizeof(BvhNode) + (uint64_t)n * (48 + 144);
+        ctx->bvhBytes = (uint64_t)wideCount * sizeof(BvhNode) + (uint64_t)n * (48 + sizeof(TriShade));
 #endif
         ctx->referenceCount = n;
     }

@@ -75,14 +75,20 @@ PT_HD int encodeLeaf(uint32_t first, uint32_t count) { return ~(int)((first << 2
 #define PT_TRI_FLAG_OPAQUE 1u
 #define PT_TRI_FLAG_MIRRORED 2u // the instance transform has a negative determinant: object-space winding = world-space winding reversed
 
+#ifndef PT_SHADE_UNIT_NORMALS
+#define PT_SHADE_UNIT_NORMALS 1 // a[9..11]: what k_shade would normalise per HIT is normalised once per TRIANGLE by k_bake
+#endif
 struct __align__(16) TriShade
 {
-    float4 a[9];
+    float4 a[PT_SHADE_UNIT_NORMALS ? 12 : 9];
     // a[0] = n0.xyz, n1.x   a[1] = n1.yz, n2.xy   a[2] = n2.z, t0.xyz
     // a[3] = t1.xyz, t2.x   a[4] = t2.yz, b0.xy   a[5] = b0.z, b1.xyz
     // a[6] = b2.xyz, uv0.x  a[7] = uv0.y, uv1.xy, uv2.x   a[8] = uv2.y, instance, geometry, primitive (bits)
+    // a[9] = normalize(n0).xyz, normalize(n1).x   a[10] = normalize(n1).yz, normalize(n2).xy
+    // a[11] = normalize(n2).z, normalize(cross(p1 - p0, p2 - p0)).xyz — the same device functions on the same
+    //         values k_shade would apply (closestHit.rchit:60-66, 76-78), so the bits are those of the per-hit evaluation
 };
-static_assert(sizeof(TriShade) == 144, "TriShade must be 144 bytes");
+static_assert(sizeof(TriShade) == (PT_SHADE_UNIT_NORMALS ? 192 : 144), "TriShade must be 144 / 192 bytes");
 
 // ---------------------------------------------------------------------------------------------
 // materials: the reference's 96-byte structs, verbatim (PT/Shaders/ShaderTypes.incl:61-118)

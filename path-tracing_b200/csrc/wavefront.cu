@@ -51,13 +51,18 @@ namespace
 #define PT_SHADE_MIN_BLOCKS 4
 #endif
 
-// the ray-load lambda of k_extend (which also regenerates ended paths) as a call (0) or inlined at its two call sites (1)
+#ifndef PT_SHADE_GRID_PER_SM
+#define PT_SHADE_GRID_PER_SM 4 // k_shade blocks per SM = the resident ones (grid-stride loop over the hits).  Measured 4 / 8 / 16 / 64: alone the kernel
+                               // likes MORE blocks (chess 55.2 / 54.3 / 53.4 / 50.2 ms), the two overlapping pools fewer (2368 / 2360 / 2352 / 2341 Mrays/s)
+#endif
+// k_shade register diet: the geometry the code after the BSDF sample needs is reduced to its results before the material fetch
 #ifndef PT_SHADE_DIET
 #define PT_SHADE_DIET 1
 #endif
 #ifndef PT_SHADE_LATE_READS
 #define PT_SHADE_LATE_READS 0 // measured: re-reading differentials / throughput / radiance where they are used exposes their latency, k_shade +12 % (chess)
 #endif
+// the ray-load lambda of k_extend (which also regenerates ended paths) as a call (0) or inlined at its two call sites (1)
 #ifndef PT_INLINE_LOADRAY
 #define PT_INLINE_LOADRAY 1
 #endif
@@ -445,10 +450,16 @@ template <bool ALPHA, bool STATS> __global__ void __launch_bounds__(128, PT_SHAD
         vec3 normal = normalize(n0r * bary.x + n1r * bary.y + n2r * bary.z);
         vec3 tangent = normalize(t0r * bary.x + t1r * bary.y + t2r * bary.z);
         vec3 bitangent = normalize(b0r * bary.x + b1r * bary.y + b2r * bary.z);
-        const vec3 n0 = normalize(n0r), n1 = normalize(n1r), n2 = normalize(n2r);
-
         const vec3 edge1 = p1 - p0, edge2 = p2 - p0;
+#if PT_SHADE_UNIT_NORMALS
+        // normalised once per triangle by k_bake (same functions, same operands)
+        const float4 a9 = __ldg(&ts.a[9]), a10 = __ldg(&ts.a[10]), a11 = __ldg(&ts.a[11]);
+        const vec3 n0 = V3(a9.x, a9.y, a9.z), n1 = V3(a9.w, a10.x, a10.y), n2 = V3(a10.z, a10.w, a11.x);
+        vec3 geometricNormal = V3(a11.y, a11.z, a11.w);
+#else
+        const vec3 n0 = normalize(n0r), n1 = normalize(n1r), n2 = normalize(n2r);
         vec3 geometricNormal = normalize(cross(edge1, edge2));
+#endif
         const bool inside = dot(geometricNormal, rayDir) > 0.0f;
         if (inside)
         {
@@ -1207,7 +1218,7 @@ pt_status renderFrames(Context *ctx, const pt_render_params *params, uint32_t fi
             pl.sortTemp = (char *)ctx->sortTemp + p * ctx->sortTempBytes;
             pl.cur = 0;
             pl.active = true;
-            pl.gridShade = std::min((slots + 127) / 128, (uint32_t)ctx->smCount * 16);
+            pl.gridShade = std::min((slots + 127) / 128, (uint32_t)ctx->smCount * PT_SHADE_GRID_PER_SM);
             // persistent warps: exactly as many blocks as are resident on the machine (occupancy query per
             // instantiation; PT_TRACE_BLOCKS overrides), never more than the rays need
             auto residentGrid = [&](auto kernel) {
