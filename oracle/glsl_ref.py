@@ -1,5 +1,6 @@
 """ctypes binding of oracle/_ref/libglsl_ref.so — the reference's own GLSL ray-tracing stages compiled
-as C++ (oracle/ref_overlay/build_glsl.sh, glsl2cpp.py).
+as C++ (oracle/ref_overlay/build_glsl.sh, glsl2cpp.py) — and of oracle/_ref/libglsl_comp_ref.so, its compute
+stages (post-process chain, skinning) compiled the same way (glsl2cpp.py --compute).
 
 TEST INFRASTRUCTURE, NOT PRODUCT: the pin of the CPU oracle (oracle/pt_oracle.cpp) to the reference's
 shader text.  Only tests/ and tests/golden/make_glsl_vectors.py import this module.  The library can only
@@ -19,6 +20,7 @@ from . import oracle as _oracle
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB_PATH = os.path.join(_HERE, "_ref", "libglsl_ref.so")
+_COMP_LIB_PATH = os.path.join(_HERE, "_ref", "libglsl_comp_ref.so")
 REFERENCE_ROOT = "/root/reference"
 
 
@@ -116,3 +118,51 @@ class GlslScene:
                                    payload_in.ctypes.data, out.ctypes.data)
         assert rc == 0, rc
         return out
+
+
+# ---- the COMPUTE stages (postprocess / bloom / composition / toneMapping / skinning .comp) --------------------------
+_comp_lib = None
+
+
+def comp_available() -> bool:
+    build()
+    return os.path.exists(_COMP_LIB_PATH)
+
+
+def comp_lib():
+    global _comp_lib
+    if _comp_lib is None:
+        if not comp_available():
+            raise RuntimeError("libglsl_comp_ref.so is not built and the reference checkout is absent")
+        L = C.CDLL(_COMP_LIB_PATH)
+        L.glc_postprocess.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_float, C.c_float, C.c_float, C.c_uint32,
+                                      C.c_void_p, C.c_void_p, C.c_void_p]
+        L.glc_skin.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p]
+        _comp_lib = L
+    return _comp_lib
+
+
+def postprocess(accum: np.ndarray, total_samples: int, exposure=1.0, bloom_threshold=1.0, bloom_intensity=0.1, tone_mapping_hdr=False):
+    """The compiled compute stages over a (H, W, 4) float32 sum image: (bloom level 0 after the up-sampling chain,
+    the post-process image after composition.comp, the same after toneMapping.comp), each (H, W, 4) float32 holding
+    the RGBA16F values."""
+    accum = np.ascontiguousarray(accum, np.float32)
+    h, w = accum.shape[:2]
+    outs = [np.zeros((h, w, 4), np.float32) for _ in range(3)]
+    rc = comp_lib().glc_postprocess(accum.ctypes.data, w, h, int(total_samples), exposure, bloom_threshold, bloom_intensity,
+                                    1 if tone_mapping_hdr else 0, *(o.ctypes.data for o in outs))
+    assert rc == 0, rc
+    return tuple(outs)
+
+
+def skin_vertices(animated: np.ndarray, indices: np.ndarray, bone_transforms: np.ndarray) -> np.ndarray:
+    """skinning.comp main() on animated[indices] -> (len(indices), 14) float32 vertices."""
+    animated = np.ascontiguousarray(animated)
+    assert animated.dtype.itemsize == 88, animated.dtype
+    indices = np.ascontiguousarray(indices, np.uint32)
+    bones = np.ascontiguousarray(bone_transforms, np.float32).reshape(-1, 12)
+    out = np.zeros((len(indices), 14), np.float32)
+    rc = comp_lib().glc_skin(animated.ctypes.data, len(animated), indices.ctypes.data, len(indices), bones.ctypes.data, len(bones),
+                             out.ctypes.data)
+    assert rc == 0, rc
+    return out

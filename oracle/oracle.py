@@ -90,22 +90,37 @@ def lib():
         L.pto_postprocess.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p]
         L.pto_debug_render.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p]
         L.pto_round_half.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64]
+        L.pto_skin_vertices.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint32, C.c_void_p]
         _lib = L
     return _lib
 
 
 def postprocess(accum: np.ndarray, total_samples: int, exposure=1.0, bloom_threshold=1.0, bloom_intensity=0.1,
-                hdr: bool = False) -> np.ndarray:
+                hdr: bool = False, tone_mapping_hdr: bool | None = None) -> np.ndarray:
     """The reference's post-process + output chain (pt_oracle_post.cpp) on a host (H, W, 4) float32 sum image:
-    (H, W, 4) uint8 sRGB (png / jpg / tga outputs) or, with hdr, (H, W, 4) float32 (the .hdr output)."""
+    (H, W, 4) uint8 sRGB (png / jpg / tga outputs) or, with hdr, (H, W, 4) float32 (the .hdr output).
+    tone_mapping_hdr overrides the tone-mapping mode the output format implies (float output of the SDR curve)."""
     from importlib import import_module
 
     core = import_module("path-tracing_b200.core")
     accum = np.ascontiguousarray(accum, np.float32)
     h, w = accum.shape[:2]
-    p = core.PostProcessParams(exposure, bloom_threshold, bloom_intensity, 1 if hdr else 0)
+    tone_hdr = hdr if tone_mapping_hdr is None else tone_mapping_hdr
+    p = core.PostProcessParams(exposure, bloom_threshold, bloom_intensity, 1 if tone_hdr else 0)
     out = np.zeros((h, w, 4), np.float32 if hdr else np.uint8)
     rc = lib().pto_postprocess(accum.ctypes.data, w, h, C.addressof(p), int(total_samples), 1 if hdr else 0, out.ctypes.data)
+    assert rc == 0, rc
+    return out
+
+
+def skin_vertices(animated: np.ndarray, indices: np.ndarray, bone_transforms: np.ndarray) -> np.ndarray:
+    """skinning.comp on animated[indices] -> (len(indices), 14) float32 vertices (pto_skin_vertices)."""
+    animated = np.ascontiguousarray(animated)
+    assert animated.dtype.itemsize == 88, animated.dtype
+    indices = np.ascontiguousarray(indices, np.uint32)
+    bones = np.ascontiguousarray(bone_transforms, np.float32).reshape(-1, 12)
+    out = np.zeros((len(indices), 14), np.float32)
+    rc = lib().pto_skin_vertices(animated.ctypes.data, indices.ctypes.data, len(indices), bones.ctypes.data, len(bones), out.ctypes.data)
     assert rc == 0, rc
     return out
 

@@ -19,6 +19,9 @@
  *     random records each), closest-hit payloads and whole accumulation images with this file: zero differing records.
  *     Golden vectors of the compiled GLSL travel in tests/golden/glsl_vectors.npz.  Where GLSL leaves an algorithm open
  *     (inverse(mat4), the summation order of mat4 * vec4) this file follows glm, the reference's own host-side choice.
+ *   - the COMPUTE stages — skinning.comp (skinVertex below) and the post-process chain (pt_oracle_post.cpp) — are pinned the
+ *     same way: glsl2cpp.py --compute -> oracle/_ref/libglsl_comp_ref.so, tests/test_oracle_vs_glsl_compute.py, golden vectors
+ *     in tests/golden/glsl_compute_vectors.npz; every float of every skinned vertex and of the composed / tone-mapped images.
  *   - RNG: additionally pinned by the known answers derived from the integer spec (tests/test_oracle_rng.py).
  *   - struct layouts: pinned by PTT/PaddingTest.cpp literals (tests/test_layout.py).
  *   - ray/box, ray/triangle, BVH: PARITY UNPINNED — in the reference they run inside the Vulkan driver / RT hardware and
@@ -1143,7 +1146,10 @@ pt_vertex skinVertex(const pt_animated_vertex &a, const float *boneTransforms, u
         const float boneWeight = a.bone_weights[i];
         const float *m = boneTransforms + 12 * (size_t)boneIndex;
         const mat3x4 transform = { { V4(m[0], m[1], m[2], m[3]), V4(m[4], m[5], m[6], m[7]), V4(m[8], m[9], m[10], m[11]) } };
-        position = position + (V4(P, 1.0f) * transform) * boneWeight;
+        /* `boneWeight * vec4(Position, 1) * transform` groups from the left: the WEIGHTED point goes through the matrix
+         * (skinning.comp:41; pinned by tests/test_oracle_vs_glsl_compute.py — weighting the transformed point instead
+         * differs in the last bit of x / y for every second vertex) */
+        position = position + V4(P.x * boneWeight, P.y * boneWeight, P.z * boneWeight, boneWeight) * transform;
         tangent = tangent + normalize(V4(T, 0.0f) * transform) * boneWeight;
         bitangent = bitangent + normalize(V4(B, 0.0f) * transform) * boneWeight;
         const vec4 n4 = V4(N, 0.0f) * transpose(inverse(M4(transform)));
@@ -2821,6 +2827,16 @@ int32_t pto_trace_closest_bruteforce_f64(const pto_scene *s, const pt_ray *rays,
         if (out_t)
             out_t[i] = h.tri == PT_NO_HIT ? 0.0 : best;
     }
+    return PT_OK;
+}
+
+int32_t pto_skin_vertices(const pt_animated_vertex *animated, const uint32_t *indices, uint64_t count,
+                          const float *bone_transforms, uint32_t bone_count, pt_vertex *out)
+{
+    if (!animated || !indices || !bone_transforms || !out || bone_count == 0)
+        return PT_ERR_INVALID_ARGUMENT;
+    for (uint64_t i = 0; i < count; i++)
+        out[i] = skinVertex(animated[indices[i]], bone_transforms, bone_count);
     return PT_OK;
 }
 

@@ -117,6 +117,11 @@ PT_API int32_t pto_debug_render(const pto_scene *scene, const pt_render_params *
 /* binary32 -> binary16 -> binary32 (round to nearest even) of n values */
 PT_API int32_t pto_round_half(const float *in, float *out, uint64_t n);
 
+/* skinning.comp:21-50 on `count` animated vertices (the probe tests/test_oracle_vs_glsl_compute.py compares with the
+ * compiled shader): out[i] = the skinned vertex of animated[indices[i]] */
+PT_API int32_t pto_skin_vertices(const pt_animated_vertex *animated, const uint32_t *indices, uint64_t count,
+                                 const float *bone_transforms, uint32_t bone_count, pt_vertex *out);
+
 #ifdef __cplusplus
 }
 #endif

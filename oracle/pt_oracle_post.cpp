@@ -12,9 +12,13 @@
 // (round to nearest even); the bloom sampler is linear / clamp-to-edge / no mips
 // (Renderer.cpp:114-119).
 //
-// PARITY UNPINNED: the reference has no test or golden image for this chain, and the two
-// hardware-defined steps (bilinear weights of the sampler, the blit's sRGB encode) are restated
-// here from the Vulkan specification's formulas in fp32 / fp64.
+// PINNED to the reference's own compute shaders: postprocess.comp, bloomDownsample.comp, bloomUpsample.comp,
+// composition.comp and toneMapping.comp compiled as C++ (oracle/ref_overlay/glsl2cpp.py --compute ->
+// oracle/_ref/libglsl_comp_ref.so) give bit-identical images after composition and after tone mapping
+// (tests/test_oracle_vs_glsl_compute.py, golden vectors in tests/golden/glsl_compute_vectors.npz).  What stays
+// PARITY UNPINNED are the steps the reference leaves to the Vulkan implementation — the sampler's bilinear weights,
+// the binary16 rounding of the image stores, the blit's sRGB encode — restated here from the Vulkan specification's
+// formulas in fp32 / fp64.
 #include <algorithm>
 #include <cmath>
 #include <cstdint>

@@ -21,8 +21,10 @@ fi
 mkdir -p "$OUT/glsl"
 GEN="$OUT/glsl/glsl_stages.cpp"
 LIB="$OUT/libglsl_ref.so"
+CGEN="$OUT/glsl/glsl_compute.cpp"
+CLIB="$OUT/libglsl_comp_ref.so"
 newest=$(ls -t "$HERE"/glsl2cpp.py "$HERE"/glsl_rt*.h "$REPO/include/pt_core.h" "$REF"/Path-Tracing/Shaders/*.* | head -1)
-if [ -f "$LIB" ] && [ "$LIB" -nt "$newest" ]; then
+if [ -f "$LIB" ] && [ "$LIB" -nt "$newest" ] && [ -f "$CLIB" ] && [ "$CLIB" -nt "$newest" ]; then
     exit 0
 fi
 python3 "$HERE/glsl2cpp.py" "$REF" "$GEN"
@@ -30,3 +32,8 @@ echo "  CXX glsl_stages.cpp -> libglsl_ref.so"
 # -ffp-contract=off: GLSL fuses only where the source says fma(); -O2 without fast-math keeps IEEE semantics
 "$CXX" -std=c++20 -O2 -fPIC -shared -ffp-contract=off -fno-fast-math -fvisibility=hidden -w \
     -I"$HERE" -I"$REF/vendor/glm" -o "$LIB" "$GEN" -pthread
+# the compute stages (post-process chain, skinning): same transform, their own runtime headers
+python3 "$HERE/glsl2cpp.py" --compute "$REF" "$CGEN"
+echo "  CXX glsl_compute.cpp -> libglsl_comp_ref.so"
+"$CXX" -std=c++20 -O2 -fPIC -shared -ffp-contract=off -fno-fast-math -fvisibility=hidden -w \
+    -I"$HERE" -I"$REF/vendor/glm" -o "$CLIB" "$CGEN" -pthread

@@ -29,7 +29,15 @@ The transform is purely textual; nothing is re-derived or re-ordered:
   9. functions listed in DROP_FUNCTIONS (GLSL array constructors; skinning helpers that are not on the
      ray-tracing path) are removed.
 
-Usage: glsl2cpp.py <reference root> <output .cpp>
+  10. (compute stages only) a GLSL array constructor assigned to an array member,
+     `v.BoneIndices = uint[4](a, b, c, d);`, is written element by element:
+     `{ v.BoneIndices[0] = (a); ... v.BoneIndices[3] = (d); }` (C++ has no array assignment).
+
+With --compute the COMPUTE stages (postprocess.comp, bloomDownsample.comp, bloomUpsample.comp, composition.comp,
+toneMapping.comp, skinning.comp) are generated instead, each in its own namespace behind the per-stage state macro of
+glsl_rt_compute.h (rows f2 / f3 of SURVEY.md 8).
+
+Usage: glsl2cpp.py [--compute] <reference root> <output .cpp>
 """
 import os
 import re
@@ -43,6 +51,14 @@ STAGES = [
     ("occ_rahit", "occlusionAnyhit.rahit"),
     ("rmiss", "miss.rmiss"),
     ("occ_rmiss", "occlusion.rmiss"),
+]
+COMPUTE_STAGES = [
+    ("comp_post", "postprocess.comp"),
+    ("comp_down", "bloomDownsample.comp"),
+    ("comp_up", "bloomUpsample.comp"),
+    ("comp_compose", "composition.comp"),
+    ("comp_tone", "toneMapping.comp"),
+    ("comp_skin", "skinning.comp"),
 ]
 TYPE_HEADERS = ["ShaderTypes.incl", "ShaderRendererTypes.incl", "Debug/DebugShaderTypes.incl"]
 DROP_FUNCTIONS = ["getAnimatedVertex", "writeVertex"]
@@ -140,6 +156,26 @@ def drop_function(text: str, name: str) -> str:
     return text[: m.start()] + f"/* {name}: dropped (rule 9) */" + text[j + 1 :]
 
 
+def array_constructors(text: str) -> str:
+    """rule 10"""
+
+    def repl(m):
+        target, count, args = m.group(1), int(m.group(3)), m.group(4)
+        parts, depth, cur = [], 0, ""
+        for ch in args:
+            if ch == "," and depth == 0:
+                parts.append(cur.strip())
+                cur = ""
+                continue
+            depth += {"(": 1, ")": -1}.get(ch, 0)
+            cur += ch
+        parts.append(cur.strip())
+        assert len(parts) == count, (target, parts)
+        return "{ " + " ".join(f"{target}[{i}] = ({a});" for i, a in enumerate(parts)) + " }"
+
+    return re.sub(r"([\w.]+)\s*=\s*(uint|int|float)\[(\d+)\]\((.*)\);", repl, text)
+
+
 def expand(path: str, shader_dir: str, seen: set, skip: set) -> str:
     rel = os.path.relpath(path, shader_dir)
     if rel in seen or rel in skip:
@@ -163,7 +199,11 @@ def expand(path: str, shader_dir: str, seen: set, skip: set) -> str:
 
 
 def main():
-    ref, out_path = sys.argv[1], sys.argv[2]
+    args = sys.argv[1:]
+    compute = "--compute" in args
+    if compute:
+        args.remove("--compute")
+    ref, out_path = args[0], args[1]
     shader_dir = os.path.join(ref, "Path-Tracing", "Shaders")
     parts = [
         "/* GENERATED by oracle/ref_overlay/glsl2cpp.py from the reference's shader sources — do not commit. */\n",
@@ -173,15 +213,21 @@ def main():
     seen = set()
     types = "".join(expand(os.path.join(shader_dir, h), shader_dir, seen, set()) for h in TYPE_HEADERS)
     parts.append(common_rules(strip_preprocessor_branches(types)))
-    parts.append('\n} // namespace glslref\n#include "glsl_rt_state.h"\nnamespace glslref\n{\n')
+    state = "glsl_rt_compute.h" if compute else "glsl_rt_state.h"
+    parts.append(f'\n}} // namespace glslref\n#include "{state}"\nnamespace glslref\n{{\n')
     skip = set(TYPE_HEADERS)
-    for ns, fname in STAGES:
+    for ns, fname in COMPUTE_STAGES if compute else STAGES:
         body = expand(os.path.join(shader_dir, fname), shader_dir, set(), skip)
         body = common_rules(strip_preprocessor_branches(body))
+        if compute:
+            body = array_constructors(body)
+            parts.append(f"\nnamespace {ns}\n{{\nGLSL_COMPUTE_STATE_{ns}\n{body}\n}} // namespace {ns}\n")
+            continue
         for fn in DROP_FUNCTIONS:
             body = drop_function(body, fn)
         parts.append(f"\nnamespace {ns}\n{{\n{body}\n}} // namespace {ns}\n")
-    parts.append('\n} // namespace glslref\n#include "glsl_rt_api.h"\n')
+    api = "glsl_rt_compute_api.h" if compute else "glsl_rt_api.h"
+    parts.append(f'\n}} // namespace glslref\n#include "{api}"\n')
     os.makedirs(os.path.dirname(out_path), exist_ok=True)
     with open(out_path, "w") as f:
         f.write("".join(parts))

@@ -178,9 +178,11 @@ __global__ void k_skin(const float *__restrict__ animated, uint32_t count, const
         const float w = a[18 + k];
         const float *m = bones + (size_t)bone * PT_BONE_STRIDE;
         // vec4(v, 1 | 0) * mat3x4: component j = dot(v4, column j)
-        auto xformPoint = [&](vec3 v) {
-            return V3(((v.x * m[0] + v.y * m[1]) + v.z * m[2]) + 1.0f * m[3], ((v.x * m[4] + v.y * m[5]) + v.z * m[6]) + 1.0f * m[7],
-                      ((v.x * m[8] + v.y * m[9]) + v.z * m[10]) + 1.0f * m[11]);
+        // `boneWeight * vec4(Position, 1) * transform` groups from the left (skinning.comp:41): the WEIGHTED point
+        // (w P, w) goes through the matrix
+        auto xformWeightedPoint = [&](vec3 v, float vw) {
+            return V3(((v.x * m[0] + v.y * m[1]) + v.z * m[2]) + vw * m[3], ((v.x * m[4] + v.y * m[5]) + v.z * m[6]) + vw * m[7],
+                      ((v.x * m[8] + v.y * m[9]) + v.z * m[10]) + vw * m[11]);
         };
         auto xformDir = [&](vec3 v) {
             return V3(((v.x * m[0] + v.y * m[1]) + v.z * m[2]) + 0.0f * m[3], ((v.x * m[4] + v.y * m[5]) + v.z * m[6]) + 0.0f * m[7],
@@ -189,7 +191,7 @@ __global__ void k_skin(const float *__restrict__ animated, uint32_t count, const
         const float *nm = m + 12;
         const vec3 nn = V3((N.x * nm[0] + N.y * nm[1]) + N.z * nm[2], (N.x * nm[3] + N.y * nm[4]) + N.z * nm[5],
                            (N.x * nm[6] + N.y * nm[7]) + N.z * nm[8]);
-        pos = pos + w * xformPoint(P);
+        pos = pos + xformWeightedPoint(w * P, w);
         tan = tan + w * normalize(xformDir(T));
         bit = bit + w * normalize(xformDir(B));
         nrm = nrm + w * normalize(nn);
