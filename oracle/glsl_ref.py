@@ -25,7 +25,7 @@ REFERENCE_ROOT = "/root/reference"
 
 
 class Callbacks(C.Structure):
-    _fields_ = [("user", C.c_void_p), ("trace", C.c_void_p), ("texture", C.c_void_p), ("sky", C.c_void_p)]
+    _fields_ = [("user", C.c_void_p), ("trace", C.c_void_p), ("texture", C.c_void_p), ("sky", C.c_void_p), ("trace_flags", C.c_void_p)]
 
 
 def build() -> str | None:
@@ -56,6 +56,7 @@ def lib():
                                  C.c_void_p, C.c_int32]
         L.glr_closest_hit.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.glr_test_shading.argtypes = [C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint32]
+        L.glr_debug_render.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p]
         _lib = L
     return _lib
 
@@ -79,6 +80,7 @@ class GlslScene:
             C.cast(ol.pto_trace_anyhit, C.c_void_p).value,
             C.cast(ol.pto_texture_sample, C.c_void_p).value,
             C.cast(ol.pto_sky_sample, C.c_void_p).value,
+            C.cast(ol.pto_trace_anyhit_flags, C.c_void_p).value,
         )
         desc, keep = scene.to_c()
         self._h = lib().glr_scene_create(C.addressof(desc), C.addressof(cb))
@@ -104,6 +106,18 @@ class GlslScene:
                               accum.ctypes.data, threads)
         assert rc >= 0, rc
         return accum, rc
+
+    def debug_render(self, params, width, height, mode=0, raygen_flags=0, hit_group_flags=0):
+        """One frame of the compiled debug pipeline (Debug/debug*.r*): (H, W, 4) float32."""
+        from importlib import import_module
+
+        core = import_module("path-tracing_b200.core")
+        d = core.DebugParams(core.DEBUG_MODES.index(mode) if isinstance(mode, str) else int(mode), raygen_flags, hit_group_flags)
+        p = params.to_c()
+        out = np.zeros((height, width, 4), np.float32)
+        rc = lib().glr_debug_render(self._h, C.addressof(p), C.addressof(d), width, height, out.ctypes.data)
+        assert rc == 0, rc
+        return out
 
     def closest_hit(self, params, hits, rays6, payload_in):
         from importlib import import_module

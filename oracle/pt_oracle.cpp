@@ -22,6 +22,8 @@
  *   - the COMPUTE stages — skinning.comp (skinVertex below) and the post-process chain (pt_oracle_post.cpp) — are pinned the
  *     same way: glsl2cpp.py --compute -> oracle/_ref/libglsl_comp_ref.so, tests/test_oracle_vs_glsl_compute.py, golden vectors
  *     in tests/golden/glsl_compute_vectors.npz; every float of every skinned vertex and of the composed / tone-mapped images.
+ *   - the debug pipeline (debugPixel / pto_debug_render below) is pinned through the same library: Debug/debug*.r* compiled next
+ *     to the path-tracing stages, every render mode and flag, bit for bit (tests/test_oracle_vs_glsl.py::test_debug_pipeline_*).
  *   - RNG: additionally pinned by the known answers derived from the integer spec (tests/test_oracle_rng.py).
  *   - struct layouts: pinned by PTT/PaddingTest.cpp literals (tests/test_layout.py).
  *   - ray/box, ray/triangle, BVH: PARITY UNPINNED — in the reference they run inside the Vulkan driver / RT hardware and
@@ -2623,6 +2625,23 @@ int32_t pto_trace_anyhit(const pto_scene *s, const float *org, const float *dir,
         traceOccluded(*s, V3(org[0], org[1], org[2]), V3(dir[0], dir[1], dir[2]), tmin, tmax, c, hp, &h);
     else
         h = traceClosest(*s, V3(org[0], org[1], org[2]), V3(dir[0], dir[1], dir[2]), tmin, tmax, c, false, hp);
+    *out = toPtHit(*s, h);
+    return h.tri != PT_NO_HIT ? 1 : 0;
+}
+
+int32_t pto_trace_anyhit_flags(const pto_scene *s, const float *org, const float *dir, float tmin, float tmax,
+                               uint32_t terminate_on_first_hit, uint32_t flags, pto_anyhit_fn anyhit, void *ctx, pt_hit *out)
+{
+    if (!s || !org || !dir || !out)
+        return 0;
+    if (terminate_on_first_hit)
+        return pto_trace_anyhit(s, org, dir, tmin, tmax, terminate_on_first_hit, anyhit, ctx, out);
+    Counters c;
+    AnyHitHook hook;
+    hook.fn = anyhit;
+    hook.ctx = ctx;
+    const HitInfo h = traceClosest(*s, V3(org[0], org[1], org[2]), V3(dir[0], dir[1], dir[2]), tmin, tmax, c, (flags & 1u) != 0,
+                                   anyhit ? &hook : nullptr, (flags & 2u) != 0);
     *out = toPtHit(*s, h);
     return h.tri != PT_NO_HIT ? 1 : 0;
 }

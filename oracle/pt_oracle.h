@@ -77,6 +77,10 @@ typedef int32_t (*pto_anyhit_fn)(void *ctx, uint32_t instance, uint32_t geometry
                                  float b2);
 PT_API int32_t pto_trace_anyhit(const pto_scene *scene, const float *org, const float *dir, float tmin, float tmax,
                                 uint32_t terminate_on_first_hit, pto_anyhit_fn anyhit, void *ctx, pt_hit *out);
+/* the same with ray flags: bit 0 = gl_RayFlagsOpaqueEXT (no candidate reaches the any-hit stage), bit 1 =
+ * gl_RayFlagsCullBackFacingTrianglesEXT — the debug pipeline's primary rays (Debug/debugRaygen.rgen:28-35) */
+PT_API int32_t pto_trace_anyhit_flags(const pto_scene *scene, const float *org, const float *dir, float tmin, float tmax,
+                                      uint32_t terminate_on_first_hit, uint32_t flags, pto_anyhit_fn anyhit, void *ctx, pt_hit *out);
 PT_API int32_t pto_sky_sample(const pto_scene *scene, uint32_t kind, const float *in3, float *out4);
 /* closestHit.rchit:52-161 on `count` given hits: rays6 = world ray origin.xyz, direction.xyz; payloads are the 36
  * words of Shaders::Payload (ShaderRendererTypes.incl:101-118; RngState as bits). */

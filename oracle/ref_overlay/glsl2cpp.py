@@ -26,6 +26,7 @@ The transform is purely textual; nothing is re-derived or re-ordered:
   8. a vector constructor whose arguments call rand() more than once is written with braces,
      `vec2(rand(s), rand(s))` -> `vec2{rand(s), rand(s)}`: GLSL evaluates arguments left to right
      (GLSL 4.60 §6.1.1), C++ only does so inside a braced initialiser list (g++ goes right to left).
+     The debug stages' `payload` (a DebugPayload) is mapped to its own object by a #define around those stages.
   9. functions listed in DROP_FUNCTIONS (GLSL array constructors; skinning helpers that are not on the
      ray-tracing path) are removed.
 
@@ -51,6 +52,11 @@ STAGES = [
     ("occ_rahit", "occlusionAnyhit.rahit"),
     ("rmiss", "miss.rmiss"),
     ("occ_rmiss", "occlusion.rmiss"),
+    # the debug pipeline (Renderer.cpp:579-589): its own raygen / miss / hit group; occlusion rays use the two above
+    ("dbg_rgen", "Debug/debugRaygen.rgen"),
+    ("dbg_rchit", "Debug/debugClosestHit.rchit"),
+    ("dbg_rahit", "Debug/debugAnyhit.rahit"),
+    ("dbg_rmiss", "Debug/debugMiss.rmiss"),
 ]
 COMPUTE_STAGES = [
     ("comp_post", "postprocess.comp"),
@@ -225,6 +231,9 @@ def main():
             continue
         for fn in DROP_FUNCTIONS:
             body = drop_function(body, fn)
+        if ns.startswith("dbg_"):
+            # the debug stages declare `payload` as a DebugPayload (Debug/debugRaygen.rgen:18): same name, other object
+            body = "#define payload dbg_payload\n" + body + "\n#undef payload\n"
         parts.append(f"\nnamespace {ns}\n{{\n{body}\n}} // namespace {ns}\n")
     api = "glsl_rt_compute_api.h" if compute else "glsl_rt_api.h"
     parts.append(f'\n}} // namespace glslref\n#include "{api}"\n')

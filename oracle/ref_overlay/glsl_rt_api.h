@@ -89,6 +89,8 @@ inline void bindHit(const Scene &s, uint32_t instance, uint32_t geometry, uint32
     sbt.MaterialId = rec.material_id;
     sbt.TransformIndex = rec.transform_index;
     gl_PrimitiveID = (int)primitive;
+    gl_GeometryIndexEXT = (int)geometry;
+    gl_InstanceID = (int)instance;
     gl_RayTmaxEXT = t;
     attribs = vec3(b1, b2, 0.0f);
     const float *m = inst.transform;
@@ -109,6 +111,8 @@ inline int32_t anyHitTrampoline(void *ctx, uint32_t instance, uint32_t geometry,
     tls_ignore = false;
     if (c->occlusion)
         occ_rahit::main_();
+    else if (tls_debug_pipeline)
+        dbg_rahit::main_();
     else
         rahit::main_();
     return tls_ignore ? 0 : 1;
@@ -120,25 +124,49 @@ void traceRayEXT(accelerationStructureEXT, uint rayFlags, uint, uint sbtRecordOf
     const Scene &s = *tls_scene;
     if (++tls_trace_calls > (1ull << 24))
         throw std::runtime_error("raygen.rgen: NaN/Inf restart loop does not terminate");
+    /* built-ins and the shader record belong to ONE invocation: a stage that traces (debugClosestHit.rchit's shadow rays)
+     * must find its own again afterwards */
+    struct Saved
+    {
+        SBTBuffer sbt_;
+        int prim, geom, inst;
+        float tmaxv;
+        vec3 attr, org, dir;
+        mat3x4 o2w;
+        Saved() : sbt_(sbt), prim(gl_PrimitiveID), geom(gl_GeometryIndexEXT), inst(gl_InstanceID), tmaxv(gl_RayTmaxEXT), attr(attribs),
+                  org(gl_WorldRayOriginEXT), dir(gl_WorldRayDirectionEXT), o2w(gl_ObjectToWorld3x4EXT) {}
+        ~Saved()
+        {
+            sbt = sbt_, gl_PrimitiveID = prim, gl_GeometryIndexEXT = geom, gl_InstanceID = inst, gl_RayTmaxEXT = tmaxv, attribs = attr;
+            gl_WorldRayOriginEXT = org, gl_WorldRayDirectionEXT = dir, gl_ObjectToWorld3x4EXT = o2w;
+        }
+    } saved;
     gl_WorldRayOriginEXT = origin;
     gl_WorldRayDirectionEXT = direction;
     const bool occlusion = sbtRecordOffset == OcclusionRayHitGroupIndex;
     AnyHitCtx ctx { &s, occlusion };
     pt_hit hit;
     const float o[3] = { origin.x, origin.y, origin.z }, d[3] = { direction.x, direction.y, direction.z };
-    const int32_t found = s.cb.trace(s.cb.user, o, d, tmin, tmax, (rayFlags & gl_RayFlagsTerminateOnFirstHitEXT) ? 1u : 0u,
-                                     anyHitTrampoline, &ctx, &hit);
+    const uint terminate = (rayFlags & gl_RayFlagsTerminateOnFirstHitEXT) ? 1u : 0u;
+    const uint flags = ((rayFlags & gl_RayFlagsOpaqueEXT) ? 1u : 0u) | ((rayFlags & gl_RayFlagsCullBackFacingTrianglesEXT) ? 2u : 0u);
+    const int32_t found = flags ? s.cb.trace_flags(s.cb.user, o, d, tmin, tmax, terminate, flags, anyHitTrampoline, &ctx, &hit)
+                                : s.cb.trace(s.cb.user, o, d, tmin, tmax, terminate, anyHitTrampoline, &ctx, &hit);
     if (found)
     {
         /* the occlusion hit group has no closest-hit shader (Renderer.cpp pipeline: any-hit only) */
         if (!occlusion)
         {
             bindHit(s, hit.instance, hit.geometry, hit.primitive, hit.t, hit.u, hit.v);
-            rchit::main_();
+            if (tls_debug_pipeline)
+                dbg_rchit::main_();
+            else
+                rchit::main_();
         }
     }
     else if (missIndex == OcclusionRayMissGroupIndex)
-        occ_rmiss::main_();
+        occ_rmiss::main_(); /* both pipelines (Renderer.cpp:558, 589) */
+    else if (tls_debug_pipeline)
+        dbg_rmiss::main_();
     else
         rmiss::main_();
 }
@@ -293,6 +321,34 @@ PT_API int32_t glr_render(const glr_scene *h, const pt_render_params *p, uint32_
             t.join();
     }
     return spinning.load();
+}
+
+/* One frame of the debug pipeline (Debug/debugRaygen.rgen main() per pixel, dispatching to debugAnyhit.rahit /
+ * debugClosestHit.rchit / debugMiss.rmiss and, for its shadow rays, occlusionAnyhit.rahit / occlusion.rmiss):
+ * width * height RGBA floats. */
+PT_API int32_t glr_debug_render(const glr_scene *h, const pt_render_params *p, const pt_debug_params *dbg, uint32_t width,
+                                uint32_t height, float *out_rgba)
+{
+    using namespace glslref;
+    if (!h || !p || !dbg || !out_rgba)
+        return PT_ERR_INVALID_ARGUMENT;
+    bindScene(h->s, *p);
+    tls_image = out_rgba;
+    gl_LaunchSizeEXT = uvec3(width, height, 1);
+    s_RenderMode = dbg->render_mode;
+    s_RaygenFlags = dbg->raygen_flags;
+    s_HitGroupFlags = dbg->hit_group_flags;
+    tls_debug_pipeline = true;
+    for (uint32_t y = 0; y < height; y++)
+        for (uint32_t x = 0; x < width; x++)
+        {
+            gl_LaunchIDEXT = uvec3(x, y, 0);
+            tls_trace_calls = 0;
+            std::memset(&dbg_payload, 0, sizeof(dbg_payload));
+            dbg_rgen::main_();
+        }
+    tls_debug_pipeline = false;
+    return PT_OK;
 }
 
 /* closestHit.rchit main() for `count` hits: rays = origin.xyz, direction.xyz (6 floats);

@@ -28,6 +28,9 @@ typedef struct glr_callbacks
     int32_t (*texture)(const void *user, uint32_t slot, const float *in6, float *out4, uint32_t count, int32_t use_grad);
     /* kind 0: 2-D sky at uv (in3[0..1]); kind 1: cube sky along direction in3 */
     int32_t (*sky)(const void *user, uint32_t kind, const float *in3, float *out4);
+    /* `trace` with ray flags (the debug pipeline): bit 0 = gl_RayFlagsOpaqueEXT, bit 1 = gl_RayFlagsCullBackFacingTrianglesEXT */
+    int32_t (*trace_flags)(const void *user, const float *org, const float *dir, float tmin, float tmax,
+                           uint32_t terminate_on_first_hit, uint32_t flags, glr_anyhit_fn anyhit, void *ctx, pt_hit *out);
 } glr_callbacks;
 }
 
@@ -36,7 +39,7 @@ namespace glslref
 
 static_assert(sizeof(Vertex) == 56 && sizeof(MetallicRoughnessMaterial) == 96 && sizeof(SpecularGlossinessMaterial) == 96 &&
                   sizeof(PhongMaterial) == 96 && sizeof(PointLight) == 48 && sizeof(DirectionalLight) == 32 &&
-                  sizeof(Payload) == 144 && sizeof(mat3x4) == 48,
+                  sizeof(Payload) == 144 && sizeof(mat3x4) == 48 && sizeof(DebugPayload) == 48,
               "the GLSL branch of the dual headers must have the host layout (PTT/PaddingTest.cpp)");
 
 struct SamplerArray
@@ -75,8 +78,18 @@ static thread_local vec3 gl_WorldRayOriginEXT;
 static thread_local vec3 gl_WorldRayDirectionEXT;
 static thread_local float gl_RayTmaxEXT;
 static thread_local mat3x4 gl_ObjectToWorld3x4EXT;
+static thread_local int gl_GeometryIndexEXT;
+static thread_local int gl_InstanceID;
 const uint gl_RayFlagsNoneEXT = 0u;
+const uint gl_RayFlagsOpaqueEXT = 1u;
 const uint gl_RayFlagsTerminateOnFirstHitEXT = 4u;
+const uint gl_RayFlagsCullBackFacingTrianglesEXT = 16u;
+/* the debug pipeline (Debug/debugRaygen.rgen:8-18, debugClosestHit.rchit:9-10): its payload and specialisation constants */
+static thread_local DebugPayload dbg_payload;
+static thread_local uint s_RenderMode;
+static thread_local uint s_RaygenFlags;
+static thread_local uint s_HitGroupFlags;
+static thread_local bool tls_debug_pipeline;
 
 /* ---- harness side ---- */
 struct Scene;

@@ -50,3 +50,15 @@ def closest_hit_inputs(oracle_scene, oracle_mod, params, width, height, frame=0)
     payload[:, 32], payload[:, 33:36] = rays[:, 14], rays[:, 15:18]
     hit = aov["instance"] != 0xFFFFFFFF
     return aov[hit], rays[hit, :6], payload[hit]
+
+
+# ---- the debug pipeline (Debug/debug*.r*): (render mode, raygen flags, hit-group flags) ------------------------------
+DEBUG_MODES = ("color", "world_position", "normal", "texture_coords", "mips", "geometry", "primitive", "instance")
+DEBUG_FLAG_SETS = ((0, 0), (1, 0), (2, 0), (3, 0x1F), (0, 0x04), (0, 0x08), (0, 0x01 | 0x02), (0, 0x10))
+# the combinations whose images travel as golden vectors
+DEBUG_GOLDEN = (("default", "color", 0, 0), ("feature", "color", 0, 0), ("feature", "color", 2, 0x10), ("feature", "normal", 1, 0x02),
+                ("feature", "mips", 0, 0), ("feature", "instance", 0, 0), ("feature", "primitive", 3, 0x1F))
+
+
+def debug_key(scene, mode, raygen_flags, hit_flags):
+    return f"dbg_{scene}_{mode}_{raygen_flags}_{hit_flags}"

@@ -8,6 +8,7 @@ the repository so that the oracle stays pinned on machines without the reference
   per function (every PT_TEST_* mode):  in_<mode>, out_<mode>       256 records each
   closestHit.rchit payloads:            chit_<scene>_{hits,rays,in,out}
   whole pipeline (raygen.rgen main):    img_<case>                  accumulation images
+  debug pipeline (debugRaygen main):    dbg_<scene>_<mode>_<raygen flags>_<hit-group flags>
 """
 import os
 import sys
@@ -44,6 +45,11 @@ def main():
             out[f"chit_{name}_rays"] = rays
             out[f"chit_{name}_in"] = pin
             out[f"chit_{name}_out"] = g.closest_hit(params, hits, rays, pin)
+    cases = gc.stage_scenes(default_scene)
+    for scene_name, mode, rf, hf in gc.DEBUG_GOLDEN:
+        scene, params, w, h = cases[scene_name][:4]
+        g = glsl_ref.GlslScene(scene, oracle.OracleScene(scene))
+        out[gc.debug_key(scene_name, mode, rf, hf)] = g.debug_render(params, w, h, mode, rf, hf)
     path = os.path.join(HERE, "glsl_vectors.npz")
     np.savez_compressed(path, **out)
     print(path, os.path.getsize(path), "bytes")

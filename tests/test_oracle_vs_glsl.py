@@ -72,6 +72,15 @@ def test_images_match_golden(oracle_mod, golden, default_scene):
         assert_bits(img.reshape(-1, 4), want.reshape(-1, 4), f"accumulation image '{name}'")
 
 
+def test_debug_pipeline_matches_golden(oracle_mod, golden, default_scene):
+    cases = gc.stage_scenes(default_scene)
+    for scene_name, mode, rf, hf in gc.DEBUG_GOLDEN:
+        scene, params, w, h = cases[scene_name][:4]
+        got = oracle_mod.OracleScene(scene).debug_render(params, w, h, mode, rf, hf)
+        assert_bits(got.reshape(-1, 4), golden[gc.debug_key(scene_name, mode, rf, hf)].reshape(-1, 4),
+                    f"debug pipeline, {scene_name} / {mode} / raygen {rf} / hit group {hf:#x}")
+
+
 # ---- live library ------------------------------------------------------------------------------------
 
 GRIDS = {0: rd.grid_vec3_float, 1: rd.grid_vec3_float, 2: rd.grid_vec3_float, 3: rd.grid_dielectric, 4: rd.grid_schlick,
@@ -152,3 +161,38 @@ def test_config_scenes_bitwise(oracle_mod, glsl):
         # the camera was built for scenes_small.W x H: same aspect ratio at 64 x 48
         c = _bitwise_images(oracle_mod, glsl, scene, params, 64, 48, 0, 1, 2, name)
         assert c["rays_closest"] > 64 * 48
+
+
+@pytest.mark.parametrize("mode", gc.DEBUG_MODES)
+def test_debug_pipeline_bitwise(oracle_mod, glsl, default_scene, mode):
+    """Debug/debugRaygen.rgen main() per pixel, dispatching to the compiled debugAnyhit / debugClosestHit / debugMiss (and
+    occlusionAnyhit / occlusion.rmiss for the shadow rays), against pto_debug_render: every render mode x force-opaque,
+    back-face culling and every hit-group flag, on the Default scene and the feature scene (decals, transmission, lights)."""
+    cases = gc.stage_scenes(default_scene)
+    for scene_name in ("default", "feature"):
+        scene, params, w, h = cases[scene_name][:4]
+        ora = oracle_mod.OracleScene(scene)
+        g = glsl.GlslScene(scene, ora)
+        for rf, hf in gc.DEBUG_FLAG_SETS:
+            want = g.debug_render(params, w, h, mode, rf, hf)
+            assert np.isfinite(want).all() and want[..., :3].max() > 0.05
+            assert_bits(ora.debug_render(params, w, h, mode, rf, hf).reshape(-1, 4), want.reshape(-1, 4),
+                        f"{scene_name} / {mode} / raygen {rf} / hit group {hf:#x}")
+
+
+def test_debug_miss_skyboxes_bitwise(oracle_mod, glsl):
+    sc = gc.sc
+    rs = np.random.default_rng(9)
+    fs = gc.scenes.feature_scene(width=48, height=36)
+    fs.skybox_2d = sc.Texture((rs.uniform(0, 1, (16, 32, 4)) * 255).astype(np.uint8), srgb=True)
+    p = fs.default_params(bounce_count=4)
+    p.miss_flags = sc.MISS_FLAGS_SKYBOX_2D
+    ora = oracle_mod.OracleScene(fs)
+    assert_bits(ora.debug_render(p, 48, 36, "color").reshape(-1, 4), glsl.GlslScene(fs, ora).debug_render(p, 48, 36, "color").reshape(-1, 4),
+                "debugMiss.rmiss, 2-D skybox")
+    fs.skybox_2d = None
+    fs.skybox_cube = [sc.Texture(rs.uniform(0, 4, (8, 8, 4)).astype(np.float32), srgb=False) for _ in range(6)]
+    p.miss_flags = sc.MISS_FLAGS_SKYBOX_CUBE
+    ora = oracle_mod.OracleScene(fs)
+    assert_bits(ora.debug_render(p, 48, 36, "color").reshape(-1, 4), glsl.GlslScene(fs, ora).debug_render(p, 48, 36, "color").reshape(-1, 4),
+                "debugMiss.rmiss, cube skybox")
